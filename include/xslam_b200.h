@@ -1,0 +1,200 @@
+/* xslam_b200.h — C-ABI of libxslam_b200.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for the CSFD/DCSFD-differentiated KinectFusion frame loop of MisEty/X-SLAM.
+ * The reference has no FFI layer; its seam is the set of C++ free functions that
+ * XKinectFusion/src/KinectFusionReconstruction.cpp calls (aggregated by
+ * XKinectFusion/include/CudaFunctions.h:4-8).  Every entry point below names the reference
+ * interface it replaces (file:line relative to the reference tree).  C++ wrappers with the
+ * reference's exact signatures live in include/xslam_b200.hpp and forward to these symbols.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = default).
+ *  - every function returns 0 on success or a negative xs_status; xs_last_error() gives text.
+ *    There is NO CPU fallback: without a CUDA device every compute call returns XS_ERR_CUDA.
+ *  - "ncomp" = number of derivative components carried besides the real value:
+ *        ncomp = dirs * comps,   comps = 1 (CSFD: eps)  or  3 (DCSFD: eps1, eps2, eps1eps2).
+ *    Derivative components are stored h-scaled exactly like the reference's imaginary parts
+ *    (Internal.h:33, H_ = 1e-7): eps = h*d/dtheta, eps1eps2 = h^2 * d2/dtheta1 dtheta2.
+ *  - maps are packed SoA: float[(1+ncomp)][3][rows][cols]  (component 0 = real part; x|y|z planes),
+ *    replacing the reference's interleaved pitched devComplex maps (Internal.h:31).
+ *  - the TSDF volume lives behind an opaque handle in a brick-tiled layout (8x8x8 voxels):
+ *    value[brick][512], weight[brick][512], deriv[brick][ncomp][512]; seam-compatible
+ *    value/weight/grad planes (TsdfVolume.h:27-36) are obtained with xs_volume_export_planes.
+ */
+#ifndef XSLAM_B200_H
+#define XSLAM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    XS_OK = 0,
+    XS_ERR_ARG = -1,
+    XS_ERR_CUDA = -2,
+    XS_ERR_ICP_DEGENERATE = -3, /* |det(Re A)| < 1e-15 or NaN, KinectFusionReconstruction.cpp:203-210 */
+    XS_ERR_NCCL = -4
+} xs_status;
+
+const char *xs_last_error(void);
+int xs_version(void);
+/* number of CUDA kernels this library has launched in the calling process (bench.py's gpu_launches) */
+long long xs_launch_count(void);
+
+/* Intr, Internal.h:49-59 */
+typedef struct {
+    float fx, fy, cx, cy;
+} xs_intr;
+
+/* A rigid transform with batched derivative components (host memory).  Replaces the by-value
+ * MatS33 + devComplex3 kernel arguments (Internal.h:63-65,146-148): R row-major. */
+typedef struct {
+    float R[9];
+    float t[3];
+    int ncomp;
+    const float *dR; /* [ncomp][9] or NULL */
+    const float *dt; /* [ncomp][3] or NULL */
+} xs_pose;
+
+/* ---------------------------------------------------------------- number types (a1-a3)
+ * Packed-SoA bicomplex arrays: float[4][n] = value | eps1 | eps2 | eps1eps2 planes, the device
+ * counterpart of DoubleComplex (DeviceArray/include/DoubleComplex.h:15-95) and d_complex<T>
+ * (DeviceArray/include/cuda_double_complex.hpp:16-134).  ops follow DoubleComplex.cpp. */
+typedef enum {
+    XS_DC_ADD = 0, XS_DC_SUB, XS_DC_MUL, XS_DC_DIV, XS_DC_SQRT, XS_DC_EXP, XS_DC_LOG, XS_DC_SIN, XS_DC_COS,
+    XS_DC_ATAN2, XS_DC_POW, XS_DC_ATAN
+} xs_dc_op;
+int xs_dc_apply(int op, const float *d_a, const float *d_b, float p, float *d_out, long n, void *stream);
+/* Experiments/test_CSFD/main.cpp:194-205: loss = f1(t*t, sin t) with t seeded (t,h | h,0) */
+int xs_dc_chain(const float *d_t, float h, float *d_out, long n, void *stream);
+
+/* ---------------------------------------------------------------- surface measurement (a6) */
+/* bilateralFilter, Map.h:16 / Map.cu:262.  out: float[rows][cols] (the reference's imaginary part is 0) */
+int xs_bilateral_filter(const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, float *d_out,
+                        void *stream);
+/* pyrDown, Map.h:22 / Map.cu:274 */
+int xs_pyr_down(const float *d_src, int rows, int cols, float *d_dst, void *stream);
+/* createVMap, Map.h:29 / Map.cu:73.  d_vmap: float[3][rows][cols]; invalid pixels get NaN in x, 0 in y,z */
+int xs_create_vmap(xs_intr intr, const float *d_depth, int rows, int cols, float *d_vmap, void *stream);
+/* createNMap, Map.h:35 / Map.cu:89 */
+int xs_create_nmap(const float *d_vmap, int rows, int cols, float *d_nmap, void *stream);
+/* resizeVMap / resizeNMap, Map.h:47,54 / Map.cu:252,257.  in: [(1+ncomp)][3][rows][cols] */
+int xs_resize_vmap(const float *d_in, int rows, int cols, int comps, int dirs, float *d_out, void *stream);
+int xs_resize_nmap(const float *d_in, int rows, int cols, int comps, int dirs, float *d_out, void *stream);
+
+/* ---------------------------------------------------------------- TSDF volume (a9, a11) */
+typedef struct xs_volume xs_volume;
+/* TsdfVolume::TsdfVolume, TsdfVolume.cpp:11-29 (trunc = max(voxel*thres_range, 2.1*voxel)); res multiple of 8 */
+xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_range, int comps, int dirs);
+void xs_volume_destroy(xs_volume *v);
+/* initVolume, TsdfVolume.h:16 / TsdfFusion.cu:34 */
+int xs_volume_reset(xs_volume *v, void *stream);
+float xs_volume_trunc_dist(const xs_volume *v);
+size_t xs_volume_bytes(const xs_volume *v);
+/* Seam views (TsdfVolume::value/weight/grad, TsdfVolume.h:46-49): dense x-fastest planes [z][y][x]
+ * on the device; comp = derivative component index in [0, ncomp) for d_grad (ignored when NULL). */
+int xs_volume_export_planes(const xs_volume *v, int comp, float *d_value, int *d_weight, float *d_grad, void *stream);
+int xs_volume_import_planes(xs_volume *v, int comp, const float *d_value, const int *d_weight, const float *d_grad,
+                            void *stream);
+/* integrateTsdfVolume, TsdfFusion.h:40-45 / TsdfFusion.cu:173.  v2c = (Rv2c, tv2c) with ncomp derivative
+ * components.  stats (optional, device-written then copied): [0] updated voxels, [1] bricks touched. */
+int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, xs_intr intr,
+                 int max_weight, const xs_pose *v2c, float bilinear_threshold, unsigned long long *stats_host,
+                 void *stream);
+/* raycast, RayCaster.h:21-25 / RayCaster.cu:327.  c2v = (Rc2v, tc2v), v2w = (Rv2w, tv2w).
+ * outputs: [(1+ncomp)][3][rows][cols] world-frame vertex / normal maps. */
+int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_pose *v2w, int rows, int cols,
+               float *d_vmap, float *d_nmap, void *stream);
+/* ComputeLocalTsdf_hessian, TsdfFusion.h:55-60 / TsdfFusion.cu:286 (DCSFD volume loss, one bicomplex
+ * direction): pose = (Rv2c, tv2c) with ncomp = 3 (eps1, eps2, eps1eps2).  d_gt: dense [z][y][x].
+ * out4 = {sum loss, sum grad, sum hessian, count} (host). */
+int xs_tsdf_hessian(const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, xs_intr intr,
+                    const int res[3], float voxel_size, const xs_pose *v2c, float trunc, const float *d_gt,
+                    double *out4_host, void *stream);
+/* extractPoints / extractNormals, ExtractPointCloud.h:19-23 (real-only output path) */
+long xs_extract_points(const xs_volume *v, float *d_points_xyz, float *d_normals_xyz, long max_points, void *stream);
+
+/* ---------------------------------------------------------------- ICP (a7) */
+/* estimateCombined, ICP.h:24-31 / ICP.cu:365.  curr = (Rcurr, tcurr), prev = (Rprev_inv, tprev).
+ * Current-frame maps are real (3 planes); previous maps carry ncomp components.
+ * A_host: double[(1+ncomp)][36] column-major 6x6, b_host: double[(1+ncomp)][6]; component 0 is the real part. */
+int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
+                         xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols,
+                         int comps, int dirs, float dist_thres, float angle_thres, double *A_host, double *b_host,
+                         void *stream);
+
+/* ---------------------------------------------------------------- pipeline (a4, a8, a13) */
+/* The YAML keys read by KinectFusionReconstruction::SetYamlParameters (KinectFusionReconstruction.cpp:12-72) */
+typedef struct {
+    int res[3];
+    float voxel_size;
+    int max_weight;
+    float thres_range;
+    float init_xyz[3];
+    float r_deg[3];
+    int width, height;
+    float fx, fy, cx, cy;
+    int num_levels;
+    float dist_thres;
+    float angle_thres_deg;
+    float bi_threshold;
+    float trunc_k;
+} xs_config;
+
+typedef enum {
+    XS_SOLVE_EIGEN_LLT = 0, /* Hermitian LLT of the complex-symmetric A, as KinectFusionReconstruction.cpp:211 (comps=1 only) */
+    XS_SOLVE_ANALYTIC = 1   /* derivative of x = A^-1 b by the truncated algebra */
+} xs_solve_mode;
+
+typedef struct xs_kinfu xs_kinfu;
+/* KinectFusionReconstruction() + SetYamlParameters, KinectFusionReconstruction.cpp:4-73.
+ * seeds: [dirs*comps][16] derivative components of the initial world2camera (row-major 4x4, h-scaled),
+ * the generalisation of the commented seeding line KinectFusionReconstruction.cpp:22; NULL = zeros. */
+xs_kinfu *xs_kinfu_create(const xs_config *cfg, int comps, int dirs, const float *seeds, int solve_mode);
+void xs_kinfu_destroy(xs_kinfu *k);
+/* ProcessFrame, KinectFusionReconstruction.cpp:147-159.  depth: 640x480 uint16 mm, dense; host pointer
+ * unless depth_on_device != 0.  Returns 1 on success, 0 when frame alignment failed (as the reference). */
+int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_device);
+/* stage entry points, KinectFusionReconstruction.h:113-141 */
+int xs_kinfu_surface_measure(xs_kinfu *k, const uint16_t *d_depth);
+int xs_kinfu_pose_estimate(xs_kinfu *k);
+int xs_kinfu_integrate_frame(xs_kinfu *k, const uint16_t *d_depth);
+int xs_kinfu_calculate_point_cloud(xs_kinfu *k);
+int xs_kinfu_frame_id(const xs_kinfu *k);
+/* world2camera (KinectFusionReconstruction.h:31): out [(1+ncomp)][16] row-major */
+int xs_kinfu_get_world2camera(const xs_kinfu *k, float *out);
+/* camera-to-world of the last frame, real part, as written to frame-%06d.pose.txt (main.cpp:61) */
+int xs_kinfu_get_pose_c2w(const xs_kinfu *k, float *out16);
+xs_volume *xs_kinfu_volume(xs_kinfu *k);
+/* which: 0 depth pyramid, 1 vmap_curr, 2 nmap_curr, 3 vmap_g_prev, 4 nmap_g_prev; device pointer + dims */
+const float *xs_kinfu_map(const xs_kinfu *k, int which, int level, int *rows, int *cols, int *ncomp);
+/* per-stage device times of the last frame (ms): surface, icp, integrate, raycast+resize, total;
+ * followed by per-stage kernel-launch counts (5 more floats) */
+int xs_kinfu_get_times(const xs_kinfu *k, float *ms10);
+/* ICP log of the last frame: iterations x (1+ncomp) x 42 doubles (A 36 column-major, b 6) */
+int xs_kinfu_take_icp_log(xs_kinfu *k, double *out, int max_iters);
+/* updated-voxel count of the last integration (drives the algorithmic-bytes model) */
+int xs_kinfu_get_stats(const xs_kinfu *k, unsigned long long *out4);
+/* Algorithmic bytes of the last frame per stage (surface, icp, integrate, raycast+resize), DESIGN.md §5 */
+int xs_kinfu_get_algorithmic_bytes(const xs_kinfu *k, double *out4);
+/* device pointer where the per-frame derivative record (world2camera, all components) is kept,
+ * laid out [(1+ncomp)][16] floats — the buffer the multi-GPU layer all-gathers. */
+float *xs_kinfu_pose_record_device(xs_kinfu *k);
+
+/* ---------------------------------------------------------------- outputs & synthetic input (a13, f1) */
+/* saveTxtMatrix, IOHelper.cpp:21-32 */
+int xs_save_pose_txt(const char *path, const float *m16);
+/* CPointCloud::exportPly, Visualization/src/CPointCloud.cpp:42-67 */
+int xs_export_ply(const char *path, const float *points_xyz, const float *normals_xyz, long n);
+/* Synthetic ICL-NUIM-shaped depth: analytic-SDF room sphere-traced to planar depth,
+ * uint16 mm, invalid outside [200,5000] -> 0.  c2w: row-major 4x4 real.  Host-side (multi-threaded). */
+int xs_synth_depth(const float *c2w16, xs_intr intr, int rows, int cols, uint16_t *out_host);
+/* closed-form smooth trajectory, frame 0 = identity; <=1.5 cm and <=0.4 deg per frame */
+int xs_synth_pose(int frame, float *c2w16_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XSLAM_B200_H */

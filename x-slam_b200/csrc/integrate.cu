@@ -1,0 +1,408 @@
+// integrate.cu — TSDF volume container and brick-tiled, direction-batched TSDF integration.
+//
+// Replaces TsdfVolume (XKinectFusion/src/TsdfVolume.cpp:11-77), initVolume (TsdfFusion.cu:4-43),
+// scaleDepthKernal (TsdfFusion.cu:68-82), tsdfFusionKernal / integrateTsdfVolume (TsdfFusion.cu:85-201)
+// and pack/unpack_tsdf (TsdfFusion.h:7-26).
+//
+// One CTA = one 8x8x8 brick (512 threads, thread = voxel, brick-local index = thread index, so every
+// warp access to value / weight / deriv[comp] is one fully coalesced 128-byte line).  The real path of a
+// voxel (projection, depth lookup, sdf, all integer decisions) is evaluated ONCE together with the
+// Jacobian (and for DCSFD the Hessian) of sdf with respect to the camera-frame position v_c; every stored
+// derivative component q is then updated from its own pose-derivative (dR_q, dt_q):
+//      d v_c,q = dR_q * v_g + dt_q,        d sdf_q = J . d v_c,q   (+ d1 v_c^T H d2 v_c for eps1eps2)
+// so one pass over the brick serves all k perturbation directions (the reference re-runs the whole
+// kernel once per direction).  Bricks that cannot project into the image are culled before any load.
+#include "xs_common.cuh"
+
+namespace xs {
+
+__global__ void scale_depth_kernel(const uint16_t *__restrict__ depth, size_t step, int rows, int cols,
+                                   float *__restrict__ out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= cols || y >= rows) return;
+    int Dp = *((const uint16_t *) ((const char *) depth + (size_t) y * step) + x);
+    // TsdfFusion.cu:76-81
+    out[(size_t) y * cols + x] = (Dp > 5000 || Dp < 200) ? 0.f : __fdiv_rn(float(Dp), 1000.f);
+}
+
+__global__ void reset_volume_kernel(float *value, int *weight, float *deriv, size_t nvox, size_t nderiv) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (size_t j = i; j < nvox; j += stride) {
+        value[j] = 0.f;
+        weight[j] = 0;
+    }
+    for (size_t j = i; j < nderiv; j += stride) deriv[j] = 0.f;
+}
+
+struct IntegrateParams {
+    VolumeView V;
+    DevPose v2c;
+    const float *dpose;  // [ncomp][12]
+    const float *depth;  // metres, [rows][cols]
+    int rows, cols;
+    xs_intr intr;
+    int max_weight;
+    float threshold;
+    float trunc_inv;
+    unsigned long long *stats;
+    int nbricks;
+};
+
+// Real path + derivative of sdf w.r.t. v_c for one voxel.  K = 3 (C=1: gradient) or 6 (C=3: pairs
+// (0,0),(0,1),(0,2),(1,1),(1,2),(2,2) -> gradient + Hessian).  Returns false when the voxel is skipped.
+template <int C, int K>
+XS_DEV bool eval_voxel(const IntegrateParams &P, float vcx, float vcy, float vcz, Jet<C, K> &sdf) {
+    typedef Jet<C, K> J;
+    J X = jconst<C, K>(vcx), Y = jconst<C, K>(vcy), Z = jconst<C, K>(vcz);
+    if (C == 1) {
+        X.d[0] = 1.f;
+        Y.d[1] = 1.f;
+        Z.d[2] = 1.f;
+    } else {
+        // direction p=(i,j): eps1 along e_i, eps2 along e_j
+        const int pi[6] = {0, 0, 0, 1, 1, 2}, pj[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+            if (pi[p] == 0) X.d[3 * p] = 1.f;
+            if (pi[p] == 1) Y.d[3 * p] = 1.f;
+            if (pi[p] == 2) Z.d[3 * p] = 1.f;
+            if (pj[p] == 0) X.d[3 * p + 1] = 1.f;
+            if (pj[p] == 1) Y.d[3 * p + 1] = 1.f;
+            if (pj[p] == 2) Z.d[3 * p + 1] = 1.f;
+        }
+    }
+    // TsdfFusion.cu:115-119
+    J inv_z = jconst<C, K>(1.0f) / Z;
+    if (inv_z.v < 0) return false;
+    J image_x = jaddf(jmulf(X, P.intr.fx) * inv_z, P.intr.cx);
+    J image_y = jaddf(jmulf(Y, P.intr.fy) * inv_z, P.intr.cy);
+    // :120-124
+    int coox = __float2int_rd(__fsub_rn(image_x.v, 0.5f));
+    int cooy = __float2int_rd(__fsub_rn(image_y.v, 0.5f));
+    if (!(coox > 1 && cooy > 1 && coox < P.cols - 1 && cooy < P.rows - 1)) return false;
+    // :125-143
+    int nx = __float2int_rn(image_x.v), ny = __float2int_rn(image_y.v);
+    const float *d = P.depth;
+    float d00 = __ldg(d + (size_t) cooy * P.cols + coox);
+    float d10 = __ldg(d + (size_t) cooy * P.cols + coox + 1);
+    float d01 = __ldg(d + (size_t) (cooy + 1) * P.cols + coox);
+    float d11 = __ldg(d + (size_t) (cooy + 1) * P.cols + coox + 1);
+    float gmax = fmaxf(d00, fmaxf(d01, fmaxf(d10, d11)));
+    float gmin = fminf(d00, fminf(d01, fminf(d10, d11)));
+    J Dp;
+    if (__fsub_rn(gmax, gmin) < P.threshold && ((d00 != 0.0f) & (d01 != 0.0f) & (d10 != 0.0f) & (d11 != 0.0f))) {
+        J a = jsubf(image_x, __fadd_rn(float(coox), 0.5f));
+        J b = jsubf(image_y, __fadd_rn(float(cooy), 0.5f));
+        J one_a = jrsubf(1.0f, a), one_b = jrsubf(1.0f, b);
+        Dp = ((jmulf(one_a, d00) * one_b + jmulf(a, d10) * one_b) + jmulf(one_a, d01) * b) + jmulf(a, d11) * b;
+    } else {
+        Dp = jconst<C, K>(__ldg(d + (size_t) ny * P.cols + nx));
+    }
+    // :144-150
+    J xl = jdivf(jsubf(image_x, P.intr.cx), P.intr.fx);
+    J yl = jdivf(jsubf(image_y, P.intr.cy), P.intr.fy);
+    Jet3<C, K> v1 = {Dp * xl, Dp * yl, Dp};
+    Jet3<C, K> vc = {X, Y, Z};
+    sdf = jnorm(v1) - jnorm(vc);
+    return Dp.v > 0 && sdf.v >= -P.V.trunc;
+}
+
+template <int C> __global__ void __launch_bounds__(512) integrate_kernel(const IntegrateParams P) {
+    constexpr int K = (C == 1) ? 3 : 6;
+    extern __shared__ float s_dpose[];  // [ncomp][12]
+    const int tid = threadIdx.x;
+    const int ncomp = P.V.ncomp;
+    for (int i = tid; i < ncomp * 12; i += 512) s_dpose[i] = P.dpose[i];
+    __syncthreads();
+
+    const float vs = P.V.voxel;
+    const float *R = P.v2c.R, *t = P.v2c.t;
+    const int lx = tid & 7, ly = (tid >> 3) & 7, lz = tid >> 6;
+    unsigned long long n_upd = 0;
+
+    for (int b = blockIdx.x; b < P.nbricks; b += gridDim.x) {
+        const int bx = b % P.V.bx, by = (b / P.V.bx) % P.V.by, bz = b / (P.V.bx * P.V.by);
+        // ---- conservative brick cull (uniform per CTA): bounding sphere vs. camera half-space / image planes
+        {
+            const float cxw = (bx * 8 + 4) * vs, cyw = (by * 8 + 4) * vs, czw = (bz * 8 + 4) * vs;
+            const float ccx = R[0] * cxw + R[1] * cyw + R[2] * czw + t[0];
+            const float ccy = R[3] * cxw + R[4] * cyw + R[5] * czw + t[1];
+            const float ccz = R[6] * cxw + R[7] * cyw + R[8] * czw + t[2];
+            const float rad = 6.4f * vs + 1e-4f;  // > half diagonal 3.5*sqrt(3) = 6.06 voxels
+            bool cull = false;
+            if (ccz + rad < 0.f) {
+                cull = true;  // every voxel has z < 0  =>  Re(1/z) < 0
+            } else if (ccz - rad > 1e-3f) {
+                const float fx = P.intr.fx, fy = P.intr.fy, pcx = P.intr.cx, pcy = P.intr.cy;
+                // ix >= lo  <=>  fx*X - (lo-cx)*Z >= 0 ; a voxel needs 2 <= ix < cols and 2 <= iy < rows
+                float nz, nn;
+                nz = -(1.5f - pcx);
+                nn = sqrtf(fx * fx + nz * nz);
+                if (fx * ccx + nz * ccz + rad * nn < 0.f) cull = true;
+                nz = (P.cols + 0.5f - pcx);
+                nn = sqrtf(fx * fx + nz * nz);
+                if (-fx * ccx + nz * ccz + rad * nn < 0.f) cull = true;
+                nz = -(1.5f - pcy);
+                nn = sqrtf(fy * fy + nz * nz);
+                if (fy * ccy + nz * ccz + rad * nn < 0.f) cull = true;
+                nz = (P.rows + 0.5f - pcy);
+                nn = sqrtf(fy * fy + nz * nz);
+                if (-fy * ccy + nz * ccz + rad * nn < 0.f) cull = true;
+            }
+            if (cull) continue;
+        }
+        // ---- per-voxel real path (TsdfFusion.cu:110-114)
+        const int x = bx * 8 + lx, y = by * 8 + ly, z = bz * 8 + lz;
+        const float vgx = __fmul_rn(__fadd_rn(float(x), 0.5f), vs);
+        const float vgy = __fmul_rn(__fadd_rn(float(y), 0.5f), vs);
+        const float vgz = __fmul_rn(__fadd_rn(float(z), 0.5f), vs);
+        const float vcx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], vgx), __fmul_rn(R[1], vgy)), __fmul_rn(R[2], vgz)), t[0]);
+        const float vcy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3], vgx), __fmul_rn(R[4], vgy)), __fmul_rn(R[5], vgz)), t[1]);
+        const float vcz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[6], vgx), __fmul_rn(R[7], vgy)), __fmul_rn(R[8], vgz)), t[2]);
+        Jet<C, K> sdf;
+        const bool upd = eval_voxel<C, K>(P, vcx, vcy, vcz, sdf);
+        if (!upd) continue;  // no barrier inside the brick loop: threads are independent
+        ++n_upd;
+        // ---- TsdfFusion.cu:152-167
+        const bool saturated = sdf.v > P.V.trunc;
+        const float tsdf = saturated ? 1.0f : __fmul_rn(sdf.v, P.trunc_inv);
+        const size_t vi = (size_t) b * BRICK_VOX + tid;
+        const int w_prev = P.V.weight[vi];
+        const float wf = __int2float_rn(w_prev), wf1 = __int2float_rn(w_prev + 1);
+        P.V.value[vi] = __fdiv_rn(__fmaf_rn(P.V.value[vi], wf, tsdf), wf1);
+        P.V.weight[vi] = min(w_prev + 1, P.max_weight);
+        if (ncomp == 0) continue;
+        // ---- derivative components
+        const float inv_w1 = __fdiv_rn(1.f, wf1);
+        const float a_keep = wf * inv_w1;
+        const float sc = saturated ? 0.f : P.trunc_inv * inv_w1;
+        float *dp = P.V.deriv + (size_t) b * ncomp * BRICK_VOX + tid;
+        if (C == 1) {
+            const float J0 = sdf.d[0] * sc, J1 = sdf.d[1] * sc, J2 = sdf.d[2] * sc;
+#pragma unroll 4
+            for (int q = 0; q < ncomp; ++q) {
+                const float *m = s_dpose + q * 12;
+                const float dx = fmaf(m[0], vgx, fmaf(m[1], vgy, fmaf(m[2], vgz, m[9])));
+                const float dy = fmaf(m[3], vgx, fmaf(m[4], vgy, fmaf(m[5], vgz, m[10])));
+                const float dz = fmaf(m[6], vgx, fmaf(m[7], vgy, fmaf(m[8], vgz, m[11])));
+                const float T = fmaf(J0, dx, fmaf(J1, dy, J2 * dz));
+                dp[(size_t) q * BRICK_VOX] = fmaf(dp[(size_t) q * BRICK_VOX], a_keep, T);
+            }
+        } else {
+            // gradient from the diagonal pairs, Hessian from eps1eps2 of each pair
+            const float J0 = sdf.d[0] * sc, J1 = sdf.d[9] * sc, J2 = sdf.d[15] * sc;
+            const float H00 = sdf.d[2] * sc, H01 = sdf.d[5] * sc, H02 = sdf.d[8] * sc, H11 = sdf.d[11] * sc,
+                        H12 = sdf.d[14] * sc, H22 = sdf.d[17] * sc;
+            const int dirs = ncomp / 3;
+#pragma unroll 2
+            for (int k = 0; k < dirs; ++k) {
+                const float *m1 = s_dpose + (3 * k) * 12, *m2 = m1 + 12, *m12 = m1 + 24;
+                const float ax = fmaf(m1[0], vgx, fmaf(m1[1], vgy, fmaf(m1[2], vgz, m1[9])));
+                const float ay = fmaf(m1[3], vgx, fmaf(m1[4], vgy, fmaf(m1[5], vgz, m1[10])));
+                const float az = fmaf(m1[6], vgx, fmaf(m1[7], vgy, fmaf(m1[8], vgz, m1[11])));
+                const float bxx = fmaf(m2[0], vgx, fmaf(m2[1], vgy, fmaf(m2[2], vgz, m2[9])));
+                const float byy = fmaf(m2[3], vgx, fmaf(m2[4], vgy, fmaf(m2[5], vgz, m2[10])));
+                const float bzz = fmaf(m2[6], vgx, fmaf(m2[7], vgy, fmaf(m2[8], vgz, m2[11])));
+                const float cx2 = fmaf(m12[0], vgx, fmaf(m12[1], vgy, fmaf(m12[2], vgz, m12[9])));
+                const float cy2 = fmaf(m12[3], vgx, fmaf(m12[4], vgy, fmaf(m12[5], vgz, m12[10])));
+                const float cz2 = fmaf(m12[6], vgx, fmaf(m12[7], vgy, fmaf(m12[8], vgz, m12[11])));
+                const float T1 = fmaf(J0, ax, fmaf(J1, ay, J2 * az));
+                const float T2 = fmaf(J0, bxx, fmaf(J1, byy, J2 * bzz));
+                const float hx = fmaf(H00, bxx, fmaf(H01, byy, H02 * bzz));
+                const float hy = fmaf(H01, bxx, fmaf(H11, byy, H12 * bzz));
+                const float hz = fmaf(H02, bxx, fmaf(H12, byy, H22 * bzz));
+                const float T12 = fmaf(J0, cx2, fmaf(J1, cy2, J2 * cz2)) + fmaf(ax, hx, fmaf(ay, hy, az * hz));
+                float *p = dp + (size_t) (3 * k) * BRICK_VOX;
+                p[0] = fmaf(p[0], a_keep, T1);
+                p[BRICK_VOX] = fmaf(p[BRICK_VOX], a_keep, T2);
+                p[2 * BRICK_VOX] = fmaf(p[2 * BRICK_VOX], a_keep, T12);
+            }
+        }
+    }
+    // updated-voxel count (drives the algorithmic-bytes model)
+    if (P.stats) {
+        for (int o = 16; o > 0; o >>= 1) n_upd += __shfl_down_sync(0xffffffffu, n_upd, o);
+        if ((tid & 31) == 0 && n_upd) atomicAdd(P.stats, n_upd);
+    }
+}
+
+// dense [z][y][x] planes <-> brick layout (seam views of TsdfVolume::value/weight/grad)
+template <bool TO_DENSE>
+__global__ void convert_planes_kernel(VolumeView V, int comp, float *value, int *weight, float *grad) {
+    size_t n = (size_t) V.rx * V.ry * V.rz;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        int x = (int) (i % V.rx), y = (int) ((i / V.rx) % V.ry), z = (int) (i / ((size_t) V.rx * V.ry));
+        size_t vi = value_index(V, x, y, z);
+        if (TO_DENSE) {
+            if (value) value[i] = V.value[vi];
+            if (weight) weight[i] = V.weight[vi];
+            if (grad) grad[i] = V.deriv[deriv_index(V, x, y, z, comp)];
+        } else {
+            if (value) V.value[vi] = value[i];
+            if (weight) V.weight[vi] = weight[i];
+            if (grad) V.deriv[deriv_index(V, x, y, z, comp)] = grad[i];
+        }
+    }
+}
+
+int upload_pose_derivs(const xs_volume *v, const xs_pose *p, int slot, cudaStream_t s);
+
+}  // namespace xs
+
+using namespace xs;
+
+extern "C" {
+
+xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_range, int comps, int dirs) {
+    if (!res || res[0] <= 0 || (res[0] % 8) || (res[1] % 8) || (res[2] % 8) || (comps != 1 && comps != 3) || dirs < 0) {
+        set_error("xs_volume_create: resolution must be a positive multiple of 8 and comps in {1,3}");
+        return nullptr;
+    }
+    xs_volume *v = new xs_volume();
+    VolumeView &V = v->view;
+    V.rx = res[0];
+    V.ry = res[1];
+    V.rz = res[2];
+    V.bx = res[0] / 8;
+    V.by = res[1] / 8;
+    V.bz = res[2] / 8;
+    V.ncomp = comps * dirs;
+    V.voxel = voxel_size;
+    V.trunc = fmaxf(voxel_size * thres_range, 2.1f * voxel_size);  // TsdfVolume.cpp:25,37
+    v->comps = comps;
+    v->dirs = dirs;
+    size_t nvox = (size_t) res[0] * res[1] * res[2];
+    v->bytes = nvox * 8 + nvox * 4 * V.ncomp;
+    cudaError_t e = cudaMalloc(&V.value, nvox * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&V.weight, nvox * sizeof(int));
+    V.deriv = nullptr;
+    if (e == cudaSuccess && V.ncomp) e = cudaMalloc(&V.deriv, nvox * sizeof(float) * V.ncomp);
+    size_t pose_floats = (size_t) (V.ncomp > 0 ? V.ncomp : 1) * 12 * 2;
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_dpose, pose_floats * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost(&v->h_dpose, pose_floats * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_stats, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&v->h_stats, 4 * sizeof(unsigned long long));
+    v->d_depth_m = nullptr;
+    v->depth_capacity = 0;
+    if (e != cudaSuccess) {
+        set_error(std::string("xs_volume_create: ") + cudaGetErrorString(e));
+        xs_volume_destroy(v);
+        return nullptr;
+    }
+    if (xs_volume_reset(v, nullptr) != XS_OK) {
+        xs_volume_destroy(v);
+        return nullptr;
+    }
+    return v;
+}
+
+void xs_volume_destroy(xs_volume *v) {
+    if (!v) return;
+    cudaFree(v->view.value);
+    cudaFree(v->view.weight);
+    cudaFree(v->view.deriv);
+    cudaFree(v->d_dpose);
+    cudaFreeHost(v->h_dpose);
+    cudaFree(v->d_depth_m);
+    cudaFree(v->d_stats);
+    cudaFreeHost(v->h_stats);
+    delete v;
+}
+
+int xs_volume_reset(xs_volume *v, void *stream) {
+    if (!v) return XS_ERR_ARG;
+    size_t nvox = (size_t) v->view.rx * v->view.ry * v->view.rz;
+    reset_volume_kernel<<<148 * 8, 256, 0, (cudaStream_t) stream>>>(v->view.value, v->view.weight, v->view.deriv, nvox,
+                                                                     nvox * v->view.ncomp);
+    XS_LAUNCH_CHECK();
+    XS_CUDA(cudaStreamSynchronize((cudaStream_t) stream));  // initVolume syncs, TsdfFusion.cu:42
+    return XS_OK;
+}
+
+float xs_volume_trunc_dist(const xs_volume *v) { return v ? v->view.trunc : 0.f; }
+size_t xs_volume_bytes(const xs_volume *v) { return v ? v->bytes : 0; }
+
+int xs_volume_export_planes(const xs_volume *v, int comp, float *d_value, int *d_weight, float *d_grad, void *stream) {
+    if (!v || (d_grad && (comp < 0 || comp >= v->view.ncomp))) return XS_ERR_ARG;
+    convert_planes_kernel<true><<<148 * 8, 256, 0, (cudaStream_t) stream>>>(v->view, comp, d_value, d_weight, d_grad);
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
+int xs_volume_import_planes(xs_volume *v, int comp, const float *d_value, const int *d_weight, const float *d_grad,
+                            void *stream) {
+    if (!v || (d_grad && (comp < 0 || comp >= v->view.ncomp))) return XS_ERR_ARG;
+    convert_planes_kernel<false><<<148 * 8, 256, 0, (cudaStream_t) stream>>>(
+        v->view, comp, const_cast<float *>(d_value), const_cast<int *>(d_weight), const_cast<float *>(d_grad));
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
+
+}  // extern "C"
+
+namespace xs {
+// Copies the derivative components of a pose into staging slot `slot` (0 or 1) of the volume.
+int upload_pose_derivs(const xs_volume *v, const xs_pose *p, int slot, cudaStream_t s) {
+    const int ncomp = v->view.ncomp;
+    if (p->ncomp != ncomp) {
+        set_error("pose carries " + std::to_string(p->ncomp) + " derivative components, volume expects " + std::to_string(ncomp));
+        return XS_ERR_ARG;
+    }
+    if (ncomp == 0) return XS_OK;
+    float *h = v->h_dpose + (size_t) slot * ncomp * 12;
+    for (int q = 0; q < ncomp; ++q) {
+        for (int e = 0; e < 9; ++e) h[q * 12 + e] = p->dR[q * 9 + e];
+        for (int e = 0; e < 3; ++e) h[q * 12 + 9 + e] = p->dt[q * 3 + e];
+    }
+    XS_CUDA(cudaMemcpyAsync(v->d_dpose + (size_t) slot * ncomp * 12, h, (size_t) ncomp * 12 * sizeof(float),
+                            cudaMemcpyHostToDevice, s));
+    return XS_OK;
+}
+}  // namespace xs
+
+extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols,
+                            xs_intr intr, int max_weight, const xs_pose *v2c, float bilinear_threshold,
+                            unsigned long long *stats_host, void *stream) {
+    if (!v || !d_depth || !v2c || rows <= 0 || cols <= 0) return XS_ERR_ARG;
+    cudaStream_t s = (cudaStream_t) stream;
+    if (v->depth_capacity < rows * cols) {
+        cudaFree(v->d_depth_m);
+        XS_CUDA(cudaMalloc(&v->d_depth_m, (size_t) rows * cols * sizeof(float)));
+        v->depth_capacity = rows * cols;
+    }
+    // the staging buffer is reused by the next call: make sure the previous consumer is done
+    XS_CUDA(cudaStreamSynchronize(s));
+    int rc = upload_pose_derivs(v, v2c, 0, s);
+    if (rc != XS_OK) return rc;
+    dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
+    scale_depth_kernel<<<grd, blk, 0, s>>>(d_depth, depth_step_bytes, rows, cols, v->d_depth_m);
+    XS_LAUNCH_CHECK();
+
+    IntegrateParams P;
+    P.V = v->view;
+    for (int i = 0; i < 9; ++i) P.v2c.R[i] = v2c->R[i];
+    for (int i = 0; i < 3; ++i) P.v2c.t[i] = v2c->t[i];
+    P.dpose = v->d_dpose;
+    P.depth = v->d_depth_m;
+    P.rows = rows;
+    P.cols = cols;
+    P.intr = intr;
+    P.max_weight = max_weight;
+    P.threshold = bilinear_threshold;
+    P.trunc_inv = 1.0f / v->view.trunc;  // TsdfFusion.cu:99
+    P.stats = v->d_stats;
+    P.nbricks = v->view.bx * v->view.by * v->view.bz;
+    XS_CUDA(cudaMemsetAsync(v->d_stats, 0, 4 * sizeof(unsigned long long), s));
+    int grid = P.nbricks < 148 * 16 ? P.nbricks : 148 * 16;
+    size_t smem = (size_t) (v->view.ncomp > 0 ? v->view.ncomp : 1) * 12 * sizeof(float);
+    if (v->comps == 1)
+        integrate_kernel<1><<<grid, 512, smem, s>>>(P);
+    else
+        integrate_kernel<3><<<grid, 512, smem, s>>>(P);
+    XS_LAUNCH_CHECK();
+    XS_CUDA(cudaMemcpyAsync(v->h_stats, v->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    XS_CUDA(cudaStreamSynchronize(s));  // integrateTsdfVolume syncs, TsdfFusion.cu:200
+    if (stats_host) stats_host[0] = v->h_stats[0];
+    return XS_OK;
+}

@@ -1,0 +1,159 @@
+// surface.cu — surface measurement: bilateral filter, depth pyramid, vertex and normal maps.
+//
+// Replaces bilateralKernel / pyrDownKernel / computeVmapKernel / computeNmapKernel and their wrappers
+// (XKinectFusion/src/Map.cu:8-102,155-230,262-283).  With real depth and real intrinsics the reference
+// writes devComplex(x, 0) everywhere on this stage (Map.cu:196-198,228-229), so these maps carry the
+// real plane only: float[rows][cols] depth levels and float[3][rows][cols] vertex / normal maps.
+// Integer rounding (bilateral -> int mm, pyrDown integer mean) follows the reference operation by
+// operation, including the exclusive, clamped window bounds (Map.cu:172-173,213-214).
+#include "xs_common.cuh"
+
+namespace xs {
+
+__global__ void __launch_bounds__(256)
+bilateral_kernel(const uint16_t *__restrict__ src, size_t step, int rows, int cols, float *__restrict__ dst,
+                 float sigma_space2_inv_half, float sigma_color2_inv_half) {
+    const int x = threadIdx.x + blockIdx.x * blockDim.x;
+    const int y = threadIdx.y + blockIdx.y * blockDim.y;
+    if (x >= cols || y >= rows) return;
+    auto at = [&](int yy, int xx) -> int { return *((const uint16_t *) ((const char *) src + (size_t) yy * step) + xx); };
+    const int value = at(y, x);
+    const int R = 6, D = R * 2 + 1;
+    const int tx = min(x - D / 2 + D, cols - 1);
+    const int ty = min(y - D / 2 + D, rows - 1);
+    float sum1 = 0, sum2 = 0;
+    for (int cy = max(y - D / 2, 0); cy < ty; ++cy) {
+        for (int cx = max(x - D / 2, 0); cx < tx; ++cx) {
+            const int tmp = at(cy, cx);
+            const float space2 = (float) (unsigned) ((x - cx) * (x - cx) + (y - cy) * (y - cy));
+            const float color2 = (float) (unsigned) ((value - tmp) * (value - tmp));
+            // Map.cu:185-189: fma(space2, s, color2*c) -> __expf -> fma accumulate
+            const float weight = __expf(-__fmaf_rn(space2, sigma_space2_inv_half, __fmul_rn(color2, sigma_color2_inv_half)));
+            sum1 = __fmaf_rn(weight, (float) tmp, sum1);
+            sum2 = __fadd_rn(sum2, weight);
+        }
+    }
+    int round = __float2int_rn(__fdiv_rn(sum1, sum2));
+    if (round > 5000 || round < 200) round = 0;
+    round = max(0, min(round, 32767));
+    dst[(size_t) y * cols + x] = __int2float_rd(round);
+}
+
+__global__ void pyr_down_kernel(const float *__restrict__ src, int srows, int scols, float *__restrict__ dst, int drows,
+                                int dcols, float sigma_color) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dcols || y >= drows) return;
+    const int D = 5;
+    const int center = __float2int_rn(src[(size_t) (2 * y) * scols + 2 * x]);
+    const int tx = min(2 * x - D / 2 + D, scols - 1);
+    const int ty = min(2 * y - D / 2 + D, srows - 1);
+    int sum = 0, count = 0;
+    for (int cy = max(0, 2 * y - D / 2); cy < ty; ++cy)
+        for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
+            const int val = __float2int_rn(src[(size_t) cy * scols + cx]);
+            if (abs(val - center) < 3 * sigma_color) {
+                sum += val;
+                ++count;
+            }
+        }
+    dst[(size_t) y * dcols + x] = __int2float_rd(sum / count);
+}
+
+__global__ void vmap_kernel(const float *__restrict__ depth, int rows, int cols, float *__restrict__ vmap, float fx_inv,
+                            float fy_inv, float cx, float cy) {
+    const int u = threadIdx.x + blockIdx.x * blockDim.x;
+    const int v = threadIdx.y + blockIdx.y * blockDim.y;
+    if (u >= cols || v >= rows) return;
+    const size_t plane = (size_t) rows * cols, pix = (size_t) v * cols + u;
+    const float z = __fdiv_rn(depth[pix], 1000.f);  // Map.cu:16
+    if (z != 0) {
+        vmap[pix] = __fmul_rn(__fmul_rn(z, __fsub_rn(float(u), cx)), fx_inv);
+        vmap[pix + plane] = __fmul_rn(__fmul_rn(z, __fsub_rn(float(v), cy)), fy_inv);
+        vmap[pix + 2 * plane] = z;
+    } else {
+        vmap[pix] = __int_as_float(0x7fffffff);  // NaN in the x plane only (Map.cu:27); y,z made deterministic
+        vmap[pix + plane] = 0.f;
+        vmap[pix + 2 * plane] = 0.f;
+    }
+}
+
+__global__ void nmap_kernel(int rows, int cols, const float *__restrict__ vmap, float *__restrict__ nmap) {
+    const int u = threadIdx.x + blockIdx.x * blockDim.x;
+    const int v = threadIdx.y + blockIdx.y * blockDim.y;
+    if (u >= cols || v >= rows) return;
+    const size_t plane = (size_t) rows * cols, pix = (size_t) v * cols + u;
+    const float qnan = __int_as_float(0x7fffffff);
+    bool ok = !(u == cols - 1 || v == rows - 1);
+    typedef Jet<1, 0> J;
+    Jet3<1, 0> v00, v01, v10;
+    if (ok) {
+        v00.x.v = vmap[pix];
+        v01.x.v = vmap[pix + 1];
+        v10.x.v = vmap[pix + cols];
+        ok = !isnan(v00.x.v) && !isnan(v01.x.v) && !isnan(v10.x.v);
+    }
+    if (!ok) {
+        nmap[pix] = qnan;
+        nmap[pix + plane] = 0.f;
+        nmap[pix + 2 * plane] = 0.f;
+        return;
+    }
+    v00.y.v = vmap[pix + plane];
+    v01.y.v = vmap[pix + plane + 1];
+    v10.y.v = vmap[pix + plane + cols];
+    v00.z.v = vmap[pix + 2 * plane];
+    v01.z.v = vmap[pix + 2 * plane + 1];
+    v10.z.v = vmap[pix + 2 * plane + cols];
+    // Map.cu:60: normalized(cross(v01 - v00, v10 - v00)) in complex arithmetic with zero imaginary parts
+    const Jet3<1, 0> r = jnormalized(jcross(v01 - v00, v10 - v00));
+    nmap[pix] = r.x.v;
+    nmap[pix + plane] = r.y.v;
+    nmap[pix + 2 * plane] = r.z.v;
+}
+
+}  // namespace xs
+
+using namespace xs;
+
+extern "C" {
+
+int xs_bilateral_filter(const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, float *d_out, void *stream) {
+    if (!d_depth || !d_out || rows <= 0 || cols <= 0) return XS_ERR_ARG;
+    const float sigma_color = 30, sigma_space = 4.5;  // Map.cu:4-5
+    dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
+    bilateral_kernel<<<grd, blk, 0, (cudaStream_t) stream>>>(d_depth, depth_step_bytes, rows, cols, d_out,
+                                                             0.5f / (sigma_space * sigma_space),
+                                                             0.5f / (sigma_color * sigma_color));
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
+
+int xs_pyr_down(const float *d_src, int rows, int cols, float *d_dst, void *stream) {
+    if (!d_src || !d_dst || rows < 2 || cols < 2) return XS_ERR_ARG;
+    const float sigma_color = 30;
+    const int drows = rows / 2, dcols = cols / 2;
+    dim3 blk(32, 8), grd(div_up(dcols, 32), div_up(drows, 8));
+    pyr_down_kernel<<<grd, blk, 0, (cudaStream_t) stream>>>(d_src, rows, cols, d_dst, drows, dcols, sigma_color);
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
+
+int xs_create_vmap(xs_intr intr, const float *d_depth, int rows, int cols, float *d_vmap, void *stream) {
+    if (!d_depth || !d_vmap || rows <= 0 || cols <= 0) return XS_ERR_ARG;
+    dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
+    vmap_kernel<<<grd, blk, 0, (cudaStream_t) stream>>>(d_depth, rows, cols, d_vmap, 1.f / intr.fx, 1.f / intr.fy, intr.cx,
+                                                        intr.cy);
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
+
+int xs_create_nmap(const float *d_vmap, int rows, int cols, float *d_nmap, void *stream) {
+    if (!d_vmap || !d_nmap || rows <= 0 || cols <= 0) return XS_ERR_ARG;
+    dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
+    nmap_kernel<<<grd, blk, 0, (cudaStream_t) stream>>>(rows, cols, d_vmap, d_nmap);
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
+
+}  // extern "C"
