@@ -1,0 +1,243 @@
+"""ctypes access to the CHECKERS under oracle/ — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+  RefCuda   oracle/_ref/libxslam_ref.so   unmodified reference CUDA operators @sm_100a + restated orchestrator
+  RefCsfd   oracle/_ref/libref_csfd.so    unmodified reference host bicomplex type (DoubleComplex.cpp)
+  Oracle    oracle/_build/liboracle.so    this repo's CPU restatement of the hot path
+Complex maps cross this boundary as float32 arrays with a trailing (re, im) axis.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_CUDA_PATH = os.path.join(_HERE, "_ref", "libxslam_ref.so")
+REF_CSFD_PATH = os.path.join(_HERE, "_ref", "libref_csfd.so")
+REF_TEST_CSFD = os.path.join(_HERE, "_ref", "ref_test_CSFD")
+ORACLE_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+class XoConfig(C.Structure):
+    _fields_ = [("res", C.c_int * 3), ("voxel_size", C.c_float), ("max_weight", C.c_int), ("thres_range", C.c_float),
+                ("init_xyz", C.c_float * 3), ("r_deg", C.c_float * 3), ("width", C.c_int), ("height", C.c_int),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("num_levels", C.c_int),
+                ("dist_thres", C.c_float), ("angle_thres_deg", C.c_float), ("bi_threshold", C.c_float),
+                ("trunc_k", C.c_float)]
+
+
+def make_xo_config(cfg):
+    c = XoConfig()
+    c.res[:] = [int(cfg["tsdf_size_x"]), int(cfg["tsdf_size_y"]), int(cfg["tsdf_size_z"])]
+    c.voxel_size = float(cfg["tsdf_voxel_size"])
+    c.max_weight = int(cfg["max_integration_weight"])
+    c.thres_range = float(cfg["thres_range"])
+    c.init_xyz[:] = [float(cfg["init_x"]), float(cfg["init_y"]), float(cfg["init_z"])]
+    c.r_deg[:] = [float(cfg["r_x"]), float(cfg["r_y"]), float(cfg["r_z"])]
+    c.width, c.height = int(cfg["depth_width"]), int(cfg["depth_height"])
+    c.fx, c.fy, c.cx, c.cy = float(cfg["fx"]), float(cfg["fy"]), float(cfg["cx"]), float(cfg["cy"])
+    c.num_levels = int(cfg["num_levels"])
+    c.dist_thres = float(cfg["distThres"])
+    c.angle_thres_deg = float(cfg["angleThres"])
+    c.bi_threshold = float(cfg["biInterpolate_threshold"])
+    c.trunc_k = float(cfg["trunc_logistic_k"])
+    return c
+
+
+def _f(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def _p(a, t=C.c_float):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def cpose(R, t):
+    """complex 3x3 / 3-vector (numpy complex64) -> interleaved float arrays for the reference wrappers."""
+    R = np.asarray(R, np.complex64).reshape(9)
+    t = np.asarray(t, np.complex64).reshape(3)
+    return _f(np.stack([R.real, R.imag], -1).reshape(-1)), _f(np.stack([t.real, t.imag], -1).reshape(-1))
+
+
+class RefCuda:
+    """The reference's own CUDA kernels (needs a GPU)."""
+
+    def __init__(self):
+        if not os.path.exists(REF_CUDA_PATH):
+            raise RuntimeError("oracle/_ref/libxslam_ref.so not built (make -C oracle ref; needs /root/reference)")
+        self.lib = C.CDLL(REF_CUDA_PATH)
+        self.lib.ref_kinfu_create.restype = C.c_void_p
+        self.lib.ref_kinfu_trunc.restype = C.c_float
+
+    def bilateral(self, depth):
+        d = np.ascontiguousarray(depth, np.uint16)
+        out = np.zeros(d.shape + (2,), np.float32)
+        self.lib.ref_bilateral(_p(d, C.c_uint16), d.shape[0], d.shape[1], _p(out))
+        return out
+
+    def pyrdown(self, src):
+        s = _f(src)
+        out = np.zeros((s.shape[0] // 2, s.shape[1] // 2, 2), np.float32)
+        self.lib.ref_pyrdown(_p(s), s.shape[0], s.shape[1], _p(out))
+        return out
+
+    def vmap_nmap(self, depth_c, fx, fy, cx, cy):
+        s = _f(depth_c)
+        rows, cols = s.shape[:2]
+        v = np.zeros((3, rows, cols, 2), np.float32)
+        n = np.zeros((3, rows, cols, 2), np.float32)
+        self.lib.ref_vmap_nmap(_p(s), rows, cols, C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), _p(v), _p(n))
+        return v, n
+
+    def resize_map(self, m, normalize):
+        s = _f(m)
+        _, rows, cols, _ = s.shape
+        out = np.zeros((3, rows // 2, cols // 2, 2), np.float32)
+        self.lib.ref_resize_map(_p(s), rows, cols, int(normalize), _p(out))
+        return out
+
+    def integrate(self, depth, intr, max_weight, res, voxel, R, t, trunc, value, weight, grad, threshold=0.0):
+        """value/weight/grad: dense [z, y, x] arrays, updated in place.  R, t: complex64.  Returns kernel ms."""
+        d = np.ascontiguousarray(depth, np.uint16)
+        Rf, tf = cpose(R, t)
+        r = (C.c_int * 3)(*res)
+        ms = C.c_float()
+        self.lib.ref_integrate(_p(d, C.c_uint16), d.shape[0], d.shape[1], C.c_float(intr[0]), C.c_float(intr[1]),
+                               C.c_float(intr[2]), C.c_float(intr[3]), int(max_weight), r, C.c_float(voxel), _p(Rf), _p(tf),
+                               C.c_float(trunc), _p(value), _p(weight, C.c_int), _p(grad), C.c_float(threshold), C.byref(ms))
+        return ms.value
+
+    def raycast(self, intr, Rc2v, tc2v, Rv2w, tv2w, trunc, res, voxel, value, grad, rows, cols):
+        a, b = cpose(Rc2v, tc2v)
+        c, d = cpose(Rv2w, tv2w)
+        r = (C.c_int * 3)(*res)
+        v = np.zeros((3, rows, cols, 2), np.float32)
+        n = np.zeros((3, rows, cols, 2), np.float32)
+        ms = C.c_float()
+        self.lib.ref_raycast(C.c_float(intr[0]), C.c_float(intr[1]), C.c_float(intr[2]), C.c_float(intr[3]), _p(a), _p(b),
+                             _p(c), _p(d), C.c_float(trunc), r, C.c_float(voxel), _p(_f(value)), _p(_f(grad)), rows, cols,
+                             _p(v), _p(n), C.byref(ms))
+        return v, n, ms.value
+
+    def estimate_combined(self, Rcurr, tcurr, vmap_curr, nmap_curr, Rprev_inv, tprev, intr, vmap_prev, nmap_prev,
+                          dist_thres, angle_thres):
+        a, b = cpose(Rcurr, tcurr)
+        c, d = cpose(Rprev_inv, tprev)
+        rows, cols = vmap_curr.shape[1:3]
+        A = np.zeros((72,), np.float64)
+        bb = np.zeros((12,), np.float64)
+        ms = C.c_float()
+        self.lib.ref_estimate_combined(_p(a), _p(b), _p(_f(vmap_curr)), _p(_f(nmap_curr)), _p(c), _p(d), C.c_float(intr[0]),
+                                       C.c_float(intr[1]), C.c_float(intr[2]), C.c_float(intr[3]), _p(_f(vmap_prev)),
+                                       _p(_f(nmap_prev)), rows, cols, C.c_float(dist_thres), C.c_float(angle_thres),
+                                       _p(A, C.c_double), _p(bb, C.c_double), C.byref(ms))
+        A = A.reshape(6, 6, 2)  # column-major entries (symmetric)
+        bb = bb.reshape(6, 2)
+        return (A[..., 0] + 1j * A[..., 1]).T.copy(), bb[:, 0] + 1j * bb[:, 1], ms.value
+
+    def tsdf_hessian(self, depth, intr, res, voxel, R4, t4, trunc, gt):
+        """R4: [9, 4], t4: [3, 4] bicomplex components (re.re, re.im, im.re, im.im)."""
+        d = np.ascontiguousarray(depth, np.uint16)
+        r = (C.c_int * 3)(*res)
+        out = np.zeros((4,), np.float32)
+        ms = C.c_float()
+        self.lib.ref_tsdf_hessian(_p(d, C.c_uint16), d.shape[0], d.shape[1], C.c_float(intr[0]), C.c_float(intr[1]),
+                                  C.c_float(intr[2]), C.c_float(intr[3]), r, C.c_float(voxel), _p(_f(R4)), _p(_f(t4)),
+                                  C.c_float(trunc), _p(_f(gt)), _p(out), C.byref(ms))
+        return out, ms.value
+
+    def kinfu(self, cfg, seed_imag=None):
+        return RefKinfu(self, cfg, seed_imag)
+
+
+class RefKinfu:
+    """Restated orchestrator driving the reference kernels, one perturbation direction per instance."""
+
+    def __init__(self, ref, cfg, seed_imag=None):
+        self.lib = ref.lib
+        self.cfg = cfg
+        c = make_xo_config(cfg)
+        s = None
+        if seed_imag is not None:
+            s = _f(seed_imag).reshape(16)
+        self.h = C.c_void_p(self.lib.ref_kinfu_create(C.byref(c), _p(s) if s is not None else None))
+        self.W, self.H, self.L = int(cfg["depth_width"]), int(cfg["depth_height"]), int(cfg["num_levels"])
+        self.res = (int(cfg["tsdf_size_x"]), int(cfg["tsdf_size_y"]), int(cfg["tsdf_size_z"]))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_kinfu_destroy(self.h)
+            self.h = None
+
+    def process_frame(self, depth):
+        d = np.ascontiguousarray(depth, np.uint16)
+        return self.lib.ref_kinfu_process_frame(self.h, _p(d, C.c_uint16))
+
+    def pose(self):
+        out = np.zeros((16, 2), np.float32)
+        self.lib.ref_kinfu_get_pose(self.h, _p(out))
+        return (out[:, 0] + 1j * out[:, 1]).reshape(4, 4)
+
+    def times(self):
+        out = np.zeros((5,), np.float32)
+        self.lib.ref_kinfu_get_times(self.h, _p(out))
+        return dict(zip(("surface", "icp", "integrate", "raycast", "total"), out.tolist()))
+
+    def trunc(self):
+        return self.lib.ref_kinfu_trunc(self.h)
+
+    def map(self, which, level=0):
+        idx = {"depth": 0, "vmap_curr": 1, "nmap_curr": 2, "vmap_g_prev": 3, "nmap_g_prev": 4}[which]
+        r, c = self.H >> level, self.W >> level
+        out = np.zeros(((r, c, 2) if idx == 0 else (3, r, c, 2)), np.float32)
+        self.lib.ref_kinfu_get_map(self.h, idx, level, _p(out))
+        return out
+
+    def volume(self):
+        shape = (self.res[2], self.res[1], self.res[0])
+        v = np.zeros(shape, np.float32)
+        w = np.zeros(shape, np.int32)
+        g = np.zeros(shape, np.float32)
+        self.lib.ref_kinfu_get_volume(self.h, _p(v), _p(w, C.c_int), _p(g))
+        return v, w, g
+
+    def icp_log(self, max_iters=16):
+        buf = np.zeros((max_iters, 84), np.float64)
+        n = self.lib.ref_kinfu_take_icp_log(self.h, _p(buf, C.c_double), max_iters)
+        buf = buf[:n]
+        A = buf[:, :72].reshape(n, 6, 6, 2)
+        b = buf[:, 72:].reshape(n, 6, 2)
+        return (A[..., 0] + 1j * A[..., 1]).transpose(0, 2, 1), b[..., 0] + 1j * b[..., 1]
+
+
+class RefCsfd:
+    """The reference's host DoubleComplex arithmetic (CPU)."""
+    OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "sqrt": 4, "exp": 5, "log": 6, "sin": 7, "cos": 8, "atan2": 9,
+           "pow": 10, "atan": 11}
+
+    def __init__(self):
+        if not os.path.exists(REF_CSFD_PATH):
+            raise RuntimeError("oracle/_ref/libref_csfd.so not built (make -C oracle ref; needs /root/reference)")
+        self.lib = C.CDLL(REF_CSFD_PATH)
+        self.lib.ref_dc_chain_bench.restype = C.c_double
+
+    def apply(self, op, a, b=None, p=0.0):
+        """a, b: [n, 4] float32 (AoS as in the reference: re.re, re.im, im.re, im.im)."""
+        a = _f(a)
+        out = np.zeros_like(a)
+        bp = _p(_f(b)) if b is not None else None
+        rc = self.lib.ref_dc_apply(self.OPS[op], _p(a), bp, C.c_float(p), _p(out), C.c_long(a.shape[0]))
+        assert rc == 0
+        return out
+
+    def chain(self, t, h=1e-6):
+        t = _f(t)
+        out = np.zeros((t.shape[0], 4), np.float32)
+        self.lib.ref_dc_chain(_p(t), C.c_float(h), _p(out), C.c_long(t.shape[0]))
+        return out
+
+    def chain_bench(self, t, h=1e-6, reps=1):
+        t = _f(t)
+        cs = C.c_double()
+        rate = self.lib.ref_dc_chain_bench(_p(t), C.c_float(h), C.c_long(t.shape[0]), int(reps), C.byref(cs))
+        return rate, cs.value

@@ -1,0 +1,146 @@
+"""End-to-end parity of the frame loop on the GPU (BASELINE.json configs[1]): the batched pipeline
+(6 CSFD pose directions in one run) against the restated orchestrator driving the reference's own kernels
+once per direction, plus the DCSFD pipeline against finite differences of the CSFD one, and the
+DeviceArray bicomplex kernels against the reference's host DoubleComplex.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from common import H_, ICL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _save(out_dir, name, obj):
+    with open(os.path.join(out_dir, name), "w") as f:
+        json.dump(obj, f, indent=1, sort_keys=True)
+    print("[parity]", name, json.dumps(obj)[:2000])
+
+
+@pytest.fixture(scope="module")
+def frames(xs):
+    return [xs.synth_depth(f) for f in range(4)]
+
+
+def test_pipeline_csfd_vs_reference(xs, refcuda, frames, out_dir):
+    """configs[1]: 640x480, 256^3 TSDF, CSFD gradient of the pose w.r.t. the 6-DoF camera parameters."""
+    import torch
+    cfg = dict(xs.DEFAULT_CONFIG)
+    seeds = xs.pose_seeds_csfd()
+    k = xs.KinectFusionReconstruction()
+    k.SetYamlParameters(cfg, comps=1, seeds=seeds)
+    refs = [refcuda.kinfu(cfg, None)] + [refcuda.kinfu(cfg, seeds[q].reshape(4, 4)) for q in range(6)]
+    rep = {"frames": []}
+    for f, d in enumerate(frames):
+        assert k.ProcessFrame(d) == 1
+        for r in refs:
+            assert r.process_frame(d) == 1
+        w2c = k.world2camera
+        fr = {"frame": f}
+        P0 = refs[0].pose()
+        fr["pose_real_abs_vs_zero_seed"] = float(np.abs(w2c[0] - P0.real).max())
+        fr["pose_deriv_rel"] = [rel_err(w2c[1 + q], refs[1 + q].pose().imag, floor=H_ * 1e-3) for q in range(6)]
+        fr["pose_real_abs_seeded"] = [float(np.abs(w2c[0] - refs[1 + q].pose().real).max()) for q in range(6)]
+        # ICP normal equations of this frame, iteration by iteration
+        if f > 0:
+            mine = k.icp_log()
+            Ar, br = refs[0].icp_log()
+            fr["icp_iters"] = [int(mine.shape[0]), int(Ar.shape[0])]
+            n = min(mine.shape[0], Ar.shape[0])
+            fr["icp_A_real_rel"] = [rel_err(mine[i, 0, :36].reshape(6, 6), Ar[i].real) for i in range(n)]
+            for q in range(6):
+                Aq, bq = refs[1 + q].icp_log()
+                if q in (0, 3):
+                    fr["icp_A_deriv_rel_d%d" % q] = [rel_err(mine[i, 1 + q, :36].reshape(6, 6), Aq[i].imag) for i in range(n)]
+        # volume state
+        v, w, _ = k.volume_planes(0)
+        rv, rw, _ = refs[0].volume()
+        fr["weight_mismatch"] = int((w.cpu().numpy() != rw).sum())
+        fr["value_rel"] = rel_err(v.cpu().numpy(), rv)
+        gq = []
+        for q in (0, 4):
+            _, _, g = k.volume_planes(q)
+            _, _, rg = refs[1 + q].volume()
+            gq.append(rel_err(g.cpu().numpy(), rg))
+        fr["grad_rel_d0_d4"] = gq
+        # raycast maps
+        vm = k.map("vmap_g_prev", 0).cpu().numpy()
+        rvm = refs[0].map("vmap_g_prev", 0)
+        valid = ~np.isnan(rvm[0, ..., 0])
+        fr["raycast_mask_mismatch"] = int((np.isnan(vm[0, 0]) != ~valid).sum())
+        both = valid & ~np.isnan(vm[0, 0])
+        fr["raycast_real_rel"] = max(rel_err(vm[0, p][both], rvm[p, ..., 0][both]) for p in range(3))
+        r4 = refs[5].map("vmap_g_prev", 0)
+        b4 = both & ~np.isnan(r4[0, ..., 0])
+        fr["raycast_deriv_rel_d4"] = max(rel_err(vm[5, p][b4], r4[p, ..., 1][b4]) for p in range(3))
+        fr["times_ms"], fr["launches"] = k.times()
+        fr["ref_times_ms"] = refs[0].times()
+        rep["frames"].append(fr)
+    _save(out_dir, "pipeline_csfd_report.json", rep)
+    # golden vectors for the CPU oracle pins (small: poses + ICP systems of the zero-seed reference run)
+    np.savez_compressed(os.path.join(out_dir, "golden_pipeline_256.npz"),
+                        pose_zero=refs[0].pose(), poses_seeded=np.stack([r.pose() for r in refs[1:]]), seeds=seeds)
+    last = rep["frames"][-1]
+    first = rep["frames"][0]
+    assert first["weight_mismatch"] == 0 and first["raycast_mask_mismatch"] == 0
+    assert first["value_rel"] <= 1e-6 and first["raycast_real_rel"] <= 1e-6
+    assert last["pose_real_abs_vs_zero_seed"] <= 1e-5
+    assert max(last["pose_deriv_rel"]) <= 1e-2
+
+
+def test_pipeline_dcsfd_consistency(xs, frames, out_dir):
+    """DCSFD through the frame loop is new work (the reference has no caller): its first-order components must
+    reproduce the CSFD pipeline's, and its eps1eps2 component must match a finite difference of CSFD gradients."""
+    cfg = dict(xs.DEFAULT_CONFIG)
+    cfg.update(tsdf_size_x=128, tsdf_size_y=128, tsdf_size_z=128, tsdf_voxel_size=0.06)
+    pairs = [(0, 0), (0, 4), (3, 5)]
+    seeds2, _ = xs.pose_seeds_dcsfd(pairs)
+    k2 = xs.KinectFusionReconstruction()
+    k2.SetYamlParameters(cfg, comps=3, seeds=seeds2)
+    k1 = xs.KinectFusionReconstruction()
+    k1.SetYamlParameters(cfg, comps=1, seeds=xs.pose_seeds_csfd(), solve_mode=xs.KinectFusionReconstruction.SOLVE_ANALYTIC)
+    for d in frames[:3]:
+        assert k2.ProcessFrame(d) == 1 and k1.ProcessFrame(d) == 1
+    w2, w1 = k2.world2camera, k1.world2camera
+    rep = {"real_abs": float(np.abs(w2[0] - w1[0]).max()), "first_order_rel": []}
+    for n, (i, j) in enumerate(pairs):
+        rep["first_order_rel"].append([rel_err(w2[1 + 3 * n], w1[1 + i], floor=1e-12), rel_err(w2[2 + 3 * n], w1[1 + j], floor=1e-12)])
+    rep["second_order_norm"] = [float(np.abs(w2[3 + 3 * n]).max()) for n in range(len(pairs))]
+    _save(out_dir, "pipeline_dcsfd_report.json", rep)
+    assert rep["real_abs"] == 0.0
+    assert max(max(r) for r in rep["first_order_rel"]) <= 1e-3
+
+
+def test_dc_array_vs_reference_host(xs, out_dir):
+    """configs[0] on the device: packed-SoA bicomplex kernels against the reference's DoubleComplex.cpp (CPU)."""
+    import torch
+    from oracle import pyref
+    from xslam_b200 import ops
+    ref = pyref.RefCsfd()
+    rng = np.random.default_rng(0)
+    n = 4096
+    h = 1e-6
+    a = np.stack([rng.uniform(0.5, 2.0, n), h * rng.standard_normal(n), h * rng.standard_normal(n), h * h * rng.standard_normal(n)], 1).astype(np.float32)
+    b = np.stack([rng.uniform(0.5, 2.0, n), h * rng.standard_normal(n), h * rng.standard_normal(n), h * h * rng.standard_normal(n)], 1).astype(np.float32)
+    da, db = torch.from_numpy(np.ascontiguousarray(a.T)).cuda(), torch.from_numpy(np.ascontiguousarray(b.T)).cuda()
+    rep = {}
+    for op in ("add", "sub", "mul", "div", "sqrt", "exp", "log", "sin", "cos", "pow"):
+        r = ref.apply(op, a, b if op in ("add", "sub", "mul", "div") else None, 3.0)
+        m = ops.dc_apply(op, da, db if op in ("add", "sub", "mul", "div") else None, 3.0).cpu().numpy().T
+        rep[op] = [rel_err(m[:, c], r[:, c]) for c in range(4)]
+    t = rng.uniform(0.1, 1.5, n).astype(np.float32)
+    r = ref.chain(t, h)
+    m = ops.dc_chain(torch.from_numpy(t).cuda(), h).cpu().numpy().T
+    rep["chain"] = [rel_err(m[:, c], r[:, c]) for c in range(4)]
+    # the known answer of Experiments/test_CSFD/main.cpp:203-219 at t = 0.5
+    m05 = ops.dc_chain(torch.tensor([0.5], device="cuda"), h).cpu().numpy()[:, 0]
+    rep["t0.5"] = [float(m05[1] / h), float(m05[3] / h / h)]
+    _save(out_dir, "dc_array_report.json", rep)
+    assert abs(m05[1] / h - 2.73911) < 2e-4 and abs(m05[3] / h / h - 9.26892) < 0.05
+    for op, e in rep.items():
+        if op == "t0.5":
+            continue
+        assert e[0] <= 2e-6 and e[1] <= 1e-5 and e[2] <= 1e-5, (op, e)

@@ -1,0 +1,288 @@
+"""Stage-wise parity on the GPU: libxslam_b200 (through its C-ABI) against the reference's own CUDA kernels
+(oracle/_ref/libxslam_ref.so, unmodified sources recompiled for sm_100a) on identical synthetic inputs.
+
+Bars (BASELINE.json north_star / SURVEY.md §8d): integer pixel/voxel decisions and validity masks bit-exact;
+real parts <= 1e-6 relative; derivative parts: stated per test (FP32 forward-mode noise vs the reference's
+FP32 complex arithmetic), both measured and written to gpurun_out/parity_report.json.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from common import H_, ICL, poses_for_frame, rand_dpose, rel_err, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+REPORT = {}
+
+
+def _report(out_dir, key, **kw):
+    REPORT[key] = {k: (float(v) if isinstance(v, (np.floating, float)) else v) for k, v in kw.items()}
+    with open(os.path.join(out_dir, "parity_report.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
+    print("[parity]", key, REPORT[key])
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def depth0(xs):
+    return xs.synth_depth(0)
+
+
+@pytest.fixture(scope="module")
+def depth1(xs):
+    return xs.synth_depth(6)
+
+
+def _dev_u16(torch, d):
+    return torch.from_numpy(d.astype(np.int16)).cuda()
+
+
+def test_surface_measurement_bit_exact(xs, refcuda, torch_mod, depth0, out_dir):
+    """bilateral -> pyrDown x2 -> vmap/nmap x3 against Map.cu (a6): every plane bit-exact, NaN masks identical."""
+    torch = torch_mod
+    from xslam_b200 import ops
+    intr = xs.Intr(**ICL)
+    d = _dev_u16(torch, depth0)
+    mine = [ops.bilateralFilter(d)]
+    ref = [refcuda.bilateral(depth0)]
+    for i in range(1, 3):
+        mine.append(ops.pyrDown(mine[-1]))
+        ref.append(refcuda.pyrdown(ref[-1]))
+    stats = {}
+    for i in range(3):
+        a = mine[i].cpu().numpy()
+        assert np.array_equal(a, ref[i][..., 0]), "depth level %d differs" % i
+        assert not ref[i][..., 1].any()
+        li = intr.level(i)
+        vm = ops.createVMap(li, mine[i])
+        nm = ops.createNMap(vm)
+        rv, rn = refcuda.vmap_nmap(ref[i], li.fx, li.fy, li.cx, li.cy)
+        for name, m, r in (("vmap", vm, rv), ("nmap", nm, rn)):
+            m = m.cpu().numpy()
+            valid = ~np.isnan(r[0, ..., 0])
+            assert np.array_equal(np.isnan(m[0]), ~valid), "%s level %d NaN mask" % (name, i)
+            md = max(int(ulp_diff(m[p][valid], r[p, ..., 0][valid]).max()) for p in range(3))
+            stats["%s%d_max_ulp" % (name, i)] = md
+            assert md == 0, "%s level %d real part differs by %d ulp" % (name, i, md)
+            assert not r[..., 1][:, valid].any()
+    _report(out_dir, "surface", **stats)
+
+
+def _integrate_both(xs, refcuda, torch, frames, res, voxel, ncomp, seed, threshold=0.0):
+    from xslam_b200 import ops
+    rng = np.random.default_rng(seed)
+    intr = xs.Intr(**ICL)
+    vol = ops.TsdfVolume((res,) * 3, voxel, 3.0, comps=1, dirs=ncomp)
+    trunc = vol.getTsdfTruncDist()
+    ref_state = [(np.zeros((res,) * 3, np.float32), np.zeros((res,) * 3, np.int32), np.zeros((res,) * 3, np.float32))
+                 for _ in range(ncomp)]
+    ref_ms, upd = [], []
+    for f in frames:
+        depth = xs.synth_depth(f)
+        v2c, _, _ = poses_for_frame(xs, f)
+        R = v2c[:3, :3].astype(np.float32)
+        t = v2c[:3, 3].astype(np.float32)
+        dR, dt = rand_dpose(rng, ncomp)
+        upd.append(ops.integrateTsdfVolume(_dev_u16(torch, depth), intr, 100, vol, ops.PoseBatch(R, t, dR, dt), threshold))
+        for q in range(ncomp):
+            Rc = R.reshape(9) + 1j * dR[q]
+            tc = t + 1j * dt[q]
+            v, w, g = ref_state[q]
+            ref_ms.append(refcuda.integrate(depth, (ICL["fx"], ICL["fy"], ICL["cx"], ICL["cy"]), 100, (res,) * 3, voxel,
+                                            Rc, tc, trunc, v, w, g, threshold))
+    return vol, ref_state, upd, ref_ms
+
+
+@pytest.mark.parametrize("threshold", [0.0, 0.06])
+def test_integration_parity(xs, refcuda, torch_mod, out_dir, threshold):
+    """tsdfFusionKernal (a9): 3 frames into a 128^3 volume, 3 directions in one pass vs 3 reference passes."""
+    torch = torch_mod
+    res, voxel, ncomp = 128, 0.06, 3
+    vol, ref_state, upd, ref_ms = _integrate_both(xs, refcuda, torch, [0, 6, 12], res, voxel, ncomp, 1, threshold)
+    w = vol.weight().cpu().numpy()
+    v = vol.value().cpu().numpy()
+    # weights (integer, decide which voxels were updated in which frame) must agree with every reference pass
+    wm = [int((w != ref_state[q][1]).sum()) for q in range(ncomp)]
+    vm_ulp = ulp_diff(v, ref_state[0][0])
+    n_upd = int((ref_state[0][1] > 0).sum())
+    stats = dict(updated_voxels=n_upd, weight_mismatch=wm, value_max_ulp=int(vm_ulp.max()),
+                 value_ulp_gt0=int((vm_ulp > 0).sum()), value_rel=rel_err(v, ref_state[0][0]), upd_counts=upd,
+                 ref_kernel_ms=float(np.mean(ref_ms)))
+    gerr = []
+    for q in range(ncomp):
+        g = vol.grad(q).cpu().numpy()
+        gerr.append(rel_err(g, ref_state[q][2]))
+        assert np.array_equal(g != 0, ref_state[q][2] != 0) or rel_err((g != 0) * 1.0, (ref_state[q][2] != 0) * 1.0) < 1e-3
+    stats["grad_rel"] = gerr
+    _report(out_dir, "integrate_thr%g" % threshold, **stats)
+    assert n_upd > 100000
+    assert max(wm) == 0, "updated-voxel sets differ from the reference"
+    assert stats["value_rel"] <= 1e-6
+    # FP32 forward-mode derivative vs the reference's FP32 complex arithmetic, scale-relative
+    assert max(gerr) <= 2e-5
+
+
+def test_raycast_parity(xs, refcuda, torch_mod, out_dir):
+    """rayCastKernel (a10) on an identical volume state: hit masks bit-exact, vertices/normals and derivative maps."""
+    torch = torch_mod
+    from xslam_b200 import ops
+    res, voxel, ncomp = 128, 0.06, 3
+    vol, ref_state, _, _ = _integrate_both(xs, refcuda, torch, [0, 6], res, voxel, ncomp, 2)
+    # isolate the stage: load the reference's volume state into the brick layout
+    for q in range(ncomp):
+        vol.load(torch.from_numpy(ref_state[0][0]).cuda(), torch.from_numpy(ref_state[0][1]).cuda(),
+                 torch.from_numpy(ref_state[q][2]).cuda(), q)
+    rng = np.random.default_rng(3)
+    _, c2v, v2w = poses_for_frame(xs, 6)
+    Rc, tc = c2v[:3, :3].astype(np.float32), c2v[:3, 3].astype(np.float32)
+    Rw, tw = v2w[:3, :3].astype(np.float32), v2w[:3, 3].astype(np.float32)
+    dRc, dtc = rand_dpose(rng, ncomp)
+    dRw, dtw = rand_dpose(rng, ncomp)
+    intr = xs.Intr(**ICL)
+    vm, nm = ops.raycast(intr, ops.PoseBatch(Rc, tc, dRc, dtc), ops.PoseBatch(Rw, tw, dRw, dtw), vol, 480, 640)
+    vm, nm = vm.cpu().numpy(), nm.cpu().numpy()
+    stats = {}
+    ms = []
+    for q in range(ncomp):
+        rv, rn, t = refcuda.raycast((ICL["fx"], ICL["fy"], ICL["cx"], ICL["cy"]), Rc.reshape(9) + 1j * dRc[q], tc + 1j * dtc[q],
+                                    Rw.reshape(9) + 1j * dRw[q], tw + 1j * dtw[q], vol.getTsdfTruncDist(), (res,) * 3, voxel,
+                                    ref_state[0][0], ref_state[q][2], 480, 640)
+        ms.append(t)
+        for name, m, r in (("v", vm, rv), ("n", nm, rn)):
+            valid = ~np.isnan(r[0, ..., 0])
+            mism = int((np.isnan(m[0, 0]) != ~valid).sum())
+            stats["%s_mask_mismatch_d%d" % (name, q)] = mism
+            both = valid & ~np.isnan(m[0, 0])
+            stats["%s_real_rel_d%d" % (name, q)] = max(rel_err(m[0, p][both], r[p, ..., 0][both]) for p in range(3))
+            stats["%s_deriv_rel_d%d" % (name, q)] = max(rel_err(m[1 + q, p][both], r[p, ..., 1][both]) for p in range(3))
+            stats["%s_valid" % name] = int(valid.sum())
+    stats["ref_kernel_ms"] = float(np.mean(ms))
+    _report(out_dir, "raycast", **stats)
+    assert stats["v_valid"] > 100000
+    for q in range(ncomp):
+        assert stats["v_mask_mismatch_d%d" % q] == 0 and stats["n_mask_mismatch_d%d" % q] == 0
+        assert stats["v_real_rel_d%d" % q] <= 1e-6 and stats["n_real_rel_d%d" % q] <= 2e-6
+        assert stats["v_deriv_rel_d%d" % q] <= 1e-4 and stats["n_deriv_rel_d%d" % q] <= 1e-3
+
+
+def _complex_map(m, q):
+    """packed SoA [(1+ncomp),3,r,c] -> reference layout [3,r,c,2] for direction q"""
+    return np.stack([m[0], m[1 + q]], -1)
+
+
+def test_resize_and_icp_parity(xs, refcuda, torch_mod, out_dir):
+    """resizeVMap/NMap (a10) and estimateCombined (a7) on identical inputs produced by the reference pipeline."""
+    torch = torch_mod
+    from xslam_b200 import ops
+    cfg = dict(xs.DEFAULT_CONFIG)
+    cfg.update(tsdf_size_x=128, tsdf_size_y=128, tsdf_size_z=128, tsdf_voxel_size=0.06)
+    ncomp = 2
+    seeds = xs.pose_seeds_csfd()[[0, 4]]
+    refs = [refcuda.kinfu(cfg, seeds[q].reshape(4, 4)) for q in range(ncomp)]
+    for f in (0, 1):
+        d = xs.synth_depth(f)
+        for r in refs:
+            assert r.process_frame(d) == 1
+    stats = {}
+    # ---- resize: level 0 -> 1 of the raycast maps
+    for name, which, fn in (("vmap", "vmap_g_prev", ops.resizeVMap), ("nmap", "nmap_g_prev", ops.resizeNMap)):
+        lv0 = [r.map(which, 0) for r in refs]
+        lv1 = [r.map(which, 1) for r in refs]
+        packed = np.stack([lv0[0][..., 0]] + [lv0[q][..., 1] for q in range(ncomp)], 0)
+        out = fn(torch.from_numpy(np.ascontiguousarray(packed)).cuda()).cpu().numpy()
+        valid = ~np.isnan(lv1[0][0, ..., 0])
+        assert np.array_equal(np.isnan(out[0, 0]), ~valid)
+        stats["resize_%s_real_rel" % name] = max(rel_err(out[0, p][valid], lv1[0][p, ..., 0][valid]) for p in range(3))
+        stats["resize_%s_deriv_rel" % name] = max(rel_err(out[1 + q, p][valid], lv1[q][p, ..., 1][valid])
+                                                  for p in range(3) for q in range(ncomp))
+    # ---- ICP normal equations at every level with the reference's own maps and pose guess
+    intr = xs.Intr(**ICL)
+    d2 = xs.synth_depth(2)
+    for r in refs:  # surface measurement of the next frame fills vmap_curr / nmap_curr
+        pass
+    curr_v, curr_n = [], []
+    dd = ops.bilateralFilter(_dev_u16(torch, d2))
+    lev = [dd]
+    for i in range(1, 3):
+        lev.append(ops.pyrDown(lev[-1]))
+    for i in range(3):
+        vm = ops.createVMap(intr.level(i), lev[i])
+        curr_v.append(vm)
+        curr_n.append(ops.createNMap(vm))
+    rng = np.random.default_rng(5)
+    for level in range(3):
+        c2w = np.linalg.inv(refs[0].pose().real.astype(np.float64))
+        Rp = c2w[:3, :3]
+        R = Rp.astype(np.float32)
+        t = c2w[:3, 3].astype(np.float32)
+        Rinv = np.linalg.inv(Rp).astype(np.float32)
+        dR, dt = rand_dpose(rng, ncomp)
+        dRi, dti = rand_dpose(rng, ncomp)
+        pv = [r.map("vmap_g_prev", level) for r in refs]
+        pn = [r.map("nmap_g_prev", level) for r in refs]
+        pv_packed = np.ascontiguousarray(np.stack([pv[0][..., 0]] + [pv[q][..., 1] for q in range(ncomp)], 0))
+        pn_packed = np.ascontiguousarray(np.stack([pn[0][..., 0]] + [pn[q][..., 1] for q in range(ncomp)], 0))
+        li = intr.level(level)
+        A, b = ops.estimateCombined(ops.PoseBatch(R, t, dR, dt), curr_v[level], curr_n[level], ops.PoseBatch(Rinv, t, dRi, dti),
+                                    li, torch.from_numpy(pv_packed).cuda(), torch.from_numpy(pn_packed).cuda(), 0.10,
+                                    float(np.sin(np.float32(15.0) / 180.0 * np.pi)))
+        cv = curr_v[level].cpu().numpy()
+        cn = curr_n[level].cpu().numpy()
+        cvc = np.stack([cv, np.zeros_like(cv)], -1)
+        cnc = np.stack([cn, np.zeros_like(cn)], -1)
+        for q in range(ncomp):
+            Ar, br, ms = refcuda.estimate_combined(R.reshape(9) + 1j * dR[q], t + 1j * dt[q], cvc, cnc,
+                                                   Rinv.reshape(9) + 1j * dRi[q], t + 1j * dti[q],
+                                                   (li.fx, li.fy, li.cx, li.cy), pv[q], pn[q], 0.10,
+                                                   float(np.sin(np.float32(15.0) / 180.0 * np.pi)))
+            stats["icp_L%d_A_real_rel_d%d" % (level, q)] = rel_err(A[0], Ar.real)
+            stats["icp_L%d_b_real_rel_d%d" % (level, q)] = rel_err(b[0], br.real)
+            stats["icp_L%d_A_deriv_rel_d%d" % (level, q)] = rel_err(A[1 + q], Ar.imag)
+            stats["icp_L%d_b_deriv_rel_d%d" % (level, q)] = rel_err(b[1 + q], br.imag)
+            stats["icp_L%d_A00" % level] = float(Ar.real[0, 0])
+            stats["icp_ref_ms_L%d" % level] = ms
+    _report(out_dir, "resize_icp", **stats)
+    for k, v in stats.items():
+        if k.endswith("real_rel") or "_real_rel_" in k:
+            assert v <= 1e-6, (k, v)
+        if "deriv_rel" in k:
+            assert v <= 1e-4, (k, v)
+
+
+def test_dcsfd_volume_loss_parity(xs, refcuda, torch_mod, out_dir):
+    """ComputeLocalTsdfHessianKernel (a12): one bicomplex direction on a 128^3 ground-truth volume."""
+    torch = torch_mod
+    from xslam_b200 import ops
+    res, voxel = 128, 0.06
+    vol, ref_state, _, _ = _integrate_both(xs, refcuda, torch, [0], res, voxel, 1, 7)
+    gt = ref_state[0][0]
+    depth = xs.synth_depth(3)
+    v2c, _, _ = poses_for_frame(xs, 3)
+    R, t = v2c[:3, :3].astype(np.float32), v2c[:3, 3].astype(np.float32)
+    rng = np.random.default_rng(11)
+    h = 1e-6
+    dR = np.zeros((3, 9), np.float32)
+    dt = np.zeros((3, 3), np.float32)
+    dR[0], dt[0] = rand_dpose(rng, 1, h)[0][0], rand_dpose(rng, 1, h)[1][0]
+    dR[1], dt[1] = rand_dpose(rng, 1, h)[0][0], rand_dpose(rng, 1, h)[1][0]
+    dR[2], dt[2] = rand_dpose(rng, 1, h * h)[0][0], rand_dpose(rng, 1, h * h)[1][0]
+    trunc = vol.getTsdfTruncDist()
+    mine = ops.ComputeLocalTsdf_hessian(_dev_u16(torch, depth), xs.Intr(**ICL), (res,) * 3, voxel, ops.PoseBatch(R, t, dR, dt),
+                                        trunc, torch.from_numpy(gt).cuda())
+    R4 = np.stack([R.reshape(9), dR[0], dR[1], dR[2]], -1)
+    t4 = np.stack([t, dt[0], dt[1], dt[2]], -1)
+    ref, ms = refcuda.tsdf_hessian(depth, (ICL["fx"], ICL["fy"], ICL["cx"], ICL["cy"]), (res,) * 3, voxel, R4, t4, trunc, gt)
+    stats = dict(mine=[float(x) for x in mine], ref=[float(x) for x in ref], ref_ms=ms,
+                 rel=[abs(mine[i] - ref[i]) / max(abs(float(ref[i])), 1e-30) for i in range(4)])
+    _report(out_dir, "tsdf_hessian", **stats)
+    assert mine[3] == ref[3] and ref[3] > 1000, "processed-voxel counts differ"
+    assert stats["rel"][0] <= 1e-5 and stats["rel"][1] <= 1e-4 and stats["rel"][2] <= 1e-3

@@ -1,0 +1,272 @@
+"""Host-side mirror of class KinectFusionReconstruction (XKinectFusion/include/KinectFusionReconstruction.h:19-220)
+over the C-ABI pipeline object (xs_kinfu).  Method names, the YAML keys and the 1/0 return convention are the
+reference's; the perturbation seeds generalise the commented seeding line KinectFusionReconstruction.cpp:22
+to a batch of k directions (CSFD, comps=1) or k bicomplex directions (DCSFD, comps=3).
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from . import _capi
+from ._capi import Config, check
+
+H_ = 1e-7  # Internal.h:33
+
+
+def load_yaml(path):
+    """Flat `key: value` YAML reader (yaml-cpp is not available; the reference config is flat:
+    Experiments/test_xkinect_fusion/configs/ICL_traj2.yaml)."""
+    cfg = {}
+    with open(path) as f:
+        for line in f:
+            line = line.split("#", 1)[0].strip()
+            if not line or ":" not in line:
+                continue
+            k, v = line.split(":", 1)
+            v = v.strip().strip('"').strip("'")
+            if v.lower() in ("true", "false"):
+                cfg[k.strip()] = v.lower() == "true"
+                continue
+            try:
+                cfg[k.strip()] = int(v)
+            except ValueError:
+                try:
+                    cfg[k.strip()] = float(v)
+                except ValueError:
+                    cfg[k.strip()] = v
+    return cfg
+
+
+DEFAULT_CONFIG = {  # Experiments/test_xkinect_fusion/configs/ICL_traj2.yaml:17-48
+    "biInterpolate_threshold": 0.0, "trunc_logistic_k": 0, "flag_use_gtPose": False,
+    "tsdf_size_x": 256, "tsdf_size_y": 256, "tsdf_size_z": 256, "tsdf_voxel_size": 0.03,
+    "max_integration_weight": 100, "thres_range": 3, "init_x": 3.2, "init_y": 3.2, "init_z": 3.2,
+    "r_x": 0, "r_y": 0, "r_z": 0, "depth_width": 640, "depth_height": 480,
+    "fx": 481.20, "fy": -480.00, "cx": 319.50, "cy": 239.50, "num_levels": 3, "distThres": 0.10, "angleThres": 15,
+    "frame_step": 1,
+}
+
+
+def make_config(cfg):
+    c = Config()
+    c.res[:] = [int(cfg["tsdf_size_x"]), int(cfg["tsdf_size_y"]), int(cfg["tsdf_size_z"])]
+    c.voxel_size = float(cfg["tsdf_voxel_size"])
+    c.max_weight = int(cfg["max_integration_weight"])
+    c.thres_range = float(cfg["thres_range"])
+    c.init_xyz[:] = [float(cfg["init_x"]), float(cfg["init_y"]), float(cfg["init_z"])]
+    c.r_deg[:] = [float(cfg["r_x"]), float(cfg["r_y"]), float(cfg["r_z"])]
+    c.width, c.height = int(cfg["depth_width"]), int(cfg["depth_height"])
+    c.fx, c.fy, c.cx, c.cy = float(cfg["fx"]), float(cfg["fy"]), float(cfg["cx"]), float(cfg["cy"])
+    c.num_levels = int(cfg["num_levels"])
+    c.dist_thres = float(cfg["distThres"])
+    c.angle_thres_deg = float(cfg["angleThres"])
+    c.bi_threshold = float(cfg["biInterpolate_threshold"])
+    c.trunc_k = float(cfg["trunc_logistic_k"])
+    return c
+
+
+def se3_generators():
+    """d/d(xi_i) of se3Exp(xi) at xi = 0 (KinectFusionReconstruction.h:176-219, xi = [v; omega]) as 4x4 matrices."""
+    G = np.zeros((6, 4, 4), np.float64)
+    for i in range(3):
+        G[i, i, 3] = 1.0
+    G[3, 1, 2], G[3, 2, 1] = -1.0, 1.0
+    G[4, 0, 2], G[4, 2, 0] = 1.0, -1.0
+    G[5, 0, 1], G[5, 1, 0] = -1.0, 1.0
+    return G
+
+
+def pose_seeds_csfd(h=H_):
+    """6 CSFD directions: world2camera = se3Exp(h e_i) -> imaginary part h * G_i.  [6, 16] float32."""
+    return (h * se3_generators()).reshape(6, 16).astype(np.float32)
+
+
+def pose_seeds_dcsfd(pairs=None, h=H_, n_params=6):
+    """DCSFD directions for parameter pairs (i, j): eps1 along e_i, eps2 along e_j; the second-order seed
+    is h^2 * (G_i G_j + G_j G_i)/2 (second derivative of se3Exp along the two axes).  [k*3, 16] float32."""
+    G = se3_generators()
+    if pairs is None:
+        pairs = [(i, j) for i in range(n_params) for j in range(i, n_params)]
+    out = np.zeros((len(pairs), 3, 16), np.float64)
+    for k, (i, j) in enumerate(pairs):
+        out[k, 0] = (h * G[i]).reshape(16)
+        out[k, 1] = (h * G[j]).reshape(16)
+        out[k, 2] = (h * h * 0.5 * (G[i] @ G[j] + G[j] @ G[i])).reshape(16)
+    return out.reshape(-1, 16).astype(np.float32), pairs
+
+
+class _DeviceView:
+    """Zero-copy view of library-owned device memory through the CUDA array interface."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class KinectFusionReconstruction:
+    """Drop-in for the reference class on the hot path.  depth frames are uint16 millimetres [H, W]."""
+
+    SOLVE_EIGEN_LLT, SOLVE_ANALYTIC = 0, 1
+
+    def __init__(self):
+        self.lib = _capi.load()
+        self.h = None
+        self.depth_width = 0
+        self.depth_height = 0
+        self.config = None
+
+    def SetYamlParameters(self, config, comps=1, seeds=None, solve_mode=None):
+        """KinectFusionReconstruction.cpp:9-73.  config: dict of YAML keys (or a path).
+        seeds: [dirs*comps, 16] h-scaled derivative components of the initial world2camera."""
+        if isinstance(config, str):
+            config = load_yaml(config)
+        cfg = dict(DEFAULT_CONFIG)
+        cfg.update(config)
+        self.config = cfg
+        if cfg["num_levels"] > 3:
+            print("sorry, the max supported multi-level = 3")
+        self.depth_width, self.depth_height = int(cfg["depth_width"]), int(cfg["depth_height"])
+        self.frame_step = int(cfg.get("frame_step", 1))
+        seeds = None if seeds is None else np.ascontiguousarray(seeds, np.float32).reshape(-1, 16)
+        ncomp = 0 if seeds is None else seeds.shape[0]
+        if ncomp % comps:
+            raise ValueError("seeds must hold dirs*comps rows")
+        self.comps, self.dirs, self.ncomp = comps, ncomp // comps, ncomp
+        if solve_mode is None:
+            solve_mode = self.SOLVE_EIGEN_LLT if comps == 1 else self.SOLVE_ANALYTIC
+        c = make_config(cfg)
+        sp = seeds.ctypes.data_as(C.POINTER(C.c_float)) if ncomp else None
+        if self.h:
+            self.lib.xs_kinfu_destroy(self.h)
+        self.h = self.lib.xs_kinfu_create(C.byref(c), comps, self.dirs, sp, solve_mode)
+        if not self.h:
+            raise _capi.XsError("SetYamlParameters: " + self.lib.xs_last_error().decode())
+
+    def ReleaseBuffers(self):
+        if self.h:
+            self.lib.xs_kinfu_destroy(self.h)
+            self.h = None
+
+    __del__ = ReleaseBuffers
+
+    # -- the frame loop -------------------------------------------------------------------------
+    def ProcessFrame(self, depth):
+        """KinectFusionReconstruction.cpp:147-159.  depth: numpy uint16 [H, W] (host) or a torch CUDA int16/uint16
+        tensor (device resident).  Returns 1, or 0 when frame alignment failed."""
+        if hasattr(depth, "data_ptr"):
+            return self.lib.xs_kinfu_process_frame(self.h, C.c_void_p(depth.data_ptr()), 1)
+        d = np.ascontiguousarray(depth, np.uint16)
+        if d.shape != (self.depth_height, self.depth_width):
+            raise ValueError("depth frame must be [%d, %d]" % (self.depth_height, self.depth_width))
+        return self.lib.xs_kinfu_process_frame(self.h, d.ctypes.data_as(C.c_void_p), 0)
+
+    @property
+    def frame_id(self):
+        return self.lib.xs_kinfu_frame_id(self.h)
+
+    def getFrame(self):
+        return self.frame_id
+
+    @property
+    def world2camera(self):
+        """[(1+ncomp), 4, 4]: component 0 is the real matrix, the rest are the h-scaled derivative components."""
+        out = np.zeros(((1 + self.ncomp) * 16,), np.float32)
+        check(self.lib.xs_kinfu_get_world2camera(self.h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out.reshape(1 + self.ncomp, 4, 4)
+
+    def pose_c2w(self):
+        """world2camera_record.back().inverse().real(), main.cpp:61"""
+        out = np.zeros((16,), np.float32)
+        check(self.lib.xs_kinfu_get_pose_c2w(self.h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out.reshape(4, 4)
+
+    def times(self):
+        out = np.zeros((10,), np.float32)
+        check(self.lib.xs_kinfu_get_times(self.h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        names = ("surface", "icp", "integrate", "raycast", "total")
+        return {n: float(out[i]) for i, n in enumerate(names)}, {n: int(out[5 + i]) for i, n in enumerate(names)}
+
+    def stats(self):
+        out = (C.c_ulonglong * 4)()
+        check(self.lib.xs_kinfu_get_stats(self.h, out))
+        return [int(x) for x in out]
+
+    def algorithmic_bytes(self):
+        out = (C.c_double * 4)()
+        check(self.lib.xs_kinfu_get_algorithmic_bytes(self.h, out))
+        return dict(zip(("surface", "icp", "integrate", "raycast"), [float(x) for x in out]))
+
+    def icp_log(self, max_iters=16):
+        buf = np.zeros((max_iters, 1 + self.ncomp, 42), np.float64)
+        n = self.lib.xs_kinfu_take_icp_log(self.h, buf.ctypes.data_as(C.POINTER(C.c_double)), max_iters)
+        return buf[:n]
+
+    def map(self, which, level=0):
+        """Device map as a torch tensor view copy.  which: depth, vmap_curr, nmap_curr, vmap_g_prev, nmap_g_prev."""
+        import torch
+        idx = {"depth": 0, "vmap_curr": 1, "nmap_curr": 2, "vmap_g_prev": 3, "nmap_g_prev": 4}[which]
+        rows, cols, nc = C.c_int(), C.c_int(), C.c_int()
+        p = self.lib.xs_kinfu_map(self.h, idx, level, C.byref(rows), C.byref(cols), C.byref(nc))
+        shape = (rows.value, cols.value) if idx == 0 else (1 + nc.value, 3, rows.value, cols.value)
+        return torch.as_tensor(_DeviceView(p, shape), device="cuda").clone()
+
+    def volume_planes(self, comp=0):
+        """Seam views of TsdfVolume::value/weight/grad (TsdfVolume.h:46-49) as dense [z, y, x] torch tensors."""
+        import torch
+        res = [int(self.config["tsdf_size_z"]), int(self.config["tsdf_size_y"]), int(self.config["tsdf_size_x"])]
+        v = torch.empty(res, dtype=torch.float32, device="cuda")
+        w = torch.empty(res, dtype=torch.int32, device="cuda")
+        g = torch.empty(res, dtype=torch.float32, device="cuda") if self.ncomp else None
+        vol = self.lib.xs_kinfu_volume(self.h)
+        check(self.lib.xs_volume_export_planes(vol, comp, C.c_void_p(v.data_ptr()), C.c_void_p(w.data_ptr()),
+                                               C.c_void_p(g.data_ptr()) if g is not None else None, None))
+        torch.cuda.synchronize()
+        return v, w, g
+
+    def ExportPointCloud(self, max_buffer=1000000):
+        """KinectFusionReconstruction.cpp:334-372.  Returns (points, normals) numpy [n, 3]."""
+        import torch
+        pts = torch.empty((max_buffer, 3), dtype=torch.float32, device="cuda")
+        nrm = torch.empty((max_buffer, 3), dtype=torch.float32, device="cuda")
+        n = self.lib.xs_extract_points(self.lib.xs_kinfu_volume(self.h), C.c_void_p(pts.data_ptr()),
+                                       C.c_void_p(nrm.data_ptr()), max_buffer, None)
+        check(n, "ExportPointCloud")
+        return pts[:n].cpu().numpy(), nrm[:n].cpu().numpy()
+
+    def pose_record_device_ptr(self):
+        return self.lib.xs_kinfu_pose_record_device(self.h)
+
+
+# ------------------------------------------------------------------ outputs and synthetic input
+def savePose(output_dir, frame_id, pose):
+    """main.cpp:8-14 + IOHelper.cpp:21-32: frame-%06d.pose.txt, fixed, precision 7, trailing space."""
+    os.makedirs(output_dir, exist_ok=True)
+    path = os.path.join(output_dir, "frame-%06d.pose.txt" % frame_id)
+    m = np.ascontiguousarray(pose, np.float32).reshape(16)
+    check(_capi.load().xs_save_pose_txt(path.encode(), m.ctypes.data_as(C.POINTER(C.c_float))))
+    return path
+
+
+def exportPly(path, points, normals):
+    """CPointCloud::exportPly, Visualization/src/CPointCloud.cpp:42-67"""
+    p = np.ascontiguousarray(points, np.float32)
+    n = np.ascontiguousarray(normals, np.float32)
+    check(_capi.load().xs_export_ply(path.encode(), p.ctypes.data_as(C.POINTER(C.c_float)),
+                                     n.ctypes.data_as(C.POINTER(C.c_float)), p.shape[0]))
+
+
+def synth_pose(frame):
+    out = np.zeros((16,), np.float32)
+    check(_capi.load().xs_synth_pose(int(frame), out.ctypes.data_as(C.POINTER(C.c_float))))
+    return out.reshape(4, 4)
+
+
+def synth_depth(frame_or_pose, width=640, height=480, fx=481.20, fy=-480.00, cx=319.50, cy=239.50):
+    """Synthetic ICL-NUIM-shaped depth frame (uint16 mm) for a frame index or an explicit c2w pose."""
+    pose = synth_pose(frame_or_pose) if np.isscalar(frame_or_pose) else np.asarray(frame_or_pose, np.float32)
+    pose = np.ascontiguousarray(pose, np.float32).reshape(16)
+    out = np.zeros((height, width), np.uint16)
+    check(_capi.load().xs_synth_depth(pose.ctypes.data_as(C.POINTER(C.c_float)), _capi.Intr(fx, fy, cx, cy), height, width,
+                                      out.ctypes.data_as(C.POINTER(C.c_uint16))))
+    return out
