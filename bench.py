@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py — differentiated frames/s of the CSFD/DCSFD KinectFusion frame loop on N B200s (one process per GPU).
+
+  python bench.py --gpus 1 --steps K --warmup W            this repo's CUDA path (libxslam_b200.so, via the C-ABI)
+  python bench.py --impl reference ...                      the CPU path timed on the box's host cores (oracle port)
+
+A "step" is one ProcessFrame (surface measurement + 12 ICP iterations + TSDF integration + raycast + pyramid) on
+the next frame of a synthetic ICL-NUIM-shaped sequence, producing the real outputs AND every requested derivative
+direction.  Workload (BASELINE.json configs[2]/[3]): 640x480 depth, 512^3 TSDF @ 0.015 m, 55 DCSFD (bicomplex)
+directions = 165 derivative components (the 21 axis pairs of the 6 pose DoF + 34 mixed pose-space directions; the
+reference's intrinsics are real floats, so intrinsic directions are an extension that is not built yet).
+With N > 1 the directions are sharded across ranks (strong scaling: total work fixed), every rank keeps a replica of
+the real state, and the per-frame pose-derivative records are all-gathered over NCCL.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--res", type=int, default=512)
+    ap.add_argument("--dirs", type=int, default=55)
+    ap.add_argument("--comps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_cfg(xs, res):
+    cfg = dict(xs.DEFAULT_CONFIG)
+    cfg.update(tsdf_size_x=res, tsdf_size_y=res, tsdf_size_z=res, tsdf_voxel_size=7.68 / res)
+    return cfg
+
+
+def all_directions(xs, comps, dirs):
+    """Seeds [dirs*comps, 16]: DCSFD -> 21 axis pairs (i<=j) of the pose DoF first, then deterministic mixed pairs."""
+    if comps == 1:
+        G = xs.se3_generators().reshape(6, 16)
+        rng = np.random.default_rng(7)
+        W = np.concatenate([np.eye(6), rng.standard_normal((max(dirs - 6, 0), 6)) / np.sqrt(6)])[:dirs]
+        return (xs.H_ * W @ G).astype(np.float32)
+    G = xs.se3_generators()
+    rng = np.random.default_rng(7)
+    pairs = [(np.eye(6)[i], np.eye(6)[j]) for i in range(6) for j in range(i, 6)]
+    while len(pairs) < dirs:
+        pairs.append((rng.standard_normal(6) / np.sqrt(6), rng.standard_normal(6) / np.sqrt(6)))
+    out = np.zeros((dirs, 3, 16))
+    for k, (u, w) in enumerate(pairs[:dirs]):
+        Gu = np.tensordot(u, G, 1)
+        Gw = np.tensordot(w, G, 1)
+        out[k, 0] = (xs.H_ * Gu).reshape(16)
+        out[k, 1] = (xs.H_ * Gw).reshape(16)
+        out[k, 2] = (xs.H_ * xs.H_ * 0.5 * (Gu @ Gw + Gw @ Gu)).reshape(16)
+    return out.reshape(-1, 16).astype(np.float32)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_port_frames(xs, cfg, n_frames, budget_s=25.0):
+    """Times the CPU oracle port of the frame loop (one first-order complex direction per run, exactly the
+    reference's one-direction-per-run mode) with all host threads.  Returns (seconds per frame-direction, frames)."""
+    from oracle import pyref
+    k = pyref.OracleKinfu(cfg, xs.pose_seeds_csfd()[0])
+    times = []
+    t_all = time.perf_counter()
+    for f in range(n_frames):
+        d = xs.synth_depth(f)
+        t0 = time.perf_counter()
+        ok = k.process_frame(d)
+        times.append(time.perf_counter() - t0)
+        if not ok or time.perf_counter() - t_all > budget_s:
+            break
+    return times
+
+
+def run_reference(args, xs, rank):
+    """--impl reference: the CPU path (oracle port of the reference's frame loop; the reference itself has no CPU
+    implementation of this path and its orchestrator cannot be built offline) on the host cores."""
+    if rank != 0:
+        return
+    cfg = workload_cfg(xs, args.res)
+    cores = os.cpu_count() or 1
+    total = args.warmup + args.steps
+    times = cpu_port_frames(xs, cfg, total, budget_s=240.0)
+    timed = times[args.warmup:] if len(times) > args.warmup else times[-1:]
+    per_dir = float(np.mean(timed))
+    ncomp_dirs = args.dirs * (1 if args.comps == 1 else 3)  # a bicomplex direction carries 3 derivative components
+    fps = 1.0 / (per_dir * ncomp_dirs)
+    sample = ("%d frames of the 640x480 / %d^3 sequence, ONE first-order complex direction per pass (the reference's "
+              "one-direction-per-run mode); value = 1 / (%d derivative components x measured pass time)" % (len(timed), args.res, ncomp_dirs))
+    line = {"impl": "reference", "metric": "differentiated_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": len(timed), "warmup": min(args.warmup, len(times) - len(timed)), "ms_per_step": per_dir * ncomp_dirs * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "icl_synth_640x480_tsdf%d_dcsfd%d" % (args.res, args.dirs)},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ CUDA path
+class DeviceRecord:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def run_ours(args, xs, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = workload_cfg(xs, args.res)
+    seeds = all_directions(xs, args.comps, args.dirs).reshape(args.dirs, args.comps, 16)
+    mine = list(range(rank, args.dirs, world))
+    my_seeds = np.ascontiguousarray(seeds[mine].reshape(-1, 16))
+    k = xs.KinectFusionReconstruction()
+    k.SetYamlParameters(cfg, comps=args.comps, seeds=my_seeds)
+    lib = xs.load()
+    max_dirs = (args.dirs + world - 1) // world
+    rec_len = (1 + max_dirs * args.comps) * 16
+    gather_out = torch.zeros((world, rec_len), dtype=torch.float32, device="cuda") if world > 1 else None
+    send = torch.zeros((rec_len,), dtype=torch.float32, device="cuda") if world > 1 else None
+    rec_view = torch.as_tensor(DeviceRecord(k.pose_record_device_ptr(), (1 + len(mine) * args.comps) * 16), device="cuda")
+
+    W, K = args.warmup, args.steps
+    n_frames = W + 2 * K
+    frames = [xs.synth_depth(f) for f in range(n_frames)]
+    dev_frames = [torch.from_numpy(f.astype(np.int16)).cuda() for f in frames[:W + K]]
+    pinned = [torch.from_numpy(f.astype(np.int16)).pin_memory() for f in frames[W + K:]]
+
+    def step(depth):
+        ok = k.ProcessFrame(depth)
+        if not ok:
+            raise RuntimeError("frame alignment failed: " + lib.xs_last_error().decode())
+        if world > 1:  # derivatives gathered by NCCL all-gather over NVLink (north_star (4))
+            send[: rec_view.numel()].copy_(rec_view)
+            dist.all_gather_into_tensor(gather_out, send)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(W):
+        step(dev_frames[i])
+    # ---------------- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    stage_ms = {n: 0.0 for n in ("surface", "icp", "integrate", "raycast", "total")}
+    abytes = {n: 0.0 for n in ("surface", "icp", "integrate", "raycast")}
+    kern_ms, upd = 0.0, 0
+    vol = lib.xs_kinfu_volume(k.h)
+    sync()
+    l0 = lib.xs_launch_count()
+    t0 = time.perf_counter()
+    for i in range(K):
+        step(dev_frames[W + i])
+        tm, _ = k.times()
+        for n in stage_ms:
+            stage_ms[n] += tm[n]
+        ab = k.algorithmic_bytes()
+        for n in abytes:
+            abytes[n] += ab[n]
+        kern_ms += lib.xs_volume_last_integrate_ms(vol)
+        upd += k.stats()[0]
+    sync()
+    t_dev = time.perf_counter() - t0
+    launches = lib.xs_launch_count() - l0
+    # ---------------- timed region 2: end to end through the public call with HOST buffers
+    sync()
+    t0 = time.perf_counter()
+    for i in range(K):
+        step(pinned[i].numpy().view(np.uint16))
+        w2c = k.world2camera  # the step's result, read on the host
+    sync()
+    t_e2e = time.perf_counter() - t0
+    clocks = sampler.summary()
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ncomp_local = len(mine) * args.comps
+    peak, peak_src = measured_hbm_peak()
+    int_bytes = abytes["integrate"] / K
+    int_ms = kern_ms / K
+    achieved = int_bytes / (int_ms * 1e-3) / 1e9 if int_ms > 0 else 0.0
+    h2d = 640 * 480 * 2 + ncomp_local * 12 * 4 * (1 + 2 + 24)
+    d2h = 12 * 27 * (1 + ncomp_local) * 8 + 32
+    line = {
+        "metric": "differentiated_frames_per_s", "value": K / t_dev, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "icl_synth_640x480_tsdf%d_dcsfd%d" % (args.res, args.dirs), "depth": "640x480 uint16 mm",
+                   "tsdf": "%d^3 @ %.4f m" % (args.res, 7.68 / args.res), "directions": args.dirs, "components_per_direction": args.comps,
+                   "derivative_planes": args.dirs * args.comps, "directions_per_rank": max_dirs, "sharding": "directions over ranks, real state replicated",
+                   "l2": "per-step working set (volume %.1f GB/rank) >> 126 MB L2, no flush needed" % (lib.xs_volume_bytes(vol) / 1e9)},
+        "e2e": {"value": K / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "integrate_kernel<%d>" % args.comps, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int_bytes, "kernel_ms": int_ms, "updated_voxels_per_launch": upd / K},
+        "stages_ms_per_step": {n: v / K for n, v in stage_ms.items()},
+        "stages_algorithmic_GBps": {n: (abytes[n] / K) / (stage_ms[n] / K * 1e-3) / 1e9 if stage_ms[n] > 0 else 0.0 for n in abytes},
+        "frame_algorithmic_bytes": sum(abytes.values()) / K,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        times = cpu_port_frames(xs, cfg, 3, budget_s=30.0)
+        per_dir = float(np.mean(times[1:])) if len(times) > 1 else float(times[0])
+        ncd = args.dirs * (1 if args.comps == 1 else 3)
+        line["cpu_baseline"] = {"value": 1.0 / (per_dir * ncd), "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": "%d frames, 640x480 / %d^3, ONE first-order complex direction per pass (reference's "
+                                          "one-direction-per-run mode, all host threads); scaled by %d derivative components" %
+                                          (max(len(times) - 1, 1), args.res, ncd), "seconds_per_direction_frame": per_dir}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import xslam_b200 as xs
+    if args.impl == "reference":
+        run_reference(args, xs, rank)
+        return
+    run_ours(args, xs, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

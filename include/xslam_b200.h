@@ -93,6 +93,8 @@ void xs_volume_destroy(xs_volume *v);
 int xs_volume_reset(xs_volume *v, void *stream);
 float xs_volume_trunc_dist(const xs_volume *v);
 size_t xs_volume_bytes(const xs_volume *v);
+/* device duration (CUDA events on the launching stream) of the last integration kernel, in ms */
+float xs_volume_last_integrate_ms(const xs_volume *v);
 /* Seam views (TsdfVolume::value/weight/grad, TsdfVolume.h:46-49): dense x-fastest planes [z][y][x]
  * on the device; comp = derivative component index in [0, ncomp) for d_grad (ignored when NULL). */
 int xs_volume_export_planes(const xs_volume *v, int comp, float *d_value, int *d_weight, float *d_grad, void *stream);

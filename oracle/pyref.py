@@ -241,3 +241,223 @@ class RefCsfd:
         cs = C.c_double()
         rate = self.lib.ref_dc_chain_bench(_p(t), C.c_float(h), C.c_long(t.shape[0]), int(reps), C.byref(cs))
         return rate, cs.value
+
+
+class Oracle:
+    """This repo's CPU restatement (oracle/xslam_oracle.cpp, oracle/csfd_oracle.cpp).  f64=True selects the FP64
+    arithmetic variant.  Complex maps are float32 arrays [3, rows, cols, 2]; poses are complex64."""
+
+    def __init__(self):
+        if not os.path.exists(ORACLE_PATH):
+            raise RuntimeError("oracle/_build/liboracle.so not built (make -C oracle oracle)")
+        self.lib = C.CDLL(ORACLE_PATH)
+        self.lib.oracle_integrate.restype = C.c_long
+
+    # ---- surface measurement
+    def bilateral(self, depth):
+        d = np.ascontiguousarray(depth, np.uint16)
+        out = np.zeros(d.shape, np.float32)
+        self.lib.oracle_bilateral(_p(d, C.c_uint16), d.shape[0], d.shape[1], _p(out))
+        return out
+
+    def pyrdown(self, src):
+        s = _f(src)
+        out = np.zeros((s.shape[0] // 2, s.shape[1] // 2), np.float32)
+        self.lib.oracle_pyrdown(_p(s), s.shape[0], s.shape[1], _p(out))
+        return out
+
+    def vmap_nmap(self, depth, intr, f64=False):
+        s = _f(depth)
+        rows, cols = s.shape
+        v = np.zeros((3, rows, cols, 2), np.float32)
+        n = np.zeros((3, rows, cols, 2), np.float32)
+        self.lib.oracle_vmap_nmap(_p(s), rows, cols, C.c_float(intr[0]), C.c_float(intr[1]), C.c_float(intr[2]),
+                                  C.c_float(intr[3]), _p(v), _p(n), int(f64))
+        return v, n
+
+    def resize_map(self, m, normalize, f64=False):
+        s = _f(m)
+        _, rows, cols, _ = s.shape
+        out = np.zeros((3, rows // 2, cols // 2, 2), np.float32)
+        self.lib.oracle_resize_map(_p(s), rows, cols, int(normalize), _p(out), int(f64))
+        return out
+
+    # ---- volume
+    def integrate(self, depth, intr, max_weight, res, voxel, R, t, trunc, value, weight, grad, threshold=0.0, f64=False,
+                  z0=0, z1=None):
+        d = np.ascontiguousarray(depth, np.uint16)
+        Rf, tf = cpose(R, t)
+        r = (C.c_int * 3)(*res)
+        return self.lib.oracle_integrate(_p(d, C.c_uint16), d.shape[0], d.shape[1], C.c_float(intr[0]), C.c_float(intr[1]),
+                                         C.c_float(intr[2]), C.c_float(intr[3]), int(max_weight), r, C.c_float(voxel), _p(Rf),
+                                         _p(tf), C.c_float(trunc), _p(value), _p(weight, C.c_int), _p(grad),
+                                         C.c_float(threshold), int(z0), int(res[2] if z1 is None else z1), int(f64))
+
+    def raycast(self, intr, Rc2v, tc2v, Rv2w, tv2w, trunc, res, voxel, value, grad, rows, cols, f64=False, y0=0, y1=None):
+        a, b = cpose(Rc2v, tc2v)
+        c, d = cpose(Rv2w, tv2w)
+        r = (C.c_int * 3)(*res)
+        v = np.zeros((3, rows, cols, 2), np.float32)
+        n = np.zeros((3, rows, cols, 2), np.float32)
+        v[0, ..., 0] = np.nan
+        n[0, ..., 0] = np.nan
+        self.lib.oracle_raycast(C.c_float(intr[0]), C.c_float(intr[1]), C.c_float(intr[2]), C.c_float(intr[3]), _p(a), _p(b),
+                                _p(c), _p(d), C.c_float(trunc), r, C.c_float(voxel), _p(_f(value)), _p(_f(grad)), rows, cols,
+                                int(y0), int(rows if y1 is None else y1), _p(v), _p(n), int(f64))
+        return v, n
+
+    # ---- ICP
+    def estimate_combined(self, Rcurr, tcurr, vmap_curr, nmap_curr, Rprev_inv, tprev, intr, vmap_prev, nmap_prev, dist_thres,
+                          angle_thres, f64=False):
+        a, b = cpose(Rcurr, tcurr)
+        c, d = cpose(Rprev_inv, tprev)
+        rows, cols = vmap_curr.shape[1:3]
+        A = np.zeros((72,), np.float64)
+        bb = np.zeros((12,), np.float64)
+        self.lib.oracle_estimate_combined(_p(a), _p(b), _p(_f(vmap_curr)), _p(_f(nmap_curr)), _p(c), _p(d), C.c_float(intr[0]),
+                                          C.c_float(intr[1]), C.c_float(intr[2]), C.c_float(intr[3]), _p(_f(vmap_prev)),
+                                          _p(_f(nmap_prev)), rows, cols, C.c_float(dist_thres), C.c_float(angle_thres),
+                                          _p(A, C.c_double), _p(bb, C.c_double), int(f64))
+        A = A.reshape(6, 6, 2)
+        bb = bb.reshape(6, 2)
+        return (A[..., 0] + 1j * A[..., 1]).T.copy(), bb[:, 0] + 1j * bb[:, 1]
+
+    def pose_update(self, A, b, R, t):
+        """One Gauss-Newton update (Hermitian-LLT solve as Eigen does); returns (ok, R, t)."""
+        Ac = np.ascontiguousarray(np.stack([A.T.real, A.T.imag], -1), np.float64)  # column-major
+        bc = np.ascontiguousarray(np.stack([b.real, b.imag], -1), np.float64)
+        Rf, tf = cpose(R, t)
+        ok = self.lib.oracle_pose_update(_p(Ac, C.c_double), _p(bc, C.c_double), _p(Rf), _p(tf))
+        Rf = Rf.reshape(9, 2)
+        tf = tf.reshape(3, 2)
+        return ok, (Rf[:, 0] + 1j * Rf[:, 1]).reshape(3, 3).astype(np.complex64), (tf[:, 0] + 1j * tf[:, 1]).astype(np.complex64)
+
+    def _m(self, fn, M, n):
+        a = np.asarray(M, np.complex64).reshape(-1)
+        buf = _f(np.stack([a.real, a.imag], -1).reshape(-1))
+        out = np.zeros_like(buf)
+        fn(_p(buf), _p(out))
+        out = out.reshape(-1, 2)
+        return (out[:, 0] + 1j * out[:, 1]).reshape(n, n).astype(np.complex64)
+
+    def inverse4(self, M):
+        return self._m(self.lib.oracle_inverse4, M, 4)
+
+    def inverse3(self, M):
+        return self._m(self.lib.oracle_inverse3, M, 3)
+
+    def mul4(self, A, B):
+        a = np.asarray(A, np.complex64).reshape(-1)
+        b = np.asarray(B, np.complex64).reshape(-1)
+        fa, fb = _f(np.stack([a.real, a.imag], -1).reshape(-1)), _f(np.stack([b.real, b.imag], -1).reshape(-1))
+        out = np.zeros_like(fa)
+        self.lib.oracle_mul4(_p(fa), _p(fb), _p(out))
+        out = out.reshape(-1, 2)
+        return (out[:, 0] + 1j * out[:, 1]).reshape(4, 4).astype(np.complex64)
+
+    # ---- DoubleComplex arrays ([n, 4])
+    def dc_apply(self, op, a, b=None, p=0.0, f64=False):
+        dt = np.float64 if f64 else np.float32
+        ct = C.c_double if f64 else C.c_float
+        a = np.ascontiguousarray(a, dt)
+        out = np.zeros_like(a)
+        bp = _p(np.ascontiguousarray(b, dt), ct) if b is not None else None
+        fn = self.lib.oracle_dc_apply_f64 if f64 else self.lib.oracle_dc_apply_f32
+        rc = fn(RefCsfd.OPS[op], _p(a, ct), bp, ct(p), _p(out, ct), C.c_long(a.shape[0]))
+        assert rc == 0
+        return out
+
+    def dc_chain(self, t, h=1e-6, f64=False):
+        dt = np.float64 if f64 else np.float32
+        ct = C.c_double if f64 else C.c_float
+        t = np.ascontiguousarray(t, dt)
+        out = np.zeros((t.shape[0], 4), dt)
+        (self.lib.oracle_dc_chain_f64 if f64 else self.lib.oracle_dc_chain_f32)(_p(t, ct), ct(h), _p(out, ct), C.c_long(t.shape[0]))
+        return out
+
+
+class OracleKinfu:
+    """CPU port of the frame loop (KinectFusionReconstruction.cpp:147-332) on the oracle stages: one perturbation
+    direction per instance, as the reference.  z_slab / row_band bound the volume sweep and the raycast for the
+    timed cpu_baseline sample (the default processes everything)."""
+
+    def __init__(self, cfg, seed_imag=None, f64=False, oracle=None):
+        self.o = oracle or Oracle()
+        self.cfg = cfg
+        self.f64 = f64
+        self.W, self.H, self.L = int(cfg["depth_width"]), int(cfg["depth_height"]), int(cfg["num_levels"])
+        self.res = (int(cfg["tsdf_size_x"]), int(cfg["tsdf_size_y"]), int(cfg["tsdf_size_z"]))
+        self.voxel = float(np.float32(cfg["tsdf_voxel_size"]))
+        self.trunc = float(max(np.float32(self.voxel) * np.float32(cfg["thres_range"]), np.float32(2.1) * np.float32(self.voxel)))
+        self.intr = tuple(float(np.float32(cfg[k])) for k in ("fx", "fy", "cx", "cy"))
+        self.w2c = np.eye(4, dtype=np.complex64)
+        if seed_imag is not None:
+            self.w2c = (self.w2c + 1j * np.asarray(seed_imag, np.float32).reshape(4, 4)).astype(np.complex64)
+        self.record = [self.w2c]
+        self.w2v = np.eye(4, dtype=np.complex64)
+        self.w2v[:3, 3] = [cfg["init_x"], cfg["init_y"], cfg["init_z"]]
+        self.angle_thres = float(np.float32(np.sin(np.float32(cfg["angleThres"]) / np.float32(180.0) * np.pi)))
+        self.dist_thres = float(cfg["distThres"])
+        shape = (self.res[2], self.res[1], self.res[0])
+        self.value = np.zeros(shape, np.float32)
+        self.weight = np.zeros(shape, np.int32)
+        self.grad = np.zeros(shape, np.float32)
+        self.vprev = [None] * self.L
+        self.nprev = [None] * self.L
+        self.frame_id = 0
+        self.iters = [5, 4, 3]
+        self.icp_log = []
+
+    def level_intr(self, i):
+        d = np.float32(1 << i)
+        return tuple(float(np.float32(v) / d) for v in self.intr)
+
+    def process_frame(self, depth, z_slab=None, row_band=None):
+        o = self.o
+        # SurfaceMeasure
+        lev = [o.bilateral(depth)]
+        for i in range(1, self.L):
+            lev.append(o.pyrdown(lev[-1]))
+        vc, nc = [], []
+        for i in range(self.L):
+            v, n = o.vmap_nmap(lev[i], self.level_intr(i), self.f64)
+            vc.append(v)
+            nc.append(n)
+        # PoseEstimate
+        self.icp_log = []
+        if self.frame_id > 0:
+            c2w_prev = o.inverse4(self.record[-1])
+            Rprev, tprev = c2w_prev[:3, :3], c2w_prev[:3, 3]
+            Rprev_inv = o.inverse3(Rprev)
+            Rcurr, tcurr = Rprev.copy(), tprev.copy()
+            for level in range(self.L - 1, -1, -1):
+                for _ in range(self.iters[level]):
+                    A, b = o.estimate_combined(Rcurr, tcurr, vc[level], nc[level], Rprev_inv, tprev, self.level_intr(level),
+                                               self.vprev[level], self.nprev[level], self.dist_thres, self.angle_thres, self.f64)
+                    self.icp_log.append((A, b))
+                    ok, Rcurr, tcurr = o.pose_update(A, b, Rcurr, tcurr)
+                    if not ok:
+                        return 0
+            c2w = np.eye(4, dtype=np.complex64)
+            c2w[:3, :3], c2w[:3, 3] = Rcurr, tcurr
+            self.w2c = o.inverse4(c2w)
+            self.record.append(self.w2c)
+        # IntegrateFrame
+        c2w = o.inverse4(self.record[-1])
+        c2v = o.mul4(self.w2v, c2w)
+        v2c = o.inverse4(c2v)
+        z0, z1 = (0, self.res[2]) if z_slab is None else z_slab
+        self.updated = o.integrate(depth, self.intr, int(self.cfg["max_integration_weight"]), self.res, self.voxel, v2c[:3, :3],
+                                   v2c[:3, 3], self.trunc, self.value, self.weight, self.grad,
+                                   float(self.cfg["biInterpolate_threshold"]), self.f64, z0, z1)
+        # raycast + pyramid
+        v2w = o.inverse4(self.w2v)
+        y0, y1 = (0, self.H) if row_band is None else row_band
+        v, n = o.raycast(self.intr, c2v[:3, :3], c2v[:3, 3], v2w[:3, :3], v2w[:3, 3], self.trunc, self.res, self.voxel, self.value,
+                         self.grad, self.H, self.W, self.f64, y0, y1)
+        self.vprev[0], self.nprev[0] = v, n
+        for i in range(1, self.L):
+            self.vprev[i] = o.resize_map(self.vprev[i - 1], False, self.f64)
+            self.nprev[i] = o.resize_map(self.nprev[i - 1], True, self.f64)
+        self.frame_id += 1
+        return 1

@@ -19,7 +19,15 @@ REPORT = {}
 
 
 def _report(out_dir, key, **kw):
-    REPORT[key] = {k: (float(v) if isinstance(v, (np.floating, float)) else v) for k, v in kw.items()}
+    def conv(v):
+        if isinstance(v, (list, tuple)):
+            return [conv(x) for x in v]
+        if isinstance(v, (np.floating, float)):
+            return float(v)
+        if isinstance(v, (np.integer,)):
+            return int(v)
+        return v
+    REPORT[key] = {k: conv(v) for k, v in kw.items()}
     with open(os.path.join(out_dir, "parity_report.json"), "w") as f:
         json.dump(REPORT, f, indent=1, sort_keys=True)
     print("[parity]", key, REPORT[key])
@@ -83,8 +91,9 @@ def _integrate_both(xs, refcuda, torch, frames, res, voxel, ncomp, seed, thresho
     intr = xs.Intr(**ICL)
     vol = ops.TsdfVolume((res,) * 3, voxel, 3.0, comps=1, dirs=ncomp)
     trunc = vol.getTsdfTruncDist()
+    # ncomp seeded reference passes + one zero-seed pass (index ncomp): the canonical real part
     ref_state = [(np.zeros((res,) * 3, np.float32), np.zeros((res,) * 3, np.int32), np.zeros((res,) * 3, np.float32))
-                 for _ in range(ncomp)]
+                 for _ in range(ncomp + 1)]
     ref_ms, upd = [], []
     for f in frames:
         depth = xs.synth_depth(f)
@@ -93,9 +102,9 @@ def _integrate_both(xs, refcuda, torch, frames, res, voxel, ncomp, seed, thresho
         t = v2c[:3, 3].astype(np.float32)
         dR, dt = rand_dpose(rng, ncomp)
         upd.append(ops.integrateTsdfVolume(_dev_u16(torch, depth), intr, 100, vol, ops.PoseBatch(R, t, dR, dt), threshold))
-        for q in range(ncomp):
-            Rc = R.reshape(9) + 1j * dR[q]
-            tc = t + 1j * dt[q]
+        for q in range(ncomp + 1):
+            Rc = R.reshape(9) + 1j * (dR[q] if q < ncomp else 0)
+            tc = t + 1j * (dt[q] if q < ncomp else 0)
             v, w, g = ref_state[q]
             ref_ms.append(refcuda.integrate(depth, (ICL["fx"], ICL["fy"], ICL["cx"], ICL["cy"]), 100, (res,) * 3, voxel,
                                             Rc, tc, trunc, v, w, g, threshold))
@@ -110,25 +119,31 @@ def test_integration_parity(xs, refcuda, torch_mod, out_dir, threshold):
     vol, ref_state, upd, ref_ms = _integrate_both(xs, refcuda, torch, [0, 6, 12], res, voxel, ncomp, 1, threshold)
     w = vol.weight().cpu().numpy()
     v = vol.value().cpu().numpy()
-    # weights (integer, decide which voxels were updated in which frame) must agree with every reference pass
-    wm = [int((w != ref_state[q][1]).sum()) for q in range(ncomp)]
-    vm_ulp = ulp_diff(v, ref_state[0][0])
-    n_upd = int((ref_state[0][1] > 0).sum())
-    stats = dict(updated_voxels=n_upd, weight_mismatch=wm, value_max_ulp=int(vm_ulp.max()),
-                 value_ulp_gt0=int((vm_ulp > 0).sum()), value_rel=rel_err(v, ref_state[0][0]), upd_counts=upd,
-                 ref_kernel_ms=float(np.mean(ref_ms)))
-    gerr = []
+    zv, zw, _ = ref_state[ncomp]
+    n_upd = int((zw > 0).sum())
+    vm_ulp = ulp_diff(v, zv)
+    stats = dict(updated_voxels=n_upd, weight_mismatch=int((w != zw).sum()), value_max_ulp=int(vm_ulp.max()),
+                 value_ulp_gt0=int((vm_ulp > 0).sum()), upd_counts=upd, ref_kernel_ms=float(np.mean(ref_ms)),
+                 ref_seeded_vs_zero_value_ulp_gt0=[int((ulp_diff(ref_state[q][0], zv) > 0).sum()) for q in range(ncomp)])
+    gmax, gp999 = [], []
     for q in range(ncomp):
         g = vol.grad(q).cpu().numpy()
-        gerr.append(rel_err(g, ref_state[q][2]))
-        assert np.array_equal(g != 0, ref_state[q][2] != 0) or rel_err((g != 0) * 1.0, (ref_state[q][2] != 0) * 1.0) < 1e-3
-    stats["grad_rel"] = gerr
+        rv, rw, rg = ref_state[q]
+        # voxels where the seeded reference pass itself reproduces its zero-seed real part (elsewhere its own
+        # branch decisions flipped, e.g. the update gate or the saturation test)
+        stable = (rw == zw) & (ulp_diff(rv, zv) <= 64) & (zw > 0)
+        d = np.abs(g - rg)[stable]
+        sc = np.abs(rg[stable]).max()
+        gmax.append(float(d.max() / sc))
+        gp999.append(float(np.percentile(d, 99.9) / sc))
+    stats["grad_max_rel"], stats["grad_p99.9_rel"] = gmax, gp999
     _report(out_dir, "integrate_thr%g" % threshold, **stats)
-    assert n_upd > 100000
-    assert max(wm) == 0, "updated-voxel sets differ from the reference"
-    assert stats["value_rel"] <= 1e-6
-    # FP32 forward-mode derivative vs the reference's FP32 complex arithmetic, scale-relative
-    assert max(gerr) <= 2e-5
+    assert n_upd > 30000
+    # integer decisions (which voxels are updated in which frame) and the FP32 real part: bit-exact
+    assert stats["weight_mismatch"] == 0, "updated-voxel sets differ from the zero-seed reference"
+    assert stats["value_max_ulp"] == 0, "TSDF real part is not bit-exact"
+    # FP32 forward-mode derivative vs the reference's FP32 complex arithmetic, relative to the plane's scale
+    assert max(gp999) <= 1e-5 and max(gmax) <= 2e-3
 
 
 def test_raycast_parity(xs, refcuda, torch_mod, out_dir):
@@ -152,26 +167,34 @@ def test_raycast_parity(xs, refcuda, torch_mod, out_dir):
     vm, nm = vm.cpu().numpy(), nm.cpu().numpy()
     stats = {}
     ms = []
+    tr = vol.getTsdfTruncDist()
+    zv, zn, _ = refcuda.raycast((ICL["fx"], ICL["fy"], ICL["cx"], ICL["cy"]), Rc.reshape(9) + 0j, tc + 0j, Rw.reshape(9) + 0j,
+                                tw + 0j, tr, (res,) * 3, voxel, ref_state[0][0], np.zeros_like(ref_state[0][0]), 480, 640)
+    for name, m, r in (("v", vm, zv), ("n", nm, zn)):
+        valid = ~np.isnan(r[0, ..., 0])
+        stats["%s_valid" % name] = int(valid.sum())
+        stats["%s_mask_mismatch" % name] = int((np.isnan(m[0, 0]) != ~valid).sum())
+        both = valid & ~np.isnan(m[0, 0])
+        stats["%s_real_max_ulp" % name] = int(max(ulp_diff(m[0, p][both], r[p, ..., 0][both]).max() for p in range(3)))
     for q in range(ncomp):
         rv, rn, t = refcuda.raycast((ICL["fx"], ICL["fy"], ICL["cx"], ICL["cy"]), Rc.reshape(9) + 1j * dRc[q], tc + 1j * dtc[q],
-                                    Rw.reshape(9) + 1j * dRw[q], tw + 1j * dtw[q], vol.getTsdfTruncDist(), (res,) * 3, voxel,
+                                    Rw.reshape(9) + 1j * dRw[q], tw + 1j * dtw[q], tr, (res,) * 3, voxel,
                                     ref_state[0][0], ref_state[q][2], 480, 640)
         ms.append(t)
-        for name, m, r in (("v", vm, rv), ("n", nm, rn)):
-            valid = ~np.isnan(r[0, ..., 0])
-            mism = int((np.isnan(m[0, 0]) != ~valid).sum())
-            stats["%s_mask_mismatch_d%d" % (name, q)] = mism
-            both = valid & ~np.isnan(m[0, 0])
-            stats["%s_real_rel_d%d" % (name, q)] = max(rel_err(m[0, p][both], r[p, ..., 0][both]) for p in range(3))
-            stats["%s_deriv_rel_d%d" % (name, q)] = max(rel_err(m[1 + q, p][both], r[p, ..., 1][both]) for p in range(3))
-            stats["%s_valid" % name] = int(valid.sum())
+        for name, m, r, z in (("v", vm, rv, zv), ("n", nm, rn, zn)):
+            both = ~np.isnan(r[0, ..., 0]) & ~np.isnan(m[0, 0]) & ~np.isnan(z[0, ..., 0])
+            d = np.max([np.abs(m[1 + q, p] - r[p, ..., 1]) for p in range(3)], 0)[both]
+            sc = np.abs(r[..., 1][:, both]).max()
+            stats["%s_deriv_max_rel_d%d" % (name, q)] = float(d.max() / sc)
+            stats["%s_deriv_p99.9_rel_d%d" % (name, q)] = float(np.percentile(d, 99.9) / sc)
     stats["ref_kernel_ms"] = float(np.mean(ms))
     _report(out_dir, "raycast", **stats)
     assert stats["v_valid"] > 100000
+    assert stats["v_mask_mismatch"] == 0 and stats["n_mask_mismatch"] == 0, "hit / normal validity masks differ"
+    assert stats["v_real_max_ulp"] == 0 and stats["n_real_max_ulp"] == 0, "raycast real maps are not bit-exact"
     for q in range(ncomp):
-        assert stats["v_mask_mismatch_d%d" % q] == 0 and stats["n_mask_mismatch_d%d" % q] == 0
-        assert stats["v_real_rel_d%d" % q] <= 1e-6 and stats["n_real_rel_d%d" % q] <= 2e-6
-        assert stats["v_deriv_rel_d%d" % q] <= 1e-4 and stats["n_deriv_rel_d%d" % q] <= 1e-3
+        assert stats["v_deriv_p99.9_rel_d%d" % q] <= 1e-5 and stats["n_deriv_p99.9_rel_d%d" % q] <= 1e-5
+        assert stats["v_deriv_max_rel_d%d" % q] <= 1e-3 and stats["n_deriv_max_rel_d%d" % q] <= 1e-3
 
 
 def _complex_map(m, q):

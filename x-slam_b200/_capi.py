@@ -56,6 +56,7 @@ SYMBOLS = {
     "xs_volume_reset": (_i, [_vp, _vp]),
     "xs_volume_trunc_dist": (_f, [_vp]),
     "xs_volume_bytes": (_sz, [_vp]),
+    "xs_volume_last_integrate_ms": (_f, [_vp]),
     "xs_volume_export_planes": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "xs_volume_import_planes": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "xs_integrate": (_i, [_vp, _vp, _sz, _i, _i, Intr, _i, _PP, _f, _pull, _vp]),

@@ -284,6 +284,10 @@ xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_rang
     if (e == cudaSuccess) e = cudaMallocHost(&v->h_dpose, pose_floats * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&v->d_stats, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&v->h_stats, 4 * sizeof(unsigned long long));
+    v->ev_k0 = v->ev_k1 = nullptr;
+    v->last_kernel_ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventCreate(&v->ev_k0);
+    if (e == cudaSuccess) e = cudaEventCreate(&v->ev_k1);
     v->d_depth_m = nullptr;
     v->depth_capacity = 0;
     if (e != cudaSuccess) {
@@ -308,6 +312,8 @@ void xs_volume_destroy(xs_volume *v) {
     cudaFree(v->d_depth_m);
     cudaFree(v->d_stats);
     cudaFreeHost(v->h_stats);
+    if (v->ev_k0) cudaEventDestroy(v->ev_k0);
+    if (v->ev_k1) cudaEventDestroy(v->ev_k1);
     delete v;
 }
 
@@ -323,6 +329,7 @@ int xs_volume_reset(xs_volume *v, void *stream) {
 
 float xs_volume_trunc_dist(const xs_volume *v) { return v ? v->view.trunc : 0.f; }
 size_t xs_volume_bytes(const xs_volume *v) { return v ? v->bytes : 0; }
+float xs_volume_last_integrate_ms(const xs_volume *v) { return v ? v->last_kernel_ms : 0.f; }
 
 int xs_volume_export_planes(const xs_volume *v, int comp, float *d_value, int *d_weight, float *d_grad, void *stream) {
     if (!v || (d_grad && (comp < 0 || comp >= v->view.ncomp))) return XS_ERR_ARG;
@@ -396,13 +403,16 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
     XS_CUDA(cudaMemsetAsync(v->d_stats, 0, 4 * sizeof(unsigned long long), s));
     int grid = P.nbricks < 148 * 16 ? P.nbricks : 148 * 16;
     size_t smem = (size_t) (v->view.ncomp > 0 ? v->view.ncomp : 1) * 12 * sizeof(float);
+    XS_CUDA(cudaEventRecord(v->ev_k0, s));
     if (v->comps == 1)
         integrate_kernel<1><<<grid, 512, smem, s>>>(P);
     else
         integrate_kernel<3><<<grid, 512, smem, s>>>(P);
     XS_LAUNCH_CHECK();
+    XS_CUDA(cudaEventRecord(v->ev_k1, s));
     XS_CUDA(cudaMemcpyAsync(v->h_stats, v->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     XS_CUDA(cudaStreamSynchronize(s));  // integrateTsdfVolume syncs, TsdfFusion.cu:200
     if (stats_host) stats_host[0] = v->h_stats[0];
+    cudaEventElapsedTime(&v->last_kernel_ms, v->ev_k0, v->ev_k1);
     return XS_OK;
 }

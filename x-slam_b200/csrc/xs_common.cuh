@@ -71,4 +71,6 @@ struct xs_volume {
     unsigned long long *d_stats;
     unsigned long long *h_stats;
     size_t bytes;
+    cudaEvent_t ev_k0, ev_k1;  // bracket the integration kernel (roofline timing)
+    float last_kernel_ms;
 };
