@@ -171,7 +171,7 @@ def run_ours(args, xs, rank, world, local_rank):
     lib = xs.load()
     max_dirs = (args.dirs + world - 1) // world
     rec_len = (1 + max_dirs * args.comps) * 16
-    gather_out = torch.zeros((world, rec_len), dtype=torch.float32, device="cuda") if world > 1 else None
+    gather_out = torch.zeros((world * rec_len,), dtype=torch.float32, device="cuda") if world > 1 else None
     send = torch.zeros((rec_len,), dtype=torch.float32, device="cuda") if world > 1 else None
     rec_view = torch.as_tensor(DeviceRecord(k.pose_record_device_ptr(), (1 + len(mine) * args.comps) * 16), device="cuda")
 
