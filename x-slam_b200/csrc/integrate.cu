@@ -56,7 +56,9 @@ template <int C, int K>
 XS_DEV bool eval_voxel(const IntegrateParams &P, float vcx, float vcy, float vcz, Jet<C, K> &sdf) {
     typedef Jet<C, K> J;
     J X = jconst<C, K>(vcx), Y = jconst<C, K>(vcy), Z = jconst<C, K>(vcz);
-    if (C == 1) {
+    if (K == 0) {
+        // real-only evaluation (decisions and the real sdf): no seeds
+    } else if (C == 1) {
         X.d[0] = 1.f;
         Y.d[1] = 1.f;
         Z.d[2] = 1.f;
@@ -161,8 +163,10 @@ template <int C> __global__ void __launch_bounds__(512) integrate_kernel(const I
         const float vcx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], vgx), __fmul_rn(R[1], vgy)), __fmul_rn(R[2], vgz)), t[0]);
         const float vcy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3], vgx), __fmul_rn(R[4], vgy)), __fmul_rn(R[5], vgz)), t[1]);
         const float vcz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[6], vgx), __fmul_rn(R[7], vgy)), __fmul_rn(R[8], vgz)), t[2]);
-        Jet<C, K> sdf;
-        const bool upd = eval_voxel<C, K>(P, vcx, vcy, vcz, sdf);
+        // real pass first: most voxels in view are skipped (behind the surface) or saturated (free space, tsdf = 1,
+        // zero derivative); only voxels inside the truncation band pay for the Jacobian / Hessian jets below.
+        Jet<1, 0> sdf;
+        const bool upd = eval_voxel<1, 0>(P, vcx, vcy, vcz, sdf);
         if (!upd) continue;  // no barrier inside the brick loop: threads are independent
         ++n_upd;
         // ---- TsdfFusion.cu:152-167
@@ -177,10 +181,16 @@ template <int C> __global__ void __launch_bounds__(512) integrate_kernel(const I
         // ---- derivative components
         const float inv_w1 = __fdiv_rn(1.f, wf1);
         const float a_keep = wf * inv_w1;
-        const float sc = saturated ? 0.f : P.trunc_inv * inv_w1;
         float *dp = P.V.deriv + (size_t) b * ncomp * BRICK_VOX + tid;
+        if (saturated) {  // tsdf = (1, 0): F_q <- F_q * w / (w + 1)
+            for (int q = 0; q < ncomp; ++q) dp[(size_t) q * BRICK_VOX] *= a_keep;
+            continue;
+        }
+        const float sc = P.trunc_inv * inv_w1;
+        Jet<C, K> sdfj;
+        eval_voxel<C, K>(P, vcx, vcy, vcz, sdfj);
         if (C == 1) {
-            const float J0 = sdf.d[0] * sc, J1 = sdf.d[1] * sc, J2 = sdf.d[2] * sc;
+            const float J0 = sdfj.d[0] * sc, J1 = sdfj.d[1] * sc, J2 = sdfj.d[2] * sc;
 #pragma unroll 4
             for (int q = 0; q < ncomp; ++q) {
                 const float *m = s_dpose + q * 12;
@@ -192,9 +202,9 @@ template <int C> __global__ void __launch_bounds__(512) integrate_kernel(const I
             }
         } else {
             // gradient from the diagonal pairs, Hessian from eps1eps2 of each pair
-            const float J0 = sdf.d[0] * sc, J1 = sdf.d[9] * sc, J2 = sdf.d[15] * sc;
-            const float H00 = sdf.d[2] * sc, H01 = sdf.d[5] * sc, H02 = sdf.d[8] * sc, H11 = sdf.d[11] * sc,
-                        H12 = sdf.d[14] * sc, H22 = sdf.d[17] * sc;
+            const float J0 = sdfj.d[0] * sc, J1 = sdfj.d[9] * sc, J2 = sdfj.d[15] * sc;
+            const float H00 = sdfj.d[2] * sc, H01 = sdfj.d[5] * sc, H02 = sdfj.d[8] * sc, H11 = sdfj.d[11] * sc,
+                        H12 = sdfj.d[14] * sc, H22 = sdfj.d[17] * sc;
             const int dirs = ncomp / 3;
 #pragma unroll 2
             for (int k = 0; k < dirs; ++k) {
@@ -290,6 +300,8 @@ xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_rang
     if (e == cudaSuccess) e = cudaEventCreate(&v->ev_k1);
     v->d_depth_m = nullptr;
     v->depth_capacity = 0;
+    v->d_hit_time = nullptr;
+    v->hit_capacity = 0;
     if (e != cudaSuccess) {
         set_error(std::string("xs_volume_create: ") + cudaGetErrorString(e));
         xs_volume_destroy(v);
@@ -310,6 +322,7 @@ void xs_volume_destroy(xs_volume *v) {
     cudaFree(v->d_dpose);
     cudaFreeHost(v->h_dpose);
     cudaFree(v->d_depth_m);
+    cudaFree(v->d_hit_time);
     cudaFree(v->d_stats);
     cudaFreeHost(v->h_stats);
     if (v->ev_k0) cudaEventDestroy(v->ev_k0);

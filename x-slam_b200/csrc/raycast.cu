@@ -103,11 +103,19 @@ XS_DEV void store3(float *map, int comp, int rows, int cols, int y, int x, float
     p[2 * plane] = c;
 }
 
+// Result of one hit evaluation for direction tile [k0,k0+K): world-frame vertex / normal with their derivative
+// components, and which of the two the reference would have written (RayCaster.cu:268-271,297-303).
+template <int C, int K> struct HitOut {
+    Jet3<C, K> vw, ng;
+    bool v_ok, n_ok;
+};
+
 // Hit evaluation for direction tile [k0,k0+K), RayCaster.cu:249-305.
 template <int C, int K>
-XS_DEV void eval_hit(const RaycastParams &P, int x, int y, float time_curr, int k0) {
+XS_DEV void eval_hit(const RaycastParams &P, int x, int y, float time_curr, int k0, HitOut<C, K> &out) {
     typedef Jet<C, K> J;
     const VolumeView &V = P.V;
+    out.v_ok = out.n_ok = false;
     Jet3<C, K> start, dir;
     ray_setup<C, K>(P, x, y, k0, start, dir);
     const float t1 = __fadd_rn(time_curr, P.time_step);
@@ -126,11 +134,8 @@ XS_DEV void eval_hit(const RaycastParams &P, int x, int y, float time_curr, int 
     for (int i = 0; i < J::N; ++i) Ts.d[i] = -P.time_step * coef.d[i];
     const Jet3<C, K> vertex = {start.x + dir.x * Ts, start.y + dir.y * Ts, start.z + dir.z * Ts};
     const JetPose<C, K> v2w = load_pose<C, K>(P.v2w, P.dpose_v2w, k0, P.dirs);
-    const Jet3<C, K> vw = jrot(v2w, vertex) + v2w.t;
-    if (k0 == 0) store3(P.vmap, 0, P.rows, P.cols, y, x, vw.x.v, vw.y.v, vw.z.v);
-#pragma unroll
-    for (int i = 0; i < J::N; ++i)
-        if (k0 * C + i < V.ncomp) store3(P.vmap, 1 + k0 * C + i, P.rows, P.cols, y, x, vw.x.d[i], vw.y.d[i], vw.z.d[i]);
+    out.vw = jrot(v2w, vertex) + v2w.t;
+    out.v_ok = true;
 
     const float vs = V.voxel;
     const int gx = __float2int_rd(__fdiv_rn(vertex.x.v, vs));
@@ -161,27 +166,20 @@ XS_DEV void eval_hit(const RaycastParams &P, int x, int y, float time_curr, int 
     n.z = F1 - F2;
     if (!ok) return;  // cannot happen for g in (1, N-2); the reference would propagate NaN
     if (jdot(n, n).v == 0.f) return;
-    const Jet3<C, K> ng = jrot(v2w, jnormalized(n));
-    if (k0 == 0) store3(P.nmap, 0, P.rows, P.cols, y, x, ng.x.v, ng.y.v, ng.z.v);
-#pragma unroll
-    for (int i = 0; i < J::N; ++i)
-        if (k0 * C + i < V.ncomp) store3(P.nmap, 1 + k0 * C + i, P.rows, P.cols, y, x, ng.x.d[i], ng.y.d[i], ng.z.d[i]);
+    out.ng = jrot(v2w, jnormalized(n));
+    out.n_ok = true;
 }
 
-template <int C, int K> __global__ void __launch_bounds__(256) raycast_kernel(const RaycastParams P) {
+// ---- pass 1: the real march, RayCaster.cu:222-247.  One thread per pixel on the value plane only; the result
+// (time of the sample before the + -> - crossing, or a negative number) is shared by every direction.
+// The loop reads LOOKAHEAD samples ahead of the exit tests (sample positions do not depend on loaded values), which
+// turns a chain of dependent L2/HBM round trips into batches; the exit tests are still applied in order.
+constexpr int MARCH_LOOKAHEAD = 4;
+__global__ void __launch_bounds__(256) raycast_march_kernel(const RaycastParams P, float *__restrict__ hit_time) {
     const int x = threadIdx.x + blockIdx.x * 32;
     const int y = threadIdx.y + blockIdx.y * 8;
     if (x >= P.cols || y >= P.rows) return;
     const VolumeView &V = P.V;
-    // RayCaster.cu:204-205 writes NaN to the x planes; the remaining planes are made deterministic (0)
-    const float qnan = __int_as_float(0x7fffffff);
-    store3(P.vmap, 0, P.rows, P.cols, y, x, qnan, 0.f, 0.f);
-    store3(P.nmap, 0, P.rows, P.cols, y, x, qnan, 0.f, 0.f);
-    for (int q = 0; q < V.ncomp; ++q) {
-        store3(P.vmap, 1 + q, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
-        store3(P.nmap, 1 + q, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
-    }
-    // ---- real march, RayCaster.cu:222-247
     Jet3<1, 0> s0, d0;
     ray_setup<1, 0>(P, x, y, 0, s0, d0);
     const float sx = s0.x.v, sy = s0.y.v, sz = s0.z.v, dx = d0.x.v, dy = d0.y.v, dz = d0.z.v;
@@ -195,24 +193,85 @@ template <int C, int K> __global__ void __launch_bounds__(256) raycast_kernel(co
     gy = max(0, min(gy, V.ry - 1));
     gz = max(0, min(gz, V.rz - 1));
     float tsdf = read_value(V, gx, gy, gz);
-    bool hit = false;
-    for (; time_curr < max_time; time_curr = __fadd_rn(time_curr, P.time_step)) {
-        const float tsdf_prev = tsdf;
-        const float tt = __fadd_rn(time_curr, P.time_step);
-        gx = __float2int_rd(__fdiv_rn(__fmaf_rn(dx, tt, sx), vs));
-        gy = __float2int_rd(__fdiv_rn(__fmaf_rn(dy, tt, sy), vs));
-        gz = __float2int_rd(__fdiv_rn(__fmaf_rn(dz, tt, sz), vs));
-        if (!(gx >= 0 && gy >= 0 && gz >= 0 && gx < V.rx && gy < V.ry && gz < V.rz)) break;
-        tsdf = read_value(V, gx, gy, gz);
-        if (tsdf_prev < 0.f && tsdf > 0.f) break;
-        if (tsdf_prev > 0.f && tsdf < 0.f) {
-            hit = true;
-            break;
+    float result = -1.f;
+    bool done = false;
+    while (!done && time_curr < max_time) {
+        float tc[MARCH_LOOKAHEAD], val[MARCH_LOOKAHEAD];
+        bool inside[MARCH_LOOKAHEAD];
+        float t = time_curr;
+#pragma unroll
+        for (int i = 0; i < MARCH_LOOKAHEAD; ++i) {
+            tc[i] = t;
+            const float tt = __fadd_rn(t, P.time_step);
+            const int ix = __float2int_rd(__fdiv_rn(__fmaf_rn(dx, tt, sx), vs));
+            const int iy = __float2int_rd(__fdiv_rn(__fmaf_rn(dy, tt, sy), vs));
+            const int iz = __float2int_rd(__fdiv_rn(__fmaf_rn(dz, tt, sz), vs));
+            inside[i] = (ix >= 0 && iy >= 0 && iz >= 0 && ix < V.rx && iy < V.ry && iz < V.rz);
+            val[i] = inside[i] ? read_value(V, ix, iy, iz) : 0.f;
+            t = tt;  // time_curr += time_step (:236)
+        }
+#pragma unroll
+        for (int i = 0; i < MARCH_LOOKAHEAD; ++i) {
+            if (done) break;
+            if (!(tc[i] < max_time) || !inside[i]) {
+                done = true;
+                break;
+            }
+            const float tsdf_prev = tsdf;
+            tsdf = val[i];
+            if (tsdf_prev < 0.f && tsdf > 0.f) {
+                done = true;
+                break;
+            }
+            if (tsdf_prev > 0.f && tsdf < 0.f) {
+                result = tc[i];
+                done = true;
+                break;
+            }
+        }
+        time_curr = t;
+    }
+    hit_time[(size_t) y * P.cols + x] = result;
+}
+
+// ---- pass 2: hit evaluation, one thread per (pixel, direction tile).  A CTA is 32 consecutive pixels of a row x
+// 8 direction tiles, so the 8 warps share the real value samples of the same pixels through L1 while each reads its
+// own derivative planes.  Every output element is written exactly once (values, or the NaN / 0 fill of :204-205).
+template <int C, int K> __global__ void __launch_bounds__(256) raycast_hit_kernel(const RaycastParams P, const float *__restrict__ hit_time) {
+    const int x = threadIdx.x + blockIdx.x * 32;
+    const int y = blockIdx.y;
+    const int tile = threadIdx.y + blockIdx.z * 8;
+    const int tiles = P.dirs > 0 ? (P.dirs + K - 1) / K : 1;
+    if (x >= P.cols || tile >= tiles) return;
+    const int k0 = tile * K;
+    HitOut<C, K> o;
+    o.v_ok = o.n_ok = false;
+    const float time_curr = hit_time[(size_t) y * P.cols + x];
+    if (time_curr >= 0.f) eval_hit<C, K>(P, x, y, time_curr, k0, o);
+    const float qnan = __int_as_float(0x7fffffff);
+    if (k0 == 0) {
+        if (o.v_ok)
+            store3(P.vmap, 0, P.rows, P.cols, y, x, o.vw.x.v, o.vw.y.v, o.vw.z.v);
+        else
+            store3(P.vmap, 0, P.rows, P.cols, y, x, qnan, 0.f, 0.f);
+        if (o.n_ok)
+            store3(P.nmap, 0, P.rows, P.cols, y, x, o.ng.x.v, o.ng.y.v, o.ng.z.v);
+        else
+            store3(P.nmap, 0, P.rows, P.cols, y, x, qnan, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < Jet<C, K>::N; ++i) {
+        if (k0 * C + i < P.V.ncomp) {
+            if (o.v_ok)
+                store3(P.vmap, 1 + k0 * C + i, P.rows, P.cols, y, x, o.vw.x.d[i], o.vw.y.d[i], o.vw.z.d[i]);
+            else
+                store3(P.vmap, 1 + k0 * C + i, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
+            if (o.n_ok)
+                store3(P.nmap, 1 + k0 * C + i, P.rows, P.cols, y, x, o.ng.x.d[i], o.ng.y.d[i], o.ng.z.d[i]);
+            else
+                store3(P.nmap, 1 + k0 * C + i, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
         }
     }
-    if (!hit) return;
-    const int tiles = P.dirs > 0 ? (P.dirs + K - 1) / K : 1;
-    for (int tile = 0; tile < tiles; ++tile) eval_hit<C, K>(P, x, y, time_curr, tile * K);
 }
 
 // resizeMapKernel, Map.cu:105-152, for packed-SoA maps with derivative components.
@@ -311,11 +370,27 @@ int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_po
     P.time_step = v->view.trunc * 0.8f;  // RayCaster.cu:350
     P.vmap = d_vmap;
     P.nmap = d_nmap;
+    if (v->hit_capacity < rows * cols) {
+        cudaFree(v->d_hit_time);
+        xs_volume *vm = const_cast<xs_volume *>(v);
+        vm->d_hit_time = nullptr;
+        XS_CUDA(cudaMalloc(&vm->d_hit_time, (size_t) rows * cols * sizeof(float)));
+        vm->hit_capacity = rows * cols;
+    }
     dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
-    if (v->comps == 1)
-        raycast_kernel<1, 6><<<grd, blk, 0, s>>>(P);
-    else
-        raycast_kernel<3, 2><<<grd, blk, 0, s>>>(P);
+    raycast_march_kernel<<<grd, blk, 0, s>>>(P, v->d_hit_time);
+    XS_LAUNCH_CHECK();
+    if (v->comps == 1) {
+        constexpr int K = 3;
+        const int tiles = v->dirs > 0 ? div_up(v->dirs, K) : 1;
+        dim3 g2(div_up(cols, 32), rows, div_up(tiles, 8));
+        raycast_hit_kernel<1, K><<<g2, blk, 0, s>>>(P, v->d_hit_time);
+    } else {
+        constexpr int K = 1;
+        const int tiles = v->dirs > 0 ? div_up(v->dirs, K) : 1;
+        dim3 g2(div_up(cols, 32), rows, div_up(tiles, 8));
+        raycast_hit_kernel<3, K><<<g2, blk, 0, s>>>(P, v->d_hit_time);
+    }
     XS_LAUNCH_CHECK();
     return XS_OK;  // raycast does not sync, RayCaster.cu:367
 }
