@@ -3,33 +3,25 @@
 // Replaces Combined::{search_newton, operator()} / combinedKernel (XKinectFusion/src/ICP.cu:166-281,357),
 // TranformReduction / TransformEstimatorKernel (ICP.cu:120-164) and estimateCombined (ICP.cu:365-429).
 //
-// Data association (projection, bounds, NaN, distance and angle gates) is evaluated once per pixel on
-// real parts; the 7-vector row [cross(s,n), n, n.(d-s)] is then formed per direction tile as Jet<C,K>
-// numbers and its 27 upper-triangular products are widened to double exactly as the reference does
-// (product in float, sum in double, ICP.cu:273-274).  Instead of the reference's 27 sequential
-// 256-thread shared-memory tree reductions plus a second kernel, each warp reduces a 32-wide vector of
-// sums with a 31-shuffle transpose reduction, warps are combined in a fixed order, per-block partials go
-// to global memory and the last block to finish (ticket) adds them in block order: one launch per
-// iteration, deterministic summation order.
+// Three launches per Gauss-Newton iteration (the reference: 2 launches per direction and iteration):
+//   1. icp_assoc_kernel   data association (projection, bounds, NaN, distance and angle gates) ONCE per pixel on real
+//                         parts, the real 7-vector row [cross(s,n), n, n.(d-s)], its 27 upper-triangular products
+//                         widened to double exactly as the reference does (product in float, sum in double,
+//                         ICP.cu:273-274), and a per-pixel association record (matched index + the 16 real numbers
+//                         every direction needs) that stays L2-resident (68 B/pixel).
+//   2. icp_deriv_kernel   one CTA per (pixel chunk, direction group): reads the record, gathers that direction's
+//                         derivative planes of the previous maps at the matched pixel and accumulates the derivative
+//                         components of the 27 products (linearised row algebra, no recomputation of the real path).
+//                         A thread sums at most 16 pixels in FP32, then everything is reduced in double: warp
+//                         transpose-reduction by shuffles, fixed-order combination of warps, per-CTA partials.
+//   3. icp_finish_kernel  fixed-order sum of the per-CTA partials.
+// Instead of the reference's 27 sequential 256-thread shared-memory tree reductions per direction, the summation
+// order is fixed by construction, so results are deterministic run to run.
 #include "xs_common.cuh"
 
 #include <utility>
 
 namespace xs {
-
-struct IcpParams {
-    DevPose curr, prev;  // prev.R = Rprev_inv, prev.t = tprev
-    const float *dpose_curr, *dpose_prev;
-    const float *vmap_curr, *nmap_curr;  // [3][rows][cols]
-    const float *vmap_prev, *nmap_prev;  // [(1+ncomp)][3][rows][cols]
-    xs_intr intr;
-    int rows, cols, dirs, ncomp;
-    float dist_thres, angle_thres;
-    double *partials;  // [gridDim.x][27*(1+ncomp)]
-    double *sums;      // [27*(1+ncomp)]
-    unsigned int *ticket;
-    int tiles_x, tiles_y;
-};
 
 // upper-triangular product order of ICP.cu:267-279: e -> (i, j), i = 0..5, j = i..6 (j == 6 is b).
 // constexpr so that the fully unrolled product loops index the row registers statically.
@@ -68,48 +60,53 @@ XS_DEV double warp_transpose_reduce(double (&v)[32]) {
     return v[0];
 }
 
-template <int C, int K> struct Row7 {
-    Jet<C, K> r[7];
+// real products row_i * row_j for e = 0..26 with compile-time row indices (fold over E)
+template <int... E> XS_DEV void fill_real(double (&v)[32], const float (&r)[7], std::integer_sequence<int, E...>) {
+    ((v[E] = (double) __fmul_rn(r[tri_i(E)], r[tri_j(E)])), ...);
+}
+
+// per-pixel association record, SoA planes of npix elements each
+constexpr int REC_F = 16;  // vc(3) s(3) n(3) e=d-s(3) cr=cross(s,n)(3) r6
+struct IcpParams {
+    DevPose curr, prev;  // prev.R = Rprev_inv, prev.t = tprev
+    const float *dpose_curr;              // [ncomp][12]
+    const float *vmap_curr, *nmap_curr;   // [3][rows][cols]
+    const float *vmap_prev, *nmap_prev;   // [(1+ncomp)][3][rows][cols]
+    xs_intr intr;
+    int rows, cols, dirs, ncomp;
+    float dist_thres, angle_thres;
+    int *rec_idx;      // [npix] matched linear index in the previous maps, -1 = no correspondence
+    float *rec_f;      // [REC_F][npix]
+    double *partials;  // real: [gridDim.x][27]
+    double *sums;      // [27*(1+ncomp)]
+    unsigned int *ticket;
+    int tiles_x, tiles_y;
+    // derivative pass
+    double *dpartials;  // [chunks][groups][81]
+    int chunks, groups, ppt;
 };
 
-// products row_i * row_j for e = 0..26 with compile-time row indices (fold over E)
-template <int C, int K, int... E>
-XS_DEV void fill_real(double (&v)[32], const Row7<C, K> &row, std::integer_sequence<int, E...>) {
-    ((v[E] = (double) __fmul_rn(row.r[tri_i(E)].v, row.r[tri_j(E)].v)), ...);
-}
-template <int C, int K> XS_DEV float prod_deriv(const Jet<C, K> &a, const Jet<C, K> &b, int i) {
-    if (C == 1 || (i % 3) != 2) return fmaf(a.v, b.d[i], a.d[i] * b.v);
-    // eps1eps2 of direction i/3
-    return fmaf(a.v, b.d[i], fmaf(a.d[i], b.v, fmaf(a.d[i - 2], b.d[i - 1], a.d[i - 1] * b.d[i - 2])));
-}
-template <int C, int K, int... E>
-XS_DEV void fill_deriv(double (&v)[32], const Row7<C, K> &row, int i, std::integer_sequence<int, E...>) {
-    ((v[E] = (double) prod_deriv<C, K>(row.r[tri_i(E)], row.r[tri_j(E)], i)), ...);
-}
-
-template <int C, int K> __global__ void __launch_bounds__(256) icp_kernel(const IcpParams P) {
-    constexpr int N = C * K;
-    extern __shared__ double s_mem[];
-    const int nvals = 27 * (1 + P.ncomp);
-    double *s_acc = s_mem;            // [nvals]
-    double *s_stage = s_mem + nvals;  // [8 warps][1+N][32]
+// ---------------------------------------------------------------------------------------------------------------
+// pass 1: association + real normal equations
+__global__ void __launch_bounds__(256) icp_assoc_kernel(const IcpParams P) {
+    __shared__ double s_acc[27];
+    __shared__ double s_stage[8][32];
     const int tid = threadIdx.y * 32 + threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < nvals; i += 256) s_acc[i] = 0.0;
+    if (tid < 27) s_acc[tid] = 0.0;
     __syncthreads();
-
     const size_t plane = (size_t) P.rows * P.cols;
     const int ntiles = P.tiles_x * P.tiles_y;
-    const int dtiles = P.dirs > 0 ? (P.dirs + K - 1) / K : 1;
-
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int x = (tile % P.tiles_x) * 32 + threadIdx.x;
         const int y = (tile / P.tiles_x) * 8 + threadIdx.y;
         // ---------------- search_newton, ICP.cu:196-244 (real parts)
         bool found = false;
         float vcx = 0, vcy = 0, vcz = 0;  // vcurr (camera frame)
+        float gx = 0, gy = 0, gz = 0;     // vcurr_g
         int ux = 0, uy = 0;
-        if (x < P.cols && y < P.rows) {
+        const bool inside = x < P.cols && y < P.rows;
+        if (inside) {
             const size_t pix = (size_t) y * P.cols + x;
             const float ncx = P.nmap_curr[pix];
             if (!isnan(ncx)) {
@@ -119,9 +116,9 @@ template <int C, int K> __global__ void __launch_bounds__(256) icp_kernel(const 
                 vcz = P.vmap_curr[pix + 2 * plane];
                 const float *R = P.curr.R, *t = P.curr.t, *Q = P.prev.R, *tp = P.prev.t;
                 // vcurr_g = Rcurr * vcurr + tcurr
-                const float gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], vcx), __fmul_rn(R[1], vcy)), __fmul_rn(R[2], vcz)), t[0]);
-                const float gy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3], vcx), __fmul_rn(R[4], vcy)), __fmul_rn(R[5], vcz)), t[1]);
-                const float gz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[6], vcx), __fmul_rn(R[7], vcy)), __fmul_rn(R[8], vcz)), t[2]);
+                gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], vcx), __fmul_rn(R[1], vcy)), __fmul_rn(R[2], vcz)), t[0]);
+                gy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3], vcx), __fmul_rn(R[4], vcy)), __fmul_rn(R[5], vcz)), t[1]);
+                gz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[6], vcx), __fmul_rn(R[7], vcy)), __fmul_rn(R[8], vcz)), t[2]);
                 // vcurr_cp = Rprev_inv * (vcurr_g - tprev)
                 const float ex = __fsub_rn(gx, tp[0]), ey = __fsub_rn(gy, tp[1]), ez = __fsub_rn(gz, tp[2]);
                 const float px = __fadd_rn(__fadd_rn(__fmul_rn(Q[0], ex), __fmul_rn(Q[1], ey)), __fmul_rn(Q[2], ez));
@@ -155,86 +152,49 @@ template <int C, int K> __global__ void __launch_bounds__(256) icp_kernel(const 
                 }
             }
         }
-        // ---------------- rows and products per direction tile, ICP.cu:254-279
-        for (int dt = 0; dt < dtiles; ++dt) {
-            const int k0 = dt * K;
-            Row7<C, K> row;
-            if (found) {
-                const JetPose<C, K> cur = load_pose<C, K>(P.curr, P.dpose_curr, k0, P.dirs);
-                const Jet3<C, K> vc = {jconst<C, K>(vcx), jconst<C, K>(vcy), jconst<C, K>(vcz)};
-                const Jet3<C, K> s = jrot(cur, vc) + cur.t;
-                const size_t q = (size_t) uy * P.cols + ux;
-                Jet3<C, K> n, d;
-                n.x.v = P.nmap_prev[q];
-                n.y.v = P.nmap_prev[q + plane];
-                n.z.v = P.nmap_prev[q + 2 * plane];
-                d.x.v = P.vmap_prev[q];
-                d.y.v = P.vmap_prev[q + plane];
-                d.z.v = P.vmap_prev[q + 2 * plane];
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const int comp = k0 * C + i;
-                    if (comp < P.ncomp) {
-                        const size_t o = q + (size_t) (1 + comp) * 3 * plane;
-                        n.x.d[i] = P.nmap_prev[o];
-                        n.y.d[i] = P.nmap_prev[o + plane];
-                        n.z.d[i] = P.nmap_prev[o + 2 * plane];
-                        d.x.d[i] = P.vmap_prev[o];
-                        d.y.d[i] = P.vmap_prev[o + plane];
-                        d.z.d[i] = P.vmap_prev[o + 2 * plane];
-                    } else {
-                        n.x.d[i] = n.y.d[i] = n.z.d[i] = 0.f;
-                        d.x.d[i] = d.y.d[i] = d.z.d[i] = 0.f;
-                    }
-                }
-                const Jet3<C, K> cr = jcross(s, n);
-                row.r[0] = cr.x;
-                row.r[1] = cr.y;
-                row.r[2] = cr.z;
-                row.r[3] = n.x;
-                row.r[4] = n.y;
-                row.r[5] = n.z;
-                row.r[6] = jdot(n, d - s);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 7; ++i) row.r[i] = jconst<C, K>(0.f);
+        // ---------------- the real row, ICP.cu:254-260: s = vcurr_g, n = nprev_g, d = vprev_g
+        float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (found) {
+            const size_t q = (size_t) uy * P.cols + ux;
+            const float nx = P.nmap_prev[q], ny = P.nmap_prev[q + plane], nz = P.nmap_prev[q + 2 * plane];
+            const float ex = __fsub_rn(P.vmap_prev[q], gx), ey = __fsub_rn(P.vmap_prev[q + plane], gy),
+                        ez = __fsub_rn(P.vmap_prev[q + 2 * plane], gz);
+            row[0] = __fsub_rn(__fmul_rn(gy, nz), __fmul_rn(gz, ny));
+            row[1] = __fsub_rn(__fmul_rn(gz, nx), __fmul_rn(gx, nz));
+            row[2] = __fsub_rn(__fmul_rn(gx, ny), __fmul_rn(gy, nx));
+            row[3] = nx;
+            row[4] = ny;
+            row[5] = nz;
+            row[6] = __fadd_rn(__fadd_rn(__fmul_rn(nx, ex), __fmul_rn(ny, ey)), __fmul_rn(nz, ez));
+            if (P.ncomp > 0) {
+                const size_t pix = (size_t) y * P.cols + x;
+                float *f = P.rec_f + pix;
+                f[0 * plane] = vcx, f[1 * plane] = vcy, f[2 * plane] = vcz;
+                f[3 * plane] = gx, f[4 * plane] = gy, f[5 * plane] = gz;
+                f[6 * plane] = nx, f[7 * plane] = ny, f[8 * plane] = nz;
+                f[9 * plane] = ex, f[10 * plane] = ey, f[11 * plane] = ez;
+                f[12 * plane] = row[0], f[13 * plane] = row[1], f[14 * plane] = row[2];
+                f[15 * plane] = row[6];
             }
-            // one 32-wide group per component: 27 products, widened to double (ICP.cu:273-274)
-            double *stage = s_stage + (size_t) warp * (1 + N) * 32;
-            if (k0 == 0) {
-                double v[32];
-#pragma unroll
-                for (int e = 27; e < 32; ++e) v[e] = 0.0;
-                fill_real<C, K>(v, row, std::make_integer_sequence<int, 27>());
-                stage[lane] = warp_transpose_reduce(v);
-            }
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                double v[32];
-#pragma unroll
-                for (int e = 27; e < 32; ++e) v[e] = 0.0;
-                fill_deriv<C, K>(v, row, i, std::make_integer_sequence<int, 27>());
-                stage[(1 + i) * 32 + lane] = warp_transpose_reduce(v);
-            }
-            __syncthreads();
-            // combine the 8 warps in fixed order; thread (g, e) owns accumulator (component, product e)
-            for (int idx = tid; idx < (1 + N) * 32; idx += 256) {
-                const int g = idx >> 5, e = idx & 31;
-                if (e >= 27) continue;
-                if (g == 0 && k0 != 0) continue;
-                const int comp = (g == 0) ? 0 : 1 + k0 * C + (g - 1);
-                if (comp > P.ncomp) continue;
-                double sum = 0.0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) sum += s_stage[(size_t) w * (1 + N) * 32 + idx];
-                s_acc[comp * 27 + e] += sum;
-            }
-            __syncthreads();
         }
+        if (inside && P.ncomp > 0) P.rec_idx[(size_t) y * P.cols + x] = found ? (int) ((size_t) uy * P.cols + ux) : -1;
+        // 27 products, widened to double (ICP.cu:273-274); warp transpose-reduce, then the 8 warps in fixed order
+        double v[32];
+#pragma unroll
+        for (int e = 27; e < 32; ++e) v[e] = 0.0;
+        fill_real(v, row, std::make_integer_sequence<int, 27>());
+        s_stage[warp][lane] = warp_transpose_reduce(v);
+        __syncthreads();
+        if (tid < 27) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sum += s_stage[w][tid];
+            s_acc[tid] += sum;
+        }
+        __syncthreads();
     }
     // ---------------- block partials, then the last block reduces over blocks in block order
-    double *mine = P.partials + (size_t) blockIdx.x * nvals;
-    for (int i = tid; i < nvals; i += 256) mine[i] = s_acc[i];
+    if (tid < 27) P.partials[(size_t) blockIdx.x * 27 + tid] = s_acc[tid];
     __threadfence();
     __shared__ bool s_last;
     __syncthreads();
@@ -242,35 +202,170 @@ template <int C, int K> __global__ void __launch_bounds__(256) icp_kernel(const 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int i = tid; i < nvals; i += 256) {
+    if (tid < 27) {
         double sum = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(P.partials + (size_t) b * nvals + i);
-        P.sums[i] = sum;
+        for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(P.partials + (size_t) b * 27 + tid);
+        P.sums[tid] = sum;
     }
     if (tid == 0) *P.ticket = 0u;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// pass 2: derivative components of the 27 products for one direction group.
+//   C == 3 : the group is one bicomplex direction, slots (0,1,2) = (eps1, eps2, eps1eps2)
+//   C == 1 : the group is three independent first-order components
+// acc[a][e] accumulates  d_a (row_i * row_j)  for e <-> (i, j).
+template <int C, int... E>
+XS_DEV void accumulate_products(float (&acc)[3][27], const float (&r)[7], const float (&d0)[7], const float (&d1)[7],
+                                const float (&d2)[7], std::integer_sequence<int, E...>) {
+    ((acc[0][E] = fmaf(r[tri_i(E)], d0[tri_j(E)], fmaf(d0[tri_i(E)], r[tri_j(E)], acc[0][E]))), ...);
+    ((acc[1][E] = fmaf(r[tri_i(E)], d1[tri_j(E)], fmaf(d1[tri_i(E)], r[tri_j(E)], acc[1][E]))), ...);
+    if (C == 3) {
+        ((acc[2][E] = fmaf(r[tri_i(E)], d2[tri_j(E)],
+                           fmaf(d2[tri_i(E)], r[tri_j(E)],
+                                fmaf(d0[tri_i(E)], d1[tri_j(E)], fmaf(d1[tri_i(E)], d0[tri_j(E)], acc[2][E]))))),
+         ...);
+    } else {
+        ((acc[2][E] = fmaf(r[tri_i(E)], d2[tri_j(E)], fmaf(d2[tri_i(E)], r[tri_j(E)], acc[2][E]))), ...);
+    }
+}
+
+XS_DEV void cross3(const float *a, const float *b, float *o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+XS_DEV void cross3_add(const float *a, const float *b, float *o) {
+    o[0] += a[1] * b[2] - a[2] * b[1];
+    o[1] += a[2] * b[0] - a[0] * b[2];
+    o[2] += a[0] * b[1] - a[1] * b[0];
+}
+XS_DEV float dot3(const float *a, const float *b) { return fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2])); }
+
+template <int C> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(const IcpParams P) {
+    __shared__ float s_pose[3][12];
+    __shared__ float s_t[8][27][33];
+    __shared__ double s_w[3][8][27];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int group = blockIdx.x, chunk = blockIdx.y;
+    const int comp0 = group * 3;
+    if (tid < 36) {
+        const int a = tid / 12, e = tid % 12;
+        s_pose[a][e] = (comp0 + a < P.ncomp) ? P.dpose_curr[(size_t) (comp0 + a) * 12 + e] : 0.f;
+    }
+    __syncthreads();
+    const size_t plane = (size_t) P.rows * P.cols;
+    const int npix = P.rows * P.cols;
+    float acc[3][27];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int e = 0; e < 27; ++e) acc[a][e] = 0.f;
+    const int base = chunk * 256 * P.ppt;
+    for (int j = 0; j < P.ppt; ++j) {
+        const int p = base + j * 256 + tid;
+        if (p >= npix) break;
+        const int q = P.rec_idx[p];
+        if (q < 0) continue;
+        const float *f = P.rec_f + p;
+        const float vc[3] = {f[0 * plane], f[1 * plane], f[2 * plane]};
+        const float s[3] = {f[3 * plane], f[4 * plane], f[5 * plane]};
+        const float n[3] = {f[6 * plane], f[7 * plane], f[8 * plane]};
+        const float e[3] = {f[9 * plane], f[10 * plane], f[11 * plane]};
+        const float r[7] = {f[12 * plane], f[13 * plane], f[14 * plane], n[0], n[1], n[2], f[15 * plane]};
+        float ds[3][3], dn[3][3], de[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float *m = s_pose[a];
+            ds[a][0] = fmaf(m[0], vc[0], fmaf(m[1], vc[1], fmaf(m[2], vc[2], m[9])));
+            ds[a][1] = fmaf(m[3], vc[0], fmaf(m[4], vc[1], fmaf(m[5], vc[2], m[10])));
+            ds[a][2] = fmaf(m[6], vc[0], fmaf(m[7], vc[1], fmaf(m[8], vc[2], m[11])));
+            const int comp = min(comp0 + a, P.ncomp - 1);  // out-of-range slots re-read a valid plane; their sums are dropped
+            const size_t o = (size_t) q + (size_t) (1 + comp) * 3 * plane;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                dn[a][c] = P.nmap_prev[o + c * plane];
+                de[a][c] = P.vmap_prev[o + c * plane] - ds[a][c];
+            }
+        }
+        float d[3][7];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            cross3(ds[a], n, d[a]);        // d(s x n) = ds x n + s x dn
+            cross3_add(s, dn[a], d[a]);
+            d[a][3] = dn[a][0];
+            d[a][4] = dn[a][1];
+            d[a][5] = dn[a][2];
+            d[a][6] = dot3(dn[a], e) + dot3(n, de[a]);  // d(n . (d - s))
+        }
+        if (C == 3) {  // eps1eps2 cross terms
+            cross3_add(ds[0], dn[1], d[2]);
+            cross3_add(ds[1], dn[0], d[2]);
+            d[2][6] += dot3(dn[0], de[1]) + dot3(dn[1], de[0]);
+        }
+        accumulate_products<C>(acc, r, d[0], d[1], d[2], std::make_integer_sequence<int, 27>());
+    }
+    // ---------------- reduce in double, fixed order: the FP32 per-thread sums go through shared memory; thread (w, e)
+    // widens and adds the 32 lanes of warp w for product e, then the 8 warps are combined.
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int e = 0; e < 27; ++e) s_t[warp][e][lane] = acc[a][e];
+        __syncthreads();
+        if (tid < 216) {
+            const int w = tid / 27, e = tid % 27;
+            double sum = 0.0;
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) sum += (double) s_t[w][e][l];
+            s_w[a][w][e] = sum;
+        }
+        __syncthreads();
+    }
+    if (tid < 81) {
+        const int a = tid / 27, e = tid % 27;
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += s_w[a][w][e];
+        P.dpartials[((size_t) chunk * P.groups + group) * 81 + tid] = sum;
+    }
+}
+
+// pass 3: fixed-order sum over the chunks
+__global__ void __launch_bounds__(96) icp_finish_kernel(const IcpParams P) {
+    const int group = blockIdx.x, tid = threadIdx.x;
+    if (tid >= 81) return;
+    const int a = tid / 27, e = tid % 27;
+    const int comp = group * 3 + a;
+    if (comp >= P.ncomp) return;
+    double sum = 0.0;
+    for (int c = 0; c < P.chunks; ++c) sum += P.dpartials[((size_t) c * P.groups + group) * 81 + tid];
+    P.sums[(size_t) (1 + comp) * 27 + e] = sum;
+}
+
 // persistent scratch of the ICP operator (gbuf / mbuf of the reference, ICP.cu:400-403)
 struct IcpScratch {
-    double *d_partials = nullptr, *d_sums = nullptr, *h_sums = nullptr;
+    double *d_partials = nullptr, *d_sums = nullptr, *h_sums = nullptr, *d_dpartials = nullptr;
     unsigned int *d_ticket = nullptr;
     float *d_dpose = nullptr, *h_dpose = nullptr;
-    int cap_vals = 0, cap_comp = -1;
+    int *d_rec_idx = nullptr;
+    float *d_rec_f = nullptr;
+    int cap_vals = 0, cap_comp = -1, cap_pix = 0;
+    size_t cap_dpart = 0;
     int max_blocks = 296;
 };
 static IcpScratch g_icp;
 
-static int icp_reserve(int ncomp) {
+static int icp_reserve(int ncomp, int npix, size_t dpart) {
     const int nvals = 27 * (1 + ncomp);
     if (nvals > g_icp.cap_vals) {
-        cudaFree(g_icp.d_partials);
         cudaFree(g_icp.d_sums);
         cudaFreeHost(g_icp.h_sums);
-        XS_CUDA(cudaMalloc(&g_icp.d_partials, (size_t) g_icp.max_blocks * nvals * sizeof(double)));
         XS_CUDA(cudaMalloc(&g_icp.d_sums, (size_t) nvals * sizeof(double)));
         XS_CUDA(cudaMallocHost(&g_icp.h_sums, (size_t) nvals * sizeof(double)));
         g_icp.cap_vals = nvals;
     }
+    if (!g_icp.d_partials) XS_CUDA(cudaMalloc(&g_icp.d_partials, (size_t) g_icp.max_blocks * 27 * sizeof(double)));
     if (!g_icp.d_ticket) {
         XS_CUDA(cudaMalloc(&g_icp.d_ticket, sizeof(unsigned int)));
         XS_CUDA(cudaMemset(g_icp.d_ticket, 0, sizeof(unsigned int)));
@@ -278,10 +373,22 @@ static int icp_reserve(int ncomp) {
     if (ncomp > g_icp.cap_comp) {
         cudaFree(g_icp.d_dpose);
         cudaFreeHost(g_icp.h_dpose);
-        const size_t n = (size_t) (ncomp > 0 ? ncomp : 1) * 24;
+        const size_t n = (size_t) (ncomp > 0 ? ncomp : 1) * 12;
         XS_CUDA(cudaMalloc(&g_icp.d_dpose, n * sizeof(float)));
         XS_CUDA(cudaMallocHost(&g_icp.h_dpose, n * sizeof(float)));
         g_icp.cap_comp = ncomp;
+    }
+    if (ncomp > 0 && npix > g_icp.cap_pix) {
+        cudaFree(g_icp.d_rec_idx);
+        cudaFree(g_icp.d_rec_f);
+        XS_CUDA(cudaMalloc(&g_icp.d_rec_idx, (size_t) npix * sizeof(int)));
+        XS_CUDA(cudaMalloc(&g_icp.d_rec_f, (size_t) npix * REC_F * sizeof(float)));
+        g_icp.cap_pix = npix;
+    }
+    if (dpart > g_icp.cap_dpart) {
+        cudaFree(g_icp.d_dpartials);
+        XS_CUDA(cudaMalloc(&g_icp.d_dpartials, dpart * sizeof(double)));
+        g_icp.cap_dpart = dpart;
     }
     return XS_OK;
 }
@@ -304,22 +411,23 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
         return XS_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t) stream;
-    int rc = icp_reserve(ncomp);
+    const int npix = rows * cols;
+    IcpParams P;
+    // derivative pass decomposition: a thread sums at most 16 pixels in FP32 before the double reduction
+    P.groups = (ncomp + 2) / 3;
+    P.ppt = npix >= 256 * 16 * 64 ? 16 : npix >= 256 * 8 * 32 ? 8 : (npix >= 256 * 4 * 64 ? 4 : (npix >= 256 * 2 * 32 ? 2 : 1));
+    P.chunks = div_up(npix, 256 * P.ppt);
+    int rc = icp_reserve(ncomp, npix, (size_t) P.chunks * P.groups * 81);
     if (rc != XS_OK) return rc;
+    // only the current pose's derivative components enter the rows (s = Rcurr*v + tcurr); the previous pose is used
+    // for the real projection only (ICP.cu:206-217 takes real parts)
     for (int q = 0; q < ncomp; ++q) {
-        float *hc = g_icp.h_dpose + q * 12, *hp = g_icp.h_dpose + (size_t) ncomp * 12 + q * 12;
-        for (int e = 0; e < 9; ++e) {
-            hc[e] = curr->dR[q * 9 + e];
-            hp[e] = prev->dR[q * 9 + e];
-        }
-        for (int e = 0; e < 3; ++e) {
-            hc[9 + e] = curr->dt[q * 3 + e];
-            hp[9 + e] = prev->dt[q * 3 + e];
-        }
+        float *hc = g_icp.h_dpose + q * 12;
+        for (int e = 0; e < 9; ++e) hc[e] = curr->dR[q * 9 + e];
+        for (int e = 0; e < 3; ++e) hc[9 + e] = curr->dt[q * 3 + e];
     }
     if (ncomp)
-        XS_CUDA(cudaMemcpyAsync(g_icp.d_dpose, g_icp.h_dpose, (size_t) ncomp * 24 * sizeof(float), cudaMemcpyHostToDevice, s));
-    IcpParams P;
+        XS_CUDA(cudaMemcpyAsync(g_icp.d_dpose, g_icp.h_dpose, (size_t) ncomp * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
     for (int i = 0; i < 9; ++i) {
         P.curr.R[i] = curr->R[i];
         P.prev.R[i] = prev->R[i];
@@ -329,7 +437,6 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
         P.prev.t[i] = prev->t[i];
     }
     P.dpose_curr = g_icp.d_dpose;
-    P.dpose_prev = g_icp.d_dpose + (size_t) ncomp * 12;
     P.vmap_curr = d_vmap_curr;
     P.nmap_curr = d_nmap_curr;
     P.vmap_prev = d_vmap_g_prev;
@@ -341,7 +448,10 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
     P.ncomp = ncomp;
     P.dist_thres = dist_thres;
     P.angle_thres = angle_thres;
+    P.rec_idx = g_icp.d_rec_idx;
+    P.rec_f = g_icp.d_rec_f;
     P.partials = g_icp.d_partials;
+    P.dpartials = g_icp.d_dpartials;
     P.sums = g_icp.d_sums;
     P.ticket = g_icp.d_ticket;
     P.tiles_x = div_up(cols, 32);
@@ -349,17 +459,18 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
     const int ntiles = P.tiles_x * P.tiles_y;
     const int grid = ntiles < g_icp.max_blocks ? ntiles : g_icp.max_blocks;
     const int nvals = 27 * (1 + ncomp);
-    const int N = (comps == 1) ? 6 : 6;
-    const size_t smem = ((size_t) nvals + (size_t) 8 * (1 + N) * 32) * sizeof(double);
-    dim3 blk(32, 8);
-    if (comps == 1) {
-        XS_CUDA(cudaFuncSetAttribute(icp_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        icp_kernel<1, 6><<<grid, blk, smem, s>>>(P);
-    } else {
-        XS_CUDA(cudaFuncSetAttribute(icp_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        icp_kernel<3, 2><<<grid, blk, smem, s>>>(P);
-    }
+    icp_assoc_kernel<<<grid, dim3(32, 8), 0, s>>>(P);
     XS_LAUNCH_CHECK();
+    if (ncomp > 0) {
+        dim3 g2(P.groups, P.chunks);
+        if (comps == 1)
+            icp_deriv_kernel<1><<<g2, 256, 0, s>>>(P);
+        else
+            icp_deriv_kernel<3><<<g2, 256, 0, s>>>(P);
+        XS_LAUNCH_CHECK();
+        icp_finish_kernel<<<P.groups, 96, 0, s>>>(P);
+        XS_LAUNCH_CHECK();
+    }
     XS_CUDA(cudaMemcpyAsync(g_icp.h_sums, g_icp.d_sums, (size_t) nvals * sizeof(double), cudaMemcpyDeviceToHost, s));
     XS_CUDA(cudaStreamSynchronize(s));  // estimateCombined syncs and downloads, ICP.cu:414-417
     // unpack upper-triangular order into column-major symmetric A and b, ICP.cu:419-428
