@@ -101,7 +101,9 @@ int xs_volume_export_planes(const xs_volume *v, int comp, float *d_value, int *d
 int xs_volume_import_planes(xs_volume *v, int comp, const float *d_value, const int *d_weight, const float *d_grad,
                             void *stream);
 /* integrateTsdfVolume, TsdfFusion.h:40-45 / TsdfFusion.cu:173.  v2c = (Rv2c, tv2c) with ncomp derivative
- * components.  stats (optional, device-written then copied): [0] updated voxels, [1] bricks touched. */
+ * components.  stats (optional, 4 values, device-written then copied): [0] updated voxels, [1] bricks surviving the
+ * frustum cull, [2] updated voxels whose derivative planes were read and written (band voxels + saturated voxels of
+ * bricks that hold non-zero derivatives; all other derivative planes are exactly zero and are not touched). */
 int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, xs_intr intr,
                  int max_weight, const xs_pose *v2c, float bilinear_threshold, unsigned long long *stats_host,
                  void *stream);

@@ -46,9 +46,57 @@ struct IntegrateParams {
     int max_weight;
     float threshold;
     float trunc_inv;
-    unsigned long long *stats;
+    unsigned long long *stats;  // [0] updated voxels, [1] bricks in the list, [2] voxels whose derivative planes were read+written
     int nbricks;
+    const int *brick_list;      // bricks that survive the cull (written by cull_bricks_kernel)
+    unsigned int *list_count;
+    unsigned char *live;        // [nbricks] 0 = every derivative plane of the brick is still exactly zero
 };
+
+// Conservative brick cull: bounding sphere vs. camera half-space / image planes.  One thread per brick; survivors are
+// appended to the brick list (warp-aggregated), so the integration kernel never touches a brick outside the frustum.
+__global__ void __launch_bounds__(256) cull_bricks_kernel(const IntegrateParams P, int *__restrict__ list) {
+    const int b = blockIdx.x * 256 + threadIdx.x;
+    bool keep = false;
+    if (b < P.nbricks) {
+        const float vs = P.V.voxel;
+        const float *R = P.v2c.R, *t = P.v2c.t;
+        const int bx = b % P.V.bx, by = (b / P.V.bx) % P.V.by, bz = b / (P.V.bx * P.V.by);
+        const float cxw = (bx * 8 + 4) * vs, cyw = (by * 8 + 4) * vs, czw = (bz * 8 + 4) * vs;
+        const float ccx = R[0] * cxw + R[1] * cyw + R[2] * czw + t[0];
+        const float ccy = R[3] * cxw + R[4] * cyw + R[5] * czw + t[1];
+        const float ccz = R[6] * cxw + R[7] * cyw + R[8] * czw + t[2];
+        const float rad = 6.4f * vs + 1e-4f;  // > half diagonal 3.5*sqrt(3) = 6.06 voxels
+        bool cull = false;
+        if (ccz + rad < 0.f) {
+            cull = true;  // every voxel has z < 0  =>  Re(1/z) < 0
+        } else if (ccz - rad > 1e-3f) {
+            const float fx = P.intr.fx, fy = P.intr.fy, pcx = P.intr.cx, pcy = P.intr.cy;
+            // ix >= lo  <=>  fx*X - (lo-cx)*Z >= 0 ; a voxel needs 2 <= ix < cols and 2 <= iy < rows
+            float nz, nn;
+            nz = -(1.5f - pcx);
+            nn = sqrtf(fx * fx + nz * nz);
+            if (fx * ccx + nz * ccz + rad * nn < 0.f) cull = true;
+            nz = (P.cols + 0.5f - pcx);
+            nn = sqrtf(fx * fx + nz * nz);
+            if (-fx * ccx + nz * ccz + rad * nn < 0.f) cull = true;
+            nz = -(1.5f - pcy);
+            nn = sqrtf(fy * fy + nz * nz);
+            if (fy * ccy + nz * ccz + rad * nn < 0.f) cull = true;
+            nz = (P.rows + 0.5f - pcy);
+            nn = sqrtf(fy * fy + nz * nz);
+            if (-fy * ccy + nz * ccz + rad * nn < 0.f) cull = true;
+        }
+        keep = !cull;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(P.list_count, (unsigned) __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = b;
+}
 
 // Real path + derivative of sdf w.r.t. v_c for one voxel.  K = 3 (C=1: gradient) or 6 (C=3: pairs
 // (0,0),(0,1),(0,2),(1,1),(1,2),(2,2) -> gradient + Hessian).  Returns false when the voxel is skipped.
@@ -122,39 +170,15 @@ template <int C> __global__ void __launch_bounds__(512) integrate_kernel(const I
     const float vs = P.V.voxel;
     const float *R = P.v2c.R, *t = P.v2c.t;
     const int lx = tid & 7, ly = (tid >> 3) & 7, lz = tid >> 6;
-    unsigned long long n_upd = 0;
+    unsigned long long n_upd = 0, n_der = 0;
+    const int nlist = (int) *P.list_count;
 
-    for (int b = blockIdx.x; b < P.nbricks; b += gridDim.x) {
+    for (int li = blockIdx.x; li < nlist; li += gridDim.x) {
+        const int b = P.brick_list[li];
         const int bx = b % P.V.bx, by = (b / P.V.bx) % P.V.by, bz = b / (P.V.bx * P.V.by);
-        // ---- conservative brick cull (uniform per CTA): bounding sphere vs. camera half-space / image planes
-        {
-            const float cxw = (bx * 8 + 4) * vs, cyw = (by * 8 + 4) * vs, czw = (bz * 8 + 4) * vs;
-            const float ccx = R[0] * cxw + R[1] * cyw + R[2] * czw + t[0];
-            const float ccy = R[3] * cxw + R[4] * cyw + R[5] * czw + t[1];
-            const float ccz = R[6] * cxw + R[7] * cyw + R[8] * czw + t[2];
-            const float rad = 6.4f * vs + 1e-4f;  // > half diagonal 3.5*sqrt(3) = 6.06 voxels
-            bool cull = false;
-            if (ccz + rad < 0.f) {
-                cull = true;  // every voxel has z < 0  =>  Re(1/z) < 0
-            } else if (ccz - rad > 1e-3f) {
-                const float fx = P.intr.fx, fy = P.intr.fy, pcx = P.intr.cx, pcy = P.intr.cy;
-                // ix >= lo  <=>  fx*X - (lo-cx)*Z >= 0 ; a voxel needs 2 <= ix < cols and 2 <= iy < rows
-                float nz, nn;
-                nz = -(1.5f - pcx);
-                nn = sqrtf(fx * fx + nz * nz);
-                if (fx * ccx + nz * ccz + rad * nn < 0.f) cull = true;
-                nz = (P.cols + 0.5f - pcx);
-                nn = sqrtf(fx * fx + nz * nz);
-                if (-fx * ccx + nz * ccz + rad * nn < 0.f) cull = true;
-                nz = -(1.5f - pcy);
-                nn = sqrtf(fy * fy + nz * nz);
-                if (fy * ccy + nz * ccz + rad * nn < 0.f) cull = true;
-                nz = (P.rows + 0.5f - pcy);
-                nn = sqrtf(fy * fy + nz * nz);
-                if (-fy * ccy + nz * ccz + rad * nn < 0.f) cull = true;
-            }
-            if (cull) continue;
-        }
+        // derivative planes of a brick that never held a truncation-band voxel are exactly zero: scaling them by
+        // w/(w+1) is the identity, so free-space bricks move no derivative bytes at all
+        const bool live = ncomp > 0 && P.live[b] != 0;
         // ---- per-voxel real path (TsdfFusion.cu:110-114)
         const int x = bx * 8 + lx, y = by * 8 + ly, z = bz * 8 + lz;
         const float vgx = __fmul_rn(__fadd_rn(float(x), 0.5f), vs);
@@ -183,9 +207,14 @@ template <int C> __global__ void __launch_bounds__(512) integrate_kernel(const I
         const float a_keep = wf * inv_w1;
         float *dp = P.V.deriv + (size_t) b * ncomp * BRICK_VOX + tid;
         if (saturated) {  // tsdf = (1, 0): F_q <- F_q * w / (w + 1)
+            if (!live) continue;
+            ++n_der;
+#pragma unroll 8
             for (int q = 0; q < ncomp; ++q) dp[(size_t) q * BRICK_VOX] *= a_keep;
             continue;
         }
+        ++n_der;
+        if (!live) P.live[b] = 1;  // benign race: every writer stores 1; other voxels of the brick hold zeros
         const float sc = P.trunc_inv * inv_w1;
         Jet<C, K> sdfj;
         eval_voxel<C, K>(P, vcx, vcy, vcz, sdfj);
@@ -233,8 +262,13 @@ template <int C> __global__ void __launch_bounds__(512) integrate_kernel(const I
     }
     // updated-voxel count (drives the algorithmic-bytes model)
     if (P.stats) {
-        for (int o = 16; o > 0; o >>= 1) n_upd += __shfl_down_sync(0xffffffffu, n_upd, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            n_upd += __shfl_down_sync(0xffffffffu, n_upd, o);
+            n_der += __shfl_down_sync(0xffffffffu, n_der, o);
+        }
         if ((tid & 31) == 0 && n_upd) atomicAdd(P.stats, n_upd);
+        if ((tid & 31) == 0 && n_der) atomicAdd(P.stats + 2, n_der);
+        if (tid == 0 && blockIdx.x == 0) P.stats[1] = (unsigned long long) nlist;
     }
 }
 
@@ -294,6 +328,13 @@ xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_rang
     if (e == cudaSuccess) e = cudaMallocHost(&v->h_dpose, pose_floats * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&v->d_stats, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&v->h_stats, 4 * sizeof(unsigned long long));
+    const size_t nbricks = nvox / BRICK_VOX;
+    v->d_brick_list = nullptr;
+    v->d_list_count = nullptr;
+    v->d_live = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_brick_list, nbricks * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_list_count, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_live, nbricks);
     v->ev_k0 = v->ev_k1 = nullptr;
     v->last_kernel_ms = 0.f;
     if (e == cudaSuccess) e = cudaEventCreate(&v->ev_k0);
@@ -325,6 +366,9 @@ void xs_volume_destroy(xs_volume *v) {
     cudaFree(v->d_hit_time);
     cudaFree(v->d_stats);
     cudaFreeHost(v->h_stats);
+    cudaFree(v->d_brick_list);
+    cudaFree(v->d_list_count);
+    cudaFree(v->d_live);
     if (v->ev_k0) cudaEventDestroy(v->ev_k0);
     if (v->ev_k1) cudaEventDestroy(v->ev_k1);
     delete v;
@@ -336,6 +380,7 @@ int xs_volume_reset(xs_volume *v, void *stream) {
     reset_volume_kernel<<<148 * 8, 256, 0, (cudaStream_t) stream>>>(v->view.value, v->view.weight, v->view.deriv, nvox,
                                                                      nvox * v->view.ncomp);
     XS_LAUNCH_CHECK();
+    XS_CUDA(cudaMemsetAsync(v->d_live, 0, nvox / BRICK_VOX, (cudaStream_t) stream));
     XS_CUDA(cudaStreamSynchronize((cudaStream_t) stream));  // initVolume syncs, TsdfFusion.cu:42
     return XS_OK;
 }
@@ -356,6 +401,8 @@ int xs_volume_import_planes(xs_volume *v, int comp, const float *d_value, const 
     convert_planes_kernel<false><<<148 * 8, 256, 0, (cudaStream_t) stream>>>(
         v->view, comp, const_cast<float *>(d_value), const_cast<int *>(d_weight), const_cast<float *>(d_grad));
     XS_LAUNCH_CHECK();
+    if (d_grad)  // imported derivative planes may be non-zero anywhere
+        XS_CUDA(cudaMemsetAsync(v->d_live, 1, (size_t) v->view.bx * v->view.by * v->view.bz, (cudaStream_t) stream));
     return XS_OK;
 }
 
@@ -413,7 +460,13 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
     P.trunc_inv = 1.0f / v->view.trunc;  // TsdfFusion.cu:99
     P.stats = v->d_stats;
     P.nbricks = v->view.bx * v->view.by * v->view.bz;
+    P.brick_list = v->d_brick_list;
+    P.list_count = v->d_list_count;
+    P.live = v->d_live;
     XS_CUDA(cudaMemsetAsync(v->d_stats, 0, 4 * sizeof(unsigned long long), s));
+    XS_CUDA(cudaMemsetAsync(v->d_list_count, 0, sizeof(unsigned int), s));
+    cull_bricks_kernel<<<div_up(P.nbricks, 256), 256, 0, s>>>(P, v->d_brick_list);
+    XS_LAUNCH_CHECK();
     int grid = P.nbricks < 148 * 16 ? P.nbricks : 148 * 16;
     size_t smem = (size_t) (v->view.ncomp > 0 ? v->view.ncomp : 1) * 12 * sizeof(float);
     XS_CUDA(cudaEventRecord(v->ev_k0, s));
@@ -425,7 +478,8 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
     XS_CUDA(cudaEventRecord(v->ev_k1, s));
     XS_CUDA(cudaMemcpyAsync(v->h_stats, v->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     XS_CUDA(cudaStreamSynchronize(s));  // integrateTsdfVolume syncs, TsdfFusion.cu:200
-    if (stats_host) stats_host[0] = v->h_stats[0];
+    if (stats_host)
+        for (int i = 0; i < 4; ++i) stats_host[i] = v->h_stats[i];
     cudaEventElapsedTime(&v->last_kernel_ms, v->ev_k0, v->ev_k1);
     return XS_OK;
 }

@@ -570,7 +570,9 @@ int xs_kinfu_get_algorithmic_bytes(const xs_kinfu *k, double *out4) {
                 icp += P0 / double(1 << (2 * level)) * (48 + 24 * D) + 27 * 8 * (1 + D);
     }
     out4[1] = icp;
-    out4[2] = (double) k->stats[0] * 2 * (4 + 4 + 4 * D) + 2 * P0;  // integration: RMW of value, weight, D planes
+    // integration: RMW of value + weight for every updated voxel, RMW of the D derivative planes for the voxels whose
+    // planes can be non-zero (truncation-band voxels and saturated voxels of live bricks; the rest are exactly zero)
+    out4[2] = (double) k->stats[0] * 2 * (4 + 4) + (double) k->stats[2] * 2 * 4 * D + 2 * P0;
     // raycast: output maps + pyramid (march / hit gathers are data dependent and reported separately)
     out4[3] = 24 * (1 + D) * P0 + 2 * 12 * (1 + D) * 5 * (P - P0);
     return XS_OK;
