@@ -5,9 +5,9 @@
 // resizeMapKernel / resizeVMap / resizeNMap (XKinectFusion/src/Map.cu:105-152,233-259).
 //
 // The march (RayCaster.cu:236-247) runs on the real value plane only and is shared by all perturbation
-// directions.  Threads leave the march loop before the (expensive) hit evaluation so that a warp does the
-// trilinear / normal work convergently; the hit is then evaluated once per direction tile with Jet<C,K>
-// numbers, reading derivative planes only at the 8 trilinear samples of the hit.
+// directions.  The hit is then evaluated in a second kernel: the real path once per pixel (reference-faithful
+// arithmetic), then one pass per direction that propagates derivative components only, reading derivative planes
+// only at the 8 trilinear samples of the hit.
 #include "xs_common.cuh"
 
 namespace xs {
@@ -26,56 +26,6 @@ struct RaycastParams {
 
 XS_DEV float read_value(const VolumeView &V, int x, int y, int z) {
     return __fadd_rn(__ldg(V.value + value_index(V, x, y, z)), 1e-5f);  // RayCaster.cu:74-76
-}
-
-template <int C, int K> XS_DEV Jet<C, K> read_tsdf(const VolumeView &V, int x, int y, int z, int k0, int dirs) {
-    Jet<C, K> r;
-    const size_t base = (size_t) brick_of(V, x, y, z) * V.ncomp * BRICK_VOX + local_of(x, y, z);
-    r.v = __fadd_rn(__ldg(V.value + value_index(V, x, y, z)), 1e-5f);
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-            r.d[k * C + c] = (k0 + k < dirs) ? __ldg(V.deriv + base + (size_t) ((k0 + k) * C + c) * BRICK_VOX) : 0.f;
-    return r;
-}
-
-// interpolateTrilineary, RayCaster.cu:99-141.  Returns false where the reference returns NaN.
-template <int C, int K>
-XS_DEV bool trilinear(const VolumeView &V, const Jet3<C, K> &p, int k0, int dirs, Jet<C, K> &out) {
-    const float vs = V.voxel;
-    int gx = __float2int_rd(__fdiv_rn(p.x.v, vs));
-    int gy = __float2int_rd(__fdiv_rn(p.y.v, vs));
-    int gz = __float2int_rd(__fdiv_rn(p.z.v, vs));
-    if (gx <= 0 || gx >= V.rx - 1) return false;
-    if (gy <= 0 || gy >= V.ry - 1) return false;
-    if (gz <= 0 || gz >= V.rz - 1) return false;
-    // g -= (v >= p): the reference's sign trick (:117-122) also steps down on equality
-    if (__fmul_rn(__fadd_rn(float(gx), 0.5f), vs) >= p.x.v) gx -= 1;
-    if (__fmul_rn(__fadd_rn(float(gy), 0.5f), vs) >= p.y.v) gy -= 1;
-    if (__fmul_rn(__fadd_rn(float(gz), 0.5f), vs) >= p.z.v) gz -= 1;
-    const float inv_vs = __fdiv_rn(1.f, vs);
-    Jet<C, K> a0, b0, c0;
-    a0.v = __fdiv_rn(__fmaf_rn(-__fadd_rn(float(gx), 0.5f), vs, p.x.v), vs);
-    b0.v = __fdiv_rn(__fmaf_rn(-__fadd_rn(float(gy), 0.5f), vs, p.y.v), vs);
-    c0.v = __fdiv_rn(__fmaf_rn(-__fadd_rn(float(gz), 0.5f), vs, p.z.v), vs);
-#pragma unroll
-    for (int i = 0; i < Jet<C, K>::N; ++i) {
-        a0.d[i] = p.x.d[i] * inv_vs;
-        b0.d[i] = p.y.d[i] * inv_vs;
-        c0.d[i] = p.z.d[i] * inv_vs;
-    }
-    const Jet<C, K> a1 = jrsubf(1.0f, a0), b1 = jrsubf(1.0f, b0), c1 = jrsubf(1.0f, c0);
-    Jet<C, K> r = ((read_tsdf<C, K>(V, gx, gy, gz, k0, dirs) * a1) * b1) * c1;
-    r = r + ((read_tsdf<C, K>(V, gx, gy, gz + 1, k0, dirs) * a1) * b1) * c0;
-    r = r + ((read_tsdf<C, K>(V, gx, gy + 1, gz, k0, dirs) * a1) * b0) * c1;
-    r = r + ((read_tsdf<C, K>(V, gx, gy + 1, gz + 1, k0, dirs) * a1) * b0) * c0;
-    r = r + ((read_tsdf<C, K>(V, gx + 1, gy, gz, k0, dirs) * a0) * b1) * c1;
-    r = r + ((read_tsdf<C, K>(V, gx + 1, gy, gz + 1, k0, dirs) * a0) * b1) * c0;
-    r = r + ((read_tsdf<C, K>(V, gx + 1, gy + 1, gz, k0, dirs) * a0) * b0) * c1;
-    r = r + ((read_tsdf<C, K>(V, gx + 1, gy + 1, gz + 1, k0, dirs) * a0) * b0) * c0;
-    out = r;
-    return true;
 }
 
 // ray origin and direction in volume coordinates, RayCaster.cu:56-62,207-213
@@ -101,73 +51,6 @@ XS_DEV void store3(float *map, int comp, int rows, int cols, int y, int x, float
     p[0] = a;
     p[plane] = b;
     p[2 * plane] = c;
-}
-
-// Result of one hit evaluation for direction tile [k0,k0+K): world-frame vertex / normal with their derivative
-// components, and which of the two the reference would have written (RayCaster.cu:268-271,297-303).
-template <int C, int K> struct HitOut {
-    Jet3<C, K> vw, ng;
-    bool v_ok, n_ok;
-};
-
-// Hit evaluation for direction tile [k0,k0+K), RayCaster.cu:249-305.
-template <int C, int K>
-XS_DEV void eval_hit(const RaycastParams &P, int x, int y, float time_curr, int k0, HitOut<C, K> &out) {
-    typedef Jet<C, K> J;
-    const VolumeView &V = P.V;
-    out.v_ok = out.n_ok = false;
-    Jet3<C, K> start, dir;
-    ray_setup<C, K>(P, x, y, k0, start, dir);
-    const float t1 = __fadd_rn(time_curr, P.time_step);
-    Jet3<C, K> p1 = {jfmaf(dir.x, t1, start.x), jfmaf(dir.y, t1, start.y), jfmaf(dir.z, t1, start.z)};
-    J Ftdt, Ft;
-    if (!trilinear<C, K>(V, p1, k0, P.dirs, Ftdt)) return;
-    Jet3<C, K> p0 = {jfmaf(dir.x, time_curr, start.x), jfmaf(dir.y, time_curr, start.y), jfmaf(dir.z, time_curr, start.z)};
-    if (!trilinear<C, K>(V, p0, k0, P.dirs, Ft)) return;
-    if (isnan(Ftdt.v) || isnan(Ft.v)) return;
-    const J coef = Ft / (Ftdt - Ft);
-    if (Ft.v < 0.0f || Ftdt.v > 0.0f) return;
-    // Ts = time_curr - time_step * coef
-    J Ts;
-    Ts.v = __fmaf_rn(-coef.v, P.time_step, time_curr);
-#pragma unroll
-    for (int i = 0; i < J::N; ++i) Ts.d[i] = -P.time_step * coef.d[i];
-    const Jet3<C, K> vertex = {start.x + dir.x * Ts, start.y + dir.y * Ts, start.z + dir.z * Ts};
-    const JetPose<C, K> v2w = load_pose<C, K>(P.v2w, P.dpose_v2w, k0, P.dirs);
-    out.vw = jrot(v2w, vertex) + v2w.t;
-    out.v_ok = true;
-
-    const float vs = V.voxel;
-    const int gx = __float2int_rd(__fdiv_rn(vertex.x.v, vs));
-    const int gy = __float2int_rd(__fdiv_rn(vertex.y.v, vs));
-    const int gz = __float2int_rd(__fdiv_rn(vertex.z.v, vs));
-    if (!(gx > 1 && gy > 1 && gz > 1 && gx < V.rx - 2 && gy < V.ry - 2 && gz < V.rz - 2)) return;
-    const float hv = __fmul_rn(vs, 0.5f);
-    Jet3<C, K> t, n;
-    J F1, F2;
-    bool ok = true;
-    t = vertex;
-    t.x = jaddf(vertex.x, hv);
-    ok &= trilinear<C, K>(V, t, k0, P.dirs, F1);
-    t.x = jsubf(vertex.x, hv);
-    ok &= trilinear<C, K>(V, t, k0, P.dirs, F2);
-    n.x = F1 - F2;
-    t = vertex;
-    t.y = jaddf(vertex.y, hv);
-    ok &= trilinear<C, K>(V, t, k0, P.dirs, F1);
-    t.y = jsubf(vertex.y, hv);
-    ok &= trilinear<C, K>(V, t, k0, P.dirs, F2);
-    n.y = F1 - F2;
-    t = vertex;
-    t.z = jaddf(vertex.z, hv);
-    ok &= trilinear<C, K>(V, t, k0, P.dirs, F1);
-    t.z = jsubf(vertex.z, hv);
-    ok &= trilinear<C, K>(V, t, k0, P.dirs, F2);
-    n.z = F1 - F2;
-    if (!ok) return;  // cannot happen for g in (1, N-2); the reference would propagate NaN
-    if (jdot(n, n).v == 0.f) return;
-    out.ng = jrot(v2w, jnormalized(n));
-    out.n_ok = true;
 }
 
 // ---- pass 1: the real march, RayCaster.cu:222-247.  One thread per pixel on the value plane only; the result
@@ -234,90 +117,358 @@ __global__ void __launch_bounds__(256) raycast_march_kernel(const RaycastParams 
     hit_time[(size_t) y * P.cols + x] = result;
 }
 
-// ---- pass 2: hit evaluation, one thread per (pixel, direction tile).  A CTA is 32 consecutive pixels of a row x
-// 8 direction tiles, so the 8 warps share the real value samples of the same pixels through L1 while each reads its
-// own derivative planes.  Every output element is written exactly once (values, or the NaN / 0 fill of :204-205).
-template <int C, int K> __global__ void __launch_bounds__(256) raycast_hit_kernel(const RaycastParams P, const float *__restrict__ hit_time) {
-    const int x = threadIdx.x + blockIdx.x * 32;
-    const int y = blockIdx.y;
-    const int tile = threadIdx.y + blockIdx.z * 8;
-    const int tiles = P.dirs > 0 ? (P.dirs + K - 1) / K : 1;
-    if (x >= P.cols || tile >= tiles) return;
-    const int k0 = tile * K;
-    HitOut<C, K> o;
-    o.v_ok = o.n_ok = false;
-    const float time_curr = hit_time[(size_t) y * P.cols + x];
-    if (time_curr >= 0.f) eval_hit<C, K>(P, x, y, time_curr, k0, o);
-    const float qnan = __int_as_float(0x7fffffff);
-    if (k0 == 0) {
-        if (o.v_ok)
-            store3(P.vmap, 0, P.rows, P.cols, y, x, o.vw.x.v, o.vw.y.v, o.vw.z.v);
-        else
-            store3(P.vmap, 0, P.rows, P.cols, y, x, qnan, 0.f, 0.f);
-        if (o.n_ok)
-            store3(P.nmap, 0, P.rows, P.cols, y, x, o.ng.x.v, o.ng.y.v, o.ng.z.v);
-        else
-            store3(P.nmap, 0, P.rows, P.cols, y, x, qnan, 0.f, 0.f);
+// ---- pass 2: hit evaluation with the real path evaluated ONCE per pixel.
+//
+// A CTA owns 32 consecutive pixels of one image row.  Warp 0 evaluates the real hit (RayCaster.cu:249-305) with the
+// reference-faithful arithmetic above and leaves, per pixel and per trilinear sample (2 for the crossing, 6 for the
+// normal), a small context in shared memory: packed per-axis corner offsets, the weights (a, b, c), the gradient G and
+// mixed second partials H of the trilinear interpolant with respect to (a, b, c), and its value.  Then the 8 warps
+// loop over the perturbation directions (warp w takes directions w, w+8, ...; thread = pixel) and propagate ONLY
+// derivative components:  d tri = <dF>_w + G.d(abc)  and, for the eps1eps2 component,
+//   d12 tri = <F12>_w + G.d12(abc) + grad<F2>.d1(abc) + grad<F1>.d2(abc) + d1(abc)^T H d2(abc),
+// where <.>_w is the trilinear contraction of that component's 8 corner values (7 lerps).  Real parts inside this loop
+// are only coefficients, so they use MUFU-based division / rsqrt instead of the reference-faithful sequences.
+constexpr int HIT_PX = 32, HIT_WARPS = 8;
+// per-sample context fields
+enum { S_PX0 = 0, S_PX1, S_PY0, S_PY1, S_PZ0, S_PZ1, S_A, S_B, S_C, S_GA, S_GB, S_GC, S_HAB, S_HAC, S_HBC, S_VAL, S_FIELDS };
+// per-pixel context fields
+enum { X_FLAGS = 0, X_T0, X_FIELDS };
+constexpr int HIT_CTX_WORDS = 8 * S_FIELDS + X_FIELDS;
+
+// packed per-axis offsets: (brick part << 9) | (brick-local part); the sum over the three axes is (brick << 9) | local
+XS_DEV unsigned pack_x(int x) { return ((unsigned) (x >> 3) << 9) | (unsigned) (x & 7); }
+XS_DEV unsigned pack_y(const VolumeView &V, int y) { return ((unsigned) ((y >> 3) * V.bx) << 9) | (unsigned) ((y & 7) << 3); }
+XS_DEV unsigned pack_z(const VolumeView &V, int z) { return ((unsigned) ((z >> 3) * V.by * V.bx) << 9) | (unsigned) ((z & 7) << 6); }
+
+// value, gradient and (optionally) mixed second partials of the trilinear interpolant of f[i*4 + j*2 + k]
+// (i, j, k = x, y, z corner bits) with respect to the weights (a, b, c)
+template <bool HESS>
+XS_DEV void contract(const float (&f)[8], float a, float b, float c, float &val, float &ga, float &gb, float &gc, float &hab,
+                     float &hac, float &hbc) {
+    const float d00 = f[1] - f[0], v00 = fmaf(c, d00, f[0]);
+    const float d01 = f[3] - f[2], v01 = fmaf(c, d01, f[2]);
+    const float d10 = f[5] - f[4], v10 = fmaf(c, d10, f[4]);
+    const float d11 = f[7] - f[6], v11 = fmaf(c, d11, f[6]);
+    const float e0 = v01 - v00, w0 = fmaf(b, e0, v00), k0 = d01 - d00, gc0 = fmaf(b, k0, d00);
+    const float e1 = v11 - v10, w1 = fmaf(b, e1, v10), k1 = d11 - d10, gc1 = fmaf(b, k1, d10);
+    ga = w1 - w0;
+    val = fmaf(a, ga, w0);
+    gb = fmaf(a, e1 - e0, e0);
+    gc = fmaf(a, gc1 - gc0, gc0);
+    if (HESS) {
+        hab = e1 - e0;
+        hac = gc1 - gc0;
+        hbc = fmaf(a, k1 - k0, k0);
     }
+}
+XS_DEV float contract_value(const float (&f)[8], float a, float b, float c) {
+    const float v00 = fmaf(c, f[1] - f[0], f[0]), v01 = fmaf(c, f[3] - f[2], f[2]);
+    const float v10 = fmaf(c, f[5] - f[4], f[4]), v11 = fmaf(c, f[7] - f[6], f[6]);
+    const float w0 = fmaf(b, v01 - v00, v00), w1 = fmaf(b, v11 - v10, v10);
+    return fmaf(a, w1 - w0, w0);
+}
+
+// Real trilinear sample, interpolateTrilineary (RayCaster.cu:99-141) in the reference's operation order, that also
+// records the sample context.  Returns false where the reference returns NaN.
+XS_DEV bool trilinear_real(const VolumeView &V, float px, float py, float pz, float *ctx /* [S_FIELDS][HIT_PX] + lane */,
+                           float &out) {
+    const float vs = V.voxel;
+    int gx = __float2int_rd(__fdiv_rn(px, vs));
+    int gy = __float2int_rd(__fdiv_rn(py, vs));
+    int gz = __float2int_rd(__fdiv_rn(pz, vs));
+    if (gx <= 0 || gx >= V.rx - 1) return false;
+    if (gy <= 0 || gy >= V.ry - 1) return false;
+    if (gz <= 0 || gz >= V.rz - 1) return false;
+    if (__fmul_rn(__fadd_rn(float(gx), 0.5f), vs) >= px) gx -= 1;
+    if (__fmul_rn(__fadd_rn(float(gy), 0.5f), vs) >= py) gy -= 1;
+    if (__fmul_rn(__fadd_rn(float(gz), 0.5f), vs) >= pz) gz -= 1;
+    const float a0 = __fdiv_rn(__fmaf_rn(-__fadd_rn(float(gx), 0.5f), vs, px), vs);
+    const float b0 = __fdiv_rn(__fmaf_rn(-__fadd_rn(float(gy), 0.5f), vs, py), vs);
+    const float c0 = __fdiv_rn(__fmaf_rn(-__fadd_rn(float(gz), 0.5f), vs, pz), vs);
+    const float a1 = __fsub_rn(1.0f, a0), b1 = __fsub_rn(1.0f, b0), c1 = __fsub_rn(1.0f, c0);
+    float f[8];
 #pragma unroll
-    for (int i = 0; i < Jet<C, K>::N; ++i) {
-        if (k0 * C + i < P.V.ncomp) {
-            if (o.v_ok)
-                store3(P.vmap, 1 + k0 * C + i, P.rows, P.cols, y, x, o.vw.x.d[i], o.vw.y.d[i], o.vw.z.d[i]);
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) f[i * 4 + j * 2 + k] = read_value(V, gx + i, gy + j, gz + k);
+    float r = __fmul_rn(__fmul_rn(__fmul_rn(f[0], a1), b1), c1);
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(__fmul_rn(f[1], a1), b1), c0));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(__fmul_rn(f[2], a1), b0), c1));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(__fmul_rn(f[3], a1), b0), c0));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(__fmul_rn(f[4], a0), b1), c1));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(__fmul_rn(f[5], a0), b1), c0));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(__fmul_rn(f[6], a0), b0), c1));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(__fmul_rn(f[7], a0), b0), c0));
+    out = r;
+    float val, ga, gb, gc, hab, hac, hbc;
+    contract<true>(f, a0, b0, c0, val, ga, gb, gc, hab, hac, hbc);
+    ctx[S_PX0 * HIT_PX] = __uint_as_float(pack_x(gx));
+    ctx[S_PX1 * HIT_PX] = __uint_as_float(pack_x(gx + 1));
+    ctx[S_PY0 * HIT_PX] = __uint_as_float(pack_y(V, gy));
+    ctx[S_PY1 * HIT_PX] = __uint_as_float(pack_y(V, gy + 1));
+    ctx[S_PZ0 * HIT_PX] = __uint_as_float(pack_z(V, gz));
+    ctx[S_PZ1 * HIT_PX] = __uint_as_float(pack_z(V, gz + 1));
+    ctx[S_A * HIT_PX] = a0;
+    ctx[S_B * HIT_PX] = b0;
+    ctx[S_C * HIT_PX] = c0;
+    ctx[S_GA * HIT_PX] = ga;
+    ctx[S_GB * HIT_PX] = gb;
+    ctx[S_GC * HIT_PX] = gc;
+    ctx[S_HAB * HIT_PX] = hab;
+    ctx[S_HAC * HIT_PX] = hac;
+    ctx[S_HBC * HIT_PX] = hbc;
+    ctx[S_VAL * HIT_PX] = r;
+    return true;
+}
+
+// Real hit evaluation (warp 0).  flags: bit 0 = vertex valid, bit 1 = normal valid, bits 2..4 = degenerate direction.
+XS_DEV unsigned eval_hit_real(const RaycastParams &P, int x, int y, float time_curr, float *ctx, float (&vw)[3], float (&ng)[3]) {
+    typedef Jet<1, 0> J;
+    const VolumeView &V = P.V;
+    Jet3<1, 0> start, dir;
+    ray_setup<1, 0>(P, x, y, 0, start, dir);
+    const float t1 = __fadd_rn(time_curr, P.time_step);
+    float Ftdt, Ft;
+    if (!trilinear_real(V, __fmaf_rn(dir.x.v, t1, start.x.v), __fmaf_rn(dir.y.v, t1, start.y.v), __fmaf_rn(dir.z.v, t1, start.z.v),
+                        ctx + 0 * S_FIELDS * HIT_PX, Ftdt))
+        return 0u;
+    if (!trilinear_real(V, __fmaf_rn(dir.x.v, time_curr, start.x.v), __fmaf_rn(dir.y.v, time_curr, start.y.v),
+                        __fmaf_rn(dir.z.v, time_curr, start.z.v), ctx + 1 * S_FIELDS * HIT_PX, Ft))
+        return 0u;
+    if (isnan(Ftdt) || isnan(Ft)) return 0u;
+    const float coef = ref_cdiv_re(Ft, __fsub_rn(Ftdt, Ft));
+    if (Ft < 0.0f || Ftdt > 0.0f) return 0u;
+    const float Ts = __fmaf_rn(-coef, P.time_step, time_curr);
+    Jet3<1, 0> vertex;
+    vertex.x.v = __fadd_rn(start.x.v, __fmul_rn(dir.x.v, Ts));
+    vertex.y.v = __fadd_rn(start.y.v, __fmul_rn(dir.y.v, Ts));
+    vertex.z.v = __fadd_rn(start.z.v, __fmul_rn(dir.z.v, Ts));
+    const JetPose<1, 0> v2w = load_pose<1, 0>(P.v2w, P.dpose_v2w, 0, P.dirs);
+    const Jet3<1, 0> w = jrot(v2w, vertex) + v2w.t;
+    vw[0] = w.x.v, vw[1] = w.y.v, vw[2] = w.z.v;
+    unsigned flags = 1u;
+    const float vs = V.voxel;
+    const int gx = __float2int_rd(__fdiv_rn(vertex.x.v, vs));
+    const int gy = __float2int_rd(__fdiv_rn(vertex.y.v, vs));
+    const int gz = __float2int_rd(__fdiv_rn(vertex.z.v, vs));
+    if (!(gx > 1 && gy > 1 && gz > 1 && gx < V.rx - 2 && gy < V.ry - 2 && gz < V.rz - 2)) return flags;
+    const float hv = __fmul_rn(vs, 0.5f);
+    float F[6];
+    bool ok = true;
+    ok &= trilinear_real(V, __fadd_rn(vertex.x.v, hv), vertex.y.v, vertex.z.v, ctx + 2 * S_FIELDS * HIT_PX, F[0]);
+    ok &= trilinear_real(V, __fsub_rn(vertex.x.v, hv), vertex.y.v, vertex.z.v, ctx + 3 * S_FIELDS * HIT_PX, F[1]);
+    ok &= trilinear_real(V, vertex.x.v, __fadd_rn(vertex.y.v, hv), vertex.z.v, ctx + 4 * S_FIELDS * HIT_PX, F[2]);
+    ok &= trilinear_real(V, vertex.x.v, __fsub_rn(vertex.y.v, hv), vertex.z.v, ctx + 5 * S_FIELDS * HIT_PX, F[3]);
+    ok &= trilinear_real(V, vertex.x.v, vertex.y.v, __fadd_rn(vertex.z.v, hv), ctx + 6 * S_FIELDS * HIT_PX, F[4]);
+    ok &= trilinear_real(V, vertex.x.v, vertex.y.v, __fsub_rn(vertex.z.v, hv), ctx + 7 * S_FIELDS * HIT_PX, F[5]);
+    if (!ok) return flags;
+    Jet3<1, 0> n;
+    n.x.v = __fsub_rn(F[0], F[1]);
+    n.y.v = __fsub_rn(F[2], F[3]);
+    n.z.v = __fsub_rn(F[4], F[5]);
+    if (jdot(n, n).v == 0.f) return flags;
+    const Jet3<1, 0> g = jrot(v2w, jnormalized(n));
+    ng[0] = g.x.v, ng[1] = g.y.v, ng[2] = g.z.v;
+    return flags | 2u;
+}
+
+// derivative components of one trilinear sample for one direction; dpos = derivative of the sample position
+template <int C>
+XS_DEV Jet<C, 1> sample_deriv(const VolumeView &V, const float *__restrict__ dq /* deriv + q*C*BRICK_VOX */, const float *ctx,
+                              const Jet3<C, 1> &pos, float inv_vs) {
+    unsigned px[2], py[2], pz[2];
+    px[0] = __float_as_uint(ctx[S_PX0 * HIT_PX]), px[1] = __float_as_uint(ctx[S_PX1 * HIT_PX]);
+    py[0] = __float_as_uint(ctx[S_PY0 * HIT_PX]), py[1] = __float_as_uint(ctx[S_PY1 * HIT_PX]);
+    pz[0] = __float_as_uint(ctx[S_PZ0 * HIT_PX]), pz[1] = __float_as_uint(ctx[S_PZ1 * HIT_PX]);
+    const float a = ctx[S_A * HIT_PX], b = ctx[S_B * HIT_PX], c = ctx[S_C * HIT_PX];
+    float f[C][8];
+    const size_t bstride = (size_t) V.ncomp * BRICK_VOX;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const unsigned pxy = px[i] + py[j];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const unsigned pk = pxy + pz[k];
+                const float *p = dq + (size_t) (pk >> 9) * bstride + (pk & 511u);
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) f[cc][i * 4 + j * 2 + k] = __ldg(p + cc * BRICK_VOX);
+            }
+        }
+    Jet<C, 1> r;
+    r.v = ctx[S_VAL * HIT_PX];
+    const float ga = ctx[S_GA * HIT_PX], gb = ctx[S_GB * HIT_PX], gc = ctx[S_GC * HIT_PX];
+    float unused;
+    if (C == 1) {
+        const float v1 = contract_value(f[0], a, b, c);
+        r.d[0] = fmaf(ga, pos.x.d[0] * inv_vs, fmaf(gb, pos.y.d[0] * inv_vs, fmaf(gc, pos.z.d[0] * inv_vs, v1)));
+    } else {
+        const float a1 = pos.x.d[0] * inv_vs, b1 = pos.y.d[0] * inv_vs, c1 = pos.z.d[0] * inv_vs;
+        const float a2 = pos.x.d[1] * inv_vs, b2 = pos.y.d[1] * inv_vs, c2 = pos.z.d[1] * inv_vs;
+        const float a12 = pos.x.d[2] * inv_vs, b12 = pos.y.d[2] * inv_vs, c12 = pos.z.d[2] * inv_vs;
+        float v1, g1a, g1b, g1c, v2, g2a, g2b, g2c;
+        contract<false>(f[0], a, b, c, v1, g1a, g1b, g1c, unused, unused, unused);
+        contract<false>(f[1 % C], a, b, c, v2, g2a, g2b, g2c, unused, unused, unused);
+        const float v12 = contract_value(f[2 % C], a, b, c);
+        const float hab = ctx[S_HAB * HIT_PX], hac = ctx[S_HAC * HIT_PX], hbc = ctx[S_HBC * HIT_PX];
+        r.d[0] = fmaf(ga, a1, fmaf(gb, b1, fmaf(gc, c1, v1)));
+        r.d[1 % C] = fmaf(ga, a2, fmaf(gb, b2, fmaf(gc, c2, v2)));
+        float t = fmaf(ga, a12, fmaf(gb, b12, fmaf(gc, c12, v12)));
+        t = fmaf(g2a, a1, fmaf(g2b, b1, fmaf(g2c, c1, t)));
+        t = fmaf(g1a, a2, fmaf(g1b, b2, fmaf(g1c, c2, t)));
+        t = fmaf(hab, fmaf(a1, b2, b1 * a2), fmaf(hac, fmaf(a1, c2, c1 * a2), fmaf(hbc, fmaf(b1, c2, c1 * b2), t)));
+        r.d[2 % C] = t;
+    }
+    return r;
+}
+
+template <int C> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS) raycast_hit_kernel(const RaycastParams P, const float *__restrict__ hit_time) {
+    __shared__ float s_ctx[HIT_CTX_WORDS * HIT_PX];
+    typedef Jet<C, 1> J;
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int x = lane + blockIdx.x * HIT_PX;
+    const int y = blockIdx.y;
+    const bool inside = x < P.cols;
+    float *ctx = s_ctx + lane;
+    float *xctx = ctx + 8 * S_FIELDS * HIT_PX;
+    const float qnan = __int_as_float(0x7fffffff);
+    if (warp == 0) {
+        unsigned flags = 0u;
+        float t0 = -1.f;
+        if (inside) {
+            t0 = hit_time[(size_t) y * P.cols + x];
+            float vw[3], ng[3];
+            if (t0 >= 0.f) flags = eval_hit_real(P, x, y, t0, ctx, vw, ng);
+            if (flags & 1u)
+                store3(P.vmap, 0, P.rows, P.cols, y, x, vw[0], vw[1], vw[2]);
             else
-                store3(P.vmap, 1 + k0 * C + i, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
-            if (o.n_ok)
-                store3(P.nmap, 1 + k0 * C + i, P.rows, P.cols, y, x, o.ng.x.d[i], o.ng.y.d[i], o.ng.z.d[i]);
+                store3(P.vmap, 0, P.rows, P.cols, y, x, qnan, 0.f, 0.f);
+            if (flags & 2u)
+                store3(P.nmap, 0, P.rows, P.cols, y, x, ng[0], ng[1], ng[2]);
             else
-                store3(P.nmap, 1 + k0 * C + i, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
+                store3(P.nmap, 0, P.rows, P.cols, y, x, qnan, 0.f, 0.f);
+        }
+        xctx[X_FLAGS * HIT_PX] = __uint_as_float(flags);
+        xctx[X_T0 * HIT_PX] = t0;
+    }
+    __syncthreads();
+    if (!inside || P.dirs == 0) return;
+    const unsigned flags = __float_as_uint(xctx[X_FLAGS * HIT_PX]);
+    const float t0 = xctx[X_T0 * HIT_PX];
+    const VolumeView &V = P.V;
+    const float inv_vs = __fdividef(1.f, V.voxel);
+    const float nx = (float(x) - P.intr.cx) * __fdividef(1.f, P.intr.fx), ny = (float(y) - P.intr.cy) * __fdividef(1.f, P.intr.fy);
+    for (int q = warp; q < P.dirs; q += HIT_WARPS) {
+        Jet3<C, 1> vw, ng;
+        if (flags & 1u) {
+            // ray: start = t, dir = normalized(R * next)  (RayCaster.cu:56-62,207-213)
+            const JetPose<C, 1> c2v = load_pose<C, 1>(P.c2v, P.dpose_c2v, q, P.dirs);
+            Jet3<C, 1> next = {jconst<C, 1>(nx), jconst<C, 1>(ny), jconst<C, 1>(1.f)};
+            const Jet3<C, 1> start = c2v.t;
+            Jet3<C, 1> dir = jnormalized_fast(jrot(c2v, next));
+            // the reference patches exactly-zero direction components with a constant (:211-213)
+            if (dir.x.v == 0.f) dir.x = jconst<C, 1>(1e-15f);
+            if (dir.y.v == 0.f) dir.y = jconst<C, 1>(1e-15f);
+            if (dir.z.v == 0.f) dir.z = jconst<C, 1>(1e-15f);
+            const float t1 = t0 + P.time_step;
+            const Jet3<C, 1> p1 = {jfmaf(dir.x, t1, start.x), jfmaf(dir.y, t1, start.y), jfmaf(dir.z, t1, start.z)};
+            const Jet3<C, 1> p0 = {jfmaf(dir.x, t0, start.x), jfmaf(dir.y, t0, start.y), jfmaf(dir.z, t0, start.z)};
+            const float *dq = V.deriv + (size_t) q * C * BRICK_VOX;
+            const J Ftdt = sample_deriv<C>(V, dq, ctx + 0 * S_FIELDS * HIT_PX, p1, inv_vs);
+            const J Ft = sample_deriv<C>(V, dq, ctx + 1 * S_FIELDS * HIT_PX, p0, inv_vs);
+            const J coef = jdiv_fast(Ft, Ftdt - Ft);
+            J Ts;
+            Ts.v = fmaf(-coef.v, P.time_step, t0);
+#pragma unroll
+            for (int i = 0; i < C; ++i) Ts.d[i] = -P.time_step * coef.d[i];
+            const Jet3<C, 1> vertex = {start.x + dir.x * Ts, start.y + dir.y * Ts, start.z + dir.z * Ts};
+            const JetPose<C, 1> v2w = load_pose<C, 1>(P.v2w, P.dpose_v2w, q, P.dirs);
+            vw = jrot(v2w, vertex) + v2w.t;
+            if (flags & 2u) {
+                // the six normal samples sit at vertex +- half a voxel along one axis: same position derivative
+                Jet3<C, 1> n;
+                n.x = sample_deriv<C>(V, dq, ctx + 2 * S_FIELDS * HIT_PX, vertex, inv_vs) -
+                      sample_deriv<C>(V, dq, ctx + 3 * S_FIELDS * HIT_PX, vertex, inv_vs);
+                n.y = sample_deriv<C>(V, dq, ctx + 4 * S_FIELDS * HIT_PX, vertex, inv_vs) -
+                      sample_deriv<C>(V, dq, ctx + 5 * S_FIELDS * HIT_PX, vertex, inv_vs);
+                n.z = sample_deriv<C>(V, dq, ctx + 6 * S_FIELDS * HIT_PX, vertex, inv_vs) -
+                      sample_deriv<C>(V, dq, ctx + 7 * S_FIELDS * HIT_PX, vertex, inv_vs);
+                ng = jrot(v2w, jnormalized_fast(n));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const int comp = 1 + q * C + i;
+            if (flags & 1u)
+                store3(P.vmap, comp, P.rows, P.cols, y, x, vw.x.d[i], vw.y.d[i], vw.z.d[i]);
+            else
+                store3(P.vmap, comp, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
+            if (flags & 2u)
+                store3(P.nmap, comp, P.rows, P.cols, y, x, ng.x.d[i], ng.y.d[i], ng.z.d[i]);
+            else
+                store3(P.nmap, comp, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
         }
     }
 }
 
 // resizeMapKernel, Map.cu:105-152, for packed-SoA maps with derivative components.
-template <int C, int K, bool NORMALIZE>
-__global__ void resize_map_kernel(int drows, int dcols, int srows, int scols, int dirs, const float *__restrict__ in,
-                                  float *__restrict__ out) {
-    const int x = threadIdx.x + blockIdx.x * blockDim.x;
-    const int y = threadIdx.y + blockIdx.y * blockDim.y;
-    if (x >= dcols || y >= drows) return;
-    const int ncomp = C * dirs;
+// Thread = (output pixel, slot): slot 0 writes the real part with the reference's arithmetic, slot s >= 1 writes the C
+// derivative components of direction s-1 (its real coefficients come from the same four real texels, MUFU-normalised).
+template <int C, bool NORMALIZE>
+__global__ void __launch_bounds__(256) resize_map_kernel(int drows, int dcols, int srows, int scols, int dirs,
+                                                         const float *__restrict__ in, float *__restrict__ out) {
+    const int x = threadIdx.x + blockIdx.x * 32;
+    const int y = blockIdx.y;
+    const int slot = threadIdx.y + blockIdx.z * 8;
+    if (x >= dcols || slot > dirs) return;
     const size_t splane = (size_t) srows * scols;
-    const int xs_ = x * 2, ys_ = y * 2;
-    const float *p00 = in + (size_t) ys_ * scols + xs_;
+    const float *p00 = in + (size_t) (y * 2) * scols + x * 2;
     const float qnan = __int_as_float(0x7fffffff);
-    const float x00 = p00[0], x01 = p00[1], x10 = p00[scols], x11 = p00[scols + 1];
-    if (isnan(x00) || isnan(x01) || isnan(x10) || isnan(x11)) {
-        store3(out, 0, drows, dcols, y, x, qnan, 0.f, 0.f);
-        for (int q = 0; q < ncomp; ++q) store3(out, 1 + q, drows, dcols, y, x, 0.f, 0.f, 0.f);
-        return;
-    }
-    const int tiles = dirs > 0 ? (dirs + K - 1) / K : 1;
-    for (int tile = 0; tile < tiles; ++tile) {
-        const int k0 = tile * K;
-        Jet<C, K> c[3];
+    const float2 t0 = *reinterpret_cast<const float2 *>(p00), t1 = *reinterpret_cast<const float2 *>(p00 + scols);
+    const bool invalid = isnan(t0.x) || isnan(t0.y) || isnan(t1.x) || isnan(t1.y);
+    if (slot == 0) {
+        if (invalid) {
+            store3(out, 0, drows, dcols, y, x, qnan, 0.f, 0.f);
+            return;
+        }
+        Jet3<1, 0> n;
+        Jet<1, 0> *c[3] = {&n.x, &n.y, &n.z};
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl) {
             const float *p = p00 + pl * splane;
             // (x00 + x01 + x10 + x11) / 4.0f
-            c[pl].v = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[scols]), p[scols + 1]), 4.0f);
-#pragma unroll
-            for (int i = 0; i < Jet<C, K>::N; ++i) {
-                const int q = k0 * C + i;
-                if (q < ncomp) {
-                    const float *pd = p + (size_t) (1 + q) * 3 * splane;
-                    c[pl].d[i] = (pd[0] + pd[1] + pd[scols] + pd[scols + 1]) * 0.25f;
-                } else
-                    c[pl].d[i] = 0.f;
-            }
+            c[pl]->v = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[scols]), p[scols + 1]), 4.0f);
         }
-        Jet3<C, K> n = {c[0], c[1], c[2]};
         if (NORMALIZE) n = jnormalized(n);
-        if (k0 == 0) store3(out, 0, drows, dcols, y, x, n.x.v, n.y.v, n.z.v);
-#pragma unroll
-        for (int i = 0; i < Jet<C, K>::N; ++i)
-            if (k0 * C + i < ncomp) store3(out, 1 + k0 * C + i, drows, dcols, y, x, n.x.d[i], n.y.d[i], n.z.d[i]);
+        store3(out, 0, drows, dcols, y, x, n.x.v, n.y.v, n.z.v);
+        return;
     }
+    const int q0 = (slot - 1) * C;
+    if (invalid) {
+#pragma unroll
+        for (int i = 0; i < C; ++i) store3(out, 1 + q0 + i, drows, dcols, y, x, 0.f, 0.f, 0.f);
+        return;
+    }
+    Jet<C, 1> c[3];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const float *p = p00 + pl * splane;
+        const float2 a = *reinterpret_cast<const float2 *>(p), b = *reinterpret_cast<const float2 *>(p + scols);
+        c[pl].v = (a.x + a.y + b.x + b.y) * 0.25f;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const float *pd = p + (size_t) (1 + q0 + i) * 3 * splane;
+            const float2 da = *reinterpret_cast<const float2 *>(pd), db = *reinterpret_cast<const float2 *>(pd + scols);
+            c[pl].d[i] = (da.x + da.y + db.x + db.y) * 0.25f;
+        }
+    }
+    Jet3<C, 1> n = {c[0], c[1], c[2]};
+    if (NORMALIZE) n = jnormalized_fast(n);
+#pragma unroll
+    for (int i = 0; i < C; ++i) store3(out, 1 + q0 + i, drows, dcols, y, x, n.x.d[i], n.y.d[i], n.z.d[i]);
 }
 
 int upload_pose_derivs(const xs_volume *v, const xs_pose *p, int slot, cudaStream_t s);
@@ -325,13 +476,14 @@ int upload_pose_derivs(const xs_volume *v, const xs_pose *p, int slot, cudaStrea
 template <bool NORMALIZE>
 static int resize_map(const float *d_in, int rows, int cols, int comps, int dirs, float *d_out, void *stream) {
     if (!d_in || !d_out || rows < 2 || cols < 2 || (comps != 1 && comps != 3) || dirs < 0) return XS_ERR_ARG;
+    if ((cols & 1) || (rows & 1)) return XS_ERR_ARG;  // 64-bit texel pairs
     const int drows = rows / 2, dcols = cols / 2;
-    dim3 blk(32, 8), grd(div_up(dcols, 32), div_up(drows, 8));
+    dim3 blk(32, 8), grd(div_up(dcols, 32), drows, div_up(dirs + 1, 8));
     cudaStream_t s = (cudaStream_t) stream;
     if (comps == 1)
-        resize_map_kernel<1, 6, NORMALIZE><<<grd, blk, 0, s>>>(drows, dcols, rows, cols, dirs, d_in, d_out);
+        resize_map_kernel<1, NORMALIZE><<<grd, blk, 0, s>>>(drows, dcols, rows, cols, dirs, d_in, d_out);
     else
-        resize_map_kernel<3, 2, NORMALIZE><<<grd, blk, 0, s>>>(drows, dcols, rows, cols, dirs, d_in, d_out);
+        resize_map_kernel<3, NORMALIZE><<<grd, blk, 0, s>>>(drows, dcols, rows, cols, dirs, d_in, d_out);
     XS_LAUNCH_CHECK();
     return XS_OK;
 }
@@ -380,17 +532,11 @@ int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_po
     dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
     raycast_march_kernel<<<grd, blk, 0, s>>>(P, v->d_hit_time);
     XS_LAUNCH_CHECK();
-    if (v->comps == 1) {
-        constexpr int K = 3;
-        const int tiles = v->dirs > 0 ? div_up(v->dirs, K) : 1;
-        dim3 g2(div_up(cols, 32), rows, div_up(tiles, 8));
-        raycast_hit_kernel<1, K><<<g2, blk, 0, s>>>(P, v->d_hit_time);
-    } else {
-        constexpr int K = 1;
-        const int tiles = v->dirs > 0 ? div_up(v->dirs, K) : 1;
-        dim3 g2(div_up(cols, 32), rows, div_up(tiles, 8));
-        raycast_hit_kernel<3, K><<<g2, blk, 0, s>>>(P, v->d_hit_time);
-    }
+    dim3 g2(div_up(cols, HIT_PX), rows), b2(HIT_PX, HIT_WARPS);
+    if (v->comps == 1)
+        raycast_hit_kernel<1><<<g2, b2, 0, s>>>(P, v->d_hit_time);
+    else
+        raycast_hit_kernel<3><<<g2, b2, 0, s>>>(P, v->d_hit_time);
     XS_LAUNCH_CHECK();
     return XS_OK;  // raycast does not sync, RayCaster.cu:367
 }

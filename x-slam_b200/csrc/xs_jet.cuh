@@ -220,6 +220,62 @@ template <int C, int K> XS_DEV Jet3<C, K> jnormalized(const Jet3<C, K> &a) {
     return {a.x / n, a.y / n, a.z / n};
 }
 
+// ---- "fast-real" variants ------------------------------------------------------------------
+// Used where a kernel re-derives derivative components per direction from a real path that was already evaluated
+// bit-faithfully elsewhere: the real part here is only a coefficient of the derivative formulas (1e-7 relative is
+// plenty), so the reference-faithful logb/scalbn quotient, IEEE division and IEEE sqrt are replaced by MUFU-based ones.
+template <int K> XS_DEV Jet<1, K> jdiv_fast(const Jet<1, K> &a, const Jet<1, K> &b) {
+    Jet<1, K> r;
+    const float inv = __fdividef(1.f, b.v);
+    r.v = a.v * inv;
+#pragma unroll
+    for (int k = 0; k < K; ++k) r.d[k] = (a.d[k] - r.v * b.d[k]) * inv;
+    return r;
+}
+template <int K> XS_DEV Jet<3, K> jdiv_fast(const Jet<3, K> &a, const Jet<3, K> &b) {
+    Jet<3, K> r;
+    const float inv = __fdividef(1.f, b.v);
+    r.v = a.v * inv;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float a1 = a.d[3 * k], a2 = a.d[3 * k + 1], a12 = a.d[3 * k + 2];
+        const float b1 = b.d[3 * k], b2 = b.d[3 * k + 1], b12 = b.d[3 * k + 2];
+        const float q1 = (a1 - r.v * b1) * inv;
+        const float q2 = (a2 - r.v * b2) * inv;
+        r.d[3 * k] = q1;
+        r.d[3 * k + 1] = q2;
+        r.d[3 * k + 2] = (a12 - r.v * b12 - q1 * b2 - q2 * b1) * inv;
+    }
+    return r;
+}
+template <int K> XS_DEV Jet<1, K> jsqrt_fast(const Jet<1, K> &a) {
+    Jet<1, K> r;
+    const float rs = rsqrtf(a.v);
+    r.v = a.v * rs;
+    const float h = 0.5f * rs;
+#pragma unroll
+    for (int k = 0; k < K; ++k) r.d[k] = a.d[k] * h;
+    return r;
+}
+template <int K> XS_DEV Jet<3, K> jsqrt_fast(const Jet<3, K> &a) {
+    Jet<3, K> r;
+    const float rs = rsqrtf(a.v);
+    r.v = a.v * rs;
+    const float h = 0.5f * rs;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float s1 = a.d[3 * k] * h, s2 = a.d[3 * k + 1] * h;
+        r.d[3 * k] = s1;
+        r.d[3 * k + 1] = s2;
+        r.d[3 * k + 2] = (a.d[3 * k + 2] - 2.f * s1 * s2) * h;
+    }
+    return r;
+}
+template <int C, int K> XS_DEV Jet3<C, K> jnormalized_fast(const Jet3<C, K> &a) {
+    const Jet<C, K> n = jsqrt_fast(jdot(a, a));
+    return {jdiv_fast(a.x, n), jdiv_fast(a.y, n), jdiv_fast(a.z, n)};
+}
+
 // ---- rigid transforms with derivative components -------------------------------------------
 struct DevPose {  // real part, passed by value
     float R[9];
