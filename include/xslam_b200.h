@@ -177,7 +177,10 @@ const float *xs_kinfu_map(const xs_kinfu *k, int which, int level, int *rows, in
 /* per-stage device times of the last frame (ms): surface, icp, integrate, raycast+resize, total;
  * followed by per-stage kernel-launch counts (5 more floats) */
 int xs_kinfu_get_times(const xs_kinfu *k, float *ms10);
-/* ICP log of the last frame: iterations x (1+ncomp) x 42 doubles (A 36 column-major, b 6) */
+/* ICP log of the last frame: iterations x (1+ncomp) x 42 doubles (A 36 column-major, b 6).  The Gauss-Newton loop
+ * runs on the device without host round trips; the per-iteration normal equations are only downloaded when the log
+ * has been enabled (off by default). */
+int xs_kinfu_enable_icp_log(xs_kinfu *k, int on);
 int xs_kinfu_take_icp_log(xs_kinfu *k, double *out, int max_iters);
 /* updated-voxel count of the last integration (drives the algorithmic-bytes model) */
 int xs_kinfu_get_stats(const xs_kinfu *k, unsigned long long *out4);

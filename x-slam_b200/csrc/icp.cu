@@ -3,7 +3,8 @@
 // Replaces Combined::{search_newton, operator()} / combinedKernel (XKinectFusion/src/ICP.cu:166-281,357),
 // TranformReduction / TransformEstimatorKernel (ICP.cu:120-164) and estimateCombined (ICP.cu:365-429).
 //
-// Three launches per Gauss-Newton iteration (the reference: 2 launches per direction and iteration):
+// Four launches per Gauss-Newton iteration and NO host round trip (the reference: 2 launches per direction and
+// iteration, then sync + download + host Eigen solve, ICP.cu:414-417 / KinectFusionReconstruction.cpp:196-224):
 //   1. icp_assoc_kernel   data association (projection, bounds, NaN, distance and angle gates) ONCE per pixel on real
 //                         parts, the real 7-vector row [cross(s,n), n, n.(d-s)], its 27 upper-triangular products
 //                         widened to double exactly as the reference does (product in float, sum in double,
@@ -15,6 +16,10 @@
 //                         A thread sums at most 16 pixels in FP32, then everything is reduced in double: warp
 //                         transpose-reduction by shuffles, fixed-order combination of warps, per-CTA partials.
 //   3. icp_finish_kernel  fixed-order sum of the per-CTA partials.
+//   4. icp_solve_kernel   the host Gauss-Newton step of KinectFusionReconstruction.cpp:203-224 on the device: det guard,
+//                         6x6 LLT solve in double, Rinc = Rz*Ry*Rx, pose update - one thread per direction, every
+//                         thread redoing the (tiny) real part.  The current pose therefore lives in device memory and
+//                         the 12 iterations of a frame are queued back to back.
 // Instead of the reference's 27 sequential 256-thread shared-memory tree reductions per direction, the summation
 // order is fixed by construction, so results are deterministic run to run.
 #include "xs_common.cuh"
@@ -68,8 +73,8 @@ template <int... E> XS_DEV void fill_real(double (&v)[32], const float (&r)[7], 
 // per-pixel association record, SoA planes of npix elements each
 constexpr int REC_F = 16;  // vc(3) s(3) n(3) e=d-s(3) cr=cross(s,n)(3) r6
 struct IcpParams {
-    DevPose curr, prev;  // prev.R = Rprev_inv, prev.t = tprev
-    const float *dpose_curr;              // [ncomp][12]
+    DevPose prev;                         // prev.R = Rprev_inv, prev.t = tprev
+    const float *pose_curr;               // [(1+ncomp)][12] device: Rcurr row-major + tcurr; component 0 = real part
     const float *vmap_curr, *nmap_curr;   // [3][rows][cols]
     const float *vmap_prev, *nmap_prev;   // [(1+ncomp)][3][rows][cols]
     xs_intr intr;
@@ -93,7 +98,9 @@ __global__ void __launch_bounds__(256) icp_assoc_kernel(const IcpParams P) {
     __shared__ double s_stage[8][32];
     const int tid = threadIdx.y * 32 + threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    __shared__ float s_curr[12];
     if (tid < 27) s_acc[tid] = 0.0;
+    if (tid < 12) s_curr[tid] = P.pose_curr[tid];
     __syncthreads();
     const size_t plane = (size_t) P.rows * P.cols;
     const int ntiles = P.tiles_x * P.tiles_y;
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(256) icp_assoc_kernel(const IcpParams P) {
                 vcx = P.vmap_curr[pix];
                 vcy = P.vmap_curr[pix + plane];
                 vcz = P.vmap_curr[pix + 2 * plane];
-                const float *R = P.curr.R, *t = P.curr.t, *Q = P.prev.R, *tp = P.prev.t;
+                const float *R = s_curr, *t = s_curr + 9, *Q = P.prev.R, *tp = P.prev.t;
                 // vcurr_g = Rcurr * vcurr + tcurr
                 gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], vcx), __fmul_rn(R[1], vcy)), __fmul_rn(R[2], vcz)), t[0]);
                 gy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3], vcx), __fmul_rn(R[4], vcy)), __fmul_rn(R[5], vcz)), t[1]);
@@ -252,7 +259,7 @@ template <int C> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(cons
     const int comp0 = group * 3;
     if (tid < 36) {
         const int a = tid / 12, e = tid % 12;
-        s_pose[a][e] = (comp0 + a < P.ncomp) ? P.dpose_curr[(size_t) (comp0 + a) * 12 + e] : 0.f;
+        s_pose[a][e] = (comp0 + a < P.ncomp) ? P.pose_curr[(size_t) (1 + comp0 + a) * 12 + e] : 0.f;
     }
     __syncthreads();
     const size_t plane = (size_t) P.rows * P.cols;
@@ -331,23 +338,280 @@ template <int C> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(cons
     }
 }
 
-// pass 3: fixed-order sum over the chunks
-__global__ void __launch_bounds__(96) icp_finish_kernel(const IcpParams P) {
-    const int group = blockIdx.x, tid = threadIdx.x;
-    if (tid >= 81) return;
-    const int a = tid / 27, e = tid % 27;
-    const int comp = group * 3 + a;
-    if (comp >= P.ncomp) return;
-    double sum = 0.0;
-    for (int c = 0; c < P.chunks; ++c) sum += P.dpartials[((size_t) c * P.groups + group) * 81 + tid];
-    P.sums[(size_t) (1 + comp) * 27 + e] = sum;
+// pass 3: fixed-order sum over the chunks.  One warp per (component slot, product): lane l sums chunks l, l+32, ...
+// in order, then a fixed xor-shuffle tree combines the lanes.
+__global__ void __launch_bounds__(32 * 27) icp_finish_kernel(const IcpParams P) {
+    const int group = blockIdx.x, lane = threadIdx.x & 31, e = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int comp = group * 3 + a;
+        if (comp >= P.ncomp) break;
+        double sum = 0.0;
+        for (int c = lane; c < P.chunks; c += 32) sum += P.dpartials[((size_t) c * P.groups + group) * 81 + a * 27 + e];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) P.sums[(size_t) (1 + comp) * 27 + e] = sum;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pass 4: the Gauss-Newton step on the device (KinectFusionReconstruction.cpp:203-224).
+struct cplx {
+    double re, im;
+};
+XS_DEV cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+XS_DEV cplx cconj(cplx a) { return {a.re, -a.im}; }
+XS_DEV cplx csub(cplx a, cplx b) { return {a.re - b.re, a.im - b.im}; }
+XS_DEV cplx cdiv(cplx a, cplx b) {
+    const double d = b.re * b.re + b.im * b.im;
+    return {(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d};
+}
+
+// unpack the upper-triangular product order of ICP.cu:419-428 into a symmetric 6x6 and b
+XS_DEV void unpack_sums(const double *v, double (&A)[6][6], double (&b)[6]) {
+    int shift = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = i; j < 7; ++j) {
+            const double val = v[shift++];
+            if (j == 6)
+                b[i] = val;
+            else
+                A[i][j] = A[j][i] = val;
+        }
+}
+
+// A.real().determinant() (KinectFusionReconstruction.cpp:203): Gaussian elimination with partial pivoting
+XS_DEV double det6_dev(const double (&A)[6][6]) {
+    double M[6][6];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) M[i][j] = A[i][j];
+    double det = 1.0;
+    for (int k = 0; k < 6; ++k) {
+        int p = k;
+        for (int i = k + 1; i < 6; ++i)
+            if (fabs(M[i][k]) > fabs(M[p][k])) p = i;
+        if (M[p][k] == 0.0) return 0.0;
+        if (p != k) {
+            for (int j = 0; j < 6; ++j) {
+                const double t = M[p][j];
+                M[p][j] = M[k][j];
+                M[k][j] = t;
+            }
+            det = -det;
+        }
+        det *= M[k][k];
+        for (int i = k + 1; i < 6; ++i) {
+            const double f = M[i][k] / M[k][k];
+            for (int j = k; j < 6; ++j) M[i][j] -= f * M[k][j];
+        }
+    }
+    return det;
+}
+
+// Eigen 3.4 LLT<Matrix<complex<double>,6,6>,Lower>::solve (unblocked, n < 32): the factor is built from the LOWER
+// triangle with real(A_kk) on the diagonal and conj() in the updates, i.e. the complex-symmetric A of ICP.cu:427 is
+// treated as Hermitian (KinectFusionReconstruction.cpp:211).  Ai / bi = imaginary parts (may be null).
+XS_DEV void llt_hermitian_solve6_dev(const double (&Ar)[6][6], const double (*Ai)[6], const double (&br)[6], const double *bi,
+                                     cplx (&x)[6]) {
+    cplx L[6][6];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) L[i][j] = {Ar[i][j], Ai ? Ai[i][j] : 0.0};
+    for (int k = 0; k < 6; ++k) {
+        double xk = L[k][k].re;
+        for (int j = 0; j < k; ++j) xk -= L[k][j].re * L[k][j].re + L[k][j].im * L[k][j].im;
+        if (xk <= 0.0) break;
+        xk = sqrt(xk);
+        L[k][k] = {xk, 0.0};
+        for (int i = k + 1; i < 6; ++i) {
+            cplx sacc = L[i][k];
+            for (int j = 0; j < k; ++j) sacc = csub(sacc, cmul(L[i][j], cconj(L[k][j])));
+            L[i][k] = {sacc.re / xk, sacc.im / xk};
+        }
+    }
+    cplx y[6];
+    for (int i = 0; i < 6; ++i) {
+        cplx sacc = {br[i], bi ? bi[i] : 0.0};
+        for (int j = 0; j < i; ++j) sacc = csub(sacc, cmul(L[i][j], y[j]));
+        y[i] = cdiv(sacc, L[i][i]);
+    }
+    for (int i = 5; i >= 0; --i) {
+        cplx sacc = y[i];
+        for (int j = i + 1; j < 6; ++j) sacc = csub(sacc, cmul(cconj(L[j][i]), x[j]));
+        x[i] = cdiv(sacc, cconj(L[i][i]));
+    }
+}
+
+XS_DEV void matvec6_dev(const double (&A)[6][6], const double (&x)[6], double (&y)[6]) {
+    for (int i = 0; i < 6; ++i) {
+        double sacc = 0;
+        for (int j = 0; j < 6; ++j) sacc += A[i][j] * x[j];
+        y[i] = sacc;
+    }
+}
+
+// sin / cos of a batched angle; the real part is evaluated in double and rounded (matches the host's correctly
+// rounded sinf / cosf), derivative components by the chain rule
+template <int C> XS_DEV void jsincos(const Jet<C, 1> &a, Jet<C, 1> &sn, Jet<C, 1> &cs) {
+    const float s0 = (float) sin((double) a.v), c0 = (float) cos((double) a.v);
+    sn.v = s0;
+    cs.v = c0;
+    sn.d[0] = c0 * a.d[0];
+    cs.d[0] = -s0 * a.d[0];
+    if (C == 3) {
+        sn.d[1 % C] = c0 * a.d[1 % C];
+        cs.d[1 % C] = -s0 * a.d[1 % C];
+        sn.d[2 % C] = c0 * a.d[2 % C] - s0 * a.d[0] * a.d[1 % C];
+        cs.d[2 % C] = -s0 * a.d[2 % C] - c0 * a.d[0] * a.d[1 % C];
+    }
+}
+template <int C> struct JMat3 {
+    Jet<C, 1> m[3][3];
+};
+// rotation about a coordinate axis: Eigen AngleAxis::toRotationMatrix() specialised to a unit axis (host_jet.h)
+template <int C> XS_DEV JMat3<C> jaxis_rotation(const Jet<C, 1> &angle, int axis) {
+    Jet<C, 1> sn, cs;
+    jsincos<C>(angle, sn, cs);
+    JMat3<C> R;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R.m[i][j] = jconst<C, 1>(0.f);
+    for (int i = 0; i < 3; ++i) R.m[i][i] = (i == axis) ? (jconst<C, 1>(1.f) - cs) + cs : cs;
+    const int a = (axis + 1) % 3, b = (axis + 2) % 3;
+    R.m[a][b] = -sn;
+    R.m[b][a] = sn;
+    return R;
+}
+template <int C> XS_DEV JMat3<C> jmatmul(const JMat3<C> &a, const JMat3<C> &b) {
+    JMat3<C> r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            Jet<C, 1> sacc = a.m[i][0] * b.m[0][j];
+            for (int k = 1; k < 3; ++k) sacc = sacc + a.m[i][k] * b.m[k][j];
+            r.m[i][j] = sacc;
+        }
+    return r;
+}
+
+struct SolveParams {
+    const double *sums;  // [27*(1+ncomp)]
+    const float *pose_in;  // [(1+ncomp)][12] current pose
+    float *pose_out;       // [(1+ncomp)][12] updated pose (a different buffer: blocks do not synchronise)
+    int *status;         // [2]: 0 = ok; 1 = |det(Re A)| < 1e-15; 2 = NaN det.  [0] sticky (later iterations are skipped)
+    double *log;         // optional [27*(1+ncomp)] copy of the sums of this iteration
+    int dirs, ncomp, solve_mode;
+};
+
+template <int C> __global__ void __launch_bounds__(64) icp_solve_kernel(const SolveParams P) {
+    typedef Jet<C, 1> J;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;  // direction handled by this thread (thread 0 also owns the real part)
+    if (P.log)
+        for (int i = q; i < 27 * (1 + P.ncomp); i += gridDim.x * blockDim.x) P.log[i] = P.sums[i];
+    if (P.status[0] != 0 || P.status[1] != 0) {  // [0] sticky flag of earlier iterations, [1] written by this launch
+        if (q == 0) P.status[0] = P.status[0] != 0 ? P.status[0] : P.status[1];
+        return;
+    }
+    if (q >= P.dirs && q != 0) return;
+    double A[6][6], b[6];
+    unpack_sums(P.sums, A, b);
+    const double det = det6_dev(A);
+    if (fabs(det) < 1e-15 || isnan(det)) {
+        // every thread of every block computes the same det and takes this branch; the flag is only read at kernel
+        // entry by later launches
+        if (q == 0) P.status[1] = isnan(det) ? 2 : 1;
+        return;
+    }
+    cplx x0[6];
+    llt_hermitian_solve6_dev(A, nullptr, b, nullptr, x0);  // zero-seed solve: the canonical real part
+    double xr[6];
+    J x[6];
+    for (int i = 0; i < 6; ++i) {
+        xr[i] = x0[i].re;
+        x[i] = jconst<C, 1>((float) xr[i]);
+    }
+    const bool has_dir = q < P.dirs;
+    if (has_dir) {
+        if (C == 1 && P.solve_mode == XS_SOLVE_EIGEN_LLT) {
+            // one Hermitian-LLT solve with this direction's imaginary part, as the reference's one-direction run
+            double Ai[6][6], bi[6];
+            unpack_sums(P.sums + (size_t) (1 + q) * 27, Ai, bi);
+            cplx xq[6];
+            llt_hermitian_solve6_dev(A, Ai, b, bi, xq);
+            for (int i = 0; i < 6; ++i) x[i].d[0] = (float) xq[i].im;
+        } else {
+            // analytic: x_a = A^-1 (b_a - A_a x);  x_12 = A^-1 (b_12 - A_12 x - A_1 x_2 - A_2 x_1)
+            double xa[3][6];
+#pragma unroll
+            for (int a = 0; a < C; ++a) {
+                if (a == 2) continue;
+                double Aa[6][6], ba[6], t[6], rhs[6];
+                unpack_sums(P.sums + (size_t) (1 + q * C + a) * 27, Aa, ba);
+                matvec6_dev(Aa, xr, t);
+                for (int i = 0; i < 6; ++i) rhs[i] = ba[i] - t[i];
+                cplx xs_[6];
+                llt_hermitian_solve6_dev(A, nullptr, rhs, nullptr, xs_);
+                for (int i = 0; i < 6; ++i) xa[a][i] = xs_[i].re;
+            }
+            if (C == 3) {
+                double A1[6][6], A2[6][6], A12[6][6], b1[6], b2[6], b12[6], t[6], rhs[6];
+                unpack_sums(P.sums + (size_t) (1 + q * C) * 27, A1, b1);
+                unpack_sums(P.sums + (size_t) (1 + q * C + 1) * 27, A2, b2);
+                unpack_sums(P.sums + (size_t) (1 + q * C + 2) * 27, A12, b12);
+                for (int i = 0; i < 6; ++i) rhs[i] = b12[i];
+                matvec6_dev(A12, xr, t);
+                for (int i = 0; i < 6; ++i) rhs[i] -= t[i];
+                matvec6_dev(A1, xa[1], t);
+                for (int i = 0; i < 6; ++i) rhs[i] -= t[i];
+                matvec6_dev(A2, xa[0], t);
+                for (int i = 0; i < 6; ++i) rhs[i] -= t[i];
+                cplx xs_[6];
+                llt_hermitian_solve6_dev(A, nullptr, rhs, nullptr, xs_);
+                for (int i = 0; i < 6; ++i) xa[2][i] = xs_[i].re;
+            }
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int a = 0; a < C; ++a) x[i].d[a] = (float) xa[a][i];
+        }
+    }
+    // ---- pose update, KinectFusionReconstruction.cpp:212-224
+    JMat3<C> Rcurr;
+    J tcurr[3];
+    const float *pr = P.pose_in;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            Rcurr.m[i][j].v = pr[i * 3 + j];
+            for (int a = 0; a < C; ++a) Rcurr.m[i][j].d[a] = has_dir ? pr[(size_t) (1 + q * C + a) * 12 + i * 3 + j] : 0.f;
+        }
+        tcurr[i].v = pr[9 + i];
+        for (int a = 0; a < C; ++a) tcurr[i].d[a] = has_dir ? pr[(size_t) (1 + q * C + a) * 12 + 9 + i] : 0.f;
+    }
+    // Rinc = Rz(gamma) * Ry(beta) * Rx(alpha)
+    const JMat3<C> Rinc = jmatmul(jmatmul(jaxis_rotation<C>(x[2], 2), jaxis_rotation<C>(x[1], 1)), jaxis_rotation<C>(x[0], 0));
+    J tn[3];
+    for (int i = 0; i < 3; ++i) {
+        J sacc = Rinc.m[i][0] * tcurr[0];
+        for (int k = 1; k < 3; ++k) sacc = sacc + Rinc.m[i][k] * tcurr[k];
+        tn[i] = sacc + x[3 + i];
+    }
+    const JMat3<C> Rn = jmatmul(Rinc, Rcurr);
+    float *pw = P.pose_out;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            if (q == 0) pw[i * 3 + j] = Rn.m[i][j].v;
+            if (has_dir)
+                for (int a = 0; a < C; ++a) pw[(size_t) (1 + q * C + a) * 12 + i * 3 + j] = Rn.m[i][j].d[a];
+        }
+        if (q == 0) pw[9 + i] = tn[i].v;
+        if (has_dir)
+            for (int a = 0; a < C; ++a) pw[(size_t) (1 + q * C + a) * 12 + 9 + i] = tn[i].d[a];
+    }
 }
 
 // persistent scratch of the ICP operator (gbuf / mbuf of the reference, ICP.cu:400-403)
 struct IcpScratch {
     double *d_partials = nullptr, *d_sums = nullptr, *h_sums = nullptr, *d_dpartials = nullptr;
     unsigned int *d_ticket = nullptr;
-    float *d_dpose = nullptr, *h_dpose = nullptr;
+    float *d_pose = nullptr, *h_pose = nullptr;  // seam-level entry point only: [(1+ncomp)][12]
     int *d_rec_idx = nullptr;
     float *d_rec_f = nullptr;
     int cap_vals = 0, cap_comp = -1, cap_pix = 0;
@@ -371,11 +635,11 @@ static int icp_reserve(int ncomp, int npix, size_t dpart) {
         XS_CUDA(cudaMemset(g_icp.d_ticket, 0, sizeof(unsigned int)));
     }
     if (ncomp > g_icp.cap_comp) {
-        cudaFree(g_icp.d_dpose);
-        cudaFreeHost(g_icp.h_dpose);
-        const size_t n = (size_t) (ncomp > 0 ? ncomp : 1) * 12;
-        XS_CUDA(cudaMalloc(&g_icp.d_dpose, n * sizeof(float)));
-        XS_CUDA(cudaMallocHost(&g_icp.h_dpose, n * sizeof(float)));
+        cudaFree(g_icp.d_pose);
+        cudaFreeHost(g_icp.h_pose);
+        const size_t n = (size_t) (1 + ncomp) * 12;
+        XS_CUDA(cudaMalloc(&g_icp.d_pose, n * sizeof(float)));
+        XS_CUDA(cudaMallocHost(&g_icp.h_pose, n * sizeof(float)));
         g_icp.cap_comp = ncomp;
     }
     if (ncomp > 0 && npix > g_icp.cap_pix) {
@@ -393,24 +657,11 @@ static int icp_reserve(int ncomp, int npix, size_t dpart) {
     return XS_OK;
 }
 
-}  // namespace xs
-
-using namespace xs;
-
-extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_curr, const float *d_nmap_curr,
-                                    const xs_pose *prev, xs_intr intr, const float *d_vmap_g_prev,
-                                    const float *d_nmap_g_prev, int rows, int cols, int comps, int dirs,
-                                    float dist_thres, float angle_thres, double *A_host, double *b_host,
-                                    void *stream) {
-    if (!curr || !prev || !d_vmap_curr || !d_nmap_curr || !d_vmap_g_prev || !d_nmap_g_prev || !A_host || !b_host ||
-        rows <= 0 || cols <= 0 || (comps != 1 && comps != 3) || dirs < 0)
-        return XS_ERR_ARG;
+// Queues the three accumulation kernels of one Gauss-Newton iteration; the sums land in g_icp.d_sums.
+int icp_accumulate_async(const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
+                         xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
+                         int dirs, float dist_thres, float angle_thres, cudaStream_t s) {
     const int ncomp = comps * dirs;
-    if (curr->ncomp != ncomp || prev->ncomp != ncomp) {
-        set_error("xs_estimate_combined: pose derivative component count mismatch");
-        return XS_ERR_ARG;
-    }
-    cudaStream_t s = (cudaStream_t) stream;
     const int npix = rows * cols;
     IcpParams P;
     // derivative pass decomposition: a thread sums at most 16 pixels in FP32 before the double reduction
@@ -421,22 +672,9 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
     if (rc != XS_OK) return rc;
     // only the current pose's derivative components enter the rows (s = Rcurr*v + tcurr); the previous pose is used
     // for the real projection only (ICP.cu:206-217 takes real parts)
-    for (int q = 0; q < ncomp; ++q) {
-        float *hc = g_icp.h_dpose + q * 12;
-        for (int e = 0; e < 9; ++e) hc[e] = curr->dR[q * 9 + e];
-        for (int e = 0; e < 3; ++e) hc[9 + e] = curr->dt[q * 3 + e];
-    }
-    if (ncomp)
-        XS_CUDA(cudaMemcpyAsync(g_icp.d_dpose, g_icp.h_dpose, (size_t) ncomp * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
-    for (int i = 0; i < 9; ++i) {
-        P.curr.R[i] = curr->R[i];
-        P.prev.R[i] = prev->R[i];
-    }
-    for (int i = 0; i < 3; ++i) {
-        P.curr.t[i] = curr->t[i];
-        P.prev.t[i] = prev->t[i];
-    }
-    P.dpose_curr = g_icp.d_dpose;
+    for (int i = 0; i < 9; ++i) P.prev.R[i] = prev->R[i];
+    for (int i = 0; i < 3; ++i) P.prev.t[i] = prev->t[i];
+    P.pose_curr = d_pose_curr;
     P.vmap_curr = d_vmap_curr;
     P.nmap_curr = d_nmap_curr;
     P.vmap_prev = d_vmap_g_prev;
@@ -458,7 +696,6 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
     P.tiles_y = div_up(rows, 8);
     const int ntiles = P.tiles_x * P.tiles_y;
     const int grid = ntiles < g_icp.max_blocks ? ntiles : g_icp.max_blocks;
-    const int nvals = 27 * (1 + ncomp);
     icp_assoc_kernel<<<grid, dim3(32, 8), 0, s>>>(P);
     XS_LAUNCH_CHECK();
     if (ncomp > 0) {
@@ -468,9 +705,67 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
         else
             icp_deriv_kernel<3><<<g2, 256, 0, s>>>(P);
         XS_LAUNCH_CHECK();
-        icp_finish_kernel<<<P.groups, 96, 0, s>>>(P);
+        icp_finish_kernel<<<P.groups, 32 * 27, 0, s>>>(P);
         XS_LAUNCH_CHECK();
     }
+    return XS_OK;
+}
+
+// Queues the device-side Gauss-Newton step on the sums of the last icp_accumulate_async.
+int icp_solve_async(const float *d_pose_in, float *d_pose_out, int comps, int dirs, int solve_mode, int *d_status,
+                    double *d_log, cudaStream_t s) {
+    SolveParams S;
+    S.sums = g_icp.d_sums;
+    S.pose_in = d_pose_in;
+    S.pose_out = d_pose_out;
+    S.status = d_status;
+    S.log = d_log;
+    S.dirs = dirs;
+    S.ncomp = comps * dirs;
+    S.solve_mode = solve_mode;
+    const int blocks = dirs > 0 ? div_up(dirs, 64) : 1;
+    if (comps == 1)
+        icp_solve_kernel<1><<<blocks, 64, 0, s>>>(S);
+    else
+        icp_solve_kernel<3><<<blocks, 64, 0, s>>>(S);
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
+
+}  // namespace xs
+
+using namespace xs;
+
+extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_curr, const float *d_nmap_curr,
+                                    const xs_pose *prev, xs_intr intr, const float *d_vmap_g_prev,
+                                    const float *d_nmap_g_prev, int rows, int cols, int comps, int dirs,
+                                    float dist_thres, float angle_thres, double *A_host, double *b_host,
+                                    void *stream) {
+    if (!curr || !prev || !d_vmap_curr || !d_nmap_curr || !d_vmap_g_prev || !d_nmap_g_prev || !A_host || !b_host ||
+        rows <= 0 || cols <= 0 || (comps != 1 && comps != 3) || dirs < 0)
+        return XS_ERR_ARG;
+    const int ncomp = comps * dirs;
+    if (curr->ncomp != ncomp || prev->ncomp != ncomp) {
+        set_error("xs_estimate_combined: pose derivative component count mismatch");
+        return XS_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t) stream;
+    int rc = icp_reserve(ncomp, rows * cols, 0);
+    if (rc != XS_OK) return rc;
+    XS_CUDA(cudaStreamSynchronize(s));  // pinned staging reuse
+    float *h = g_icp.h_pose;
+    for (int e = 0; e < 9; ++e) h[e] = curr->R[e];
+    for (int e = 0; e < 3; ++e) h[9 + e] = curr->t[e];
+    for (int q = 0; q < ncomp; ++q) {
+        float *hc = h + (size_t) (1 + q) * 12;
+        for (int e = 0; e < 9; ++e) hc[e] = curr->dR[q * 9 + e];
+        for (int e = 0; e < 3; ++e) hc[9 + e] = curr->dt[q * 3 + e];
+    }
+    XS_CUDA(cudaMemcpyAsync(g_icp.d_pose, h, (size_t) (1 + ncomp) * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = icp_accumulate_async(g_icp.d_pose, d_vmap_curr, d_nmap_curr, prev, intr, d_vmap_g_prev, d_nmap_g_prev, rows, cols,
+                              comps, dirs, dist_thres, angle_thres, s);
+    if (rc != XS_OK) return rc;
+    const int nvals = 27 * (1 + ncomp);
     XS_CUDA(cudaMemcpyAsync(g_icp.h_sums, g_icp.d_sums, (size_t) nvals * sizeof(double), cudaMemcpyDeviceToHost, s));
     XS_CUDA(cudaStreamSynchronize(s));  // estimateCombined syncs and downloads, ICP.cu:414-417
     // unpack upper-triangular order into column-major symmetric A and b, ICP.cu:419-428

@@ -25,6 +25,12 @@
 namespace xs {
 void set_error(const std::string &msg);
 extern long long g_launches;
+// icp.cu: one Gauss-Newton iteration queued on the stream, no host round trip
+int icp_accumulate_async(const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
+                         xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
+                         int dirs, float dist_thres, float angle_thres, cudaStream_t s);
+int icp_solve_async(const float *d_pose_in, float *d_pose_out, int comps, int dirs, int solve_mode, int *d_status,
+                    double *d_log, cudaStream_t s);
 }  // namespace xs
 using namespace xs;
 
@@ -52,7 +58,11 @@ struct xs_kinfu {
     uint16_t *h_depth = nullptr;  // pinned staging
     std::vector<float *> depths, vmaps_curr, nmaps_curr, vmaps_prev, nmaps_prev;
     float *d_record = nullptr, *h_record = nullptr;  // [(1+ncomp)][16]
-    std::vector<double> A, b;                        // [(1+ncomp)][36], [(1+ncomp)][6]
+    float *d_pose[2] = {nullptr, nullptr};           // ICP current pose, ping-pong: [(1+ncomp)][12] (R row-major, t)
+    float *h_pose = nullptr;                         // pinned staging of the same
+    int *d_status = nullptr, *h_status = nullptr;    // [2] ICP degeneracy flag (icp.cu SolveParams::status)
+    bool log_icp = false;
+    double *d_icp_log = nullptr, *h_icp_log = nullptr;  // [max 16 iterations][27*(1+ncomp)] sums per iteration
     std::vector<double> icp_log;
     cudaEvent_t ev[5];
     float ms[5] = {0, 0, 0, 0, 0};
@@ -84,143 +94,6 @@ void to_pose(const HMat3 &R, const HVec3 &t, int ncomp, std::vector<float> &dR, 
     p.ncomp = ncomp;
     p.dR = dR.data();
     p.dt = dt.data();
-}
-
-typedef std::complex<double> cd;
-
-// Eigen 3.4 LLT<Matrix<complex<double>,6,6>,Lower> (unblocked, n < 32) followed by solve(): the factor is
-// built from the LOWER triangle with real(A_kk) on the diagonal and conj() in the updates, i.e. it treats the
-// complex-symmetric A of ICP.cu:427 as Hermitian (KinectFusionReconstruction.cpp:211).
-void llt_hermitian_solve6(const cd *A, const cd *b, cd *x) {
-    cd L[6][6];
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) L[i][j] = A[j * 6 + i];
-    for (int k = 0; k < 6; ++k) {
-        double xk = L[k][k].real();
-        for (int j = 0; j < k; ++j) xk -= std::norm(L[k][j]);
-        if (xk <= 0.0) break;
-        xk = std::sqrt(xk);
-        L[k][k] = cd(xk, 0.0);
-        for (int i = k + 1; i < 6; ++i) {
-            cd s = L[i][k];
-            for (int j = 0; j < k; ++j) s -= L[i][j] * std::conj(L[k][j]);
-            L[i][k] = s / xk;
-        }
-    }
-    cd y[6];
-    for (int i = 0; i < 6; ++i) {
-        cd s = b[i];
-        for (int j = 0; j < i; ++j) s -= L[i][j] * y[j];
-        y[i] = s / L[i][i];
-    }
-    for (int i = 5; i >= 0; --i) {
-        cd s = y[i];
-        for (int j = i + 1; j < 6; ++j) s -= std::conj(L[j][i]) * x[j];
-        x[i] = s / std::conj(L[i][i]);
-    }
-}
-
-double det6(const double *A /* column-major */) {
-    double M[6][6];
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) M[i][j] = A[j * 6 + i];
-    double det = 1.0;
-    for (int k = 0; k < 6; ++k) {
-        int p = k;
-        for (int i = k + 1; i < 6; ++i)
-            if (std::fabs(M[i][k]) > std::fabs(M[p][k])) p = i;
-        if (M[p][k] == 0.0) return 0.0;
-        if (p != k) {
-            for (int j = 0; j < 6; ++j) std::swap(M[p][j], M[k][j]);
-            det = -det;
-        }
-        det *= M[k][k];
-        for (int i = k + 1; i < 6; ++i) {
-            const double f = M[i][k] / M[k][k];
-            for (int j = k; j < 6; ++j) M[i][j] -= f * M[k][j];
-        }
-    }
-    return det;
-}
-
-void matvec6(const double *A, const double *x, double *y) {  // column-major
-    for (int i = 0; i < 6; ++i) {
-        double s = 0;
-        for (int j = 0; j < 6; ++j) s += A[j * 6 + i] * x[j];
-        y[i] = s;
-    }
-}
-
-// Solves the batched normal equations.  out: 6 HJets (alpha, beta, gamma, tx, ty, tz), cast to float as
-// KinectFusionReconstruction.cpp:211 does.
-void solve_batched(const xs_kinfu *k, HJet out[6]) {
-    const int ncomp = k->ncomp;
-    const double *A0 = k->A.data(), *b0 = k->b.data();
-    cd Ac[36], bc[6], x0[6];
-    for (int i = 0; i < 36; ++i) Ac[i] = cd(A0[i], 0.0);
-    for (int i = 0; i < 6; ++i) bc[i] = cd(b0[i], 0.0);
-    llt_hermitian_solve6(Ac, bc, x0);  // zero-seed solve: the canonical real part
-    double xr[6];
-    for (int i = 0; i < 6; ++i) {
-        xr[i] = x0[i].real();
-        out[i] = HJet((float) xr[i]);
-    }
-    if (k->solve_mode == XS_SOLVE_EIGEN_LLT && k->comps == 1) {
-        // one Hermitian-LLT solve per direction with that direction's imaginary part, as the reference
-        // would do in its one-direction-per-run mode
-        for (int q = 0; q < ncomp; ++q) {
-            const double *Aq = A0 + (size_t) (1 + q) * 36, *bq = b0 + (size_t) (1 + q) * 6;
-            cd xq[6];
-            for (int i = 0; i < 36; ++i) Ac[i] = cd(A0[i], Aq[i]);
-            for (int i = 0; i < 6; ++i) bc[i] = cd(b0[i], bq[i]);
-            llt_hermitian_solve6(Ac, bc, xq);
-            for (int i = 0; i < 6; ++i) out[i].d[q] = (float) xq[i].imag();
-        }
-        return;
-    }
-    // analytic: x_q = A^-1 (b_q - A_q x); x_12 = A^-1 (b_12 - A_12 x - A_1 x_2 - A_2 x_1)
-    auto solve_real = [&](const double *rhs, double *x) {
-        cd r[6], s[6];
-        for (int i = 0; i < 36; ++i) Ac[i] = cd(A0[i], 0.0);
-        for (int i = 0; i < 6; ++i) r[i] = cd(rhs[i], 0.0);
-        llt_hermitian_solve6(Ac, r, s);
-        for (int i = 0; i < 6; ++i) x[i] = s[i].real();
-    };
-    auto first_order = [&](int q, double *xq) {
-        const double *Aq = A0 + (size_t) (1 + q) * 36, *bq = b0 + (size_t) (1 + q) * 6;
-        double t[6], rhs[6];
-        matvec6(Aq, xr, t);
-        for (int i = 0; i < 6; ++i) rhs[i] = bq[i] - t[i];
-        solve_real(rhs, xq);
-    };
-    if (k->comps == 1) {
-        for (int q = 0; q < ncomp; ++q) {
-            double xq[6];
-            first_order(q, xq);
-            for (int i = 0; i < 6; ++i) out[i].d[q] = (float) xq[i];
-        }
-    } else {
-        for (int d = 0; d < k->dirs; ++d) {
-            double x1[6], x2[6], x12[6], t[6], rhs[6];
-            first_order(3 * d, x1);
-            first_order(3 * d + 1, x2);
-            const double *A1 = A0 + (size_t) (1 + 3 * d) * 36, *A2 = A1 + 36, *A12 = A2 + 36;
-            const double *b12 = b0 + (size_t) (1 + 3 * d + 2) * 6;
-            for (int i = 0; i < 6; ++i) rhs[i] = b12[i];
-            matvec6(A12, xr, t);
-            for (int i = 0; i < 6; ++i) rhs[i] -= t[i];
-            matvec6(A1, x2, t);
-            for (int i = 0; i < 6; ++i) rhs[i] -= t[i];
-            matvec6(A2, x1, t);
-            for (int i = 0; i < 6; ++i) rhs[i] -= t[i];
-            solve_real(rhs, x12);
-            for (int i = 0; i < 6; ++i) {
-                out[i].d[3 * d] = (float) x1[i];
-                out[i].d[3 * d + 1] = (float) x2[i];
-                out[i].d[3 * d + 2] = (float) x12[i];
-            }
-        }
-    }
 }
 
 size_t map_floats(const xs_kinfu *k, int level, bool jets) {
@@ -299,8 +172,11 @@ xs_kinfu *xs_kinfu_create(const xs_config *cfg, int comps, int dirs, const float
     if (e == cudaSuccess) e = cudaMalloc((void **) &k->d_record, rec * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost((void **) &k->h_record, rec * sizeof(float));
     for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&k->ev[i]);
-    k->A.assign((size_t) (1 + k->ncomp) * 36, 0.0);
-    k->b.assign((size_t) (1 + k->ncomp) * 6, 0.0);
+    const size_t pose_floats = (size_t) (1 + k->ncomp) * 12;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc((void **) &k->d_pose[i], pose_floats * sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost((void **) &k->h_pose, pose_floats * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **) &k->d_status, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void **) &k->h_status, 2 * sizeof(int));
     if (e != cudaSuccess) {
         set_error(std::string("xs_kinfu_create: ") + cudaGetErrorString(e));
         xs_kinfu_destroy(k);
@@ -328,6 +204,13 @@ void xs_kinfu_destroy(xs_kinfu *k) {
     }
     cudaFree(k->d_record);
     cudaFreeHost(k->h_record);
+    cudaFree(k->d_pose[0]);
+    cudaFree(k->d_pose[1]);
+    cudaFreeHost(k->h_pose);
+    cudaFree(k->d_status);
+    cudaFreeHost(k->h_status);
+    cudaFree(k->d_icp_log);
+    cudaFreeHost(k->h_icp_log);
     for (int i = 0; i < 5; ++i)
         if (k->ev[i]) cudaEventDestroy(k->ev[i]);
     if (k->stream) cudaStreamDestroy(k->stream);
@@ -353,56 +236,89 @@ int xs_kinfu_surface_measure(xs_kinfu *k, const uint16_t *d_depth) {
 
 // AlignDepthToReconstruction (after SurfaceMeasure) + PoseEstimate, KinectFusionReconstruction.cpp:161-235.
 // Returns 1 when a pose was estimated, 0 on frame 0 or when the normal equations are degenerate.
+// The Gauss-Newton loop (levels 2..0 with 3, 4, 5 iterations, :186-192) is queued on the stream without any host
+// round trip: accumulation kernels + the device-side solve / pose update per iteration (icp.cu), one download of the
+// final pose (all derivative components) and the degeneracy flag at the end.
 int xs_kinfu_pose_estimate(xs_kinfu *k) {
     set_ctx(k);
     k->icp_iters_done = 0;
     k->icp_log.clear();
     if (k->frame_id == 0) return 0;
     const xs_config &c = k->cfg;
+    const int ncomp = k->ncomp;
     HMat4 c2w_prev = hinverse(k->record.back());
     HMat3 Rprev = hrotation(c2w_prev);
     HVec3 tprev = htranslation(c2w_prev);
     HMat3 Rprev_inv = hinverse(Rprev);
-    HMat3 Rcurr = Rprev;
-    HVec3 tcurr = tprev;
-    HMat4 c2w_curr = c2w_prev;
-    xs_pose prev_pose, curr_pose;
-    to_pose(Rprev_inv, tprev, k->ncomp, k->dR2, k->dt2, prev_pose);
-    const size_t stride = (size_t) (1 + k->ncomp) * 42;
+    xs_pose prev_pose;
+    to_pose(Rprev_inv, tprev, ncomp, k->dR2, k->dt2, prev_pose);
+    // initial estimate = previous pose (:182-185)
+    const size_t pose_floats = (size_t) (1 + ncomp) * 12;
+    for (int q = 0; q <= ncomp; ++q) {
+        float *h = k->h_pose + (size_t) q * 12;
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) h[i * 3 + j] = q == 0 ? Rprev.m[i][j].v : Rprev.m[i][j].d[q - 1];
+            h[9 + i] = q == 0 ? tprev.v[i].v : tprev.v[i].d[q - 1];
+        }
+    }
+    KCUDA(cudaMemcpyAsync(k->d_pose[0], k->h_pose, pose_floats * sizeof(float), cudaMemcpyHostToDevice, k->stream));
+    KCUDA(cudaMemsetAsync(k->d_status, 0, 2 * sizeof(int), k->stream));
+    const size_t log_stride = (size_t) 27 * (1 + ncomp);
+    if (k->log_icp && !k->d_icp_log) {
+        KCUDA(cudaMalloc((void **) &k->d_icp_log, 16 * log_stride * sizeof(double)));
+        KCUDA(cudaMallocHost((void **) &k->h_icp_log, 16 * log_stride * sizeof(double)));
+    }
+    int it = 0;
     for (int level = c.num_levels - 1; level >= 0; --level) {
         const int rows = c.height >> level, cols = c.width >> level;
-        for (int iter = 0; iter < k->icp_iterations[level]; ++iter) {
-            to_pose(Rcurr, tcurr, k->ncomp, k->dR, k->dt, curr_pose);
-            int rc = xs_estimate_combined(&curr_pose, k->vmaps_curr[level], k->nmaps_curr[level], &prev_pose,
-                                          level_intr(k->intr, level), k->vmaps_prev[level], k->nmaps_prev[level], rows,
-                                          cols, k->comps, k->dirs, c.dist_thres, k->angle_thres, k->A.data(),
-                                          k->b.data(), k->stream);
+        for (int iter = 0; iter < k->icp_iterations[level]; ++iter, ++it) {
+            int rc = icp_accumulate_async(k->d_pose[it & 1], k->vmaps_curr[level], k->nmaps_curr[level], &prev_pose,
+                                          level_intr(k->intr, level), k->vmaps_prev[level], k->nmaps_prev[level], rows, cols,
+                                          k->comps, k->dirs, c.dist_thres, k->angle_thres, k->stream);
+            if (rc == XS_OK)
+                rc = icp_solve_async(k->d_pose[it & 1], k->d_pose[(it + 1) & 1], k->comps, k->dirs, k->solve_mode, k->d_status,
+                                     k->log_icp && it < 16 ? k->d_icp_log + (size_t) it * log_stride : nullptr, k->stream);
             if (rc != XS_OK) return 0;
-            const size_t at = k->icp_log.size();
-            k->icp_log.resize(at + stride);
-            for (int q = 0; q <= k->ncomp; ++q) {
-                std::memcpy(&k->icp_log[at + (size_t) q * 42], &k->A[(size_t) q * 36], 36 * sizeof(double));
-                std::memcpy(&k->icp_log[at + (size_t) q * 42 + 36], &k->b[(size_t) q * 6], 6 * sizeof(double));
-            }
-            ++k->icp_iters_done;
-            const double det = det6(k->A.data());  // A.real().determinant(), :203
-            if (std::fabs(det) < 1e-15 || std::isnan(det)) {
-                set_error(std::isnan(det) ? "qnan det" : "eps det");
-                return 0;
-            }
-            HJet x[6];
-            solve_batched(k, x);
-            // Rinc = Rz(gamma) * Ry(beta) * Rx(alpha), :212-218
-            HMat3 Rinc = hmul(hmul(haxis_rotation(x[2], 2), haxis_rotation(x[1], 1)), haxis_rotation(x[0], 0));
-            HVec3 t = hmul(Rinc, tcurr);
-            for (int i = 0; i < 3; ++i) tcurr.v[i] = t.v[i] + x[3 + i];
-            Rcurr = hmul(Rinc, Rcurr);
-            for (int i = 0; i < 3; ++i) {
-                for (int j = 0; j < 3; ++j) c2w_curr.m[i][j] = Rcurr.m[i][j];
-                c2w_curr.m[i][3] = tcurr.v[i];
-            }
-            c2w_curr.m[3][3] = HJet(1.f);
         }
+    }
+    KCUDA(cudaMemcpyAsync(k->h_pose, k->d_pose[it & 1], pose_floats * sizeof(float), cudaMemcpyDeviceToHost, k->stream));
+    KCUDA(cudaMemcpyAsync(k->h_status, k->d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, k->stream));
+    if (k->log_icp)
+        KCUDA(cudaMemcpyAsync(k->h_icp_log, k->d_icp_log, (size_t) (it < 16 ? it : 16) * log_stride * sizeof(double),
+                              cudaMemcpyDeviceToHost, k->stream));
+    KCUDA(cudaStreamSynchronize(k->stream));
+    k->icp_iters_done = it;
+    if (k->log_icp) {  // repack the 27 sums per component into A (36, column-major) + b (6), ICP.cu:419-428
+        const int n = it < 16 ? it : 16;
+        k->icp_log.assign((size_t) n * (1 + ncomp) * 42, 0.0);
+        for (int i = 0; i < n; ++i)
+            for (int q = 0; q <= ncomp; ++q) {
+                const double *v = k->h_icp_log + (size_t) i * log_stride + (size_t) q * 27;
+                double *A = &k->icp_log[((size_t) i * (1 + ncomp) + q) * 42], *b = A + 36;
+                int shift = 0;
+                for (int r = 0; r < 6; ++r)
+                    for (int cc = r; cc < 7; ++cc) {
+                        const double val = v[shift++];
+                        if (cc == 6)
+                            b[r] = val;
+                        else
+                            A[cc * 6 + r] = A[r * 6 + cc] = val;
+                    }
+            }
+    }
+    const int status = k->h_status[0] != 0 ? k->h_status[0] : k->h_status[1];
+    if (status != 0) {  // A.real().determinant() guard, :203-210
+        set_error(status == 2 ? "qnan det" : "eps det");
+        return 0;
+    }
+    HMat4 c2w_curr = HMat4::identity();
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            c2w_curr.m[i][j].v = k->h_pose[i * 3 + j];
+            for (int q = 0; q < ncomp; ++q) c2w_curr.m[i][j].d[q] = k->h_pose[(size_t) (1 + q) * 12 + i * 3 + j];
+        }
+        c2w_curr.m[i][3].v = k->h_pose[9 + i];
+        for (int q = 0; q < ncomp; ++q) c2w_curr.m[i][3].d[q] = k->h_pose[(size_t) (1 + q) * 12 + 9 + i];
     }
     k->world2camera = hinverse(c2w_curr);  // :231
     k->record.push_back(k->world2camera);
@@ -547,6 +463,12 @@ int xs_kinfu_take_icp_log(xs_kinfu *k, double *out, int max_iters) {
     if (out) std::memcpy(out, k->icp_log.data(), (size_t) n * stride * sizeof(double));
     k->icp_log.clear();
     return n;
+}
+
+int xs_kinfu_enable_icp_log(xs_kinfu *k, int on) {
+    if (!k) return XS_ERR_ARG;
+    k->log_icp = on != 0;
+    return XS_OK;
 }
 
 int xs_kinfu_get_stats(const xs_kinfu *k, unsigned long long *out4) {

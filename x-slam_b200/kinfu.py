@@ -197,6 +197,10 @@ class KinectFusionReconstruction:
         check(self.lib.xs_kinfu_get_algorithmic_bytes(self.h, out))
         return dict(zip(("surface", "icp", "integrate", "raycast"), [float(x) for x in out]))
 
+    def enable_icp_log(self, on=True):
+        """The per-iteration normal equations stay on the device unless the log is enabled."""
+        check(self.lib.xs_kinfu_enable_icp_log(self.h, 1 if on else 0))
+
     def icp_log(self, max_iters=16):
         buf = np.zeros((max_iters, 1 + self.ncomp, 42), np.float64)
         n = self.lib.xs_kinfu_take_icp_log(self.h, buf.ctypes.data_as(C.POINTER(C.c_double)), max_iters)
