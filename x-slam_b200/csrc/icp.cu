@@ -382,70 +382,147 @@ XS_DEV void unpack_sums(const double *v, double (&A)[6][6], double (&b)[6]) {
         }
 }
 
-// A.real().determinant() (KinectFusionReconstruction.cpp:203): Gaussian elimination with partial pivoting
+// A.real().determinant() (KinectFusionReconstruction.cpp:203): Gaussian elimination with partial pivoting.  All loops
+// are fully unrolled with static row indices (the pivot is bubbled into row k by predicated swaps) so the matrix
+// lives in registers.
 XS_DEV double det6_dev(const double (&A)[6][6]) {
     double M[6][6];
+#pragma unroll
     for (int i = 0; i < 6; ++i)
+#pragma unroll
         for (int j = 0; j < 6; ++j) M[i][j] = A[i][j];
     double det = 1.0;
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
-        int p = k;
-        for (int i = k + 1; i < 6; ++i)
-            if (fabs(M[i][k]) > fabs(M[p][k])) p = i;
-        if (M[p][k] == 0.0) return 0.0;
-        if (p != k) {
-            for (int j = 0; j < 6; ++j) {
-                const double t = M[p][j];
-                M[p][j] = M[k][j];
-                M[k][j] = t;
-            }
-            det = -det;
-        }
-        det *= M[k][k];
+#pragma unroll
         for (int i = k + 1; i < 6; ++i) {
-            const double f = M[i][k] / M[k][k];
-            for (int j = k; j < 6; ++j) M[i][j] -= f * M[k][j];
+            if (fabs(M[i][k]) > fabs(M[k][k])) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const double t = M[i][j];
+                    M[i][j] = M[k][j];
+                    M[k][j] = t;
+                }
+                det = -det;
+            }
+        }
+        if (M[k][k] == 0.0) return 0.0;
+        det *= M[k][k];
+        const double inv = 1.0 / M[k][k];
+#pragma unroll
+        for (int i = k + 1; i < 6; ++i) {
+            const double f = M[i][k] * inv;
+#pragma unroll
+            for (int j = k + 1; j < 6; ++j) M[i][j] -= f * M[k][j];
         }
     }
     return det;
 }
 
-// Eigen 3.4 LLT<Matrix<complex<double>,6,6>,Lower>::solve (unblocked, n < 32): the factor is built from the LOWER
-// triangle with real(A_kk) on the diagonal and conj() in the updates, i.e. the complex-symmetric A of ICP.cu:427 is
-// treated as Hermitian (KinectFusionReconstruction.cpp:211).  Ai / bi = imaginary parts (may be null).
-XS_DEV void llt_hermitian_solve6_dev(const double (&Ar)[6][6], const double (*Ai)[6], const double (&br)[6], const double *bi,
-                                     cplx (&x)[6]) {
-    cplx L[6][6];
+// Real Cholesky factor of the lower triangle of A as Eigen's unblocked LLT computes it (KinectFusionReconstruction.cpp:
+// 211; with zero imaginary parts the Hermitian factorisation of SURVEY.md 0.6 is the real one).  L holds the factor,
+// Linv the reciprocals of its diagonal.  A non-positive pivot stops the factorisation like Eigen does.
+struct Chol6 {
+    double L[6][6];
+    double inv[6];
+};
+XS_DEV void chol6_factor(const double (&A)[6][6], Chol6 &F) {
+#pragma unroll
     for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < 6; ++j) L[i][j] = {Ar[i][j], Ai ? Ai[i][j] : 0.0};
+#pragma unroll
+        for (int j = 0; j < 6; ++j) F.L[i][j] = A[i][j];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) F.inv[k] = 1.0 / A[k][k];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double xk = F.L[k][k];
+#pragma unroll
+        for (int j = 0; j < k; ++j) xk -= F.L[k][j] * F.L[k][j];
+        ok = ok && xk > 0.0;
+        if (ok) {
+            const double r = rsqrt(xk);
+            F.L[k][k] = xk * r;
+            F.inv[k] = r;
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) {
+                double sacc = F.L[i][k];
+#pragma unroll
+                for (int j = 0; j < k; ++j) sacc -= F.L[i][j] * F.L[k][j];
+                F.L[i][k] = sacc * r;
+            }
+        }
+    }
+}
+XS_DEV void chol6_solve(const Chol6 &F, const double (&b)[6], double (&x)[6]) {
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double sacc = b[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) sacc -= F.L[i][j] * y[j];
+        y[i] = sacc * F.inv[i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double sacc = y[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) sacc -= F.L[j][i] * x[j];
+        x[i] = sacc * F.inv[i];
+    }
+}
+
+// Eigen 3.4 LLT<Matrix<complex<double>,6,6>,Lower>::solve (unblocked, n < 32) with a non-zero imaginary part: the
+// factor is built from the LOWER triangle with real(A_kk) on the diagonal and conj() in the updates, i.e. the
+// complex-symmetric A of ICP.cu:427 is treated as Hermitian (KinectFusionReconstruction.cpp:211).
+XS_DEV void llt_hermitian_solve6_dev(const double (&Ar)[6][6], const double (&Ai)[6][6], const double (&br)[6],
+                                     const double (&bi)[6], cplx (&x)[6]) {
+    cplx L[6][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) L[i][j] = {Ar[i][j], Ai[i][j]};
+    bool ok = true;
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
         double xk = L[k][k].re;
+#pragma unroll
         for (int j = 0; j < k; ++j) xk -= L[k][j].re * L[k][j].re + L[k][j].im * L[k][j].im;
-        if (xk <= 0.0) break;
-        xk = sqrt(xk);
-        L[k][k] = {xk, 0.0};
-        for (int i = k + 1; i < 6; ++i) {
-            cplx sacc = L[i][k];
-            for (int j = 0; j < k; ++j) sacc = csub(sacc, cmul(L[i][j], cconj(L[k][j])));
-            L[i][k] = {sacc.re / xk, sacc.im / xk};
+        ok = ok && xk > 0.0;
+        if (ok) {
+            const double r = rsqrt(xk);
+            L[k][k] = {xk * r, 0.0};
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) {
+                cplx sacc = L[i][k];
+#pragma unroll
+                for (int j = 0; j < k; ++j) sacc = csub(sacc, cmul(L[i][j], cconj(L[k][j])));
+                L[i][k] = {sacc.re * r, sacc.im * r};
+            }
         }
     }
     cplx y[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
-        cplx sacc = {br[i], bi ? bi[i] : 0.0};
+        cplx sacc = {br[i], bi[i]};
+#pragma unroll
         for (int j = 0; j < i; ++j) sacc = csub(sacc, cmul(L[i][j], y[j]));
         y[i] = cdiv(sacc, L[i][i]);
     }
+#pragma unroll
     for (int i = 5; i >= 0; --i) {
         cplx sacc = y[i];
+#pragma unroll
         for (int j = i + 1; j < 6; ++j) sacc = csub(sacc, cmul(cconj(L[j][i]), x[j]));
         x[i] = cdiv(sacc, cconj(L[i][i]));
     }
 }
 
 XS_DEV void matvec6_dev(const double (&A)[6][6], const double (&x)[6], double (&y)[6]) {
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
         double sacc = 0;
+#pragma unroll
         for (int j = 0; j < 6; ++j) sacc += A[i][j] * x[j];
         y[i] = sacc;
     }
@@ -521,14 +598,13 @@ template <int C> __global__ void __launch_bounds__(64) icp_solve_kernel(const So
         if (q == 0) P.status[1] = isnan(det) ? 2 : 1;
         return;
     }
-    cplx x0[6];
-    llt_hermitian_solve6_dev(A, nullptr, b, nullptr, x0);  // zero-seed solve: the canonical real part
+    Chol6 F;
+    chol6_factor(A, F);
     double xr[6];
+    chol6_solve(F, b, xr);  // zero-seed solve: the canonical real part
     J x[6];
-    for (int i = 0; i < 6; ++i) {
-        xr[i] = x0[i].re;
-        x[i] = jconst<C, 1>((float) xr[i]);
-    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = jconst<C, 1>((float) xr[i]);
     const bool has_dir = q < P.dirs;
     if (has_dir) {
         if (C == 1 && P.solve_mode == XS_SOLVE_EIGEN_LLT) {
@@ -542,15 +618,12 @@ template <int C> __global__ void __launch_bounds__(64) icp_solve_kernel(const So
             // analytic: x_a = A^-1 (b_a - A_a x);  x_12 = A^-1 (b_12 - A_12 x - A_1 x_2 - A_2 x_1)
             double xa[3][6];
 #pragma unroll
-            for (int a = 0; a < C; ++a) {
-                if (a == 2) continue;
+            for (int a = 0; a < (C == 3 ? 2 : 1); ++a) {
                 double Aa[6][6], ba[6], t[6], rhs[6];
                 unpack_sums(P.sums + (size_t) (1 + q * C + a) * 27, Aa, ba);
                 matvec6_dev(Aa, xr, t);
                 for (int i = 0; i < 6; ++i) rhs[i] = ba[i] - t[i];
-                cplx xs_[6];
-                llt_hermitian_solve6_dev(A, nullptr, rhs, nullptr, xs_);
-                for (int i = 0; i < 6; ++i) xa[a][i] = xs_[i].re;
+                chol6_solve(F, rhs, xa[a]);
             }
             if (C == 3) {
                 double A1[6][6], A2[6][6], A12[6][6], b1[6], b2[6], b12[6], t[6], rhs[6];
@@ -564,9 +637,7 @@ template <int C> __global__ void __launch_bounds__(64) icp_solve_kernel(const So
                 for (int i = 0; i < 6; ++i) rhs[i] -= t[i];
                 matvec6_dev(A2, xa[0], t);
                 for (int i = 0; i < 6; ++i) rhs[i] -= t[i];
-                cplx xs_[6];
-                llt_hermitian_solve6_dev(A, nullptr, rhs, nullptr, xs_);
-                for (int i = 0; i < 6; ++i) xa[2][i] = xs_[i].re;
+                chol6_solve(F, rhs, xa[2]);
             }
             for (int i = 0; i < 6; ++i)
 #pragma unroll
