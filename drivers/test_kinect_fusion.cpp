@@ -1,0 +1,222 @@
+// test_kinect_fusion — the YAML-driven frame-loop driver, mirroring Experiments/test_xkinect_fusion/main.cpp:16-84:
+// config -> dataset -> loop { upload depth, time ProcessFrame, log slam / gt poses, optional point cloud } ->
+// "mean frame time".  Host C++ over the C-ABI of libxslam_b200.so (include/xslam_b200.h); no CPU fallback.
+//
+// Differences from the reference driver, all stated:
+//  * dataset_format "synthetic" (analytic-SDF room + closed-form trajectory, xs_synth_depth / xs_synth_pose) replaces
+//    the ICL-NUIM / 7-Scenes PNG readers (Dataset.cpp), which need files and OpenCV that do not exist offline;
+//  * csfd_mode (none | gradient | hessian) seeds k perturbation directions on world2camera — the batched form of the
+//    commented seeding line KinectFusionReconstruction.cpp:22 — and log_pose_derivatives writes, next to every
+//    frame-%06d.pose.txt, frame-%06d.dpose.txt with one row of 16 values per derivative component (d world2camera
+//    / d theta, i.e. the stored h-scaled component divided by h, or by h^2 for eps1eps2);
+//  * when frame alignment fails the driver stops (the reference spins forever).
+#include "../include/xslam_b200.h"
+#include "flat_yaml.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <iomanip>
+#include <vector>
+
+int xs_driver_device_alloc(float **p, size_t floats);
+int xs_driver_device_download(float *dst, const float *src, size_t floats);
+void xs_driver_device_free(float *p);
+
+static const float H_ = 1e-7f;  // Internal.h:33
+
+// savePose, main.cpp:8-14
+static void savePose(const std::string &output_dir, int frame_id, const float *pose16) {
+    std::stringstream ss;
+    ss << "frame-" << std::setw(6) << std::setfill('0') << frame_id << ".pose.txt";
+    xs_save_pose_txt((output_dir + ss.str()).c_str(), pose16);
+}
+
+static void mul4(const float *a, const float *b, float *c) {
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            float s = 0;
+            for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+            c[i * 4 + j] = s;
+        }
+}
+static void rigid_inverse(const float *m, float *o) {
+    std::memset(o, 0, 16 * sizeof(float));
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) o[i * 4 + j] = m[j * 4 + i];
+    for (int i = 0; i < 3; ++i) o[i * 4 + 3] = -(o[i * 4] * m[3] + o[i * 4 + 1] * m[7] + o[i * 4 + 2] * m[11]);
+    o[15] = 1.f;
+}
+static void print4(const char *name, const float *m) {
+    std::cout << name << ":\n";
+    for (int i = 0; i < 4; ++i) std::cout << " " << m[i * 4] << " " << m[i * 4 + 1] << " " << m[i * 4 + 2] << " " << m[i * 4 + 3] << "\n";
+}
+
+// se3Exp generators (KinectFusionReconstruction.h:176-219, xi = [v; omega]) as row-major 4x4
+static void generator(int i, float *G) {
+    std::memset(G, 0, 16 * sizeof(float));
+    if (i < 3) G[i * 4 + 3] = 1.f;
+    if (i == 3) G[1 * 4 + 2] = -1.f, G[2 * 4 + 1] = 1.f;
+    if (i == 4) G[0 * 4 + 2] = 1.f, G[2 * 4 + 0] = -1.f;
+    if (i == 5) G[0 * 4 + 1] = -1.f, G[1 * 4 + 0] = 1.f;
+}
+
+int main(int argc, char *argv[]) {
+    std::cout << "Demo of XKinectFusion" << std::endl;
+    if (argc < 2) {
+        std::cout << "please enter the config file name\n";
+        return -1;
+    }
+    FlatYaml config(argv[1]);
+    const std::string dataset_format = config.str("dataset_format");
+    const int start_frame = config.i("start_frame"), end_frame = config.i("end_frame");
+    std::string output_path = config.str("output_dir");
+    if (argc > 2) output_path = argv[2];
+    if (!output_path.empty() && output_path.back() != '/') output_path += '/';
+    if (dataset_format != "synthetic") {
+        std::cerr << "dataset_format '" << dataset_format << "': only the synthetic source is built (no datasets offline; "
+                  << "the ICL / 7-Scenes readers are a next row, DESIGN.md 7)\n";
+        return -1;
+    }
+    std::cout << "frame num: " << end_frame - start_frame << std::endl;
+    std::cout << "initialize kinect fusion......" << std::endl;
+    // KinectFusionReconstruction::SetYamlParameters, KinectFusionReconstruction.cpp:12-72
+    xs_config cfg;
+    cfg.res[0] = config.i("tsdf_size_x"), cfg.res[1] = config.i("tsdf_size_y"), cfg.res[2] = config.i("tsdf_size_z");
+    cfg.voxel_size = config.f("tsdf_voxel_size");
+    cfg.max_weight = config.i("max_integration_weight");
+    cfg.thres_range = config.f("thres_range");
+    cfg.init_xyz[0] = config.f("init_x"), cfg.init_xyz[1] = config.f("init_y"), cfg.init_xyz[2] = config.f("init_z");
+    cfg.r_deg[0] = config.f("r_x"), cfg.r_deg[1] = config.f("r_y"), cfg.r_deg[2] = config.f("r_z");
+    cfg.width = config.i("depth_width"), cfg.height = config.i("depth_height");
+    cfg.fx = config.f("fx"), cfg.fy = config.f("fy"), cfg.cx = config.f("cx"), cfg.cy = config.f("cy");
+    cfg.num_levels = config.i("num_levels");
+    if (cfg.num_levels > 3) std::cout << "sorry, the max supported multi-level = 3" << std::endl;
+    cfg.dist_thres = config.f("distThres");
+    cfg.angle_thres_deg = config.f("angleThres");
+    cfg.bi_threshold = config.f("biInterpolate_threshold");
+    cfg.trunc_k = config.f("trunc_logistic_k");
+    const xs_intr intr = {cfg.fx, cfg.fy, cfg.cx, cfg.cy};
+
+    // perturbation directions
+    const std::string mode = config.str("csfd_mode", "none");
+    int comps = 1, dirs = 0;
+    std::vector<float> seeds;
+    if (mode == "gradient") {
+        comps = 1, dirs = 6;
+        seeds.assign((size_t) dirs * 16, 0.f);
+        for (int i = 0; i < 6; ++i) {
+            float G[16];
+            generator(i, G);
+            for (int e = 0; e < 16; ++e) seeds[(size_t) i * 16 + e] = H_ * G[e];
+        }
+    } else if (mode == "hessian") {
+        comps = 3, dirs = 21;
+        seeds.assign((size_t) dirs * 3 * 16, 0.f);
+        int k = 0;
+        for (int i = 0; i < 6; ++i)
+            for (int j = i; j < 6; ++j, ++k) {
+                float Gi[16], Gj[16], GiGj[16], GjGi[16];
+                generator(i, Gi), generator(j, Gj);
+                mul4(Gi, Gj, GiGj), mul4(Gj, Gi, GjGi);
+                for (int e = 0; e < 16; ++e) {
+                    seeds[((size_t) k * 3 + 0) * 16 + e] = H_ * Gi[e];
+                    seeds[((size_t) k * 3 + 1) * 16 + e] = H_ * Gj[e];
+                    seeds[((size_t) k * 3 + 2) * 16 + e] = H_ * H_ * 0.5f * (GiGj[e] + GjGi[e]);
+                }
+            }
+    } else if (mode != "none") {
+        std::cerr << "csfd_mode must be none, gradient or hessian\n";
+        return -1;
+    }
+    xs_kinfu *kinfu = xs_kinfu_create(&cfg, comps, dirs, seeds.empty() ? nullptr : seeds.data(),
+                                      comps == 1 ? XS_SOLVE_EIGEN_LLT : XS_SOLVE_ANALYTIC);
+    if (!kinfu) {
+        std::cerr << "initialisation failed: " << xs_last_error() << "\n";
+        return -1;
+    }
+    const bool log_slam = config.b("log_slam_pose"), log_gt = config.b("log_gt_pose"), draw_pcd = config.b("draw_pcd");
+    const bool log_deriv = config.b("log_pose_derivatives", false) && dirs > 0;
+    const int ncomp = comps * dirs;
+    double total_time = 0;
+    std::cout << "start slam!" << std::endl;
+    std::vector<uint16_t> depth((size_t) cfg.width * cfg.height);
+    std::vector<float> w2c((size_t) (1 + ncomp) * 16);
+    float gt0_inv[16];
+    {
+        float gt0[16];
+        xs_synth_pose(start_frame, gt0);
+        rigid_inverse(gt0, gt0_inv);
+    }
+    std::vector<float> pts, nrm;
+    while (xs_kinfu_frame_id(kinfu) < end_frame - start_frame) {
+        const int frame_id = xs_kinfu_frame_id(kinfu);
+        std::cout << "current frame is " << frame_id << "\n";
+        float gt_pose[16];
+        xs_synth_pose(start_frame + frame_id, gt_pose);
+        xs_synth_depth(gt_pose, intr, cfg.height, cfg.width, depth.data());
+        // c. process kinect fusion (timed like main.cpp:57-60; the upload of the frame is inside ProcessFrame here)
+        const auto t0 = std::chrono::steady_clock::now();
+        const int ok = xs_kinfu_process_frame(kinfu, depth.data(), 0);
+        const double frame_time = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (!ok) {
+            std::cerr << "Frame align failed! (" << xs_last_error() << ")\n";
+            break;
+        }
+        total_time += frame_time;
+        float pose_c2w[16];
+        xs_kinfu_get_pose_c2w(kinfu, pose_c2w);
+        if (log_slam) {
+            std::filesystem::create_directories(output_path + "slam/");
+            print4("slam c2w", pose_c2w);
+            savePose(output_path + "slam/", frame_id, pose_c2w);
+        }
+        if (log_gt) {
+            std::filesystem::create_directories(output_path + "gt/");
+            float gt_c2w[16];
+            mul4(gt0_inv, gt_pose, gt_c2w);  // dataset.getPose(0).inverse() * dataset.getPose(frame_id), main.cpp:72
+            print4("gt c2w", gt_c2w);
+            savePose(output_path + "gt/", frame_id, gt_c2w);
+        }
+        if (log_deriv) {
+            std::filesystem::create_directories(output_path + "slam/");
+            xs_kinfu_get_world2camera(kinfu, w2c.data());
+            std::stringstream ss;
+            ss << output_path << "slam/frame-" << std::setw(6) << std::setfill('0') << frame_id << ".dpose.txt";
+            std::ofstream out(ss.str());
+            for (int q = 0; q < ncomp; ++q) {
+                const double scale = (comps == 3 && q % 3 == 2) ? 1.0 / ((double) H_ * H_) : 1.0 / H_;
+                for (int e = 0; e < 16; ++e) out << std::setprecision(7) << std::scientific << w2c[(size_t) (1 + q) * 16 + e] * scale << " ";
+                out << "\n";
+            }
+        }
+        if (draw_pcd && frame_id == end_frame - start_frame - 1) {
+            // ExportPointCloud(1000000) + exportPly on the last frame, main.cpp:76-81 / KinectFusionReconstruction.cpp:334-372
+            const long max_buffer = 1000000;
+            float *d_pts = nullptr, *d_nrm = nullptr;
+            if (xs_driver_device_alloc(&d_pts, 3 * max_buffer) || xs_driver_device_alloc(&d_nrm, 3 * max_buffer)) {
+                std::cerr << "point-cloud buffers: out of device memory\n";
+                return -1;
+            }
+            const long n = xs_extract_points(xs_kinfu_volume(kinfu), d_pts, d_nrm, max_buffer, nullptr);
+            if (n < 0) {
+                std::cerr << "ExportPointCloud failed: " << xs_last_error() << "\n";
+                return -1;
+            }
+            pts.resize((size_t) 3 * n), nrm.resize((size_t) 3 * n);
+            xs_driver_device_download(pts.data(), d_pts, (size_t) 3 * n);
+            xs_driver_device_download(nrm.data(), d_nrm, (size_t) 3 * n);
+            xs_driver_device_free(d_pts), xs_driver_device_free(d_nrm);
+            xs_export_ply((output_path + "pcd.ply").c_str(), pts.data(), nrm.data(), n);
+            std::cout << "point cloud: " << n << " points -> " << output_path << "pcd.ply\n";
+        }
+    }
+    const int frames = xs_kinfu_frame_id(kinfu);
+    printf("mean frame time = %.3f ms\n", total_time / (frames > 0 ? frames : 1));
+    xs_kinfu_destroy(kinfu);
+    return 0;
+}

@@ -84,6 +84,16 @@ int xs_create_nmap(const float *d_vmap, int rows, int cols, float *d_nmap, void 
 int xs_resize_vmap(const float *d_in, int rows, int cols, int comps, int dirs, float *d_out, void *stream);
 int xs_resize_nmap(const float *d_in, int rows, int cols, int comps, int dirs, float *d_out, void *stream);
 
+/* Seam layout <-> packed SoA (a4).  The reference's MapArr is a pitched DeviceArray2D<devComplex> (interleaved re, im;
+ * Internal.h:31) with `nplanes` planes stacked by rows (3 for vertex / normal maps, 1 for depth).  Component 0 of the
+ * SoA map [(1+ncomp)][nplanes][rows][cols] is the real part; the imaginary part maps to derivative component `comp`
+ * (comp < 0: dropped on import / written as zero on export).  These are what the C++ wrappers with the reference's
+ * signatures (include/xslam_b200.hpp) use at the boundary. */
+int xs_map_complex_to_soa(const void *d_src, size_t step_bytes, int nplanes, int rows, int cols, float *d_soa, int ncomp,
+                          int comp, void *stream);
+int xs_map_soa_to_complex(const float *d_soa, int ncomp, int comp, int nplanes, int rows, int cols, void *d_dst,
+                          size_t step_bytes, void *stream);
+
 /* ---------------------------------------------------------------- TSDF volume (a9, a11) */
 typedef struct xs_volume xs_volume;
 /* TsdfVolume::TsdfVolume, TsdfVolume.cpp:11-29 (trunc = max(voxel*thres_range, 2.1*voxel)); res multiple of 8 */
@@ -189,6 +199,8 @@ int xs_kinfu_get_algorithmic_bytes(const xs_kinfu *k, double *out4);
 /* device pointer where the per-frame derivative record (world2camera, all components) is kept,
  * laid out [(1+ncomp)][16] floats — the buffer the multi-GPU layer all-gathers. */
 float *xs_kinfu_pose_record_device(xs_kinfu *k);
+/* the cudaStream_t every kernel of this pipeline object is launched on (for event timing and stream-ordered consumers) */
+void *xs_kinfu_stream(xs_kinfu *k);
 
 /* ---------------------------------------------------------------- outputs & synthetic input (a13, f1) */
 /* saveTxtMatrix, IOHelper.cpp:21-32 */

@@ -1,0 +1,232 @@
+// xslam_b200.hpp — C++ wrappers with the REFERENCE's operator signatures over the C-ABI of libxslam_b200.so.
+//
+// The reference's seam is the set of free functions declared in XKinectFusion/include/{Map,TsdfFusion,RayCaster,ICP}.h
+// (aggregated by CudaFunctions.h:4-8) and called only from KinectFusionReconstruction.cpp.  A maintainer switches the
+// frame loop to this library by including this header instead of CudaFunctions.h and adding
+// `using namespace xslam_b200::seam;` — the calls in KinectFusionReconstruction.cpp then compile unchanged
+// (INTEGRATION.md shows the diff).  The wrappers are templates over the reference's own container / POD types
+// (DeviceArray2D<T>, PtrStep<T>, PtrStepSz<T>, Intr, MatS33, devComplex3 — Internal.h, device_array.hpp,
+// kernel_containers.hpp), so this header does not include any reference header; oracle/hpp_check.cu instantiates
+// every wrapper with the real reference types as a compile check.
+//
+// Layout at the seam: maps are pitched interleaved complex<float>, three planes stacked by rows;
+// volumes are three pitched (Y*Z) x X planes.  Behind the seam everything is packed SoA / brick-tiled, so each
+// wrapper converts at the boundary (xs_map_complex_to_soa / xs_map_soa_to_complex, xs_volume_import/export_planes).
+// One perturbation direction is carried — the reference's imaginary part — i.e. comps = 1, dirs = 1.  Code that wants
+// k directions per pass uses the C-ABI (or xs_kinfu) directly.  Errors follow the reference: print and exit(-1)
+// (cudaSafeCall, Common/include/cx.h:124-130).
+#pragma once
+#include "xslam_b200.h"
+
+#include <cuda_runtime_api.h>
+
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+
+namespace xslam_b200 {
+
+inline void check(int rc, const char *what) {
+    if (rc < 0) {
+        std::fprintf(stderr, "CUDA error(%s): %s\n", what, xs_last_error());
+        std::exit(-1);
+    }
+}
+
+// scratch SoA buffers, grown on demand and reused (the caller owns every seam buffer; these are library-side temporaries)
+struct Scratch {
+    float *p = nullptr;
+    size_t cap = 0;
+    float *get(size_t floats) {
+        if (floats > cap) {
+            cudaFree(p);
+            if (cudaMalloc((void **) &p, floats * sizeof(float)) != cudaSuccess) check(XS_ERR_CUDA, "scratch");
+            cap = floats;
+        }
+        return p;
+    }
+};
+inline Scratch &scratch(int slot) {
+    static Scratch s[8];
+    return s[slot];
+}
+
+template <class IntrT> inline xs_intr to_intr(const IntrT &k) { return xs_intr{k.fx, k.fy, k.cx, k.cy}; }
+
+// MatS33 (Internal.h:146-148: data[3] rows of devComplex3) + devComplex3 -> xs_pose with one derivative component
+struct PoseHolder {
+    xs_pose p;
+    float dR[9], dt[3];
+    template <class Mat, class Vec> PoseHolder(const Mat &R, const Vec &t) {
+        const auto *rows = R.data;
+        for (int i = 0; i < 3; ++i) {
+            const std::complex<float> e[3] = {{rows[i].x.real(), rows[i].x.imag()}, {rows[i].y.real(), rows[i].y.imag()}, {rows[i].z.real(), rows[i].z.imag()}};
+            for (int j = 0; j < 3; ++j) {
+                p.R[i * 3 + j] = e[j].real();
+                dR[i * 3 + j] = e[j].imag();
+            }
+        }
+        p.t[0] = t.x.real(), p.t[1] = t.y.real(), p.t[2] = t.z.real();
+        dt[0] = t.x.imag(), dt[1] = t.y.imag(), dt[2] = t.z.imag();
+        p.ncomp = 1;
+        p.dR = dR;
+        p.dt = dt;
+    }
+};
+
+// import a seam map ([nplanes*rows] x cols interleaved complex) into scratch slot `slot` as SoA [(1+ncomp)][nplanes][rows][cols]
+template <class MapT> inline float *import_map(const MapT &m, int nplanes, int ncomp, int slot) {
+    const int rows = m.rows() / nplanes, cols = m.cols();
+    float *soa = scratch(slot).get((size_t) (1 + ncomp) * nplanes * rows * cols);
+    check(xs_map_complex_to_soa(m.ptr(), m.step(), nplanes, rows, cols, soa, ncomp, ncomp ? 0 : -1, nullptr), "import_map");
+    return soa;
+}
+template <class MapT> inline void export_map(const float *soa, int ncomp, int nplanes, int rows, int cols, MapT &m) {
+    m.create(nplanes * rows, cols);
+    check(xs_map_soa_to_complex(soa, ncomp, ncomp ? 0 : -1, nplanes, rows, cols, m.ptr(), m.step(), nullptr), "export_map");
+}
+
+namespace seam {
+
+// Map.h:16 / Map.cu:262 (no sync, like the reference)
+template <class DepthT, class MapT> void bilateralFilter(const DepthT &src, MapT &dst) {
+    float *out = scratch(0).get((size_t) src.rows() * src.cols());
+    check(xs_bilateral_filter(src.ptr(), src.step(), src.rows(), src.cols(), out, nullptr), "bilateralFilter");
+    export_map(out, 0, 1, src.rows(), src.cols(), dst);
+}
+// Map.h:22 / Map.cu:274
+template <class MapT> void pyrDown(const MapT &src, MapT &dst) {
+    float *in = import_map(src, 1, 0, 0);
+    float *out = scratch(1).get((size_t) (src.rows() / 2) * (src.cols() / 2));
+    check(xs_pyr_down(in, src.rows(), src.cols(), out, nullptr), "pyrDown");
+    export_map(out, 0, 1, src.rows() / 2, src.cols() / 2, dst);
+}
+// Map.h:29 / Map.cu:73
+template <class IntrT, class MapT> void createVMap(const IntrT &intr, const MapT &depth, MapT &vmap) {
+    float *in = import_map(depth, 1, 0, 0);
+    float *out = scratch(1).get((size_t) 3 * depth.rows() * depth.cols());
+    check(xs_create_vmap(to_intr(intr), in, depth.rows(), depth.cols(), out, nullptr), "createVMap");
+    export_map(out, 0, 3, depth.rows(), depth.cols(), vmap);
+}
+// Map.h:35 / Map.cu:89
+template <class MapT> void createNMap(const MapT &vmap, MapT &nmap) {
+    const int rows = vmap.rows() / 3, cols = vmap.cols();
+    float *in = import_map(vmap, 3, 0, 0);
+    float *out = scratch(1).get((size_t) 3 * rows * cols);
+    check(xs_create_nmap(in, rows, cols, out, nullptr), "createNMap");
+    export_map(out, 0, 3, rows, cols, nmap);
+}
+// Map.h:47,54 / Map.cu:252,257 (sync, like the reference)
+template <class MapT> void resizeVMap(const MapT &input, MapT &output) {
+    const int rows = input.rows() / 3, cols = input.cols();
+    float *in = import_map(input, 3, 1, 0);
+    float *out = scratch(1).get((size_t) 2 * 3 * (rows / 2) * (cols / 2));
+    check(xs_resize_vmap(in, rows, cols, 1, 1, out, nullptr), "resizeVMap");
+    export_map(out, 1, 3, rows / 2, cols / 2, output);
+    cudaDeviceSynchronize();
+}
+template <class MapT> void resizeNMap(const MapT &input, MapT &output) {
+    const int rows = input.rows() / 3, cols = input.cols();
+    float *in = import_map(input, 3, 1, 0);
+    float *out = scratch(1).get((size_t) 2 * 3 * (rows / 2) * (cols / 2));
+    check(xs_resize_nmap(in, rows, cols, 1, 1, out, nullptr), "resizeNMap");
+    export_map(out, 1, 3, rows / 2, cols / 2, output);
+    cudaDeviceSynchronize();
+}
+
+// The brick-tiled volume that shadows one reference TsdfVolume (keyed by the address of its value plane).  A maintainer
+// would instead hold the xs_volume inside class TsdfVolume; this cache keeps the call sites unchanged.
+struct VolumeShadow {
+    xs_volume *v = nullptr;
+    float *dense = nullptr;  // 3 dense [z][y][x] planes: value, weight, grad
+    int res[3] = {0, 0, 0};
+};
+inline VolumeShadow &shadow_of(const void *value_plane, const int res[3], float voxel, float trunc) {
+    static std::map<const void *, VolumeShadow> cache;
+    VolumeShadow &s = cache[value_plane];
+    if (!s.v) {
+        // trunc = max(voxel * thres_range, 2.1 voxel) (TsdfVolume.cpp:25,37): recover thres_range from the caller's trunc
+        s.v = xs_volume_create(res, voxel, trunc / voxel, 1, 1);
+        if (!s.v) check(XS_ERR_CUDA, "xs_volume_create");
+        const size_t n = (size_t) res[0] * res[1] * res[2];
+        if (cudaMalloc((void **) &s.dense, 3 * n * sizeof(float)) != cudaSuccess) check(XS_ERR_CUDA, "volume shadow");
+        for (int i = 0; i < 3; ++i) s.res[i] = res[i];
+    }
+    return s;
+}
+// pitched (Y*Z) x X seam planes <-> dense planes <-> bricks
+template <class PV, class PW> inline void volume_pull(VolumeShadow &s, const PV &value, const PW &weight, const PV &grad) {
+    const size_t n = (size_t) s.res[0] * s.res[1] * s.res[2], row = (size_t) s.res[0] * sizeof(float);
+    const size_t h = (size_t) s.res[1] * s.res[2];
+    cudaMemcpy2D(s.dense, row, value.data, value.step, row, h, cudaMemcpyDeviceToDevice);
+    cudaMemcpy2D(s.dense + n, row, weight.data, weight.step, row, h, cudaMemcpyDeviceToDevice);
+    cudaMemcpy2D(s.dense + 2 * n, row, grad.data, grad.step, row, h, cudaMemcpyDeviceToDevice);
+    check(xs_volume_import_planes(s.v, 0, s.dense, (const int *) (s.dense + n), s.dense + 2 * n, nullptr), "volume import");
+}
+template <class PV, class PW> inline void volume_push(VolumeShadow &s, PV &value, PW &weight, PV &grad) {
+    const size_t n = (size_t) s.res[0] * s.res[1] * s.res[2], row = (size_t) s.res[0] * sizeof(float);
+    const size_t h = (size_t) s.res[1] * s.res[2];
+    check(xs_volume_export_planes(s.v, 0, s.dense, (int *) (s.dense + n), s.dense + 2 * n, nullptr), "volume export");
+    cudaMemcpy2D((void *) value.data, value.step, s.dense, row, row, h, cudaMemcpyDeviceToDevice);
+    cudaMemcpy2D((void *) weight.data, weight.step, s.dense + n, row, row, h, cudaMemcpyDeviceToDevice);
+    cudaMemcpy2D((void *) grad.data, grad.step, s.dense + 2 * n, row, row, h, cudaMemcpyDeviceToDevice);
+}
+
+// TsdfFusion.h:40-45 / TsdfFusion.cu:173 (sync).  tc2v, depthScaled, frame_id and k are unused by the reference too.
+template <class DepthT, class IntrT, class Int3, class Mat, class Vec, class PV, class PW, class ScaledT>
+void integrateTsdfVolume(const DepthT &depth, const IntrT &intr, int max_weight, const Int3 &volume_size, float voxel_size,
+                         const Mat &Rv2c, const Vec &tv2c, const Vec & /*tc2v*/, float trunc_dist, PV value_volume,
+                         PW weight_volume, PV grad_volume, ScaledT & /*depthScaled*/, int /*frame_id*/, float threshold,
+                         float /*k*/) {
+    const int res[3] = {volume_size.x, volume_size.y, volume_size.z};
+    VolumeShadow &s = shadow_of(value_volume.data, res, voxel_size, trunc_dist);
+    volume_pull(s, value_volume, weight_volume, grad_volume);
+    PoseHolder v2c(Rv2c, tv2c);
+    check(xs_integrate(s.v, depth.data, depth.step, depth.rows, depth.cols, to_intr(intr), max_weight, &v2c.p, threshold,
+                       nullptr, nullptr),
+          "integrateTsdfVolume");
+    volume_push(s, value_volume, weight_volume, grad_volume);
+    cudaDeviceSynchronize();
+}
+
+// RayCaster.h:21-25 / RayCaster.cu:327 (no sync)
+template <class IntrT, class Mat, class Vec, class Int3, class PV, class MapT>
+void raycast(const IntrT &intr, const Mat &Rc2v, const Vec &tc2v, const Mat &Rv2w, const Vec &tv2w, float trunc_dist,
+             const Int3 &volume_size, float voxel_size, const PV &value_volume, const PV &grad_volume, MapT &vmap, MapT &nmap) {
+    const int res[3] = {volume_size.x, volume_size.y, volume_size.z};
+    VolumeShadow &s = shadow_of(value_volume.data, res, voxel_size, trunc_dist);
+    {   // the planes may have been written by the caller since the last integration
+        const size_t n = (size_t) res[0] * res[1] * res[2], row = (size_t) res[0] * sizeof(float), h = (size_t) res[1] * res[2];
+        cudaMemcpy2D(s.dense, row, value_volume.data, value_volume.step, row, h, cudaMemcpyDeviceToDevice);
+        cudaMemcpy2D(s.dense + 2 * n, row, grad_volume.data, grad_volume.step, row, h, cudaMemcpyDeviceToDevice);
+        check(xs_volume_import_planes(s.v, 0, s.dense, nullptr, s.dense + 2 * n, nullptr), "volume import");
+    }
+    const int rows = vmap.rows() / 3, cols = vmap.cols();
+    PoseHolder c2v(Rc2v, tc2v), v2w(Rv2w, tv2w);
+    float *v = scratch(2).get((size_t) 2 * 3 * rows * cols), *n = scratch(3).get((size_t) 2 * 3 * rows * cols);
+    check(xs_raycast(s.v, to_intr(intr), &c2v.p, &v2w.p, rows, cols, v, n, nullptr), "raycast");
+    export_map(v, 1, 3, rows, cols, vmap);
+    export_map(n, 1, 3, rows, cols, nmap);
+}
+
+// ICP.h:24-31 / ICP.cu:365 (sync + download).  gbuf / mbuf are the reference's scratch; unused here.
+template <class Mat, class Vec, class MapT, class IntrT, class GBuf, class MBuf, class HostC>
+void estimateCombined(const Mat &Rcurr, const Vec &tcurr, const MapT &vmap_curr, const MapT &nmap_curr, const Mat &Rprev_inv,
+                      const Vec &tprev, const IntrT &intr, const MapT &vmap_g_prev, const MapT &nmap_g_prev, float distThres,
+                      float angleThres, GBuf & /*gbuf*/, MBuf & /*mbuf*/, HostC *matrixA_host, HostC *vectorB_host) {
+    const int rows = vmap_curr.rows() / 3, cols = vmap_curr.cols();
+    // current-frame maps are real in the reference pipeline (Map.cu:196,229); their imaginary parts are dropped
+    float *vc = import_map(vmap_curr, 3, 0, 4), *nc = import_map(nmap_curr, 3, 0, 5);
+    float *vp = import_map(vmap_g_prev, 3, 1, 6), *np_ = import_map(nmap_g_prev, 3, 1, 7);
+    PoseHolder curr(Rcurr, tcurr), prev(Rprev_inv, tprev);
+    double A[2][36], b[2][6];
+    check(xs_estimate_combined(&curr.p, vc, nc, &prev.p, to_intr(intr), vp, np_, rows, cols, 1, 1, distThres, angleThres,
+                               &A[0][0], &b[0][0], nullptr),
+          "estimateCombined");
+    for (int i = 0; i < 36; ++i) matrixA_host[i] = HostC(A[0][i], A[1][i]);  // column-major 6x6, ICP.cu:419-428
+    for (int i = 0; i < 6; ++i) vectorB_host[i] = HostC(b[0][i], b[1][i]);
+}
+
+}  // namespace seam
+}  // namespace xslam_b200

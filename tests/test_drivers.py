@@ -1,0 +1,108 @@
+"""The C++ drivers (drivers/test_kinect_fusion.cpp, drivers/test_CSFD.cpp): the reference's Experiments/* surface.
+
+CPU part: the binaries are built, link the library, read the reference's flat YAML and fail LOUDLY without a CUDA
+device (no CPU fallback).  GPU part: outputs in the reference's formats (frame-%06d.pose.txt as IOHelper.cpp:21-32,
+pcd.ply as CPointCloud.cpp:42-67), the test_CSFD known answers (main.cpp:194-219: 2.73911 / 9.26892), and agreement of
+the driver's trajectory with the Python mirror of the same C-ABI."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "x-slam_b200", "bin")
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_driver_binaries_exist_and_link():
+    for name in ("test_kinect_fusion", "test_CSFD"):
+        path = os.path.join(BIN, name)
+        assert os.path.exists(path), "run `make -C x-slam_b200` (__graft_entry__.build())"
+        out = subprocess.run(["ldd", path], capture_output=True, text=True).stdout
+        assert "libxslam_b200.so" in out and "not found" not in out.split("libxslam_b200.so")[1].split("\n")[0]
+
+
+def test_driver_usage_and_missing_key(tmp_path):
+    r = subprocess.run([os.path.join(BIN, "test_kinect_fusion")], capture_output=True, text=True)
+    assert r.returncode != 0 and "please enter the config file name" in r.stdout  # main.cpp:19-24
+    bad = tmp_path / "bad.yaml"
+    bad.write_text("dataset_format: synthetic\nstart_frame: 0\n")
+    r = subprocess.run([os.path.join(BIN, "test_kinect_fusion"), str(bad)], capture_output=True, text=True)
+    assert r.returncode != 0  # yaml-cpp throws on a missing key; so does the flat reader
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure mode")
+def test_drivers_fail_loudly_without_gpu(tmp_path):
+    r = subprocess.run([os.path.join(BIN, "test_CSFD")], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    r = subprocess.run([os.path.join(BIN, "test_kinect_fusion"), os.path.join(ROOT, "configs", "synth_traj2.yaml"), str(tmp_path)],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_flat_yaml_reads_reference_style_config(xs):
+    cfg = xs.load_yaml(os.path.join(ROOT, "configs", "synth_traj2.yaml"))
+    for key in ("tsdf_size_x", "tsdf_voxel_size", "max_integration_weight", "thres_range", "init_x", "r_x", "depth_width", "fx", "fy",
+                "num_levels", "distThres", "angleThres", "biInterpolate_threshold", "start_frame", "end_frame", "log_slam_pose"):
+        assert key in cfg, key  # the keys KinectFusionReconstruction.cpp:12-72 and main.cpp:28-33 read
+    assert cfg["fy"] == -480.0 and cfg["log_slam_pose"] is True and cfg["dataset_format"] == "synthetic"
+
+
+@pytest.mark.gpu
+def test_csfd_driver_known_answers():
+    r = subprocess.run([os.path.join(BIN, "test_CSFD")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    grads = [float(x) for x in re.findall(r"gradient = ([-0-9.eE+]+)", r.stdout)]
+    seconds = [float(x) for x in re.findall(r"second order differentiation = ([-0-9.eE+]+)", r.stdout)]
+    assert len(grads) == 2 and len(seconds) == 2
+    assert abs(grads[0] - 2.73911) < 2e-3 and abs(grads[1] - 2.73911) < 1e-4      # test_CSFD prints 2.73911
+    assert abs(seconds[0] - 9.26892) < 0.1 and abs(seconds[1] - 9.26892) < 1e-4    # and 9.26892
+    vals = re.findall(r"result = \(([-0-9.eE+]+),([-0-9.eE+]+)\)", r.stdout)
+    # main.cpp prints (-0.75,-1e-06) (-0.333333,-8.88889e-07) (0.367879,7.35759e-07) (-0.841471,1.0806e-06); pow on a = (0.5, h)
+    want = [(-0.75, -1e-6), (-0.333333, -8.88889e-7), (0.367879, 7.35759e-7), (-0.841471, 1.0806e-6), (0.125, 0.75e-6)]
+    assert len(vals) == 5
+    for (re_, im_), (wr, wi) in zip(vals, want):
+        assert abs(float(re_) - wr) < 2e-5 * max(1, abs(wr)) and abs(float(im_) - wi) < 2e-5 * max(abs(wi), 1e-7) + 1e-11, (re_, im_, wr, wi)
+
+
+@pytest.mark.gpu
+def test_kinect_fusion_driver_outputs(xs, tmp_path):
+    cfg_text = open(os.path.join(ROOT, "configs", "synth_traj2.yaml")).read().replace("end_frame: 30", "end_frame: 4")
+    cfg_path = tmp_path / "cfg.yaml"
+    cfg_path.write_text(cfg_text)
+    out = str(tmp_path / "out") + "/"
+    r = subprocess.run([os.path.join(BIN, "test_kinect_fusion"), str(cfg_path), out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr + r.stdout[-2000:]
+    assert re.search(r"mean frame time = [0-9.]+ ms", r.stdout)  # main.cpp:83
+    # trajectory files: 4 lines x 4 fixed-precision-7 values, each followed by a space (IOHelper.cpp:21-32)
+    k = xs.KinectFusionReconstruction()
+    k.SetYamlParameters(xs.load_yaml(str(cfg_path)), comps=1, seeds=xs.pose_seeds_csfd())
+    for f in range(4):
+        for sub in ("slam", "gt"):
+            path = os.path.join(out, sub, "frame-%06d.pose.txt" % f)
+            lines = open(path).read().split("\n")
+            assert len(lines) == 5 and lines[4] == ""
+            for ln in lines[:4]:
+                assert re.fullmatch(r"(-?[0-9]+\.[0-9]{7} ){4}", ln), repr(ln)
+        assert k.ProcessFrame(xs.synth_depth(f)) == 1
+        slam = np.loadtxt(os.path.join(out, "slam", "frame-%06d.pose.txt" % f))
+        assert np.abs(slam - k.pose_c2w()).max() < 5e-7  # same C-ABI, same frames: identical up to the printed precision
+        gt = np.loadtxt(os.path.join(out, "gt", "frame-%06d.pose.txt" % f))
+        assert np.abs(slam - gt).max() < 2e-2  # the tracker follows the synthetic trajectory
+        d = np.loadtxt(os.path.join(out, "slam", "frame-%06d.dpose.txt" % f))
+        assert d.shape == (6, 16)
+        want = k.world2camera[1:].reshape(6, 16) / 1e-7
+        assert np.abs(d - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
+    ply = open(os.path.join(out, "pcd.ply")).read().split("\n")
+    assert ply[0] == "ply" and ply[1] == "format ascii 1.0" and ply[3].startswith("element vertex ")
+    n = int(ply[3].split()[-1])
+    assert n > 10000 and ply[10] == "end_header" and len(ply[11].split()) == 6

@@ -51,6 +51,8 @@ SYMBOLS = {
     "xs_create_nmap": (_i, [_vp, _i, _i, _vp, _vp]),
     "xs_resize_vmap": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "xs_resize_nmap": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "xs_map_complex_to_soa": (_i, [_vp, _sz, _i, _i, _i, _vp, _i, _i, _vp]),
+    "xs_map_soa_to_complex": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "xs_volume_create": (_vp, [_pi, _f, _f, _i, _i]),
     "xs_volume_destroy": (None, [_vp]),
     "xs_volume_reset": (_i, [_vp, _vp]),
@@ -82,6 +84,7 @@ SYMBOLS = {
     "xs_kinfu_get_stats": (_i, [_vp, _pull]),
     "xs_kinfu_get_algorithmic_bytes": (_i, [_vp, _pd]),
     "xs_kinfu_pose_record_device": (_vp, [_vp]),
+    "xs_kinfu_stream": (_vp, [_vp]),
     "xs_save_pose_txt": (_i, [C.c_char_p, _pf]),
     "xs_export_ply": (_i, [C.c_char_p, _pf, _pf, _l]),
     "xs_synth_depth": (_i, [_pf, Intr, _i, _i, C.POINTER(C.c_uint16)]),

@@ -502,4 +502,6 @@ int xs_kinfu_get_algorithmic_bytes(const xs_kinfu *k, double *out4) {
 
 float *xs_kinfu_pose_record_device(xs_kinfu *k) { return k ? k->d_record : nullptr; }
 
+void *xs_kinfu_stream(xs_kinfu *k) { return k ? (void *) k->stream : nullptr; }
+
 }  // extern "C"

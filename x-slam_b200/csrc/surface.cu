@@ -112,11 +112,52 @@ __global__ void nmap_kernel(int rows, int cols, const float *__restrict__ vmap, 
     nmap[pix + 2 * plane] = r.z.v;
 }
 
+// Seam layout <-> packed SoA.  The reference's maps are pitched arrays of interleaved complex<float> with the planes
+// stacked by rows (MapArr = DeviceArray2D<devComplex>, Internal.h:31; `nplanes*rows` x cols).  Component 0 of the SoA
+// map is the real part; the imaginary part maps to derivative component `comp` (comp < 0: dropped / written as zero).
+__global__ void complex_to_soa_kernel(const char *__restrict__ src, size_t step, int prow, int cols, float *__restrict__ real,
+                                      float *__restrict__ imag) {
+    const int x = threadIdx.x + blockIdx.x * blockDim.x, y = threadIdx.y + blockIdx.y * blockDim.y;
+    if (x >= cols || y >= prow) return;
+    const float2 v = reinterpret_cast<const float2 *>(src + (size_t) y * step)[x];
+    real[(size_t) y * cols + x] = v.x;
+    if (imag) imag[(size_t) y * cols + x] = v.y;
+}
+__global__ void soa_to_complex_kernel(const float *__restrict__ real, const float *__restrict__ imag, int prow, int cols,
+                                      char *__restrict__ dst, size_t step) {
+    const int x = threadIdx.x + blockIdx.x * blockDim.x, y = threadIdx.y + blockIdx.y * blockDim.y;
+    if (x >= cols || y >= prow) return;
+    reinterpret_cast<float2 *>(dst + (size_t) y * step)[x] =
+        make_float2(real[(size_t) y * cols + x], imag ? imag[(size_t) y * cols + x] : 0.f);
+}
+
 }  // namespace xs
 
 using namespace xs;
 
 extern "C" {
+
+int xs_map_complex_to_soa(const void *d_src, size_t step_bytes, int nplanes, int rows, int cols, float *d_soa, int ncomp,
+                          int comp, void *stream) {
+    if (!d_src || !d_soa || nplanes <= 0 || rows <= 0 || cols <= 0 || comp >= ncomp) return XS_ERR_ARG;
+    const size_t csize = (size_t) nplanes * rows * cols;
+    dim3 blk(32, 8), grd(div_up(cols, 32), div_up(nplanes * rows, 8));
+    complex_to_soa_kernel<<<grd, blk, 0, (cudaStream_t) stream>>>((const char *) d_src, step_bytes, nplanes * rows, cols, d_soa,
+                                                                  comp >= 0 ? d_soa + (size_t) (1 + comp) * csize : nullptr);
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
+
+int xs_map_soa_to_complex(const float *d_soa, int ncomp, int comp, int nplanes, int rows, int cols, void *d_dst,
+                          size_t step_bytes, void *stream) {
+    if (!d_dst || !d_soa || nplanes <= 0 || rows <= 0 || cols <= 0 || comp >= ncomp) return XS_ERR_ARG;
+    const size_t csize = (size_t) nplanes * rows * cols;
+    dim3 blk(32, 8), grd(div_up(cols, 32), div_up(nplanes * rows, 8));
+    soa_to_complex_kernel<<<grd, blk, 0, (cudaStream_t) stream>>>(d_soa, comp >= 0 ? d_soa + (size_t) (1 + comp) * csize : nullptr,
+                                                                  nplanes * rows, cols, (char *) d_dst, step_bytes);
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
 
 int xs_bilateral_filter(const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, float *d_out, void *stream) {
     if (!d_depth || !d_out || rows <= 0 || cols <= 0) return XS_ERR_ARG;

@@ -241,6 +241,10 @@ class KinectFusionReconstruction:
     def pose_record_device_ptr(self):
         return self.lib.xs_kinfu_pose_record_device(self.h)
 
+    def stream_ptr(self):
+        """cudaStream_t (as an integer) all kernels of this object are launched on."""
+        return self.lib.xs_kinfu_stream(self.h) or 0
+
 
 # ------------------------------------------------------------------ outputs and synthetic input
 def savePose(output_dir, frame_id, pose):
