@@ -130,15 +130,12 @@ __global__ void __launch_bounds__(256) raycast_march_kernel(const RaycastParams 
 // are only coefficients, so they use MUFU-based division / rsqrt instead of the reference-faithful sequences.
 constexpr int HIT_PX = 32, HIT_WARPS = 8;
 // per-sample context fields
-enum { S_PX0 = 0, S_PX1, S_PY0, S_PY1, S_PZ0, S_PZ1, S_A, S_B, S_C, S_GA, S_GB, S_GC, S_HAB, S_HAC, S_HBC, S_VAL, S_FIELDS };
+// S_OFF: the 8 corner offsets into the derivative planes (64-bit element offsets of component 0 of direction 0,
+// corner c = i*4 + j*2 + k; low / high words in S_OFF + 2c, S_OFF + 2c + 1)
+enum { S_OFF = 0, S_A = 16, S_B, S_C, S_GA, S_GB, S_GC, S_HAB, S_HAC, S_HBC, S_VAL, S_FIELDS };
 // per-pixel context fields
-enum { X_FLAGS = 0, X_T0, X_FIELDS };
+enum { X_FLAGS = 0, X_T0, X_VX, X_VY, X_VZ, X_OK, X_FIELDS };
 constexpr int HIT_CTX_WORDS = 8 * S_FIELDS + X_FIELDS;
-
-// packed per-axis offsets: (brick part << 9) | (brick-local part); the sum over the three axes is (brick << 9) | local
-XS_DEV unsigned pack_x(int x) { return ((unsigned) (x >> 3) << 9) | (unsigned) (x & 7); }
-XS_DEV unsigned pack_y(const VolumeView &V, int y) { return ((unsigned) ((y >> 3) * V.bx) << 9) | (unsigned) ((y & 7) << 3); }
-XS_DEV unsigned pack_z(const VolumeView &V, int z) { return ((unsigned) ((z >> 3) * V.by * V.bx) << 9) | (unsigned) ((z & 7) << 6); }
 
 // value, gradient and (optionally) mixed second partials of the trilinear interpolant of f[i*4 + j*2 + k]
 // (i, j, k = x, y, z corner bits) with respect to the weights (a, b, c)
@@ -204,12 +201,17 @@ XS_DEV bool trilinear_real(const VolumeView &V, float px, float py, float pz, fl
     out = r;
     float val, ga, gb, gc, hab, hac, hbc;
     contract<true>(f, a0, b0, c0, val, ga, gb, gc, hab, hac, hbc);
-    ctx[S_PX0 * HIT_PX] = __uint_as_float(pack_x(gx));
-    ctx[S_PX1 * HIT_PX] = __uint_as_float(pack_x(gx + 1));
-    ctx[S_PY0 * HIT_PX] = __uint_as_float(pack_y(V, gy));
-    ctx[S_PY1 * HIT_PX] = __uint_as_float(pack_y(V, gy + 1));
-    ctx[S_PZ0 * HIT_PX] = __uint_as_float(pack_z(V, gz));
-    ctx[S_PZ1 * HIT_PX] = __uint_as_float(pack_z(V, gz + 1));
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const unsigned long long off = (unsigned long long) deriv_index(V, gx + i, gy + j, gz + k, 0);
+                const int cidx = i * 4 + j * 2 + k;
+                ctx[(S_OFF + 2 * cidx) * HIT_PX] = __uint_as_float((unsigned) off);
+                ctx[(S_OFF + 2 * cidx + 1) * HIT_PX] = __uint_as_float((unsigned) (off >> 32));
+            }
     ctx[S_A * HIT_PX] = a0;
     ctx[S_B * HIT_PX] = b0;
     ctx[S_C * HIT_PX] = c0;
@@ -223,9 +225,10 @@ XS_DEV bool trilinear_real(const VolumeView &V, float px, float py, float pz, fl
     return true;
 }
 
-// Real hit evaluation (warp 0).  flags: bit 0 = vertex valid, bit 1 = normal valid, bits 2..4 = degenerate direction.
-XS_DEV unsigned eval_hit_real(const RaycastParams &P, int x, int y, float time_curr, float *ctx, float (&vw)[3], float (&ng)[3]) {
-    typedef Jet<1, 0> J;
+// Real hit evaluation, RayCaster.cu:249-305, in three phases so that the six normal samples run on six warps.
+// flags: bit 0 = vertex valid, bit 1 = normal valid, bit 2 = the normal samples are needed (vertex well inside).
+// phase A (warp 0): crossing samples, hit time, vertex -> world vertex; leaves the volume-frame vertex in the context
+XS_DEV unsigned hit_phase_a(const RaycastParams &P, int x, int y, float time_curr, float *ctx, float *xctx, float (&vw)[3]) {
     const VolumeView &V = P.V;
     Jet3<1, 0> start, dir;
     ray_setup<1, 0>(P, x, y, 0, start, dir);
@@ -248,56 +251,53 @@ XS_DEV unsigned eval_hit_real(const RaycastParams &P, int x, int y, float time_c
     const JetPose<1, 0> v2w = load_pose<1, 0>(P.v2w, P.dpose_v2w, 0, P.dirs);
     const Jet3<1, 0> w = jrot(v2w, vertex) + v2w.t;
     vw[0] = w.x.v, vw[1] = w.y.v, vw[2] = w.z.v;
-    unsigned flags = 1u;
+    xctx[X_VX * HIT_PX] = vertex.x.v;
+    xctx[X_VY * HIT_PX] = vertex.y.v;
+    xctx[X_VZ * HIT_PX] = vertex.z.v;
     const float vs = V.voxel;
     const int gx = __float2int_rd(__fdiv_rn(vertex.x.v, vs));
     const int gy = __float2int_rd(__fdiv_rn(vertex.y.v, vs));
     const int gz = __float2int_rd(__fdiv_rn(vertex.z.v, vs));
-    if (!(gx > 1 && gy > 1 && gz > 1 && gx < V.rx - 2 && gy < V.ry - 2 && gz < V.rz - 2)) return flags;
-    const float hv = __fmul_rn(vs, 0.5f);
-    float F[6];
-    bool ok = true;
-    ok &= trilinear_real(V, __fadd_rn(vertex.x.v, hv), vertex.y.v, vertex.z.v, ctx + 2 * S_FIELDS * HIT_PX, F[0]);
-    ok &= trilinear_real(V, __fsub_rn(vertex.x.v, hv), vertex.y.v, vertex.z.v, ctx + 3 * S_FIELDS * HIT_PX, F[1]);
-    ok &= trilinear_real(V, vertex.x.v, __fadd_rn(vertex.y.v, hv), vertex.z.v, ctx + 4 * S_FIELDS * HIT_PX, F[2]);
-    ok &= trilinear_real(V, vertex.x.v, __fsub_rn(vertex.y.v, hv), vertex.z.v, ctx + 5 * S_FIELDS * HIT_PX, F[3]);
-    ok &= trilinear_real(V, vertex.x.v, vertex.y.v, __fadd_rn(vertex.z.v, hv), ctx + 6 * S_FIELDS * HIT_PX, F[4]);
-    ok &= trilinear_real(V, vertex.x.v, vertex.y.v, __fsub_rn(vertex.z.v, hv), ctx + 7 * S_FIELDS * HIT_PX, F[5]);
-    if (!ok) return flags;
+    if (!(gx > 1 && gy > 1 && gz > 1 && gx < V.rx - 2 && gy < V.ry - 2 && gz < V.rz - 2)) return 1u;
+    return 1u | 4u;
+}
+// phase B (warps 2..7, sample = warp index): one normal sample at vertex +- half a voxel along axis (sample-2)/2
+XS_DEV void hit_phase_b(const RaycastParams &P, int sample, float *ctx, float *xctx) {
+    const float hv = __fmul_rn(P.V.voxel, 0.5f);
+    float p[3] = {xctx[X_VX * HIT_PX], xctx[X_VY * HIT_PX], xctx[X_VZ * HIT_PX]};
+    const int axis = (sample - 2) >> 1;
+    p[axis] = (sample & 1) ? __fsub_rn(p[axis], hv) : __fadd_rn(p[axis], hv);
+    float F;
+    const bool ok = trilinear_real(P.V, p[0], p[1], p[2], ctx + sample * S_FIELDS * HIT_PX, F);
+    if (!ok) xctx[X_OK * HIT_PX] = 0.f;  // cannot happen for g in (1, N-2); the reference would propagate NaN
+}
+// phase C (warp 0): the world-frame normal
+XS_DEV bool hit_phase_c(const RaycastParams &P, const float *ctx, float (&ng)[3]) {
     Jet3<1, 0> n;
-    n.x.v = __fsub_rn(F[0], F[1]);
-    n.y.v = __fsub_rn(F[2], F[3]);
-    n.z.v = __fsub_rn(F[4], F[5]);
-    if (jdot(n, n).v == 0.f) return flags;
+    n.x.v = __fsub_rn(ctx[(2 * S_FIELDS + S_VAL) * HIT_PX], ctx[(3 * S_FIELDS + S_VAL) * HIT_PX]);
+    n.y.v = __fsub_rn(ctx[(4 * S_FIELDS + S_VAL) * HIT_PX], ctx[(5 * S_FIELDS + S_VAL) * HIT_PX]);
+    n.z.v = __fsub_rn(ctx[(6 * S_FIELDS + S_VAL) * HIT_PX], ctx[(7 * S_FIELDS + S_VAL) * HIT_PX]);
+    if (jdot(n, n).v == 0.f) return false;
+    const JetPose<1, 0> v2w = load_pose<1, 0>(P.v2w, P.dpose_v2w, 0, P.dirs);
     const Jet3<1, 0> g = jrot(v2w, jnormalized(n));
     ng[0] = g.x.v, ng[1] = g.y.v, ng[2] = g.z.v;
-    return flags | 2u;
+    return true;
 }
 
 // derivative components of one trilinear sample for one direction; dpos = derivative of the sample position
 template <int C>
 XS_DEV Jet<C, 1> sample_deriv(const VolumeView &V, const float *__restrict__ dq /* deriv + q*C*BRICK_VOX */, const float *ctx,
                               const Jet3<C, 1> &pos, float inv_vs) {
-    unsigned px[2], py[2], pz[2];
-    px[0] = __float_as_uint(ctx[S_PX0 * HIT_PX]), px[1] = __float_as_uint(ctx[S_PX1 * HIT_PX]);
-    py[0] = __float_as_uint(ctx[S_PY0 * HIT_PX]), py[1] = __float_as_uint(ctx[S_PY1 * HIT_PX]);
-    pz[0] = __float_as_uint(ctx[S_PZ0 * HIT_PX]), pz[1] = __float_as_uint(ctx[S_PZ1 * HIT_PX]);
     const float a = ctx[S_A * HIT_PX], b = ctx[S_B * HIT_PX], c = ctx[S_C * HIT_PX];
     float f[C][8];
-    const size_t bstride = (size_t) V.ncomp * BRICK_VOX;
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int cidx = 0; cidx < 8; ++cidx) {
+        const unsigned long long off = (unsigned long long) __float_as_uint(ctx[(S_OFF + 2 * cidx) * HIT_PX]) |
+                                       ((unsigned long long) __float_as_uint(ctx[(S_OFF + 2 * cidx + 1) * HIT_PX]) << 32);
+        const float *p = dq + off;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const unsigned pxy = px[i] + py[j];
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const unsigned pk = pxy + pz[k];
-                const float *p = dq + (size_t) (pk >> 9) * bstride + (pk & 511u);
-#pragma unroll
-                for (int cc = 0; cc < C; ++cc) f[cc][i * 4 + j * 2 + k] = __ldg(p + cc * BRICK_VOX);
-            }
-        }
+        for (int cc = 0; cc < C; ++cc) f[cc][cidx] = __ldg(p + cc * BRICK_VOX);
+    }
     Jet<C, 1> r;
     r.v = ctx[S_VAL * HIT_PX];
     const float ga = ctx[S_GA * HIT_PX], gb = ctx[S_GB * HIT_PX], gc = ctx[S_GC * HIT_PX];
@@ -335,24 +335,36 @@ template <int C> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS) raycast_hi
     float *ctx = s_ctx + lane;
     float *xctx = ctx + 8 * S_FIELDS * HIT_PX;
     const float qnan = __int_as_float(0x7fffffff);
+    unsigned flags_a = 0u;
     if (warp == 0) {
-        unsigned flags = 0u;
         float t0 = -1.f;
+        xctx[X_OK * HIT_PX] = 1.f;
         if (inside) {
             t0 = hit_time[(size_t) y * P.cols + x];
-            float vw[3], ng[3];
-            if (t0 >= 0.f) flags = eval_hit_real(P, x, y, t0, ctx, vw, ng);
-            if (flags & 1u)
+            float vw[3];
+            if (t0 >= 0.f) flags_a = hit_phase_a(P, x, y, t0, ctx, xctx, vw);
+            if (flags_a & 1u)
                 store3(P.vmap, 0, P.rows, P.cols, y, x, vw[0], vw[1], vw[2]);
             else
                 store3(P.vmap, 0, P.rows, P.cols, y, x, qnan, 0.f, 0.f);
-            if (flags & 2u)
+        }
+        xctx[X_FLAGS * HIT_PX] = __uint_as_float(flags_a);
+        xctx[X_T0 * HIT_PX] = t0;
+    }
+    __syncthreads();
+    if (warp >= 2 && (__float_as_uint(xctx[X_FLAGS * HIT_PX]) & 4u)) hit_phase_b(P, warp, ctx, xctx);
+    __syncthreads();
+    if (warp == 0) {
+        if (inside) {
+            float ng[3];
+            bool n_ok = false;
+            if ((flags_a & 4u) && xctx[X_OK * HIT_PX] != 0.f) n_ok = hit_phase_c(P, ctx, ng);
+            if (n_ok)
                 store3(P.nmap, 0, P.rows, P.cols, y, x, ng[0], ng[1], ng[2]);
             else
                 store3(P.nmap, 0, P.rows, P.cols, y, x, qnan, 0.f, 0.f);
+            xctx[X_FLAGS * HIT_PX] = __uint_as_float((flags_a & 1u) | (n_ok ? 2u : 0u));
         }
-        xctx[X_FLAGS * HIT_PX] = __uint_as_float(flags);
-        xctx[X_T0 * HIT_PX] = t0;
     }
     __syncthreads();
     if (!inside || P.dirs == 0) return;
@@ -365,7 +377,7 @@ template <int C> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS) raycast_hi
         Jet3<C, 1> vw, ng;
         if (flags & 1u) {
             // ray: start = t, dir = normalized(R * next)  (RayCaster.cu:56-62,207-213)
-            const JetPose<C, 1> c2v = load_pose<C, 1>(P.c2v, P.dpose_c2v, q, P.dirs);
+            const JetPose<C, 1> c2v = load_pose_vec<C>(P.c2v, P.dpose_c2v, q);
             Jet3<C, 1> next = {jconst<C, 1>(nx), jconst<C, 1>(ny), jconst<C, 1>(1.f)};
             const Jet3<C, 1> start = c2v.t;
             Jet3<C, 1> dir = jnormalized_fast(jrot(c2v, next));
@@ -385,7 +397,7 @@ template <int C> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS) raycast_hi
 #pragma unroll
             for (int i = 0; i < C; ++i) Ts.d[i] = -P.time_step * coef.d[i];
             const Jet3<C, 1> vertex = {start.x + dir.x * Ts, start.y + dir.y * Ts, start.z + dir.z * Ts};
-            const JetPose<C, 1> v2w = load_pose<C, 1>(P.v2w, P.dpose_v2w, q, P.dirs);
+            const JetPose<C, 1> v2w = load_pose_vec<C>(P.v2w, P.dpose_v2w, q);
             vw = jrot(v2w, vertex) + v2w.t;
             if (flags & 2u) {
                 // the six normal samples sit at vertex +- half a voxel along one axis: same position derivative
