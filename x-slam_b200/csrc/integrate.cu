@@ -4,7 +4,7 @@
 // scaleDepthKernal (TsdfFusion.cu:68-82), tsdfFusionKernal / integrateTsdfVolume (TsdfFusion.cu:85-201)
 // and pack/unpack_tsdf (TsdfFusion.h:7-26).
 //
-// One CTA = one 8x8x8 brick (512 threads, thread = voxel, brick-local index = thread index, so every
+// One CTA pass = half of an 8x8x8 brick (256 threads, thread = voxel, brick-local index = thread index, so every
 // warp access to value / weight / deriv[comp] is one fully coalesced 128-byte line).  The real path of a
 // voxel (projection, depth lookup, sdf, all integer decisions) is evaluated ONCE together with the
 // Jacobian (and for DCSFD the Hessian) of sdf with respect to the camera-frame position v_c; every stored
@@ -48,20 +48,21 @@ struct IntegrateParams {
     float trunc_inv;
     unsigned long long *stats;  // [0] updated voxels, [1] bricks in the list, [2] voxels whose derivative planes were read+written
     int nbricks;
-    const int *brick_list;      // bricks that survive the cull (written by cull_bricks_kernel)
+    const int2 *brick_list;     // bricks that survive the cull (written by cull_bricks_kernel): (index, packed x|y<<10|z<<20)
     unsigned int *list_count;
     unsigned char *live;        // [nbricks] 0 = every derivative plane of the brick is still exactly zero
 };
 
 // Conservative brick cull: bounding sphere vs. camera half-space / image planes.  One thread per brick; survivors are
 // appended to the brick list (warp-aggregated), so the integration kernel never touches a brick outside the frustum.
-__global__ void __launch_bounds__(256) cull_bricks_kernel(const IntegrateParams P, int *__restrict__ list) {
+__global__ void __launch_bounds__(256) cull_bricks_kernel(const IntegrateParams P, int2 *__restrict__ list) {
     const int b = blockIdx.x * 256 + threadIdx.x;
     bool keep = false;
+    int bx = 0, by = 0, bz = 0;
     if (b < P.nbricks) {
         const float vs = P.V.voxel;
         const float *R = P.v2c.R, *t = P.v2c.t;
-        const int bx = b % P.V.bx, by = (b / P.V.bx) % P.V.by, bz = b / (P.V.bx * P.V.by);
+        bx = b % P.V.bx, by = (b / P.V.bx) % P.V.by, bz = b / (P.V.bx * P.V.by);
         const float cxw = (bx * 8 + 4) * vs, cyw = (by * 8 + 4) * vs, czw = (bz * 8 + 4) * vs;
         const float ccx = R[0] * cxw + R[1] * cyw + R[2] * czw + t[0];
         const float ccy = R[3] * cxw + R[4] * cyw + R[5] * czw + t[1];
@@ -95,7 +96,8 @@ __global__ void __launch_bounds__(256) cull_bricks_kernel(const IntegrateParams 
     unsigned base = 0;
     if (lane == __ffs(m) - 1) base = atomicAdd(P.list_count, (unsigned) __popc(m));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = b;
+    // entry = (brick index, packed brick coordinates) so the integration kernel does no integer division
+    if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = make_int2(b, bx | (by << 10) | (bz << 20));
 }
 
 // Real path + derivative of sdf w.r.t. v_c for one voxel.  K = 3 (C=1: gradient) or 6 (C=3: pairs
@@ -159,23 +161,29 @@ XS_DEV bool eval_voxel(const IntegrateParams &P, float vcx, float vcy, float vcz
     return Dp.v > 0 && sdf.v >= -P.V.trunc;
 }
 
-template <int C> __global__ void __launch_bounds__(512) integrate_kernel(const IntegrateParams P) {
+// One CTA pass = half a brick (256 threads, 4 z-slices): 3 CTAs per SM at <= 85 registers instead of one 512-thread CTA,
+// i.e. 24 resident warps and three independent streams of derivative-plane loads per SM.
+constexpr int INT_THREADS = 256;
+template <int C> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_kernel(const IntegrateParams P) {
     constexpr int K = (C == 1) ? 3 : 6;
-    extern __shared__ float s_dpose[];  // [ncomp][12]
-    const int tid = threadIdx.x;
+    extern __shared__ float4 s_dpose4[];  // [ncomp][3] float4 = [ncomp][12] floats
+    float *s_dpose = reinterpret_cast<float *>(s_dpose4);
     const int ncomp = P.V.ncomp;
-    for (int i = tid; i < ncomp * 12; i += 512) s_dpose[i] = P.dpose[i];
+    for (int i = threadIdx.x; i < ncomp * 12; i += INT_THREADS) s_dpose[i] = P.dpose[i];
     __syncthreads();
 
     const float vs = P.V.voxel;
     const float *R = P.v2c.R, *t = P.v2c.t;
-    const int lx = tid & 7, ly = (tid >> 3) & 7, lz = tid >> 6;
     unsigned long long n_upd = 0, n_der = 0;
     const int nlist = (int) *P.list_count;
 
-    for (int li = blockIdx.x; li < nlist; li += gridDim.x) {
-        const int b = P.brick_list[li];
-        const int bx = b % P.V.bx, by = (b / P.V.bx) % P.V.by, bz = b / (P.V.bx * P.V.by);
+    for (int hi = blockIdx.x; hi < 2 * nlist; hi += gridDim.x) {
+        const int li = hi >> 1;
+        const int tid = ((hi & 1) << 8) | threadIdx.x;  // brick-local voxel index
+        const int lx = tid & 7, ly = (tid >> 3) & 7, lz = tid >> 6;
+        const int2 entry = P.brick_list[li];
+        const int b = entry.x;
+        const int bx = entry.y & 1023, by = (entry.y >> 10) & 1023, bz = entry.y >> 20;
         // derivative planes of a brick that never held a truncation-band voxel are exactly zero: scaling them by
         // w/(w+1) is the identity, so free-space bricks move no derivative bytes at all
         const bool live = ncomp > 0 && P.live[b] != 0;
@@ -237,26 +245,28 @@ template <int C> __global__ void __launch_bounds__(512) integrate_kernel(const I
             const int dirs = ncomp / 3;
 #pragma unroll 2
             for (int k = 0; k < dirs; ++k) {
-                const float *m1 = s_dpose + (3 * k) * 12, *m2 = m1 + 12, *m12 = m1 + 24;
-                const float ax = fmaf(m1[0], vgx, fmaf(m1[1], vgy, fmaf(m1[2], vgz, m1[9])));
-                const float ay = fmaf(m1[3], vgx, fmaf(m1[4], vgy, fmaf(m1[5], vgz, m1[10])));
-                const float az = fmaf(m1[6], vgx, fmaf(m1[7], vgy, fmaf(m1[8], vgz, m1[11])));
-                const float bxx = fmaf(m2[0], vgx, fmaf(m2[1], vgy, fmaf(m2[2], vgz, m2[9])));
-                const float byy = fmaf(m2[3], vgx, fmaf(m2[4], vgy, fmaf(m2[5], vgz, m2[10])));
-                const float bzz = fmaf(m2[6], vgx, fmaf(m2[7], vgy, fmaf(m2[8], vgz, m2[11])));
-                const float cx2 = fmaf(m12[0], vgx, fmaf(m12[1], vgy, fmaf(m12[2], vgz, m12[9])));
-                const float cy2 = fmaf(m12[3], vgx, fmaf(m12[4], vgy, fmaf(m12[5], vgz, m12[10])));
-                const float cz2 = fmaf(m12[6], vgx, fmaf(m12[7], vgy, fmaf(m12[8], vgz, m12[11])));
+                float *p = dp + (size_t) (3 * k) * BRICK_VOX;
+                const float o1 = p[0], o2 = p[BRICK_VOX], o12 = p[2 * BRICK_VOX];  // loads first: they bound this loop
+                const float4 *m = s_dpose4 + 9 * k;  // rows of (dR | dt) for eps1, eps2, eps1eps2
+                const float4 a0 = m[0], a1 = m[1], a2 = m[2], b0 = m[3], b1 = m[4], b2 = m[5], c0 = m[6], c1 = m[7], c2 = m[8];
+                const float ax = fmaf(a0.x, vgx, fmaf(a0.y, vgy, fmaf(a0.z, vgz, a2.y)));
+                const float ay = fmaf(a0.w, vgx, fmaf(a1.x, vgy, fmaf(a1.y, vgz, a2.z)));
+                const float az = fmaf(a1.z, vgx, fmaf(a1.w, vgy, fmaf(a2.x, vgz, a2.w)));
+                const float bxx = fmaf(b0.x, vgx, fmaf(b0.y, vgy, fmaf(b0.z, vgz, b2.y)));
+                const float byy = fmaf(b0.w, vgx, fmaf(b1.x, vgy, fmaf(b1.y, vgz, b2.z)));
+                const float bzz = fmaf(b1.z, vgx, fmaf(b1.w, vgy, fmaf(b2.x, vgz, b2.w)));
+                const float cx2 = fmaf(c0.x, vgx, fmaf(c0.y, vgy, fmaf(c0.z, vgz, c2.y)));
+                const float cy2 = fmaf(c0.w, vgx, fmaf(c1.x, vgy, fmaf(c1.y, vgz, c2.z)));
+                const float cz2 = fmaf(c1.z, vgx, fmaf(c1.w, vgy, fmaf(c2.x, vgz, c2.w)));
                 const float T1 = fmaf(J0, ax, fmaf(J1, ay, J2 * az));
                 const float T2 = fmaf(J0, bxx, fmaf(J1, byy, J2 * bzz));
                 const float hx = fmaf(H00, bxx, fmaf(H01, byy, H02 * bzz));
                 const float hy = fmaf(H01, bxx, fmaf(H11, byy, H12 * bzz));
                 const float hz = fmaf(H02, bxx, fmaf(H12, byy, H22 * bzz));
                 const float T12 = fmaf(J0, cx2, fmaf(J1, cy2, J2 * cz2)) + fmaf(ax, hx, fmaf(ay, hy, az * hz));
-                float *p = dp + (size_t) (3 * k) * BRICK_VOX;
-                p[0] = fmaf(p[0], a_keep, T1);
-                p[BRICK_VOX] = fmaf(p[BRICK_VOX], a_keep, T2);
-                p[2 * BRICK_VOX] = fmaf(p[2 * BRICK_VOX], a_keep, T12);
+                p[0] = fmaf(o1, a_keep, T1);
+                p[BRICK_VOX] = fmaf(o2, a_keep, T2);
+                p[2 * BRICK_VOX] = fmaf(o12, a_keep, T12);
             }
         }
     }
@@ -266,9 +276,9 @@ template <int C> __global__ void __launch_bounds__(512) integrate_kernel(const I
             n_upd += __shfl_down_sync(0xffffffffu, n_upd, o);
             n_der += __shfl_down_sync(0xffffffffu, n_der, o);
         }
-        if ((tid & 31) == 0 && n_upd) atomicAdd(P.stats, n_upd);
-        if ((tid & 31) == 0 && n_der) atomicAdd(P.stats + 2, n_der);
-        if (tid == 0 && blockIdx.x == 0) P.stats[1] = (unsigned long long) nlist;
+        if ((threadIdx.x & 31) == 0 && n_upd) atomicAdd(P.stats, n_upd);
+        if ((threadIdx.x & 31) == 0 && n_der) atomicAdd(P.stats + 2, n_der);
+        if (threadIdx.x == 0 && blockIdx.x == 0) P.stats[1] = (unsigned long long) nlist;
     }
 }
 
@@ -332,7 +342,7 @@ xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_rang
     v->d_brick_list = nullptr;
     v->d_list_count = nullptr;
     v->d_live = nullptr;
-    if (e == cudaSuccess) e = cudaMalloc(&v->d_brick_list, nbricks * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_brick_list, nbricks * sizeof(int2));
     if (e == cudaSuccess) e = cudaMalloc(&v->d_list_count, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&v->d_live, nbricks);
     v->ev_k0 = v->ev_k1 = nullptr;
@@ -467,13 +477,13 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
     XS_CUDA(cudaMemsetAsync(v->d_list_count, 0, sizeof(unsigned int), s));
     cull_bricks_kernel<<<div_up(P.nbricks, 256), 256, 0, s>>>(P, v->d_brick_list);
     XS_LAUNCH_CHECK();
-    int grid = P.nbricks < 148 * 16 ? P.nbricks : 148 * 16;
+    int grid = 2 * P.nbricks < 148 * 24 ? 2 * P.nbricks : 148 * 24;
     size_t smem = (size_t) (v->view.ncomp > 0 ? v->view.ncomp : 1) * 12 * sizeof(float);
     XS_CUDA(cudaEventRecord(v->ev_k0, s));
     if (v->comps == 1)
-        integrate_kernel<1><<<grid, 512, smem, s>>>(P);
+        integrate_kernel<1><<<grid, INT_THREADS, smem, s>>>(P);
     else
-        integrate_kernel<3><<<grid, 512, smem, s>>>(P);
+        integrate_kernel<3><<<grid, INT_THREADS, smem, s>>>(P);
     XS_LAUNCH_CHECK();
     XS_CUDA(cudaEventRecord(v->ev_k1, s));
     XS_CUDA(cudaMemcpyAsync(v->h_stats, v->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));

@@ -72,7 +72,7 @@ struct xs_volume {
     int hit_capacity;    // pixels
     unsigned long long *d_stats;
     unsigned long long *h_stats;
-    int *d_brick_list;            // [nbricks] bricks surviving the frustum cull of the current integration
+    int2 *d_brick_list;           // [nbricks] bricks surviving the frustum cull of the current integration
     unsigned int *d_list_count;
     unsigned char *d_live;        // [nbricks] brick has (possibly) non-zero derivative planes
     size_t bytes;
