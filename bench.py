@@ -131,6 +131,11 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this same
+# command (profiles/r01e_ncu_summary.md, 55 DCSFD directions); None where no capture exists for the configuration.
+TRAFFIC = {}
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -257,6 +262,9 @@ def run_ours(args, xs, rank, world, local_rank):
     stage_ms = {n: 0.0 for n in ("surface", "icp", "integrate", "raycast", "total")}
     abytes = {n: 0.0 for n in ("surface", "icp", "integrate", "raycast")}
     kern_ms, upd = 0.0, 0
+    icp_ms, icp_n = 0.0, 0
+    t_ms = (ctypes.c_float * 16)()
+    t_px = (ctypes.c_int * 16)()
     vol = lib.xs_kinfu_volume(k.h)
     sync()
     l0 = lib.xs_launch_count()
@@ -275,6 +283,10 @@ def run_ours(args, xs, rank, world, local_rank):
             abytes[n] += ab[n]
         kern_ms += lib.xs_volume_last_integrate_ms(vol)
         upd += k.stats()[0]
+        for j in range(lib.xs_icp_deriv_times(t_ms, t_px, 16)):  # level-0 launches of the dominant kernel
+            if t_px[j] == 640 * 480:
+                icp_ms += t_ms[j]
+                icp_n += 1
     ev1.record(lib_stream)
     sync()
     t_wall = time.perf_counter() - t0
@@ -304,6 +316,13 @@ def run_ours(args, xs, rank, world, local_rank):
     int_bytes = abytes["integrate"] / K
     int_ms = kern_ms / K
     achieved = int_bytes / (int_ms * 1e-3) / 1e9 if int_ms > 0 else 0.0
+    # dominant kernel of the step: icp_deriv_kernel at pyramid level 0 (5 launches per frame).  Algorithmic bytes per
+    # launch: per pixel the real current + previous maps (48 B) and 24 B per derivative
+    # component of the previous maps, plus the 27 sums per component written out.
+    D = ncomp_local
+    icp_bytes = 640 * 480 * (48 + 24 * D) + 27 * 8 * (1 + D)
+    icp_kernel_ms = icp_ms / icp_n if icp_n else 0.0
+    icp_achieved = icp_bytes / (icp_kernel_ms * 1e-3) / 1e9 if icp_kernel_ms > 0 else 0.0
     # per step: depth frame + pose derivative components for ICP (initial pose), integration (v2c) and raycast
     # (c2v, v2w) in; final ICP pose with all derivative components, status and integration statistics out
     h2d = 640 * 480 * 2 + (1 + ncomp_local) * 48 + ncomp_local * 48 * 3 + (1 + ncomp_local) * 64
@@ -319,9 +338,13 @@ def run_ours(args, xs, rank, world, local_rank):
         "e2e": {"value": K / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "integrate_kernel<%d>" % args.comps, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": int_bytes, "kernel_ms": int_ms, "updated_voxels_per_launch": upd / K},
+        "roofline": {"bound": "hbm", "kernel": "icp_deriv_kernel<%d> (pyramid level 0; %.0f%% of the step)" % (args.comps, 100 * 5 * icp_kernel_ms / (t_dev / K * 1e3)),
+                     "achieved": icp_achieved, "peak": peak, "unit": "GB/s", "frac": icp_achieved / peak, "traffic": TRAFFIC.get("icp_deriv"),
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": icp_bytes, "kernel_ms": icp_kernel_ms, "launches_timed": icp_n,
+                     "fp32_floor_note": "this kernel is co-bound by the FP32 FMA pipe (DESIGN.md 5.2)"},
+        "roofline_integrate": {"bound": "hbm", "kernel": "integrate_kernel<%d>" % args.comps, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                               "frac": achieved / peak, "traffic": TRAFFIC.get("integrate"), "algorithmic_bytes_per_launch": int_bytes,
+                               "kernel_ms": int_ms, "updated_voxels_per_launch": upd / K},
         "wall_ms_per_step": t_wall / K * 1e3,
         "stages_ms_per_step": {n: v / K for n, v in stage_ms.items()},
         "stages_algorithmic_GBps": {n: (abytes[n] / K) / (stage_ms[n] / K * 1e-3) / 1e9 if stage_ms[n] > 0 else 0.0 for n in abytes},

@@ -139,6 +139,10 @@ int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_curr, const fl
                          int comps, int dirs, float dist_thres, float angle_thres, double *A_host, double *b_host,
                          void *stream);
 
+/* Device durations (CUDA events on the launching stream) of the derivative-accumulation kernel launches of the last
+ * xs_kinfu_pose_estimate / xs_estimate_combined, with the pixel count of each launch (roofline timing). */
+int xs_icp_deriv_times(float *ms, int *npix, int max_n);
+
 /* ---------------------------------------------------------------- pipeline (a4, a8, a13) */
 /* The YAML keys read by KinectFusionReconstruction::SetYamlParameters (KinectFusionReconstruction.cpp:12-72) */
 typedef struct {

@@ -79,6 +79,7 @@ SYMBOLS = {
     "xs_kinfu_volume": (_vp, [_vp]),
     "xs_kinfu_map": (_vp, [_vp, _i, _i, _pi, _pi, _pi]),
     "xs_kinfu_get_times": (_i, [_vp, _pf]),
+    "xs_icp_deriv_times": (_i, [_vp, _vp, _i]),
     "xs_kinfu_enable_icp_log": (_i, [_vp, _i]),
     "xs_kinfu_take_icp_log": (_i, [_vp, _pd, _i]),
     "xs_kinfu_get_stats": (_i, [_vp, _pull]),

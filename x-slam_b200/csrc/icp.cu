@@ -66,8 +66,8 @@ XS_DEV double warp_transpose_reduce(double (&v)[32]) {
 }
 
 // real products row_i * row_j for e = 0..26 with compile-time row indices (fold over E)
-template <int... E> XS_DEV void fill_real(double (&v)[32], const float (&r)[7], std::integer_sequence<int, E...>) {
-    ((v[E] = (double) __fmul_rn(r[tri_i(E)], r[tri_j(E)])), ...);
+template <int... E> XS_DEV void add_real(double (&v)[32], const float (&r)[7], std::integer_sequence<int, E...>) {
+    ((v[E] += (double) __fmul_rn(r[tri_i(E)], r[tri_j(E)])), ...);
 }
 
 // per-pixel association record, SoA planes of npix elements each
@@ -81,7 +81,7 @@ struct IcpParams {
     int rows, cols, dirs, ncomp;
     float dist_thres, angle_thres;
     int *rec_idx;      // [npix] matched linear index in the previous maps, -1 = no correspondence
-    float *rec_f;      // [REC_F][npix]
+    float4 *rec_f;     // [npix][4]: (vc.xyz, s.x) (s.yz, n.xy) (n.z, e.xyz) (cr.xyz, r6) - 64 contiguous bytes per pixel
     double *partials;  // real: [gridDim.x][27]
     double *sums;      // [27*(1+ncomp)]
     unsigned int *ticket;
@@ -104,6 +104,10 @@ __global__ void __launch_bounds__(256) icp_assoc_kernel(const IcpParams P) {
     __syncthreads();
     const size_t plane = (size_t) P.rows * P.cols;
     const int ntiles = P.tiles_x * P.tiles_y;
+    // per-thread double sums over the CTA's tiles (a thread sees at most ceil(ntiles / gridDim.x) pixels), reduced once
+    double v[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = 0.0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int x = (tile % P.tiles_x) * 32 + threadIdx.x;
         const int y = (tile / P.tiles_x) * 8 + threadIdx.y;
@@ -174,32 +178,27 @@ __global__ void __launch_bounds__(256) icp_assoc_kernel(const IcpParams P) {
             row[5] = nz;
             row[6] = __fadd_rn(__fadd_rn(__fmul_rn(nx, ex), __fmul_rn(ny, ey)), __fmul_rn(nz, ez));
             if (P.ncomp > 0) {
-                const size_t pix = (size_t) y * P.cols + x;
-                float *f = P.rec_f + pix;
-                f[0 * plane] = vcx, f[1 * plane] = vcy, f[2 * plane] = vcz;
-                f[3 * plane] = gx, f[4 * plane] = gy, f[5 * plane] = gz;
-                f[6 * plane] = nx, f[7 * plane] = ny, f[8 * plane] = nz;
-                f[9 * plane] = ex, f[10 * plane] = ey, f[11 * plane] = ez;
-                f[12 * plane] = row[0], f[13 * plane] = row[1], f[14 * plane] = row[2];
-                f[15 * plane] = row[6];
+                float4 *f = P.rec_f + ((size_t) y * P.cols + x) * 4;
+                f[0] = make_float4(vcx, vcy, vcz, gx);
+                f[1] = make_float4(gy, gz, nx, ny);
+                f[2] = make_float4(nz, ex, ey, ez);
+                f[3] = make_float4(row[0], row[1], row[2], row[6]);
             }
         }
         if (inside && P.ncomp > 0) P.rec_idx[(size_t) y * P.cols + x] = found ? (int) ((size_t) uy * P.cols + ux) : -1;
-        // 27 products, widened to double (ICP.cu:273-274); warp transpose-reduce, then the 8 warps in fixed order
-        double v[32];
-#pragma unroll
-        for (int e = 27; e < 32; ++e) v[e] = 0.0;
-        fill_real(v, row, std::make_integer_sequence<int, 27>());
-        s_stage[warp][lane] = warp_transpose_reduce(v);
-        __syncthreads();
-        if (tid < 27) {
-            double sum = 0.0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) sum += s_stage[w][tid];
-            s_acc[tid] += sum;
-        }
-        __syncthreads();
+        // 27 products, widened to double (ICP.cu:273-274)
+        if (found) add_real(v, row, std::make_integer_sequence<int, 27>());
     }
+    // warp transpose-reduce, then the 8 warps in fixed order
+    s_stage[warp][lane] = warp_transpose_reduce(v);
+    __syncthreads();
+    if (tid < 27) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += s_stage[w][tid];
+        s_acc[tid] = sum;
+    }
+    __syncthreads();
     // ---------------- block partials, then the last block reduces over blocks in block order
     if (tid < 27) P.partials[(size_t) blockIdx.x * 27 + tid] = s_acc[tid];
     __threadfence();
@@ -249,10 +248,27 @@ XS_DEV void cross3_add(const float *a, const float *b, float *o) {
 }
 XS_DEV float dot3(const float *a, const float *b) { return fmaf(a[0], b[0], fmaf(a[1], b[1], a[2] * b[2])); }
 
+// asynchronous 4-byte global -> shared copies (LDGSTS): the prefetch of the next pixel costs no registers
+XS_DEV void cp_async4(float *smem_dst, const float *gsrc) {
+    const unsigned sdst = (unsigned) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+XS_DEV void cp_async16(float4 *smem_dst, const float4 *gsrc) {
+    const unsigned sdst = (unsigned) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+XS_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> XS_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// staged per-pixel inputs: 16 record floats + 3 components x (dn[3], dd[3]) gathered at the matched pixel
+constexpr int DERIV_IN = REC_F + 18;
+constexpr int DERIV_STAGES = 2;
+constexpr size_t DERIV_SMEM = (size_t) DERIV_STAGES * DERIV_IN * 256 * sizeof(float);  // also covers the reduction buffers
+
 template <int C> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(const IcpParams P) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ float s_pose[3][12];
-    __shared__ float s_t[8][27][33];
-    __shared__ double s_w[3][8][27];
+    float *s_in = reinterpret_cast<float *>(s_raw);  // [stage][DERIV_IN][256]
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int group = blockIdx.x, chunk = blockIdx.y;
@@ -270,17 +286,53 @@ template <int C> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(cons
 #pragma unroll
         for (int e = 0; e < 27; ++e) acc[a][e] = 0.f;
     const int base = chunk * 256 * P.ppt;
+    // Software pipeline without registers: the inputs of pixel j+1 (record + the gathers that depend on its matched
+    // index) are copied global -> shared asynchronously while pixel j is processed; matched indices run two pixels
+    // ahead in registers.  Every thread reads back only what it copied itself, so no barrier is needed.
+    auto issue = [&](int stage, int p, int q) {
+        if (q >= 0) {
+            float *dst = s_in + (size_t) stage * DERIV_IN * 256 + tid;
+            float4 *dst4 = reinterpret_cast<float4 *>(s_in + (size_t) stage * DERIV_IN * 256) + tid;  // [4][256] float4
+            const float4 *f = P.rec_f + (size_t) p * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async16(dst4 + i * 256, f + i);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int comp = min(comp0 + a, P.ncomp - 1);  // out-of-range slots re-read a valid plane; their sums are dropped
+                // 32-bit element offsets (a map set is < 2^32 floats: checked by the host wrapper): one IMAD.WIDE per copy
+                const unsigned uplane = (unsigned) plane;
+                const unsigned o = (unsigned) q + (unsigned) (1 + comp) * 3u * uplane;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    cp_async4(dst + (REC_F + a * 6 + c) * 256, P.nmap_prev + (o + c * uplane));
+                    cp_async4(dst + (REC_F + a * 6 + 3 + c) * 256, P.vmap_prev + (o + c * uplane));
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    auto idx_at = [&](int j) {
+        const int p = base + j * 256 + tid;
+        return (j < P.ppt && p < npix) ? P.rec_idx[p] : -1;
+    };
+    int q_cur = idx_at(0), q_nxt = idx_at(1);
+    issue(0, base + tid, q_cur);
     for (int j = 0; j < P.ppt; ++j) {
         const int p = base + j * 256 + tid;
-        if (p >= npix) break;
-        const int q = P.rec_idx[p];
+        issue((j + 1) & 1, p + 256, q_nxt);
+        const int q = q_cur;
+        q_cur = q_nxt;
+        q_nxt = idx_at(j + 2);
+        cp_async_wait<1>();  // the copies of pixel j have landed
         if (q < 0) continue;
-        const float *f = P.rec_f + p;
-        const float vc[3] = {f[0 * plane], f[1 * plane], f[2 * plane]};
-        const float s[3] = {f[3 * plane], f[4 * plane], f[5 * plane]};
-        const float n[3] = {f[6 * plane], f[7 * plane], f[8 * plane]};
-        const float e[3] = {f[9 * plane], f[10 * plane], f[11 * plane]};
-        const float r[7] = {f[12 * plane], f[13 * plane], f[14 * plane], n[0], n[1], n[2], f[15 * plane]};
+        const float *in = s_in + (size_t) (j & 1) * DERIV_IN * 256 + tid;
+        const float4 *in4 = reinterpret_cast<const float4 *>(s_in + (size_t) (j & 1) * DERIV_IN * 256) + tid;
+        const float4 f0 = in4[0], f1 = in4[256], f2 = in4[512], f3 = in4[768];
+        const float vc[3] = {f0.x, f0.y, f0.z};
+        const float s[3] = {f0.w, f1.x, f1.y};
+        const float n[3] = {f1.z, f1.w, f2.x};
+        const float e[3] = {f2.y, f2.z, f2.w};
+        const float r[7] = {f3.x, f3.y, f3.z, n[0], n[1], n[2], f3.w};
         float ds[3][3], dn[3][3], de[3][3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -288,12 +340,10 @@ template <int C> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(cons
             ds[a][0] = fmaf(m[0], vc[0], fmaf(m[1], vc[1], fmaf(m[2], vc[2], m[9])));
             ds[a][1] = fmaf(m[3], vc[0], fmaf(m[4], vc[1], fmaf(m[5], vc[2], m[10])));
             ds[a][2] = fmaf(m[6], vc[0], fmaf(m[7], vc[1], fmaf(m[8], vc[2], m[11])));
-            const int comp = min(comp0 + a, P.ncomp - 1);  // out-of-range slots re-read a valid plane; their sums are dropped
-            const size_t o = (size_t) q + (size_t) (1 + comp) * 3 * plane;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                dn[a][c] = P.nmap_prev[o + c * plane];
-                de[a][c] = P.vmap_prev[o + c * plane] - ds[a][c];
+                dn[a][c] = in[(REC_F + a * 6 + c) * 256];
+                de[a][c] = in[(REC_F + a * 6 + 3 + c) * 256] - ds[a][c];
             }
         }
         float d[3][7];
@@ -314,7 +364,12 @@ template <int C> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(cons
         accumulate_products<C>(acc, r, d[0], d[1], d[2], std::make_integer_sequence<int, 27>());
     }
     // ---------------- reduce in double, fixed order: the FP32 per-thread sums go through shared memory; thread (w, e)
-    // widens and adds the 32 lanes of warp w for product e, then the 8 warps are combined.
+    // widens and adds the 32 lanes of warp w for product e, then the 8 warps are combined.  The reduction buffers
+    // reuse the staging memory.
+    cp_async_wait<0>();
+    __syncthreads();
+    float(*s_t)[27][33] = reinterpret_cast<float(*)[27][33]>(s_raw);                                   // [8][27][33]
+    double(*s_w)[8][27] = reinterpret_cast<double(*)[8][27]>(s_raw + sizeof(float) * 8 * 27 * 33 + 64);  // [3][8][27]
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
@@ -684,10 +739,15 @@ struct IcpScratch {
     unsigned int *d_ticket = nullptr;
     float *d_pose = nullptr, *h_pose = nullptr;  // seam-level entry point only: [(1+ncomp)][12]
     int *d_rec_idx = nullptr;
-    float *d_rec_f = nullptr;
+    float4 *d_rec_f = nullptr;
     int cap_vals = 0, cap_comp = -1, cap_pix = 0;
     size_t cap_dpart = 0;
     int max_blocks = 296;
+    // CUDA-event brackets of the derivative kernel launches since the last reset (roofline timing, bench.py)
+    static constexpr int MAX_TIMED = 16;
+    cudaEvent_t ev0[MAX_TIMED] = {}, ev1[MAX_TIMED] = {};
+    int timed_npix[MAX_TIMED] = {};
+    int n_timed = 0;
 };
 static IcpScratch g_icp;
 
@@ -717,7 +777,7 @@ static int icp_reserve(int ncomp, int npix, size_t dpart) {
         cudaFree(g_icp.d_rec_idx);
         cudaFree(g_icp.d_rec_f);
         XS_CUDA(cudaMalloc(&g_icp.d_rec_idx, (size_t) npix * sizeof(int)));
-        XS_CUDA(cudaMalloc(&g_icp.d_rec_f, (size_t) npix * REC_F * sizeof(float)));
+        XS_CUDA(cudaMalloc(&g_icp.d_rec_f, (size_t) npix * 4 * sizeof(float4)));
         g_icp.cap_pix = npix;
     }
     if (dpart > g_icp.cap_dpart) {
@@ -734,6 +794,10 @@ int icp_accumulate_async(const float *d_pose_curr, const float *d_vmap_curr, con
                          int dirs, float dist_thres, float angle_thres, cudaStream_t s) {
     const int ncomp = comps * dirs;
     const int npix = rows * cols;
+    if ((double) (1 + ncomp) * 3.0 * npix >= 4294967296.0) {
+        set_error("icp: a map set must hold fewer than 2^32 floats");
+        return XS_ERR_ARG;
+    }
     IcpParams P;
     // derivative pass decomposition: a thread sums at most 16 pixels in FP32 before the double reduction
     P.groups = (ncomp + 2) / 3;
@@ -771,11 +835,30 @@ int icp_accumulate_async(const float *d_pose_curr, const float *d_vmap_curr, con
     XS_LAUNCH_CHECK();
     if (ncomp > 0) {
         dim3 g2(P.groups, P.chunks);
+        const int slot = g_icp.n_timed < IcpScratch::MAX_TIMED ? g_icp.n_timed : -1;
+        if (slot >= 0) {
+            if (!g_icp.ev0[slot]) {
+                XS_CUDA(cudaEventCreate(&g_icp.ev0[slot]));
+                XS_CUDA(cudaEventCreate(&g_icp.ev1[slot]));
+            }
+            XS_CUDA(cudaEventRecord(g_icp.ev0[slot], s));
+        }
+        static bool smem_set = false;
+        if (!smem_set) {
+            XS_CUDA(cudaFuncSetAttribute(icp_deriv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DERIV_SMEM));
+            XS_CUDA(cudaFuncSetAttribute(icp_deriv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DERIV_SMEM));
+            smem_set = true;
+        }
         if (comps == 1)
-            icp_deriv_kernel<1><<<g2, 256, 0, s>>>(P);
+            icp_deriv_kernel<1><<<g2, 256, DERIV_SMEM, s>>>(P);
         else
-            icp_deriv_kernel<3><<<g2, 256, 0, s>>>(P);
+            icp_deriv_kernel<3><<<g2, 256, DERIV_SMEM, s>>>(P);
         XS_LAUNCH_CHECK();
+        if (slot >= 0) {
+            XS_CUDA(cudaEventRecord(g_icp.ev1[slot], s));
+            g_icp.timed_npix[slot] = npix;
+            ++g_icp.n_timed;
+        }
         icp_finish_kernel<<<P.groups, 32 * 27, 0, s>>>(P);
         XS_LAUNCH_CHECK();
     }
@@ -803,9 +886,22 @@ int icp_solve_async(const float *d_pose_in, float *d_pose_out, int comps, int di
     return XS_OK;
 }
 
+void icp_timing_reset() { g_icp.n_timed = 0; }
+
 }  // namespace xs
 
 using namespace xs;
+
+// Device durations (CUDA events on the launching stream) of the icp_deriv_kernel launches since the last
+// xs_kinfu_pose_estimate / xs_estimate_combined began; call after the stream has been synchronised.
+extern "C" int xs_icp_deriv_times(float *ms, int *npix, int max_n) {
+    int n = 0;
+    for (; n < g_icp.n_timed && n < max_n; ++n) {
+        if (cudaEventElapsedTime(&ms[n], g_icp.ev0[n], g_icp.ev1[n]) != cudaSuccess) break;
+        npix[n] = g_icp.timed_npix[n];
+    }
+    return n;
+}
 
 extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_curr, const float *d_nmap_curr,
                                     const xs_pose *prev, xs_intr intr, const float *d_vmap_g_prev,
@@ -823,6 +919,7 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
     cudaStream_t s = (cudaStream_t) stream;
     int rc = icp_reserve(ncomp, rows * cols, 0);
     if (rc != XS_OK) return rc;
+    icp_timing_reset();
     XS_CUDA(cudaStreamSynchronize(s));  // pinned staging reuse
     float *h = g_icp.h_pose;
     for (int e = 0; e < 9; ++e) h[e] = curr->R[e];

@@ -29,6 +29,7 @@ extern long long g_launches;
 int icp_accumulate_async(const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
                          xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
                          int dirs, float dist_thres, float angle_thres, cudaStream_t s);
+void icp_timing_reset();
 int icp_solve_async(const float *d_pose_in, float *d_pose_out, int comps, int dirs, int solve_mode, int *d_status,
                     double *d_log, cudaStream_t s);
 }  // namespace xs
@@ -243,6 +244,7 @@ int xs_kinfu_pose_estimate(xs_kinfu *k) {
     set_ctx(k);
     k->icp_iters_done = 0;
     k->icp_log.clear();
+    icp_timing_reset();
     if (k->frame_id == 0) return 0;
     const xs_config &c = k->cfg;
     const int ncomp = k->ncomp;
