@@ -183,6 +183,8 @@ int xs_kinfu_calculate_point_cloud(xs_kinfu *k);
 int xs_kinfu_frame_id(const xs_kinfu *k);
 /* world2camera (KinectFusionReconstruction.h:31): out [(1+ncomp)][16] row-major */
 int xs_kinfu_get_world2camera(const xs_kinfu *k, float *out);
+/* sets world2camera (real part + all derivative components, [(1+ncomp)][16]) before the first frame */
+int xs_kinfu_set_world2camera(xs_kinfu *k, const float *in);
 /* camera-to-world of the last frame, real part, as written to frame-%06d.pose.txt (main.cpp:61) */
 int xs_kinfu_get_pose_c2w(const xs_kinfu *k, float *out16);
 xs_volume *xs_kinfu_volume(xs_kinfu *k);

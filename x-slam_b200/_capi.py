@@ -86,6 +86,7 @@ SYMBOLS = {
     "xs_kinfu_get_algorithmic_bytes": (_i, [_vp, _pd]),
     "xs_kinfu_pose_record_device": (_vp, [_vp]),
     "xs_kinfu_stream": (_vp, [_vp]),
+    "xs_kinfu_set_world2camera": (_i, [_vp, _pf]),
     "xs_save_pose_txt": (_i, [C.c_char_p, _pf]),
     "xs_export_ply": (_i, [C.c_char_p, _pf, _pf, _l]),
     "xs_synth_depth": (_i, [_pf, Intr, _i, _i, C.POINTER(C.c_uint16)]),

@@ -422,6 +422,28 @@ int xs_kinfu_get_world2camera(const xs_kinfu *k, float *out) {
     return XS_OK;
 }
 
+// Replaces world2camera (real part and every derivative component) before the first frame: the general form of the
+// reference's commented seeding line (KinectFusionReconstruction.cpp:22), e.g. to start from a relocalised pose.
+int xs_kinfu_set_world2camera(xs_kinfu *k, const float *in) {
+    if (!k || !in || k->frame_id != 0) {
+        set_error("xs_kinfu_set_world2camera: only before the first frame");
+        return XS_ERR_ARG;
+    }
+    set_ctx(k);
+    for (int q = 0; q <= k->ncomp; ++q)
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                const float v = in[(size_t) q * 16 + i * 4 + j];
+                if (q == 0)
+                    k->world2camera.m[i][j].v = v;
+                else
+                    k->world2camera.m[i][j].d[q - 1] = v;
+            }
+    k->record.clear();
+    k->record.push_back(k->world2camera);
+    return XS_OK;
+}
+
 int xs_kinfu_get_pose_c2w(const xs_kinfu *k, float *out16) {
     if (!k || !out16) return XS_ERR_ARG;
     set_ctx(k);

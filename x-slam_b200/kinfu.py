@@ -175,6 +175,14 @@ class KinectFusionReconstruction:
         check(self.lib.xs_kinfu_get_world2camera(self.h, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out.reshape(1 + self.ncomp, 4, 4)
 
+    @world2camera.setter
+    def world2camera(self, value):
+        """Only before the first frame: real part + every derivative component, [(1+ncomp), 4, 4]."""
+        v = np.ascontiguousarray(value, np.float32).reshape(-1)
+        if v.size != (1 + self.ncomp) * 16:
+            raise ValueError("world2camera must hold (1+ncomp) 4x4 matrices")
+        check(self.lib.xs_kinfu_set_world2camera(self.h, v.ctypes.data_as(C.POINTER(C.c_float))), "world2camera")
+
     def pose_c2w(self):
         """world2camera_record.back().inverse().real(), main.cpp:61"""
         out = np.zeros((16,), np.float32)
