@@ -136,3 +136,55 @@ def test_integration_second_order_vs_finite_differences(xs, pair, threshold):
         f.write("integrate pair %s thr %g band voxels %d scale %.3g rel err q50 %.3g q75 %.3g q90 %.3g\n" %
                 (pair, threshold, int(m.sum()), scale, q50, q75, q90))
     assert q50 <= 1e-3 and q75 <= 2e-2, (q50, q75, q90)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pair", [(0, 4), (5, 2), (3, 3)])
+def test_raycast_second_order_vs_finite_differences(xs, pair):
+    """eps1eps2 maps of one DCSFD raycast == central difference of the eps maps of two CSFD raycasts taken at
+    theta2 = +-delta, where BOTH the camera pose and the volume (value + derivative planes) are moved along the second
+    parameter.  Pins the derivative-only hit kernel (trilinear gradient / mixed-partial contractions) for C = 3."""
+    import torch
+    from xslam_b200 import ops
+    from common import ICL, poses_for_frame
+    G = xs.se3_generators()
+    A, B = G[pair[0]], G[pair[1]]
+    res, voxel = 128, 0.06
+    intr = xs.Intr(**ICL)
+    # a volume with consistent real / eps1 / eps2 / eps1eps2 planes: two DCSFD integrations along the same family
+    vol3 = ops.TsdfVolume((res,) * 3, voxel, 3, comps=3, dirs=1)
+    for f in (0, 6):
+        V0, _, _ = poses_for_frame(xs, f)
+        base, d1, dB, d12 = _pose_family(V0, A, B)
+        depth = torch.from_numpy(xs.synth_depth(f).astype(np.int16)).cuda()
+        ops.integrateTsdfVolume(depth, intr, 100, vol3, _batch(ops, base(0.0), [H_ * d1(0.0), H_ * dB, H_ * H_ * d12]), 0.06)
+    _, C0, v2w = poses_for_frame(xs, 6)
+    cbase, cd1, cdB, cd12 = _pose_family(C0, A, B)
+    Z = np.zeros((4, 4))
+    vm3, nm3 = ops.raycast(intr, _batch(ops, cbase(0.0), [H_ * cd1(0.0), H_ * cdB, H_ * H_ * cd12]), _batch(ops, v2w, [Z, Z, Z]),
+                           vol3, 480, 640)
+    vm3, nm3 = vm3.cpu().numpy().astype(np.float64), nm3.cpu().numpy().astype(np.float64)
+    val, wgt = vol3.value(), vol3.weight()
+    D1, D2, D12 = vol3.grad(0), vol3.grad(1), vol3.grad(2)
+    delta = 1e-3
+    maps = []
+    for sgn in (+1.0, -1.0):
+        vol1 = ops.TsdfVolume((res,) * 3, voxel, 3, comps=1, dirs=1)
+        vol1.load((val + (sgn * delta / H_) * D2).contiguous(), wgt, (D1 + (sgn * delta / H_) * D12).contiguous(), 0)
+        vm, nm = ops.raycast(intr, _batch(ops, cbase(sgn * delta), [H_ * cd1(sgn * delta)]), _batch(ops, v2w, [Z]), vol1, 480, 640)
+        maps.append((vm.cpu().numpy().astype(np.float64), nm.cpu().numpy().astype(np.float64)))
+    out = []
+    for name, m3, idx in (("vertex", vm3, 0), ("normal", nm3, 1)):
+        mp, mn = maps[0][idx], maps[1][idx]
+        ok = ~np.isnan(m3[0, 0]) & ~np.isnan(mp[0, 0]) & ~np.isnan(mn[0, 0])
+        assert int(ok.sum()) > 100000
+        fd = (mp[1] - mn[1])[:, ok] / (2 * delta) / H_
+        d12m = m3[3][:, ok] / H_ / H_
+        scale = max(np.percentile(np.abs(d12m), 99), np.percentile(np.abs(m3[1][:, ok]) / H_, 99), 0.05)
+        err = np.abs(fd - d12m).max(0)
+        q50, q75, q90 = (np.percentile(err, q) / scale for q in (50, 75, 90))
+        out.append((name, q50, q75, q90, scale))
+        with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "fd_second_order.txt"), "a") as f:
+            f.write("raycast %s pair %s pixels %d scale %.3g rel err q50 %.3g q75 %.3g q90 %.3g\n" % (name, pair, int(ok.sum()), scale, q50, q75, q90))
+    for name, q50, q75, q90, scale in out:
+        assert q50 <= 2e-3 and q75 <= 2e-2, (name, q50, q75, q90)
