@@ -131,8 +131,9 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this same
-# command (profiles/r01e_ncu_summary.md, 55 DCSFD directions); None where no capture exists for the configuration.
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this same
+# command (profiles/r01d_ncu_summary.md: 512^3, 55 DCSFD directions, 1 GPU); None for any other configuration.
+TRAFFIC_55 = {"icp_deriv": 1.2355e9, "integrate": 6.35e8}
 TRAFFIC = {}
 
 
@@ -312,6 +313,8 @@ def run_ours(args, xs, rank, world, local_rank):
             dist.destroy_process_group()
         return
     ncomp_local = len(mine) * args.comps
+    if world == 1 and args.res == 512 and args.dirs == 55 and args.comps == 3:
+        TRAFFIC.update(TRAFFIC_55)
     peak, peak_src = measured_hbm_peak()
     int_bytes = abytes["integrate"] / K
     int_ms = kern_ms / K
