@@ -53,6 +53,17 @@ XS_DEV void store3(float *map, int comp, int rows, int cols, int y, int x, float
     p[2 * plane] = c;
 }
 
+// floor(RN(p / vs)) — the voxel index of RayCaster.cu:80-86 — without an IEEE division on the common path: the product
+// with the rounded reciprocal is within a few ulp of the correctly rounded quotient, so its floor can only differ when
+// the quotient is that close to an integer; those cases (a fraction below 1e-3 of the samples) take the exact division.
+XS_DEV int voxel_floor(float p, float vs, float inv_vs) {
+    const float q = p * inv_vs;
+    const float f = floorf(q);
+    const float frac = q - f;
+    if (frac < 1e-3f || frac > 0.999f || !(fabsf(q) < 4096.f)) return __float2int_rd(__fdiv_rn(p, vs));
+    return (int) f;
+}
+
 // ---- pass 1: the real march, RayCaster.cu:222-247.  One thread per pixel on the value plane only; the result
 // (time of the sample before the + -> - crossing, or a negative number) is shared by every direction.
 // The loop reads LOOKAHEAD samples ahead of the exit tests (sample positions do not depend on loaded values), which
@@ -67,6 +78,7 @@ __global__ void __launch_bounds__(256) raycast_march_kernel(const RaycastParams 
     ray_setup<1, 0>(P, x, y, 0, s0, d0);
     const float sx = s0.x.v, sy = s0.y.v, sz = s0.z.v, dx = d0.x.v, dy = d0.y.v, dz = d0.z.v;
     const float vs = V.voxel;
+    const float inv_vs = __fdiv_rn(1.f, vs);
     float time_curr = 0.2f;
     const float max_time = 5.0f;
     int gx = __float2int_rd(__fdiv_rn(__fmaf_rn(dx, time_curr, sx), vs));
@@ -86,9 +98,9 @@ __global__ void __launch_bounds__(256) raycast_march_kernel(const RaycastParams 
         for (int i = 0; i < MARCH_LOOKAHEAD; ++i) {
             tc[i] = t;
             const float tt = __fadd_rn(t, P.time_step);
-            const int ix = __float2int_rd(__fdiv_rn(__fmaf_rn(dx, tt, sx), vs));
-            const int iy = __float2int_rd(__fdiv_rn(__fmaf_rn(dy, tt, sy), vs));
-            const int iz = __float2int_rd(__fdiv_rn(__fmaf_rn(dz, tt, sz), vs));
+            const int ix = voxel_floor(__fmaf_rn(dx, tt, sx), vs, inv_vs);
+            const int iy = voxel_floor(__fmaf_rn(dy, tt, sy), vs, inv_vs);
+            const int iz = voxel_floor(__fmaf_rn(dz, tt, sz), vs, inv_vs);
             inside[i] = (ix >= 0 && iy >= 0 && iz >= 0 && ix < V.rx && iy < V.ry && iz < V.rz);
             val[i] = inside[i] ? read_value(V, ix, iy, iz) : 0.f;
             t = tt;  // time_curr += time_step (:236)
