@@ -3,7 +3,7 @@
 // Replaces Combined::{search_newton, operator()} / combinedKernel (XKinectFusion/src/ICP.cu:166-281,357),
 // TranformReduction / TransformEstimatorKernel (ICP.cu:120-164) and estimateCombined (ICP.cu:365-429).
 //
-// Four launches per Gauss-Newton iteration and NO host round trip (the reference: 2 launches per direction and
+// Two launches per Gauss-Newton iteration and NO host round trip (the reference: 2 launches per direction and
 // iteration, then sync + download + host Eigen solve, ICP.cu:414-417 / KinectFusionReconstruction.cpp:196-224):
 //   1. icp_assoc_kernel   data association (projection, bounds, NaN, distance and angle gates) ONCE per pixel on real
 //                         parts, the real 7-vector row [cross(s,n), n, n.(d-s)], its 27 upper-triangular products
@@ -13,13 +13,13 @@
 //   2. icp_deriv_kernel   one CTA per (pixel chunk, direction group): reads the record, gathers that direction's
 //                         derivative planes of the previous maps at the matched pixel and accumulates the derivative
 //                         components of the 27 products (linearised row algebra, no recomputation of the real path).
-//                         A thread sums at most 32 pixels in FP32, then everything is reduced in double: warp
-//                         transpose-reduction by shuffles, fixed-order combination of warps, per-CTA partials.
-//   3. icp_finish_kernel  fixed-order sum of the per-CTA partials.
-//   4. icp_solve_kernel   the host Gauss-Newton step of KinectFusionReconstruction.cpp:203-224 on the device: det guard,
-//                         6x6 LLT solve in double, Rinc = Rz*Ry*Rx, pose update - one thread per direction, every
-//                         thread redoing the (tiny) real part.  The current pose therefore lives in device memory and
-//                         the 12 iterations of a frame are queued back to back.
+//                         A thread sums at most 32 pixels in FP32, then everything is reduced in double: fixed-order
+//                         combination of lanes and warps, per-CTA partials.  The LAST CTA of a direction group to
+//                         arrive adds the per-chunk partials in a fixed order and runs the host Gauss-Newton step of
+//                         KinectFusionReconstruction.cpp:203-224 for its direction on the device (icp_solve_direction:
+//                         det guard, 6x6 LLT solve in double, Rinc = Rz*Ry*Rx, pose update - one thread per direction,
+//                         every thread redoing the tiny real part).  The current pose therefore lives in device memory
+//                         and the 12 iterations of a frame are queued back to back.
 // Instead of the reference's 27 sequential 256-thread shared-memory tree reductions per direction, the summation
 // order is fixed by construction, so results are deterministic run to run.
 #include "xs_common.cuh"
@@ -89,7 +89,20 @@ struct IcpParams {
     // derivative pass
     double *dpartials;  // [chunks][groups][81]
     int chunks, groups, ppt;
+    unsigned int *group_ticket;  // [groups] arrival counters of the derivative pass (self-resetting)
 };
+
+// the Gauss-Newton step that closes an iteration (icp_solve_direction below)
+struct SolveParams {
+    const double *sums;    // [27*(1+ncomp)]
+    const float *pose_in;  // [(1+ncomp)][12] current pose
+    float *pose_out;       // [(1+ncomp)][12] updated pose (a different buffer: blocks do not synchronise); null = no solve
+    int *status;           // [2]: 0 = ok; 1 = |det(Re A)| < 1e-15; 2 = NaN det.  [0] sticky (later iterations are skipped)
+    double *log;           // optional [27*(1+ncomp)] copy of the sums of this iteration
+    int dirs, ncomp, solve_mode;
+};
+template <int C> __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, const double *real_sums,
+                                                                  const double *comp_sums);
 
 // ---------------------------------------------------------------------------------------------------------------
 // pass 1: association + real normal equations
@@ -262,12 +275,16 @@ template <int N> XS_DEV void cp_async_wait() { asm volatile("cp.async.wait_group
 
 // staged per-pixel inputs: 16 record floats + 3 components x (dn[3], dd[3]) gathered at the matched pixel
 constexpr int DERIV_IN = REC_F + 18;
-constexpr int DERIV_STAGES = 2;
-constexpr size_t DERIV_SMEM = (size_t) DERIV_STAGES * DERIV_IN * 256 * sizeof(float);  // also covers the reduction buffers
+constexpr int DERIV_MAX_STAGES = 3;
+constexpr size_t deriv_smem(int stages) { return (size_t) stages * DERIV_IN * 256 * sizeof(float); }  // also covers the reduction buffers
 
-template <int C> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(const IcpParams P) {
+// ST = depth of the cp.async pipeline: the inputs of pixel j + ST - 1 are in flight while pixel j is processed.  The
+// gathers are DRAM round trips (the derivative planes of the previous maps do not fit L2 at level 0), so the bytes in
+// flight per SM - threads x 72 B x (ST - 1) - set the achievable bandwidth (Little's law).
+template <int C, int ST> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(const IcpParams P, const SolveParams S) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ float s_pose[3][12];
+    __shared__ bool s_last;
     float *s_in = reinterpret_cast<float *>(s_raw);  // [stage][DERIV_IN][256]
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -286,9 +303,9 @@ template <int C> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(cons
 #pragma unroll
         for (int e = 0; e < 27; ++e) acc[a][e] = 0.f;
     const int base = chunk * 256 * P.ppt;
-    // Software pipeline without registers: the inputs of pixel j+1 (record + the gathers that depend on its matched
-    // index) are copied global -> shared asynchronously while pixel j is processed; matched indices run two pixels
-    // ahead in registers.  Every thread reads back only what it copied itself, so no barrier is needed.
+    // Software pipeline without registers: the inputs of the pixels ahead (record + the gathers that depend on the
+    // matched index) are copied global -> shared asynchronously while pixel j is processed; matched indices run ST
+    // pixels ahead in registers.  Every thread reads back only what it copied itself, so no barrier is needed.
     auto issue = [&](int stage, int p, int q) {
         if (q >= 0) {
             float *dst = s_in + (size_t) stage * DERIV_IN * 256 + tid;
@@ -315,18 +332,27 @@ template <int C> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(cons
         const int p = base + j * 256 + tid;
         return (j < P.ppt && p < npix) ? P.rec_idx[p] : -1;
     };
-    int q_cur = idx_at(0), q_nxt = idx_at(1);
-    issue(0, base + tid, q_cur);
+    int qs[ST];  // qs[i] = matched index of pixel j + i
+#pragma unroll
+    for (int i = 0; i < ST; ++i) qs[i] = idx_at(i);
+#pragma unroll
+    for (int i = 0; i < ST - 1; ++i) issue(i, base + i * 256 + tid, qs[i]);
+    int st = 0;  // stage that holds pixel j
     for (int j = 0; j < P.ppt; ++j) {
         const int p = base + j * 256 + tid;
-        issue((j + 1) & 1, p + 256, q_nxt);
-        const int q = q_cur;
-        q_cur = q_nxt;
-        q_nxt = idx_at(j + 2);
-        cp_async_wait<1>();  // the copies of pixel j have landed
+        int st_in = st + ST - 1;
+        if (st_in >= ST) st_in -= ST;
+        issue(st_in, p + (ST - 1) * 256, qs[ST - 1]);
+        const int q = qs[0];
+#pragma unroll
+        for (int i = 0; i < ST - 1; ++i) qs[i] = qs[i + 1];
+        qs[ST - 1] = idx_at(j + ST);
+        const int cur = st;
+        st = (st + 1 == ST) ? 0 : st + 1;
+        cp_async_wait<ST - 1>();  // the copies of pixel j have landed
         if (q < 0) continue;
-        const float *in = s_in + (size_t) (j & 1) * DERIV_IN * 256 + tid;
-        const float4 *in4 = reinterpret_cast<const float4 *>(s_in + (size_t) (j & 1) * DERIV_IN * 256) + tid;
+        const float *in = s_in + (size_t) cur * DERIV_IN * 256 + tid;
+        const float4 *in4 = reinterpret_cast<const float4 *>(s_in + (size_t) cur * DERIV_IN * 256) + tid;
         const float4 f0 = in4[0], f1 = in4[256], f2 = in4[512], f3 = in4[768];
         const float vc[3] = {f0.x, f0.y, f0.z};
         const float s[3] = {f0.w, f1.x, f1.y};
@@ -391,21 +417,51 @@ template <int C> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(cons
         for (int w = 0; w < 8; ++w) sum += s_w[a][w][e];
         P.dpartials[((size_t) chunk * P.groups + group) * 81 + tid] = sum;
     }
-}
-
-// pass 3: fixed-order sum over the chunks.  One warp per (component slot, product): lane l sums chunks l, l+32, ...
-// in order, then a fixed xor-shuffle tree combines the lanes.
-__global__ void __launch_bounds__(32 * 27) icp_finish_kernel(const IcpParams P) {
-    const int group = blockIdx.x, lane = threadIdx.x & 31, e = threadIdx.x >> 5;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const int comp = group * 3 + a;
-        if (comp >= P.ncomp) break;
+    // ---------------- tail: the last CTA of a direction group to arrive sums the per-chunk partials in a fixed order
+    // (warp w adds its contiguous eighth of the chunks in order for products lane, lane + 32, lane + 64 - coalesced
+    // 648-byte rows, independent loads - then the eight segment sums are added in warp order) and runs the
+    // Gauss-Newton step of its direction(s) from shared memory: no separate finish / solve launches.
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(P.group_ticket + group, 1u) == (unsigned) P.chunks - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double(*s_seg)[81] = reinterpret_cast<double(*)[81]>(s_raw);               // [8][81]
+    double *s_sums = reinterpret_cast<double *>(s_raw) + 8 * 81;               // [27 real][81 of this group]
+    {
+        const int seg = (P.chunks + 7) / 8, c0 = warp * seg, c1 = min(P.chunks, c0 + seg);
+        double sum[3] = {0.0, 0.0, 0.0};
+        const double *src = P.dpartials + (size_t) group * 81 + lane;
+        const size_t cstride = (size_t) P.groups * 81;
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) {
+            const double *row = src + (size_t) c * cstride;
+            sum[0] += __ldcg(row);
+            sum[1] += __ldcg(row + 32);
+            if (lane < 17) sum[2] += __ldcg(row + 64);
+        }
+        s_seg[warp][lane] = sum[0];
+        s_seg[warp][lane + 32] = sum[1];
+        if (lane < 17) s_seg[warp][lane + 64] = sum[2];
+    }
+    if (tid == 0) P.group_ticket[group] = 0u;
+    __syncthreads();
+    if (tid < 81) {
         double sum = 0.0;
-        for (int c = lane; c < P.chunks; c += 32) sum += P.dpartials[((size_t) c * P.groups + group) * 81 + a * 27 + e];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) P.sums[(size_t) (1 + comp) * 27 + e] = sum;
+        for (int w = 0; w < 8; ++w) sum += s_seg[w][tid];
+        s_sums[27 + tid] = sum;
+        const int comp = comp0 + tid / 27;
+        if (comp < P.ncomp) P.sums[(size_t) (1 + comp) * 27 + tid % 27] = sum;
+    } else if (tid >= 96 && tid < 96 + 27) {
+        s_sums[tid - 96] = __ldcg(P.sums + (tid - 96));  // real sums of icp_assoc_kernel (previous launch)
+    }
+    if (!S.pose_out) return;
+    __syncthreads();
+    if (tid < (C == 3 ? 1 : 3)) {
+        const int q = C == 3 ? group : group * 3 + tid;
+        if (q < S.dirs) icp_solve_direction<C>(S, q, s_sums, s_sums + 27 + (C == 3 ? 0 : tid * 27));
     }
 }
 
@@ -625,27 +681,26 @@ template <int C> XS_DEV JMat3<C> jmatmul(const JMat3<C> &a, const JMat3<C> &b) {
     return r;
 }
 
-struct SolveParams {
-    const double *sums;  // [27*(1+ncomp)]
-    const float *pose_in;  // [(1+ncomp)][12] current pose
-    float *pose_out;       // [(1+ncomp)][12] updated pose (a different buffer: blocks do not synchronise)
-    int *status;         // [2]: 0 = ok; 1 = |det(Re A)| < 1e-15; 2 = NaN det.  [0] sticky (later iterations are skipped)
-    double *log;         // optional [27*(1+ncomp)] copy of the sums of this iteration
-    int dirs, ncomp, solve_mode;
-};
-
-template <int C> __global__ void __launch_bounds__(64) icp_solve_kernel(const SolveParams P) {
+// One direction q of the Gauss-Newton step (direction 0 also owns the real part).  Called by the last CTA of a direction
+// group in icp_deriv_kernel, or by icp_solve_kernel when there are no derivative components.
+// real_sums: the 27 real sums; comp_sums: the C x 27 sums of this direction's components (shared memory in both callers).
+template <int C>
+__device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, const double *real_sums, const double *comp_sums) {
     typedef Jet<C, 1> J;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;  // direction handled by this thread (thread 0 also owns the real part)
-    if (P.log)
-        for (int i = q; i < 27 * (1 + P.ncomp); i += gridDim.x * blockDim.x) P.log[i] = P.sums[i];
-    if (P.status[0] != 0 || P.status[1] != 0) {  // [0] sticky flag of earlier iterations, [1] written by this launch
-        if (q == 0) P.status[0] = P.status[0] != 0 ? P.status[0] : P.status[1];
+    const bool has_dir = q < P.dirs;
+    if (P.log) {
+        if (q == 0)
+            for (int i = 0; i < 27; ++i) P.log[i] = real_sums[i];
+        if (has_dir)
+            for (int i = 0; i < 27 * C; ++i) P.log[27 * (1 + q * C) + i] = comp_sums[i];
+    }
+    const int st0 = __ldcg(P.status), st1 = __ldcg(P.status + 1);
+    if (st0 != 0 || st1 != 0) {  // [0] sticky flag of earlier iterations, [1] written by an earlier launch
+        if (q == 0) P.status[0] = st0 != 0 ? st0 : st1;
         return;
     }
-    if (q >= P.dirs && q != 0) return;
     double A[6][6], b[6];
-    unpack_sums(P.sums, A, b);
+    unpack_sums(real_sums, A, b);
     const double det = det6_dev(A);
     if (fabs(det) < 1e-15 || isnan(det)) {
         // every thread of every block computes the same det and takes this branch; the flag is only read at kernel
@@ -660,12 +715,11 @@ template <int C> __global__ void __launch_bounds__(64) icp_solve_kernel(const So
     J x[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = jconst<C, 1>((float) xr[i]);
-    const bool has_dir = q < P.dirs;
     if (has_dir) {
         if (C == 1 && P.solve_mode == XS_SOLVE_EIGEN_LLT) {
             // one Hermitian-LLT solve with this direction's imaginary part, as the reference's one-direction run
             double Ai[6][6], bi[6];
-            unpack_sums(P.sums + (size_t) (1 + q) * 27, Ai, bi);
+            unpack_sums(comp_sums, Ai, bi);
             cplx xq[6];
             llt_hermitian_solve6_dev(A, Ai, b, bi, xq);
             for (int i = 0; i < 6; ++i) x[i].d[0] = (float) xq[i].im;
@@ -675,16 +729,16 @@ template <int C> __global__ void __launch_bounds__(64) icp_solve_kernel(const So
 #pragma unroll
             for (int a = 0; a < (C == 3 ? 2 : 1); ++a) {
                 double Aa[6][6], ba[6], t[6], rhs[6];
-                unpack_sums(P.sums + (size_t) (1 + q * C + a) * 27, Aa, ba);
+                unpack_sums(comp_sums + a * 27, Aa, ba);
                 matvec6_dev(Aa, xr, t);
                 for (int i = 0; i < 6; ++i) rhs[i] = ba[i] - t[i];
                 chol6_solve(F, rhs, xa[a]);
             }
             if (C == 3) {
                 double A1[6][6], A2[6][6], A12[6][6], b1[6], b2[6], b12[6], t[6], rhs[6];
-                unpack_sums(P.sums + (size_t) (1 + q * C) * 27, A1, b1);
-                unpack_sums(P.sums + (size_t) (1 + q * C + 1) * 27, A2, b2);
-                unpack_sums(P.sums + (size_t) (1 + q * C + 2) * 27, A12, b12);
+                unpack_sums(comp_sums, A1, b1);
+                unpack_sums(comp_sums + 27, A2, b2);
+                unpack_sums(comp_sums + 54, A12, b12);
                 for (int i = 0; i < 6; ++i) rhs[i] = b12[i];
                 matvec6_dev(A12, xr, t);
                 for (int i = 0; i < 6; ++i) rhs[i] -= t[i];
@@ -733,10 +787,19 @@ template <int C> __global__ void __launch_bounds__(64) icp_solve_kernel(const So
     }
 }
 
+// the step without derivative components (dirs == 0): one thread
+template <int C> __global__ void __launch_bounds__(32) icp_solve_kernel(const SolveParams P) {
+    __shared__ double s_real[27];
+    if (threadIdx.x < 27) s_real[threadIdx.x] = P.sums[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x == 0) icp_solve_direction<C>(P, 0, s_real, s_real);
+}
+
 // persistent scratch of the ICP operator (gbuf / mbuf of the reference, ICP.cu:400-403)
 struct IcpScratch {
     double *d_partials = nullptr, *d_sums = nullptr, *h_sums = nullptr, *d_dpartials = nullptr;
-    unsigned int *d_ticket = nullptr;
+    unsigned int *d_ticket = nullptr, *d_group_ticket = nullptr;
+    int cap_groups = 0;
     float *d_pose = nullptr, *h_pose = nullptr;  // seam-level entry point only: [(1+ncomp)][12]
     int *d_rec_idx = nullptr;
     float4 *d_rec_f = nullptr;
@@ -751,7 +814,7 @@ struct IcpScratch {
 };
 static IcpScratch g_icp;
 
-static int icp_reserve(int ncomp, int npix, size_t dpart) {
+static int icp_reserve(int ncomp, int npix, size_t dpart, int groups) {
     const int nvals = 27 * (1 + ncomp);
     if (nvals > g_icp.cap_vals) {
         cudaFree(g_icp.d_sums);
@@ -780,6 +843,12 @@ static int icp_reserve(int ncomp, int npix, size_t dpart) {
         XS_CUDA(cudaMalloc(&g_icp.d_rec_f, (size_t) npix * 4 * sizeof(float4)));
         g_icp.cap_pix = npix;
     }
+    if (groups > g_icp.cap_groups) {
+        cudaFree(g_icp.d_group_ticket);
+        XS_CUDA(cudaMalloc(&g_icp.d_group_ticket, (size_t) groups * sizeof(unsigned int)));
+        XS_CUDA(cudaMemset(g_icp.d_group_ticket, 0, (size_t) groups * sizeof(unsigned int)));
+        g_icp.cap_groups = groups;
+    }
     if (dpart > g_icp.cap_dpart) {
         cudaFree(g_icp.d_dpartials);
         XS_CUDA(cudaMalloc(&g_icp.d_dpartials, dpart * sizeof(double)));
@@ -788,10 +857,29 @@ static int icp_reserve(int ncomp, int npix, size_t dpart) {
     return XS_OK;
 }
 
-// Queues the three accumulation kernels of one Gauss-Newton iteration; the sums land in g_icp.d_sums.
-int icp_accumulate_async(const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
-                         xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
-                         int dirs, float dist_thres, float angle_thres, cudaStream_t s) {
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+template <int C, int ST> static int launch_deriv(const IcpParams &P, const SolveParams &S, cudaStream_t s) {
+    static bool smem_set = false;
+    if (!smem_set) {
+        XS_CUDA(cudaFuncSetAttribute(icp_deriv_kernel<C, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) deriv_smem(ST)));
+        smem_set = true;
+    }
+    icp_deriv_kernel<C, ST><<<dim3(P.groups, P.chunks), 256, deriv_smem(ST), s>>>(P, S);
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
+
+// Queues one Gauss-Newton iteration: association + real sums, then (ncomp > 0) the derivative pass whose tail sums the
+// partials and - when d_pose_out is given - runs the Gauss-Newton step per direction; with ncomp == 0 the step is a
+// one-thread kernel.  d_pose_out == nullptr: accumulate only (the sums land in g_icp.d_sums).
+int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
+                        xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
+                        int dirs, float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
+                        double *d_log, cudaStream_t s) {
     const int ncomp = comps * dirs;
     const int npix = rows * cols;
     if ((double) (1 + ncomp) * 3.0 * npix >= 4294967296.0) {
@@ -799,13 +887,19 @@ int icp_accumulate_async(const float *d_pose_curr, const float *d_vmap_curr, con
         return XS_ERR_ARG;
     }
     IcpParams P;
-    // derivative pass decomposition: a thread sums at most 32 pixels in FP32 before the double reduction
+    // derivative pass decomposition: a thread sums at most 32 pixels in FP32 before the double reduction.  Pixels per
+    // thread amortise the per-CTA prologue (pipeline fill), reduction and arrival ticket (~7 us per CTA against ~2 us per
+    // pixel); measured on B200 at 640x480 / 55 directions: 16 -> 0.474 ms, 32 -> 0.454 ms, 64 -> 0.469 ms per launch.
+    // With few direction groups (a rank of an 8-GPU run holds 7) the grid would not fill the 296 CTA slots, so pixels
+    // per thread are halved until it does (7 groups, level 0: 32 -> 90 us, 16 -> 93 us but shorter coarse levels, 8 ->
+    // 103 us, 4 -> 123 us per launch; whole ICP stage 1.16 / 1.06 / 1.14 / 1.19 ms).
     P.groups = (ncomp + 2) / 3;
-    // pixels per thread: the per-CTA prologue (pipeline fill) and reduction are amortised over them; measured on B200 at
-    // 640x480 / 55 directions: 16 -> 0.474 ms, 32 -> 0.454 ms, 64 -> 0.469 ms per launch
-    P.ppt = npix >= 256 * 32 * 32 ? 32 : npix >= 256 * 8 * 32 ? 8 : (npix >= 256 * 4 * 64 ? 4 : (npix >= 256 * 2 * 32 ? 2 : 1));
+    static const int ppt_env = env_int("XS_ICP_PPT", 0), stages_env = env_int("XS_ICP_STAGES", 0);
+    P.ppt = 32;
+    while (P.ppt > 1 && (long long) div_up(npix, 256 * P.ppt) * P.groups < 296) P.ppt >>= 1;
+    if (ppt_env > 0) P.ppt = ppt_env < 32 ? ppt_env : 32;
     P.chunks = div_up(npix, 256 * P.ppt);
-    int rc = icp_reserve(ncomp, npix, (size_t) P.chunks * P.groups * 81);
+    int rc = icp_reserve(ncomp, npix, (size_t) P.chunks * P.groups * 81, P.groups);
     if (rc != XS_OK) return rc;
     // only the current pose's derivative components enter the rows (s = Rcurr*v + tcurr); the previous pose is used
     // for the real projection only (ICP.cu:206-217 takes real parts)
@@ -829,14 +923,23 @@ int icp_accumulate_async(const float *d_pose_curr, const float *d_vmap_curr, con
     P.dpartials = g_icp.d_dpartials;
     P.sums = g_icp.d_sums;
     P.ticket = g_icp.d_ticket;
+    P.group_ticket = g_icp.d_group_ticket;
     P.tiles_x = div_up(cols, 32);
     P.tiles_y = div_up(rows, 8);
+    SolveParams S;
+    S.sums = g_icp.d_sums;
+    S.pose_in = d_pose_curr;
+    S.pose_out = d_pose_out;
+    S.status = d_status;
+    S.log = d_log;
+    S.dirs = dirs;
+    S.ncomp = ncomp;
+    S.solve_mode = solve_mode;
     const int ntiles = P.tiles_x * P.tiles_y;
     const int grid = ntiles < g_icp.max_blocks ? ntiles : g_icp.max_blocks;
     icp_assoc_kernel<<<grid, dim3(32, 8), 0, s>>>(P);
     XS_LAUNCH_CHECK();
     if (ncomp > 0) {
-        dim3 g2(P.groups, P.chunks);
         const int slot = g_icp.n_timed < IcpScratch::MAX_TIMED ? g_icp.n_timed : -1;
         if (slot >= 0) {
             if (!g_icp.ev0[slot]) {
@@ -845,46 +948,26 @@ int icp_accumulate_async(const float *d_pose_curr, const float *d_vmap_curr, con
             }
             XS_CUDA(cudaEventRecord(g_icp.ev0[slot], s));
         }
-        static bool smem_set = false;
-        if (!smem_set) {
-            XS_CUDA(cudaFuncSetAttribute(icp_deriv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DERIV_SMEM));
-            XS_CUDA(cudaFuncSetAttribute(icp_deriv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) DERIV_SMEM));
-            smem_set = true;
-        }
+        // pipeline depth: 2 stages (one pixel ahead) measured faster than 3 on B200 (0.475 vs 0.542 ms per level-0 launch at
+        // 55 directions: the deeper pipeline costs L1 capacity and does not raise issue utilisation); XS_ICP_STAGES=3 selects it
+        const int stages = stages_env == 3 ? 3 : 2;
         if (comps == 1)
-            icp_deriv_kernel<1><<<g2, 256, DERIV_SMEM, s>>>(P);
+            rc = stages == 2 ? launch_deriv<1, 2>(P, S, s) : launch_deriv<1, DERIV_MAX_STAGES>(P, S, s);
         else
-            icp_deriv_kernel<3><<<g2, 256, DERIV_SMEM, s>>>(P);
-        XS_LAUNCH_CHECK();
+            rc = stages == 2 ? launch_deriv<3, 2>(P, S, s) : launch_deriv<3, DERIV_MAX_STAGES>(P, S, s);
+        if (rc != XS_OK) return rc;
         if (slot >= 0) {
             XS_CUDA(cudaEventRecord(g_icp.ev1[slot], s));
             g_icp.timed_npix[slot] = npix;
             ++g_icp.n_timed;
         }
-        icp_finish_kernel<<<P.groups, 32 * 27, 0, s>>>(P);
+    } else if (d_pose_out) {
+        if (comps == 1)
+            icp_solve_kernel<1><<<1, 32, 0, s>>>(S);
+        else
+            icp_solve_kernel<3><<<1, 32, 0, s>>>(S);
         XS_LAUNCH_CHECK();
     }
-    return XS_OK;
-}
-
-// Queues the device-side Gauss-Newton step on the sums of the last icp_accumulate_async.
-int icp_solve_async(const float *d_pose_in, float *d_pose_out, int comps, int dirs, int solve_mode, int *d_status,
-                    double *d_log, cudaStream_t s) {
-    SolveParams S;
-    S.sums = g_icp.d_sums;
-    S.pose_in = d_pose_in;
-    S.pose_out = d_pose_out;
-    S.status = d_status;
-    S.log = d_log;
-    S.dirs = dirs;
-    S.ncomp = comps * dirs;
-    S.solve_mode = solve_mode;
-    const int blocks = dirs > 0 ? div_up(dirs, 64) : 1;
-    if (comps == 1)
-        icp_solve_kernel<1><<<blocks, 64, 0, s>>>(S);
-    else
-        icp_solve_kernel<3><<<blocks, 64, 0, s>>>(S);
-    XS_LAUNCH_CHECK();
     return XS_OK;
 }
 
@@ -919,7 +1002,7 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
         return XS_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t) stream;
-    int rc = icp_reserve(ncomp, rows * cols, 0);
+    int rc = icp_reserve(ncomp, rows * cols, 0, 0);
     if (rc != XS_OK) return rc;
     icp_timing_reset();
     XS_CUDA(cudaStreamSynchronize(s));  // pinned staging reuse
@@ -932,8 +1015,8 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
         for (int e = 0; e < 3; ++e) hc[9 + e] = curr->dt[q * 3 + e];
     }
     XS_CUDA(cudaMemcpyAsync(g_icp.d_pose, h, (size_t) (1 + ncomp) * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = icp_accumulate_async(g_icp.d_pose, d_vmap_curr, d_nmap_curr, prev, intr, d_vmap_g_prev, d_nmap_g_prev, rows, cols,
-                              comps, dirs, dist_thres, angle_thres, s);
+    rc = icp_iteration_async(g_icp.d_pose, d_vmap_curr, d_nmap_curr, prev, intr, d_vmap_g_prev, d_nmap_g_prev, rows, cols,
+                             comps, dirs, dist_thres, angle_thres, nullptr, 0, nullptr, nullptr, s);
     if (rc != XS_OK) return rc;
     const int nvals = 27 * (1 + ncomp);
     XS_CUDA(cudaMemcpyAsync(g_icp.h_sums, g_icp.d_sums, (size_t) nvals * sizeof(double), cudaMemcpyDeviceToHost, s));

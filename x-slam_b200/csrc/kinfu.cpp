@@ -26,12 +26,11 @@ namespace xs {
 void set_error(const std::string &msg);
 extern long long g_launches;
 // icp.cu: one Gauss-Newton iteration queued on the stream, no host round trip
-int icp_accumulate_async(const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
-                         xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
-                         int dirs, float dist_thres, float angle_thres, cudaStream_t s);
+int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
+                        xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
+                        int dirs, float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
+                        double *d_log, cudaStream_t s);
 void icp_timing_reset();
-int icp_solve_async(const float *d_pose_in, float *d_pose_out, int comps, int dirs, int solve_mode, int *d_status,
-                    double *d_log, cudaStream_t s);
 }  // namespace xs
 using namespace xs;
 
@@ -238,7 +237,7 @@ int xs_kinfu_surface_measure(xs_kinfu *k, const uint16_t *d_depth) {
 // AlignDepthToReconstruction (after SurfaceMeasure) + PoseEstimate, KinectFusionReconstruction.cpp:161-235.
 // Returns 1 when a pose was estimated, 0 on frame 0 or when the normal equations are degenerate.
 // The Gauss-Newton loop (levels 2..0 with 3, 4, 5 iterations, :186-192) is queued on the stream without any host
-// round trip: accumulation kernels + the device-side solve / pose update per iteration (icp.cu), one download of the
+// round trip: two kernels per iteration (association, derivative pass + device-side solve / pose update in its tail, icp.cu), one download of the
 // final pose (all derivative components) and the degeneracy flag at the end.
 int xs_kinfu_pose_estimate(xs_kinfu *k) {
     set_ctx(k);
@@ -274,12 +273,12 @@ int xs_kinfu_pose_estimate(xs_kinfu *k) {
     for (int level = c.num_levels - 1; level >= 0; --level) {
         const int rows = c.height >> level, cols = c.width >> level;
         for (int iter = 0; iter < k->icp_iterations[level]; ++iter, ++it) {
-            int rc = icp_accumulate_async(k->d_pose[it & 1], k->vmaps_curr[level], k->nmaps_curr[level], &prev_pose,
-                                          level_intr(k->intr, level), k->vmaps_prev[level], k->nmaps_prev[level], rows, cols,
-                                          k->comps, k->dirs, c.dist_thres, k->angle_thres, k->stream);
-            if (rc == XS_OK)
-                rc = icp_solve_async(k->d_pose[it & 1], k->d_pose[(it + 1) & 1], k->comps, k->dirs, k->solve_mode, k->d_status,
-                                     k->log_icp && it < 16 ? k->d_icp_log + (size_t) it * log_stride : nullptr, k->stream);
+            const int rc = icp_iteration_async(k->d_pose[it & 1], k->vmaps_curr[level], k->nmaps_curr[level], &prev_pose,
+                                               level_intr(k->intr, level), k->vmaps_prev[level], k->nmaps_prev[level], rows,
+                                               cols, k->comps, k->dirs, c.dist_thres, k->angle_thres, k->d_pose[(it + 1) & 1],
+                                               k->solve_mode, k->d_status,
+                                               k->log_icp && it < 16 ? k->d_icp_log + (size_t) it * log_stride : nullptr,
+                                               k->stream);
             if (rc != XS_OK) return 0;
         }
     }
