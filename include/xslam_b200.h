@@ -127,6 +127,12 @@ int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_po
 int xs_tsdf_hessian(const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, xs_intr intr,
                     const int res[3], float voxel_size, const xs_pose *v2c, float trunc, const float *d_gt,
                     double *out4_host, void *stream);
+/* ComputeLocalTsdf_loss, TsdfFusion.h:48-52 / TsdfFusion.cu:409 (real-only twin of the DCSFD volume loss, used with
+ * se3Exp-parameterised pose sets in relocalisation-style optimisation): (Rv2c row-major, tv2c) are plain floats.
+ * out2 = {sum loss, count} (host). */
+int xs_tsdf_loss(const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, xs_intr intr, const int res[3],
+                 float voxel_size, const float Rv2c[9], const float tv2c[3], float trunc, const float *d_gt,
+                 double *out2_host, void *stream);
 /* extractPoints / extractNormals, ExtractPointCloud.h:19-23 (real-only output path) */
 long xs_extract_points(const xs_volume *v, float *d_points_xyz, float *d_normals_xyz, long max_points, void *stream);
 
@@ -138,6 +144,13 @@ int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_curr, const fl
                          xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols,
                          int comps, int dirs, float dist_thres, float angle_thres, double *A_host, double *b_host,
                          void *stream);
+/* computeOptimizeMatrix, ICP.h:34-40 / ICP.cu:431-489 (inputs of the second-order pose optimiser the header reserves for
+ * PoseNewtonEstimate): same data association as estimateCombined, real parts only.  jacobi_host: double[3][4] row-major
+ * (jacobi_host(i, j)); hessian_host: double[12][12], index i * 4 + j on both sides (hessian_host[i1][j1](i2, j2)).
+ * Returns the number of correspondences, or -1 on error. */
+long xs_compute_optimize_matrix(const xs_pose *curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
+                                xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols,
+                                float dist_thres, float angle_thres, double *jacobi_host, double *hessian_host, void *stream);
 
 /* Device durations (CUDA events on the launching stream) of the derivative-accumulation kernel launches of the last
  * xs_kinfu_pose_estimate / xs_estimate_combined, with the pixel count of each launch (roofline timing). */

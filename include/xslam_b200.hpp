@@ -228,5 +228,80 @@ void estimateCombined(const Mat &Rcurr, const Vec &tcurr, const MapT &vmap_curr,
     for (int i = 0; i < 6; ++i) vectorB_host[i] = HostC(b[0][i], b[1][i]);
 }
 
+// TsdfFusion.h:55-60 / TsdfFusion.cu:286 (sync).  MatD33 / devDComplex3 hold d_complex<float> = (value, eps1 | eps2, eps1eps2);
+// the reference's per-voxel temporaries real_vec / grad_vec / hessian_vec / count_vec are not materialised (the sums are
+// formed in one pass); depthScaled, threshold and k are unused by the reference kernel too.
+template <class DepthT, class IntrT, class ScaledT, class Int3, class MatD, class VecD, class FVec, class IVec>
+float4 ComputeLocalTsdf_hessian(const DepthT &depth, const IntrT &intr, ScaledT & /*depthScaled*/, const Int3 &volume_resolution,
+                                float voxel_size, const MatD &Rv2c, const VecD &tv2c, float tranc_dist, float /*threshold*/,
+                                float /*k*/, FVec &gt_vec, FVec & /*real_vec*/, FVec & /*grad_vec*/, FVec & /*hessian_vec*/,
+                                IVec & /*count_vec*/) {
+    const int res[3] = {volume_resolution.x, volume_resolution.y, volume_resolution.z};
+    xs_pose p;
+    float dR[27], dt[9];
+    const auto *rows = Rv2c.data;
+    for (int i = 0; i < 3; ++i) {
+        const auto *e = &rows[i].x;  // x, y, z are consecutive members (Internal.h devDComplex3)
+        for (int j = 0; j < 3; ++j) {
+            p.R[i * 3 + j] = e[j].real().real();
+            dR[i * 3 + j] = e[j].real().imag();
+            dR[9 + i * 3 + j] = e[j].imag().real();
+            dR[18 + i * 3 + j] = e[j].imag().imag();
+        }
+    }
+    const auto *tv = &tv2c.x;
+    for (int i = 0; i < 3; ++i) {
+        p.t[i] = tv[i].real().real();
+        dt[i] = tv[i].real().imag();
+        dt[3 + i] = tv[i].imag().real();
+        dt[6 + i] = tv[i].imag().imag();
+    }
+    p.ncomp = 3;
+    p.dR = dR;
+    p.dt = dt;
+    double out[4];
+    check(xs_tsdf_hessian(depth.data, depth.step, depth.rows, depth.cols, to_intr(intr), res, voxel_size, &p, tranc_dist,
+                          gt_vec.data().get(), out, nullptr),
+          "ComputeLocalTsdf_hessian");
+    return make_float4((float) out[0], (float) out[1], (float) out[2], (float) out[3]);
+}
+
+// TsdfFusion.h:48-52 / TsdfFusion.cu:409 (sync).  Mat33 = float3 data[3] (Internal.h:229-231).
+template <class DepthT, class IntrT, class ScaledT, class Int3, class Mat, class FVec, class IVec>
+float2 ComputeLocalTsdf_loss(const DepthT &depth, const IntrT &intr, ScaledT & /*depthScaled*/, const Int3 &volume_resolution,
+                             float voxel_size, const Mat &Rv2c, const float3 &tv2c, float tranc_dist, float /*threshold*/,
+                             float /*k*/, FVec &gt_vec, FVec & /*real_vec*/, IVec & /*count_vec*/) {
+    const int res[3] = {volume_resolution.x, volume_resolution.y, volume_resolution.z};
+    const float R[9] = {Rv2c.data[0].x, Rv2c.data[0].y, Rv2c.data[0].z, Rv2c.data[1].x, Rv2c.data[1].y,
+                        Rv2c.data[1].z, Rv2c.data[2].x, Rv2c.data[2].y, Rv2c.data[2].z};
+    const float t[3] = {tv2c.x, tv2c.y, tv2c.z};
+    double out[2];
+    check(xs_tsdf_loss(depth.data, depth.step, depth.rows, depth.cols, to_intr(intr), res, voxel_size, R, t, tranc_dist,
+                       gt_vec.data().get(), out, nullptr),
+          "ComputeLocalTsdf_loss");
+    return make_float2((float) out[0], (float) out[1]);
+}
+
+// ICP.h:34-40 / ICP.cu:431 (sync).  jacobi_buf / hessian_buf are the reference's scratch; unused here.  jacobi_host is an
+// Eigen::Matrix4f of which rows 0..2 are written; hessian_host[i1][j1](i2, j2) as the reference.
+template <class MapT, class Mat, class Vec, class IntrT, class JBuf, class M4>
+void computeOptimizeMatrix(const MapT &vmap_curr, const MapT &nmap_curr, const MapT &vmap_g_prev, const MapT &nmap_g_prev,
+                           const Mat &Rcurr, const Vec &tcurr, const Mat &Rprev_inv, const Vec &tprev, const IntrT &intr,
+                           float distThres, float angleThres, JBuf & /*jacobi_buf*/, M4 &jacobi_host, JBuf * /*hessian_buf*/,
+                           M4 **hessian_host) {
+    const int rows = vmap_curr.rows() / 3, cols = vmap_curr.cols();
+    float *vc = import_map(vmap_curr, 3, 0, 4), *nc = import_map(nmap_curr, 3, 0, 5);
+    float *vp = import_map(vmap_g_prev, 3, 0, 6), *np_ = import_map(nmap_g_prev, 3, 0, 7);
+    PoseHolder curr(Rcurr, tcurr), prev(Rprev_inv, tprev);
+    double J[12], H[144];
+    if (xs_compute_optimize_matrix(&curr.p, vc, nc, &prev.p, to_intr(intr), vp, np_, rows, cols, distThres, angleThres, J, H,
+                                   nullptr) < 0)
+        check(XS_ERR_CUDA, "computeOptimizeMatrix");
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) jacobi_host(i, j) = (float) J[i * 4 + j];
+    for (int a = 0; a < 12; ++a)
+        for (int b = 0; b < 12; ++b) hessian_host[a / 4][a % 4](b / 4, b % 4) = (float) H[a * 12 + b];
+}
+
 }  // namespace seam
 }  // namespace xslam_b200

@@ -31,4 +31,20 @@ void hpp_check_instantiate() {
     DeviceArray<devComplexICP> mbuf;
     hostComplexICP A[36], b[6];
     S::estimateCombined(R, t, vmap, nmap, R, t, intr, vprev, nprev, 0.1f, 0.26f, gbuf, mbuf, A, b);  // ICP.h:24-31
+    DeviceArray2D<float> jacobi_buf, hessian_buf[12];
+    Eigen::Matrix4f jacobi_host, hessian_store[3][4], *hessian_host[3] = {hessian_store[0], hessian_store[1], hessian_store[2]};
+    S::computeOptimizeMatrix(vmap, nmap, vprev, nprev, R, t, R, t, intr, 0.1f, 0.26f, jacobi_buf, jacobi_host, hessian_buf,
+                             hessian_host);  // ICP.h:34-40
+    thrustDvec<float> gt_vec, real_vec, grad_vec, hessian_vec;
+    thrustDvec<int> count_vec;
+    MatD33 RD;
+    devDComplex3 tD;
+    float4 h4 = S::ComputeLocalTsdf_hessian(d, intr, depthScaled, res, 0.03f, RD, tD, 0.09f, 0.f, 0.f, gt_vec, real_vec, grad_vec,
+                                            hessian_vec, count_vec);  // TsdfFusion.h:55-60
+    Mat33 Rf;
+    float3 tf = make_float3(0.f, 0.f, 0.f);
+    float2 l2 = S::ComputeLocalTsdf_loss(d, intr, depthScaled, res, 0.03f, Rf, tf, 0.09f, 0.f, 0.f, gt_vec, real_vec,
+                                         count_vec);  // TsdfFusion.h:48-52
+    (void) h4;
+    (void) l2;
 }

@@ -135,6 +135,20 @@ class RefCuda:
         bb = bb.reshape(6, 2)
         return (A[..., 0] + 1j * A[..., 1]).T.copy(), bb[:, 0] + 1j * bb[:, 1], ms.value
 
+    def compute_optimize_matrix(self, Rcurr, tcurr, vmap_curr, nmap_curr, Rprev_inv, tprev, intr, vmap_prev, nmap_prev,
+                                dist_thres, angle_thres):
+        """ICP.cu:431 computeOptimizeMatrix.  Returns (J [3, 4], H [12, 12]) float32."""
+        a, b = cpose(Rcurr, tcurr)
+        c, d = cpose(Rprev_inv, tprev)
+        rows, cols = vmap_curr.shape[1:3]
+        J = np.zeros((12,), np.float32)
+        H = np.zeros((144,), np.float32)
+        self.lib.ref_compute_optimize_matrix(_p(a), _p(b), _p(_f(vmap_curr)), _p(_f(nmap_curr)), _p(c), _p(d),
+                                             C.c_float(intr[0]), C.c_float(intr[1]), C.c_float(intr[2]), C.c_float(intr[3]),
+                                             _p(_f(vmap_prev)), _p(_f(nmap_prev)), rows, cols, C.c_float(dist_thres),
+                                             C.c_float(angle_thres), _p(J), _p(H))
+        return J.reshape(3, 4), H.reshape(12, 12)
+
     def tsdf_hessian(self, depth, intr, res, voxel, R4, t4, trunc, gt):
         """R4: [9, 4], t4: [3, 4] bicomplex components (re.re, re.im, im.re, im.im)."""
         d = np.ascontiguousarray(depth, np.uint16)
@@ -144,6 +158,17 @@ class RefCuda:
         self.lib.ref_tsdf_hessian(_p(d, C.c_uint16), d.shape[0], d.shape[1], C.c_float(intr[0]), C.c_float(intr[1]),
                                   C.c_float(intr[2]), C.c_float(intr[3]), r, C.c_float(voxel), _p(_f(R4)), _p(_f(t4)),
                                   C.c_float(trunc), _p(_f(gt)), _p(out), C.byref(ms))
+        return out, ms.value
+
+    def tsdf_loss(self, depth, intr, res, voxel, R, t, trunc, gt):
+        """TsdfFusion.cu:409 ComputeLocalTsdf_loss.  R: [3, 3] float32 row-major, t: [3]."""
+        d = np.ascontiguousarray(depth, np.uint16)
+        r = (C.c_int * 3)(*res)
+        out = np.zeros((2,), np.float32)
+        ms = C.c_float()
+        self.lib.ref_tsdf_loss(_p(d, C.c_uint16), d.shape[0], d.shape[1], C.c_float(intr[0]), C.c_float(intr[1]),
+                               C.c_float(intr[2]), C.c_float(intr[3]), r, C.c_float(voxel), _p(_f(R)), _p(_f(t)),
+                               C.c_float(trunc), _p(_f(gt)), _p(out), C.byref(ms))
         return out, ms.value
 
     def kinfu(self, cfg, seed_imag=None):
@@ -321,6 +346,31 @@ class Oracle:
         A = A.reshape(6, 6, 2)
         bb = bb.reshape(6, 2)
         return (A[..., 0] + 1j * A[..., 1]).T.copy(), bb[:, 0] + 1j * bb[:, 1]
+
+    def optimize_matrix(self, Rcurr, tcurr, vmap_curr, nmap_curr, Rprev_inv, tprev, intr, vmap_prev, nmap_prev, dist_thres,
+                        angle_thres, f64=False):
+        """computeOptimizeMatrix (ICP.cu:283-355, 431-489).  Returns (count, J [3, 4], H [12, 12]) float64."""
+        a, b = cpose(Rcurr, tcurr)
+        c, d = cpose(Rprev_inv, tprev)
+        rows, cols = vmap_curr.shape[1:3]
+        J = np.zeros((12,), np.float64)
+        H = np.zeros((144,), np.float64)
+        self.lib.oracle_optimize_matrix.restype = C.c_long
+        n = self.lib.oracle_optimize_matrix(_p(a), _p(b), _p(_f(vmap_curr)), _p(_f(nmap_curr)), _p(c), _p(d), C.c_float(intr[0]),
+                                            C.c_float(intr[1]), C.c_float(intr[2]), C.c_float(intr[3]), _p(_f(vmap_prev)),
+                                            _p(_f(nmap_prev)), rows, cols, C.c_float(dist_thres), C.c_float(angle_thres),
+                                            _p(J, C.c_double), _p(H, C.c_double), int(f64))
+        return int(n), J.reshape(3, 4), H.reshape(12, 12)
+
+    def tsdf_loss(self, depth, intr, res, voxel, R, t, trunc, gt, f64=False):
+        """ComputeLocalTsdf_loss (TsdfFusion.cu:335-447).  Returns [sum loss, count]."""
+        d = np.ascontiguousarray(depth, np.uint16)
+        r = (C.c_int * 3)(*res)
+        out = np.zeros((2,), np.float64)
+        self.lib.oracle_tsdf_loss(_p(d, C.c_uint16), d.shape[0], d.shape[1], C.c_float(intr[0]), C.c_float(intr[1]),
+                                  C.c_float(intr[2]), C.c_float(intr[3]), r, C.c_float(voxel), _p(_f(R)), _p(_f(t)),
+                                  C.c_float(trunc), _p(_f(gt)), _p(out, C.c_double), int(f64))
+        return out
 
     def pose_update(self, A, b, R, t):
         """One Gauss-Newton update (Hermitian-LLT solve as Eigen does); returns (ok, R, t)."""

@@ -236,6 +236,31 @@ int ref_estimate_combined(const float *Rcurr, const float *tcurr, const float *v
     return 0;
 }
 
+// ICP.cu:431 computeOptimizeMatrix (dormant in the reference's frame loop).  J: [3][4] row-major; H: [12][12].
+int ref_compute_optimize_matrix(const float *Rcurr, const float *tcurr, const float *vmap_curr, const float *nmap_curr,
+                                const float *Rprev_inv, const float *tprev, float fx, float fy, float cx, float cy,
+                                const float *vmap_g_prev, const float *nmap_g_prev, int rows, int cols, float dist_thres,
+                                float angle_thres, float *J_out /*12*/, float *H_out /*144*/) {
+    Map vc, nc, vp, np;
+    up(vc, vmap_curr, rows * 3, cols);
+    up(nc, nmap_curr, rows * 3, cols);
+    up(vp, vmap_g_prev, rows * 3, cols);
+    up(np, nmap_g_prev, rows * 3, cols);
+    DeviceArray2D<float> jacobi_buf, hessian_buf[12];
+    Eigen::Matrix4f jacobi_host, hessian_store[3][4], *hessian_rows[3] = {hessian_store[0], hessian_store[1], hessian_store[2]};
+    jacobi_host.setZero();
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) hessian_store[i][j].setZero();
+    computeOptimizeMatrix(vc, nc, vp, np, to_mat(Rcurr), to_vec(tcurr), to_mat(Rprev_inv), to_vec(tprev), Intr(fx, fy, cx, cy),
+                          dist_thres, angle_thres, jacobi_buf, jacobi_host, hessian_buf, hessian_rows);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) J_out[i * 4 + j] = jacobi_host(i, j);
+    for (int a = 0; a < 12; ++a)
+        for (int b = 0; b < 12; ++b) H_out[a * 12 + b] = hessian_store[a / 4][a % 4](b / 4, b % 4);
+    return 0;
+}
+
 // TsdfFusion.cu:286 ComputeLocalTsdf_hessian.  Rv2c: 9 x (re.re, re.im, im.re, im.im); tv2c: 3 x 4.
 int ref_tsdf_hessian(const uint16_t *depth, int rows, int cols, float fx, float fy, float cx, float cy, const int *res,
                      float voxel, const float *Rv2c /*36*/, const float *tv2c /*12*/, float trunc, const float *gt,
@@ -263,6 +288,29 @@ int ref_tsdf_hessian(const uint16_t *depth, int rows, int cols, float fx, float 
     out4[1] = r.y;
     out4[2] = r.z;
     out4[3] = r.w;
+    return 0;
+}
+
+// TsdfFusion.cu:409 ComputeLocalTsdf_loss (real-only).  Rv2c: 9 floats row-major; tv2c: 3 floats.
+int ref_tsdf_loss(const uint16_t *depth, int rows, int cols, float fx, float fy, float cx, float cy, const int *res, float voxel,
+                  const float *Rv2c, const float *tv2c, float trunc, const float *gt, float *out2, float *ms_out) {
+    DeviceArray2D<ushort> d;
+    d.upload(depth, cols * sizeof(ushort), rows, cols);
+    DeviceArray2D<float> scaled;
+    size_t n = (size_t) res[0] * res[1] * res[2];
+    thrustDvec<float> gt_vec(gt, gt + n), real_vec;
+    thrustDvec<int> count_vec;
+    Mat33 R;
+    for (int i = 0; i < 3; ++i) R.data[i] = make_float3(Rv2c[3 * i], Rv2c[3 * i + 1], Rv2c[3 * i + 2]);
+    float3 t = make_float3(tv2c[0], tv2c[1], tv2c[2]);
+    int3 r3 = make_int3(res[0], res[1], res[2]);
+    Timer tm;
+    tm.start();
+    float2 r = ComputeLocalTsdf_loss(d, Intr(fx, fy, cx, cy), scaled, r3, voxel, R, t, trunc, 0.f, 0.f, gt_vec, real_vec, count_vec);
+    float ms = tm.stop();
+    if (ms_out) *ms_out = ms;
+    out2[0] = r.x;
+    out2[1] = r.y;
     return 0;
 }
 

@@ -110,6 +110,19 @@ def main(out):
     A, b, _ = ref.estimate_combined(Rc.reshape(9), tc, vc, nc, Rinv.reshape(9), tc, li, vp, np_, 0.10, ang)
     np.savez_compressed(os.path.join(out, "icp.npz"), vmap_curr=vc, nmap_curr=nc, vmap_prev=vp, nmap_prev=np_, Rcurr=Rc, tcurr=tc,
                         Rprev_inv=Rinv, intr=np.array(li, np.float32), angle_thres=ang, A=A, b=b)
+    # ---- "next" rows: computeOptimizeMatrix on the ICP inputs above, ComputeLocalTsdf_loss / _hessian on the
+    # nearest-branch golden volume as ground truth
+    Jr, Hr = ref.compute_optimize_matrix(Rc.reshape(9), tc, vc, nc, Rinv.reshape(9), tc, li, vp, np_, 0.10, ang)
+    gv = np.load(os.path.join(out, "volume_nearest.npz"))
+    gt = gv["value"]
+    trunc = float(gv["trunc"])
+    loss = {}
+    for f in (0, 8):
+        (Rv2c, tv2c), _, _ = stage_poses(f, rng)
+        R, t = Rv2c.real.astype(np.float32), tv2c.real.astype(np.float32)
+        loss["loss_R_%d" % f], loss["loss_t_%d" % f] = R, t
+        loss["loss_out_%d" % f], _ = ref.tsdf_loss(depth_frame(f), INTR, (RES,) * 3, VOXEL, R, t, trunc, gt)
+    np.savez_compressed(os.path.join(out, "next_rows.npz"), optmat_J=Jr, optmat_H=Hr, frames=np.array([0, 8]), **loss)
     # ---- resize
     np.savez_compressed(os.path.join(out, "resize.npz"), vmap_in=r.map("vmap_g_prev", 1), vmap_out=r.map("vmap_g_prev", 2),
                         nmap_in=r.map("nmap_g_prev", 1), nmap_out=r.map("nmap_g_prev", 2))

@@ -297,6 +297,28 @@ def test_resize_and_icp_parity(xs, refcuda, torch_mod, out_dir):
             stats["icp_L%d_b_deriv_rel_d%d" % (level, q)] = rel_err(b[1 + q], br.imag)
             stats["icp_L%d_A00" % level] = float(Ar.real[0, 0])
             stats["icp_ref_ms_L%d" % level] = ms
+        # ---- computeOptimizeMatrix on the same inputs: real parts only
+        ang = float(np.sin(np.float32(15.0) / 180.0 * np.pi))
+        n_mine, J, Hm = ops.computeOptimizeMatrix(curr_v[level], curr_n[level], torch.from_numpy(pv_packed).cuda(),
+                                                  torch.from_numpy(pn_packed).cuda(), ops.PoseBatch(R, t, dR, dt),
+                                                  ops.PoseBatch(Rinv, t, dRi, dti), li, 0.10, ang)
+        Jr, Hr = refcuda.compute_optimize_matrix(R.reshape(9) + 0j, t + 0j, cvc, cnc, Rinv.reshape(9) + 0j, t + 0j,
+                                                 (li.fx, li.fy, li.cx, li.cy), pv[0], pn[0], 0.10, ang)
+        from oracle import pyref
+        n_or, Jo, Ho = pyref.Oracle().optimize_matrix(R.reshape(9) + 0j, t + 0j, cvc, cnc, Rinv.reshape(9) + 0j, t + 0j,
+                                                      (li.fx, li.fy, li.cx, li.cy), pv[0], pn[0], 0.10, ang, f64=True)
+        stats["optmat_L%d_count" % level] = n_mine
+        stats["optmat_L%d_count_vs_oracle" % level] = n_mine - n_or
+        stats["optmat_L%d_H_rel_vs_ref" % level] = rel_err(Hm, Hr)
+        stats["optmat_L%d_J_rel_vs_ref" % level] = float(np.abs(J - Jr).max() / np.abs(Hr).max())
+        stats["optmat_L%d_H_rel_vs_oracle" % level] = rel_err(Hm, Ho)
+        stats["optmat_L%d_J_rel_vs_oracle" % level] = float(np.abs(J - Jo).max() / np.abs(Ho).max())
+        assert n_mine > 1000 and abs(n_mine - n_or) <= 3
+        assert np.array_equal(Hm, Hm.T)
+        # J sums signed residuals (cancellation): compared on the scale of H like b against A above; the reference adds in
+        # FP32 (block tree + thrust::reduce), hence 2e-5 against it and 1e-5 against the FP64 restatement
+        assert stats["optmat_L%d_H_rel_vs_ref" % level] <= 2e-5 and stats["optmat_L%d_J_rel_vs_ref" % level] <= 2e-5
+        assert stats["optmat_L%d_H_rel_vs_oracle" % level] <= 1e-5 and stats["optmat_L%d_J_rel_vs_oracle" % level] <= 1e-5
     _report(out_dir, "resize_icp", **stats)
     for k, v in stats.items():
         if k.endswith("real_rel") or "_real_rel_" in k:
@@ -333,3 +355,29 @@ def test_dcsfd_volume_loss_parity(xs, refcuda, torch_mod, out_dir):
     _report(out_dir, "tsdf_hessian", **stats)
     assert mine[3] == ref[3] and ref[3] > 1000, "processed-voxel counts differ"
     assert stats["rel"][0] <= 1e-5 and stats["rel"][1] <= 1e-4 and stats["rel"][2] <= 1e-3
+
+
+def test_real_volume_loss_parity(xs, refcuda, torch_mod, out_dir):
+    """ComputeLocalTsdfLossKernel, the real-only twin of a12, on a 128^3 ground-truth volume: processed-voxel
+    count exact against the reference kernel, loss sum <= 1e-5 (the reference adds FP32 terms with thrust::reduce)."""
+    torch = torch_mod
+    from xslam_b200 import ops
+    from oracle import pyref
+    res, voxel = 128, 0.06
+    vol, ref_state, _, _ = _integrate_both(xs, refcuda, torch, [0], res, voxel, 1, 7)
+    gt = ref_state[0][0]
+    trunc = vol.getTsdfTruncDist()
+    intr = (ICL["fx"], ICL["fy"], ICL["cx"], ICL["cy"])
+    stats = {}
+    for frame in (0, 3):
+        depth = xs.synth_depth(frame)
+        v2c, _, _ = poses_for_frame(xs, frame)
+        R, t = v2c[:3, :3].astype(np.float32), v2c[:3, 3].astype(np.float32)
+        mine = ops.ComputeLocalTsdf_loss(_dev_u16(torch, depth), xs.Intr(**ICL), (res,) * 3, voxel, R, t, trunc, torch.from_numpy(gt).cuda())
+        ref, ms = refcuda.tsdf_loss(depth, intr, (res,) * 3, voxel, R, t, trunc, gt)
+        orc = pyref.Oracle().tsdf_loss(depth, intr, (res,) * 3, voxel, R, t, trunc, gt, f64=False)
+        stats["f%d" % frame] = dict(mine=[float(x) for x in mine], ref=[float(x) for x in ref], oracle=[float(x) for x in orc], ref_ms=ms)
+        assert mine[1] == ref[1] and ref[1] > 1000, "processed-voxel counts differ"
+        assert abs(mine[0] - ref[0]) <= 1e-5 * abs(ref[0])
+        assert abs(mine[1] - orc[1]) <= 1e-3 * ref[1] and abs(mine[0] - orc[0]) <= 1e-3 * abs(ref[0])
+    _report(out_dir, "tsdf_loss", **stats)

@@ -64,8 +64,10 @@ SYMBOLS = {
     "xs_integrate": (_i, [_vp, _vp, _sz, _i, _i, Intr, _i, _PP, _f, _pull, _vp]),
     "xs_raycast": (_i, [_vp, Intr, _PP, _PP, _i, _i, _vp, _vp, _vp]),
     "xs_tsdf_hessian": (_i, [_vp, _sz, _i, _i, Intr, _pi, _f, _PP, _f, _vp, _pd, _vp]),
+    "xs_tsdf_loss": (_i, [_vp, _sz, _i, _i, Intr, _pi, _f, _pf, _pf, _f, _vp, _pd, _vp]),
     "xs_extract_points": (_l, [_vp, _vp, _vp, _l, _vp]),
     "xs_estimate_combined": (_i, [_PP, _vp, _vp, _PP, Intr, _vp, _vp, _i, _i, _i, _i, _f, _f, _pd, _pd, _vp]),
+    "xs_compute_optimize_matrix": (_l, [_PP, _vp, _vp, _PP, Intr, _vp, _vp, _i, _i, _f, _f, _pd, _pd, _vp]),
     "xs_kinfu_create": (_vp, [C.POINTER(Config), _i, _i, _pf, _i]),
     "xs_kinfu_destroy": (None, [_vp]),
     "xs_kinfu_process_frame": (_i, [_vp, _vp, _i]),

@@ -104,6 +104,50 @@ struct SolveParams {
 template <int C> __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, const double *real_sums,
                                                                   const double *comp_sums);
 
+// search_newton (ICP.cu:196-244) on real parts with the reference's rounding sequence: projection of the current
+// vertex into the previous frame, bounds / NaN / distance / angle gates.  Outputs vcurr, vcurr_g and the matched pixel.
+XS_DEV bool search_newton_real(const IcpParams &P, const float *s_curr, int x, int y, size_t plane, float &vcx, float &vcy,
+                               float &vcz, float &gx, float &gy, float &gz, int &ux, int &uy) {
+    const size_t pix = (size_t) y * P.cols + x;
+    const float ncx = P.nmap_curr[pix];
+    if (isnan(ncx)) return false;
+    const float ncy = P.nmap_curr[pix + plane], ncz = P.nmap_curr[pix + 2 * plane];
+    vcx = P.vmap_curr[pix];
+    vcy = P.vmap_curr[pix + plane];
+    vcz = P.vmap_curr[pix + 2 * plane];
+    const float *R = s_curr, *t = s_curr + 9, *Q = P.prev.R, *tp = P.prev.t;
+    // vcurr_g = Rcurr * vcurr + tcurr
+    gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], vcx), __fmul_rn(R[1], vcy)), __fmul_rn(R[2], vcz)), t[0]);
+    gy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3], vcx), __fmul_rn(R[4], vcy)), __fmul_rn(R[5], vcz)), t[1]);
+    gz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[6], vcx), __fmul_rn(R[7], vcy)), __fmul_rn(R[8], vcz)), t[2]);
+    // vcurr_cp = Rprev_inv * (vcurr_g - tprev)
+    const float ex = __fsub_rn(gx, tp[0]), ey = __fsub_rn(gy, tp[1]), ez = __fsub_rn(gz, tp[2]);
+    const float px = __fadd_rn(__fadd_rn(__fmul_rn(Q[0], ex), __fmul_rn(Q[1], ey)), __fmul_rn(Q[2], ez));
+    const float py = __fadd_rn(__fadd_rn(__fmul_rn(Q[3], ex), __fmul_rn(Q[4], ey)), __fmul_rn(Q[5], ez));
+    const float pz = __fadd_rn(__fadd_rn(__fmul_rn(Q[6], ex), __fmul_rn(Q[7], ey)), __fmul_rn(Q[8], ez));
+    ux = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(px, P.intr.fx), pz), P.intr.cx));
+    uy = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(py, P.intr.fy), pz), P.intr.cy));
+    if (ux < 0 || uy < 0 || ux >= P.cols || uy >= P.rows || pz < 0) return false;
+    const size_t q = (size_t) uy * P.cols + ux;
+    const float npx = P.nmap_prev[q];
+    if (isnan(npx)) return false;
+    const float npy = P.nmap_prev[q + plane], npz = P.nmap_prev[q + 2 * plane];
+    const float vpx = P.vmap_prev[q], vpy = P.vmap_prev[q + plane], vpz = P.vmap_prev[q + 2 * plane];
+    // dist = norm(vprev_g - vcurr_g)
+    const float ddx = __fsub_rn(vpx, gx), ddy = __fsub_rn(vpy, gy), ddz = __fsub_rn(vpz, gz);
+    const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz)));
+    if (dist > P.dist_thres) return false;
+    // sine = norm(cross(Rcurr * ncurr, nprev_g))
+    const float mx = __fadd_rn(__fadd_rn(__fmul_rn(R[0], ncx), __fmul_rn(R[1], ncy)), __fmul_rn(R[2], ncz));
+    const float my = __fadd_rn(__fadd_rn(__fmul_rn(R[3], ncx), __fmul_rn(R[4], ncy)), __fmul_rn(R[5], ncz));
+    const float mz = __fadd_rn(__fadd_rn(__fmul_rn(R[6], ncx), __fmul_rn(R[7], ncy)), __fmul_rn(R[8], ncz));
+    const float kx = __fsub_rn(__fmul_rn(my, npz), __fmul_rn(mz, npy));
+    const float ky = __fsub_rn(__fmul_rn(mz, npx), __fmul_rn(mx, npz));
+    const float kz = __fsub_rn(__fmul_rn(mx, npy), __fmul_rn(my, npx));
+    const float sine = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(kx, kx), __fmul_rn(ky, ky)), __fmul_rn(kz, kz)));
+    return !(sine >= P.angle_thres);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // pass 1: association + real normal equations
 __global__ void __launch_bounds__(256) icp_assoc_kernel(const IcpParams P) {
@@ -125,57 +169,11 @@ __global__ void __launch_bounds__(256) icp_assoc_kernel(const IcpParams P) {
         const int x = (tile % P.tiles_x) * 32 + threadIdx.x;
         const int y = (tile / P.tiles_x) * 8 + threadIdx.y;
         // ---------------- search_newton, ICP.cu:196-244 (real parts)
-        bool found = false;
         float vcx = 0, vcy = 0, vcz = 0;  // vcurr (camera frame)
         float gx = 0, gy = 0, gz = 0;     // vcurr_g
         int ux = 0, uy = 0;
         const bool inside = x < P.cols && y < P.rows;
-        if (inside) {
-            const size_t pix = (size_t) y * P.cols + x;
-            const float ncx = P.nmap_curr[pix];
-            if (!isnan(ncx)) {
-                const float ncy = P.nmap_curr[pix + plane], ncz = P.nmap_curr[pix + 2 * plane];
-                vcx = P.vmap_curr[pix];
-                vcy = P.vmap_curr[pix + plane];
-                vcz = P.vmap_curr[pix + 2 * plane];
-                const float *R = s_curr, *t = s_curr + 9, *Q = P.prev.R, *tp = P.prev.t;
-                // vcurr_g = Rcurr * vcurr + tcurr
-                gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], vcx), __fmul_rn(R[1], vcy)), __fmul_rn(R[2], vcz)), t[0]);
-                gy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[3], vcx), __fmul_rn(R[4], vcy)), __fmul_rn(R[5], vcz)), t[1]);
-                gz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[6], vcx), __fmul_rn(R[7], vcy)), __fmul_rn(R[8], vcz)), t[2]);
-                // vcurr_cp = Rprev_inv * (vcurr_g - tprev)
-                const float ex = __fsub_rn(gx, tp[0]), ey = __fsub_rn(gy, tp[1]), ez = __fsub_rn(gz, tp[2]);
-                const float px = __fadd_rn(__fadd_rn(__fmul_rn(Q[0], ex), __fmul_rn(Q[1], ey)), __fmul_rn(Q[2], ez));
-                const float py = __fadd_rn(__fadd_rn(__fmul_rn(Q[3], ex), __fmul_rn(Q[4], ey)), __fmul_rn(Q[5], ez));
-                const float pz = __fadd_rn(__fadd_rn(__fmul_rn(Q[6], ex), __fmul_rn(Q[7], ey)), __fmul_rn(Q[8], ez));
-                ux = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(px, P.intr.fx), pz), P.intr.cx));
-                uy = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(py, P.intr.fy), pz), P.intr.cy));
-                if (!(ux < 0 || uy < 0 || ux >= P.cols || uy >= P.rows || pz < 0)) {
-                    const size_t q = (size_t) uy * P.cols + ux;
-                    const float npx = P.nmap_prev[q];
-                    if (!isnan(npx)) {
-                        const float npy = P.nmap_prev[q + plane], npz = P.nmap_prev[q + 2 * plane];
-                        const float vpx = P.vmap_prev[q], vpy = P.vmap_prev[q + plane], vpz = P.vmap_prev[q + 2 * plane];
-                        // dist = norm(vprev_g - vcurr_g)
-                        const float ddx = __fsub_rn(vpx, gx), ddy = __fsub_rn(vpy, gy), ddz = __fsub_rn(vpz, gz);
-                        const float dist = __fsqrt_rn(
-                            __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz)));
-                        if (!(dist > P.dist_thres)) {
-                            // sine = norm(cross(Rcurr * ncurr, nprev_g))
-                            const float mx = __fadd_rn(__fadd_rn(__fmul_rn(R[0], ncx), __fmul_rn(R[1], ncy)), __fmul_rn(R[2], ncz));
-                            const float my = __fadd_rn(__fadd_rn(__fmul_rn(R[3], ncx), __fmul_rn(R[4], ncy)), __fmul_rn(R[5], ncz));
-                            const float mz = __fadd_rn(__fadd_rn(__fmul_rn(R[6], ncx), __fmul_rn(R[7], ncy)), __fmul_rn(R[8], ncz));
-                            const float kx = __fsub_rn(__fmul_rn(my, npz), __fmul_rn(mz, npy));
-                            const float ky = __fsub_rn(__fmul_rn(mz, npx), __fmul_rn(mx, npz));
-                            const float kz = __fsub_rn(__fmul_rn(mx, npy), __fmul_rn(my, npx));
-                            const float sine = __fsqrt_rn(
-                                __fadd_rn(__fadd_rn(__fmul_rn(kx, kx), __fmul_rn(ky, ky)), __fmul_rn(kz, kz)));
-                            found = !(sine >= P.angle_thres);
-                        }
-                    }
-                }
-            }
-        }
+        const bool found = inside && search_newton_real(P, s_curr, x, y, plane, vcx, vcy, vcz, gx, gy, gz, ux, uy);
         // ---------------- the real row, ICP.cu:254-260: s = vcurr_g, n = nprev_g, d = vprev_g
         float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (found) {
@@ -971,6 +969,83 @@ int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, cons
     return XS_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Combined::computeOptimizeMatrix (ICP.cu:283-355): per-correspondence analytic Jacobian (3x4) and Gauss-Newton Hessian
+// (12x12, upper triangle = 78 sums) of the point-to-plane energy with respect to the 12 entries of [R | t], real parts.
+// The reference runs 12 + 78 sequential 256-thread shared-memory tree reductions per block and 90 thrust::reduce calls;
+// here a thread accumulates its pixels in double, the block reduces with shuffles and the last block adds the partials.
+constexpr int OPT_VALS = 12 + 78;
+__global__ void __launch_bounds__(256) icp_optimize_matrix_kernel(const IcpParams P, double *partials, double *out,
+                                                                   unsigned long long *count_out) {
+    __shared__ float s_curr[12];
+    __shared__ double s_red[8][OPT_VALS];
+    __shared__ unsigned int s_cnt[8];
+    __shared__ bool s_last;
+    const int tid = threadIdx.y * 32 + threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < 12) s_curr[tid] = P.pose_curr[tid];
+    __syncthreads();
+    const size_t plane = (size_t) P.rows * P.cols;
+    const int ntiles = P.tiles_x * P.tiles_y;
+    double acc[OPT_VALS];
+#pragma unroll
+    for (int e = 0; e < OPT_VALS; ++e) acc[e] = 0.0;
+    unsigned int cnt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int x = (tile % P.tiles_x) * 32 + threadIdx.x;
+        const int y = (tile / P.tiles_x) * 8 + threadIdx.y;
+        float vcx, vcy, vcz, gx, gy, gz;
+        int ux, uy;
+        if (!(x < P.cols && y < P.rows && search_newton_real(P, s_curr, x, y, plane, vcx, vcy, vcz, gx, gy, gz, ux, uy))) continue;
+        ++cnt;
+        const size_t q = (size_t) uy * P.cols + ux;
+        const float n1[3] = {P.nmap_prev[q], P.nmap_prev[q + plane], P.nmap_prev[q + 2 * plane]};
+        const float p0[4] = {vcx, vcy, vcz, 1.f};
+        // proj_norm = (p0_trans - p1) . n1, ICP.cu:312-314
+        const float proj = (gx - P.vmap_prev[q]) * n1[0] + (gy - P.vmap_prev[q + plane]) * n1[1] + (gz - P.vmap_prev[q + 2 * plane]) * n1[2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i * 4 + j] += (double) (2 * n1[i] * proj * p0[j]);  // :315
+        int e = 12;
+#pragma unroll
+        for (int a = 0; a < 12; ++a)
+#pragma unroll
+            for (int b = a; b < 12; ++b, ++e) acc[e] += (double) (2 * (p0[a % 4] * (n1[a / 4] * n1[b / 4] * p0[b % 4])));  // :334-342
+    }
+#pragma unroll
+    for (int e = 0; e < OPT_VALS; ++e) {
+        double v = acc[e];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[warp][e] = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    if (tid < OPT_VALS) {
+        double v = 0;
+        for (int w = 0; w < 8; ++w) v += s_red[w][tid];
+        partials[(size_t) blockIdx.x * OPT_VALS + tid] = v;
+    }
+    if (tid == 0) {
+        unsigned int c = 0;
+        for (int w = 0; w < 8; ++w) c += s_cnt[w];
+        atomicAdd(count_out, (unsigned long long) c);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < OPT_VALS) {
+        double v = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partials + (size_t) b * OPT_VALS + tid);
+        out[tid] = v;
+    }
+    if (tid == 0) *P.ticket = 0u;
+}
+
 void icp_timing_reset() { g_icp.n_timed = 0; }
 
 }  // namespace xs
@@ -1036,4 +1111,67 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
             }
     }
     return XS_OK;
+}
+
+extern "C" long xs_compute_optimize_matrix(const xs_pose *curr, const float *d_vmap_curr, const float *d_nmap_curr,
+                                           const xs_pose *prev, xs_intr intr, const float *d_vmap_g_prev,
+                                           const float *d_nmap_g_prev, int rows, int cols, float dist_thres, float angle_thres,
+                                           double *jacobi_host, double *hessian_host, void *stream) {
+    if (!curr || !prev || !d_vmap_curr || !d_nmap_curr || !d_vmap_g_prev || !d_nmap_g_prev || !jacobi_host || !hessian_host ||
+        rows <= 0 || cols <= 0) {
+        set_error("xs_compute_optimize_matrix: null argument");
+        return -1;
+    }
+    cudaStream_t s = (cudaStream_t) stream;
+    if (icp_reserve(0, rows * cols, 0, 0) != XS_OK) return -1;
+    const int grid = 296;
+    double *d_buf = nullptr;
+    if (cudaMalloc(&d_buf, ((size_t) (grid + 1) * OPT_VALS + 1) * sizeof(double) + 12 * sizeof(float)) != cudaSuccess) {
+        set_error("xs_compute_optimize_matrix: cudaMalloc failed");
+        return -1;
+    }
+    double *d_out = d_buf + (size_t) grid * OPT_VALS;
+    unsigned long long *d_count = reinterpret_cast<unsigned long long *>(d_out + OPT_VALS);
+    float *d_pose = reinterpret_cast<float *>(d_count + 1);
+    float h_pose[12];
+    for (int e = 0; e < 9; ++e) h_pose[e] = curr->R[e];
+    for (int e = 0; e < 3; ++e) h_pose[9 + e] = curr->t[e];
+    cudaMemcpyAsync(d_pose, h_pose, sizeof(h_pose), cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), s);
+    IcpParams P = {};
+    for (int i = 0; i < 9; ++i) P.prev.R[i] = prev->R[i];
+    for (int i = 0; i < 3; ++i) P.prev.t[i] = prev->t[i];
+    P.pose_curr = d_pose;
+    P.vmap_curr = d_vmap_curr;
+    P.nmap_curr = d_nmap_curr;
+    P.vmap_prev = d_vmap_g_prev;
+    P.nmap_prev = d_nmap_g_prev;
+    P.intr = intr;
+    P.rows = rows;
+    P.cols = cols;
+    P.dist_thres = dist_thres;
+    P.angle_thres = angle_thres;
+    P.ticket = g_icp.d_ticket;
+    P.tiles_x = div_up(cols, 32);
+    P.tiles_y = div_up(rows, 8);
+    const int ntiles = P.tiles_x * P.tiles_y;
+    icp_optimize_matrix_kernel<<<ntiles < grid ? ntiles : grid, dim3(32, 8), 0, s>>>(P, d_buf, d_out, d_count);
+    long rc = -1;
+    double h_out[OPT_VALS];
+    unsigned long long h_count = 0;
+    if (cudaGetLastError() == cudaSuccess && cudaMemcpyAsync(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+        cudaMemcpyAsync(&h_count, d_count, sizeof(h_count), cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+        cudaStreamSynchronize(s) == cudaSuccess) {
+        ++xs::g_launches;
+        // jacobi_host(i, j), i < 3, j < 4 -> row-major [3][4]; hessian_host[i1][j1](i2, j2) -> [12][12], index i * 4 + j (ICP.cu:471-488)
+        for (int e = 0; e < 12; ++e) jacobi_host[e] = h_out[e];
+        int e = 12;
+        for (int a = 0; a < 12; ++a)
+            for (int b = a; b < 12; ++b, ++e) hessian_host[a * 12 + b] = hessian_host[b * 12 + a] = h_out[e];
+        rc = (long) h_count;
+    } else {
+        set_error("xs_compute_optimize_matrix: CUDA failure");
+    }
+    cudaFree(d_buf);
+    return rc;
 }

@@ -78,6 +78,38 @@ struct BiC3 {
 XS_DEV BiC bdot(const BiC3 &a, const BiC3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // Internal.h:171-174
 XS_DEV BiC bnorm(const BiC3 &a) { return bic_sqrt(bdot(a, a)); }                              // Internal.h:186-189
 
+// block sums of N per-thread doubles (warp shuffles, then the 8 warps in order), per-block partials, and the last block
+// to arrive adds the partials in block order: deterministic run to run
+template <int N> XS_DEV void block_reduce_to_out(const double (&acc)[N], double *partials, double *out, unsigned int *ticket) {
+    __shared__ double s_part[8][N];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        double v = acc[c];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) s_part[warp][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        double v = 0;
+        for (int w = 0; w < 8; ++w) v += s_part[w][threadIdx.x];
+        partials[(size_t) blockIdx.x * N + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < N) {
+        double v = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partials + (size_t) b * N + threadIdx.x);
+        out[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
 struct LossParams {
     const float *depth;  // metres
     int rows, cols;
@@ -133,33 +165,69 @@ __global__ void __launch_bounds__(256) tsdf_hessian_kernel(const LossParams P) {
         acc[2] += (double) loss.im.im;  // hessian()
         acc[3] += 1.0;
     }
-    __shared__ double s_part[8][4];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        double v = acc[c];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) s_part[warp][c] = v;
+    block_reduce_to_out<4>(acc, P.partials, P.out, P.ticket);
+}
+
+// ComputeLocalTsdfLossKernel (TsdfFusion.cu:335-406): the real-only twin of the kernel above - plain FP32 with the
+// reference's expression shapes (so nvcc contracts the same FMAs), reduced to {sum loss, count}.
+struct RealLossParams {
+    const float *depth;  // metres
+    int rows, cols;
+    int rx, ry, rz;
+    float voxel, trunc;
+    xs_intr intr;
+    float R[9], t[3];
+    const float *gt;
+    double *partials;  // [grid][2]
+    double *out;       // [2]
+    unsigned int *ticket;
+};
+XS_DEV float fdot3(float ax, float ay, float az, float bx, float by, float bz) { return ax * bx + ay * by + az * bz; }  // Internal.h:215-218
+
+__global__ void __launch_bounds__(256) tsdf_loss_kernel(const RealLossParams P) {
+    const size_t nvox = (size_t) P.rx * P.ry * P.rz;
+    const float tranc_dist_inv = 1.0f / P.trunc;
+    double acc[2] = {0, 0};
+    for (size_t index = (size_t) blockIdx.x * blockDim.x + threadIdx.x; index < nvox; index += (size_t) gridDim.x * blockDim.x) {
+        const float gt_tsdf = __ldg(P.gt + index);
+        if (gt_tsdf == 0 || fabs(gt_tsdf) > 0.95) continue;  // :352 (compared in double, as the literal is)
+        const int x = (int) (index % P.rx), y = (int) ((index / P.rx) % P.ry), z = (int) (index / ((size_t) P.rx * P.ry));
+        const float v_g_x = (float(x) + 0.5f) * P.voxel, v_g_y = (float(y) + 0.5f) * P.voxel, v_g_z = (float(z) + 0.5f) * P.voxel;
+        const float v_c_x = fdot3(P.R[0], P.R[1], P.R[2], v_g_x, v_g_y, v_g_z) + P.t[0];  // Rv2c * v_g + tv2c, :358
+        const float v_c_y = fdot3(P.R[3], P.R[4], P.R[5], v_g_x, v_g_y, v_g_z) + P.t[1];
+        const float v_c_z = fdot3(P.R[6], P.R[7], P.R[8], v_g_x, v_g_y, v_g_z) + P.t[2];
+        const float inv_z = 1.0f / v_c_z;
+        if (inv_z < 0) continue;
+        const float image_x = v_c_x * inv_z * P.intr.fx + P.intr.cx;
+        const float image_y = v_c_y * inv_z * P.intr.fy + P.intr.cy;
+        const int coox = __float2int_rd(image_x - 0.5f), cooy = __float2int_rd(image_y - 0.5f);
+        if (!(coox > 1 && cooy > 1 && coox < P.cols - 1 && cooy < P.rows - 1)) continue;
+        const int nx = __float2int_rn(image_x), ny = __float2int_rn(image_y);
+        const float d00 = __ldg(P.depth + (size_t) cooy * P.cols + coox), d10 = __ldg(P.depth + (size_t) cooy * P.cols + coox + 1);
+        const float d01 = __ldg(P.depth + (size_t) (cooy + 1) * P.cols + coox),
+                    d11 = __ldg(P.depth + (size_t) (cooy + 1) * P.cols + coox + 1);
+        float Dp;
+        if (d00 != 0.0f && d01 != 0.0f && d10 != 0.0f && d11 != 0.0f) {  // :378-386
+            const float one = 1.0f;
+            const float a = image_x - (float(coox) + 0.5f);
+            const float b = image_y - (float(cooy) + 0.5f);
+            Dp = d00 * (one - a) * (one - b) + d10 * a * (one - b) + d01 * (one - a) * b + d11 * a * b;
+        } else {
+            Dp = __ldg(P.depth + (size_t) ny * P.cols + nx);
+        }
+        if (Dp > 5 || Dp < 0.2) continue;  // :390
+        const float xl = (image_x - P.intr.cx) / P.intr.fx;
+        const float yl = (image_y - P.intr.cy) / P.intr.fy;
+        const float v1x = Dp * xl, v1y = Dp * yl, v1z = Dp;
+        const float distance = sqrt(fdot3(v1x, v1y, v1z, v1x, v1y, v1z)) - sqrt(fdot3(v_c_x, v_c_y, v_c_z, v_c_x, v_c_y, v_c_z));
+        const float gt_distance = gt_tsdf * P.trunc;
+        const float error = (distance - gt_distance) * tranc_dist_inv;
+        if (fabs(error) > 1) continue;
+        const float loss = error * error;
+        acc[0] += (double) loss;
+        acc[1] += 1.0;
     }
-    __syncthreads();
-    __shared__ bool s_last;
-    if (threadIdx.x < 4) {
-        double v = 0;
-        for (int w = 0; w < 8; ++w) v += s_part[w][threadIdx.x];
-        P.partials[(size_t) blockIdx.x * 4 + threadIdx.x] = v;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (threadIdx.x < 4) {
-        double v = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(P.partials + (size_t) b * 4 + threadIdx.x);
-        P.out[threadIdx.x] = v;
-    }
-    if (threadIdx.x == 0) *P.ticket = 0u;
+    block_reduce_to_out<2>(acc, P.partials, P.out, P.ticket);
 }
 
 __global__ void scale_depth_kernel2(const uint16_t *__restrict__ depth, size_t step, int rows, int cols, float *__restrict__ out) {
@@ -211,6 +279,51 @@ extern "C" int xs_tsdf_hessian(const uint16_t *d_depth, size_t depth_step_bytes,
     tsdf_hessian_kernel<<<grid, 256, 0, s>>>(P);
     XS_LAUNCH_CHECK();
     XS_CUDA(cudaMemcpyAsync(out4_host, P.out, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    XS_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_scaled);
+    cudaFree(d_part);
+    cudaFree(d_ticket);
+    return XS_OK;
+}
+
+extern "C" int xs_tsdf_loss(const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, xs_intr intr, const int res[3],
+                            float voxel_size, const float Rv2c[9], const float tv2c[3], float trunc, const float *d_gt,
+                            double *out2_host, void *stream) {
+    if (!d_depth || !res || !Rv2c || !tv2c || !d_gt || !out2_host || rows <= 0 || cols <= 0) {
+        set_error("xs_tsdf_loss: null argument");
+        return XS_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t) stream;
+    const int grid = 148 * 8;
+    float *d_scaled = nullptr;
+    double *d_part = nullptr;
+    unsigned int *d_ticket = nullptr;
+    XS_CUDA(cudaMalloc(&d_scaled, (size_t) rows * cols * sizeof(float)));
+    XS_CUDA(cudaMalloc(&d_part, (size_t) (grid + 1) * 2 * sizeof(double)));
+    XS_CUDA(cudaMalloc(&d_ticket, sizeof(unsigned int)));
+    XS_CUDA(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), s));
+    dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
+    scale_depth_kernel2<<<grd, blk, 0, s>>>(d_depth, depth_step_bytes, rows, cols, d_scaled);
+    XS_LAUNCH_CHECK();
+    RealLossParams P;
+    P.depth = d_scaled;
+    P.rows = rows;
+    P.cols = cols;
+    P.rx = res[0];
+    P.ry = res[1];
+    P.rz = res[2];
+    P.voxel = voxel_size;
+    P.trunc = trunc;
+    P.intr = intr;
+    for (int i = 0; i < 9; ++i) P.R[i] = Rv2c[i];
+    for (int i = 0; i < 3; ++i) P.t[i] = tv2c[i];
+    P.gt = d_gt;
+    P.partials = d_part;
+    P.out = d_part + (size_t) grid * 2;
+    P.ticket = d_ticket;
+    tsdf_loss_kernel<<<grid, 256, 0, s>>>(P);
+    XS_LAUNCH_CHECK();
+    XS_CUDA(cudaMemcpyAsync(out2_host, P.out, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     XS_CUDA(cudaStreamSynchronize(s));
     cudaFree(d_scaled);
     cudaFree(d_part);

@@ -4,7 +4,7 @@ ICP,ExtractPointCloud}.h) on torch CUDA tensors.
 torch is used only for device memory and streams; every computation is a call through the C-ABI of
 libxslam_b200.so.  Names and argument meaning follow the reference (bilateralFilter, pyrDown, createVMap,
 createNMap, resizeVMap, resizeNMap, integrateTsdfVolume, raycast, estimateCombined,
-ComputeLocalTsdf_hessian, extractPoints/extractNormals); maps are packed SoA tensors
+ComputeLocalTsdf_hessian, ComputeLocalTsdf_loss, extractPoints/extractNormals); maps are packed SoA tensors
 [(1+ncomp), 3, rows, cols] instead of interleaved pitched devComplex arrays.
 """
 import ctypes as C
@@ -188,6 +188,20 @@ def ComputeLocalTsdf_hessian(depth_u16, intr, resolution, voxel_size, v2c, trunc
     return [out[i] for i in range(4)]
 
 
+def ComputeLocalTsdf_loss(depth_u16, intr, resolution, voxel_size, Rv2c, tv2c, trunc, gt):
+    """TsdfFusion.h:48-52 (real-only volume loss).  Rv2c: float32 [3, 3] row-major, tv2c: float32 [3]; gt: float32 [z, y, x].
+    Returns [sum loss, count]."""
+    _need_cuda(depth_u16, gt)
+    rows, cols = depth_u16.shape
+    res = (C.c_int * 3)(*[int(r) for r in resolution])
+    out = (C.c_double * 2)()
+    R = (C.c_float * 9)(*[float(v) for v in np.asarray(Rv2c, np.float32).reshape(9)])
+    t = (C.c_float * 3)(*[float(v) for v in np.asarray(tv2c, np.float32).reshape(3)])
+    check(_capi.load().xs_tsdf_loss(_ptr(depth_u16), cols * 2, rows, cols, intr, res, voxel_size, R, t, trunc, _ptr(gt), out,
+                                    _stream()), "ComputeLocalTsdf_loss")
+    return [out[0], out[1]]
+
+
 def extractPoints(volume, max_points=1000000, normals=True):
     """ExtractPointCloud.h:19-23 (extractPoints + extractNormals).  Returns (points [n,3], normals [n,3])."""
     pts = torch.empty((max_points, 3), dtype=torch.float32, device="cuda")
@@ -214,6 +228,24 @@ def estimateCombined(curr, vmap_curr, nmap_curr, prev, intr, vmap_g_prev, nmap_g
                                             b.ctypes.data_as(C.POINTER(C.c_double)), _stream()), "estimateCombined")
     # column-major 6x6 (symmetric, so the transpose is the same matrix)
     return A.reshape(1 + ncomp, 6, 6).transpose(0, 2, 1).copy(), b
+
+
+def computeOptimizeMatrix(vmap_curr, nmap_curr, vmap_g_prev, nmap_g_prev, curr, prev, intr, distThres, angleThres):
+    """ICP.h:34-40 (argument order as the reference).  Real parts only: vmap_g_prev / nmap_g_prev may carry derivative
+    components, which are ignored.  Returns (count, jacobi [3, 4], hessian [12, 12]) - hessian[i1 * 4 + j1, i2 * 4 + j2] is
+    the reference's hessian_host[i1][j1](i2, j2)."""
+    _need_cuda(vmap_curr, nmap_curr, vmap_g_prev, nmap_g_prev)
+    _, rows, cols = vmap_curr.shape
+    J = np.zeros((12,), np.float64)
+    H = np.zeros((144,), np.float64)
+    pc, pp = curr.c(), prev.c()
+    n = _capi.load().xs_compute_optimize_matrix(C.byref(pc), _ptr(vmap_curr), _ptr(nmap_curr), C.byref(pp), intr,
+                                                _ptr(vmap_g_prev), _ptr(nmap_g_prev), rows, cols, distThres, angleThres,
+                                                J.ctypes.data_as(C.POINTER(C.c_double)), H.ctypes.data_as(C.POINTER(C.c_double)),
+                                                _stream())
+    if n < 0:
+        check(-1, "computeOptimizeMatrix")
+    return int(n), J.reshape(3, 4), H.reshape(12, 12)
 
 
 # ------------------------------------------------------------------ DeviceArray second-order complex (DoubleComplex)
