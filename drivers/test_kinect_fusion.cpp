@@ -3,8 +3,9 @@
 // "mean frame time".  Host C++ over the C-ABI of libxslam_b200.so (include/xslam_b200.h); no CPU fallback.
 //
 // Differences from the reference driver, all stated:
-//  * dataset_format "synthetic" (analytic-SDF room + closed-form trajectory, xs_synth_depth / xs_synth_pose) replaces
-//    the ICL-NUIM / 7-Scenes PNG readers (Dataset.cpp), which need files and OpenCV that do not exist offline;
+//  * dataset_format: "ICL" (ICL_Dataset, as the reference driver), "7-Scenes" (seven_scenes_Dataset with the `seq_info`
+//    file readInfo parses) - both through the library's OpenCV-free readers (xs_dataset_*, csrc/dataset.cpp) - or
+//    "synthetic" (analytic-SDF room + closed-form trajectory, xs_synth_depth / xs_synth_pose; no datasets offline);
 //  * csfd_mode (none | gradient | hessian) seeds k perturbation directions on world2camera — the batched form of the
 //    commented seeding line KinectFusionReconstruction.cpp:22 — and log_pose_derivatives writes, next to every
 //    frame-%06d.pose.txt, frame-%06d.dpose.txt with one row of 16 values per derivative component (d world2camera
@@ -13,6 +14,7 @@
 #include "../include/xslam_b200.h"
 #include "flat_yaml.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -44,11 +46,19 @@ static void mul4(const float *a, const float *b, float *c) {
             c[i * 4 + j] = s;
         }
 }
-static void rigid_inverse(const float *m, float *o) {
+// inverse of [A t; 0 0 0 1] by cofactors of A (Eigen's Matrix4f::inverse on dataset.getPose(0), main.cpp:72; dataset poses
+// need not be exactly orthonormal)
+static void affine_inverse(const float *m, float *o) {
+    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    const double inv[9] = {(e * i - f * h) / det, (c * h - b * i) / det, (b * f - c * e) / det,
+                           (f * g - d * i) / det, (a * i - c * g) / det, (c * d - a * f) / det,
+                           (d * h - e * g) / det, (b * g - a * h) / det, (a * e - b * d) / det};
     std::memset(o, 0, 16 * sizeof(float));
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) o[i * 4 + j] = m[j * 4 + i];
-    for (int i = 0; i < 3; ++i) o[i * 4 + 3] = -(o[i * 4] * m[3] + o[i * 4 + 1] * m[7] + o[i * 4 + 2] * m[11]);
+    for (int r = 0; r < 3; ++r) {
+        for (int cc = 0; cc < 3; ++cc) o[r * 4 + cc] = (float) inv[r * 3 + cc];
+        o[r * 4 + 3] = (float) -(inv[r * 3] * m[3] + inv[r * 3 + 1] * m[7] + inv[r * 3 + 2] * m[11]);
+    }
     o[15] = 1.f;
 }
 static void print4(const char *name, const float *m) {
@@ -77,12 +87,30 @@ int main(int argc, char *argv[]) {
     std::string output_path = config.str("output_dir");
     if (argc > 2) output_path = argv[2];
     if (!output_path.empty() && output_path.back() != '/') output_path += '/';
-    if (dataset_format != "synthetic") {
-        std::cerr << "dataset_format '" << dataset_format << "': only the synthetic source is built (no datasets offline; "
-                  << "the ICL / 7-Scenes readers are a next row, DESIGN.md 7)\n";
+    // dataset = ICL_Dataset(dataset_dir, start_frame, end_frame, is_flip), main.cpp:34
+    xs_dataset *dataset = nullptr;
+    if (dataset_format == "ICL") {
+        dataset = xs_dataset_open_icl(config.str("dataset_dir").c_str(), start_frame, end_frame, config.b("is_flip", false));
+    } else if (dataset_format == "7-Scenes" || dataset_format == "seven_scenes") {
+        int s[64], e[64];
+        char names[64 * 16];
+        const std::string dir = config.str("dataset_dir");
+        const int n = xs_seven_scenes_read_info(config.str("seq_info", dir + "info.txt").c_str(), s, e, names, 64);
+        const char *name_ptr[64];
+        for (int i = 0; i < n; ++i) name_ptr[i] = names + 16 * i;
+        if (n > 0) dataset = xs_dataset_open_seven_scenes(dir.c_str(), s, e, name_ptr, n, config.b("is_flip", false));
+    } else if (dataset_format != "synthetic") {
+        std::cerr << "dataset_format must be ICL, 7-Scenes or synthetic\n";
         return -1;
     }
-    std::cout << "frame num: " << end_frame - start_frame << std::endl;
+    if (dataset_format != "synthetic" && !dataset) {
+        std::cerr << "cannot open the dataset: " << xs_last_error() << "\n";
+        return -1;
+    }
+    // with a dataset, frame ids index it from 0 and the loop runs to end_frame like main.cpp:45 (clamped to its size)
+    const int first_frame = dataset ? 0 : start_frame;
+    const int last_frame = dataset ? std::min(end_frame, xs_dataset_size(dataset)) : end_frame - start_frame;
+    std::cout << "frame num: " << (dataset ? xs_dataset_size(dataset) : end_frame - start_frame) << std::endl;
     std::cout << "initialize kinect fusion......" << std::endl;
     // KinectFusionReconstruction::SetYamlParameters, KinectFusionReconstruction.cpp:12-72
     xs_config cfg;
@@ -149,16 +177,27 @@ int main(int argc, char *argv[]) {
     float gt0_inv[16];
     {
         float gt0[16];
-        xs_synth_pose(start_frame, gt0);
-        rigid_inverse(gt0, gt0_inv);
+        if (dataset)
+            xs_dataset_get_pose(dataset, 0, gt0);
+        else
+            xs_synth_pose(start_frame, gt0);
+        affine_inverse(gt0, gt0_inv);
     }
     std::vector<float> pts, nrm;
-    while (xs_kinfu_frame_id(kinfu) < end_frame - start_frame) {
+    while (xs_kinfu_frame_id(kinfu) < last_frame) {
         const int frame_id = xs_kinfu_frame_id(kinfu);
         std::cout << "current frame is " << frame_id << "\n";
         float gt_pose[16];
-        xs_synth_pose(start_frame + frame_id, gt_pose);
-        xs_synth_depth(gt_pose, intr, cfg.height, cfg.width, depth.data());
+        if (dataset) {  // dataset.getDepthData(frame_id, depth_map), main.cpp:50
+            if (xs_dataset_get_depth(dataset, first_frame + frame_id, depth.data(), cfg.height, cfg.width) != XS_OK) {
+                std::cerr << "getDepthData failed: " << xs_last_error() << "\n";
+                return -1;
+            }
+            xs_dataset_get_pose(dataset, first_frame + frame_id, gt_pose);
+        } else {
+            xs_synth_pose(start_frame + frame_id, gt_pose);
+            xs_synth_depth(gt_pose, intr, cfg.height, cfg.width, depth.data());
+        }
         // c. process kinect fusion (timed like main.cpp:57-60; the upload of the frame is inside ProcessFrame here)
         const auto t0 = std::chrono::steady_clock::now();
         const int ok = xs_kinfu_process_frame(kinfu, depth.data(), 0);
@@ -194,7 +233,7 @@ int main(int argc, char *argv[]) {
                 out << "\n";
             }
         }
-        if (draw_pcd && frame_id == end_frame - start_frame - 1) {
+        if (draw_pcd && frame_id == last_frame - 1) {
             // ExportPointCloud(1000000) + exportPly on the last frame, main.cpp:76-81 / KinectFusionReconstruction.cpp:334-372
             const long max_buffer = 1000000;
             float *d_pts = nullptr, *d_nrm = nullptr;
@@ -218,5 +257,6 @@ int main(int argc, char *argv[]) {
     const int frames = xs_kinfu_frame_id(kinfu);
     printf("mean frame time = %.3f ms\n", total_time / (frames > 0 ? frames : 1));
     xs_kinfu_destroy(kinfu);
+    xs_dataset_close(dataset);
     return 0;
 }

@@ -218,6 +218,9 @@ int xs_kinfu_get_algorithmic_bytes(const xs_kinfu *k, double *out4);
 /* device pointer where the per-frame derivative record (world2camera, all components) is kept,
  * laid out [(1+ncomp)][16] floats — the buffer the multi-GPU layer all-gathers. */
 float *xs_kinfu_pose_record_device(xs_kinfu *k);
+/* gt_poses + flag_use_gtPose (KinectFusionReconstruction.h:36,82 / .cpp:69,164-166,239-247): with use_gt_pose != 0 frames are
+ * fused at the given camera-to-world poses (row-major 4x4 per frame, real) and ICP is skipped (mapping mode). */
+int xs_kinfu_set_gt_poses(xs_kinfu *k, const float *poses16, int n, int use_gt_pose);
 /* the cudaStream_t every kernel of this pipeline object is launched on (for event timing and stream-ordered consumers) */
 void *xs_kinfu_stream(xs_kinfu *k);
 
@@ -231,6 +234,36 @@ int xs_export_ply(const char *path, const float *points_xyz, const float *normal
 int xs_synth_depth(const float *c2w16, xs_intr intr, int rows, int cols, uint16_t *out_host);
 /* closed-form smooth trajectory, frame 0 = identity; <=1.5 cm and <=0.4 deg per frame */
 int xs_synth_pose(int frame, float *c2w16_out);
+
+
+/* ---------------------------------------------------------------- dataset readers (f2: the step before the path) */
+/* Dataset / ICL_Dataset / seven_scenes_Dataset, Dataset.h:18-81 / Dataset.cpp:3-124 - host code, no OpenCV. */
+typedef struct xs_dataset xs_dataset;
+/* cv::imread(path, IMREAD_UNCHANGED) for non-interlaced 8/16-bit greyscale PNG (Dataset.cpp:7).  out_host may be NULL to
+ * query the size. */
+int xs_read_png16(const char *path, uint16_t *out_host, long capacity, int *rows, int *cols);
+/* loadTxtMatrix, IOHelper.cpp:4-19 (row-major out[rows*cols]) */
+int xs_load_txt_matrix(const char *path, int rows, int cols, float *out);
+/* ICL_Dataset::readPoseFile, Dataset.cpp:90-124: lines [start, end) -> 3x4 top of a row-major 4x4, last row 0 0 0 1 */
+int xs_icl_read_pose_file(const char *poses_path, int start, int end, float *pose16);
+/* ICL_Dataset(dataset_dir, start_frame, end_frame, is_flip), Dataset.cpp:69-88: `depth/<i>.png` (raw / 5 = mm) and
+ * `livingRoom1n.gt.sim`; frames start_frame..end_frame inclusive.  NULL on error (xs_last_error). */
+xs_dataset *xs_dataset_open_icl(const char *dataset_dir, int start_frame, int end_frame, int is_flip);
+/* seven_scenes_Dataset(dataset_dir, start_frames, end_frames, seq_names, is_flip), Dataset.cpp:13-39:
+ * `<seq_name>frame-%06d.depth.png` / `.pose.txt`, seq_name as readInfo returns it ("seq-01/"). */
+xs_dataset *xs_dataset_open_seven_scenes(const char *dataset_dir, const int *start_frames, const int *end_frames,
+                                         const char *const *seq_names, int nseq, int is_flip);
+/* seven_scenes_Dataset::readInfo, Dataset.cpp:41-67.  seq_names_out: max_seq x 16 chars.  Returns the sequence count. */
+int xs_seven_scenes_read_info(const char *filename, int *start_frames, int *end_frames, char *seq_names_out, int max_seq);
+int xs_dataset_size(const xs_dataset *d);
+/* Dataset::getDepthData, Dataset.cpp:3-11: decode, divide by the dataset factor (rounded like cv::Mat /=), optional
+ * horizontal flip; out_host: rows x cols uint16 millimetres, ready for xs_kinfu_process_frame. */
+int xs_dataset_get_depth(const xs_dataset *d, int index, uint16_t *out_host, int rows, int cols);
+int xs_dataset_get_pose(const xs_dataset *d, int index, float *pose16);       /* Dataset::getPose, row-major 4x4 */
+int xs_dataset_set_pose(xs_dataset *d, int index, const float *pose16);       /* Dataset::setPose */
+const char *xs_dataset_timestamp(const xs_dataset *d, int index);            /* Dataset::getTimestamp */
+const char *xs_dataset_depth_filename(const xs_dataset *d, int index);
+void xs_dataset_close(xs_dataset *d);
 
 #ifdef __cplusplus
 }

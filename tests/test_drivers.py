@@ -106,3 +106,46 @@ def test_kinect_fusion_driver_outputs(xs, tmp_path):
     assert ply[0] == "ply" and ply[1] == "format ascii 1.0" and ply[3].startswith("element vertex ")
     n = int(ply[3].split()[-1])
     assert n > 10000 and ply[10] == "end_header" and len(ply[11].split()) == 6
+
+
+@pytest.mark.gpu
+def test_kinect_fusion_driver_icl_dataset(xs, tmp_path):
+    """dataset_format ICL (the reference driver's path, main.cpp:34-51): an ICL-NUIM-shaped tree written from the synthetic
+    frames (raw = 5 x mm, `livingRoom1n.gt.sim`) must reproduce the synthetic run's trajectory bit for bit."""
+    from common import write_png16_fast
+    root = str(tmp_path / "icl") + "/"
+    os.makedirs(root + "depth")
+    lines = []
+    for f in range(4):
+        d = xs.synth_depth(f)
+        assert int(d.max()) * 5 < 65536
+        write_png16_fast(root + "depth/%d.png" % f, (d.astype(np.uint32) * 5).astype(np.uint16))
+        P = xs.synth_pose(f)
+        for r in range(3):
+            lines.append(" ".join("%.9g" % v for v in P[r]))
+        lines.append("")
+    open(root + "livingRoom1n.gt.sim", "w").write("\n".join(lines) + "\n")
+    base = open(os.path.join(ROOT, "configs", "synth_traj2.yaml")).read().replace("end_frame: 30", "end_frame: 3")
+    outs = {}
+    for fmt in ("synthetic", "ICL"):
+        text = base.replace("dataset_format: synthetic", "dataset_format: " + fmt).replace('dataset_dir: ""', 'dataset_dir: "%s"' % root)
+        if fmt == "synthetic":
+            text = text.replace("end_frame: 3", "end_frame: 4")  # synthetic: frames [start, end); ICL: start..end inclusive
+        cfg_path = tmp_path / (fmt + ".yaml")
+        cfg_path.write_text(text)
+        out = str(tmp_path / ("out_" + fmt)) + "/"
+        r = subprocess.run([os.path.join(BIN, "test_kinect_fusion"), str(cfg_path), out], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr + r.stdout[-2000:]
+        if fmt == "ICL":
+            assert "pose path:" + root + "livingRoom1n.gt.sim" in r.stdout and "frame num: 4" in r.stdout
+        outs[fmt] = out
+    for f in range(3):  # the reference loop stops at frame_id == end_frame (main.cpp:45): 3 of the 4 ICL frames
+        for sub in ("slam", "gt"):
+            a = open(os.path.join(outs["ICL"], sub, "frame-%06d.pose.txt" % f)).read()
+            b = open(os.path.join(outs["synthetic"], sub, "frame-%06d.pose.txt" % f)).read()
+            if sub == "slam":
+                assert a == b, (f, sub)
+            else:
+                assert np.abs(np.loadtxt(os.path.join(outs["ICL"], sub, "frame-%06d.pose.txt" % f)) -
+                              np.loadtxt(os.path.join(outs["synthetic"], sub, "frame-%06d.pose.txt" % f))).max() < 2e-6
+    assert not os.path.exists(os.path.join(outs["ICL"], "slam", "frame-000003.pose.txt"))

@@ -144,3 +144,34 @@ def test_dc_array_vs_reference_host(xs, out_dir):
         if op == "t0.5":
             continue
         assert e[0] <= 2e-6 and e[1] <= 1e-5 and e[2] <= 1e-5, (op, e)
+
+
+def test_gt_pose_mapping_mode(xs):
+    """flag_use_gtPose (KinectFusionReconstruction.cpp:69,164-166,239-247): frames are fused at the given poses, ICP is
+    skipped, the record keeps one entry that is overwritten.  Fusing the synthetic frames at their generating poses must give
+    the volume that stage-level integration at those poses gives, and a raycast that tracking can start from."""
+    import torch
+    cfg = dict(xs.DEFAULT_CONFIG)
+    cfg.update(tsdf_size_x=128, tsdf_size_y=128, tsdf_size_z=128, tsdf_voxel_size=0.06, flag_use_gtPose=True)
+    k = xs.KinectFusionReconstruction()
+    k.SetYamlParameters(cfg)
+    assert k.ProcessFrame(xs.synth_depth(0)) == 0  # no pose given for frame 0: an error, not a silent identity
+    k.SetYamlParameters(cfg)
+    k.gt_poses = [xs.synth_pose(f) for f in range(4)]
+    launches0 = xs.load().xs_launch_count()
+    for f in range(4):
+        assert k.ProcessFrame(xs.synth_depth(f)) == 1
+        assert np.abs(k.pose_c2w() - xs.synth_pose(f)).max() < 1e-6
+    per_frame = (xs.load().xs_launch_count() - launches0) / 4
+    assert per_frame < 30, "ICP kernels must not run in mapping mode"
+    # the same frames through tracking: poses agree with ground truth to tracking accuracy, volumes nearly everywhere
+    cfg2 = dict(cfg, flag_use_gtPose=False)
+    t = xs.KinectFusionReconstruction()
+    t.SetYamlParameters(cfg2)
+    for f in range(4):
+        assert t.ProcessFrame(xs.synth_depth(f)) == 1
+    vg, wg, _ = k.volume_planes(0)
+    vt, wt, _ = t.volume_planes(0)
+    assert float((wg != wt).float().mean()) < 2e-2
+    both = (wg > 0) & (wt > 0)
+    assert float((vg[both] - vt[both]).abs().mean()) < 2e-2

@@ -89,10 +89,24 @@ SYMBOLS = {
     "xs_kinfu_pose_record_device": (_vp, [_vp]),
     "xs_kinfu_stream": (_vp, [_vp]),
     "xs_kinfu_set_world2camera": (_i, [_vp, _pf]),
+    "xs_kinfu_set_gt_poses": (_i, [_vp, _pf, _i, _i]),
     "xs_save_pose_txt": (_i, [C.c_char_p, _pf]),
     "xs_export_ply": (_i, [C.c_char_p, _pf, _pf, _l]),
     "xs_synth_depth": (_i, [_pf, Intr, _i, _i, C.POINTER(C.c_uint16)]),
     "xs_synth_pose": (_i, [_i, _pf]),
+    "xs_read_png16": (_i, [C.c_char_p, C.POINTER(C.c_uint16), _l, _pi, _pi]),
+    "xs_load_txt_matrix": (_i, [C.c_char_p, _i, _i, _pf]),
+    "xs_icl_read_pose_file": (_i, [C.c_char_p, _i, _i, _pf]),
+    "xs_dataset_open_icl": (_vp, [C.c_char_p, _i, _i, _i]),
+    "xs_dataset_open_seven_scenes": (_vp, [C.c_char_p, _pi, _pi, C.POINTER(C.c_char_p), _i, _i]),
+    "xs_seven_scenes_read_info": (_i, [C.c_char_p, _pi, _pi, C.c_char_p, _i]),
+    "xs_dataset_size": (_i, [_vp]),
+    "xs_dataset_get_depth": (_i, [_vp, _i, C.POINTER(C.c_uint16), _i, _i]),
+    "xs_dataset_get_pose": (_i, [_vp, _i, _pf]),
+    "xs_dataset_set_pose": (_i, [_vp, _i, _pf]),
+    "xs_dataset_timestamp": (C.c_char_p, [_vp, _i]),
+    "xs_dataset_depth_filename": (C.c_char_p, [_vp, _i]),
+    "xs_dataset_close": (None, [_vp]),
 }
 
 _lib = None

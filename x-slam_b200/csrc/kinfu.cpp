@@ -60,6 +60,8 @@ struct xs_kinfu {
     float *d_record = nullptr, *h_record = nullptr;  // [(1+ncomp)][16]
     float *d_pose[2] = {nullptr, nullptr};           // ICP current pose, ping-pong: [(1+ncomp)][12] (R row-major, t)
     float *h_pose = nullptr;                         // pinned staging of the same
+    std::vector<float> gt_poses;  // [n][16] camera-to-world, KinectFusionReconstruction.h:36
+    bool use_gt_pose = false;     // flag_use_gtPose, KinectFusionReconstruction.cpp:69
     int *d_status = nullptr, *h_status = nullptr;    // [2] ICP degeneracy flag (icp.cu SolveParams::status)
     bool log_icp = false;
     double *d_icp_log = nullptr, *h_icp_log = nullptr;  // [max 16 iterations][27*(1+ncomp)] sums per iteration
@@ -244,6 +246,7 @@ int xs_kinfu_pose_estimate(xs_kinfu *k) {
     k->icp_iters_done = 0;
     k->icp_log.clear();
     icp_timing_reset();
+    if (k->use_gt_pose) return 1;  // mapping with known poses: AlignDepthToReconstruction returns before ICP, :164-166
     if (k->frame_id == 0) return 0;
     const xs_config &c = k->cfg;
     const int ncomp = k->ncomp;
@@ -347,10 +350,21 @@ int xs_kinfu_calculate_point_cloud(xs_kinfu *k) {
     return rc;
 }
 
-// IntegrateFrame, KinectFusionReconstruction.cpp:237-278 (gt-pose mode is a "next" row)
+// IntegrateFrame, KinectFusionReconstruction.cpp:237-278
 int xs_kinfu_integrate_frame(xs_kinfu *k, const uint16_t *d_depth) {
     set_ctx(k);
     const xs_config &c = k->cfg;
+    if (k->use_gt_pose) {  // :239-247: world2camera = inverse(gt c2w) with zero imaginary part; the record's last entry is replaced
+        if ((size_t) k->frame_id >= k->gt_poses.size() / 16) {
+            set_error("IntegrateFrame: flag_use_gtPose is set but no ground-truth pose was given for this frame");
+            return XS_ERR_ARG;
+        }
+        HMat4 gt = HMat4::identity();
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) gt.m[i][j] = HJet(k->gt_poses[(size_t) k->frame_id * 16 + i * 4 + j]);
+        k->world2camera = hinverse(gt);
+        k->record.back() = k->world2camera;
+    }
     HMat4 c2w = hinverse(k->record.back());
     HMat4 c2v = hmul(k->world2volume, c2w);
     HMat4 v2c = hinverse(c2v);
@@ -440,6 +454,15 @@ int xs_kinfu_set_world2camera(xs_kinfu *k, const float *in) {
             }
     k->record.clear();
     k->record.push_back(k->world2camera);
+    return XS_OK;
+}
+
+// gt_poses (camera-to-world, row-major 4x4 per frame) + flag_use_gtPose (KinectFusionReconstruction.h:36,82): with the flag
+// set, frames are fused at the given poses and ICP is skipped (mapping mode of the relocalisation experiments).
+int xs_kinfu_set_gt_poses(xs_kinfu *k, const float *poses16, int n, int use_gt_pose) {
+    if (!k || n < 0 || (n > 0 && !poses16)) return XS_ERR_ARG;
+    k->gt_poses.assign(poses16, poses16 + (size_t) n * 16);
+    k->use_gt_pose = use_gt_pose != 0;
     return XS_OK;
 }
 

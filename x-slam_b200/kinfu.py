@@ -142,6 +142,22 @@ class KinectFusionReconstruction:
         self.h = self.lib.xs_kinfu_create(C.byref(c), comps, self.dirs, sp, solve_mode)
         if not self.h:
             raise _capi.XsError("SetYamlParameters: " + self.lib.xs_last_error().decode())
+        self.use_gtPose = bool(cfg.get("flag_use_gtPose", False))  # KinectFusionReconstruction.cpp:69
+        self._gt_poses = []                                        # :70 gt_poses.resize(0)
+        if self.use_gtPose:
+            self.lib.xs_kinfu_set_gt_poses(self.h, None, 0, 1)
+
+    @property
+    def gt_poses(self):
+        """KinectFusionReconstruction.h:36: camera-to-world ground-truth poses, used when flag_use_gtPose is set."""
+        return self._gt_poses
+
+    @gt_poses.setter
+    def gt_poses(self, poses):
+        self._gt_poses = [np.asarray(p, np.float32).reshape(4, 4) for p in poses]
+        flat = np.ascontiguousarray(np.stack(self._gt_poses), np.float32) if self._gt_poses else np.zeros((0, 16), np.float32)
+        _capi.check(self.lib.xs_kinfu_set_gt_poses(self.h, flat.ctypes.data_as(C.POINTER(C.c_float)), len(self._gt_poses),
+                                                  int(self.use_gtPose)), "gt_poses")
 
     def ReleaseBuffers(self):
         if self.h:
