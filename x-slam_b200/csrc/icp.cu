@@ -219,9 +219,22 @@ __global__ void __launch_bounds__(256) icp_assoc_kernel(const IcpParams P) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // fixed-order sum over the blocks: warp w adds its contiguous eighth of the per-block partials in order (lane = product,
+    // independent L2 loads in flight), then the eight segment sums are added in warp order
+    {
+        const int nb = (int) gridDim.x, seg = (nb + 7) / 8, b0 = warp * seg, b1 = min(nb, b0 + seg);
+        double sum = 0.0;
+        if (lane < 27) {
+#pragma unroll 8
+            for (int b = b0; b < b1; ++b) sum += __ldcg(P.partials + (size_t) b * 27 + lane);
+        }
+        s_stage[warp][lane] = sum;
+    }
+    __syncthreads();
     if (tid < 27) {
         double sum = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(P.partials + (size_t) b * 27 + tid);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += s_stage[w][tid];
         P.sums[tid] = sum;
     }
     if (tid == 0) *P.ticket = 0u;
