@@ -19,7 +19,7 @@ wc -l gpurun_out/launches_$TAG.csv
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'raycast_hit_kernel|raycast_march_kernel|integrate_kernel|resize_map' -s 14 -c 7 \
     -f -o gpurun_out/prof_${TAG}_vol python bench.py --steps 1 --warmup 3 --no-cpu-baseline --dirs $ND > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "ncu full (volume kernels) rc=$?"; tail -1 gpurun_out/ncu_full_$TAG.log
-# level-0 iteration of frame 2: assoc, deriv, finish, solve
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'icp_' -s 76 -c 4 \
+# level-0 iteration of frame 2: assoc, deriv (two launches per iteration; frame 1 has 24, levels 2 and 1 of frame 2 have 14)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'icp_' -s 38 -c 2 \
     -f -o gpurun_out/prof_${TAG}_icp python bench.py --steps 1 --warmup 3 --no-cpu-baseline --dirs $ND > gpurun_out/ncu_full_${TAG}_icp.log 2>&1
 echo "ncu full (icp) rc=$?"; tail -1 gpurun_out/ncu_full_${TAG}_icp.log; ls -la gpurun_out/ | tail -12

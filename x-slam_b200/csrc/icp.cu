@@ -87,9 +87,10 @@ struct IcpParams {
     unsigned int *ticket;
     int tiles_x, tiles_y;
     // derivative pass
-    double *dpartials;  // [chunks][groups][81]
-    int chunks, groups, ppt;
+    double *dpartials;  // [groups][max_writers][81]
+    int chunks, groups, ppt;  // chunks = pixel units of 256 * ppt pixels
     unsigned int *group_ticket;  // [groups] arrival counters of the derivative pass (self-resetting)
+    int max_writers;             // upper bound of the CTAs that write a partial for one group
 };
 
 // the Gauss-Newton step that closes an iteration (icp_solve_direction below)
@@ -287,192 +288,226 @@ template <int N> XS_DEV void cp_async_wait() { asm volatile("cp.async.wait_group
 // staged per-pixel inputs: 16 record floats + 3 components x (dn[3], dd[3]) gathered at the matched pixel
 constexpr int DERIV_IN = REC_F + 18;
 constexpr int DERIV_MAX_STAGES = 3;
-constexpr size_t deriv_smem(int stages) { return (size_t) stages * DERIV_IN * 256 * sizeof(float); }  // also covers the reduction buffers
+// staging [stage][DERIV_IN][256] floats + per-thread double totals [3][256]
+constexpr size_t deriv_smem(int stages) { return (size_t) stages * DERIV_IN * 256 * sizeof(float) + 3 * 256 * sizeof(double); }
 
-// ST = depth of the cp.async pipeline: the inputs of pixel j + ST - 1 are in flight while pixel j is processed.  The
-// gathers are DRAM round trips (the derivative planes of the previous maps do not fit L2 at level 0), so the bytes in
-// flight per SM - threads x 72 B x (ST - 1) - set the achievable bandwidth (Little's law).
+// Sums v[e] over the 32 lanes of a warp for e = 0..31 in FP32 (fixed butterfly order); lane L returns the total of element L.
+XS_DEV float warp_transpose_reduce_f(float (&v)[32]) {
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = upper ? v[i + half] : v[i];
+            const float send = upper ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+// Work decomposition of the derivative pass.  The (direction group, pixel unit) pairs - a unit is 256 * upt consecutive
+// pixels - are linearised group-major into U = groups * units items and cut into gridDim.x equal contiguous ranges, one per
+// persistent CTA (grid = min(296, U): every CTA slot of the 148 SMs gets the same amount of work whatever the number of
+// directions, e.g. the 7 directions a rank of an 8-GPU run holds).  A CTA therefore walks at most a few group segments;
+// per segment it writes one 81-value partial and takes a ticket of that group.
+//   owner(u) = the CTA whose range [b U / B, (b + 1) U / B) holds item u
+XS_DEV int deriv_owner(long long u, long long U, long long B) { return (int) (((u + 1) * B - 1) / U); }
+
+// ST = depth of the cp.async pipeline: the inputs of pixel j + ST - 1 are in flight while pixel j is processed.
 template <int C, int ST> __global__ void __launch_bounds__(256, 2) icp_deriv_kernel(const IcpParams P, const SolveParams S) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ float s_pose[3][12];
     __shared__ bool s_last;
     float *s_in = reinterpret_cast<float *>(s_raw);  // [stage][DERIV_IN][256]
+    double *s_tot = reinterpret_cast<double *>(s_raw + (size_t) ST * DERIV_IN * 256 * sizeof(float));  // [3][256]
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int group = blockIdx.x, chunk = blockIdx.y;
-    const int comp0 = group * 3;
-    if (tid < 36) {
-        const int a = tid / 12, e = tid % 12;
-        s_pose[a][e] = (comp0 + a < P.ncomp) ? P.pose_curr[(size_t) (1 + comp0 + a) * 12 + e] : 0.f;
-    }
-    __syncthreads();
     const size_t plane = (size_t) P.rows * P.cols;
     const int npix = P.rows * P.cols;
-    float acc[3][27];
+    const long long U = (long long) P.groups * P.chunks, B = gridDim.x;
+    const long long u_begin = blockIdx.x * U / B, u_end = (blockIdx.x + 1) * U / B;
+    for (long long u = u_begin; u < u_end;) {
+        const int group = (int) (u / P.chunks), c_begin = (int) (u % P.chunks);
+        const int c_end = (int) min((long long) P.chunks, c_begin + (u_end - u));
+        u += c_end - c_begin;
+        const int comp0 = group * 3;
+        __syncthreads();  // s_pose / s_tot of the previous segment are no longer read
+        if (tid < 36) {
+            const int a = tid / 12, e = tid % 12;
+            s_pose[a][e] = (comp0 + a < P.ncomp) ? P.pose_curr[(size_t) (1 + comp0 + a) * 12 + e] : 0.f;
+        }
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+        for (int a = 0; a < 3; ++a) s_tot[a * 256 + tid] = 0.0;
+        __syncthreads();
+        float acc[3][27];
 #pragma unroll
-        for (int e = 0; e < 27; ++e) acc[a][e] = 0.f;
-    const int base = chunk * 256 * P.ppt;
-    // Software pipeline without registers: the inputs of the pixels ahead (record + the gathers that depend on the
-    // matched index) are copied global -> shared asynchronously while pixel j is processed; matched indices run ST
-    // pixels ahead in registers.  Every thread reads back only what it copied itself, so no barrier is needed.
-    auto issue = [&](int stage, int p, int q) {
-        if (q >= 0) {
-            float *dst = s_in + (size_t) stage * DERIV_IN * 256 + tid;
-            float4 *dst4 = reinterpret_cast<float4 *>(s_in + (size_t) stage * DERIV_IN * 256) + tid;  // [4][256] float4
-            const float4 *f = P.rec_f + (size_t) p * 4;
+        for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) cp_async16(dst4 + i * 256, f + i);
+            for (int e = 0; e < 27; ++e) acc[a][e] = 0.f;
+        // A thread sums at most 32 pixels in FP32; then the 32 lanes are combined by a fixed FP32 butterfly and lane e adds
+        // the warp total of product e to its double total in shared memory (no barrier, the pipeline keeps running).
+        auto flush = [&]() {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                const int comp = min(comp0 + a, P.ncomp - 1);  // out-of-range slots re-read a valid plane; their sums are dropped
-                // 32-bit element offsets (a map set is < 2^32 floats: checked by the host wrapper): one IMAD.WIDE per copy
-                const unsigned uplane = (unsigned) plane;
-                const unsigned o = (unsigned) q + (unsigned) (1 + comp) * 3u * uplane;
+                float v[32];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    cp_async4(dst + (REC_F + a * 6 + c) * 256, P.nmap_prev + (o + c * uplane));
-                    cp_async4(dst + (REC_F + a * 6 + 3 + c) * 256, P.vmap_prev + (o + c * uplane));
+                for (int e = 0; e < 32; ++e) v[e] = e < 27 ? acc[a][e] : 0.f;
+                s_tot[a * 256 + tid] += (double) warp_transpose_reduce_f(v);
+#pragma unroll
+                for (int e = 0; e < 27; ++e) acc[a][e] = 0.f;
+            }
+        };
+        const int base = c_begin * 256 * P.ppt;
+        const int nitems = (c_end - c_begin) * P.ppt;
+        // Software pipeline without registers: the inputs of the pixels ahead (record + the gathers that depend on the
+        // matched index) are copied global -> shared asynchronously while pixel j is processed; matched indices run ST
+        // pixels ahead in registers.  Every thread reads back only what it copied itself, so no barrier is needed.
+        auto issue = [&](int stage, int p, int q) {
+            if (q >= 0) {
+                float *dst = s_in + (size_t) stage * DERIV_IN * 256 + tid;
+                float4 *dst4 = reinterpret_cast<float4 *>(s_in + (size_t) stage * DERIV_IN * 256) + tid;  // [4][256] float4
+                const float4 *f = P.rec_f + (size_t) p * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cp_async16(dst4 + i * 256, f + i);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const int comp = min(comp0 + a, P.ncomp - 1);  // out-of-range slots re-read a valid plane; their sums are dropped
+                    // 32-bit element offsets (a map set is < 2^32 floats: checked by the host wrapper): one IMAD.WIDE per copy
+                    const unsigned uplane = (unsigned) plane;
+                    const unsigned o = (unsigned) q + (unsigned) (1 + comp) * 3u * uplane;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        cp_async4(dst + (REC_F + a * 6 + c) * 256, P.nmap_prev + (o + c * uplane));
+                        cp_async4(dst + (REC_F + a * 6 + 3 + c) * 256, P.vmap_prev + (o + c * uplane));
+                    }
                 }
             }
-        }
-        cp_async_commit();
-    };
-    auto idx_at = [&](int j) {
-        const int p = base + j * 256 + tid;
-        return (j < P.ppt && p < npix) ? P.rec_idx[p] : -1;
-    };
-    int qs[ST];  // qs[i] = matched index of pixel j + i
+            cp_async_commit();
+        };
+        auto idx_at = [&](int j) {
+            const int p = base + j * 256 + tid;
+            return (j < nitems && p < npix) ? P.rec_idx[p] : -1;
+        };
+        int qs[ST];  // qs[i] = matched index of pixel j + i
 #pragma unroll
-    for (int i = 0; i < ST; ++i) qs[i] = idx_at(i);
+        for (int i = 0; i < ST; ++i) qs[i] = idx_at(i);
 #pragma unroll
-    for (int i = 0; i < ST - 1; ++i) issue(i, base + i * 256 + tid, qs[i]);
-    int st = 0;  // stage that holds pixel j
-    for (int j = 0; j < P.ppt; ++j) {
-        const int p = base + j * 256 + tid;
-        int st_in = st + ST - 1;
-        if (st_in >= ST) st_in -= ST;
-        issue(st_in, p + (ST - 1) * 256, qs[ST - 1]);
-        const int q = qs[0];
+        for (int i = 0; i < ST - 1; ++i) issue(i, base + i * 256 + tid, qs[i]);
+        int st = 0;  // stage that holds pixel j
+        for (int j = 0; j < nitems; ++j) {
+            const int p = base + j * 256 + tid;
+            int st_in = st + ST - 1;
+            if (st_in >= ST) st_in -= ST;
+            issue(st_in, p + (ST - 1) * 256, qs[ST - 1]);
+            const int q = qs[0];
 #pragma unroll
-        for (int i = 0; i < ST - 1; ++i) qs[i] = qs[i + 1];
-        qs[ST - 1] = idx_at(j + ST);
-        const int cur = st;
-        st = (st + 1 == ST) ? 0 : st + 1;
-        cp_async_wait<ST - 1>();  // the copies of pixel j have landed
-        if (q < 0) continue;
-        const float *in = s_in + (size_t) cur * DERIV_IN * 256 + tid;
-        const float4 *in4 = reinterpret_cast<const float4 *>(s_in + (size_t) cur * DERIV_IN * 256) + tid;
-        const float4 f0 = in4[0], f1 = in4[256], f2 = in4[512], f3 = in4[768];
-        const float vc[3] = {f0.x, f0.y, f0.z};
-        const float s[3] = {f0.w, f1.x, f1.y};
-        const float n[3] = {f1.z, f1.w, f2.x};
-        const float e[3] = {f2.y, f2.z, f2.w};
-        const float r[7] = {f3.x, f3.y, f3.z, n[0], n[1], n[2], f3.w};
-        float ds[3][3], dn[3][3], de[3][3];
+            for (int i = 0; i < ST - 1; ++i) qs[i] = qs[i + 1];
+            qs[ST - 1] = idx_at(j + ST);
+            const int cur = st;
+            st = (st + 1 == ST) ? 0 : st + 1;
+            cp_async_wait<ST - 1>();  // the copies of pixel j have landed
+            if (q >= 0) {
+                const float *in = s_in + (size_t) cur * DERIV_IN * 256 + tid;
+                const float4 *in4 = reinterpret_cast<const float4 *>(s_in + (size_t) cur * DERIV_IN * 256) + tid;
+                const float4 f0 = in4[0], f1 = in4[256], f2 = in4[512], f3 = in4[768];
+                const float vc[3] = {f0.x, f0.y, f0.z};
+                const float s[3] = {f0.w, f1.x, f1.y};
+                const float n[3] = {f1.z, f1.w, f2.x};
+                const float e[3] = {f2.y, f2.z, f2.w};
+                const float r[7] = {f3.x, f3.y, f3.z, n[0], n[1], n[2], f3.w};
+                float ds[3][3], dn[3][3], de[3][3];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float *m = s_pose[a];
-            ds[a][0] = fmaf(m[0], vc[0], fmaf(m[1], vc[1], fmaf(m[2], vc[2], m[9])));
-            ds[a][1] = fmaf(m[3], vc[0], fmaf(m[4], vc[1], fmaf(m[5], vc[2], m[10])));
-            ds[a][2] = fmaf(m[6], vc[0], fmaf(m[7], vc[1], fmaf(m[8], vc[2], m[11])));
+                for (int a = 0; a < 3; ++a) {
+                    const float *m = s_pose[a];
+                    ds[a][0] = fmaf(m[0], vc[0], fmaf(m[1], vc[1], fmaf(m[2], vc[2], m[9])));
+                    ds[a][1] = fmaf(m[3], vc[0], fmaf(m[4], vc[1], fmaf(m[5], vc[2], m[10])));
+                    ds[a][2] = fmaf(m[6], vc[0], fmaf(m[7], vc[1], fmaf(m[8], vc[2], m[11])));
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                dn[a][c] = in[(REC_F + a * 6 + c) * 256];
-                de[a][c] = in[(REC_F + a * 6 + 3 + c) * 256] - ds[a][c];
+                    for (int c = 0; c < 3; ++c) {
+                        dn[a][c] = in[(REC_F + a * 6 + c) * 256];
+                        de[a][c] = in[(REC_F + a * 6 + 3 + c) * 256] - ds[a][c];
+                    }
+                }
+                float d[3][7];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    cross3(ds[a], n, d[a]);        // d(s x n) = ds x n + s x dn
+                    cross3_add(s, dn[a], d[a]);
+                    d[a][3] = dn[a][0];
+                    d[a][4] = dn[a][1];
+                    d[a][5] = dn[a][2];
+                    d[a][6] = dot3(dn[a], e) + dot3(n, de[a]);  // d(n . (d - s))
+                }
+                if (C == 3) {  // eps1eps2 cross terms
+                    cross3_add(ds[0], dn[1], d[2]);
+                    cross3_add(ds[1], dn[0], d[2]);
+                    d[2][6] += dot3(dn[0], de[1]) + dot3(dn[1], de[0]);
+                }
+                accumulate_products<C>(acc, r, d[0], d[1], d[2], std::make_integer_sequence<int, 27>());
             }
+            if ((j & 31) == 31) flush();  // warp-uniform: j is
         }
-        float d[3][7];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            cross3(ds[a], n, d[a]);        // d(s x n) = ds x n + s x dn
-            cross3_add(s, dn[a], d[a]);
-            d[a][3] = dn[a][0];
-            d[a][4] = dn[a][1];
-            d[a][5] = dn[a][2];
-            d[a][6] = dot3(dn[a], e) + dot3(n, de[a]);  // d(n . (d - s))
-        }
-        if (C == 3) {  // eps1eps2 cross terms
-            cross3_add(ds[0], dn[1], d[2]);
-            cross3_add(ds[1], dn[0], d[2]);
-            d[2][6] += dot3(dn[0], de[1]) + dot3(dn[1], de[0]);
-        }
-        accumulate_products<C>(acc, r, d[0], d[1], d[2], std::make_integer_sequence<int, 27>());
-    }
-    // ---------------- reduce in double, fixed order: the FP32 per-thread sums go through shared memory; thread (w, e)
-    // widens and adds the 32 lanes of warp w for product e, then the 8 warps are combined.  The reduction buffers
-    // reuse the staging memory.
-    cp_async_wait<0>();
-    __syncthreads();
-    float(*s_t)[27][33] = reinterpret_cast<float(*)[27][33]>(s_raw);                                   // [8][27][33]
-    double(*s_w)[8][27] = reinterpret_cast<double(*)[8][27]>(s_raw + sizeof(float) * 8 * 27 * 33 + 64);  // [3][8][27]
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int e = 0; e < 27; ++e) s_t[warp][e][lane] = acc[a][e];
+        if (nitems & 31) flush();
+        cp_async_wait<0>();
         __syncthreads();
-        if (tid < 216) {
-            const int w = tid / 27, e = tid % 27;
+        // ---------------- the 8 warps in order -> one 81-value partial of this CTA for this group
+        const int first_b = deriv_owner((long long) group * P.chunks, U, B);
+        const int writers = deriv_owner((long long) (group + 1) * P.chunks - 1, U, B) - first_b + 1;
+        double *part = P.dpartials + ((size_t) group * P.max_writers + (blockIdx.x - first_b)) * 81;
+        if (tid < 81) {
+            const int a = tid / 27, e = tid % 27;
             double sum = 0.0;
-#pragma unroll 8
-            for (int l = 0; l < 32; ++l) sum += (double) s_t[w][e][l];
-            s_w[a][w][e] = sum;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sum += s_tot[a * 256 + w * 32 + e];
+            part[tid] = sum;
+        }
+        // ---------------- tail: the last CTA of a direction group to arrive adds the partials of its writers in CTA order
+        // and runs the Gauss-Newton step of its direction(s) from shared memory: no separate finish / solve launches.
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(P.group_ticket + group, 1u) == (unsigned) writers - 1u;
+        __syncthreads();
+        if (!s_last) continue;
+        __threadfence();
+        // warp w adds its contiguous eighth of the writers' partials in order for products lane, lane + 32, lane + 64
+        // (coalesced 648-byte rows, independent L2 loads in flight), then the eight segment sums are added in warp order
+        double(*s_seg)[81] = reinterpret_cast<double(*)[81]>(s_raw);   // [8][81]; the staging area is idle here
+        double *s_sums = reinterpret_cast<double *>(s_raw) + 8 * 81;   // [27 real][81 of this group]
+        {
+            const int seg = (writers + 7) / 8, w0 = warp * seg, w1 = min(writers, w0 + seg);
+            double sum[3] = {0.0, 0.0, 0.0};
+            const double *src = P.dpartials + (size_t) group * P.max_writers * 81 + lane;
+#pragma unroll 4
+            for (int w = w0; w < w1; ++w) {
+                const double *row = src + (size_t) w * 81;
+                sum[0] += __ldcg(row);
+                sum[1] += __ldcg(row + 32);
+                if (lane < 17) sum[2] += __ldcg(row + 64);
+            }
+            s_seg[warp][lane] = sum[0];
+            s_seg[warp][lane + 32] = sum[1];
+            if (lane < 17) s_seg[warp][lane + 64] = sum[2];
         }
         __syncthreads();
-    }
-    if (tid < 81) {
-        const int a = tid / 27, e = tid % 27;
-        double sum = 0.0;
+        if (tid < 81) {
+            double sum = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) sum += s_w[a][w][e];
-        P.dpartials[((size_t) chunk * P.groups + group) * 81 + tid] = sum;
-    }
-    // ---------------- tail: the last CTA of a direction group to arrive sums the per-chunk partials in a fixed order
-    // (warp w adds its contiguous eighth of the chunks in order for products lane, lane + 32, lane + 64 - coalesced
-    // 648-byte rows, independent loads - then the eight segment sums are added in warp order) and runs the
-    // Gauss-Newton step of its direction(s) from shared memory: no separate finish / solve launches.
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(P.group_ticket + group, 1u) == (unsigned) P.chunks - 1u;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    double(*s_seg)[81] = reinterpret_cast<double(*)[81]>(s_raw);               // [8][81]
-    double *s_sums = reinterpret_cast<double *>(s_raw) + 8 * 81;               // [27 real][81 of this group]
-    {
-        const int seg = (P.chunks + 7) / 8, c0 = warp * seg, c1 = min(P.chunks, c0 + seg);
-        double sum[3] = {0.0, 0.0, 0.0};
-        const double *src = P.dpartials + (size_t) group * 81 + lane;
-        const size_t cstride = (size_t) P.groups * 81;
-#pragma unroll 4
-        for (int c = c0; c < c1; ++c) {
-            const double *row = src + (size_t) c * cstride;
-            sum[0] += __ldcg(row);
-            sum[1] += __ldcg(row + 32);
-            if (lane < 17) sum[2] += __ldcg(row + 64);
+            for (int w = 0; w < 8; ++w) sum += s_seg[w][tid];
+            s_sums[27 + tid] = sum;
+            const int comp = comp0 + tid / 27;
+            if (comp < P.ncomp) P.sums[(size_t) (1 + comp) * 27 + tid % 27] = sum;
+        } else if (tid >= 96 && tid < 96 + 27) {
+            s_sums[tid - 96] = __ldcg(P.sums + (tid - 96));  // real sums of icp_assoc_kernel (previous launch)
         }
-        s_seg[warp][lane] = sum[0];
-        s_seg[warp][lane + 32] = sum[1];
-        if (lane < 17) s_seg[warp][lane + 64] = sum[2];
-    }
-    if (tid == 0) P.group_ticket[group] = 0u;
-    __syncthreads();
-    if (tid < 81) {
-        double sum = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) sum += s_seg[w][tid];
-        s_sums[27 + tid] = sum;
-        const int comp = comp0 + tid / 27;
-        if (comp < P.ncomp) P.sums[(size_t) (1 + comp) * 27 + tid % 27] = sum;
-    } else if (tid >= 96 && tid < 96 + 27) {
-        s_sums[tid - 96] = __ldcg(P.sums + (tid - 96));  // real sums of icp_assoc_kernel (previous launch)
-    }
-    if (!S.pose_out) return;
-    __syncthreads();
-    if (tid < (C == 3 ? 1 : 3)) {
-        const int q = C == 3 ? group : group * 3 + tid;
-        if (q < S.dirs) icp_solve_direction<C>(S, q, s_sums, s_sums + 27 + (C == 3 ? 0 : tid * 27));
+        if (tid == 0) P.group_ticket[group] = 0u;
+        __syncthreads();
+        if (S.pose_out && tid < (C == 3 ? 1 : 3)) {
+            const int q = C == 3 ? group : group * 3 + tid;
+            if (q < S.dirs) icp_solve_direction<C>(S, q, s_sums, s_sums + 27 + (C == 3 ? 0 : tid * 27));
+        }
+        __syncthreads();  // s_sums aliases the staging area the next segment copies into
     }
 }
 
@@ -873,13 +908,13 @@ static int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-template <int C, int ST> static int launch_deriv(const IcpParams &P, const SolveParams &S, cudaStream_t s) {
+template <int C, int ST> static int launch_deriv(const IcpParams &P, const SolveParams &S, int grid, cudaStream_t s) {
     static bool smem_set = false;
     if (!smem_set) {
         XS_CUDA(cudaFuncSetAttribute(icp_deriv_kernel<C, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) deriv_smem(ST)));
         smem_set = true;
     }
-    icp_deriv_kernel<C, ST><<<dim3(P.groups, P.chunks), 256, deriv_smem(ST), s>>>(P, S);
+    icp_deriv_kernel<C, ST><<<grid, 256, deriv_smem(ST), s>>>(P, S);
     XS_LAUNCH_CHECK();
     return XS_OK;
 }
@@ -898,19 +933,18 @@ int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, cons
         return XS_ERR_ARG;
     }
     IcpParams P;
-    // derivative pass decomposition: a thread sums at most 32 pixels in FP32 before the double reduction.  Pixels per
-    // thread amortise the per-CTA prologue (pipeline fill), reduction and arrival ticket (~7 us per CTA against ~2 us per
-    // pixel); measured on B200 at 640x480 / 55 directions: 16 -> 0.474 ms, 32 -> 0.454 ms, 64 -> 0.469 ms per launch.
-    // With few direction groups (a rank of an 8-GPU run holds 7) the grid would not fill the 296 CTA slots, so pixels
-    // per thread are halved until it does (7 groups, level 0: 32 -> 90 us, 16 -> 93 us but shorter coarse levels, 8 ->
-    // 103 us, 4 -> 123 us per launch; whole ICP stage 1.16 / 1.06 / 1.14 / 1.19 ms).
+    // derivative pass decomposition (icp_deriv_kernel): pixel units of 256 * ppt pixels, (group, unit) items cut into equal
+    // contiguous ranges for min(296, items) persistent CTAs; ppt shrinks until there are at least as many items as CTA slots
     P.groups = (ncomp + 2) / 3;
     static const int ppt_env = env_int("XS_ICP_PPT", 0), stages_env = env_int("XS_ICP_STAGES", 0);
-    P.ppt = 32;
+    P.ppt = 4;
     while (P.ppt > 1 && (long long) div_up(npix, 256 * P.ppt) * P.groups < 296) P.ppt >>= 1;
     if (ppt_env > 0) P.ppt = ppt_env < 32 ? ppt_env : 32;
     P.chunks = div_up(npix, 256 * P.ppt);
-    int rc = icp_reserve(ncomp, npix, (size_t) P.chunks * P.groups * 81, P.groups);
+    const long long items = (long long) P.groups * P.chunks;
+    const int deriv_grid = (int) (items < 296 ? items : 296);
+    P.max_writers = ncomp > 0 ? (int) (P.chunks / (items / deriv_grid)) + 2 : 0;
+    int rc = icp_reserve(ncomp, npix, (size_t) P.groups * P.max_writers * 81, P.groups);
     if (rc != XS_OK) return rc;
     // only the current pose's derivative components enter the rows (s = Rcurr*v + tcurr); the previous pose is used
     // for the real projection only (ICP.cu:206-217 takes real parts)
@@ -963,9 +997,9 @@ int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, cons
         // 55 directions: the deeper pipeline costs L1 capacity and does not raise issue utilisation); XS_ICP_STAGES=3 selects it
         const int stages = stages_env == 3 ? 3 : 2;
         if (comps == 1)
-            rc = stages == 2 ? launch_deriv<1, 2>(P, S, s) : launch_deriv<1, DERIV_MAX_STAGES>(P, S, s);
+            rc = stages == 2 ? launch_deriv<1, 2>(P, S, deriv_grid, s) : launch_deriv<1, DERIV_MAX_STAGES>(P, S, deriv_grid, s);
         else
-            rc = stages == 2 ? launch_deriv<3, 2>(P, S, s) : launch_deriv<3, DERIV_MAX_STAGES>(P, S, s);
+            rc = stages == 2 ? launch_deriv<3, 2>(P, S, deriv_grid, s) : launch_deriv<3, DERIV_MAX_STAGES>(P, S, deriv_grid, s);
         if (rc != XS_OK) return rc;
         if (slot >= 0) {
             XS_CUDA(cudaEventRecord(g_icp.ev1[slot], s));
