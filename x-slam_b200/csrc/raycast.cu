@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) raycast_march_kernel(const RaycastParams 
 
 // ---- pass 2: hit evaluation with the real path evaluated ONCE per pixel.
 //
-// A CTA owns 32 consecutive pixels of one image row.  Warp 0 evaluates the real hit (RayCaster.cu:249-305) with the
+// A CTA owns HIT_PG groups of 32 consecutive pixels of one image row.  One warp per group evaluates the real hit (RayCaster.cu:249-305) with the
 // reference-faithful arithmetic above and leaves, per pixel and per trilinear sample (2 for the crossing, 6 for the
 // normal), a small context in shared memory: packed per-axis corner offsets, the weights (a, b, c), the gradient G and
 // mixed second partials H of the trilinear interpolant with respect to (a, b, c), and its value.  Then the 8 warps
@@ -337,21 +337,25 @@ XS_DEV Jet<C, 1> sample_deriv(const VolumeView &V, const float *__restrict__ dq 
     return r;
 }
 
-template <int C> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS) raycast_hit_kernel(const RaycastParams P, const float *__restrict__ hit_time) {
-    __shared__ float s_ctx[HIT_CTX_WORDS * HIT_PX];
+// HIT_PG pixel groups of 32 pixels per CTA: the real phases (A: one warp per group, B: one warp per (group, normal
+// sample), C: one warp per group) fill the 8 warps four times better than with a single group, and the derivative loop
+// runs over (direction, group) tasks.
+constexpr int HIT_PG = 4;
+template <int C> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS, 2) raycast_hit_kernel(const RaycastParams P, const float *__restrict__ hit_time) {
+    extern __shared__ float s_ctx[];  // [HIT_PG][HIT_CTX_WORDS][HIT_PX]
     typedef Jet<C, 1> J;
     const int lane = threadIdx.x, warp = threadIdx.y;
-    const int x = lane + blockIdx.x * HIT_PX;
     const int y = blockIdx.y;
-    const bool inside = x < P.cols;
-    float *ctx = s_ctx + lane;
-    float *xctx = ctx + 8 * S_FIELDS * HIT_PX;
     const float qnan = __int_as_float(0x7fffffff);
-    unsigned flags_a = 0u;
-    if (warp == 0) {
+    auto ctx_of = [&](int pg) { return s_ctx + (size_t) pg * HIT_CTX_WORDS * HIT_PX + lane; };
+    auto x_of = [&](int pg) { return lane + (blockIdx.x * HIT_PG + pg) * HIT_PX; };
+    unsigned flags_a = 0u;  // of the group this warp owns in phases A and C (warp < HIT_PG)
+    if (warp < HIT_PG) {
+        float *ctx = ctx_of(warp), *xctx = ctx + 8 * S_FIELDS * HIT_PX;
+        const int x = x_of(warp);
         float t0 = -1.f;
         xctx[X_OK * HIT_PX] = 1.f;
-        if (inside) {
+        if (x < P.cols) {
             t0 = hit_time[(size_t) y * P.cols + x];
             float vw[3];
             if (t0 >= 0.f) flags_a = hit_phase_a(P, x, y, t0, ctx, xctx, vw);
@@ -364,10 +368,16 @@ template <int C> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS) raycast_hi
         xctx[X_T0 * HIT_PX] = t0;
     }
     __syncthreads();
-    if (warp >= 2 && (__float_as_uint(xctx[X_FLAGS * HIT_PX]) & 4u)) hit_phase_b(P, warp, ctx, xctx);
+    for (int task = warp; task < 6 * HIT_PG; task += HIT_WARPS) {
+        const int pg = task / 6, sample = 2 + task % 6;
+        float *ctx = ctx_of(pg), *xctx = ctx + 8 * S_FIELDS * HIT_PX;
+        if (__float_as_uint(xctx[X_FLAGS * HIT_PX]) & 4u) hit_phase_b(P, sample, ctx, xctx);
+    }
     __syncthreads();
-    if (warp == 0) {
-        if (inside) {
+    if (warp < HIT_PG) {
+        float *ctx = ctx_of(warp), *xctx = ctx + 8 * S_FIELDS * HIT_PX;
+        const int x = x_of(warp);
+        if (x < P.cols) {
             float ng[3];
             bool n_ok = false;
             if ((flags_a & 4u) && xctx[X_OK * HIT_PX] != 0.f) n_ok = hit_phase_c(P, ctx, ng);
@@ -379,13 +389,18 @@ template <int C> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS) raycast_hi
         }
     }
     __syncthreads();
-    if (!inside || P.dirs == 0) return;
-    const unsigned flags = __float_as_uint(xctx[X_FLAGS * HIT_PX]);
-    const float t0 = xctx[X_T0 * HIT_PX];
+    if (P.dirs == 0) return;
     const VolumeView &V = P.V;
     const float inv_vs = __fdividef(1.f, V.voxel);
-    const float nx = (float(x) - P.intr.cx) * __fdividef(1.f, P.intr.fx), ny = (float(y) - P.intr.cy) * __fdividef(1.f, P.intr.fy);
-    for (int q = warp; q < P.dirs; q += HIT_WARPS) {
+    const float ny = (float(y) - P.intr.cy) * __fdividef(1.f, P.intr.fy);
+    for (int task = warp; task < P.dirs * HIT_PG; task += HIT_WARPS) {
+        const int q = task / HIT_PG, pg = task % HIT_PG;
+        const int x = x_of(pg);
+        if (x >= P.cols) continue;
+        const float *ctx = ctx_of(pg), *xctx = ctx + 8 * S_FIELDS * HIT_PX;
+        const unsigned flags = __float_as_uint(xctx[X_FLAGS * HIT_PX]);
+        const float t0 = xctx[X_T0 * HIT_PX];
+        const float nx = (float(x) - P.intr.cx) * __fdividef(1.f, P.intr.fx);
         Jet3<C, 1> vw, ng;
         if (flags & 1u) {
             // ray: start = t, dir = normalized(R * next)  (RayCaster.cu:56-62,207-213)
@@ -561,11 +576,18 @@ int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_po
     dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
     raycast_march_kernel<<<grd, blk, 0, s>>>(P, v->d_hit_time);
     XS_LAUNCH_CHECK();
-    dim3 g2(div_up(cols, HIT_PX), rows), b2(HIT_PX, HIT_WARPS);
+    dim3 g2(div_up(cols, HIT_PX * HIT_PG), rows), b2(HIT_PX, HIT_WARPS);
+    const size_t hit_smem = (size_t) HIT_PG * HIT_CTX_WORDS * HIT_PX * sizeof(float);
+    static bool hit_smem_set = false;
+    if (!hit_smem_set) {
+        XS_CUDA(cudaFuncSetAttribute(raycast_hit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hit_smem));
+        XS_CUDA(cudaFuncSetAttribute(raycast_hit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hit_smem));
+        hit_smem_set = true;
+    }
     if (v->comps == 1)
-        raycast_hit_kernel<1><<<g2, b2, 0, s>>>(P, v->d_hit_time);
+        raycast_hit_kernel<1><<<g2, b2, hit_smem, s>>>(P, v->d_hit_time);
     else
-        raycast_hit_kernel<3><<<g2, b2, 0, s>>>(P, v->d_hit_time);
+        raycast_hit_kernel<3><<<g2, b2, hit_smem, s>>>(P, v->d_hit_time);
     XS_LAUNCH_CHECK();
     return XS_OK;  // raycast does not sync, RayCaster.cu:367
 }
