@@ -117,6 +117,11 @@ int xs_volume_import_planes(xs_volume *v, int comp, const float *d_value, const 
 int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, xs_intr intr,
                  int max_weight, const xs_pose *v2c, float bilinear_threshold, unsigned long long *stats_host,
                  void *stream);
+/* Frame-loop mode: with pipelined != 0, xs_integrate and xs_raycast only queue work (no host synchronisation, separate pose
+ * staging slots); the caller synchronises the stream once per frame and then calls xs_volume_finish_frame to collect the
+ * integration statistics / kernel time.  Off by default (the seam-level calls synchronise like the reference's). */
+int xs_volume_set_pipelined(xs_volume *v, int on);
+int xs_volume_finish_frame(xs_volume *v, unsigned long long *stats_host4);
 /* raycast, RayCaster.h:21-25 / RayCaster.cu:327.  c2v = (Rc2v, tc2v), v2w = (Rv2w, tv2w).
  * outputs: [(1+ncomp)][3][rows][cols] world-frame vertex / normal maps. */
 int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_pose *v2w, int rows, int cols,

@@ -62,6 +62,8 @@ SYMBOLS = {
     "xs_volume_export_planes": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "xs_volume_import_planes": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "xs_integrate": (_i, [_vp, _vp, _sz, _i, _i, Intr, _i, _PP, _f, _pull, _vp]),
+    "xs_volume_set_pipelined": (_i, [_vp, _i]),
+    "xs_volume_finish_frame": (_i, [_vp, _pull]),
     "xs_raycast": (_i, [_vp, Intr, _PP, _PP, _i, _i, _vp, _vp, _vp]),
     "xs_tsdf_hessian": (_i, [_vp, _sz, _i, _i, Intr, _pi, _f, _PP, _f, _vp, _pd, _vp]),
     "xs_tsdf_loss": (_i, [_vp, _sz, _i, _i, Intr, _pi, _f, _pf, _pf, _f, _vp, _pd, _vp]),

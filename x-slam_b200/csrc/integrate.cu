@@ -333,7 +333,8 @@ xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_rang
     if (e == cudaSuccess) e = cudaMalloc(&V.weight, nvox * sizeof(int));
     V.deriv = nullptr;
     if (e == cudaSuccess && V.ncomp) e = cudaMalloc(&V.deriv, nvox * sizeof(float) * V.ncomp);
-    size_t pose_floats = (size_t) (V.ncomp > 0 ? V.ncomp : 1) * 12 * 2;
+    size_t pose_floats = (size_t) (V.ncomp > 0 ? V.ncomp : 1) * 12 * 3;
+    v->pipelined = false;
     if (e == cudaSuccess) e = cudaMalloc(&v->d_dpose, pose_floats * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost(&v->h_dpose, pose_floats * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&v->d_stats, 4 * sizeof(unsigned long long));
@@ -438,6 +439,8 @@ int upload_pose_derivs(const xs_volume *v, const xs_pose *p, int slot, cudaStrea
 }
 }  // namespace xs
 
+extern "C" int xs_volume_finish_frame(xs_volume *v, unsigned long long *stats_host);
+
 extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols,
                             xs_intr intr, int max_weight, const xs_pose *v2c, float bilinear_threshold,
                             unsigned long long *stats_host, void *stream) {
@@ -448,9 +451,10 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
         XS_CUDA(cudaMalloc(&v->d_depth_m, (size_t) rows * cols * sizeof(float)));
         v->depth_capacity = rows * cols;
     }
-    // the staging buffer is reused by the next call: make sure the previous consumer is done
-    XS_CUDA(cudaStreamSynchronize(s));
-    int rc = upload_pose_derivs(v, v2c, 0, s);
+    // the staging buffer is reused by the next call: make sure the previous consumer is done.  In the frame loop (pipelined)
+    // the caller synchronises once per frame and integration has a staging slot of its own, so nothing waits here.
+    if (!v->pipelined) XS_CUDA(cudaStreamSynchronize(s));
+    int rc = upload_pose_derivs(v, v2c, 2, s);
     if (rc != XS_OK) return rc;
     dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
     scale_depth_kernel<<<grd, blk, 0, s>>>(d_depth, depth_step_bytes, rows, cols, v->d_depth_m);
@@ -460,7 +464,7 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
     P.V = v->view;
     for (int i = 0; i < 9; ++i) P.v2c.R[i] = v2c->R[i];
     for (int i = 0; i < 3; ++i) P.v2c.t[i] = v2c->t[i];
-    P.dpose = v->d_dpose;
+    P.dpose = v->d_dpose + (size_t) 2 * v->view.ncomp * 12;
     P.depth = v->d_depth_m;
     P.rows = rows;
     P.cols = cols;
@@ -487,9 +491,22 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
     XS_LAUNCH_CHECK();
     XS_CUDA(cudaEventRecord(v->ev_k1, s));
     XS_CUDA(cudaMemcpyAsync(v->h_stats, v->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    if (v->pipelined) return XS_OK;     // the frame loop queues the raycast behind this without a host round trip
     XS_CUDA(cudaStreamSynchronize(s));  // integrateTsdfVolume syncs, TsdfFusion.cu:200
+    return xs_volume_finish_frame(v, stats_host);
+}
+
+// After the stream has been synchronised: statistics and kernel time of the last integration.
+extern "C" int xs_volume_finish_frame(xs_volume *v, unsigned long long *stats_host) {
+    if (!v) return XS_ERR_ARG;
     if (stats_host)
         for (int i = 0; i < 4; ++i) stats_host[i] = v->h_stats[i];
     cudaEventElapsedTime(&v->last_kernel_ms, v->ev_k0, v->ev_k1);
+    return XS_OK;
+}
+
+extern "C" int xs_volume_set_pipelined(xs_volume *v, int on) {
+    if (!v) return XS_ERR_ARG;
+    v->pipelined = on != 0;
     return XS_OK;
 }

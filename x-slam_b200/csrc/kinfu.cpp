@@ -400,11 +400,18 @@ int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_devi
         fprintf(stderr, "Frame align failed!\n");
         return 0;
     }
-    if (xs_kinfu_integrate_frame(k, d_depth) != XS_OK) return 0;
+    // integration and raycast are queued back to back (no host round trip between them): their only host input is the pose
+    xs_volume_set_pipelined(k->volume, 1);
+    const int rc_int = xs_kinfu_integrate_frame(k, d_depth);
     cudaEventRecord(k->ev[3], k->stream);
     k->launches[2] = g_launches - l0;
     l0 = g_launches;
-    if (xs_kinfu_calculate_point_cloud(k) != XS_OK) return 0;
+    const int rc_ray = rc_int == XS_OK ? xs_kinfu_calculate_point_cloud(k) : rc_int;
+    xs_volume_set_pipelined(k->volume, 0);
+    if (rc_int != XS_OK || rc_ray != XS_OK) {
+        cudaStreamSynchronize(k->stream);
+        return 0;
+    }
     // per-frame derivative record for the multi-GPU gather
     for (int q = 0; q <= k->ncomp; ++q)
         for (int i = 0; i < 4; ++i)
@@ -417,6 +424,7 @@ int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_devi
         set_error("xs_kinfu_process_frame: stream synchronize failed");
         return 0;
     }
+    xs_volume_finish_frame(k->volume, k->stats);
     for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&k->ms[i], k->ev[i], k->ev[i + 1]);
     cudaEventElapsedTime(&k->ms[4], k->ev[0], k->ev[4]);
     k->launches[4] = k->launches[0] + k->launches[1] + k->launches[2] + k->launches[3];

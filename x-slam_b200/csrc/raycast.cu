@@ -542,7 +542,7 @@ int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_po
         return XS_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t) stream;
-    XS_CUDA(cudaStreamSynchronize(s));  // staging buffer reuse
+    if (!v->pipelined) XS_CUDA(cudaStreamSynchronize(s));  // staging buffer reuse (the frame loop synchronises once per frame)
     int rc = upload_pose_derivs(v, c2v, 0, s);
     if (rc != XS_OK) return rc;
     rc = upload_pose_derivs(v, v2w, 1, s);

@@ -64,7 +64,8 @@ XS_DEV size_t deriv_index(const VolumeView &V, int x, int y, int z, int comp) {
 struct xs_volume {
     xs::VolumeView view;
     int comps, dirs;
-    float *d_dpose;      // staging for pose derivative components [ncomp][12] (x2: c2v, v2w for raycast)
+    float *d_dpose;      // staging for pose derivative components [3][ncomp][12]: slots 0, 1 = c2v, v2w (raycast), 2 = v2c (integration)
+    bool pipelined;      // frame-loop mode: xs_integrate / xs_raycast do not synchronise (xs_volume_finish_frame collects stats)
     float *h_dpose;      // pinned host mirror
     float *d_depth_m;    // scaled depth (metres), TsdfFusion.cu:68-82
     int depth_capacity;  // pixels
