@@ -108,14 +108,14 @@ template <int C> __device__ __noinline__ void icp_solve_direction(const SolvePar
 // search_newton (ICP.cu:196-244) on real parts with the reference's rounding sequence: projection of the current
 // vertex into the previous frame, bounds / NaN / distance / angle gates.  Outputs vcurr, vcurr_g and the matched pixel.
 XS_DEV bool search_newton_real(const IcpParams &P, const float *s_curr, int x, int y, size_t plane, float &vcx, float &vcy,
-                               float &vcz, float &gx, float &gy, float &gz, int &ux, int &uy) {
+                               float &vcz, float &gx, float &gy, float &gz, int &ux, int &uy, float (&nprev)[3], float (&vprev)[3]) {
     const size_t pix = (size_t) y * P.cols + x;
-    const float ncx = P.nmap_curr[pix];
-    if (isnan(ncx)) return false;
-    const float ncy = P.nmap_curr[pix + plane], ncz = P.nmap_curr[pix + 2 * plane];
+    // the six current-frame values in one round trip (the reference tests the NaN first; the loads are valid either way)
+    const float ncx = P.nmap_curr[pix], ncy = P.nmap_curr[pix + plane], ncz = P.nmap_curr[pix + 2 * plane];
     vcx = P.vmap_curr[pix];
     vcy = P.vmap_curr[pix + plane];
     vcz = P.vmap_curr[pix + 2 * plane];
+    if (isnan(ncx)) return false;
     const float *R = s_curr, *t = s_curr + 9, *Q = P.prev.R, *tp = P.prev.t;
     // vcurr_g = Rcurr * vcurr + tcurr
     gx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(R[0], vcx), __fmul_rn(R[1], vcy)), __fmul_rn(R[2], vcz)), t[0]);
@@ -130,10 +130,12 @@ XS_DEV bool search_newton_real(const IcpParams &P, const float *s_curr, int x, i
     uy = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(py, P.intr.fy), pz), P.intr.cy));
     if (ux < 0 || uy < 0 || ux >= P.cols || uy >= P.rows || pz < 0) return false;
     const size_t q = (size_t) uy * P.cols + ux;
-    const float npx = P.nmap_prev[q];
-    if (isnan(npx)) return false;
-    const float npy = P.nmap_prev[q + plane], npz = P.nmap_prev[q + 2 * plane];
+    // the six matched values in one round trip
+    const float npx = P.nmap_prev[q], npy = P.nmap_prev[q + plane], npz = P.nmap_prev[q + 2 * plane];
     const float vpx = P.vmap_prev[q], vpy = P.vmap_prev[q + plane], vpz = P.vmap_prev[q + 2 * plane];
+    if (isnan(npx)) return false;
+    nprev[0] = npx, nprev[1] = npy, nprev[2] = npz;
+    vprev[0] = vpx, vprev[1] = vpy, vprev[2] = vpz;
     // dist = norm(vprev_g - vcurr_g)
     const float ddx = __fsub_rn(vpx, gx), ddy = __fsub_rn(vpy, gy), ddz = __fsub_rn(vpz, gz);
     const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz)));
@@ -174,14 +176,13 @@ __global__ void __launch_bounds__(256) icp_assoc_kernel(const IcpParams P) {
         float gx = 0, gy = 0, gz = 0;     // vcurr_g
         int ux = 0, uy = 0;
         const bool inside = x < P.cols && y < P.rows;
-        const bool found = inside && search_newton_real(P, s_curr, x, y, plane, vcx, vcy, vcz, gx, gy, gz, ux, uy);
+        float np_[3], vp_[3];
+        const bool found = inside && search_newton_real(P, s_curr, x, y, plane, vcx, vcy, vcz, gx, gy, gz, ux, uy, np_, vp_);
         // ---------------- the real row, ICP.cu:254-260: s = vcurr_g, n = nprev_g, d = vprev_g
         float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (found) {
-            const size_t q = (size_t) uy * P.cols + ux;
-            const float nx = P.nmap_prev[q], ny = P.nmap_prev[q + plane], nz = P.nmap_prev[q + 2 * plane];
-            const float ex = __fsub_rn(P.vmap_prev[q], gx), ey = __fsub_rn(P.vmap_prev[q + plane], gy),
-                        ez = __fsub_rn(P.vmap_prev[q + 2 * plane], gz);
+            const float nx = np_[0], ny = np_[1], nz = np_[2];
+            const float ex = __fsub_rn(vp_[0], gx), ey = __fsub_rn(vp_[1], gy), ez = __fsub_rn(vp_[2], gz);
             row[0] = __fsub_rn(__fmul_rn(gy, nz), __fmul_rn(gz, ny));
             row[1] = __fsub_rn(__fmul_rn(gz, nx), __fmul_rn(gx, nz));
             row[2] = __fsub_rn(__fmul_rn(gx, ny), __fmul_rn(gy, nx));
@@ -1055,13 +1056,12 @@ __global__ void __launch_bounds__(256) icp_optimize_matrix_kernel(const IcpParam
         const int y = (tile / P.tiles_x) * 8 + threadIdx.y;
         float vcx, vcy, vcz, gx, gy, gz;
         int ux, uy;
-        if (!(x < P.cols && y < P.rows && search_newton_real(P, s_curr, x, y, plane, vcx, vcy, vcz, gx, gy, gz, ux, uy))) continue;
+        float n1[3], p1[3];
+        if (!(x < P.cols && y < P.rows && search_newton_real(P, s_curr, x, y, plane, vcx, vcy, vcz, gx, gy, gz, ux, uy, n1, p1))) continue;
         ++cnt;
-        const size_t q = (size_t) uy * P.cols + ux;
-        const float n1[3] = {P.nmap_prev[q], P.nmap_prev[q + plane], P.nmap_prev[q + 2 * plane]};
         const float p0[4] = {vcx, vcy, vcz, 1.f};
         // proj_norm = (p0_trans - p1) . n1, ICP.cu:312-314
-        const float proj = (gx - P.vmap_prev[q]) * n1[0] + (gy - P.vmap_prev[q + plane]) * n1[1] + (gz - P.vmap_prev[q + 2 * plane]) * n1[2];
+        const float proj = (gx - p1[0]) * n1[0] + (gy - p1[1]) * n1[1] + (gz - p1[2]) * n1[2];
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
