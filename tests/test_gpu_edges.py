@@ -132,3 +132,33 @@ def test_unsupported_shapes_fail_loudly(xs):
     with pytest.raises(ValueError):
         k.SetYamlParameters(_cfg(xs))
         k.ProcessFrame(np.zeros((479, 640), np.uint16))
+
+
+def test_maximum_volume_1024(xs, refcuda):
+    """BASELINE.json configs[4] resolution: a 1024^3 volume (0.0075 m voxels, 4 GiB per plane, derivative-plane offsets beyond
+    2^31 elements) with one first-order direction.  One fused frame: the weight plane and the raycast validity masks must equal
+    the reference kernels' bit for bit, the values to 1e-6."""
+    import torch
+    cfg = _cfg(xs, res=(1024, 1024, 1024), voxel=0.0075)
+    seed = xs.pose_seeds_csfd()[1:2]
+    k = xs.KinectFusionReconstruction()
+    k.SetYamlParameters(cfg, comps=1, seeds=seed)
+    r = refcuda.kinfu(cfg, None)
+    d = xs.synth_depth(0)
+    assert k.ProcessFrame(d) == 1 and r.process_frame(d) == 1
+    v, w, g = k.volume_planes(0)
+    rv, rw, _ = r.volume()
+    rw_t = torch.from_numpy(rw).cuda()
+    assert int((rw_t > 0).sum()) > 10_000_000
+    assert bool(torch.equal(w, rw_t)), "updated-voxel sets differ at 1024^3"
+    del rw_t
+    rv_t = torch.from_numpy(rv).cuda()
+    assert float((v - rv_t).abs().max()) <= 1e-6
+    assert float(g.abs().max()) > 0  # the seeded direction reached the derivative plane
+    del rv_t, v, w, g
+    for which in ("vmap_g_prev", "nmap_g_prev"):
+        m = k.map(which, 0).cpu().numpy()
+        rm = r.map(which, 0)
+        valid = ~np.isnan(rm[0, ..., 0])
+        assert valid.sum() > 200000 and np.array_equal(np.isnan(m[0, 0]), ~valid)
+        assert max(rel_err(m[0, p][valid], rm[p, ..., 0][valid]) for p in range(3)) <= 1e-6
