@@ -132,6 +132,12 @@ int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_po
 int xs_tsdf_hessian(const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, xs_intr intr,
                     const int res[3], float voxel_size, const xs_pose *v2c, float trunc, const float *d_gt,
                     double *out4_host, void *stream);
+/* The same loss for dirs bicomplex directions in one call (BASELINE.json configs[4]: derivatives w.r.t. a multi-frame pose
+ * set): v2c carries ncomp = 3 * dirs components; the ground-truth volume is streamed once per 8 directions instead of once per
+ * direction.  out_host: double[dirs][4]; every row is bit-identical to an xs_tsdf_hessian call with that direction. */
+int xs_tsdf_hessian_batch(const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, xs_intr intr,
+                          const int res[3], float voxel_size, const xs_pose *v2c, float trunc, const float *d_gt,
+                          double *out_host, void *stream);
 /* ComputeLocalTsdf_loss, TsdfFusion.h:48-52 / TsdfFusion.cu:409 (real-only twin of the DCSFD volume loss, used with
  * se3Exp-parameterised pose sets in relocalisation-style optimisation): (Rv2c row-major, tv2c) are plain floats.
  * out2 = {sum loss, count} (host). */

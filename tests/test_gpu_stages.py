@@ -381,3 +381,51 @@ def test_real_volume_loss_parity(xs, refcuda, torch_mod, out_dir):
         assert abs(mine[0] - ref[0]) <= 1e-5 * abs(ref[0])
         assert abs(mine[1] - orc[1]) <= 1e-3 * ref[1] and abs(mine[0] - orc[0]) <= 1e-3 * abs(ref[0])
     _report(out_dir, "tsdf_loss", **stats)
+
+
+def test_dcsfd_volume_loss_batch(xs, refcuda, torch_mod, out_dir):
+    """xs_tsdf_hessian_batch (configs[4] consumer): 11 bicomplex directions in one call (sweeps of 8 + 2 + 1) must reproduce 11
+    single-direction calls bit for bit, and one of them the reference kernel within the a12 tolerances."""
+    torch = torch_mod
+    import time
+    from xslam_b200 import ops
+    res, voxel, dirs = 128, 0.06, 11
+    vol, ref_state, _, _ = _integrate_both(xs, refcuda, torch, [0], res, voxel, 1, 7)
+    gt = ref_state[0][0]
+    gt_d = torch.from_numpy(gt).cuda()
+    depth = xs.synth_depth(3)
+    d_d = _dev_u16(torch, depth)
+    v2c, _, _ = poses_for_frame(xs, 3)
+    R, t = v2c[:3, :3].astype(np.float32), v2c[:3, 3].astype(np.float32)
+    rng = np.random.default_rng(12)
+    h = 1e-6
+    dR = np.zeros((3 * dirs, 9), np.float32)
+    dt = np.zeros((3 * dirs, 3), np.float32)
+    for q in range(dirs):
+        for a, sc in enumerate((h, h, h * h)):
+            r_, t_ = rand_dpose(rng, 1, sc)
+            dR[3 * q + a], dt[3 * q + a] = r_[0], t_[0]
+    trunc = vol.getTsdfTruncDist()
+    batch = ops.ComputeLocalTsdf_hessian_batch(d_d, xs.Intr(**ICL), (res,) * 3, voxel, ops.PoseBatch(R, t, dR, dt), trunc, gt_d)
+    singles = np.array([ops.ComputeLocalTsdf_hessian(d_d, xs.Intr(**ICL), (res,) * 3, voxel,
+                                                     ops.PoseBatch(R, t, dR[3 * q:3 * q + 3], dt[3 * q:3 * q + 3]), trunc, gt_d)
+                        for q in range(dirs)])
+    assert batch.shape == (dirs, 4) and np.array_equal(batch, singles), "batched sums differ from single-direction sums"
+    q = 9
+    R4 = np.stack([R.reshape(9), dR[3 * q], dR[3 * q + 1], dR[3 * q + 2]], -1)
+    t4 = np.stack([t, dt[3 * q], dt[3 * q + 1], dt[3 * q + 2]], -1)
+    ref, _ = refcuda.tsdf_hessian(depth, (ICL["fx"], ICL["fy"], ICL["cx"], ICL["cy"]), (res,) * 3, voxel, R4, t4, trunc, gt)
+    rel = [abs(batch[q, i] - ref[i]) / max(abs(float(ref[i])), 1e-30) for i in range(4)]
+    assert batch[q, 3] == ref[3] and rel[0] <= 1e-5 and rel[1] <= 1e-4 and rel[2] <= 1e-3, rel
+    # one sweep per 8 directions: time against 11 separate sweeps on a 512^3 ground truth (bound by the volume stream)
+    big = torch.zeros((512,) * 3, dtype=torch.float32, device="cuda")
+    big[192:320, 192:320, 192:320] = gt_d
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ops.ComputeLocalTsdf_hessian_batch(d_d, xs.Intr(**ICL), (512,) * 3, voxel / 4, ops.PoseBatch(R, t, dR, dt), trunc, big)
+    t1 = time.perf_counter()
+    for qq in range(dirs):
+        ops.ComputeLocalTsdf_hessian(d_d, xs.Intr(**ICL), (512,) * 3, voxel / 4, ops.PoseBatch(R, t, dR[3 * qq:3 * qq + 3], dt[3 * qq:3 * qq + 3]),
+                                     trunc, big)
+    t2 = time.perf_counter()
+    _report(out_dir, "tsdf_hessian_batch", rel_vs_ref=rel, batch_ms=(t1 - t0) * 1e3, singles_ms=(t2 - t1) * 1e3, dirs=dirs)

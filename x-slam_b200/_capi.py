@@ -66,6 +66,7 @@ SYMBOLS = {
     "xs_volume_finish_frame": (_i, [_vp, _pull]),
     "xs_raycast": (_i, [_vp, Intr, _PP, _PP, _i, _i, _vp, _vp, _vp]),
     "xs_tsdf_hessian": (_i, [_vp, _sz, _i, _i, Intr, _pi, _f, _PP, _f, _vp, _pd, _vp]),
+    "xs_tsdf_hessian_batch": (_i, [_vp, _sz, _i, _i, Intr, _pi, _f, _PP, _f, _vp, _pd, _vp]),
     "xs_tsdf_loss": (_i, [_vp, _sz, _i, _i, Intr, _pi, _f, _pf, _pf, _f, _vp, _pd, _vp]),
     "xs_extract_points": (_l, [_vp, _vp, _vp, _l, _vp]),
     "xs_estimate_combined": (_i, [_PP, _vp, _vp, _PP, Intr, _vp, _vp, _i, _i, _i, _i, _f, _f, _pd, _pd, _vp]),

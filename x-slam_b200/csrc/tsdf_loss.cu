@@ -10,6 +10,8 @@
 // block reduces in double with warp shuffles and the last block combines the partials in block order.
 #include "xs_common.cuh"
 
+#include <vector>
+
 namespace xs {
 
 struct Cx {
@@ -102,9 +104,22 @@ template <int N> XS_DEV void block_reduce_to_out(const double (&acc)[N], double 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // fixed order: warp w adds its contiguous eighth of the blocks (lane = value, independent L2 loads), then the 8 warps in order
+    static_assert(N <= 32, "one lane per value");
+    __shared__ double s_seg[8][N];
+    {
+        const int nb = (int) gridDim.x, seg = (nb + 7) / 8, b0 = warp * seg, b1 = min(nb, b0 + seg);
+        double v = 0;
+        if (lane < N) {
+#pragma unroll 8
+            for (int b = b0; b < b1; ++b) v += __ldcg(partials + (size_t) b * N + lane);
+            s_seg[warp][lane] = v;
+        }
+    }
+    __syncthreads();
     if (threadIdx.x < N) {
         double v = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partials + (size_t) b * N + threadIdx.x);
+        for (int w = 0; w < 8; ++w) v += s_seg[w][threadIdx.x];
         out[threadIdx.x] = v;
     }
     if (threadIdx.x == 0) *ticket = 0u;
@@ -123,6 +138,42 @@ struct LossParams {
     unsigned int *ticket;
 };
 
+// One voxel of ComputeLocalTsdfHessianKernel (TsdfFusion.cu:214-281) for the bicomplex pose (R, t); false where the
+// reference `continue`s.
+XS_DEV bool hessian_voxel(const LossParams &P, const BiC *R, const BiC *t, float gt, size_t index, float trunc_inv, BiC &loss) {
+    const int x = (int) (index % P.rx), y = (int) ((index / P.rx) % P.ry), z = (int) (index / ((size_t) P.rx * P.ry));
+    const BiC3 vg = {bic((float(x) + 0.5f) * P.voxel), bic((float(y) + 0.5f) * P.voxel), bic((float(z) + 0.5f) * P.voxel)};
+    const BiC3 r0 = {R[0], R[1], R[2]}, r1 = {R[3], R[4], R[5]}, r2 = {R[6], R[7], R[8]};
+    const BiC3 vc = {bdot(r0, vg) + t[0], bdot(r1, vg) + t[1], bdot(r2, vg) + t[2]};
+    const BiC inv_z = bic(1.0f) / vc.z;
+    if (inv_z.re.re < 0) return false;
+    const BiC image_x = vc.x * inv_z * P.intr.fx + P.intr.cx;  // :232-233
+    const BiC image_y = vc.y * inv_z * P.intr.fy + P.intr.cy;
+    const int coox = __float2int_rd(image_x.re.re - 0.5f), cooy = __float2int_rd(image_y.re.re - 0.5f);
+    if (!(coox > 1 && cooy > 1 && coox < P.cols - 1 && cooy < P.rows - 1)) return false;
+    const int nx = __float2int_rn(image_x.re.re), ny = __float2int_rn(image_y.re.re);
+    const float d00 = __ldg(P.depth + (size_t) cooy * P.cols + coox), d10 = __ldg(P.depth + (size_t) cooy * P.cols + coox + 1);
+    const float d01 = __ldg(P.depth + (size_t) (cooy + 1) * P.cols + coox),
+                d11 = __ldg(P.depth + (size_t) (cooy + 1) * P.cols + coox + 1);
+    BiC Dp;
+    if (d00 != 0.0f && d01 != 0.0f && d10 != 0.0f && d11 != 0.0f) {  // :248-256 (no threshold test)
+        const BiC one = bic(1.0f);
+        const BiC a = image_x - bic(float(coox) + 0.5f), b = image_y - bic(float(cooy) + 0.5f);
+        Dp = bic(d00) * (one - a) * (one - b) + bic(d10) * a * (one - b) + bic(d01) * (one - a) * b + bic(d11) * a * b;
+    } else {
+        Dp = bic(__ldg(P.depth + (size_t) ny * P.cols + nx));
+    }
+    if (Dp.re.re > 5 || Dp.re.re < 0.2) return false;  // :260 (compared in double, as the literals are)
+    const BiC xl = (image_x - P.intr.cx) / P.intr.fx, yl = (image_y - P.intr.cy) / P.intr.fy;
+    const BiC3 v1 = {Dp * xl, Dp * yl, Dp};
+    const BiC distance = bnorm(v1) - bnorm(vc);
+    const BiC gt_distance = bic(gt) * P.trunc;
+    const BiC error = (distance - gt_distance) * trunc_inv;
+    if (fabsf(error.re.re) > 1) return false;
+    loss = error * error;
+    return true;
+}
+
 __global__ void __launch_bounds__(256) tsdf_hessian_kernel(const LossParams P) {
     const size_t nvox = (size_t) P.rx * P.ry * P.rz;
     const float trunc_inv = 1.0f / P.trunc;
@@ -130,42 +181,43 @@ __global__ void __launch_bounds__(256) tsdf_hessian_kernel(const LossParams P) {
     for (size_t index = (size_t) blockIdx.x * blockDim.x + threadIdx.x; index < nvox; index += (size_t) gridDim.x * blockDim.x) {
         const float gt = __ldg(P.gt + index);
         if (gt == 0 || fabsf(gt) > 0.95f) continue;  // TsdfFusion.cu:222
-        const int x = (int) (index % P.rx), y = (int) ((index / P.rx) % P.ry), z = (int) (index / ((size_t) P.rx * P.ry));
-        const BiC3 vg = {bic((float(x) + 0.5f) * P.voxel), bic((float(y) + 0.5f) * P.voxel), bic((float(z) + 0.5f) * P.voxel)};
-        const BiC3 r0 = {P.R[0], P.R[1], P.R[2]}, r1 = {P.R[3], P.R[4], P.R[5]}, r2 = {P.R[6], P.R[7], P.R[8]};
-        const BiC3 vc = {bdot(r0, vg) + P.t[0], bdot(r1, vg) + P.t[1], bdot(r2, vg) + P.t[2]};
-        const BiC inv_z = bic(1.0f) / vc.z;
-        if (inv_z.re.re < 0) continue;
-        const BiC image_x = vc.x * inv_z * P.intr.fx + P.intr.cx;  // :232-233
-        const BiC image_y = vc.y * inv_z * P.intr.fy + P.intr.cy;
-        const int coox = __float2int_rd(image_x.re.re - 0.5f), cooy = __float2int_rd(image_y.re.re - 0.5f);
-        if (!(coox > 1 && cooy > 1 && coox < P.cols - 1 && cooy < P.rows - 1)) continue;
-        const int nx = __float2int_rn(image_x.re.re), ny = __float2int_rn(image_y.re.re);
-        const float d00 = __ldg(P.depth + (size_t) cooy * P.cols + coox), d10 = __ldg(P.depth + (size_t) cooy * P.cols + coox + 1);
-        const float d01 = __ldg(P.depth + (size_t) (cooy + 1) * P.cols + coox),
-                    d11 = __ldg(P.depth + (size_t) (cooy + 1) * P.cols + coox + 1);
-        BiC Dp;
-        if (d00 != 0.0f && d01 != 0.0f && d10 != 0.0f && d11 != 0.0f) {  // :248-256 (no threshold test)
-            const BiC one = bic(1.0f);
-            const BiC a = image_x - bic(float(coox) + 0.5f), b = image_y - bic(float(cooy) + 0.5f);
-            Dp = bic(d00) * (one - a) * (one - b) + bic(d10) * a * (one - b) + bic(d01) * (one - a) * b + bic(d11) * a * b;
-        } else {
-            Dp = bic(__ldg(P.depth + (size_t) ny * P.cols + nx));
-        }
-        if (Dp.re.re > 5 || Dp.re.re < 0.2) continue;  // :260 (compared in double, as the literals are)
-        const BiC xl = (image_x - P.intr.cx) / P.intr.fx, yl = (image_y - P.intr.cy) / P.intr.fy;
-        const BiC3 v1 = {Dp * xl, Dp * yl, Dp};
-        const BiC distance = bnorm(v1) - bnorm(vc);
-        const BiC gt_distance = bic(gt) * P.trunc;
-        const BiC error = (distance - gt_distance) * trunc_inv;
-        if (fabsf(error.re.re) > 1) continue;
-        const BiC loss = error * error;
+        BiC loss;
+        if (!hessian_voxel(P, P.R, P.t, gt, index, trunc_inv, loss)) continue;
         acc[0] += (double) loss.re.re;  // value()
         acc[1] += (double) loss.re.im;  // grad()
         acc[2] += (double) loss.im.im;  // hessian()
         acc[3] += 1.0;
     }
     block_reduce_to_out<4>(acc, P.partials, P.out, P.ticket);
+}
+
+// DB bicomplex directions per sweep of the ground-truth volume: the volume (4 GiB at 1024^3) is streamed once for all of
+// them instead of once per direction - the kernel is bound by that stream, since only the few per cent of voxels inside
+// the ground truth's truncation band reach the bicomplex arithmetic.  Every direction runs the single-direction code on
+// the same voxels in the same order, so its sums are bit-identical to a tsdf_hessian_kernel launch of its own.
+template <int DB> __global__ void __launch_bounds__(256) tsdf_hessian_batch_kernel(const LossParams P, const BiC *__restrict__ poses /* [DB][12] */) {
+    __shared__ BiC s_pose[DB][12];
+    for (int i = threadIdx.x; i < DB * 12; i += blockDim.x) s_pose[i / 12][i % 12] = poses[i];
+    __syncthreads();
+    const size_t nvox = (size_t) P.rx * P.ry * P.rz;
+    const float trunc_inv = 1.0f / P.trunc;
+    double acc[DB * 4];
+#pragma unroll
+    for (int i = 0; i < DB * 4; ++i) acc[i] = 0.0;
+    for (size_t index = (size_t) blockIdx.x * blockDim.x + threadIdx.x; index < nvox; index += (size_t) gridDim.x * blockDim.x) {
+        const float gt = __ldg(P.gt + index);
+        if (gt == 0 || fabsf(gt) > 0.95f) continue;
+#pragma unroll
+        for (int q = 0; q < DB; ++q) {
+            BiC loss;
+            if (!hessian_voxel(P, s_pose[q], s_pose[q] + 9, gt, index, trunc_inv, loss)) continue;
+            acc[q * 4 + 0] += (double) loss.re.re;
+            acc[q * 4 + 1] += (double) loss.re.im;
+            acc[q * 4 + 2] += (double) loss.im.im;
+            acc[q * 4 + 3] += 1.0;
+        }
+    }
+    block_reduce_to_out<DB * 4>(acc, P.partials, P.out, P.ticket);
 }
 
 // ComputeLocalTsdfLossKernel (TsdfFusion.cu:335-406): the real-only twin of the kernel above - plain FP32 with the
@@ -328,5 +380,79 @@ extern "C" int xs_tsdf_loss(const uint16_t *d_depth, size_t depth_step_bytes, in
     cudaFree(d_scaled);
     cudaFree(d_part);
     cudaFree(d_ticket);
+    return XS_OK;
+}
+
+// Batched ComputeLocalTsdf_hessian: v2c carries ncomp = 3 * dirs components (eps1, eps2, eps1eps2 per direction); out_host is
+// [dirs][4] = {sum loss, sum grad, sum hessian, count} per direction.  Directions are processed 8 (then 4, 2, 1) per sweep of the
+// ground-truth volume.
+extern "C" int xs_tsdf_hessian_batch(const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, xs_intr intr,
+                                     const int res[3], float voxel_size, const xs_pose *v2c, float trunc, const float *d_gt,
+                                     double *out_host, void *stream) {
+    if (!d_depth || !res || !v2c || !d_gt || !out_host || v2c->ncomp <= 0 || v2c->ncomp % 3 || !v2c->dR || !v2c->dt) {
+        set_error("xs_tsdf_hessian_batch: needs ncomp = 3 * dirs components (eps1, eps2, eps1eps2 per direction)");
+        return XS_ERR_ARG;
+    }
+    const int dirs = v2c->ncomp / 3;
+    cudaStream_t s = (cudaStream_t) stream;
+    const int grid = 148 * 8;
+    float *d_scaled = nullptr;
+    double *d_part = nullptr;
+    unsigned int *d_ticket = nullptr;
+    BiC *d_poses = nullptr;
+    std::vector<BiC> h_poses((size_t) dirs * 12);
+    for (int q = 0; q < dirs; ++q) {
+        for (int i = 0; i < 9; ++i)
+            h_poses[(size_t) q * 12 + i] = {{v2c->R[i], v2c->dR[(3 * q) * 9 + i]}, {v2c->dR[(3 * q + 1) * 9 + i], v2c->dR[(3 * q + 2) * 9 + i]}};
+        for (int i = 0; i < 3; ++i)
+            h_poses[(size_t) q * 12 + 9 + i] = {{v2c->t[i], v2c->dt[(3 * q) * 3 + i]}, {v2c->dt[(3 * q + 1) * 3 + i], v2c->dt[(3 * q + 2) * 3 + i]}};
+    }
+    XS_CUDA(cudaMalloc(&d_scaled, (size_t) rows * cols * sizeof(float)));
+    XS_CUDA(cudaMalloc(&d_part, ((size_t) grid * 32 + (size_t) dirs * 4) * sizeof(double)));
+    XS_CUDA(cudaMalloc(&d_ticket, sizeof(unsigned int)));
+    XS_CUDA(cudaMalloc(&d_poses, h_poses.size() * sizeof(BiC)));
+    XS_CUDA(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned int), s));
+    XS_CUDA(cudaMemcpyAsync(d_poses, h_poses.data(), h_poses.size() * sizeof(BiC), cudaMemcpyHostToDevice, s));
+    dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
+    scale_depth_kernel2<<<grd, blk, 0, s>>>(d_depth, depth_step_bytes, rows, cols, d_scaled);
+    XS_LAUNCH_CHECK();
+    LossParams P;
+    P.depth = d_scaled;
+    P.rows = rows;
+    P.cols = cols;
+    P.rx = res[0];
+    P.ry = res[1];
+    P.rz = res[2];
+    P.voxel = voxel_size;
+    P.trunc = trunc;
+    P.intr = intr;
+    P.gt = d_gt;
+    P.partials = d_part;
+    P.ticket = d_ticket;
+    double *d_out = d_part + (size_t) grid * 32;
+    for (int q = 0; q < dirs;) {  // stream-ordered launches share the partial buffer and the (self-resetting) ticket
+        P.out = d_out + (size_t) q * 4;
+        const BiC *pq = d_poses + (size_t) q * 12;
+        if (dirs - q >= 8) {
+            tsdf_hessian_batch_kernel<8><<<grid, 256, 0, s>>>(P, pq);
+            q += 8;
+        } else if (dirs - q >= 4) {
+            tsdf_hessian_batch_kernel<4><<<grid, 256, 0, s>>>(P, pq);
+            q += 4;
+        } else if (dirs - q >= 2) {
+            tsdf_hessian_batch_kernel<2><<<grid, 256, 0, s>>>(P, pq);
+            q += 2;
+        } else {
+            tsdf_hessian_batch_kernel<1><<<grid, 256, 0, s>>>(P, pq);
+            q += 1;
+        }
+        XS_LAUNCH_CHECK();
+    }
+    XS_CUDA(cudaMemcpyAsync(out_host, d_out, (size_t) dirs * 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    XS_CUDA(cudaStreamSynchronize(s));
+    cudaFree(d_scaled);
+    cudaFree(d_part);
+    cudaFree(d_ticket);
+    cudaFree(d_poses);
     return XS_OK;
 }

@@ -188,6 +188,21 @@ def ComputeLocalTsdf_hessian(depth_u16, intr, resolution, voxel_size, v2c, trunc
     return [out[i] for i in range(4)]
 
 
+def ComputeLocalTsdf_hessian_batch(depth_u16, intr, resolution, voxel_size, v2c, trunc, gt):
+    """ComputeLocalTsdf_hessian for dirs bicomplex directions at once (v2c: PoseBatch with ncomp = 3 * dirs); the ground-truth
+    volume is streamed once per 8 directions.  Returns float64 [dirs, 4] = (sum loss, sum grad, sum hessian, count)."""
+    _need_cuda(depth_u16, gt)
+    rows, cols = depth_u16.shape
+    res = (C.c_int * 3)(*[int(r) for r in resolution])
+    p = v2c.c()
+    dirs = v2c.ncomp // 3
+    out = np.zeros((dirs, 4), np.float64)
+    check(_capi.load().xs_tsdf_hessian_batch(_ptr(depth_u16), cols * 2, rows, cols, intr, res, voxel_size, C.byref(p), trunc,
+                                             _ptr(gt), out.ctypes.data_as(C.POINTER(C.c_double)), _stream()),
+          "ComputeLocalTsdf_hessian_batch")
+    return out
+
+
 def ComputeLocalTsdf_loss(depth_u16, intr, resolution, voxel_size, Rv2c, tv2c, trunc, gt):
     """TsdfFusion.h:48-52 (real-only volume loss).  Rv2c: float32 [3, 3] row-major, tv2c: float32 [3]; gt: float32 [z, y, x].
     Returns [sum loss, count]."""
