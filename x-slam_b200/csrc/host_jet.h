@@ -24,10 +24,12 @@ inline HJetCtx &hj_ctx() {
     return c;
 }
 
+struct HJetNoInit {};
 struct HJet {
     float v = 0.f;
     float d[HJ_MAX];
     HJet() { std::memset(d, 0, sizeof(float) * hj_ctx().ncomp()); }
+    explicit HJet(HJetNoInit) {}  // every live component is about to be overwritten
     HJet(float x) : v(x) { std::memset(d, 0, sizeof(float) * hj_ctx().ncomp()); }
     // copies touch only the live components
     HJet(const HJet &o) : v(o.v) { std::memcpy(d, o.d, sizeof(float) * hj_ctx().ncomp()); }
@@ -39,45 +41,47 @@ struct HJet {
 };
 
 inline HJet operator+(const HJet &a, const HJet &b) {
-    HJet r;
+    HJet r{HJetNoInit()};
     r.v = a.v + b.v;
     const int n = hj_ctx().ncomp();
     for (int i = 0; i < n; ++i) r.d[i] = a.d[i] + b.d[i];
     return r;
 }
 inline HJet operator-(const HJet &a, const HJet &b) {
-    HJet r;
+    HJet r{HJetNoInit()};
     r.v = a.v - b.v;
     const int n = hj_ctx().ncomp();
     for (int i = 0; i < n; ++i) r.d[i] = a.d[i] - b.d[i];
     return r;
 }
 inline HJet operator-(const HJet &a) {
-    HJet r;
+    HJet r{HJetNoInit()};
     r.v = -a.v;
     const int n = hj_ctx().ncomp();
     for (int i = 0; i < n; ++i) r.d[i] = -a.d[i];
     return r;
 }
 inline HJet operator*(const HJet &a, const HJet &b) {
-    HJet r;
+    HJet r{HJetNoInit()};
     r.v = a.v * b.v;
     const HJetCtx &c = hj_ctx();
-    if (c.comps == 1) {
-        for (int k = 0; k < c.dirs; ++k) r.d[k] = a.v * b.d[k] + a.d[k] * b.v;
-    } else {
+    const int n = c.ncomp();
+    const float av = a.v, bv = b.v;
+    // the product rule term of every component as one flat (vectorisable) loop; the eps1eps2 cross terms are added after, in
+    // the order of the expression  a.v*b12 + a12*b.v + a1*b2 + a2*b1
+    for (int i = 0; i < n; ++i) r.d[i] = av * b.d[i] + a.d[i] * bv;
+    if (c.comps == 3) {
         for (int k = 0; k < c.dirs; ++k) {
-            const float a1 = a.d[3 * k], a2 = a.d[3 * k + 1], a12 = a.d[3 * k + 2];
-            const float b1 = b.d[3 * k], b2 = b.d[3 * k + 1], b12 = b.d[3 * k + 2];
-            r.d[3 * k] = a.v * b1 + a1 * b.v;
-            r.d[3 * k + 1] = a.v * b2 + a2 * b.v;
-            r.d[3 * k + 2] = a.v * b12 + a12 * b.v + a1 * b2 + a2 * b1;
+            float t = r.d[3 * k + 2];
+            t = t + a.d[3 * k] * b.d[3 * k + 1];
+            t = t + a.d[3 * k + 1] * b.d[3 * k];
+            r.d[3 * k + 2] = t;
         }
     }
     return r;
 }
 inline HJet operator/(const HJet &a, const HJet &b) {
-    HJet r;
+    HJet r{HJetNoInit()};
     r.v = a.v / b.v;
     const float inv = 1.f / b.v;
     const HJetCtx &c = hj_ctx();

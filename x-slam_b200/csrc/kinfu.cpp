@@ -393,6 +393,7 @@ int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_devi
     k->launches[0] = g_launches - l0;
     l0 = g_launches;
     const int aligned = xs_kinfu_pose_estimate(k);
+    const auto dbg_t0 = std::chrono::steady_clock::now();
     cudaEventRecord(k->ev[2], k->stream);
     k->launches[1] = g_launches - l0;
     l0 = g_launches;
@@ -403,11 +404,18 @@ int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_devi
     // integration and raycast are queued back to back (no host round trip between them): their only host input is the pose
     xs_volume_set_pipelined(k->volume, 1);
     const int rc_int = xs_kinfu_integrate_frame(k, d_depth);
+    const auto dbg_t1 = std::chrono::steady_clock::now();
     cudaEventRecord(k->ev[3], k->stream);
     k->launches[2] = g_launches - l0;
     l0 = g_launches;
     const int rc_ray = rc_int == XS_OK ? xs_kinfu_calculate_point_cloud(k) : rc_int;
     xs_volume_set_pipelined(k->volume, 0);
+    if (getenv("XS_TIMING")) {
+        const auto dbg_t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[xs timing] host: integrate queued after %.1f us, raycast queued after %.1f us more\n",
+                std::chrono::duration<double, std::micro>(dbg_t1 - dbg_t0).count(),
+                std::chrono::duration<double, std::micro>(dbg_t2 - dbg_t1).count());
+    }
     if (rc_int != XS_OK || rc_ray != XS_OK) {
         cudaStreamSynchronize(k->stream);
         return 0;
