@@ -10,12 +10,13 @@
 //                         widened to double exactly as the reference does (product in float, sum in double,
 //                         ICP.cu:273-274), and a per-pixel association record (matched index + the 16 real numbers
 //                         every direction needs) that stays L2-resident (68 B/pixel).
-//   2. icp_deriv_kernel   one CTA per (pixel chunk, direction group): reads the record, gathers that direction's
-//                         derivative planes of the previous maps at the matched pixel and accumulates the derivative
-//                         components of the 27 products (linearised row algebra, no recomputation of the real path).
-//                         A thread sums at most 32 pixels in FP32, then everything is reduced in double: fixed-order
-//                         combination of lanes and warps, per-CTA partials.  The LAST CTA of a direction group to
-//                         arrive adds the per-chunk partials in a fixed order and runs the host Gauss-Newton step of
+//   2. icp_deriv_kernel   persistent: the (direction group, pixel unit) items are cut into equal contiguous ranges for
+//                         296 CTAs.  A thread reads the record, gathers its direction's derivative planes of the previous
+//                         maps at the matched pixel (cp.async, one pixel ahead) and accumulates the derivative components
+//                         of the 27 products (linearised row algebra, no recomputation of the real path) for at most 32
+//                         pixels in FP32; then a fixed FP32 butterfly over the lanes, double totals per thread, the 8 warps
+//                         and the CTAs of a group in fixed order.  The LAST CTA of a direction group to arrive adds the
+//                         group's partials and runs the host Gauss-Newton step of
 //                         KinectFusionReconstruction.cpp:203-224 for its direction on the device (icp_solve_direction:
 //                         det guard, 6x6 LLT solve in double, Rinc = Rz*Ry*Rx, pose update - one thread per direction,
 //                         every thread redoing the tiny real part).  The current pose therefore lives in device memory
