@@ -51,9 +51,29 @@ struct IntegrateParams {
     const int2 *brick_list;     // bricks that survive the cull (written by cull_bricks_kernel): (index, packed x|y<<10|z<<20)
     unsigned int *list_count;
     unsigned char *live;        // [nbricks] 0 = every derivative plane of the brick is still exactly zero
+    const float *tile_max;      // [tiles_y][tiles_x] largest valid depth (metres) of each 16 x 16 pixel tile, 0 = none
+    int tiles_x, tiles_y;
 };
 
-// Conservative brick cull: bounding sphere vs. camera half-space / image planes.  One thread per brick; survivors are
+// Largest depth of every 16 x 16 pixel tile (invalid pixels are 0), for the depth-aware part of the brick cull.
+constexpr int CULL_TILE = 16;
+__global__ void __launch_bounds__(256) depth_tile_max_kernel(const float *__restrict__ depth, int rows, int cols, float *__restrict__ tile_max,
+                                                             int tiles_x) {
+    const int x = blockIdx.x * CULL_TILE + (threadIdx.x & 15), y = blockIdx.y * CULL_TILE + (threadIdx.x >> 4);
+    float v = (x < cols && y < rows) ? depth[(size_t) y * cols + x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __shared__ float s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) v = fmaxf(v, s[w]);
+        tile_max[blockIdx.y * tiles_x + blockIdx.x] = v;
+    }
+}
+
+// Conservative brick cull: bounding sphere vs. camera half-space / image planes, then against the depth image: a brick
+// whose nearest point lies farther than the largest depth under its (padded) footprint plus the truncation distance holds
+// only voxels the update rule skips (sdf < -trunc, TsdfFusion.cu:150) - in a room that is every brick behind the walls.  One thread per brick; survivors are
 // appended to the brick list (warp-aggregated), so the integration kernel never touches a brick outside the frustum.
 __global__ void __launch_bounds__(256) cull_bricks_kernel(const IntegrateParams P, int2 *__restrict__ list) {
     const int b = blockIdx.x * 256 + threadIdx.x;
@@ -87,6 +107,22 @@ __global__ void __launch_bounds__(256) cull_bricks_kernel(const IntegrateParams 
             nz = (P.rows + 0.5f - pcy);
             nn = sqrtf(fy * fy + nz * nz);
             if (-fy * ccy + nz * ccz + rad * nn < 0.f) cull = true;
+            if (!cull) {
+                // footprint of the bounding sphere: |u - u_c| <= |f| rad (Z + |X|) / (Z (Z - rad)), padded by the 2 pixels the
+                // bilinear / nearest depth look-up can reach; sdf = (Dp - z) * |ray| with |ray| >= 1, so z_min > max Dp + trunc
+                // implies sdf < -trunc for every voxel (and max Dp = 0, no valid depth, implies Dp <= 0 for every voxel)
+                const float zmin = ccz - rad, inv = 1.f / (ccz * zmin);
+                const float ru = fabsf(fx) * rad * (ccz + fabsf(ccx)) * inv + 2.5f, rv = fabsf(fy) * rad * (ccz + fabsf(ccy)) * inv + 2.5f;
+                const float uc = fx * ccx / ccz + pcx, vc = fy * ccy / ccz + pcy;
+                const int tx0 = max(0, (int) floorf((uc - ru) * (1.f / CULL_TILE))), tx1 = min(P.tiles_x - 1, (int) floorf((uc + ru) * (1.f / CULL_TILE)));
+                const int ty0 = max(0, (int) floorf((vc - rv) * (1.f / CULL_TILE))), ty1 = min(P.tiles_y - 1, (int) floorf((vc + rv) * (1.f / CULL_TILE)));
+                if (tx1 >= tx0 && ty1 >= ty0 && (tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= 64) {
+                    float dmax = 0.f;
+                    for (int ty = ty0; ty <= ty1; ++ty)
+                        for (int tx = tx0; tx <= tx1; ++tx) dmax = fmaxf(dmax, __ldg(P.tile_max + ty * P.tiles_x + tx));
+                    if (zmin > dmax + P.V.trunc + 2e-3f) cull = true;
+                }
+            }
         }
         keep = !cull;
     }
@@ -335,6 +371,8 @@ xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_rang
     if (e == cudaSuccess && V.ncomp) e = cudaMalloc(&V.deriv, nvox * sizeof(float) * V.ncomp);
     size_t pose_floats = (size_t) (V.ncomp > 0 ? V.ncomp : 1) * 12 * 3;
     v->pipelined = false;
+    v->d_tile_max = nullptr;
+    v->tile_capacity = 0;
     if (e == cudaSuccess) e = cudaMalloc(&v->d_dpose, pose_floats * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost(&v->h_dpose, pose_floats * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&v->d_stats, 4 * sizeof(unsigned long long));
@@ -372,6 +410,7 @@ void xs_volume_destroy(xs_volume *v) {
     cudaFree(v->view.weight);
     cudaFree(v->view.deriv);
     cudaFree(v->d_dpose);
+    cudaFree(v->d_tile_max);
     cudaFreeHost(v->h_dpose);
     cudaFree(v->d_depth_m);
     cudaFree(v->d_hit_time);
@@ -477,6 +516,17 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
     P.brick_list = v->d_brick_list;
     P.list_count = v->d_list_count;
     P.live = v->d_live;
+    P.tiles_x = div_up(cols, CULL_TILE);
+    P.tiles_y = div_up(rows, CULL_TILE);
+    if (v->tile_capacity < P.tiles_x * P.tiles_y) {
+        cudaFree(v->d_tile_max);
+        v->d_tile_max = nullptr;
+        XS_CUDA(cudaMalloc(&v->d_tile_max, (size_t) P.tiles_x * P.tiles_y * sizeof(float)));
+        v->tile_capacity = P.tiles_x * P.tiles_y;
+    }
+    P.tile_max = v->d_tile_max;
+    depth_tile_max_kernel<<<dim3(P.tiles_x, P.tiles_y), 256, 0, s>>>(v->d_depth_m, rows, cols, v->d_tile_max, P.tiles_x);
+    XS_LAUNCH_CHECK();
     XS_CUDA(cudaMemsetAsync(v->d_stats, 0, 4 * sizeof(unsigned long long), s));
     XS_CUDA(cudaMemsetAsync(v->d_list_count, 0, sizeof(unsigned int), s));
     cull_bricks_kernel<<<div_up(P.nbricks, 256), 256, 0, s>>>(P, v->d_brick_list);

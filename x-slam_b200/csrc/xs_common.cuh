@@ -69,6 +69,8 @@ struct xs_volume {
     float *h_dpose;      // pinned host mirror
     float *d_depth_m;    // scaled depth (metres), TsdfFusion.cu:68-82
     int depth_capacity;  // pixels
+    float *d_tile_max;   // largest depth per 16 x 16 pixel tile (depth-aware brick cull)
+    int tile_capacity;   // tiles
     float *d_hit_time;   // raycast pass 1 -> pass 2: time of the sample before the crossing, < 0 = no hit
     int hit_capacity;    // pixels
     unsigned long long *d_stats;
