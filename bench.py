@@ -132,8 +132,8 @@ class ClockSampler(threading.Thread):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this same
-# command (profiles/r01f_ncu_summary.md: 512^3, 55 DCSFD directions, 1 GPU); None for any other configuration.
-TRAFFIC_55 = {"icp_deriv": 1.239e9, "integrate": 6.34e8}
+# command (profiles/r01g_ncu_summary.md: 512^3, 55 DCSFD directions, 1 GPU); None for any other configuration.
+TRAFFIC_55 = {"icp_deriv": 1.243e9, "integrate": 6.40e8}
 TRAFFIC = {}
 
 
