@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--dirs", type=int, default=55)
     ap.add_argument("--comps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-frames", action="store_true",
+                    help="ProcessFrame waits for the end of each frame like the reference's (default: deferred mode, the "
+                         "end-of-frame wait moves to the start of the next call)")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA kernels (oracle/_ref)")
     return ap.parse_args()
 
@@ -241,15 +244,31 @@ def run_ours(args, xs, rank, world, local_rank):
     dev_frames = [torch.from_numpy(f.astype(np.int16)).cuda() for f in frames[:W + K]]
     pinned = [torch.from_numpy(f.astype(np.int16)).pin_memory() for f in frames[W + K:]]
 
+    lib_stream = torch.cuda.ExternalStream(k.stream_ptr())
+    deferred = not args.sync_frames
+    if deferred:
+        k.set_deferred(True)
+
     def step(depth):
         ok = k.ProcessFrame(depth)
         if not ok:
             raise RuntimeError("frame alignment failed: " + lib.xs_last_error().decode())
         if world > 1:  # derivatives gathered by NCCL all-gather over NVLink (north_star (4))
-            send[: rec_view.numel()].copy_(rec_view)
-            dist.all_gather_into_tensor(gather_out, send)
+            # stream-ordered behind the frame's record upload, no host wait; the collective runs on NCCL's stream beside the
+            # next frame's kernels (async_op: the pipeline's stream does not wait for it until the send buffer is reused)
+            with torch.cuda.stream(lib_stream):
+                if gather_work[0] is not None:
+                    gather_work[0].wait()
+                send[: rec_view.numel()].copy_(rec_view)
+                gather_work[0] = dist.all_gather_into_tensor(gather_out, send, async_op=True)
+
+    gather_work = [None]
 
     def sync():
+        k.sync()  # collects a deferred frame
+        if gather_work[0] is not None:
+            gather_work[0].wait()
+            gather_work[0] = None
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -270,12 +289,11 @@ def run_ours(args, xs, rank, world, local_rank):
     sync()
     l0 = lib.xs_launch_count()
     # CUDA events on the stream the library launches on (torch.cuda.Event sees only the stream it is recorded on)
-    lib_stream = torch.cuda.ExternalStream(k.stream_ptr())
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(lib_stream)
     t0 = time.perf_counter()
-    for i in range(K):
-        step(dev_frames[W + i])
+    def collect():  # stage times / statistics of the last collected frame
+        nonlocal kern_ms, upd
         tm, _ = k.times()
         for n in stage_ms:
             stage_ms[n] += tm[n]
@@ -284,14 +302,27 @@ def run_ours(args, xs, rank, world, local_rank):
             abytes[n] += ab[n]
         kern_ms += lib.xs_volume_last_integrate_ms(vol)
         upd += k.stats()[0]
-        for j in range(lib.xs_icp_deriv_times(t_ms, t_px, 16)):  # level-0 launches of the dominant kernel
+
+    for i in range(K):
+        step(dev_frames[W + i])
+        # deferred mode: frame i is still integrating / raycasting here; the getters describe frame i - 1 (collected at the
+        # start of this step), so the per-stage sums lag by one frame and the last frame is collected after the final sync
+        if not deferred or i > 0:
+            collect()
+        for j in range(lib.xs_icp_deriv_times(t_ms, t_px, 16)):  # level-0 launches of the dominant kernel (ICP is complete)
             if t_px[j] == 640 * 480:
                 icp_ms += t_ms[j]
                 icp_n += 1
+    if gather_work[0] is not None:  # the closing event also covers the last frame's all-gather
+        with torch.cuda.stream(lib_stream):
+            gather_work[0].wait()
     ev1.record(lib_stream)
     sync()
     t_wall = time.perf_counter() - t0
-    # the frame loop synchronises with the host once per stage, so the device-event bracket and the wall clock agree;
+    if deferred:
+        collect()
+    # the frame loop synchronises with the host at least once per frame (the ICP result), so the device-event bracket and
+    # the wall clock agree;
     # the reported value uses the device events (max over ranks below)
     t_dev = ev0.elapsed_time(ev1) * 1e-3
     launches = lib.xs_launch_count() - l0
@@ -337,6 +368,7 @@ def run_ours(args, xs, rank, world, local_rank):
         "config": {"workload": "icl_synth_640x480_tsdf%d_dcsfd%d" % (args.res, args.dirs), "depth": "640x480 uint16 mm",
                    "tsdf": "%d^3 @ %.4f m" % (args.res, 7.68 / args.res), "directions": args.dirs, "components_per_direction": args.comps,
                    "derivative_planes": args.dirs * args.comps, "directions_per_rank": max_dirs, "sharding": "directions over ranks, real state replicated",
+                   "frame_sync": "deferred (end-of-frame wait at the start of the next ProcessFrame; ICP result read on the host every frame)" if deferred else "every frame",
                    "l2": "per-step working set (volume %.1f GB/rank) >> 126 MB L2, no flush needed" % (lib.xs_volume_bytes(vol) / 1e9)},
         "e2e": {"value": K / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),

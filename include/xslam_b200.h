@@ -199,6 +199,14 @@ void xs_kinfu_destroy(xs_kinfu *k);
 /* ProcessFrame, KinectFusionReconstruction.cpp:147-159.  depth: 640x480 uint16 mm, dense; host pointer
  * unless depth_on_device != 0.  Returns 1 on success, 0 when frame alignment failed (as the reference). */
 int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_device);
+/* Deferred mode (off by default; the reference's ProcessFrame is synchronous, KinectFusionReconstruction.cpp:147-159 with the
+ * syncs of resizeVMap / resizeNMap, Map.cu:234-260).  With on != 0 xs_kinfu_process_frame returns once integration, raycast and
+ * the pyramid are queued on the stream - pose and return status are final, the volume and the maps follow in stream order -
+ * and the end-of-frame wait moves to the start of the next xs_kinfu_process_frame or to xs_kinfu_sync.  Statistics and stage
+ * times then describe the last collected frame; a device-resident depth frame must stay valid until that point. */
+int xs_kinfu_set_deferred(xs_kinfu *k, int on);
+/* waits for all queued work of the pipeline and collects the statistics of a deferred frame */
+int xs_kinfu_sync(xs_kinfu *k);
 /* stage entry points, KinectFusionReconstruction.h:113-141 */
 int xs_kinfu_surface_measure(xs_kinfu *k, const uint16_t *d_depth);
 int xs_kinfu_pose_estimate(xs_kinfu *k);

@@ -108,3 +108,13 @@ def test_synthetic_depth_source(xs):
     assert np.linalg.norm(p1[:3, 3]) <= 0.015  # <= 1.5 cm per frame
     ang = np.degrees(np.arccos(np.clip((np.trace(p1[:3, :3]) - 1) / 2, -1, 1)))
     assert ang <= 0.4
+
+
+def test_null_handles_are_argument_errors(xs):
+    """Entry points that take a pipeline handle reject NULL with XS_ERR_ARG (no device needed, nothing is launched)."""
+    lib = xs.load()
+    assert lib.xs_kinfu_set_deferred(None, 1) < 0
+    assert lib.xs_kinfu_sync(None) < 0
+    assert lib.xs_kinfu_frame_id(None) == -1
+    assert lib.xs_kinfu_process_frame(None, None, 0) == 0
+    assert lib.xs_volume_set_pipelined(None, 1) < 0

@@ -175,3 +175,41 @@ def test_gt_pose_mapping_mode(xs):
     assert float((wg != wt).float().mean()) < 2e-2
     both = (wg > 0) & (wt > 0)
     assert float((vg[both] - vt[both]).abs().mean()) < 2e-2
+
+
+def test_deferred_frame_loop_is_bit_identical(xs, frames):
+    """xs_kinfu_set_deferred only moves the end-of-frame wait: poses (all derivative components), the volume, the raycast
+    maps and the per-frame statistics are bit-identical to the synchronous loop, with host and device-resident frames."""
+    import torch
+    cfg = dict(xs.DEFAULT_CONFIG)
+    seeds, _ = xs.pose_seeds_dcsfd([(0, 0), (1, 4), (3, 5)])
+    runs = []
+    for deferred in (False, True):
+        k = xs.KinectFusionReconstruction()
+        k.SetYamlParameters(cfg, comps=3, seeds=seeds)
+        if deferred:
+            k.set_deferred(True)
+        dev = [torch.from_numpy(d.astype(np.int16)).cuda() for d in frames]
+        poses, stats = [], []
+        for f, d in enumerate(frames):
+            assert k.ProcessFrame(dev[f] if f % 2 else d) == 1
+            poses.append(k.world2camera.copy())  # final when the call returns, in both modes
+            if deferred and f > 0:
+                stats.append(k.stats())          # last collected frame = f - 1
+            elif not deferred:
+                stats.append(k.stats())
+        k.sync()
+        if deferred:
+            stats.append(k.stats())
+        assert k.frame_id == len(frames)
+        v, w, g = k.volume_planes(7)
+        runs.append((poses, stats, v.cpu().numpy(), w.cpu().numpy(), g.cpu().numpy(),
+                     k.map("vmap_g_prev", 0).cpu().numpy(), k.map("nmap_g_prev", 2).cpu().numpy(), k.times()[0]))
+        k.ReleaseBuffers()
+    a, b = runs
+    for pa, pb in zip(a[0], b[0]):
+        assert np.array_equal(pa, pb)
+    assert a[1] == b[1]
+    for i in range(2, 7):
+        assert np.array_equal(a[i], b[i], equal_nan=True)
+    assert b[7]["total"] > 0 and b[7]["raycast"] > 0

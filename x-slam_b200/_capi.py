@@ -74,6 +74,8 @@ SYMBOLS = {
     "xs_kinfu_create": (_vp, [C.POINTER(Config), _i, _i, _pf, _i]),
     "xs_kinfu_destroy": (None, [_vp]),
     "xs_kinfu_process_frame": (_i, [_vp, _vp, _i]),
+    "xs_kinfu_set_deferred": (_i, [_vp, _i]),
+    "xs_kinfu_sync": (_i, [_vp]),
     "xs_kinfu_surface_measure": (_i, [_vp, _vp]),
     "xs_kinfu_pose_estimate": (_i, [_vp]),
     "xs_kinfu_integrate_frame": (_i, [_vp, _vp]),

@@ -480,24 +480,52 @@ int upload_pose_derivs(const xs_volume *v, const xs_pose *p, int slot, cudaStrea
 
 extern "C" int xs_volume_finish_frame(xs_volume *v, unsigned long long *stats_host);
 
-extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols,
-                            xs_intr intr, int max_weight, const xs_pose *v2c, float bilinear_threshold,
-                            unsigned long long *stats_host, void *stream) {
-    if (!v || !d_depth || !v2c || rows <= 0 || cols <= 0) return XS_ERR_ARG;
-    cudaStream_t s = (cudaStream_t) stream;
+namespace xs {
+// The pose-independent head of an integration: metric depth, the per-tile depth maxima of the brick cull, cleared counters.
+// The frame loop queues it behind the download of the ICP result so that it runs while the host does the pose algebra;
+// xs_integrate then finds it done (same frame, same stream) and starts with the cull.
+int integrate_prepare(xs_volume *v, const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, cudaStream_t s) {
     if (v->depth_capacity < rows * cols) {
         cudaFree(v->d_depth_m);
         XS_CUDA(cudaMalloc(&v->d_depth_m, (size_t) rows * cols * sizeof(float)));
         v->depth_capacity = rows * cols;
     }
+    const int tiles_x = div_up(cols, CULL_TILE), tiles_y = div_up(rows, CULL_TILE);
+    if (v->tile_capacity < tiles_x * tiles_y) {
+        cudaFree(v->d_tile_max);
+        v->d_tile_max = nullptr;
+        XS_CUDA(cudaMalloc(&v->d_tile_max, (size_t) tiles_x * tiles_y * sizeof(float)));
+        v->tile_capacity = tiles_x * tiles_y;
+    }
+    dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
+    scale_depth_kernel<<<grd, blk, 0, s>>>(d_depth, depth_step_bytes, rows, cols, v->d_depth_m);
+    XS_LAUNCH_CHECK();
+    depth_tile_max_kernel<<<dim3(tiles_x, tiles_y), 256, 0, s>>>(v->d_depth_m, rows, cols, v->d_tile_max, tiles_x);
+    XS_LAUNCH_CHECK();
+    XS_CUDA(cudaMemsetAsync(v->d_stats, 0, 4 * sizeof(unsigned long long), s));
+    XS_CUDA(cudaMemsetAsync(v->d_list_count, 0, sizeof(unsigned int), s));
+    v->prepared_depth = d_depth;
+    return XS_OK;
+}
+}  // namespace xs
+
+extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols,
+                            xs_intr intr, int max_weight, const xs_pose *v2c, float bilinear_threshold,
+                            unsigned long long *stats_host, void *stream) {
+    if (!v || !d_depth || !v2c || rows <= 0 || cols <= 0) return XS_ERR_ARG;
+    cudaStream_t s = (cudaStream_t) stream;
     // the staging buffer is reused by the next call: make sure the previous consumer is done.  In the frame loop (pipelined)
     // the caller synchronises once per frame and integration has a staging slot of its own, so nothing waits here.
     if (!v->pipelined) XS_CUDA(cudaStreamSynchronize(s));
     int rc = upload_pose_derivs(v, v2c, 2, s);
     if (rc != XS_OK) return rc;
-    dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
-    scale_depth_kernel<<<grd, blk, 0, s>>>(d_depth, depth_step_bytes, rows, cols, v->d_depth_m);
-    XS_LAUNCH_CHECK();
+    const bool prepared = v->pipelined && v->prepared_depth == d_depth;
+    v->prepared_depth = nullptr;
+    if (!prepared) {
+        rc = integrate_prepare(v, d_depth, depth_step_bytes, rows, cols, s);
+        v->prepared_depth = nullptr;
+        if (rc != XS_OK) return rc;
+    }
 
     IntegrateParams P;
     P.V = v->view;
@@ -518,17 +546,7 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
     P.live = v->d_live;
     P.tiles_x = div_up(cols, CULL_TILE);
     P.tiles_y = div_up(rows, CULL_TILE);
-    if (v->tile_capacity < P.tiles_x * P.tiles_y) {
-        cudaFree(v->d_tile_max);
-        v->d_tile_max = nullptr;
-        XS_CUDA(cudaMalloc(&v->d_tile_max, (size_t) P.tiles_x * P.tiles_y * sizeof(float)));
-        v->tile_capacity = P.tiles_x * P.tiles_y;
-    }
     P.tile_max = v->d_tile_max;
-    depth_tile_max_kernel<<<dim3(P.tiles_x, P.tiles_y), 256, 0, s>>>(v->d_depth_m, rows, cols, v->d_tile_max, P.tiles_x);
-    XS_LAUNCH_CHECK();
-    XS_CUDA(cudaMemsetAsync(v->d_stats, 0, 4 * sizeof(unsigned long long), s));
-    XS_CUDA(cudaMemsetAsync(v->d_list_count, 0, sizeof(unsigned int), s));
     cull_bricks_kernel<<<div_up(P.nbricks, 256), 256, 0, s>>>(P, v->d_brick_list);
     XS_LAUNCH_CHECK();
     int grid = 2 * P.nbricks < 148 * 24 ? 2 * P.nbricks : 148 * 24;
@@ -558,5 +576,6 @@ extern "C" int xs_volume_finish_frame(xs_volume *v, unsigned long long *stats_ho
 extern "C" int xs_volume_set_pipelined(xs_volume *v, int on) {
     if (!v) return XS_ERR_ARG;
     v->pipelined = on != 0;
+    if (!v->pipelined) v->prepared_depth = nullptr;
     return XS_OK;
 }

@@ -69,6 +69,7 @@ struct xs_volume {
     float *h_dpose;      // pinned host mirror
     float *d_depth_m;    // scaled depth (metres), TsdfFusion.cu:68-82
     int depth_capacity;  // pixels
+    const uint16_t *prepared_depth = nullptr;  // depth frame whose pose-independent head (integrate_prepare) is already queued
     float *d_tile_max;   // largest depth per 16 x 16 pixel tile (depth-aware brick cull)
     int tile_capacity;   // tiles
     float *d_hit_time;   // raycast pass 1 -> pass 2: time of the sample before the crossing, < 0 = no hit

@@ -177,6 +177,14 @@ class KinectFusionReconstruction:
             raise ValueError("depth frame must be [%d, %d]" % (self.depth_height, self.depth_width))
         return self.lib.xs_kinfu_process_frame(self.h, d.ctypes.data_as(C.c_void_p), 0)
 
+    def set_deferred(self, on=True):
+        """Throughput mode: ProcessFrame returns once integration + raycast are queued (pose and status are final); the
+        end-of-frame wait moves to the next ProcessFrame or to sync().  times() / stats() lag by one frame until then."""
+        check(self.lib.xs_kinfu_set_deferred(self.h, 1 if on else 0), "set_deferred")
+
+    def sync(self):
+        check(self.lib.xs_kinfu_sync(self.h), "sync")
+
     @property
     def frame_id(self):
         return self.lib.xs_kinfu_frame_id(self.h)
