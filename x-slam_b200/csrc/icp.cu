@@ -21,6 +21,11 @@
 //                         det guard, 6x6 LLT solve in double, Rinc = Rz*Ry*Rx, pose update - one thread per direction,
 //                         every thread redoing the tiny real part).  The current pose therefore lives in device memory
 //                         and the 12 iterations of a frame are queued back to back.
+// Split chains (frame loop with derivative components): the real part of an iteration - association, real sums, real step
+// - depends on no derivative component, so the real chain of a frame (icp_assoc_kernel + a one-thread icp_solve_kernel per
+// iteration) runs ahead on a second stream, leaving record, sums and real pose of every iteration in a slot of its own; the
+// derivative kernels follow back to back on the pipeline's stream and their tail updates derivative components only
+// (SolveParams::deriv_only).  The latency-bound association launches leave the critical path.
 // Instead of the reference's 27 sequential 256-thread shared-memory tree reductions per direction, the summation
 // order is fixed by construction, so results are deterministic run to run.
 #include "xs_common.cuh"
@@ -102,6 +107,8 @@ struct SolveParams {
     int *status;           // [2]: 0 = ok; 1 = |det(Re A)| < 1e-15; 2 = NaN det.  [0] sticky (later iterations are skipped)
     double *log;           // optional [27*(1+ncomp)] copy of the sums of this iteration
     int dirs, ncomp, solve_mode;
+    int deriv_only;        // the real part of the step is owned by another launch (split chains): only the derivative
+                           // components of pose_out are written, the status flags are read but not set
 };
 template <int C> __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, const double *real_sums,
                                                                   const double *comp_sums);
@@ -755,8 +762,9 @@ __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, co
             for (int i = 0; i < 27 * C; ++i) P.log[27 * (1 + q * C) + i] = comp_sums[i];
     }
     const int st0 = __ldcg(P.status), st1 = __ldcg(P.status + 1);
+    const bool owns_real = q == 0 && !P.deriv_only;
     if (st0 != 0 || st1 != 0) {  // [0] sticky flag of earlier iterations, [1] written by an earlier launch
-        if (q == 0) P.status[0] = st0 != 0 ? st0 : st1;
+        if (owns_real) P.status[0] = st0 != 0 ? st0 : st1;
         return;
     }
     double A[6][6], b[6];
@@ -765,7 +773,7 @@ __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, co
     if (fabs(det) < 1e-15 || isnan(det)) {
         // every thread of every block computes the same det and takes this branch; the flag is only read at kernel
         // entry by later launches
-        if (q == 0) P.status[1] = isnan(det) ? 2 : 1;
+        if (owns_real) P.status[1] = isnan(det) ? 2 : 1;
         return;
     }
     Chol6 F;
@@ -837,11 +845,11 @@ __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, co
     float *pw = P.pose_out;
     for (int i = 0; i < 3; ++i) {
         for (int j = 0; j < 3; ++j) {
-            if (q == 0) pw[i * 3 + j] = Rn.m[i][j].v;
+            if (owns_real) pw[i * 3 + j] = Rn.m[i][j].v;
             if (has_dir)
                 for (int a = 0; a < C; ++a) pw[(size_t) (1 + q * C + a) * 12 + i * 3 + j] = Rn.m[i][j].d[a];
         }
-        if (q == 0) pw[9 + i] = tn[i].v;
+        if (owns_real) pw[9 + i] = tn[i].v;
         if (has_dir)
             for (int a = 0; a < C; ++a) pw[(size_t) (1 + q * C + a) * 12 + 9 + i] = tn[i].d[a];
     }
@@ -863,7 +871,11 @@ struct IcpScratch {
     float *d_pose = nullptr, *h_pose = nullptr;  // seam-level entry point only: [(1+ncomp)][12]
     int *d_rec_idx = nullptr;
     float4 *d_rec_f = nullptr;
-    int cap_vals = 0, cap_comp = -1, cap_pix = 0;
+    int cap_vals = 0, cap_comp = -1, cap_pix = 0, cap_slots = 0;
+    // split chains (icp_iteration_async with a second stream): per-iteration slots of the sums and of the association record,
+    // and the event that marks the real chain's iteration as complete
+    static constexpr int MAX_SLOTS = 16;
+    cudaEvent_t ev_real[MAX_SLOTS] = {};
     size_t cap_dpart = 0;
     int max_blocks = 296;
     // CUDA-event brackets of the derivative kernel launches since the last reset (roofline timing, bench.py)
@@ -874,12 +886,20 @@ struct IcpScratch {
 };
 static IcpScratch g_icp;
 
-static int icp_reserve(int ncomp, int npix, size_t dpart, int groups) {
+static int icp_reserve(int ncomp, int npix, size_t dpart, int groups, int slots = 1) {
     const int nvals = 27 * (1 + ncomp);
+    if (slots > g_icp.cap_slots) {  // the slot count multiplies the sums and the record: start over with the larger one
+        g_icp.cap_vals = 0;
+        g_icp.cap_pix = 0;
+        g_icp.cap_slots = slots;
+    }
+    slots = g_icp.cap_slots;
     if (nvals > g_icp.cap_vals) {
         cudaFree(g_icp.d_sums);
         cudaFreeHost(g_icp.h_sums);
-        XS_CUDA(cudaMalloc(&g_icp.d_sums, (size_t) nvals * sizeof(double)));
+        g_icp.d_sums = nullptr;
+        g_icp.h_sums = nullptr;
+        XS_CUDA(cudaMalloc(&g_icp.d_sums, (size_t) nvals * slots * sizeof(double)));
         XS_CUDA(cudaMallocHost(&g_icp.h_sums, (size_t) nvals * sizeof(double)));
         g_icp.cap_vals = nvals;
     }
@@ -899,8 +919,10 @@ static int icp_reserve(int ncomp, int npix, size_t dpart, int groups) {
     if (ncomp > 0 && npix > g_icp.cap_pix) {
         cudaFree(g_icp.d_rec_idx);
         cudaFree(g_icp.d_rec_f);
-        XS_CUDA(cudaMalloc(&g_icp.d_rec_idx, (size_t) npix * sizeof(int)));
-        XS_CUDA(cudaMalloc(&g_icp.d_rec_f, (size_t) npix * 4 * sizeof(float4)));
+        g_icp.d_rec_idx = nullptr;
+        g_icp.d_rec_f = nullptr;
+        XS_CUDA(cudaMalloc(&g_icp.d_rec_idx, (size_t) npix * slots * sizeof(int)));
+        XS_CUDA(cudaMalloc(&g_icp.d_rec_f, (size_t) npix * slots * 4 * sizeof(float4)));
         g_icp.cap_pix = npix;
     }
     if (groups > g_icp.cap_groups) {
@@ -939,8 +961,14 @@ template <int C, int ST> static int launch_deriv(const IcpParams &P, const Solve
 int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
                         xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
                         int dirs, float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
-                        double *d_log, cudaStream_t s) {
+                        double *d_log, cudaStream_t s, cudaStream_t s_real, int slot) {
     const int ncomp = comps * dirs;
+    // Split chains: the real part of an iteration (association, real sums, real Gauss-Newton step) does not depend on any
+    // derivative component, so with a second stream the real chain of a frame - association + one-thread solve per
+    // iteration - runs ahead on s_real, each iteration leaving its record, sums and real pose in a slot of its own, and
+    // the derivative kernels follow back to back on s (their tail then only updates derivative components).
+    const bool split = s_real != nullptr && ncomp > 0 && d_pose_out != nullptr;
+    if (slot < 0 || slot >= IcpScratch::MAX_SLOTS || !split) slot = 0;
     const int npix = rows * cols;
     if ((double) (1 + ncomp) * 3.0 * npix >= 4294967296.0) {
         set_error("icp: a map set must hold fewer than 2^32 floats");
@@ -958,8 +986,9 @@ int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, cons
     const long long items = (long long) P.groups * P.chunks;
     const int deriv_grid = (int) (items < 296 ? items : 296);
     P.max_writers = ncomp > 0 ? (int) (P.chunks / (items / deriv_grid)) + 2 : 0;
-    int rc = icp_reserve(ncomp, npix, (size_t) P.groups * P.max_writers * 81, P.groups);
+    int rc = icp_reserve(ncomp, npix, (size_t) P.groups * P.max_writers * 81, P.groups, split ? IcpScratch::MAX_SLOTS : 1);
     if (rc != XS_OK) return rc;
+    const int nvals = 27 * (1 + ncomp);
     // only the current pose's derivative components enter the rows (s = Rcurr*v + tcurr); the previous pose is used
     // for the real projection only (ICP.cu:206-217 takes real parts)
     for (int i = 0; i < 9; ++i) P.prev.R[i] = prev->R[i];
@@ -976,17 +1005,18 @@ int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, cons
     P.ncomp = ncomp;
     P.dist_thres = dist_thres;
     P.angle_thres = angle_thres;
-    P.rec_idx = g_icp.d_rec_idx;
-    P.rec_f = g_icp.d_rec_f;
+    P.rec_idx = g_icp.d_rec_idx ? g_icp.d_rec_idx + (size_t) slot * g_icp.cap_pix : nullptr;
+    P.rec_f = g_icp.d_rec_f ? g_icp.d_rec_f + (size_t) slot * g_icp.cap_pix * 4 : nullptr;
     P.partials = g_icp.d_partials;
     P.dpartials = g_icp.d_dpartials;
-    P.sums = g_icp.d_sums;
+    P.sums = g_icp.d_sums + (size_t) slot * nvals;
     P.ticket = g_icp.d_ticket;
     P.group_ticket = g_icp.d_group_ticket;
     P.tiles_x = div_up(cols, 32);
     P.tiles_y = div_up(rows, 8);
     SolveParams S;
-    S.sums = g_icp.d_sums;
+    S.sums = P.sums;
+    S.deriv_only = split ? 1 : 0;
     S.pose_in = d_pose_curr;
     S.pose_out = d_pose_out;
     S.status = d_status;
@@ -996,16 +1026,28 @@ int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, cons
     S.solve_mode = solve_mode;
     const int ntiles = P.tiles_x * P.tiles_y;
     const int grid = ntiles < g_icp.max_blocks ? ntiles : g_icp.max_blocks;
-    icp_assoc_kernel<<<grid, dim3(32, 8), 0, s>>>(P);
+    icp_assoc_kernel<<<grid, dim3(32, 8), 0, split ? s_real : s>>>(P);
     XS_LAUNCH_CHECK();
+    if (split) {
+        SolveParams SR = S;  // the real step: one thread, no derivative components, owns the status flags
+        SR.dirs = 0;
+        SR.ncomp = 0;
+        SR.deriv_only = 0;
+        SR.log = nullptr;
+        icp_solve_kernel<1><<<1, 32, 0, s_real>>>(SR);
+        XS_LAUNCH_CHECK();
+        if (!g_icp.ev_real[slot]) XS_CUDA(cudaEventCreateWithFlags(&g_icp.ev_real[slot], cudaEventDisableTiming));
+        XS_CUDA(cudaEventRecord(g_icp.ev_real[slot], s_real));
+        XS_CUDA(cudaStreamWaitEvent(s, g_icp.ev_real[slot], 0));
+    }
     if (ncomp > 0) {
-        const int slot = g_icp.n_timed < IcpScratch::MAX_TIMED ? g_icp.n_timed : -1;
-        if (slot >= 0) {
-            if (!g_icp.ev0[slot]) {
-                XS_CUDA(cudaEventCreate(&g_icp.ev0[slot]));
-                XS_CUDA(cudaEventCreate(&g_icp.ev1[slot]));
+        const int tslot = g_icp.n_timed < IcpScratch::MAX_TIMED ? g_icp.n_timed : -1;
+        if (tslot >= 0) {
+            if (!g_icp.ev0[tslot]) {
+                XS_CUDA(cudaEventCreate(&g_icp.ev0[tslot]));
+                XS_CUDA(cudaEventCreate(&g_icp.ev1[tslot]));
             }
-            XS_CUDA(cudaEventRecord(g_icp.ev0[slot], s));
+            XS_CUDA(cudaEventRecord(g_icp.ev0[tslot], s));
         }
         // pipeline depth: 2 stages (one pixel ahead) measured faster than 3 on B200 (0.475 vs 0.542 ms per level-0 launch at
         // 55 directions: the deeper pipeline costs L1 capacity and does not raise issue utilisation); XS_ICP_STAGES=3 selects it
@@ -1015,9 +1057,9 @@ int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, cons
         else
             rc = stages == 2 ? launch_deriv<3, 2>(P, S, deriv_grid, s) : launch_deriv<3, DERIV_MAX_STAGES>(P, S, deriv_grid, s);
         if (rc != XS_OK) return rc;
-        if (slot >= 0) {
-            XS_CUDA(cudaEventRecord(g_icp.ev1[slot], s));
-            g_icp.timed_npix[slot] = npix;
+        if (tslot >= 0) {
+            XS_CUDA(cudaEventRecord(g_icp.ev1[tslot], s));
+            g_icp.timed_npix[tslot] = npix;
             ++g_icp.n_timed;
         }
     } else if (d_pose_out) {
@@ -1151,7 +1193,7 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
     }
     XS_CUDA(cudaMemcpyAsync(g_icp.d_pose, h, (size_t) (1 + ncomp) * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
     rc = icp_iteration_async(g_icp.d_pose, d_vmap_curr, d_nmap_curr, prev, intr, d_vmap_g_prev, d_nmap_g_prev, rows, cols,
-                             comps, dirs, dist_thres, angle_thres, nullptr, 0, nullptr, nullptr, s);
+                             comps, dirs, dist_thres, angle_thres, nullptr, 0, nullptr, nullptr, s, nullptr, 0);
     if (rc != XS_OK) return rc;
     const int nvals = 27 * (1 + ncomp);
     XS_CUDA(cudaMemcpyAsync(g_icp.h_sums, g_icp.d_sums, (size_t) nvals * sizeof(double), cudaMemcpyDeviceToHost, s));

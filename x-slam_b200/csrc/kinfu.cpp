@@ -29,7 +29,7 @@ extern long long g_launches;
 int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
                         xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
                         int dirs, float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
-                        double *d_log, cudaStream_t s);
+                        double *d_log, cudaStream_t s, cudaStream_t s_real, int slot);
 void icp_timing_reset();
 // integrate.cu: pose-independent head of the integration (metric depth, tile maxima, cleared counters)
 int integrate_prepare(xs_volume *v, const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, cudaStream_t s);
@@ -60,7 +60,11 @@ struct xs_kinfu {
     uint16_t *h_depth = nullptr;  // pinned staging
     std::vector<float *> depths, vmaps_curr, nmaps_curr, vmaps_prev, nmaps_prev;
     float *d_record = nullptr, *h_record = nullptr;  // [(1+ncomp)][16]
-    float *d_pose[2] = {nullptr, nullptr};           // ICP current pose, ping-pong: [(1+ncomp)][12] (R row-major, t)
+    static constexpr int POSE_SLOTS = 13;            // 12 Gauss-Newton iterations + the initial estimate
+    float *d_pose_all = nullptr;                     // ICP pose after each iteration: [POSE_SLOTS][(1+ncomp)][12] (R row-major, t)
+    float *d_pose_slot(int it) const { return d_pose_all + (size_t) (it % POSE_SLOTS) * (1 + ncomp) * 12; }
+    cudaStream_t stream_real = nullptr;              // the real chain of the ICP runs ahead of the derivative kernels (icp.cu)
+    cudaEvent_t ev_icp_start = nullptr;              // inputs of the ICP (maps, initial pose, cleared status) are ready
     float *h_pose = nullptr;                         // pinned staging of the same
     std::vector<float> gt_poses;  // [n][16] camera-to-world, KinectFusionReconstruction.h:36
     bool use_gt_pose = false;     // flag_use_gtPose, KinectFusionReconstruction.cpp:69
@@ -204,7 +208,9 @@ xs_kinfu *xs_kinfu_create(const xs_config *cfg, int comps, int dirs, const float
     for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&k->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&k->ev_icp, cudaEventDisableTiming);
     const size_t pose_floats = (size_t) (1 + k->ncomp) * 12;
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc((void **) &k->d_pose[i], pose_floats * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **) &k->d_pose_all, xs_kinfu::POSE_SLOTS * pose_floats * sizeof(float));
+    if (e == cudaSuccess) e = cudaStreamCreate(&k->stream_real);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&k->ev_icp_start, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost((void **) &k->h_pose, pose_floats * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void **) &k->d_status, 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost((void **) &k->h_status, 2 * sizeof(int));
@@ -236,8 +242,10 @@ void xs_kinfu_destroy(xs_kinfu *k) {
     }
     cudaFree(k->d_record);
     cudaFreeHost(k->h_record);
-    cudaFree(k->d_pose[0]);
-    cudaFree(k->d_pose[1]);
+    if (k->stream_real) cudaStreamSynchronize(k->stream_real);
+    cudaFree(k->d_pose_all);
+    if (k->ev_icp_start) cudaEventDestroy(k->ev_icp_start);
+    if (k->stream_real) cudaStreamDestroy(k->stream_real);
     cudaFreeHost(k->h_pose);
     cudaFree(k->d_status);
     cudaFreeHost(k->h_status);
@@ -296,8 +304,14 @@ int xs_kinfu_pose_estimate(xs_kinfu *k) {
             h[9 + i] = q == 0 ? tprev.v[i].v : tprev.v[i].d[q - 1];
         }
     }
-    KCUDA(cudaMemcpyAsync(k->d_pose[0], k->h_pose, pose_floats * sizeof(float), cudaMemcpyHostToDevice, k->stream));
+    KCUDA(cudaMemcpyAsync(k->d_pose_slot(0), k->h_pose, pose_floats * sizeof(float), cudaMemcpyHostToDevice, k->stream));
     KCUDA(cudaMemsetAsync(k->d_status, 0, 2 * sizeof(int), k->stream));
+    // with derivative components the real chain (association + real step per iteration) runs ahead on its own stream
+    const bool split = ncomp > 0 && !getenv("XS_ICP_NO_SPLIT");
+    if (split) {
+        KCUDA(cudaEventRecord(k->ev_icp_start, k->stream));
+        KCUDA(cudaStreamWaitEvent(k->stream_real, k->ev_icp_start, 0));
+    }
     const size_t log_stride = (size_t) 27 * (1 + ncomp);
     if (k->log_icp && !k->d_icp_log) {
         KCUDA(cudaMalloc((void **) &k->d_icp_log, 16 * log_stride * sizeof(double)));
@@ -307,16 +321,19 @@ int xs_kinfu_pose_estimate(xs_kinfu *k) {
     for (int level = c.num_levels - 1; level >= 0; --level) {
         const int rows = c.height >> level, cols = c.width >> level;
         for (int iter = 0; iter < k->icp_iterations[level]; ++iter, ++it) {
-            const int rc = icp_iteration_async(k->d_pose[it & 1], k->vmaps_curr[level], k->nmaps_curr[level], &prev_pose,
+            const int rc = icp_iteration_async(k->d_pose_slot(it), k->vmaps_curr[level], k->nmaps_curr[level], &prev_pose,
                                                level_intr(k->intr, level), k->vmaps_prev[level], k->nmaps_prev[level], rows,
-                                               cols, k->comps, k->dirs, c.dist_thres, k->angle_thres, k->d_pose[(it + 1) & 1],
+                                               cols, k->comps, k->dirs, c.dist_thres, k->angle_thres, k->d_pose_slot(it + 1),
                                                k->solve_mode, k->d_status,
                                                k->log_icp && it < 16 ? k->d_icp_log + (size_t) it * log_stride : nullptr,
-                                               k->stream);
-            if (rc != XS_OK) return 0;
+                                               k->stream, split ? k->stream_real : nullptr, it);
+            if (rc != XS_OK) {
+                cudaStreamSynchronize(k->stream_real);
+                return 0;
+            }
         }
     }
-    KCUDA(cudaMemcpyAsync(k->h_pose, k->d_pose[it & 1], pose_floats * sizeof(float), cudaMemcpyDeviceToHost, k->stream));
+    KCUDA(cudaMemcpyAsync(k->h_pose, k->d_pose_slot(it), pose_floats * sizeof(float), cudaMemcpyDeviceToHost, k->stream));
     KCUDA(cudaMemcpyAsync(k->h_status, k->d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, k->stream));
     if (k->log_icp)
         KCUDA(cudaMemcpyAsync(k->h_icp_log, k->d_icp_log, (size_t) (it < 16 ? it : 16) * log_stride * sizeof(double),
