@@ -109,7 +109,11 @@ struct SolveParams {
     int dirs, ncomp, solve_mode;
     int deriv_only;        // the real part of the step is owned by another launch (split chains): only the derivative
                            // components of pose_out are written, the status flags are read but not set
+    double *real_cache;    // split chains, [REAL_CACHE]: Cholesky factor (36), reciprocal pivots (6) and real solution (6) of
+                           // this iteration, stored by the real step and loaded by the derivative tails (which then skip the
+                           // determinant guard - the real step has already set the status - the factorisation and the real solve)
 };
+constexpr int REAL_CACHE = 48;
 template <int C> __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, const double *real_sums,
                                                                   const double *comp_sums);
 
@@ -769,17 +773,39 @@ __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, co
     }
     double A[6][6], b[6];
     unpack_sums(real_sums, A, b);
-    const double det = det6_dev(A);
-    if (fabs(det) < 1e-15 || isnan(det)) {
-        // every thread of every block computes the same det and takes this branch; the flag is only read at kernel
-        // entry by later launches
-        if (owns_real) P.status[1] = isnan(det) ? 2 : 1;
-        return;
-    }
     Chol6 F;
-    chol6_factor(A, F);
     double xr[6];
-    chol6_solve(F, b, xr);  // zero-seed solve: the canonical real part
+    if (P.deriv_only && P.real_cache) {
+        // the real step of this iteration has completed (stream order): a degenerate system was caught by the status test
+        // above; its factor and solution are loaded instead of being recomputed
+        const double *rc = P.real_cache;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) F.L[i][j] = __ldcg(rc + i * 6 + j);
+            F.inv[i] = __ldcg(rc + 36 + i);
+            xr[i] = __ldcg(rc + 42 + i);
+        }
+    } else {
+        const double det = det6_dev(A);
+        if (fabs(det) < 1e-15 || isnan(det)) {
+            // every thread of every block computes the same det and takes this branch; the flag is only read at kernel
+            // entry by later launches
+            if (owns_real) P.status[1] = isnan(det) ? 2 : 1;
+            return;
+        }
+        chol6_factor(A, F);
+        chol6_solve(F, b, xr);  // zero-seed solve: the canonical real part
+        if (owns_real && P.real_cache) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) P.real_cache[i * 6 + j] = F.L[i][j];
+                P.real_cache[36 + i] = F.inv[i];
+                P.real_cache[42 + i] = xr[i];
+            }
+        }
+    }
     J x[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = jconst<C, 1>((float) xr[i]);
@@ -876,6 +902,7 @@ struct IcpScratch {
     // and the event that marks the real chain's iteration as complete
     static constexpr int MAX_SLOTS = 16;
     cudaEvent_t ev_real[MAX_SLOTS] = {};
+    double *d_real_cache = nullptr;  // [MAX_SLOTS][REAL_CACHE]
     size_t cap_dpart = 0;
     int max_blocks = 296;
     // CUDA-event brackets of the derivative kernel launches since the last reset (roofline timing, bench.py)
@@ -1017,6 +1044,11 @@ int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, cons
     SolveParams S;
     S.sums = P.sums;
     S.deriv_only = split ? 1 : 0;
+    S.real_cache = nullptr;
+    if (split) {
+        if (!g_icp.d_real_cache) XS_CUDA(cudaMalloc(&g_icp.d_real_cache, (size_t) IcpScratch::MAX_SLOTS * REAL_CACHE * sizeof(double)));
+        S.real_cache = g_icp.d_real_cache + (size_t) slot * REAL_CACHE;
+    }
     S.pose_in = d_pose_curr;
     S.pose_out = d_pose_out;
     S.status = d_status;

@@ -56,7 +56,8 @@ struct xs_kinfu {
     float angle_thres;
     xs_volume *volume = nullptr;
     cudaStream_t stream = nullptr;
-    uint16_t *d_depth = nullptr;
+    uint16_t *d_depth2[2] = {nullptr, nullptr};  // uploaded host frames, alternating (the previous frame may still be integrating)
+    int depth_idx = 0;
     uint16_t *h_depth = nullptr;  // pinned staging
     std::vector<float *> depths, vmaps_curr, nmaps_curr, vmaps_prev, nmaps_prev;
     float *d_record = nullptr, *h_record = nullptr;  // [(1+ncomp)][16]
@@ -72,7 +73,9 @@ struct xs_kinfu {
     bool log_icp = false;
     double *d_icp_log = nullptr, *h_icp_log = nullptr;  // [max 16 iterations][27*(1+ncomp)] sums per iteration
     std::vector<double> icp_log;
-    cudaEvent_t ev[5];
+    cudaEvent_t ev[2][6];  // stage brackets ([5] = the pipeline's stream takes over after the head), two sets: a deferred frame is collected after the next frame's head is queued
+    int ev_cur = 0;        // set of the frame being queued / last queued
+    cudaEvent_t ev_head = nullptr;  // the early head (upload + surface measurement on stream_real) is complete
     float ms[5] = {0, 0, 0, 0, 0};
     long long launches[5] = {0, 0, 0, 0, 0};
     unsigned long long stats[4] = {0, 0, 0, 0};
@@ -122,8 +125,14 @@ void set_ctx(const xs_kinfu *k) {
 // After the frame's work has completed on the stream: integration statistics and per-stage device times.
 void collect_frame(xs_kinfu *k) {
     xs_volume_finish_frame(k->volume, k->stats);
-    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&k->ms[i], k->ev[i], k->ev[i + 1]);
-    cudaEventElapsedTime(&k->ms[4], k->ev[0], k->ev[4]);
+    cudaEvent_t *ev = k->ev[k->ev_cur];
+    // surface: head (in deferred mode it may have run beside the previous frame's raycast, on the second stream); icp,
+    // integrate, raycast: on the pipeline's stream from the point where it takes over; total = their sum
+    cudaEventElapsedTime(&k->ms[0], ev[0], ev[1]);
+    cudaEventElapsedTime(&k->ms[1], ev[5], ev[2]);
+    cudaEventElapsedTime(&k->ms[2], ev[2], ev[3]);
+    cudaEventElapsedTime(&k->ms[3], ev[3], ev[4]);
+    k->ms[4] = k->ms[0] + k->ms[1] + k->ms[2] + k->ms[3];
     k->launches[4] = k->launches[0] + k->launches[1] + k->launches[2] + k->launches[3];
 }
 
@@ -190,7 +199,7 @@ xs_kinfu *xs_kinfu_create(const xs_config *cfg, int comps, int dirs, const float
     k->vmaps_prev.assign(L, nullptr);
     k->nmaps_prev.assign(L, nullptr);
     const size_t px = (size_t) cfg->width * cfg->height;
-    if (e == cudaSuccess) e = cudaMalloc((void **) &k->d_depth, px * sizeof(uint16_t));
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc((void **) &k->d_depth2[i], px * sizeof(uint16_t));
     if (e == cudaSuccess) e = cudaMallocHost((void **) &k->h_depth, px * sizeof(uint16_t));
     for (int i = 0; i < L && e == cudaSuccess; ++i) {  // AllocateBuffers, :84-92
         const size_t r = cfg->height >> i, c = cfg->width >> i;
@@ -205,7 +214,8 @@ xs_kinfu *xs_kinfu_create(const xs_config *cfg, int comps, int dirs, const float
     const size_t rec = (size_t) (1 + k->ncomp) * 16;
     if (e == cudaSuccess) e = cudaMalloc((void **) &k->d_record, rec * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost((void **) &k->h_record, rec * sizeof(float));
-    for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&k->ev[i]);
+    for (int i = 0; i < 12 && e == cudaSuccess; ++i) e = cudaEventCreate(&k->ev[i / 6][i % 6]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&k->ev_head, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&k->ev_icp, cudaEventDisableTiming);
     const size_t pose_floats = (size_t) (1 + k->ncomp) * 12;
     if (e == cudaSuccess) e = cudaMalloc((void **) &k->d_pose_all, xs_kinfu::POSE_SLOTS * pose_floats * sizeof(float));
@@ -231,7 +241,8 @@ void xs_kinfu_destroy(xs_kinfu *k) {
     if (!k) return;
     if (k->stream) cudaStreamSynchronize(k->stream);
     xs_volume_destroy(k->volume);
-    cudaFree(k->d_depth);
+    cudaFree(k->d_depth2[0]);
+    cudaFree(k->d_depth2[1]);
     cudaFreeHost(k->h_depth);
     for (size_t i = 0; i < k->depths.size(); ++i) {
         cudaFree(k->depths[i]);
@@ -251,26 +262,29 @@ void xs_kinfu_destroy(xs_kinfu *k) {
     cudaFreeHost(k->h_status);
     cudaFree(k->d_icp_log);
     cudaFreeHost(k->h_icp_log);
-    for (int i = 0; i < 5; ++i)
-        if (k->ev[i]) cudaEventDestroy(k->ev[i]);
+    for (int i = 0; i < 12; ++i)
+        if (k->ev[i / 6][i % 6]) cudaEventDestroy(k->ev[i / 6][i % 6]);
+    if (k->ev_head) cudaEventDestroy(k->ev_head);
     if (k->ev_icp) cudaEventDestroy(k->ev_icp);
     if (k->stream) cudaStreamDestroy(k->stream);
     delete k;
 }
 
 // SurfaceMeasure, KinectFusionReconstruction.cpp:280-299
-int xs_kinfu_surface_measure(xs_kinfu *k, const uint16_t *d_depth) {
+static int surface_measure_on(xs_kinfu *k, const uint16_t *d_depth, cudaStream_t stream);
+int xs_kinfu_surface_measure(xs_kinfu *k, const uint16_t *d_depth) { return k ? surface_measure_on(k, d_depth, k->stream) : XS_ERR_ARG; }
+static int surface_measure_on(xs_kinfu *k, const uint16_t *d_depth, cudaStream_t stream) {
     const xs_config &c = k->cfg;
     if (c.width <= 0 || c.height <= 0) {
         set_error("error::KinectFusionReconstruction, not created yet");
         return XS_ERR_ARG;
     }
-    int rc = xs_bilateral_filter(d_depth, c.width * sizeof(uint16_t), c.height, c.width, k->depths[0], k->stream);
+    int rc = xs_bilateral_filter(d_depth, c.width * sizeof(uint16_t), c.height, c.width, k->depths[0], stream);
     for (int i = 1; i < c.num_levels && rc == XS_OK; ++i)
-        rc = xs_pyr_down(k->depths[i - 1], c.height >> (i - 1), c.width >> (i - 1), k->depths[i], k->stream);
+        rc = xs_pyr_down(k->depths[i - 1], c.height >> (i - 1), c.width >> (i - 1), k->depths[i], stream);
     for (int i = 0; i < c.num_levels && rc == XS_OK; ++i) {
-        rc = xs_create_vmap(level_intr(k->intr, i), k->depths[i], c.height >> i, c.width >> i, k->vmaps_curr[i], k->stream);
-        if (rc == XS_OK) rc = xs_create_nmap(k->vmaps_curr[i], c.height >> i, c.width >> i, k->nmaps_curr[i], k->stream);
+        rc = xs_create_vmap(level_intr(k->intr, i), k->depths[i], c.height >> i, c.width >> i, k->vmaps_curr[i], stream);
+        if (rc == XS_OK) rc = xs_create_nmap(k->vmaps_curr[i], c.height >> i, c.width >> i, k->nmaps_curr[i], stream);
     }
     return rc;
 }
@@ -439,29 +453,46 @@ int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_devi
     const xs_config &c = k->cfg;
     const size_t bytes = (size_t) c.width * c.height * sizeof(uint16_t);
     const uint16_t *d_depth = depth;
-    // when the pinned staging frame is known to be free (its upload completed before the previous frame's ICP result was
-    // read), the host copy is made before waiting for a deferred frame, i.e. beside that frame's raycast
+    // Deferred mode with a frame in flight: the head of this frame (upload + surface measurement: it reads the new depth
+    // frame and writes the current-frame maps, which the integration / raycast still running do not touch) is queued on the
+    // second stream BEFORE waiting for that frame, so that it runs beside its raycast.
+    const bool early = k->pending;
+    cudaStream_t hs = early ? k->stream_real : k->stream;
+    cudaEvent_t *ev = k->ev[k->ev_cur ^ 1];
+    // the pinned staging frame is free once its previous upload is known to be complete (ICP result read, or a full wait)
     const bool early_copy = !depth_on_device && k->h_depth_free;
     if (early_copy) std::memcpy(k->h_depth, depth, bytes);
-    if (finish_pending(k) != XS_OK) return 0;
+    if (!early || (!depth_on_device && !early_copy)) {
+        if (finish_pending(k) != XS_OK) return 0;
+        hs = k->stream;
+    }
     if (!depth_on_device) {
         // the upload is outside the reference's timed region (main.cpp:51-57) but inside bench.py's e2e region
         if (!early_copy) std::memcpy(k->h_depth, depth, bytes);
         k->h_depth_free = false;
-        if (cudaMemcpyAsync(k->d_depth, k->h_depth, bytes, cudaMemcpyHostToDevice, k->stream) != cudaSuccess) return 0;
-        d_depth = k->d_depth;
+        k->depth_idx ^= 1;  // the frame before this one may still be integrating from the other buffer
+        uint16_t *dd = k->d_depth2[k->depth_idx];
+        if (cudaMemcpyAsync(dd, k->h_depth, bytes, cudaMemcpyHostToDevice, hs) != cudaSuccess) return 0;
+        d_depth = dd;
     }
     long long l0 = g_launches;
-    cudaEventRecord(k->ev[0], k->stream);
-    if (xs_kinfu_surface_measure(k, d_depth) != XS_OK) return 0;
-    cudaEventRecord(k->ev[1], k->stream);
+    cudaEventRecord(ev[0], hs);
+    if (surface_measure_on(k, d_depth, hs) != XS_OK) return 0;
+    cudaEventRecord(ev[1], hs);
+    if (hs != k->stream) {
+        cudaEventRecord(k->ev_head, hs);
+        if (finish_pending(k) != XS_OK) return 0;  // collects the previous frame from its own event set
+        cudaStreamWaitEvent(k->stream, k->ev_head, 0);
+    }
+    cudaEventRecord(ev[5], k->stream);
+    k->ev_cur ^= 1;
     k->launches[0] = g_launches - l0;
     l0 = g_launches;
     k->next_depth = d_depth;
     const int aligned = xs_kinfu_pose_estimate(k);
     k->next_depth = nullptr;
     const auto dbg_t0 = std::chrono::steady_clock::now();
-    cudaEventRecord(k->ev[2], k->stream);
+    cudaEventRecord(ev[2], k->stream);
     k->launches[1] = g_launches - l0;
     l0 = g_launches;
     if (k->frame_id > 0 && !aligned) {
@@ -474,7 +505,7 @@ int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_devi
     xs_volume_set_pipelined(k->volume, 1);
     const int rc_int = xs_kinfu_integrate_frame(k, d_depth);
     const auto dbg_t1 = std::chrono::steady_clock::now();
-    cudaEventRecord(k->ev[3], k->stream);
+    cudaEventRecord(ev[3], k->stream);
     k->launches[2] = g_launches - l0;
     l0 = g_launches;
     const int rc_ray = rc_int == XS_OK ? xs_kinfu_calculate_point_cloud(k) : rc_int;
@@ -495,7 +526,7 @@ int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_devi
             for (int j = 0; j < 4; ++j)
                 k->h_record[(size_t) q * 16 + i * 4 + j] = q == 0 ? k->world2camera.m[i][j].v : k->world2camera.m[i][j].d[q - 1];
     cudaMemcpyAsync(k->d_record, k->h_record, (size_t) (1 + k->ncomp) * 16 * sizeof(float), cudaMemcpyHostToDevice, k->stream);
-    cudaEventRecord(k->ev[4], k->stream);
+    cudaEventRecord(ev[4], k->stream);
     k->launches[3] = g_launches - l0;
     if (k->deferred) {  // pose and status are final (the ICP result was read on the host); the volume and the maps follow
         k->pending = true;
