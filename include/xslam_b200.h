@@ -240,7 +240,9 @@ float *xs_kinfu_pose_record_device(xs_kinfu *k);
 /* gt_poses + flag_use_gtPose (KinectFusionReconstruction.h:36,82 / .cpp:69,164-166,239-247): with use_gt_pose != 0 frames are
  * fused at the given camera-to-world poses (row-major 4x4 per frame, real) and ICP is skipped (mapping mode). */
 int xs_kinfu_set_gt_poses(xs_kinfu *k, const float *poses16, int n, int use_gt_pose);
-/* the cudaStream_t every kernel of this pipeline object is launched on (for event timing and stream-ordered consumers) */
+/* the cudaStream_t of this pipeline object: every result a consumer can observe (maps, volume, pose record) is ordered on it
+ * (for event timing and stream-ordered consumers).  Work that depends on no derivative component - the real chain of the ICP,
+ * the head of a deferred frame - runs on an internal second stream and is joined back by events. */
 void *xs_kinfu_stream(xs_kinfu *k);
 
 /* ---------------------------------------------------------------- outputs & synthetic input (a13, f1) */
