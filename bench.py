@@ -382,6 +382,9 @@ def run_ours(args, xs, rank, world, local_rank):
                                "kernel_ms": int_ms, "updated_voxels_per_launch": upd / K},
         "wall_ms_per_step": t_wall / K * 1e3,
         "stages_ms_per_step": {n: v / K for n, v in stage_ms.items()},
+        "stages_note": ("icp / integrate / raycast: CUDA-event brackets on the pipeline's stream; surface: the next frame's head runs "
+                        "on the second stream beside the previous frame's raycast (deferred mode), total = sum of the four") if deferred
+                       else "CUDA-event brackets on the pipeline's stream",
         "stages_algorithmic_GBps": {n: (abytes[n] / K) / (stage_ms[n] / K * 1e-3) / 1e9 if stage_ms[n] > 0 else 0.0 for n in abytes},
         "frame_algorithmic_bytes": sum(abytes.values()) / K,
     }

@@ -222,8 +222,10 @@ int xs_kinfu_get_pose_c2w(const xs_kinfu *k, float *out16);
 xs_volume *xs_kinfu_volume(xs_kinfu *k);
 /* which: 0 depth pyramid, 1 vmap_curr, 2 nmap_curr, 3 vmap_g_prev, 4 nmap_g_prev; device pointer + dims */
 const float *xs_kinfu_map(const xs_kinfu *k, int which, int level, int *rows, int *cols, int *ncomp);
-/* per-stage device times of the last frame (ms): surface, icp, integrate, raycast+resize, total;
- * followed by per-stage kernel-launch counts (5 more floats) */
+/* per-stage device times of the last collected frame (ms): surface, icp, integrate, raycast+resize, total (= their sum);
+ * followed by per-stage kernel-launch counts (5 more floats).  icp / integrate / raycast are brackets on the pipeline's
+ * stream; in deferred mode the surface measurement of a frame runs beside the previous frame's raycast (second stream), so its
+ * bracket is not part of the frame's critical path. */
 int xs_kinfu_get_times(const xs_kinfu *k, float *ms10);
 /* ICP log of the last frame: iterations x (1+ncomp) x 42 doubles (A 36 column-major, b 6).  The Gauss-Newton loop
  * runs on the device without host round trips; the per-iteration normal equations are only downloaded when the log
