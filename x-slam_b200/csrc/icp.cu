@@ -25,7 +25,8 @@
 // - depends on no derivative component, so the real chain of a frame (icp_assoc_kernel + a one-thread icp_solve_kernel per
 // iteration) runs ahead on a second stream, leaving record, sums and real pose of every iteration in a slot of its own; the
 // derivative kernels follow back to back on the pipeline's stream and their tail updates derivative components only
-// (SolveParams::deriv_only).  The latency-bound association launches leave the critical path.
+// (SolveParams::deriv_only).  The derivative kernel fills every SM, so the real chain advances in the tails of the derivative
+// launches (where the SMs would idle behind the one-thread solves): about a third of its latency is hidden.
 // Instead of the reference's 27 sequential 256-thread shared-memory tree reductions per direction, the summation
 // order is fixed by construction, so results are deterministic run to run.
 #include "xs_common.cuh"
