@@ -1,0 +1,114 @@
+"""CPU test of the host jet algebra (x-slam_b200/csrc/host_jet.h): the 4x4 / 3x3 cofactor inverses, products and axis
+rotations the frame loop evaluates on the host between ICP and integration (KinectFusionReconstruction.cpp:167-173,231,
+248-258,305-320), for first-order (CSFD) and second-order (DCSFD: eps1, eps2, eps1eps2) components, against the analytic
+matrix derivatives in float64:
+
+    d(A^-1)      = -A^-1 dA A^-1
+    d12(A^-1)    = -A^-1 d12A A^-1 + A^-1 d1A A^-1 d2A A^-1 + A^-1 d2A A^-1 d1A A^-1
+    d12(A B)     = d12A B + A d12B + d1A d2B + d2A d1B
+    d12 R(theta) = R'(theta) d12theta + R''(theta) d1theta d2theta
+
+Tolerance: FP32 evaluation, 2e-5 of the largest entry of each component."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("hj") / "host_jet_harness")
+    subprocess.run(["g++", "-std=c++17", "-O3", "-o", exe, os.path.join(ROOT, "tests", "harness", "host_jet_harness.cpp")],
+                   check=True)
+    return exe
+
+
+def rigid(rng):
+    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    T = np.eye(4)
+    T[:3, :3] = q
+    T[:3, 3] = rng.standard_normal(3) * 2
+    return T
+
+
+def rot(axis, t, order=0):
+    """rotation about a coordinate axis and its first / second derivative with respect to the angle"""
+    s, c = {0: (np.sin(t), np.cos(t)), 1: (np.cos(t), -np.sin(t)), 2: (-np.sin(t), -np.cos(t))}[order]
+    R = np.zeros((3, 3))
+    for i in range(3):
+        R[i, i] = c if i != axis else (1.0 if order == 0 else 0.0)
+    a, b = (axis + 1) % 3, (axis + 2) % 3
+    R[a, b], R[b, a] = -s, s
+    return R
+
+
+def run(harness, comps, dirs, A, B, angle):
+    txt = "%d %d\n" % (comps, dirs) + "\n".join("%.9g" % x for x in np.concatenate([A.ravel(), B.ravel(), angle.ravel()]))
+    out = subprocess.run([harness], input=txt, capture_output=True, text=True, check=True).stdout.split()
+    v = np.array([float(x) for x in out])
+    n = 1 + comps * dirs
+    o = 0
+    res = []
+    for sz in (16, 16, 9, 9):
+        side = 4 if sz == 16 else 3
+        res.append(v[o:o + n * sz].reshape(n, side, side))
+        o += n * sz
+    assert o == v.size
+    return res
+
+
+def close(a, b, what):
+    scale = max(np.abs(b).max(), 1e-30)
+    assert np.abs(a - b).max() <= 2e-5 * scale, "%s: %g of %g" % (what, np.abs(a - b).max(), scale)
+
+
+@pytest.mark.parametrize("comps,dirs", [(1, 6), (3, 4), (3, 55)])
+def test_host_pose_algebra_matches_analytic_derivatives(harness, comps, dirs):
+    rng = np.random.default_rng(11 + comps + dirs)
+    n = comps * dirs
+    A = np.concatenate([rigid(rng)[None], rng.standard_normal((n, 4, 4))]).astype(np.float32).astype(np.float64)
+    B = np.concatenate([rigid(rng)[None], rng.standard_normal((n, 4, 4))]).astype(np.float32).astype(np.float64)
+    A[0, 3], B[0, 3] = (0, 0, 0, 1), (0, 0, 0, 1)
+    angle = np.concatenate([[0.37], rng.standard_normal(n)]).astype(np.float32).astype(np.float64)
+    inv, prod, inv3, rzyx = run(harness, comps, dirs, A, B, angle)
+
+    def groups():
+        if comps == 1:
+            for q in range(dirs):
+                yield (1 + q, None, None)
+        else:
+            for k in range(dirs):
+                yield (1 + 3 * k, 2 + 3 * k, 3 + 3 * k)
+
+    for M, got, tag in ((A, inv, "inverse4"), (A[:, :3, :3], inv3, "inverse3")):
+        Mi = np.linalg.inv(M[0])
+        close(got[0], Mi, tag + " real")
+        for i1, i2, i12 in groups():
+            close(got[i1], -Mi @ M[i1] @ Mi, tag + " first order")
+            if i2 is not None:
+                close(got[i2], -Mi @ M[i2] @ Mi, tag + " first order (eps2)")
+                close(got[i12], -Mi @ M[i12] @ Mi + Mi @ M[i1] @ Mi @ M[i2] @ Mi + Mi @ M[i2] @ Mi @ M[i1] @ Mi, tag + " second order")
+    close(prod[0], A[0] @ B[0], "product real")
+    for i1, i2, i12 in groups():
+        close(prod[i1], A[i1] @ B[0] + A[0] @ B[i1], "product first order")
+        if i2 is not None:
+            close(prod[i12], A[i12] @ B[0] + A[0] @ B[i12] + A[i1] @ B[i2] + A[i2] @ B[i1], "product second order")
+    # Rinc = Rz * Ry * Rx of one batched angle (KinectFusionReconstruction.cpp:215-218)
+    t = angle[0]
+    R = [rot(ax, t) for ax in (2, 1, 0)]
+    R1 = [rot(ax, t, 1) for ax in (2, 1, 0)]
+    R2 = [rot(ax, t, 2) for ax in (2, 1, 0)]
+    f0 = R[0] @ R[1] @ R[2]
+    f1 = R1[0] @ R[1] @ R[2] + R[0] @ R1[1] @ R[2] + R[0] @ R[1] @ R1[2]
+    f2 = (R2[0] @ R[1] @ R[2] + R[0] @ R2[1] @ R[2] + R[0] @ R[1] @ R2[2] +
+          2 * (R1[0] @ R1[1] @ R[2] + R1[0] @ R[1] @ R1[2] + R[0] @ R1[1] @ R1[2]))
+    close(rzyx[0], f0, "rotation real")
+    for i1, i2, i12 in groups():
+        close(rzyx[i1], f1 * angle[i1], "rotation first order")
+        if i2 is not None:
+            close(rzyx[i12], f1 * angle[i12] + f2 * angle[i1] * angle[i2], "rotation second order")
