@@ -30,8 +30,11 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--frames-per-step", type=int, default=10,
+                    help="a step is one batch of this many consecutive depth frames (each one ProcessFrame); the timed region "
+                         "is steps x frames-per-step frames so that it lasts ~1 s at the default flags")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--dirs", type=int, default=55)
@@ -151,15 +154,57 @@ def measured_hbm_peak():
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_port_frames(xs, cfg, n_frames, budget_s=25.0):
+# Everything in this section runs on the checker's side only (oracle/): it never imports the product package, so the
+# reference arm's process maps no x-slam_b200/*.so.
+REF_DEFAULTS = {  # Experiments/test_xkinect_fusion/configs/ICL_traj2.yaml:17-48 (the keys the frame loop reads)
+    "biInterpolate_threshold": 0.0, "trunc_logistic_k": 0, "flag_use_gtPose": False, "max_integration_weight": 100, "thres_range": 3,
+    "init_x": 3.2, "init_y": 3.2, "init_z": 3.2, "r_x": 0, "r_y": 0, "r_z": 0, "depth_width": 640, "depth_height": 480,
+    "fx": 481.20, "fy": -480.00, "cx": 319.50, "cy": 239.50, "num_levels": 3, "distThres": 0.10, "angleThres": 15, "frame_step": 1}
+H_STEP = 1e-7  # Internal.h:33
+
+
+def ref_cfg(res):
+    cfg = dict(REF_DEFAULTS)
+    cfg.update(tsdf_size_x=res, tsdf_size_y=res, tsdf_size_z=res, tsdf_voxel_size=7.68 / res)
+    return cfg
+
+
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core, so the value is set
+    explicitly before the OpenMP runtime of liboracle.so starts, and again through the runtime's own API."""
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except OSError:
+        pass
+    return cores
+
+
+def oracle_synth_depth(oracle, frame):
+    """The synthetic stream restated on the checker's side (oracle/synth_oracle.cpp), pinned bit for bit against the
+    product's generator by tests/test_bench_contract.py."""
+    pose = np.zeros((16,), np.float32)
+    oracle.lib.oracle_synth_pose(int(frame), pose.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+    out = np.zeros((480, 640), np.uint16)
+    c = REF_DEFAULTS
+    oracle.lib.oracle_synth_depth(pose.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), ctypes.c_float(c["fx"]), ctypes.c_float(c["fy"]),
+                                  ctypes.c_float(c["cx"]), ctypes.c_float(c["cy"]), 480, 640, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)))
+    return out
+
+
+def cpu_port_frames(cfg, n_frames, budget_s=25.0):
     """Times the CPU oracle port of the frame loop (one first-order complex direction per run, exactly the
-    reference's one-direction-per-run mode) with all host threads.  Returns (seconds per frame-direction, frames)."""
+    reference's one-direction-per-run mode) with all host threads.  Returns the seconds of each frame-pass."""
     from oracle import pyref
-    k = pyref.OracleKinfu(cfg, xs.pose_seeds_csfd()[0])
+    seed = np.zeros((4, 4), np.float32)
+    seed[0, 3] = H_STEP  # world2camera(0,3) += i h: the commented seeding line KinectFusionReconstruction.cpp:22
+    o = pyref.Oracle()
+    k = pyref.OracleKinfu(cfg, seed, oracle=o)
     times = []
     t_all = time.perf_counter()
     for f in range(n_frames):
-        d = xs.synth_depth(f)
+        d = oracle_synth_depth(o, f)
         t0 = time.perf_counter()
         ok = k.process_frame(d)
         times.append(time.perf_counter() - t0)
@@ -168,7 +213,42 @@ def cpu_port_frames(xs, cfg, n_frames, budget_s=25.0):
     return times
 
 
-def ref_cuda_frames(xs, cfg, n_frames=4):
+def test_csfd_baseline():
+    """north_star's CPU baseline: the reference's host-side DeviceArray CSFD math as exercised by test_CSFD, on ONE host
+    thread (the program is single-threaded): wall time of the unmodified Experiments/test_CSFD binary at -O0 (the reference's
+    default build) and -O2, and consumed-result throughput of the unmodified DoubleComplex.cpp (oracle/_ref/libref_csfd.so):
+    the test's own chain f1(t*t, sin t) and the element-wise ops * / sqrt sin."""
+    from oracle import pyref
+    out = {"kind": "reference", "cores": 1, "unit": "bicomplex chain evaluations/s",
+           "what": "unmodified DeviceArray/src/DoubleComplex.cpp + Experiments/test_CSFD/main.cpp (oracle/_ref)"}
+    for tag, path in (("O0", pyref.REF_TEST_CSFD), ("O2", pyref.REF_TEST_CSFD + "_O2")):
+        if os.path.exists(path):
+            t0 = time.perf_counter()
+            r = subprocess.run([path], capture_output=True, text=True, timeout=120)
+            out["test_CSFD_%s_wall_s" % tag] = time.perf_counter() - t0
+            out["test_CSFD_%s_rc" % tag] = r.returncode
+    if not os.path.exists(pyref.REF_CSFD_PATH):
+        out["unavailable"] = "oracle/_ref/libref_csfd.so not built"
+        return out
+    ref = pyref.RefCsfd()
+    rng = np.random.default_rng(0)
+    n = 1 << 20
+    t = rng.uniform(0.1, 1.5, n).astype(np.float32)
+    rate, cs = ref.chain_bench(t, 1e-6, reps=4)
+    out["value"] = rate
+    out["sample"] = "4 x 2^20 evaluations of loss = f1(t*t, sin t) with seeded t (main.cpp:194-205), results summed (checksum %.6g)" % cs
+    a = np.stack([rng.uniform(0.5, 2.0, n), 1e-6 * rng.standard_normal(n), 1e-6 * rng.standard_normal(n), 1e-12 * rng.standard_normal(n)], 1).astype(np.float32)
+    b = np.stack([rng.uniform(0.5, 2.0, n), 1e-6 * rng.standard_normal(n), 1e-6 * rng.standard_normal(n), 1e-12 * rng.standard_normal(n)], 1).astype(np.float32)
+    ops = {}
+    for op in ("mul", "div", "sqrt", "sin"):
+        t0 = time.perf_counter()
+        ref.apply(op, a, b if op in ("mul", "div") else None)
+        ops[op] = n / (time.perf_counter() - t0)
+    out["ops_per_s"] = ops
+    return out
+
+
+def ref_cuda_frames(xs, cfg, n_frames=24):
     """The reference's own CUDA kernels (oracle/_ref/libxslam_ref.so: unmodified XKinectFusion/src/*.cu recompiled for
     sm_100a, driven by the restated orchestrator) on the same GPU: one first-order complex direction per pass, exactly
     how the reference would produce k directions (k passes).  Returns seconds per pass-frame (frames 1.. only)."""
@@ -189,23 +269,38 @@ def ref_cuda_frames(xs, cfg, n_frames=4):
     return times
 
 
-def run_reference(args, xs, rank):
+def distinct_planes(args):
+    """Derivative planes a differentiated frame of the workload consists of, counted once: the DCSFD Hessian of n parameters
+    has n first-order and n(n+1)/2 second-order components (65 at n = 10, i.e. 55 bicomplex directions)."""
+    if args.comps == 1:
+        return args.dirs
+    n = int(round((np.sqrt(8 * args.dirs + 1) - 1) / 2))
+    return n + args.dirs if n * (n + 1) // 2 == args.dirs else 3 * args.dirs
+
+
+def run_reference(args, rank):
     """--impl reference: the CPU path (oracle port of the reference's frame loop; the reference itself has no CPU
-    implementation of this path and its orchestrator cannot be built offline) on the host cores."""
+    implementation of this path and its orchestrator cannot be built offline) on all host cores.  A step is ONE pass of the
+    frame loop over one frame with ONE complex perturbation direction - the reference's own mode of operation (one
+    imaginary part per run) and a bounded sample of the workload.  steps / ms_per_step are what was timed; `value` scales
+    the measured pass time by the number of passes a differentiated frame needs (every distinct derivative plane is at
+    least one pass), stated in `passes_per_differentiated_frame`."""
     if rank != 0:
         return
-    cfg = workload_cfg(xs, args.res)
-    cores = os.cpu_count() or 1
+    cores = use_all_host_threads()
+    cfg = ref_cfg(args.res)
     total = args.warmup + args.steps
-    times = cpu_port_frames(xs, cfg, total, budget_s=240.0)
+    times = cpu_port_frames(cfg, total, budget_s=240.0)
     timed = times[args.warmup:] if len(times) > args.warmup else times[-1:]
-    per_dir = float(np.mean(timed))
-    ncomp_dirs = args.dirs * (1 if args.comps == 1 else 3)  # a bicomplex direction carries 3 derivative components
-    fps = 1.0 / (per_dir * ncomp_dirs)
-    sample = ("%d frames of the 640x480 / %d^3 sequence, ONE first-order complex direction per pass (the reference's "
-              "one-direction-per-run mode); value = 1 / (%d derivative components x measured pass time)" % (len(timed), args.res, ncomp_dirs))
+    per_pass = float(np.mean(timed))
+    passes = distinct_planes(args)
+    fps = 1.0 / (per_pass * passes)
+    sample = ("%d frame-passes of the 640x480 / %d^3 sequence timed, ONE first-order complex direction per pass (the reference's "
+              "one-direction-per-run mode, %d host threads); value = 1 / (%d passes per differentiated frame x measured pass time)"
+              % (len(timed), args.res, cores, passes))
     line = {"impl": "reference", "metric": "differentiated_frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": len(timed), "warmup": min(args.warmup, len(times) - len(timed)), "ms_per_step": per_dir * ncomp_dirs * 1e3,
+            "steps": len(timed), "warmup": min(args.warmup, len(times) - len(timed)), "ms_per_step": per_pass * 1e3,
+            "step_is": "one frame-pass with one complex direction (bounded sample)", "passes_per_differentiated_frame": passes,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "icl_synth_640x480_tsdf%d_dcsfd%d" % (args.res, args.dirs)},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
@@ -238,11 +333,16 @@ def run_ours(args, xs, rank, world, local_rank):
     send = torch.zeros((rec_len,), dtype=torch.float32, device="cuda") if world > 1 else None
     rec_view = torch.as_tensor(DeviceRecord(k.pose_record_device_ptr(), (1 + len(mine) * args.comps) * 16), device="cuda")
 
-    W, K = args.warmup, args.steps
-    n_frames = W + 2 * K
-    frames = [xs.synth_depth(f) for f in range(n_frames)]
-    dev_frames = [torch.from_numpy(f.astype(np.int16)).cuda() for f in frames[:W + K]]
-    pinned = [torch.from_numpy(f.astype(np.int16)).pin_memory() for f in frames[W + K:]]
+    # A step is one batch of FPS consecutive frames (each one ProcessFrame).  The synthetic trajectory is a closed loop of
+    # period 300 frames, so frame f of the stream is frame f % 300 of the generator: at most 300 distinct frames are rendered
+    # on the host, resident copies live in HBM (timed region 1) and in pinned host memory (timed region 2).
+    W, K, FPS = args.warmup, args.steps, max(1, args.frames_per_step)
+    n_stream = (W + 2 * K) * FPS
+    PERIOD = 300
+    frames = [xs.synth_depth(f) for f in range(min(n_stream, PERIOD))]
+    dev_frames = [torch.from_numpy(f.astype(np.int16)).cuda() for f in frames]
+    pinned = [torch.from_numpy(f.astype(np.int16)).pin_memory() for f in frames]
+    frame_no = [0]  # index of the next frame of the stream
 
     lib_stream = torch.cuda.ExternalStream(k.stream_ptr())
     deferred = not args.sync_frames
@@ -274,8 +374,13 @@ def run_ours(args, xs, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(W):
-        step(dev_frames[i])
+    def next_frame(pool):
+        f = pool[frame_no[0] % len(pool)]
+        frame_no[0] += 1
+        return f
+
+    for i in range(W * FPS):
+        step(next_frame(dev_frames))
     # ---------------- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -303,8 +408,9 @@ def run_ours(args, xs, rank, world, local_rank):
         kern_ms += lib.xs_volume_last_integrate_ms(vol)
         upd += k.stats()[0]
 
-    for i in range(K):
-        step(dev_frames[W + i])
+    NF = K * FPS  # frames in each timed region
+    for i in range(NF):
+        step(next_frame(dev_frames))
         # deferred mode: frame i is still integrating / raycasting here; the getters describe frame i - 1 (collected at the
         # start of this step), so the per-stage sums lag by one frame and the last frame is collected after the final sync
         if not deferred or i > 0:
@@ -329,9 +435,9 @@ def run_ours(args, xs, rank, world, local_rank):
     # ---------------- timed region 2: end to end through the public call with HOST buffers
     sync()
     t0 = time.perf_counter()
-    for i in range(K):
-        step(pinned[i].numpy().view(np.uint16))
-        w2c = k.world2camera  # the step's result, read on the host
+    for i in range(NF):
+        step(next_frame(pinned).numpy().view(np.uint16))
+        w2c = k.world2camera  # the frame's result, read on the host
     sync()
     t_e2e = time.perf_counter() - t0
     clocks = sampler.summary()
@@ -347,8 +453,8 @@ def run_ours(args, xs, rank, world, local_rank):
     if world == 1 and args.res == 512 and args.dirs == 55 and args.comps == 3:
         TRAFFIC.update(TRAFFIC_55)
     peak, peak_src = measured_hbm_peak()
-    int_bytes = abytes["integrate"] / K
-    int_ms = kern_ms / K
+    int_bytes = abytes["integrate"] / NF
+    int_ms = kern_ms / NF
     achieved = int_bytes / (int_ms * 1e-3) / 1e9 if int_ms > 0 else 0.0
     # dominant kernel of the step: icp_deriv_kernel at pyramid level 0 (5 launches per frame).  Algorithmic bytes per
     # launch: per pixel the real current + previous maps (48 B) and 24 B per derivative
@@ -362,41 +468,64 @@ def run_ours(args, xs, rank, world, local_rank):
     h2d = 640 * 480 * 2 + (1 + ncomp_local) * 48 + ncomp_local * 48 * 3 + (1 + ncomp_local) * 64
     d2h = (1 + ncomp_local) * 48 + 8 + 32
     line = {
-        "metric": "differentiated_frames_per_s", "value": K / t_dev, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "metric": "differentiated_frames_per_s", "value": NF / t_dev, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_dev / K * 1e3, "frames_per_step": FPS, "ms_per_frame": t_dev / NF * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "icl_synth_640x480_tsdf%d_dcsfd%d" % (args.res, args.dirs), "depth": "640x480 uint16 mm",
+        "config": {"workload": "icl_synth_640x480_tsdf%d_dcsfd%d" % (args.res, args.dirs), "step": "one batch of %d consecutive depth frames, each one ProcessFrame" % FPS,
+                   "depth": "640x480 uint16 mm",
                    "tsdf": "%d^3 @ %.4f m" % (args.res, 7.68 / args.res), "directions": args.dirs, "components_per_direction": args.comps,
                    "derivative_planes": args.dirs * args.comps, "directions_per_rank": max_dirs, "sharding": "directions over ranks, real state replicated",
                    "frame_sync": "deferred (end-of-frame wait at the start of the next ProcessFrame; ICP result read on the host every frame)" if deferred else "every frame",
                    "l2": "per-step working set (volume %.1f GB/rank) >> 126 MB L2, no flush needed" % (lib.xs_volume_bytes(vol) / 1e9)},
-        "e2e": {"value": K / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": NF / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d * FPS, "d2h_bytes_per_step": d2h * FPS},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "icp_deriv_kernel<%d> (pyramid level 0; %.0f%% of the step)" % (args.comps, 100 * 5 * icp_kernel_ms / (t_dev / K * 1e3)),
+        "roofline": {"bound": "hbm", "kernel": "icp_deriv_kernel<%d> (pyramid level 0; %.0f%% of the step)" % (args.comps, 100 * 5 * icp_kernel_ms / (t_dev / NF * 1e3)),
                      "achieved": icp_achieved, "peak": peak, "unit": "GB/s", "frac": icp_achieved / peak, "traffic": TRAFFIC.get("icp_deriv"),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": icp_bytes, "kernel_ms": icp_kernel_ms, "launches_timed": icp_n,
                      "fp32_floor_note": "this kernel is co-bound by the FP32 FMA pipe (DESIGN.md 5.2)"},
         "roofline_integrate": {"bound": "hbm", "kernel": "integrate_kernel<%d>" % args.comps, "achieved": achieved, "peak": peak, "unit": "GB/s",
                                "frac": achieved / peak, "traffic": TRAFFIC.get("integrate"), "algorithmic_bytes_per_launch": int_bytes,
-                               "kernel_ms": int_ms, "updated_voxels_per_launch": upd / K},
-        "wall_ms_per_step": t_wall / K * 1e3,
-        "stages_ms_per_step": {n: v / K for n, v in stage_ms.items()},
+                               "kernel_ms": int_ms, "updated_voxels_per_launch": upd / NF},
+        "wall_ms_per_frame": t_wall / NF * 1e3,
+        "stages_ms_per_frame": {n: v / NF for n, v in stage_ms.items()},
         "stages_note": ("icp / integrate / raycast: CUDA-event brackets on the pipeline's stream; surface: the next frame's head runs "
                         "on the second stream beside the previous frame's raycast (deferred mode), total = sum of the four") if deferred
                        else "CUDA-event brackets on the pipeline's stream",
-        "stages_algorithmic_GBps": {n: (abytes[n] / K) / (stage_ms[n] / K * 1e-3) / 1e9 if stage_ms[n] > 0 else 0.0 for n in abytes},
-        "frame_algorithmic_bytes": sum(abytes.values()) / K,
+        "stages_algorithmic_GBps": {n: abytes[n] / (stage_ms[n] * 1e-3) / 1e9 if stage_ms[n] > 0 else 0.0 for n in abytes},
+        "frame_algorithmic_bytes": sum(abytes.values()) / NF,
     }
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        times = cpu_port_frames(xs, cfg, 3, budget_s=30.0)
+        cores = use_all_host_threads()
+        times = cpu_port_frames(ref_cfg(args.res), 40, budget_s=20.0)
         per_dir = float(np.mean(times[1:])) if len(times) > 1 else float(times[0])
-        ncd = args.dirs * (1 if args.comps == 1 else 3)
+        ncd = distinct_planes(args)
         line["cpu_baseline"] = {"value": 1.0 / (per_dir * ncd), "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": "%d frames, 640x480 / %d^3, ONE first-order complex direction per pass (reference's "
-                                          "one-direction-per-run mode, all host threads); scaled by %d derivative components" %
-                                          (max(len(times) - 1, 1), args.res, ncd), "seconds_per_direction_frame": per_dir}
+                                "sample": "%d frame-passes timed, 640x480 / %d^3, ONE first-order complex direction per pass (reference's "
+                                          "one-direction-per-run mode, all host threads); value = 1 / (%d passes per differentiated frame "
+                                          "x measured pass time)" % (max(len(times) - 1, 1), args.res, ncd),
+                                "seconds_per_direction_frame": per_dir, "passes_per_differentiated_frame": ncd}
+        # north_star's own CPU baseline: the host DeviceArray CSFD math of test_CSFD (unmodified reference sources), beside the
+        # same chain on the packed-SoA device arrays (xs_dc_chain)
+        tc = test_csfd_baseline()
+        try:
+            from xslam_b200 import ops
+            n = 1 << 24
+            tt = torch.rand(n, device="cuda") * 1.4 + 0.1
+            for _ in range(3):
+                ops.dc_chain(tt, 1e-6)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                ops.dc_chain(tt, 1e-6)
+            e1.record()
+            torch.cuda.synchronize()
+            tc["gpu_value"] = 10 * n / (e0.elapsed_time(e1) * 1e-3)
+            tc["gpu_sample"] = "10 x 2^24 evaluations of the same chain on packed-SoA device arrays (xs_dc_chain), inputs resident in HBM"
+        except Exception as e:
+            tc["gpu_value"] = None
+            tc["gpu_error"] = str(e)[:200]
+        line["cpu_baseline_test_csfd"] = tc
     if world == 1 and not args.no_ref_cuda and not args.no_cpu_baseline:
         del k
         torch.cuda.empty_cache()
@@ -407,10 +536,11 @@ def run_ours(args, xs, rank, world, local_rank):
             line["ref_cuda_baseline"] = {"unavailable": str(e)[:200]}
         if rt:
             per = float(np.mean(rt[1:])) if len(rt) > 1 else float(rt[0])
-            ncd = args.dirs * (1 if args.comps == 1 else 3)
+            ncd = distinct_planes(args)
             line["ref_cuda_baseline"] = {
                 "value": 1.0 / (per * ncd), "unit": "frames/s", "kind": "reference CUDA kernels recompiled for sm_100a (oracle/_ref/libxslam_ref.so), same B200",
-                "seconds_per_direction_frame": per, "sample": "%d frames, 640x480 / %d^3, one first-order complex direction per pass; scaled by %d derivative components" % (max(len(rt) - 1, 1), args.res, ncd)}
+                "seconds_per_direction_frame": per, "passes_per_differentiated_frame": ncd,
+                "sample": "%d frames timed, 640x480 / %d^3, one first-order complex direction per pass; value = 1 / (%d passes x measured pass time)" % (max(len(rt) - 1, 1), args.res, ncd)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -421,10 +551,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    import xslam_b200 as xs
-    if args.impl == "reference":
-        run_reference(args, xs, rank)
+    if args.impl == "reference":  # never imports the product
+        run_reference(args, rank)
         return
+    import xslam_b200 as xs
     run_ours(args, xs, rank, world, local_rank)
 
 

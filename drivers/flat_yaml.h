@@ -31,6 +31,7 @@ class FlatYaml {
     }
     std::string str(const std::string &k, const std::string &dflt) const { return has(k) ? kv_.at(k) : dflt; }
     int i(const std::string &k) const { return std::stoi(str(k)); }
+    int i(const std::string &k, int dflt) const { return has(k) ? i(k) : dflt; }
     float f(const std::string &k) const { return std::stof(str(k)); }
     bool b(const std::string &k) const {
         const std::string v = str(k);

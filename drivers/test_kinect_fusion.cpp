@@ -128,6 +128,11 @@ int main(int argc, char *argv[]) {
     cfg.angle_thres_deg = config.f("angleThres");
     cfg.bi_threshold = config.f("biInterpolate_threshold");
     cfg.trunc_k = config.f("trunc_logistic_k");
+    cfg.frame_step = config.i("frame_step", 1);  // KinectFusionReconstruction.cpp:72: frame_id += frame_step per processed frame
+    if (cfg.frame_step < 1) {
+        std::cerr << "frame_step must be >= 1\n";
+        return -1;
+    }
     const xs_intr intr = {cfg.fx, cfg.fy, cfg.cx, cfg.cy};
 
     // perturbation directions
@@ -233,7 +238,7 @@ int main(int argc, char *argv[]) {
                 out << "\n";
             }
         }
-        if (draw_pcd && frame_id == last_frame - 1) {
+        if (draw_pcd && frame_id + cfg.frame_step >= last_frame) {
             // ExportPointCloud(1000000) + exportPly on the last frame, main.cpp:76-81 / KinectFusionReconstruction.cpp:334-372
             const long max_buffer = 1000000;
             float *d_pts = nullptr, *d_nrm = nullptr;
@@ -254,7 +259,7 @@ int main(int argc, char *argv[]) {
             std::cout << "point cloud: " << n << " points -> " << output_path << "pcd.ply\n";
         }
     }
-    const int frames = xs_kinfu_frame_id(kinfu);
+    const int frames = (xs_kinfu_frame_id(kinfu) + cfg.frame_step - 1) / cfg.frame_step;  // frames processed
     printf("mean frame time = %.3f ms\n", total_time / (frames > 0 ? frames : 1));
     xs_kinfu_destroy(kinfu);
     xs_dataset_close(dataset);

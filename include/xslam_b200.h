@@ -146,6 +146,9 @@ int xs_tsdf_loss(const uint16_t *d_depth, size_t depth_step_bytes, int rows, int
                  double *out2_host, void *stream);
 /* extractPoints / extractNormals, ExtractPointCloud.h:19-23 (real-only output path) */
 long xs_extract_points(const xs_volume *v, float *d_points_xyz, float *d_normals_xyz, long max_points, void *stream);
+/* extractNormals alone, ExtractPointCloud.h:22-23 / ExtractPointCloud.cu:342-362: trilinear central differences at +-1 voxel
+ * divided by the SQUARED norm (reference quirk, :305-306) for n given points (device, xyz interleaved). */
+int xs_extract_normals(const xs_volume *v, const float *d_points_xyz, float *d_normals_xyz, long n, void *stream);
 
 /* ---------------------------------------------------------------- ICP (a7) */
 /* estimateCombined, ICP.h:24-31 / ICP.cu:365.  curr = (Rcurr, tcurr), prev = (Rprev_inv, tprev).
@@ -183,10 +186,13 @@ typedef struct {
     float angle_thres_deg;
     float bi_threshold;
     float trunc_k;
+    int frame_step; /* KinectFusionReconstruction.cpp:72,157: frame_id advances by it (gt_poses[frame_id], dataset index); <= 0 reads as 1 */
 } xs_config;
 
 typedef enum {
-    XS_SOLVE_EIGEN_LLT = 0, /* Hermitian LLT of the complex-symmetric A, as KinectFusionReconstruction.cpp:211 (comps=1 only) */
+    XS_SOLVE_EIGEN_LLT = 0, /* Hermitian LLT of the complex-symmetric A, as KinectFusionReconstruction.cpp:211; with comps=3 each
+                               first-order component (eps1, eps2) is solved that way - what a one-direction complex run of the
+                               reference yields - and eps1eps2 is the truncated-algebra second derivative on top of them */
     XS_SOLVE_ANALYTIC = 1   /* derivative of x = A^-1 b by the truncated algebra */
 } xs_solve_mode;
 

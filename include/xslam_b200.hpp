@@ -7,7 +7,8 @@
 // (INTEGRATION.md shows the diff).  The wrappers are templates over the reference's own container / POD types
 // (DeviceArray2D<T>, PtrStep<T>, PtrStepSz<T>, Intr, MatS33, devComplex3 — Internal.h, device_array.hpp,
 // kernel_containers.hpp), so this header does not include any reference header; oracle/hpp_check.cu instantiates
-// every wrapper with the real reference types as a compile check.
+// every wrapper with the real reference types as a compile check, and oracle/seam_run.cu links and RUNS a frame through
+// them on the reference's own containers beside the same calls into the reference's kernels (tests/test_seam_run.py).
 //
 // Layout at the seam: maps are pitched interleaved complex<float>, three planes stacked by rows;
 // volumes are three pitched (Y*Z) x X planes.  Behind the seam everything is packed SoA / brick-tiled, so each
@@ -53,6 +54,26 @@ inline Scratch &scratch(int slot) {
 }
 
 template <class IntrT> inline xs_intr to_intr(const IntrT &k) { return xs_intr{k.fx, k.fy, k.cx, k.cy}; }
+
+// The reference's call sites pass either the owning containers (DeviceArray2D<T>: ptr(), step(), rows(), cols(); DeviceArray<T>:
+// ptr(), size()) or their kernel views (PtrStep / PtrStepSz / PtrSz: data, step, rows, cols, size members) - the containers
+// convert implicitly to the views in the reference's non-template signatures (device_array.hpp:96-98,225-231).  These
+// adapters accept both, so that the template wrappers below bind to unchanged call sites.
+struct Plane {
+    void *data;
+    size_t step;
+    int rows, cols;
+};
+template <class T> inline auto as_plane(const T &p, int) -> decltype(p.step(), Plane()) { return Plane{(void *) p.ptr(), p.step(), p.rows(), p.cols()}; }
+template <class T> inline auto as_plane_dims(const T &p, int) -> decltype(p.rows + 0, Plane()) { return Plane{(void *) p.data, p.step, p.rows, p.cols}; }
+template <class T> inline Plane as_plane_dims(const T &p, long) { return Plane{(void *) p.data, p.step, 0, 0}; }
+template <class T> inline auto as_plane(const T &p, long) -> decltype(p.step + 0, Plane()) { return as_plane_dims(p, 0); }
+struct Linear {
+    void *data;
+    size_t size;
+};
+template <class T> inline auto as_linear(const T &p, int) -> decltype(p.size(), Linear()) { return Linear{(void *) p.ptr(), p.size()}; }
+template <class T> inline auto as_linear(const T &p, long) -> decltype(p.size + 0, Linear()) { return Linear{(void *) p.data, p.size}; }
 
 // MatS33 (Internal.h:146-148: data[3] rows of devComplex3) + devComplex3 -> xs_pose with one derivative component
 struct PoseHolder {
@@ -142,9 +163,12 @@ struct VolumeShadow {
     float *dense = nullptr;  // 3 dense [z][y][x] planes: value, weight, grad
     int res[3] = {0, 0, 0};
 };
-inline VolumeShadow &shadow_of(const void *value_plane, const int res[3], float voxel, float trunc) {
+inline std::map<const void *, VolumeShadow> &shadow_cache() {
     static std::map<const void *, VolumeShadow> cache;
-    VolumeShadow &s = cache[value_plane];
+    return cache;
+}
+inline VolumeShadow &shadow_of(const void *value_plane, const int res[3], float voxel, float trunc) {
+    VolumeShadow &s = shadow_cache()[value_plane];
     if (!s.v) {
         // trunc = max(voxel * thres_range, 2.1 voxel) (TsdfVolume.cpp:25,37): recover thres_range from the caller's trunc
         s.v = xs_volume_create(res, voxel, trunc / voxel, 1, 1);
@@ -156,7 +180,7 @@ inline VolumeShadow &shadow_of(const void *value_plane, const int res[3], float 
     return s;
 }
 // pitched (Y*Z) x X seam planes <-> dense planes <-> bricks
-template <class PV, class PW> inline void volume_pull(VolumeShadow &s, const PV &value, const PW &weight, const PV &grad) {
+inline void volume_pull(VolumeShadow &s, const Plane &value, const Plane &weight, const Plane &grad) {
     const size_t n = (size_t) s.res[0] * s.res[1] * s.res[2], row = (size_t) s.res[0] * sizeof(float);
     const size_t h = (size_t) s.res[1] * s.res[2];
     cudaMemcpy2D(s.dense, row, value.data, value.step, row, h, cudaMemcpyDeviceToDevice);
@@ -164,7 +188,7 @@ template <class PV, class PW> inline void volume_pull(VolumeShadow &s, const PV 
     cudaMemcpy2D(s.dense + 2 * n, row, grad.data, grad.step, row, h, cudaMemcpyDeviceToDevice);
     check(xs_volume_import_planes(s.v, 0, s.dense, (const int *) (s.dense + n), s.dense + 2 * n, nullptr), "volume import");
 }
-template <class PV, class PW> inline void volume_push(VolumeShadow &s, PV &value, PW &weight, PV &grad) {
+inline void volume_push(VolumeShadow &s, const Plane &value, const Plane &weight, const Plane &grad) {
     const size_t n = (size_t) s.res[0] * s.res[1] * s.res[2], row = (size_t) s.res[0] * sizeof(float);
     const size_t h = (size_t) s.res[1] * s.res[2];
     check(xs_volume_export_planes(s.v, 0, s.dense, (int *) (s.dense + n), s.dense + 2 * n, nullptr), "volume export");
@@ -173,20 +197,36 @@ template <class PV, class PW> inline void volume_push(VolumeShadow &s, PV &value
     cudaMemcpy2D((void *) grad.data, grad.step, s.dense + 2 * n, row, row, h, cudaMemcpyDeviceToDevice);
 }
 
+// TsdfVolume.h:16 / TsdfFusion.cu:34-43 (sync): value, weight and grad planes are zeroed (pack_tsdf(0, 0)); like the reference's
+// kernel, the packed short2 `volume` plane is not touched.  The brick-tiled shadow of this volume, if one exists, is reset.
+template <class PS, class PV, class PW, class Int3>
+void initVolume(const PS & /*volume*/, const PV &value_volume, const PW &weight_volume, const PV &grad_volume,
+                const Int3 &volume_resolution) {
+    const size_t h = (size_t) volume_resolution.y * volume_resolution.z, row = (size_t) volume_resolution.x * sizeof(float);
+    const Plane pv = as_plane(value_volume, 0), pw = as_plane(weight_volume, 0), pg = as_plane(grad_volume, 0);
+    if (cudaMemset2D(pv.data, pv.step, 0, row, h) != cudaSuccess || cudaMemset2D(pw.data, pw.step, 0, row, h) != cudaSuccess ||
+        cudaMemset2D(pg.data, pg.step, 0, row, h) != cudaSuccess)
+        check(XS_ERR_CUDA, "initVolume");
+    auto it = shadow_cache().find((const void *) pv.data);
+    if (it != shadow_cache().end() && it->second.v) check(xs_volume_reset(it->second.v, nullptr), "initVolume");
+    cudaDeviceSynchronize();
+}
+
 // TsdfFusion.h:40-45 / TsdfFusion.cu:173 (sync).  tc2v, depthScaled, frame_id and k are unused by the reference too.
 template <class DepthT, class IntrT, class Int3, class Mat, class Vec, class PV, class PW, class ScaledT>
 void integrateTsdfVolume(const DepthT &depth, const IntrT &intr, int max_weight, const Int3 &volume_size, float voxel_size,
-                         const Mat &Rv2c, const Vec &tv2c, const Vec & /*tc2v*/, float trunc_dist, PV value_volume,
-                         PW weight_volume, PV grad_volume, ScaledT & /*depthScaled*/, int /*frame_id*/, float threshold,
+                         const Mat &Rv2c, const Vec &tv2c, const Vec & /*tc2v*/, float trunc_dist, const PV &value_volume,
+                         const PW &weight_volume, const PV &grad_volume, ScaledT & /*depthScaled*/, int /*frame_id*/, float threshold,
                          float /*k*/) {
     const int res[3] = {volume_size.x, volume_size.y, volume_size.z};
-    VolumeShadow &s = shadow_of(value_volume.data, res, voxel_size, trunc_dist);
-    volume_pull(s, value_volume, weight_volume, grad_volume);
+    const Plane pv = as_plane(value_volume, 0), pw = as_plane(weight_volume, 0), pg = as_plane(grad_volume, 0), d = as_plane(depth, 0);
+    VolumeShadow &s = shadow_of(pv.data, res, voxel_size, trunc_dist);
+    volume_pull(s, pv, pw, pg);
     PoseHolder v2c(Rv2c, tv2c);
-    check(xs_integrate(s.v, depth.data, depth.step, depth.rows, depth.cols, to_intr(intr), max_weight, &v2c.p, threshold,
+    check(xs_integrate(s.v, (const uint16_t *) d.data, d.step, d.rows, d.cols, to_intr(intr), max_weight, &v2c.p, threshold,
                        nullptr, nullptr),
           "integrateTsdfVolume");
-    volume_push(s, value_volume, weight_volume, grad_volume);
+    volume_push(s, pv, pw, pg);
     cudaDeviceSynchronize();
 }
 
@@ -195,11 +235,12 @@ template <class IntrT, class Mat, class Vec, class Int3, class PV, class MapT>
 void raycast(const IntrT &intr, const Mat &Rc2v, const Vec &tc2v, const Mat &Rv2w, const Vec &tv2w, float trunc_dist,
              const Int3 &volume_size, float voxel_size, const PV &value_volume, const PV &grad_volume, MapT &vmap, MapT &nmap) {
     const int res[3] = {volume_size.x, volume_size.y, volume_size.z};
-    VolumeShadow &s = shadow_of(value_volume.data, res, voxel_size, trunc_dist);
+    const Plane pv = as_plane(value_volume, 0), pg = as_plane(grad_volume, 0);
+    VolumeShadow &s = shadow_of(pv.data, res, voxel_size, trunc_dist);
     {   // the planes may have been written by the caller since the last integration
         const size_t n = (size_t) res[0] * res[1] * res[2], row = (size_t) res[0] * sizeof(float), h = (size_t) res[1] * res[2];
-        cudaMemcpy2D(s.dense, row, value_volume.data, value_volume.step, row, h, cudaMemcpyDeviceToDevice);
-        cudaMemcpy2D(s.dense + 2 * n, row, grad_volume.data, grad_volume.step, row, h, cudaMemcpyDeviceToDevice);
+        cudaMemcpy2D(s.dense, row, pv.data, pv.step, row, h, cudaMemcpyDeviceToDevice);
+        cudaMemcpy2D(s.dense + 2 * n, row, pg.data, pg.step, row, h, cudaMemcpyDeviceToDevice);
         check(xs_volume_import_planes(s.v, 0, s.dense, nullptr, s.dense + 2 * n, nullptr), "volume import");
     }
     const int rows = vmap.rows() / 3, cols = vmap.cols();
@@ -208,6 +249,35 @@ void raycast(const IntrT &intr, const Mat &Rc2v, const Vec &tc2v, const Mat &Rv2
     check(xs_raycast(s.v, to_intr(intr), &c2v.p, &v2w.p, rows, cols, v, n, nullptr), "raycast");
     export_map(v, 1, 3, rows, cols, vmap);
     export_map(n, 1, 3, rows, cols, nmap);
+}
+
+// ExtractPointCloud.h:19-20 / ExtractPointCloud.cu:181-210 (sync).  output: PtrSz<float3>; returns min(size, points found).
+// The order of the points is scheduling dependent on both sides (atomic appends); the point SET is the reference's.
+template <class PV, class PW, class Int3, class Out>
+size_t extractPoints(const PV &value_volume, const PW &weight_volume, const PV &grad_volume, const Int3 &volume_resolution,
+                     float voxel_size, const Out &output) {
+    const int res[3] = {volume_resolution.x, volume_resolution.y, volume_resolution.z};
+    const Plane pv = as_plane(value_volume, 0), pw = as_plane(weight_volume, 0), pg = as_plane(grad_volume, 0);
+    const Linear out = as_linear(output, 0);
+    VolumeShadow &s = shadow_of(pv.data, res, voxel_size, 3.f * voxel_size);  // the truncation distance plays no role here
+    volume_pull(s, pv, pw, pg);
+    const long n = xs_extract_points(s.v, reinterpret_cast<float *>(out.data), nullptr, (long) out.size, nullptr);
+    if (n < 0) check((int) n, "extractPoints");
+    return (size_t) n;
+}
+// ExtractPointCloud.h:22-23 / ExtractPointCloud.cu:342-362 (sync): one normal per entry of `points` (points.size entries, as
+// the reference: ExportPointCloud passes the whole buffer), divided by the squared norm (:305-306).
+template <class PV, class PW, class Int3, class Pts>
+void extractNormals(const PV &value_volume, const PW &weight_volume, const PV &grad_volume, const Int3 &volume_resolution,
+                    float voxel_size, const Pts &points, const Pts &normal) {
+    const int res[3] = {volume_resolution.x, volume_resolution.y, volume_resolution.z};
+    const Plane pv = as_plane(value_volume, 0), pw = as_plane(weight_volume, 0), pg = as_plane(grad_volume, 0);
+    const Linear pts = as_linear(points, 0), nrm = as_linear(normal, 0);
+    VolumeShadow &s = shadow_of(pv.data, res, voxel_size, 3.f * voxel_size);
+    volume_pull(s, pv, pw, pg);
+    check(xs_extract_normals(s.v, reinterpret_cast<const float *>(pts.data), reinterpret_cast<float *>(nrm.data), (long) pts.size,
+                             nullptr),
+          "extractNormals");
 }
 
 // ICP.h:24-31 / ICP.cu:365 (sync + download).  gbuf / mbuf are the reference's scratch; unused here.
@@ -260,7 +330,8 @@ float4 ComputeLocalTsdf_hessian(const DepthT &depth, const IntrT &intr, ScaledT 
     p.dR = dR;
     p.dt = dt;
     double out[4];
-    check(xs_tsdf_hessian(depth.data, depth.step, depth.rows, depth.cols, to_intr(intr), res, voxel_size, &p, tranc_dist,
+    const Plane d = as_plane(depth, 0);
+    check(xs_tsdf_hessian((const uint16_t *) d.data, d.step, d.rows, d.cols, to_intr(intr), res, voxel_size, &p, tranc_dist,
                           gt_vec.data().get(), out, nullptr),
           "ComputeLocalTsdf_hessian");
     return make_float4((float) out[0], (float) out[1], (float) out[2], (float) out[3]);
@@ -276,7 +347,8 @@ float2 ComputeLocalTsdf_loss(const DepthT &depth, const IntrT &intr, ScaledT & /
                         Rv2c.data[1].z, Rv2c.data[2].x, Rv2c.data[2].y, Rv2c.data[2].z};
     const float t[3] = {tv2c.x, tv2c.y, tv2c.z};
     double out[2];
-    check(xs_tsdf_loss(depth.data, depth.step, depth.rows, depth.cols, to_intr(intr), res, voxel_size, R, t, tranc_dist,
+    const Plane d = as_plane(depth, 0);
+    check(xs_tsdf_loss((const uint16_t *) d.data, d.step, d.rows, d.cols, to_intr(intr), res, voxel_size, R, t, tranc_dist,
                        gt_vec.data().get(), out, nullptr),
           "ComputeLocalTsdf_loss");
     return make_float2((float) out[0], (float) out[1]);

@@ -2,7 +2,8 @@
 // types.  Instantiates every seam wrapper with DeviceArray2D / PtrStep / Intr / MatS33 / devComplex3 from
 // /root/reference (XKinectFusion/include/Internal.h, DeviceArray/include/*.hpp), i.e. with exactly the argument types
 // KinectFusionReconstruction.cpp passes (:143,198,264,274-275,290,293-296,327).  Built by `make -C oracle ref`
-// (object file only; nothing links or runs it).
+// (object file only: this translation unit checks that every wrapper INSTANTIATES with the reference types, including the
+// dormant operators; oracle/seam_run.cu is the linked, executed counterpart for the frame loop's call sequence).
 #include "Internal.h"
 #include "../include/xslam_b200.hpp"
 
@@ -45,6 +46,12 @@ void hpp_check_instantiate() {
     float3 tf = make_float3(0.f, 0.f, 0.f);
     float2 l2 = S::ComputeLocalTsdf_loss(d, intr, depthScaled, res, 0.03f, Rf, tf, 0.09f, 0.f, 0.f, gt_vec, real_vec,
                                          count_vec);  // TsdfFusion.h:48-52
+    DeviceArray2D<int> packed;
+    S::initVolume(packed, value, weight, grad, res);  // TsdfVolume.h:16, as TsdfVolume::reset calls it (TsdfVolume.cpp:50)
+    DeviceArray<float3> cloud, normals;
+    const size_t n_pts = S::extractPoints(value, weight, grad, res, 0.03f, cloud);  // ExtractPointCloud.h:19-20
+    S::extractNormals(value, weight, grad, res, 0.03f, cloud, normals);               // ExtractPointCloud.h:22-23
+    (void) n_pts;
     (void) h4;
     (void) l2;
 }

@@ -171,6 +171,16 @@ class RefCuda:
                                C.c_float(trunc), _p(_f(gt)), _p(out), C.byref(ms))
         return out, ms.value
 
+    def extract(self, res, voxel, value, weight, grad, max_points=1000000):
+        """ExtractPointCloud.cu extractPoints + extractNormals as ExportPointCloud calls them.  Returns (points, normals)."""
+        r = (C.c_int * 3)(*res)
+        pts = np.zeros((max_points, 3), np.float32)
+        nrm = np.zeros((max_points, 3), np.float32)
+        self.lib.ref_extract.restype = C.c_long
+        n = self.lib.ref_extract(r, C.c_float(voxel), _p(_f(value)), _p(np.ascontiguousarray(weight, np.int32), C.c_int), _p(_f(grad)),
+                                 C.c_long(max_points), _p(pts), _p(nrm))
+        return pts[:n], nrm[:n]
+
     def kinfu(self, cfg, seed_imag=None):
         return RefKinfu(self, cfg, seed_imag)
 
@@ -381,6 +391,14 @@ class Oracle:
         Rf = Rf.reshape(9, 2)
         tf = tf.reshape(3, 2)
         return ok, (Rf[:, 0] + 1j * Rf[:, 1]).reshape(3, 3).astype(np.complex64), (tf[:, 0] + 1j * tf[:, 1]).astype(np.complex64)
+
+    def llt_solve6(self, A, b):
+        """The restated Eigen LLT (lower, Hermitian semantics) solve alone; A: [6, 6] complex, b: [6] complex."""
+        Ac = np.ascontiguousarray(np.stack([A.T.real, A.T.imag], -1), np.float64)  # column-major
+        bc = np.ascontiguousarray(np.stack([b.real, b.imag], -1), np.float64)
+        x = np.zeros((6, 2), np.float64)
+        ok = self.lib.oracle_llt_solve6(_p(Ac, C.c_double), _p(bc, C.c_double), _p(x, C.c_double))
+        return ok, x[:, 0] + 1j * x[:, 1]
 
     def _m(self, fn, M, n):
         a = np.asarray(M, np.complex64).reshape(-1)

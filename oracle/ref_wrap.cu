@@ -187,6 +187,29 @@ int ref_integrate(const uint16_t *depth, int rows, int cols, float fx, float fy,
     return 0;
 }
 
+// ExtractPointCloud.cu:181-210 extractPoints + :342-362 extractNormals on a host-provided volume, exactly as
+// KinectFusionReconstruction::ExportPointCloud calls them (KinectFusionReconstruction.cpp:334-346): normals are computed
+// for the whole buffer (points.size = max_points), only the first `count` entries are meaningful.  Returns the count.
+long ref_extract(const int *res, float voxel, const float *value, const int *weight, const float *grad, long max_points,
+                 float *points_out /* [max_points][3] */, float *normals_out /* [max_points][3] */) {
+    DeviceArray2D<float> dv, dg;
+    DeviceArray2D<int> dw;
+    int R = res[1] * res[2], C = res[0];
+    dv.upload(value, C * sizeof(float), R, C);
+    dg.upload(grad, C * sizeof(float), R, C);
+    dw.upload(weight, C * sizeof(int), R, C);
+    DeviceArray<float3> cloud, normals;
+    cloud.create(max_points);
+    normals.create(max_points);
+    cudaMemset(cloud.ptr(), 0, max_points * sizeof(float3));
+    int3 r3 = make_int3(res[0], res[1], res[2]);
+    const size_t n = extractPoints(dv, dw, dg, r3, voxel, cloud);
+    extractNormals(dv, dw, dg, r3, voxel, cloud, normals);
+    cudaMemcpy(points_out, cloud.ptr(), n * sizeof(float3), cudaMemcpyDeviceToHost);
+    cudaMemcpy(normals_out, normals.ptr(), n * sizeof(float3), cudaMemcpyDeviceToHost);
+    return (long) n;
+}
+
 // RayCaster.cu:327 raycast on a host-provided volume.
 int ref_raycast(float fx, float fy, float cx, float cy, const float *Rc2v, const float *tc2v, const float *Rv2w,
                 const float *tv2w, float trunc, const int *res, float voxel, const float *value, const float *grad,

@@ -429,3 +429,40 @@ def test_dcsfd_volume_loss_batch(xs, refcuda, torch_mod, out_dir):
                                      trunc, big)
     t2 = time.perf_counter()
     _report(out_dir, "tsdf_hessian_batch", rel_vs_ref=rel, batch_ms=(t1 - t0) * 1e3, singles_ms=(t2 - t1) * 1e3, dirs=dirs)
+
+
+def test_point_extraction_parity(xs, refcuda, torch_mod, out_dir):
+    """extractPoints / extractNormals (f1; ExtractPointCloud.cu:25-210, 213-362): the point SET and the normals (divided by
+    the squared norm, :305-306) of a 3-frame 128^3 volume against the reference kernels.  The reference appends per
+    scheduling order (atomics), so both sides are sorted; a truncated buffer (max_points < count) keeps the count rule
+    output_count = min(size, global_count) (:175)."""
+    torch = torch_mod
+    from xslam_b200 import ops
+    res, voxel = 128, 0.06
+    vol, ref_state, _, _ = _integrate_both(xs, refcuda, torch, [0, 6, 12], res, voxel, 1, 1, 0.0)
+    zv, zw, zg = ref_state[1]  # the zero-seed reference pass
+    assert np.array_equal(vol.value().cpu().numpy(), zv)
+    rp, rn = refcuda.extract((res,) * 3, voxel, zv, zw, zg, 1000000)
+    mp, mn = ops.extractPoints(vol, 1000000, normals=True)
+    mp, mn = mp.cpu().numpy(), mn.cpu().numpy()
+    assert rp.shape[0] > 20000
+    om, orf = np.lexsort(mp.T[::-1]), np.lexsort(rp.T[::-1])
+    n = min(len(om), len(orf))
+    pts_equal = len(om) == len(orf) and np.array_equal(mp[om], rp[orf])
+    pt_ulp = int(ulp_diff(mp[om][:n], rp[orf][:n]).max()) if n else -1
+    # normals of identical points: same kernel arithmetic on both sides (plain float, no +1e-5 bias)
+    fin = np.isfinite(rn[orf][:n]).all(1) & np.isfinite(mn[om][:n]).all(1)
+    nrm_ulp = ulp_diff(mn[om][:n][fin], rn[orf][:n][fin])
+    nan_equal = bool(np.array_equal(np.isfinite(mn[om][:n]), np.isfinite(rn[orf][:n])))
+    # squared-norm quirk: |n| = 1 / |grad| rather than 1
+    norms = np.linalg.norm(rn[orf][:n][fin], axis=1)
+    # truncated buffer
+    small = 5000
+    mp_small, _ = ops.extractPoints(vol, small, normals=False)
+    _report(out_dir, "extract", ref_points=int(rp.shape[0]), points=int(mp.shape[0]), point_set_equal=bool(pts_equal),
+            point_max_ulp=pt_ulp, normal_max_ulp=int(nrm_ulp.max()), normal_ulp_gt2=int((nrm_ulp > 2).sum()),
+            normal_nan_pattern_equal=nan_equal, mean_normal_length=float(norms[norms > 0].mean()), truncated=int(mp_small.shape[0]))
+    assert pts_equal, "point sets differ (max %d ulp)" % pt_ulp
+    assert nan_equal and int(nrm_ulp.max()) <= 4
+    assert mp_small.shape[0] == small
+    assert abs(float(norms[norms > 0].mean()) - 1.0) > 0.05, "normals are divided by the squared norm (reference quirk)"

@@ -31,7 +31,7 @@ class Config(C.Structure):
                 ("init_xyz", C.c_float * 3), ("r_deg", C.c_float * 3), ("width", C.c_int), ("height", C.c_int),
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("num_levels", C.c_int),
                 ("dist_thres", C.c_float), ("angle_thres_deg", C.c_float), ("bi_threshold", C.c_float),
-                ("trunc_k", C.c_float)]
+                ("trunc_k", C.c_float), ("frame_step", C.c_int)]
 
 
 # every symbol include/xslam_b200.h declares: name -> (restype, argtypes)
@@ -69,6 +69,7 @@ SYMBOLS = {
     "xs_tsdf_hessian_batch": (_i, [_vp, _sz, _i, _i, Intr, _pi, _f, _PP, _f, _vp, _pd, _vp]),
     "xs_tsdf_loss": (_i, [_vp, _sz, _i, _i, Intr, _pi, _f, _pf, _pf, _f, _vp, _pd, _vp]),
     "xs_extract_points": (_l, [_vp, _vp, _vp, _l, _vp]),
+    "xs_extract_normals": (_i, [_vp, _vp, _vp, _l, _vp]),
     "xs_estimate_combined": (_i, [_PP, _vp, _vp, _PP, Intr, _vp, _vp, _i, _i, _i, _i, _f, _f, _pd, _pd, _vp]),
     "xs_compute_optimize_matrix": (_l, [_PP, _vp, _vp, _PP, Intr, _vp, _vp, _i, _i, _f, _f, _pd, _pd, _vp]),
     "xs_kinfu_create": (_vp, [C.POINTER(Config), _i, _i, _pf, _i]),

@@ -6,6 +6,8 @@
 // offline; its scene, intrinsics and depth encoding are the ones fixed by SURVEY.md §8(d).
 #include "../../include/xslam_b200.h"
 
+#include <cuda_runtime_api.h>
+
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -16,6 +18,17 @@ namespace xs {
 static thread_local std::string g_error;
 long long g_launches = 0;
 void set_error(const std::string &msg) { g_error = msg; }
+// cudaDevAttrMultiProcessorCount of the current device, cached per device ordinal (148 on B200)
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    }
+    return cached[dev];
+}
 }  // namespace xs
 
 namespace {

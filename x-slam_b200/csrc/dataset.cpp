@@ -10,7 +10,9 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <fstream>
 #include <iostream>
 #include <sstream>
@@ -28,7 +30,7 @@ uint32_t be32(const unsigned char *p) { return ((uint32_t) p[0] << 24) | ((uint3
 
 // Decodes a non-interlaced greyscale PNG (bit depth 8 or 16) into 16-bit samples, i.e. what
 // cv::imread(path, cv::IMREAD_UNCHANGED) yields for the benchmark depth images (Dataset.cpp:7); 8-bit samples are widened.
-bool decode_png_gray(const std::string &path, int &rows, int &cols, std::vector<uint16_t> &out, std::string &err) {
+bool decode_png_gray_impl(const std::string &path, int &rows, int &cols, std::vector<uint16_t> &out, std::string &err) {
     std::ifstream in(path, std::ios::binary);
     if (!in) {
         err = "cannot open " + path;
@@ -74,6 +76,11 @@ bool decode_png_gray(const std::string &path, int &rows, int &cols, std::vector<
         err = path + ": only non-interlaced 8/16-bit greyscale PNG depth images are supported";
         return false;
     }
+    // the header is untrusted: bound the allocation (a depth frame is far below 64 Mpixel) before trusting it
+    if ((uint64_t) rows * (uint64_t) cols > (1ull << 26)) {
+        err = path + ": IHDR announces an implausible image size";
+        return false;
+    }
     const size_t bpp = depth / 8, stride = (size_t) cols * bpp;
     std::vector<unsigned char> raw((stride + 1) * (size_t) rows);
     uLongf raw_len = (uLongf) raw.size();
@@ -109,6 +116,16 @@ bool decode_png_gray(const std::string &path, int &rows, int &cols, std::vector<
         prev.swap(cur);
     }
     return true;
+}
+
+// no exception leaves the library through an extern "C" function: allocation failures on corrupt input become errors
+bool decode_png_gray(const std::string &path, int &rows, int &cols, std::vector<uint16_t> &out, std::string &err) {
+    try {
+        return decode_png_gray_impl(path, rows, cols, out, err);
+    } catch (const std::exception &e) {
+        err = path + ": " + e.what();
+        return false;
+    }
 }
 
 // IOHelper.cpp:4-19 loadTxtMatrix: whitespace-separated floats, row by row
@@ -182,7 +199,7 @@ int xs_icl_read_pose_file(const char *poses_path, int start, int end, float *pos
             std::stringstream linestream(temp);
             std::string sub;
             while (linestream >> sub) {
-                if (i - start < 4 && j < 4) pose16[(i - start) * 4 + j] = (float) std::stod(sub);
+                if (i - start < 4 && j < 4) pose16[(i - start) * 4 + j] = (float) std::strtod(sub.c_str(), nullptr);
                 j++;
             }
             i++;
@@ -196,7 +213,16 @@ int xs_icl_read_pose_file(const char *poses_path, int start, int end, float *pos
 }
 
 // ICL_Dataset::ICL_Dataset, Dataset.cpp:69-88
+static xs_dataset *open_icl_impl(const char *dataset_dir, int start_frame, int end_frame, int is_flip);
 xs_dataset *xs_dataset_open_icl(const char *dataset_dir, int start_frame, int end_frame, int is_flip) {
+    try {
+        return open_icl_impl(dataset_dir, start_frame, end_frame, is_flip);
+    } catch (const std::exception &e) {
+        set_error(std::string("xs_dataset_open_icl: ") + e.what());
+        return nullptr;
+    }
+}
+static xs_dataset *open_icl_impl(const char *dataset_dir, int start_frame, int end_frame, int is_flip) {
     if (!dataset_dir) return nullptr;
     xs_dataset *d = new xs_dataset;
     d->flip = is_flip != 0;
@@ -228,7 +254,7 @@ xs_dataset *xs_dataset_open_icl(const char *dataset_dir, int start_frame, int en
             std::stringstream ss(lines[ln]);
             std::string sub;
             for (int j = 0; ss >> sub; ++j)
-                if (j < 4) pose[r * 4 + j] = (float) std::stod(sub);
+                if (j < 4) pose[r * 4 + j] = (float) std::strtod(sub.c_str(), nullptr);
         }
         pose[12] = pose[13] = pose[14] = 0.f;
         pose[15] = 1.f;
@@ -238,8 +264,19 @@ xs_dataset *xs_dataset_open_icl(const char *dataset_dir, int start_frame, int en
 }
 
 // seven_scenes_Dataset::seven_scenes_Dataset, Dataset.cpp:13-39.  seq_names as readInfo returns them ("seq-01/").
+static xs_dataset *open_seven_scenes_impl(const char *dataset_dir, const int *start_frames, const int *end_frames,
+                                          const char *const *seq_names, int nseq, int is_flip);
 xs_dataset *xs_dataset_open_seven_scenes(const char *dataset_dir, const int *start_frames, const int *end_frames,
                                          const char *const *seq_names, int nseq, int is_flip) {
+    try {
+        return open_seven_scenes_impl(dataset_dir, start_frames, end_frames, seq_names, nseq, is_flip);
+    } catch (const std::exception &e) {
+        set_error(std::string("xs_dataset_open_seven_scenes: ") + e.what());
+        return nullptr;
+    }
+}
+static xs_dataset *open_seven_scenes_impl(const char *dataset_dir, const int *start_frames, const int *end_frames,
+                                          const char *const *seq_names, int nseq, int is_flip) {
     if (!dataset_dir || !start_frames || !end_frames || !seq_names || nseq < 0) return nullptr;
     xs_dataset *d = new xs_dataset;
     d->flip = is_flip != 0;

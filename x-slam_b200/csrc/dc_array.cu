@@ -183,7 +183,7 @@ int xs_dc_apply(int op, const float *d_a, const float *d_b, float p, float *d_ou
     long done = 0;
     if (aligned) {
         const long n4 = n / 4;
-        const int grid = (int) (n4 / 256 + 1 < 148 * 8 ? n4 / 256 + 1 : 148 * 8);
+        const int grid = (int) (n4 / 256 + 1 < sm_count() * 8 ? n4 / 256 + 1 : sm_count() * 8);
         dc_apply_vec4<<<grid, 256, 0, s>>>(op, d_a, binary ? d_b : nullptr, p, d_out, n, n4);
         XS_LAUNCH_CHECK();
         done = n;
@@ -197,7 +197,7 @@ int xs_dc_apply(int op, const float *d_a, const float *d_b, float p, float *d_ou
 
 int xs_dc_chain(const float *d_t, float h, float *d_out, long n, void *stream) {
     if (!d_t || !d_out || n <= 0) return XS_ERR_ARG;
-    const int grid = (int) (n / 256 + 1 < 148 * 8 ? n / 256 + 1 : 148 * 8);
+    const int grid = (int) (n / 256 + 1 < sm_count() * 8 ? n / 256 + 1 : sm_count() * 8);
     dc_chain_kernel<<<grid, 256, 0, (cudaStream_t) stream>>>(d_t, h, d_out, n);
     XS_LAUNCH_CHECK();
     return XS_OK;

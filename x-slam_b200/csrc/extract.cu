@@ -122,21 +122,37 @@ extern "C" long xs_extract_points(const xs_volume *v, float *d_points_xyz, float
                                   void *stream) {
     if (!v || !d_points_xyz || max_points <= 0) return XS_ERR_ARG;
     cudaStream_t s = (cudaStream_t) stream;
-    if (cudaMemsetAsync(v->d_stats + 2, 0, sizeof(unsigned long long), s) != cudaSuccess) return XS_ERR_CUDA;
+    // The point counter is a slot of its own ([3]; [0..2] are the integration's statistics, which a deferred frame may not
+    // have collected yet).  A frame that is still integrating on another (non-blocking) stream must be complete before the
+    // volume is scanned: the extraction is an end-of-sequence call, so a device-wide wait is the simple, safe order.
+    if (cudaDeviceSynchronize() != cudaSuccess) return XS_ERR_CUDA;
+    unsigned long long *d_count = v->d_stats + 3, *h_count = v->h_stats + 3;
+    if (cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), s) != cudaSuccess) return XS_ERR_CUDA;
     const int nbricks = v->view.bx * v->view.by * v->view.bz;
-    extract_points_kernel<<<nbricks < 148 * 8 ? nbricks : 148 * 8, 512, 0, s>>>(v->view, d_points_xyz, max_points, v->d_stats + 2);
+    const int max_grid = sm_count() * 8;
+    extract_points_kernel<<<nbricks < max_grid ? nbricks : max_grid, 512, 0, s>>>(v->view, d_points_xyz, max_points, d_count);
     ++g_launches;
     if (cudaGetLastError() != cudaSuccess) return XS_ERR_CUDA;
-    if (cudaMemcpyAsync(v->h_stats + 2, v->d_stats + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    if (cudaMemcpyAsync(h_count, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s) != cudaSuccess)
         return XS_ERR_CUDA;
     if (cudaStreamSynchronize(s) != cudaSuccess) return XS_ERR_CUDA;
-    long n = (long) v->h_stats[2];
+    long n = (long) *h_count;
     if (n > max_points) n = max_points;  // output_count = min(size, global_count), :175
     if (d_normals_xyz && n > 0) {
-        extract_normals_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(v->view, d_points_xyz, d_normals_xyz, n);
-        ++g_launches;
-        if (cudaGetLastError() != cudaSuccess) return XS_ERR_CUDA;
-        if (cudaStreamSynchronize(s) != cudaSuccess) return XS_ERR_CUDA;
+        const int rc = xs_extract_normals(v, d_points_xyz, d_normals_xyz, n, stream);
+        if (rc != XS_OK) return rc;
     }
     return n;
+}
+
+// extractNormals, ExtractPointCloud.h:22-23 / ExtractPointCloud.cu:342-362 (sync)
+extern "C" int xs_extract_normals(const xs_volume *v, const float *d_points_xyz, float *d_normals_xyz, long n, void *stream) {
+    if (!v || !d_points_xyz || !d_normals_xyz || n < 0) return XS_ERR_ARG;
+    if (n == 0) return XS_OK;
+    cudaStream_t s = (cudaStream_t) stream;
+    extract_normals_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(v->view, d_points_xyz, d_normals_xyz, n);
+    ++g_launches;
+    if (cudaGetLastError() != cudaSuccess) return XS_ERR_CUDA;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return XS_ERR_CUDA;
+    return XS_OK;
 }

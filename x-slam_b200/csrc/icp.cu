@@ -825,6 +825,15 @@ __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, co
             for (int a = 0; a < (C == 3 ? 2 : 1); ++a) {
                 double Aa[6][6], ba[6], t[6], rhs[6];
                 unpack_sums(comp_sums + a * 27, Aa, ba);
+                if (C == 3 && P.solve_mode == XS_SOLVE_EIGEN_LLT) {
+                    // bicomplex direction in LLT mode: each first-order component is what a one-direction complex run of
+                    // the reference yields for that imaginary part (Hermitian LLT quirk); the eps1eps2 component below is
+                    // the truncated-algebra second derivative built on them
+                    cplx xq[6];
+                    llt_hermitian_solve6_dev(A, Aa, b, ba, xq);
+                    for (int i = 0; i < 6; ++i) xa[a][i] = xq[i].im;
+                    continue;
+                }
                 matvec6_dev(Aa, xr, t);
                 for (int i = 0; i < 6; ++i) rhs[i] = ba[i] - t[i];
                 chol6_solve(F, rhs, xa[a]);
@@ -905,16 +914,57 @@ struct IcpScratch {
     cudaEvent_t ev_real[MAX_SLOTS] = {};
     double *d_real_cache = nullptr;  // [MAX_SLOTS][REAL_CACHE]
     size_t cap_dpart = 0;
-    int max_blocks = 296;
+    int max_blocks = 296;  // set from the device's SM count at creation (two CTAs per SM)
+    int device = -1;       // the device every buffer and event of this scratch lives on
     // CUDA-event brackets of the derivative kernel launches since the last reset (roofline timing, bench.py)
     static constexpr int MAX_TIMED = 16;
     cudaEvent_t ev0[MAX_TIMED] = {}, ev1[MAX_TIMED] = {};
     int timed_npix[MAX_TIMED] = {};
     int n_timed = 0;
 };
-static IcpScratch g_icp;
+// One scratch per pipeline object (xs_kinfu owns one; two pipelines in one process - e.g. one per device - never share
+// tickets, slots or events).  The seam-level entry points (xs_estimate_combined, xs_compute_optimize_matrix), which have
+// no handle, share one lazily created scratch per device and are therefore not re-entrant, like the reference's
+// estimateCombined with its caller-owned gbuf / mbuf (ICP.cu:400-403).
+IcpScratch *icp_scratch_create() {
+    IcpScratch *sc = new IcpScratch();
+    cudaGetDevice(&sc->device);
+    sc->max_blocks = 2 * sm_count();
+    return sc;
+}
+void icp_scratch_destroy(IcpScratch *sc) {
+    if (!sc) return;
+    cudaFree(sc->d_partials);
+    cudaFree(sc->d_sums);
+    cudaFreeHost(sc->h_sums);
+    cudaFree(sc->d_dpartials);
+    cudaFree(sc->d_ticket);
+    cudaFree(sc->d_group_ticket);
+    cudaFree(sc->d_pose);
+    cudaFreeHost(sc->h_pose);
+    cudaFree(sc->d_rec_idx);
+    cudaFree(sc->d_rec_f);
+    cudaFree(sc->d_real_cache);
+    for (int i = 0; i < IcpScratch::MAX_SLOTS; ++i)
+        if (sc->ev_real[i]) cudaEventDestroy(sc->ev_real[i]);
+    for (int i = 0; i < IcpScratch::MAX_TIMED; ++i) {
+        if (sc->ev0[i]) cudaEventDestroy(sc->ev0[i]);
+        if (sc->ev1[i]) cudaEventDestroy(sc->ev1[i]);
+    }
+    delete sc;
+}
+static IcpScratch *g_last_timed = nullptr;  // scratch whose derivative launches xs_icp_deriv_times reports
+static IcpScratch *seam_scratch() {
+    static IcpScratch *per_device[64] = {nullptr};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!per_device[dev]) per_device[dev] = icp_scratch_create();
+    return per_device[dev];
+}
 
-static int icp_reserve(int ncomp, int npix, size_t dpart, int groups, int slots = 1) {
+static int icp_reserve(IcpScratch *scp, int ncomp, int npix, size_t dpart, int groups, int slots = 1) {
+    IcpScratch &g_icp = *scp;
     const int nvals = 27 * (1 + ncomp);
     if (slots > g_icp.cap_slots) {  // the slot count multiplies the sums and the record: start over with the larger one
         g_icp.cap_vals = 0;
@@ -986,10 +1036,12 @@ template <int C, int ST> static int launch_deriv(const IcpParams &P, const Solve
 // Queues one Gauss-Newton iteration: association + real sums, then (ncomp > 0) the derivative pass whose tail sums the
 // partials and - when d_pose_out is given - runs the Gauss-Newton step per direction; with ncomp == 0 the step is a
 // one-thread kernel.  d_pose_out == nullptr: accumulate only (the sums land in g_icp.d_sums).
-int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
+int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
                         xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
                         int dirs, float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
                         double *d_log, cudaStream_t s, cudaStream_t s_real, int slot) {
+    IcpScratch &g_icp = *scp;
+    g_last_timed = scp;
     const int ncomp = comps * dirs;
     // Split chains: the real part of an iteration (association, real sums, real Gauss-Newton step) does not depend on any
     // derivative component, so with a second stream the real chain of a frame - association + one-thread solve per
@@ -1008,13 +1060,14 @@ int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, cons
     P.groups = (ncomp + 2) / 3;
     static const int ppt_env = env_int("XS_ICP_PPT", 0), stages_env = env_int("XS_ICP_STAGES", 0);
     P.ppt = 4;
-    while (P.ppt > 1 && (long long) div_up(npix, 256 * P.ppt) * P.groups < 296) P.ppt >>= 1;
+    const int cta_slots = g_icp.max_blocks;  // two persistent CTAs per SM
+    while (P.ppt > 1 && (long long) div_up(npix, 256 * P.ppt) * P.groups < cta_slots) P.ppt >>= 1;
     if (ppt_env > 0) P.ppt = ppt_env < 32 ? ppt_env : 32;
     P.chunks = div_up(npix, 256 * P.ppt);
     const long long items = (long long) P.groups * P.chunks;
-    const int deriv_grid = (int) (items < 296 ? items : 296);
+    const int deriv_grid = (int) (items < cta_slots ? items : cta_slots);
     P.max_writers = ncomp > 0 ? (int) (P.chunks / (items / deriv_grid)) + 2 : 0;
-    int rc = icp_reserve(ncomp, npix, (size_t) P.groups * P.max_writers * 81, P.groups, split ? IcpScratch::MAX_SLOTS : 1);
+    int rc = icp_reserve(scp, ncomp, npix, (size_t) P.groups * P.max_writers * 81, P.groups, split ? IcpScratch::MAX_SLOTS : 1);
     if (rc != XS_OK) return rc;
     const int nvals = 27 * (1 + ncomp);
     // only the current pose's derivative components enter the rows (s = Rcurr*v + tcurr); the previous pose is used
@@ -1181,7 +1234,9 @@ __global__ void __launch_bounds__(256) icp_optimize_matrix_kernel(const IcpParam
     if (tid == 0) *P.ticket = 0u;
 }
 
-void icp_timing_reset() { g_icp.n_timed = 0; }
+void icp_timing_reset(IcpScratch *sc) {
+    if (sc) sc->n_timed = 0;
+}
 
 }  // namespace xs
 
@@ -1191,6 +1246,8 @@ using namespace xs;
 // xs_kinfu_pose_estimate / xs_estimate_combined began; call after the stream has been synchronised.
 extern "C" int xs_icp_deriv_times(float *ms, int *npix, int max_n) {
     int n = 0;
+    if (!g_last_timed) return 0;
+    IcpScratch &g_icp = *g_last_timed;
     for (; n < g_icp.n_timed && n < max_n; ++n) {
         if (cudaEventElapsedTime(&ms[n], g_icp.ev0[n], g_icp.ev1[n]) != cudaSuccess) break;
         npix[n] = g_icp.timed_npix[n];
@@ -1212,9 +1269,11 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
         return XS_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t) stream;
-    int rc = icp_reserve(ncomp, rows * cols, 0, 0);
+    IcpScratch *scp = seam_scratch();
+    IcpScratch &g_icp = *scp;
+    int rc = icp_reserve(scp, ncomp, rows * cols, 0, 0);
     if (rc != XS_OK) return rc;
-    icp_timing_reset();
+    icp_timing_reset(scp);
     XS_CUDA(cudaStreamSynchronize(s));  // pinned staging reuse
     float *h = g_icp.h_pose;
     for (int e = 0; e < 9; ++e) h[e] = curr->R[e];
@@ -1225,7 +1284,7 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
         for (int e = 0; e < 3; ++e) hc[9 + e] = curr->dt[q * 3 + e];
     }
     XS_CUDA(cudaMemcpyAsync(g_icp.d_pose, h, (size_t) (1 + ncomp) * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = icp_iteration_async(g_icp.d_pose, d_vmap_curr, d_nmap_curr, prev, intr, d_vmap_g_prev, d_nmap_g_prev, rows, cols,
+    rc = icp_iteration_async(scp, g_icp.d_pose, d_vmap_curr, d_nmap_curr, prev, intr, d_vmap_g_prev, d_nmap_g_prev, rows, cols,
                              comps, dirs, dist_thres, angle_thres, nullptr, 0, nullptr, nullptr, s, nullptr, 0);
     if (rc != XS_OK) return rc;
     const int nvals = 27 * (1 + ncomp);
@@ -1258,8 +1317,10 @@ extern "C" long xs_compute_optimize_matrix(const xs_pose *curr, const float *d_v
         return -1;
     }
     cudaStream_t s = (cudaStream_t) stream;
-    if (icp_reserve(0, rows * cols, 0, 0) != XS_OK) return -1;
-    const int grid = 296;
+    IcpScratch *scp = seam_scratch();
+    IcpScratch &g_icp = *scp;
+    if (icp_reserve(scp, 0, rows * cols, 0, 0) != XS_OK) return -1;
+    const int grid = 2 * sm_count();
     double *d_buf = nullptr;
     if (cudaMalloc(&d_buf, ((size_t) (grid + 1) * OPT_VALS + 1) * sizeof(double) + 12 * sizeof(float)) != cudaSuccess) {
         set_error("xs_compute_optimize_matrix: cudaMalloc failed");

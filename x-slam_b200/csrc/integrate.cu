@@ -427,7 +427,7 @@ void xs_volume_destroy(xs_volume *v) {
 int xs_volume_reset(xs_volume *v, void *stream) {
     if (!v) return XS_ERR_ARG;
     size_t nvox = (size_t) v->view.rx * v->view.ry * v->view.rz;
-    reset_volume_kernel<<<148 * 8, 256, 0, (cudaStream_t) stream>>>(v->view.value, v->view.weight, v->view.deriv, nvox,
+    reset_volume_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t) stream>>>(v->view.value, v->view.weight, v->view.deriv, nvox,
                                                                      nvox * v->view.ncomp);
     XS_LAUNCH_CHECK();
     XS_CUDA(cudaMemsetAsync(v->d_live, 0, nvox / BRICK_VOX, (cudaStream_t) stream));
@@ -441,14 +441,14 @@ float xs_volume_last_integrate_ms(const xs_volume *v) { return v ? v->last_kerne
 
 int xs_volume_export_planes(const xs_volume *v, int comp, float *d_value, int *d_weight, float *d_grad, void *stream) {
     if (!v || (d_grad && (comp < 0 || comp >= v->view.ncomp))) return XS_ERR_ARG;
-    convert_planes_kernel<true><<<148 * 8, 256, 0, (cudaStream_t) stream>>>(v->view, comp, d_value, d_weight, d_grad);
+    convert_planes_kernel<true><<<sm_count() * 8, 256, 0, (cudaStream_t) stream>>>(v->view, comp, d_value, d_weight, d_grad);
     XS_LAUNCH_CHECK();
     return XS_OK;
 }
 int xs_volume_import_planes(xs_volume *v, int comp, const float *d_value, const int *d_weight, const float *d_grad,
                             void *stream) {
     if (!v || (d_grad && (comp < 0 || comp >= v->view.ncomp))) return XS_ERR_ARG;
-    convert_planes_kernel<false><<<148 * 8, 256, 0, (cudaStream_t) stream>>>(
+    convert_planes_kernel<false><<<sm_count() * 8, 256, 0, (cudaStream_t) stream>>>(
         v->view, comp, const_cast<float *>(d_value), const_cast<int *>(d_weight), const_cast<float *>(d_grad));
     XS_LAUNCH_CHECK();
     if (d_grad)  // imported derivative planes may be non-zero anywhere
@@ -549,7 +549,7 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
     P.tile_max = v->d_tile_max;
     cull_bricks_kernel<<<div_up(P.nbricks, 256), 256, 0, s>>>(P, v->d_brick_list);
     XS_LAUNCH_CHECK();
-    int grid = 2 * P.nbricks < 148 * 24 ? 2 * P.nbricks : 148 * 24;
+    int grid = 2 * P.nbricks < sm_count() * 24 ? 2 * P.nbricks : sm_count() * 24;
     size_t smem = (size_t) (v->view.ncomp > 0 ? v->view.ncomp : 1) * 12 * sizeof(float);
     XS_CUDA(cudaEventRecord(v->ev_k0, s));
     if (v->comps == 1)

@@ -26,11 +26,14 @@ namespace xs {
 void set_error(const std::string &msg);
 extern long long g_launches;
 // icp.cu: one Gauss-Newton iteration queued on the stream, no host round trip
-int icp_iteration_async(const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
+struct IcpScratch;
+IcpScratch *icp_scratch_create();
+void icp_scratch_destroy(IcpScratch *sc);
+int icp_iteration_async(IcpScratch *sc, const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
                         xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
                         int dirs, float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
                         double *d_log, cudaStream_t s, cudaStream_t s_real, int slot);
-void icp_timing_reset();
+void icp_timing_reset(IcpScratch *sc);
 // integrate.cu: pose-independent head of the integration (metric depth, tile maxima, cleared counters)
 int integrate_prepare(xs_volume *v, const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, cudaStream_t s);
 }  // namespace xs
@@ -45,6 +48,17 @@ using namespace xs;
         }                                                                                    \
     } while (0)
 
+// xs_kinfu_pose_estimate returns 1 / 0 like the reference's AlignDepthToReconstruction: a CUDA failure is "not aligned" (0)
+// with the error text set, never a negative status that a caller's `if (!aligned)` would read as success.
+#define KCUDA0(expr)                                                                         \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            set_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at kinfu.cpp:" + std::to_string(__LINE__)); \
+            return 0;                                                                        \
+        }                                                                                    \
+    } while (0)
+
 struct xs_kinfu {
     xs_config cfg;
     int comps, dirs, ncomp, solve_mode;
@@ -52,9 +66,11 @@ struct xs_kinfu {
     HMat4 world2camera, world2volume;
     std::vector<HMat4> record;  // world2camera_record
     int frame_id = 0;
+    int frame_step = 1;  // KinectFusionReconstruction.cpp:72: frame_id += frame_step after every processed frame
     int icp_iterations[3] = {5, 4, 3};  // KinectFusionReconstruction.cpp:54
     float angle_thres;
     xs_volume *volume = nullptr;
+    IcpScratch *icp = nullptr;  // ICP scratch of this pipeline (records, sums, tickets, events): nothing process-wide
     cudaStream_t stream = nullptr;
     uint16_t *d_depth2[2] = {nullptr, nullptr};  // uploaded host frames, alternating (the previous frame may still be integrating)
     int depth_idx = 0;
@@ -172,6 +188,7 @@ xs_kinfu *xs_kinfu_create(const xs_config *cfg, int comps, int dirs, const float
     k->dirs = dirs;
     k->ncomp = comps * dirs;
     k->solve_mode = solve_mode;
+    k->frame_step = cfg->frame_step > 0 ? cfg->frame_step : 1;
     k->intr = xs_intr{cfg->fx, cfg->fy, cfg->cx, cfg->cy};
     // KinectFusionReconstruction.cpp:21-38
     k->world2camera = HMat4::identity();
@@ -229,6 +246,7 @@ xs_kinfu *xs_kinfu_create(const xs_config *cfg, int comps, int dirs, const float
         xs_kinfu_destroy(k);
         return nullptr;
     }
+    k->icp = icp_scratch_create();
     k->volume = xs_volume_create(cfg->res, cfg->voxel_size, cfg->thres_range, comps, dirs);  // :66-67
     if (!k->volume) {
         xs_kinfu_destroy(k);
@@ -241,6 +259,8 @@ void xs_kinfu_destroy(xs_kinfu *k) {
     if (!k) return;
     if (k->stream) cudaStreamSynchronize(k->stream);
     xs_volume_destroy(k->volume);
+    if (k->stream_real) cudaStreamSynchronize(k->stream_real);
+    icp_scratch_destroy(k->icp);
     cudaFree(k->d_depth2[0]);
     cudaFree(k->d_depth2[1]);
     cudaFreeHost(k->h_depth);
@@ -298,7 +318,7 @@ int xs_kinfu_pose_estimate(xs_kinfu *k) {
     set_ctx(k);
     k->icp_iters_done = 0;
     k->icp_log.clear();
-    icp_timing_reset();
+    icp_timing_reset(k->icp);
     if (k->use_gt_pose) return 1;  // mapping with known poses: AlignDepthToReconstruction returns before ICP, :164-166
     if (k->frame_id == 0) return 0;
     const xs_config &c = k->cfg;
@@ -318,24 +338,24 @@ int xs_kinfu_pose_estimate(xs_kinfu *k) {
             h[9 + i] = q == 0 ? tprev.v[i].v : tprev.v[i].d[q - 1];
         }
     }
-    KCUDA(cudaMemcpyAsync(k->d_pose_slot(0), k->h_pose, pose_floats * sizeof(float), cudaMemcpyHostToDevice, k->stream));
-    KCUDA(cudaMemsetAsync(k->d_status, 0, 2 * sizeof(int), k->stream));
+    KCUDA0(cudaMemcpyAsync(k->d_pose_slot(0), k->h_pose, pose_floats * sizeof(float), cudaMemcpyHostToDevice, k->stream));
+    KCUDA0(cudaMemsetAsync(k->d_status, 0, 2 * sizeof(int), k->stream));
     // with derivative components the real chain (association + real step per iteration) runs ahead on its own stream
     const bool split = ncomp > 0 && !getenv("XS_ICP_NO_SPLIT");
     if (split) {
-        KCUDA(cudaEventRecord(k->ev_icp_start, k->stream));
-        KCUDA(cudaStreamWaitEvent(k->stream_real, k->ev_icp_start, 0));
+        KCUDA0(cudaEventRecord(k->ev_icp_start, k->stream));
+        KCUDA0(cudaStreamWaitEvent(k->stream_real, k->ev_icp_start, 0));
     }
     const size_t log_stride = (size_t) 27 * (1 + ncomp);
     if (k->log_icp && !k->d_icp_log) {
-        KCUDA(cudaMalloc((void **) &k->d_icp_log, 16 * log_stride * sizeof(double)));
-        KCUDA(cudaMallocHost((void **) &k->h_icp_log, 16 * log_stride * sizeof(double)));
+        KCUDA0(cudaMalloc((void **) &k->d_icp_log, 16 * log_stride * sizeof(double)));
+        KCUDA0(cudaMallocHost((void **) &k->h_icp_log, 16 * log_stride * sizeof(double)));
     }
     int it = 0;
     for (int level = c.num_levels - 1; level >= 0; --level) {
         const int rows = c.height >> level, cols = c.width >> level;
         for (int iter = 0; iter < k->icp_iterations[level]; ++iter, ++it) {
-            const int rc = icp_iteration_async(k->d_pose_slot(it), k->vmaps_curr[level], k->nmaps_curr[level], &prev_pose,
+            const int rc = icp_iteration_async(k->icp, k->d_pose_slot(it), k->vmaps_curr[level], k->nmaps_curr[level], &prev_pose,
                                                level_intr(k->intr, level), k->vmaps_prev[level], k->nmaps_prev[level], rows,
                                                cols, k->comps, k->dirs, c.dist_thres, k->angle_thres, k->d_pose_slot(it + 1),
                                                k->solve_mode, k->d_status,
@@ -347,21 +367,21 @@ int xs_kinfu_pose_estimate(xs_kinfu *k) {
             }
         }
     }
-    KCUDA(cudaMemcpyAsync(k->h_pose, k->d_pose_slot(it), pose_floats * sizeof(float), cudaMemcpyDeviceToHost, k->stream));
-    KCUDA(cudaMemcpyAsync(k->h_status, k->d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, k->stream));
+    KCUDA0(cudaMemcpyAsync(k->h_pose, k->d_pose_slot(it), pose_floats * sizeof(float), cudaMemcpyDeviceToHost, k->stream));
+    KCUDA0(cudaMemcpyAsync(k->h_status, k->d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, k->stream));
     if (k->log_icp)
-        KCUDA(cudaMemcpyAsync(k->h_icp_log, k->d_icp_log, (size_t) (it < 16 ? it : 16) * log_stride * sizeof(double),
+        KCUDA0(cudaMemcpyAsync(k->h_icp_log, k->d_icp_log, (size_t) (it < 16 ? it : 16) * log_stride * sizeof(double),
                               cudaMemcpyDeviceToHost, k->stream));
     if (k->next_depth) {
         // ProcessFrame: the pose-independent head of the integration runs on the device while the host turns the ICP
         // result into the volume-to-camera pose; the host waits for the download only
-        KCUDA(cudaEventRecord(k->ev_icp, k->stream));
+        KCUDA0(cudaEventRecord(k->ev_icp, k->stream));
         xs_volume_set_pipelined(k->volume, 1);
         if (integrate_prepare(k->volume, k->next_depth, c.width * sizeof(uint16_t), c.height, c.width, k->stream) != XS_OK)
             return 0;
-        KCUDA(cudaEventSynchronize(k->ev_icp));
+        KCUDA0(cudaEventSynchronize(k->ev_icp));
     } else {
-        KCUDA(cudaStreamSynchronize(k->stream));
+        KCUDA0(cudaStreamSynchronize(k->stream));
     }
     k->h_depth_free = true;  // everything queued before the ICP download has completed
     k->icp_iters_done = it;
@@ -495,7 +515,7 @@ int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_devi
     cudaEventRecord(ev[2], k->stream);
     k->launches[1] = g_launches - l0;
     l0 = g_launches;
-    if (k->frame_id > 0 && !aligned) {
+    if (aligned < 0 || (k->frame_id > 0 && !aligned)) {
         fprintf(stderr, "Frame align failed!\n");
         xs_volume_set_pipelined(k->volume, 0);  // drops the queued integration head: the volume is not touched
         cudaStreamSynchronize(k->stream);
@@ -530,7 +550,7 @@ int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_devi
     k->launches[3] = g_launches - l0;
     if (k->deferred) {  // pose and status are final (the ICP result was read on the host); the volume and the maps follow
         k->pending = true;
-        k->frame_id += 1;
+        k->frame_id += k->frame_step;
         return 1;
     }
     if (cudaStreamSynchronize(k->stream) != cudaSuccess) {
@@ -539,7 +559,7 @@ int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_devi
     }
     k->h_depth_free = true;
     collect_frame(k);
-    k->frame_id += 1;
+    k->frame_id += k->frame_step;  // KinectFusionReconstruction.cpp:157
     return 1;
 }
 

@@ -301,7 +301,7 @@ extern "C" int xs_tsdf_hessian(const uint16_t *d_depth, size_t depth_step_bytes,
         return XS_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t) stream;
-    const int grid = 148 * 8;
+    const int grid = sm_count() * 8;
     float *d_scaled = nullptr;
     double *d_part = nullptr;
     unsigned int *d_ticket = nullptr;
@@ -346,7 +346,7 @@ extern "C" int xs_tsdf_loss(const uint16_t *d_depth, size_t depth_step_bytes, in
         return XS_ERR_ARG;
     }
     cudaStream_t s = (cudaStream_t) stream;
-    const int grid = 148 * 8;
+    const int grid = sm_count() * 8;
     float *d_scaled = nullptr;
     double *d_part = nullptr;
     unsigned int *d_ticket = nullptr;
@@ -395,7 +395,7 @@ extern "C" int xs_tsdf_hessian_batch(const uint16_t *d_depth, size_t depth_step_
     }
     const int dirs = v2c->ncomp / 3;
     cudaStream_t s = (cudaStream_t) stream;
-    const int grid = 148 * 8;
+    const int grid = sm_count() * 8;
     float *d_scaled = nullptr;
     double *d_part = nullptr;
     unsigned int *d_ticket = nullptr;

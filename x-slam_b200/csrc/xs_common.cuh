@@ -30,6 +30,9 @@ extern long long g_launches;  // kernels launched by this library (xs_launch_cou
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }  // cx::divUp, cx.h:131
 
+// Streaming multiprocessors of the current device (148 on B200): persistent grids are sized in multiples of it.
+int sm_count();
+
 // ---- brick-tiled volume ------------------------------------------------------------------
 // 8x8x8 bricks, x fastest inside a brick and across bricks:
 //   value [brick][512] float, weight [brick][512] int32, deriv [brick][ncomp][512] float

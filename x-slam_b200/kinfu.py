@@ -64,6 +64,7 @@ def make_config(cfg):
     c.angle_thres_deg = float(cfg["angleThres"])
     c.bi_threshold = float(cfg["biInterpolate_threshold"])
     c.trunc_k = float(cfg["trunc_logistic_k"])
+    c.frame_step = int(cfg.get("frame_step", 1))  # KinectFusionReconstruction.cpp:72
     return c
 
 
