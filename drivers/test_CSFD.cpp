@@ -1,11 +1,15 @@
-// test_CSFD — the bicomplex demo of Experiments/test_CSFD/main.cpp:88-219 on the packed-SoA device arrays.
-//   1. complex-step arithmetic on arrays of n = 10^6 bicomplex numbers (value | eps1 | eps2 | eps1eps2 planes):
-//      * / exp sin pow at a = (0.5, h), b = (-1.5, h) — the five value pairs the reference prints (main.cpp:90-191) —
-//      timed per launch (the reference times 10^6 scalar host calls);
-//   2. the DCSFD chain-rule self check (main.cpp:194-219): t = ((0.5, h), (h, 0)), x = t*t, y = sin t,
-//      loss = (x + y)^2; gradient = loss.eps1 / h, second order = loss.eps1eps2 / h^2, next to the analytic chain rule.
-// Host C++ over the C-ABI (xs_dc_apply, xs_dc_chain); fails loudly without a CUDA device.
-#include "../include/xslam_b200.h"
+// test_CSFD — the DCSFD demo of Experiments/test_CSFD/main.cpp:88-219, written against this repo's number types the way the
+// reference writes it against its own:
+//   1. "simple test for complex acceleration" (main.cpp:90-191): the five complex-step operations * / exp sin pow at
+//      a = (0.5, h), b = (-1.5, h) - printed as value pairs ("ours", i.e. the truncated first-order form, beside std::complex)
+//      - and, as the B200 counterpart of the reference's 10^6-iteration host loops, the same operations on packed-SoA device
+//      arrays of 10^6 bicomplex elements (xslam_b200::DeviceArray4 over xs_dc_apply), timed per launch;
+//   2. "test high order chain rule" (main.cpp:193-219): t = ((0.5, h), (h, 0)), x = t*t, y = sin t, loss = f1(x, y) with the
+//      host scalar xslam_b200::DoubleComplex: gradient = loss.real().imag() / h, second order = loss.imag().imag() / h^2,
+//      next to the chain rule assembled from partial derivatives exactly as the reference does; the same chain evaluated on
+//      the device (xs_dc_chain) must print the same two numbers.
+// Host C++ over the C-ABI; the device part fails loudly without a CUDA device (no CPU fallback for device arrays).
+#include "../include/xslam_dcomplex.hpp"
 
 #include <chrono>
 #include <cmath>
@@ -13,71 +17,90 @@
 #include <iostream>
 #include <vector>
 
-int xs_driver_device_alloc(float **p, size_t floats);
-int xs_driver_device_download(float *dst, const float *src, size_t floats);
-int xs_driver_device_upload(float *dst, const float *src, size_t floats);
-void xs_driver_device_free(float *p);
+using xslam_b200::DeviceArray4;
+using xslam_b200::DoubleComplex;
+using xslam_b200::MyFloat;
+using xslam_b200::SingleComplex;
+
+static DoubleComplex f1(DoubleComplex x, DoubleComplex y) { return (x + y) * (x + y); }  // main.cpp:9-12
+
+// first-order ("ours") forms of main.cpp:17-86: the real part ignores h^2 terms
+static SingleComplex mul_first_order(SingleComplex a, SingleComplex b) { return {a.real() * b.real(), a.imag() * b.real() + a.real() * b.imag()}; }
+static SingleComplex div_first_order(SingleComplex a, SingleComplex b) {
+    return {a.real() / b.real(), (a.imag() * b.real() - a.real() * b.imag()) / (b.real() * b.real() + b.imag() * b.imag())};
+}
+static SingleComplex exp_first_order(SingleComplex a) { return {std::exp(a.real()), std::exp(a.real()) * std::sin(a.imag())}; }
+static SingleComplex sin_first_order(SingleComplex a) { return {std::sin(a.real()), -std::sinh(-a.imag()) * std::cos(a.real())}; }
+static SingleComplex pow_first_order(SingleComplex a, int n) { return {std::pow(a.real(), n), std::pow(std::norm(a), n) * std::sin(n * std::arg(a))}; }
 
 int main() {
-    const long n = 1000000;  // launch_number, main.cpp:94
-    const float h = 1e-6f;   // main.cpp:93
-    float *d_a, *d_b, *d_o;
-    if (xs_driver_device_alloc(&d_a, 4 * n) || xs_driver_device_alloc(&d_b, 4 * n) || xs_driver_device_alloc(&d_o, 4 * n)) {
-        std::cerr << "test_CSFD needs a CUDA device (libxslam_b200 has no CPU fallback)\n";
-        return -1;
-    }
-    std::vector<float> a(4 * n, 0.f), b(4 * n, 0.f), o(4 * n);
-    for (long i = 0; i < n; ++i) {
-        a[i] = 0.5f, a[n + i] = h;   // a = (0.5, h): value plane, eps1 plane
-        b[i] = -1.5f, b[n + i] = h;  // b = (-1.5, h)
-    }
-    xs_driver_device_upload(d_a, a.data(), 4 * n);
-    xs_driver_device_upload(d_b, b.data(), 4 * n);
-    std::cout << "1. simple test for complex acceleration (" << n << " bicomplex elements per launch)" << std::endl;
-    // c = a + b = (-1, 2h): the argument the reference feeds to exp and sin (main.cpp:130-171)
-    float *d_c;
-    if (xs_driver_device_alloc(&d_c, 4 * n) || xs_dc_apply(XS_DC_ADD, d_a, d_b, 0.f, d_c, n, nullptr) != XS_OK) {
-        std::cerr << "xs_dc_apply failed: " << xs_last_error() << "\n";
+    const float h = 1e-6f;       // main.cpp:93
+    const long n = 1000000;      // launch_number, main.cpp:94
+    std::cout << "1. simple test for complex acceleration" << std::endl;
+    const SingleComplex a(0.5f, h), b(-1.5f, h);
+    std::cout << "multiplication value: " << mul_first_order(a, b) << "\t" << a * b << std::endl;
+    std::cout << "division value: " << div_first_order(a, b) << "\t" << a / b << std::endl;
+    std::cout << "exp value: " << exp_first_order(a + b) << "\t" << std::exp(a + b) << std::endl;
+    std::cout << "sin value: " << sin_first_order(a + b) << "\t" << std::sin(a + b) << std::endl;
+    std::cout << "pow value: " << pow_first_order(a + b, 3) << "\t" << std::pow(a + b, 3) << std::endl;
+
+    // the same operations on device arrays of n bicomplex elements (value | eps1 | eps2 | eps1eps2 planes)
+    std::vector<DoubleComplex> ha(n, DoubleComplex(0.5f, h, 0.f, 0.f)), hb(n, DoubleComplex(-1.5f, h, 0.f, 0.f)), ho;
+    DeviceArray4 da, db, dc, dout;
+    if (!da.upload(ha) || !db.upload(hb) || !da.apply(XS_DC_ADD, &db, 0.f, dc)) {
+        std::cerr << "test_CSFD needs a CUDA device (libxslam_b200 has no CPU fallback): " << xs_last_error() << "\n";
         return -1;
     }
     struct Op {
         const char *name;
-        int op;
+        xs_dc_op op;
         float p;
-        const float *x;
-    } ops[] = {{"multiplication a*b", XS_DC_MUL, 0, d_a}, {"division a/b", XS_DC_DIV, 0, d_a}, {"exp(a+b)", XS_DC_EXP, 0, d_c},
-               {"sin(a+b)", XS_DC_SIN, 0, d_c}, {"pow(a,3)", XS_DC_POW, 3, d_a}};
+        const DeviceArray4 *x;
+    } ops[] = {{"multiplication", XS_DC_MUL, 0, &da}, {"division", XS_DC_DIV, 0, &da}, {"exp", XS_DC_EXP, 0, &dc}, {"sin", XS_DC_SIN, 0, &dc},
+               {"pow", XS_DC_POW, 3, &dc}};
     for (const Op &op : ops) {
-        if (xs_dc_apply(op.op, op.x, d_b, op.p, d_o, n, nullptr) != XS_OK) {  // warm-up
+        if (!op.x->apply(op.op, &db, op.p, dout) || !dout.download(ho)) {  // warm-up launch + result
             std::cerr << "xs_dc_apply failed: " << xs_last_error() << "\n";
             return -1;
         }
-        xs_driver_device_download(o.data(), d_o, 4 * n);
-        const auto t0 = std::chrono::steady_clock::now();
         const int reps = 20;
-        for (int r = 0; r < reps; ++r) xs_dc_apply(op.op, op.x, d_b, op.p, d_o, n, nullptr);
-        xs_driver_device_download(o.data(), d_o, 4);  // synchronises
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int r = 0; r < reps; ++r) op.x->apply(op.op, &db, op.p, dout);
+        DeviceArray4 probe;
+        dout.copyTo(probe);  // blocking: the launches above have completed
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / reps;
-        std::cout << "run our " << op.name << std::endl;
+        std::cout << "run our " << op.name << " on the device" << std::endl;
         printf("mean compute time = %.3f ms per %ld elements\n", ms, n);
-        std::cout << "result = (" << o[0] << "," << o[n] << ")" << std::endl;
+        std::cout << "value: " << ho[0].real() << std::endl;
     }
-    std::cout << "2. test for DCSFD" << std::endl;
-    std::vector<float> t(n, 0.5f);
-    xs_driver_device_upload(d_a, t.data(), n);
-    if (xs_dc_chain(d_a, h, d_o, n, nullptr) != XS_OK) {
+
+    // main.cpp:193-219
+    std::cout << "2. test high order chain rule by compute f1(x,y)=(x+y)^2, x=t*t,  y=sin(t)" << std::endl;
+    DoubleComplex t(0.5f);
+    t.addPerturbation();  // t + i h + j h, h = 1e-6 (DoubleComplex.cpp:61-66)
+    const DoubleComplex x = t * t, y = sin(t), loss = f1(x, y);
+    std::cout << "a. compute gradient and second order differentiation by DCSFD" << std::endl;
+    std::cout << "gradient = " << loss.grad() / h << std::endl;
+    std::cout << "second order differentiation = " << loss.hessian() / h / h << std::endl;
+    // b. the chain rule from partial derivatives, each obtained by seeding one argument of f1 (main.cpp:206-219)
+    const float xv = x.value(), yv = y.value();
+    const DoubleComplex both_x(xv, h, h, 0), both_y(yv, h, h, 0), plain_x(xv), plain_y(yv);
+    const float fx = f1(both_x, plain_y).grad() / h, fy = f1(plain_x, both_y).grad() / h;
+    const float fxx = f1(both_x, plain_y).hessian() / h / h, fyy = f1(plain_x, both_y).hessian() / h / h;
+    const float fxy = f1(DoubleComplex(xv, h, 0, 0), DoubleComplex(yv, 0, h, 0)).hessian() / h / h;
+    const float xt = x.grad() / h, xtt = x.hessian() / h / h, yt = y.grad() / h, ytt = y.hessian() / h / h;
+    std::cout << "b. compute gradient and second order differentiation by chain rule" << std::endl;
+    std::cout << "gradient = " << fx * xt + fy * yt << std::endl;
+    std::cout << "second order differentiation = " << fx * xtt + fy * ytt + xt * xt * fxx + yt * yt * fyy + 2 * xt * yt * fxy << std::endl;
+    // c. the same chain on the device arrays (xs_dc_chain takes the real parts of t and seeds them itself)
+    DeviceArray4 dt_, dl;
+    std::vector<DoubleComplex> ht(n, DoubleComplex(0.5f)), hl;
+    if (!dt_.upload(ht) || !dl.create(n) || xs_dc_chain(dt_.ptr(), h, dl.ptr(), n, nullptr) != XS_OK || !dl.download(hl)) {
         std::cerr << "xs_dc_chain failed: " << xs_last_error() << "\n";
         return -1;
     }
-    xs_driver_device_download(o.data(), d_o, 4 * n);
-    std::cout << "DCSFD result: " << std::endl;
-    std::cout << "gradient = " << o[n] / h << std::endl;
-    std::cout << "second order differentiation = " << o[3 * n] / h / h << std::endl;
-    // chain rule: f = (x + y)^2, x = t^2, y = sin t
-    const double tt = 0.5, x = tt * tt, y = std::sin(tt), dx = 2 * tt, dy = std::cos(tt);
-    std::cout << "chain rule result: " << std::endl;
-    std::cout << "gradient = " << 2 * (x + y) * (dx + dy) << std::endl;
-    std::cout << "second order differentiation = " << 2 * (dx + dy) * (dx + dy) + 2 * (x + y) * (2 - std::sin(tt)) << std::endl;
-    xs_driver_device_free(d_a), xs_driver_device_free(d_b), xs_driver_device_free(d_o), xs_driver_device_free(d_c);
+    std::cout << "c. the same chain on " << n << " device elements (packed-SoA DeviceArray4)" << std::endl;
+    std::cout << "gradient = " << hl[n / 2].grad() / h << std::endl;
+    std::cout << "second order differentiation = " << hl[n / 2].hessian() / h / h << std::endl;
     return 0;
 }

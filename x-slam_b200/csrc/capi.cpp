@@ -5,6 +5,7 @@
 // replaces the dataset readers (XKinectFusion/src/Dataset.cpp), which need files that do not exist
 // offline; its scene, intrinsics and depth encoding are the ones fixed by SURVEY.md §8(d).
 #include "../../include/xslam_b200.h"
+#include "../../include/xslam_dcomplex.hpp"
 
 #include <cuda_runtime_api.h>
 
@@ -61,6 +62,38 @@ extern "C" {
 const char *xs_last_error(void) { return xs::g_error.c_str(); }
 int xs_version(void) { return 100; }
 long long xs_launch_count(void) { return xs::g_launches; }
+
+// The host number type of include/xslam_dcomplex.hpp evaluated element-wise over host AoS arrays (n x 4 floats).  The
+// reference's DoubleComplex is a HOST type (DeviceArray/src/DoubleComplex.cpp), so this is the host side of the API surface,
+// not a fallback for any device path; tests hold it against the reference's own DoubleComplex.cpp.
+int xs_dc_host_apply(int op, const float *a_aos, const float *b_aos, float p, float *out_aos, long n) {
+    using xslam_b200::DoubleComplex;
+    if (!a_aos || !out_aos || n < 0 || op < 0 || op > XS_DC_ATAN) return XS_ERR_ARG;
+    const bool binary = op <= XS_DC_DIV || op == XS_DC_ATAN2;
+    if (binary && !b_aos) return XS_ERR_ARG;
+    for (long i = 0; i < n; ++i) {
+        const DoubleComplex a(a_aos[4 * i], a_aos[4 * i + 1], a_aos[4 * i + 2], a_aos[4 * i + 3]);
+        const DoubleComplex b = binary ? DoubleComplex(b_aos[4 * i], b_aos[4 * i + 1], b_aos[4 * i + 2], b_aos[4 * i + 3]) : DoubleComplex();
+        DoubleComplex r;
+        switch (op) {
+        case XS_DC_ADD: r = a + b; break;
+        case XS_DC_SUB: r = a - b; break;
+        case XS_DC_MUL: r = a * b; break;
+        case XS_DC_DIV: r = a / b; break;
+        case XS_DC_SQRT: r = sqrt(a); break;
+        case XS_DC_EXP: r = exp(a); break;
+        case XS_DC_LOG: r = log(a); break;
+        case XS_DC_SIN: r = sin(a); break;
+        case XS_DC_COS: r = cos(a); break;
+        case XS_DC_ATAN2: r = atan2(a, b); break;
+        case XS_DC_POW: r = pow(a, p); break;
+        default: r = atan(a); break;
+        }
+        out_aos[4 * i] = r.real().real(), out_aos[4 * i + 1] = r.real().imag();
+        out_aos[4 * i + 2] = r.imag().real(), out_aos[4 * i + 3] = r.imag().imag();
+    }
+    return XS_OK;
+}
 
 int xs_save_pose_txt(const char *path, const float *m16) {
     if (!path || !m16) return XS_ERR_ARG;

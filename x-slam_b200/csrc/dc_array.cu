@@ -168,11 +168,96 @@ __global__ void __launch_bounds__(256) dc_chain_kernel(const float *__restrict__
     }
 }
 
+// AoS (the host DoubleComplex object: re.re, re.im, im.re, im.im - DoubleComplex.h:15-19) <-> packed-SoA planes
+__global__ void dc_aos_to_soa_kernel(const float4 *__restrict__ aos, float *__restrict__ soa, long n) {
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x) {
+        const float4 v = aos[i];
+        soa[i] = v.x, soa[n + i] = v.y, soa[2 * n + i] = v.z, soa[3 * n + i] = v.w;
+    }
+}
+__global__ void dc_soa_to_aos_kernel(const float *__restrict__ soa, float4 *__restrict__ aos, long n) {
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long) gridDim.x * blockDim.x)
+        aos[i] = make_float4(soa[i], soa[n + i], soa[2 * n + i], soa[3 * n + i]);
+}
+
 }  // namespace xs
+
+// Owning packed-SoA bicomplex array with the semantics of the reference's DeviceArray<T> (device_array.hpp:25-134,
+// device_memory.cpp:72-178): create(n) is a no-op when the size is unchanged, upload / download block and synchronise,
+// copyTo is a deep copy that (re)creates the destination, release frees.
+struct xs_dc_array {
+    float *d = nullptr;      // float[4][n]: value | eps1 | eps2 | eps1eps2
+    float4 *stage = nullptr;  // device staging for the AoS <-> SoA conversion
+    long n = 0;
+};
 
 using namespace xs;
 
 extern "C" {
+
+xs_dc_array *xs_dc_array_create(long n) {
+    int ndev = 0;
+    if (n < 0 || cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("xs_dc_array_create: no CUDA device (libxslam_b200 has no CPU fallback) or negative size");
+        return nullptr;
+    }
+    xs_dc_array *a = new xs_dc_array();
+    if (xs_dc_array_resize(a, n) != XS_OK) {
+        delete a;
+        return nullptr;
+    }
+    return a;
+}
+void xs_dc_array_release(xs_dc_array *a) {
+    if (!a) return;
+    cudaFree(a->d);
+    cudaFree(a->stage);
+    delete a;
+}
+int xs_dc_array_resize(xs_dc_array *a, long n) {  // DeviceArray::create
+    if (!a || n < 0) return XS_ERR_ARG;
+    if (n == a->n) return XS_OK;
+    cudaFree(a->d);
+    cudaFree(a->stage);
+    a->d = nullptr, a->stage = nullptr, a->n = 0;
+    if (n > 0) {
+        XS_CUDA(cudaMalloc(&a->d, (size_t) n * 4 * sizeof(float)));
+        XS_CUDA(cudaMalloc(&a->stage, (size_t) n * sizeof(float4)));
+    }
+    a->n = n;
+    return XS_OK;
+}
+long xs_dc_array_size(const xs_dc_array *a) { return a ? a->n : 0; }
+float *xs_dc_array_ptr(xs_dc_array *a) { return a ? a->d : nullptr; }
+int xs_dc_array_upload(xs_dc_array *a, const float *host_aos, long n) {  // DeviceArray::upload (create + blocking copy)
+    if (!a || (n > 0 && !host_aos)) return XS_ERR_ARG;
+    const int rc = xs_dc_array_resize(a, n);
+    if (rc != XS_OK || n == 0) return rc;
+    XS_CUDA(cudaMemcpy(a->stage, host_aos, (size_t) n * sizeof(float4), cudaMemcpyHostToDevice));
+    const int grid = (int) (n / 256 + 1 < sm_count() * 8 ? n / 256 + 1 : sm_count() * 8);
+    dc_aos_to_soa_kernel<<<grid, 256>>>(a->stage, a->d, n);
+    XS_LAUNCH_CHECK();
+    XS_CUDA(cudaDeviceSynchronize());  // device_memory.cpp:141-146 synchronises after the copy
+    return XS_OK;
+}
+int xs_dc_array_download(const xs_dc_array *a, float *host_aos) {  // DeviceArray::download
+    if (!a || (a->n > 0 && !host_aos)) return XS_ERR_ARG;
+    if (a->n == 0) return XS_OK;
+    const int grid = (int) (a->n / 256 + 1 < sm_count() * 8 ? a->n / 256 + 1 : sm_count() * 8);
+    dc_soa_to_aos_kernel<<<grid, 256>>>(a->d, a->stage, a->n);
+    XS_LAUNCH_CHECK();
+    XS_CUDA(cudaMemcpy(host_aos, a->stage, (size_t) a->n * sizeof(float4), cudaMemcpyDeviceToHost));
+    XS_CUDA(cudaDeviceSynchronize());
+    return XS_OK;
+}
+int xs_dc_array_copy(const xs_dc_array *src, xs_dc_array *dst) {  // DeviceArray::copyTo
+    if (!src || !dst) return XS_ERR_ARG;
+    const int rc = xs_dc_array_resize(dst, src->n);
+    if (rc != XS_OK || src->n == 0) return rc;
+    XS_CUDA(cudaMemcpy(dst->d, src->d, (size_t) src->n * 4 * sizeof(float), cudaMemcpyDeviceToDevice));
+    XS_CUDA(cudaDeviceSynchronize());
+    return XS_OK;
+}
 
 int xs_dc_apply(int op, const float *d_a, const float *d_b, float p, float *d_out, long n, void *stream) {
     if (!d_a || !d_out || n <= 0 || op < 0 || op > XS_DC_ATAN) return XS_ERR_ARG;
