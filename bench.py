@@ -37,8 +37,12 @@ def parse():
                          "is steps x frames-per-step frames so that it lasts ~1 s at the default flags")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--res", type=int, default=512)
-    ap.add_argument("--dirs", type=int, default=55)
-    ap.add_argument("--comps", type=int, default=3)
+    ap.add_argument("--dirs", type=int, default=55, help="bicomplex directions (mode dcsfd / hessian: pairs of the parameters) or first-order directions (csfd)")
+    ap.add_argument("--comps", type=int, default=3, help="legacy selector: 1 = --mode csfd, 3 = the default DCSFD workload")
+    ap.add_argument("--mode", default=None, choices=["hessian", "dcsfd", "csfd"],
+                    help="how the DCSFD workload is carried: hessian (default) = Hessian-structured batch, n first-order + one "
+                         "second-order plane per parameter pair (65 planes for the 55 pairs of 10 parameters); dcsfd = the same 55 "
+                         "pairs as independent bicomplex directions (165 planes, round 1's layout); csfd = first-order directions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-frames", action="store_true",
                     help="ProcessFrame waits for the end of each frame like the reference's (default: deferred mode, the "
@@ -73,6 +77,18 @@ def all_directions(xs, comps, dirs):
         out[k, 1] = (xs.H_ * Gw).reshape(16)
         out[k, 2] = (xs.H_ * xs.H_ * 0.5 * (Gu @ Gw + Gw @ Gu)).reshape(16)
     return out.reshape(-1, 16).astype(np.float32)
+
+
+def hessian_params(dirs):
+    """The parameters whose Hessian the DCSFD workload asks for: n with n (n + 1) / 2 = dirs (10 for 55 pairs): the 6 pose axes,
+    then deterministic mixed pose-space directions (intrinsic parameters are not seedable in the reference: Intr is plain
+    floats, Internal.h:49-59).  Returns (U [n, 6], pairs)."""
+    n = int(round((np.sqrt(8 * dirs + 1) - 1) / 2))
+    if n * (n + 1) // 2 != dirs:
+        raise SystemExit("--mode hessian needs --dirs = n (n + 1) / 2 (21, 55, ...)")
+    rng = np.random.default_rng(7)
+    U = np.concatenate([np.eye(6), rng.standard_normal((max(n - 6, 0), 6)) / np.sqrt(6)])[:n]
+    return U, [(i, j) for i in range(n) for j in range(i, n)]
 
 
 class ClockSampler(threading.Thread):
@@ -139,7 +155,7 @@ class ClockSampler(threading.Thread):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this same
 # command (profiles/r01g_ncu_summary.md: 512^3, 55 DCSFD directions, 1 GPU); None for any other configuration.
-TRAFFIC_55 = {"icp_deriv": 1.243e9, "integrate": 6.40e8}
+TRAFFIC_BY_MODE = {"dcsfd": {"icp_deriv": 1.243e9, "integrate": 6.40e8, "raycast_hit": 1.40e9}}  # profiles/r01g_ncu_summary.md
 TRAFFIC = {}
 
 
@@ -272,7 +288,7 @@ def ref_cuda_frames(xs, cfg, n_frames=24):
 def distinct_planes(args):
     """Derivative planes a differentiated frame of the workload consists of, counted once: the DCSFD Hessian of n parameters
     has n first-order and n(n+1)/2 second-order components (65 at n = 10, i.e. 55 bicomplex directions)."""
-    if args.comps == 1:
+    if args.comps == 1 or args.mode == "csfd":
         return args.dirs
     n = int(round((np.sqrt(8 * args.dirs + 1) - 1) / 2))
     return n + args.dirs if n * (n + 1) // 2 == args.dirs else 3 * args.dirs
@@ -309,6 +325,12 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------ CUDA path
+BATCH_NOTE = {"hessian": "Hessian-structured batch (comps = 2): n first-order planes + one second-order plane per parameter pair",
+              "dcsfd": "DCSFD list (comps = 3): every pair an independent bicomplex direction (eps1, eps2, eps1eps2)",
+              "csfd": "CSFD list (comps = 1): independent first-order directions"}
+ICP_KERNEL = {"hessian": "icp_deriv_h_kernel", "dcsfd": "icp_deriv_kernel<3>", "csfd": "icp_deriv_kernel<1>"}
+
+
 class DeviceRecord:
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
@@ -321,17 +343,39 @@ def run_ours(args, xs, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = workload_cfg(xs, args.res)
-    seeds = all_directions(xs, args.comps, args.dirs).reshape(args.dirs, args.comps, 16)
-    mine = list(range(rank, args.dirs, world))
-    my_seeds = np.ascontiguousarray(seeds[mine].reshape(-1, 16))
+    mode = args.mode
     k = xs.KinectFusionReconstruction()
-    k.SetYamlParameters(cfg, comps=args.comps, seeds=my_seeds)
-    lib = xs.load()
     max_dirs = (args.dirs + world - 1) // world
-    rec_len = (1 + max_dirs * args.comps) * 16
+    if mode == "hessian":
+        # every rank carries the n first-order components (cheap, and every pair needs two of them) and its share of the pairs
+        U, pairs = hessian_params(args.dirs)
+        n_params = U.shape[0]
+        my_pairs = pairs[rank::world]
+        my_seeds, _ = xs.hessian_seeds(U, my_pairs)
+        k.SetYamlParameters(cfg, comps=2, seeds=my_seeds, pairs=my_pairs, n_params=n_params)
+        ncomp_local, ncomp_max = n_params + len(my_pairs), n_params + max_dirs
+        planes_total = n_params + len(pairs)
+    else:
+        comps = 1 if mode == "csfd" else 3
+        if mode == "dcsfd":  # the pairs of the same parameters as independent bicomplex directions (eps1, eps2, eps1eps2)
+            U, pairs = hessian_params(args.dirs)
+            G = np.tensordot(U, xs.se3_generators(), 1)
+            seeds = np.zeros((args.dirs, 3, 16))
+            for d, (i, j) in enumerate(pairs):
+                seeds[d, 0], seeds[d, 1] = (xs.H_ * G[i]).reshape(16), (xs.H_ * G[j]).reshape(16)
+                seeds[d, 2] = (xs.H_ * xs.H_ * 0.5 * (G[i] @ G[j] + G[j] @ G[i])).reshape(16)
+            seeds = seeds.astype(np.float32)
+        else:
+            seeds = all_directions(xs, 1, args.dirs).reshape(args.dirs, 1, 16)
+        mine = list(range(rank, args.dirs, world))
+        k.SetYamlParameters(cfg, comps=comps, seeds=np.ascontiguousarray(seeds[mine].reshape(-1, 16)))
+        ncomp_local, ncomp_max = len(mine) * comps, max_dirs * comps
+        planes_total = args.dirs * comps
+    lib = xs.load()
+    rec_len = (1 + ncomp_max) * 16
     gather_out = torch.zeros((world * rec_len,), dtype=torch.float32, device="cuda") if world > 1 else None
     send = torch.zeros((rec_len,), dtype=torch.float32, device="cuda") if world > 1 else None
-    rec_view = torch.as_tensor(DeviceRecord(k.pose_record_device_ptr(), (1 + len(mine) * args.comps) * 16), device="cuda")
+    rec_view = torch.as_tensor(DeviceRecord(k.pose_record_device_ptr(), (1 + ncomp_local) * 16), device="cuda")
 
     # A step is one batch of FPS consecutive frames (each one ProcessFrame).  The synthetic trajectory is a closed loop of
     # period 300 frames, so frame f of the stream is frame f % 300 of the generator: at most 300 distinct frames are rendered
@@ -387,6 +431,8 @@ def run_ours(args, xs, rank, world, local_rank):
     stage_ms = {n: 0.0 for n in ("surface", "icp", "integrate", "raycast", "total")}
     abytes = {n: 0.0 for n in ("surface", "icp", "integrate", "raycast")}
     kern_ms, upd = 0.0, 0
+    hit_ms, hits, normals = 0.0, 0, 0
+    rstats = (ctypes.c_ulonglong * 2)()
     icp_ms, icp_n = 0.0, 0
     t_ms = (ctypes.c_float * 16)()
     t_px = (ctypes.c_int * 16)()
@@ -398,7 +444,11 @@ def run_ours(args, xs, rank, world, local_rank):
     ev0.record(lib_stream)
     t0 = time.perf_counter()
     def collect():  # stage times / statistics of the last collected frame
-        nonlocal kern_ms, upd
+        nonlocal kern_ms, upd, hit_ms, hits, normals
+        hit_ms += lib.xs_volume_last_raycast_hit_ms(vol)
+        lib.xs_volume_raycast_stats(vol, rstats)
+        hits += rstats[0]
+        normals += rstats[1]
         tm, _ = k.times()
         for n in stage_ms:
             stage_ms[n] += tm[n]
@@ -449,9 +499,8 @@ def run_ours(args, xs, rank, world, local_rank):
         if world > 1:
             dist.destroy_process_group()
         return
-    ncomp_local = len(mine) * args.comps
-    if world == 1 and args.res == 512 and args.dirs == 55 and args.comps == 3:
-        TRAFFIC.update(TRAFFIC_55)
+    if world == 1 and args.res == 512 and args.dirs == 55:
+        TRAFFIC.update(TRAFFIC_BY_MODE.get(mode, {}))
     peak, peak_src = measured_hbm_peak()
     int_bytes = abytes["integrate"] / NF
     int_ms = kern_ms / NF
@@ -463,6 +512,14 @@ def run_ours(args, xs, rank, world, local_rank):
     icp_bytes = 640 * 480 * (48 + 24 * D) + 27 * 8 * (1 + D)
     icp_kernel_ms = icp_ms / icp_n if icp_n else 0.0
     icp_achieved = icp_bytes / (icp_kernel_ms * 1e-3) / 1e9 if icp_kernel_ms > 0 else 0.0
+    # raycast hit kernel: its unavoidable traffic is the output maps (24 B per pixel and component incl. the real one) plus
+    # the hit-time image; the trilinear gathers (SURVEY 8d counts 64 x 4 B per hit pixel and component, before any cache
+    # reuse between neighbouring pixels) are data dependent and reported separately
+    hit_kernel_ms = hit_ms / NF
+    hit_bytes = 640 * 480 * (24 * (1 + D) + 4)
+    hit_achieved = hit_bytes / (hit_kernel_ms * 1e-3) / 1e9 if hit_kernel_ms > 0 else 0.0
+    kernels = {"icp_deriv (pyramid level 0, 5 launches per frame)": 5 * icp_kernel_ms, "raycast_hit": hit_kernel_ms, "integrate": int_ms}
+    dominant = max(kernels, key=kernels.get)
     # per step: depth frame + pose derivative components for ICP (initial pose), integration (v2c) and raycast
     # (c2v, v2w) in; final ICP pose with all derivative components, status and integration statistics out
     h2d = 640 * 480 * 2 + (1 + ncomp_local) * 48 + ncomp_local * 48 * 3 + (1 + ncomp_local) * 64
@@ -473,20 +530,30 @@ def run_ours(args, xs, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": "icl_synth_640x480_tsdf%d_dcsfd%d" % (args.res, args.dirs), "step": "one batch of %d consecutive depth frames, each one ProcessFrame" % FPS,
                    "depth": "640x480 uint16 mm",
-                   "tsdf": "%d^3 @ %.4f m" % (args.res, 7.68 / args.res), "directions": args.dirs, "components_per_direction": args.comps,
-                   "derivative_planes": args.dirs * args.comps, "directions_per_rank": max_dirs, "sharding": "directions over ranks, real state replicated",
+                   "tsdf": "%d^3 @ %.4f m" % (args.res, 7.68 / args.res), "directions": args.dirs, "batch": BATCH_NOTE[mode],
+                   "derivative_planes": planes_total, "derivative_planes_rank0": ncomp_local, "directions_per_rank": max_dirs,
+                   "sharding": "second-order pairs over ranks, first-order components and real state replicated" if mode == "hessian"
+                               else "directions over ranks, real state replicated",
                    "frame_sync": "deferred (end-of-frame wait at the start of the next ProcessFrame; ICP result read on the host every frame)" if deferred else "every frame",
                    "l2": "per-step working set (volume %.1f GB/rank) >> 126 MB L2, no flush needed" % (lib.xs_volume_bytes(vol) / 1e9)},
         "e2e": {"value": NF / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d * FPS, "d2h_bytes_per_step": d2h * FPS},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "icp_deriv_kernel<%d> (pyramid level 0; %.0f%% of the step)" % (args.comps, 100 * 5 * icp_kernel_ms / (t_dev / NF * 1e3)),
+        "roofline": {"bound": "hbm", "kernel": "%s (pyramid level 0; 5 launches = %.0f%% of the frame)" % (ICP_KERNEL[mode], 100 * 5 * icp_kernel_ms / (t_dev / NF * 1e3)),
                      "achieved": icp_achieved, "peak": peak, "unit": "GB/s", "frac": icp_achieved / peak, "traffic": TRAFFIC.get("icp_deriv"),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": icp_bytes, "kernel_ms": icp_kernel_ms, "launches_timed": icp_n,
+                     "bytes_model": "P0 x (48 + 24 D) + 27 x 8 x (1 + D), D = derivative planes, each counted once (SURVEY 8d)",
                      "fp32_floor_note": "this kernel is co-bound by the FP32 FMA pipe (DESIGN.md 5.2)"},
-        "roofline_integrate": {"bound": "hbm", "kernel": "integrate_kernel<%d>" % args.comps, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline_integrate": {"bound": "hbm", "kernel": "integrate_kernel<%s>" % mode, "achieved": achieved, "peak": peak, "unit": "GB/s",
                                "frac": achieved / peak, "traffic": TRAFFIC.get("integrate"), "algorithmic_bytes_per_launch": int_bytes,
-                               "kernel_ms": int_ms, "updated_voxels_per_launch": upd / NF},
+                               "kernel_ms": int_ms, "updated_voxels_per_launch": upd / NF,
+                               "survey_8d_bytes_per_launch": (upd / NF) * 2 * (8 + 4 * D) + 2 * 640 * 480},
+        "roofline_raycast": {"bound": "hbm", "kernel": "raycast_hit_kernel<%s>" % mode, "achieved": hit_achieved, "peak": peak, "unit": "GB/s",
+                             "frac": hit_achieved / peak, "traffic": TRAFFIC.get("raycast_hit"), "algorithmic_bytes_per_launch": hit_bytes,
+                             "kernel_ms": hit_kernel_ms, "hit_pixels_per_launch": hits / NF, "normal_pixels_per_launch": normals / NF,
+                             "bytes_model": "output maps 24 B x (1 + D) per pixel + hit-time image; gathers excluded (data dependent)",
+                             "survey_8d_gather_bytes_per_launch": (hits / NF) * 64 * 4 * (1 + D)},
+        "kernel_ms_per_frame": kernels, "dominant_kernel": dominant,
         "wall_ms_per_frame": t_wall / NF * 1e3,
         "stages_ms_per_frame": {n: v / NF for n, v in stage_ms.items()},
         "stages_note": ("icp / integrate / raycast: CUDA-event brackets on the pipeline's stream; surface: the next frame's head runs "
@@ -548,6 +615,12 @@ def run_ours(args, xs, rank, world, local_rank):
 
 def main():
     args = parse()
+    if args.mode is None:
+        args.mode = "csfd" if args.comps == 1 else "hessian"
+        if args.mode == "hessian":  # a direction count that is not a full pair set runs as a plain DCSFD list
+            n = int(round((np.sqrt(8 * args.dirs + 1) - 1) / 2))
+            if n * (n + 1) // 2 != args.dirs:
+                args.mode = "dcsfd"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -11,8 +11,13 @@
  *  - plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = default).
  *  - every function returns 0 on success or a negative xs_status; xs_last_error() gives text.
  *    There is NO CPU fallback: without a CUDA device every compute call returns XS_ERR_CUDA.
- *  - "ncomp" = number of derivative components carried besides the real value:
- *        ncomp = dirs * comps,   comps = 1 (CSFD: eps)  or  3 (DCSFD: eps1, eps2, eps1eps2).
+ *  - "ncomp" = number of derivative components carried besides the real value.  Batch kinds ("comps"):
+ *        comps = 1  CSFD list: dirs independent first-order directions (eps), ncomp = dirs;
+ *        comps = 3  DCSFD list: dirs independent bicomplex directions (eps1, eps2, eps1eps2), ncomp = 3 * dirs;
+ *        comps = 2  Hessian batch over dirs = n parameters: n first-order components F_i followed by one second-order
+ *                   component S_k per listed parameter pair (i <= j; default all n (n + 1) / 2), ncomp = n + pairs.  It
+ *                   equals the DCSFD list of those pairs with (eps1, eps2, eps1eps2) = (F_i, F_j, S_ij), but stores and
+ *                   moves every first-order plane once (65 planes instead of 165 for the Hessian of 10 parameters).
  *    Derivative components are stored h-scaled exactly like the reference's imaginary parts
  *    (Internal.h:33, H_ = 1e-7): eps = h*d/dtheta, eps1eps2 = h^2 * d2/dtheta1 dtheta2.
  *  - maps are packed SoA: float[(1+ncomp)][3][rows][cols]  (component 0 = real part; x|y|z planes),
@@ -117,6 +122,8 @@ int xs_map_soa_to_complex(const float *d_soa, int ncomp, int comp, int nplanes, 
 typedef struct xs_volume xs_volume;
 /* TsdfVolume::TsdfVolume, TsdfVolume.cpp:11-29 (trunc = max(voxel*thres_range, 2.1*voxel)); res multiple of 8 */
 xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_range, int comps, int dirs);
+/* Hessian batch (comps = 2) with an explicit pair list: pairs = int[npairs][2], 0 <= i <= j < nparams, sorted by i (NULL: all) */
+xs_volume *xs_volume_create_hessian(const int res[3], float voxel_size, float thres_range, int nparams, int npairs, const int *pairs);
 void xs_volume_destroy(xs_volume *v);
 /* initVolume, TsdfVolume.h:16 / TsdfFusion.cu:34 */
 int xs_volume_reset(xs_volume *v, void *stream);
@@ -124,6 +131,9 @@ float xs_volume_trunc_dist(const xs_volume *v);
 size_t xs_volume_bytes(const xs_volume *v);
 /* device duration (CUDA events on the launching stream) of the last integration kernel, in ms */
 float xs_volume_last_integrate_ms(const xs_volume *v);
+/* the same for the last raycast hit kernel, and the pixels with a valid vertex / valid normal it found (out2) */
+float xs_volume_last_raycast_hit_ms(const xs_volume *v);
+int xs_volume_raycast_stats(const xs_volume *v, unsigned long long *out2);
 /* Seam views (TsdfVolume::value/weight/grad, TsdfVolume.h:46-49): dense x-fastest planes [z][y][x]
  * on the device; comp = derivative component index in [0, ncomp) for d_grad (ignored when NULL). */
 int xs_volume_export_planes(const xs_volume *v, int comp, float *d_value, int *d_weight, float *d_grad, void *stream);
@@ -220,6 +230,10 @@ typedef struct xs_kinfu xs_kinfu;
  * seeds: [dirs*comps][16] derivative components of the initial world2camera (row-major 4x4, h-scaled),
  * the generalisation of the commented seeding line KinectFusionReconstruction.cpp:22; NULL = zeros. */
 xs_kinfu *xs_kinfu_create(const xs_config *cfg, int comps, int dirs, const float *seeds, int solve_mode);
+/* Hessian batch (comps = 2) with an explicit pair list (multi-GPU: every rank carries the nparams first-order components and its
+ * share of the pairs).  pairs = int[npairs][2] sorted by i (NULL: all pairs); seeds: [(nparams + npairs)][16]: h G_i for the
+ * parameters, h^2 (G_i G_j + G_j G_i) / 2 for the pairs when the parameters are se3Exp coordinates. */
+xs_kinfu *xs_kinfu_create_hessian(const xs_config *cfg, int nparams, int npairs, const int *pairs, const float *seeds, int solve_mode);
 void xs_kinfu_destroy(xs_kinfu *k);
 /* ProcessFrame, KinectFusionReconstruction.cpp:147-159.  depth: 640x480 uint16 mm, dense; host pointer
  * unless depth_on_device != 0.  Returns 1 on success, 0 when frame alignment failed (as the reference). */

@@ -148,3 +148,17 @@ def test_pose_chain_matches_reference_complex_semantics(tmp_path):
     assert identical >= 0.97 * total
     assert worst_real <= 2.0 ** -23, worst_real  # one ulp of the largest entry
     assert worst_deriv <= 1e-5, worst_deriv
+
+
+def test_hessian_batch_equals_dcsfd_list_on_the_host(tmp_path):
+    """The host jets of a Hessian batch (comps = 2: first-order components stored once, one second-order component per listed
+    pair) against the DCSFD list of the same pairs on a pose chain of inverses, products, axis rotations and a quotient:
+    (F_i, F_j, S_ij) == (eps1, eps2, eps1eps2) up to FP32 evaluation order."""
+    exe = str(tmp_path / "host_jet_hessian")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "harness", "host_jet_hessian.cpp")],
+                   check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == 9
+    for line in out:
+        i, j, e1, e2, e12 = line.split()
+        assert float(e1) <= 1e-6 and float(e2) <= 1e-6 and float(e12) <= 1e-5, line

@@ -63,6 +63,9 @@ SYMBOLS = {
     "xs_map_complex_to_soa": (_i, [_vp, _sz, _i, _i, _i, _vp, _i, _i, _vp]),
     "xs_map_soa_to_complex": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "xs_volume_create": (_vp, [_pi, _f, _f, _i, _i]),
+    "xs_volume_create_hessian": (_vp, [_pi, _f, _f, _i, _i, _pi]),
+    "xs_volume_last_raycast_hit_ms": (_f, [_vp]),
+    "xs_volume_raycast_stats": (_i, [_vp, _pull]),
     "xs_volume_destroy": (None, [_vp]),
     "xs_volume_reset": (_i, [_vp, _vp]),
     "xs_volume_trunc_dist": (_f, [_vp]),
@@ -82,6 +85,7 @@ SYMBOLS = {
     "xs_estimate_combined": (_i, [_PP, _vp, _vp, _PP, Intr, _vp, _vp, _i, _i, _i, _i, _f, _f, _pd, _pd, _vp]),
     "xs_compute_optimize_matrix": (_l, [_PP, _vp, _vp, _PP, Intr, _vp, _vp, _i, _i, _f, _f, _pd, _pd, _vp]),
     "xs_kinfu_create": (_vp, [C.POINTER(Config), _i, _i, _pf, _i]),
+    "xs_kinfu_create_hessian": (_vp, [C.POINTER(Config), _i, _i, _pi, _pf, _i]),
     "xs_kinfu_destroy": (None, [_vp]),
     "xs_kinfu_process_frame": (_i, [_vp, _vp, _i]),
     "xs_kinfu_set_deferred": (_i, [_vp, _i]),

@@ -1,7 +1,8 @@
 // host_jet.h — host-side batched complex-step numbers and the small pose algebra of the orchestrator.
 //
-// HJet is the host counterpart of xs::Jet: one float real part plus ncomp = dirs*comps h-scaled
-// derivative components (comps = 1: eps; comps = 3: eps1, eps2, eps1eps2 per direction).  It replaces the
+// HJet is the host counterpart of xs::Jet: one float real part plus ncomp h-scaled derivative components
+// (comps = 1: eps per direction; comps = 3: eps1, eps2, eps1eps2 per direction; comps = 2: Hessian batch - dirs first-order
+// components F_i followed by one second-order component S_k per listed parameter pair, xs_common.cuh).  It replaces the
 // Eigen::Matrix4cf / Matrix3frm / Vector3cf algebra of the reference orchestrator
 // (XKinectFusion/src/KinectFusionReconstruction.cpp:161-332, std::complex<float> scalars) for a whole
 // batch of perturbation directions at once.  Real parts are evaluated with plain float operations, which
@@ -15,9 +16,14 @@ namespace xs {
 
 constexpr int HJ_MAX = 256;  // max derivative components per number
 
+struct HPair {
+    int i, j;
+};
 struct HJetCtx {
     int comps = 1, dirs = 0;
-    int ncomp() const { return comps * dirs; }
+    int npairs = 0;                 // comps == 2 only
+    const HPair *pairs = nullptr;   // comps == 2 only: [npairs], component dirs + k is S(pairs[k].i, pairs[k].j)
+    int ncomp() const { return comps == 2 ? dirs + npairs : comps * dirs; }
 };
 inline HJetCtx &hj_ctx() {
     static thread_local HJetCtx c;
@@ -77,6 +83,14 @@ inline HJet operator*(const HJet &a, const HJet &b) {
             t = t + a.d[3 * k + 1] * b.d[3 * k];
             r.d[3 * k + 2] = t;
         }
+    } else if (c.comps == 2) {
+        for (int k = 0; k < c.npairs; ++k) {
+            const int i = c.pairs[k].i, j = c.pairs[k].j;
+            float t = r.d[c.dirs + k];
+            t = t + a.d[i] * b.d[j];
+            t = t + a.d[j] * b.d[i];
+            r.d[c.dirs + k] = t;
+        }
     }
     return r;
 }
@@ -87,6 +101,12 @@ inline HJet operator/(const HJet &a, const HJet &b) {
     const HJetCtx &c = hj_ctx();
     if (c.comps == 1) {
         for (int k = 0; k < c.dirs; ++k) r.d[k] = (a.d[k] - r.v * b.d[k]) * inv;
+    } else if (c.comps == 2) {
+        for (int i = 0; i < c.dirs; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
+        for (int k = 0; k < c.npairs; ++k) {
+            const int i = c.pairs[k].i, j = c.pairs[k].j, s = c.dirs + k;
+            r.d[s] = (a.d[s] - r.v * b.d[s] - r.d[i] * b.d[j] - r.d[j] * b.d[i]) * inv;
+        }
     } else {
         for (int k = 0; k < c.dirs; ++k) {
             const float a1 = a.d[3 * k], a2 = a.d[3 * k + 1], a12 = a.d[3 * k + 2];
@@ -106,6 +126,9 @@ inline HJet hj_apply(const HJet &a, float f0, float f1, float f2) {
     const HJetCtx &c = hj_ctx();
     if (c.comps == 1) {
         for (int k = 0; k < c.dirs; ++k) r.d[k] = f1 * a.d[k];
+    } else if (c.comps == 2) {
+        for (int i = 0; i < c.dirs; ++i) r.d[i] = f1 * a.d[i];
+        for (int k = 0; k < c.npairs; ++k) r.d[c.dirs + k] = f1 * a.d[c.dirs + k] + f2 * a.d[c.pairs[k].i] * a.d[c.pairs[k].j];
     } else {
         for (int k = 0; k < c.dirs; ++k) {
             r.d[3 * k] = f1 * a.d[3 * k];

@@ -98,6 +98,8 @@ struct IcpParams {
     int chunks, groups, ppt;  // chunks = pixel units of 256 * ppt pixels
     unsigned int *group_ticket;  // [groups] arrival counters of the derivative pass (self-resetting)
     int max_writers;             // upper bound of the CTAs that write a partial for one group
+    BatchView batch;             // Hessian batch (kind 2): a group is one task = parameter i (component i) or pair k (component n + k)
+    unsigned int *done_ticket;   // kind 2: tasks whose sums are complete (self-resetting); the CTA that completes the last one solves
 };
 
 // the Gauss-Newton step that closes an iteration (icp_solve_direction below)
@@ -117,6 +119,8 @@ struct SolveParams {
 constexpr int REAL_CACHE = 48;
 template <int C> __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, const double *real_sums,
                                                                   const double *comp_sums);
+__device__ __noinline__ void icp_solve_hessian_first(const SolveParams &P, int i, const double *real_sums, double *x_out);
+__device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n, int k, int2 pr, const double *real_sums, const double *x_first);
 
 // search_newton (ICP.cu:196-244) on real parts with the reference's rounding sequence: projection of the current
 // vertex into the previous frame, bounds / NaN / distance / angle gates.  Outputs vcurr, vcurr_g and the matched pixel.
@@ -899,10 +903,359 @@ template <int C> __global__ void __launch_bounds__(32) icp_solve_kernel(const So
     if (threadIdx.x == 0 && blockIdx.x == 0) icp_solve_direction<C>(P, 0, s_real, s_real);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// pass 2 for a Hessian batch (kind 2).  A task is one parameter i (first-order component i: gathers F_i of the previous
+// maps) or one listed pair k = (i, j) (second-order component n + k: gathers F_i, F_j and S_k); either way a thread
+// accumulates ONE set of 27 sums - those of the task's own component - so 27 instead of 81 FP32 accumulators per thread
+// (three CTAs per SM instead of two) and every first-order plane contributes its sums once instead of once per pair.
+//   first order :  d(r_a r_b) = r_a F(r_b) + F(r_a) r_b
+//   pair        :  d(r_a r_b) = r_a S(r_b) + S(r_a) r_b + F_i(r_a) F_j(r_b) + F_j(r_a) F_i(r_b)        (xs_batch.h)
+// Work decomposition, staging, flush and per-task partial reduction are those of icp_deriv_kernel; the CTA that completes the
+// LAST task's sums (done_ticket) runs the Gauss-Newton step of every component: first-order solves first (their solutions
+// are needed by the pairs), then the pairs.
+constexpr size_t deriv_h_smem(int stages) { return (size_t) stages * DERIV_IN * 256 * sizeof(float) + 256 * sizeof(double); }
+
+template <int... E>
+XS_DEV void accumulate_first(float (&acc)[27], const float (&r)[7], const float (&d0)[7], std::integer_sequence<int, E...>) {
+    ((acc[E] = fmaf(r[tri_i(E)], d0[tri_j(E)], fmaf(d0[tri_i(E)], r[tri_j(E)], acc[E]))), ...);
+}
+template <int... E>
+XS_DEV void accumulate_pair(float (&acc)[27], const float (&r)[7], const float (&d0)[7], const float (&d1)[7], const float (&d2)[7],
+                            std::integer_sequence<int, E...>) {
+    ((acc[E] = fmaf(r[tri_i(E)], d2[tri_j(E)],
+                    fmaf(d2[tri_i(E)], r[tri_j(E)], fmaf(d0[tri_i(E)], d1[tri_j(E)], fmaf(d1[tri_i(E)], d0[tri_j(E)], acc[E]))))),
+     ...);
+}
+
+template <int ST> __global__ void __launch_bounds__(256, 3) icp_deriv_h_kernel(const IcpParams P, const SolveParams S) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ float s_pose[3][12];
+    __shared__ bool s_last, s_final;
+    float *s_in = reinterpret_cast<float *>(s_raw);  // [stage][DERIV_IN][256]
+    double *s_tot = reinterpret_cast<double *>(s_raw + (size_t) ST * DERIV_IN * 256 * sizeof(float));  // [256]
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const size_t plane = (size_t) P.rows * P.cols;
+    const int npix = P.rows * P.cols;
+    const int n = P.batch.n, ntasks = P.batch.n + P.batch.m;
+    const unsigned long long stream_policy = l2_policy_evict_first();
+    const long long U = (long long) P.groups * P.chunks, B = gridDim.x;
+    const long long u_begin = blockIdx.x * U / B, u_end = (blockIdx.x + 1) * U / B;
+    bool final_cta = false;
+    for (long long u = u_begin; u < u_end;) {
+        const int task = (int) (u / P.chunks), c_begin = (int) (u % P.chunks);
+        const int c_end = (int) min((long long) P.chunks, c_begin + (u_end - u));
+        u += c_end - c_begin;
+        const bool pair = task >= n;
+        int comp3[3] = {task, task, task};  // components whose planes / pose derivatives the task reads: F_i | F_i, F_j, S_k
+        if (pair) {
+            const int2 pr = __ldg(P.batch.pairs + (task - n));
+            comp3[0] = pr.x, comp3[1] = pr.y;
+        }
+        const int nslots = pair ? 3 : 1;
+        __syncthreads();  // s_pose / s_tot of the previous segment are no longer read
+        if (tid < 36) {
+            const int a = tid / 12, e = tid % 12;
+            s_pose[a][e] = P.pose_curr[(size_t) (1 + comp3[a]) * 12 + e];
+        }
+        s_tot[tid] = 0.0;
+        __syncthreads();
+        float acc[27];
+#pragma unroll
+        for (int e = 0; e < 27; ++e) acc[e] = 0.f;
+        auto flush = [&]() {
+            float v[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = e < 27 ? acc[e] : 0.f;
+            s_tot[tid] += (double) warp_transpose_reduce_f(v);
+#pragma unroll
+            for (int e = 0; e < 27; ++e) acc[e] = 0.f;
+        };
+        const int base = c_begin * 256 * P.ppt;
+        const int nitems = (c_end - c_begin) * P.ppt;
+        auto issue = [&](int stage, int p, int q) {
+            if (q >= 0) {
+                float *dst = s_in + (size_t) stage * DERIV_IN * 256 + tid;
+                float4 *dst4 = reinterpret_cast<float4 *>(s_in + (size_t) stage * DERIV_IN * 256) + tid;  // [4][256] float4
+                const float4 *f = P.rec_f + (size_t) p * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cp_async16(dst4 + i * 256, f + i);
+                const unsigned uplane = (unsigned) plane;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    if (a < nslots) {  // block-uniform
+                        const unsigned o = (unsigned) q + (unsigned) (1 + comp3[a]) * 3u * uplane;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            // first-order planes are re-read by every pair they occur in (L2-resident); second-order planes are streamed once
+                            if (a == 2) {
+                                cp_async4_stream(dst + (REC_F + a * 6 + c) * 256, P.nmap_prev + (o + c * uplane), stream_policy);
+                                cp_async4_stream(dst + (REC_F + a * 6 + 3 + c) * 256, P.vmap_prev + (o + c * uplane), stream_policy);
+                            } else {
+                                cp_async4(dst + (REC_F + a * 6 + c) * 256, P.nmap_prev + (o + c * uplane));
+                                cp_async4(dst + (REC_F + a * 6 + 3 + c) * 256, P.vmap_prev + (o + c * uplane));
+                            }
+                        }
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+        auto idx_at = [&](int j) {
+            const int p = base + j * 256 + tid;
+            return (j < nitems && p < npix) ? P.rec_idx[p] : -1;
+        };
+        int qs[ST];
+#pragma unroll
+        for (int i = 0; i < ST; ++i) qs[i] = idx_at(i);
+#pragma unroll
+        for (int i = 0; i < ST - 1; ++i) issue(i, base + i * 256 + tid, qs[i]);
+        int st = 0;
+        for (int j = 0; j < nitems; ++j) {
+            const int p = base + j * 256 + tid;
+            int st_in = st + ST - 1;
+            if (st_in >= ST) st_in -= ST;
+            issue(st_in, p + (ST - 1) * 256, qs[ST - 1]);
+            const int q = qs[0];
+#pragma unroll
+            for (int i = 0; i < ST - 1; ++i) qs[i] = qs[i + 1];
+            qs[ST - 1] = idx_at(j + ST);
+            const int cur = st;
+            st = (st + 1 == ST) ? 0 : st + 1;
+            cp_async_wait<ST - 1>();
+            if (q >= 0) {
+                const float *in = s_in + (size_t) cur * DERIV_IN * 256 + tid;
+                const float4 *in4 = reinterpret_cast<const float4 *>(s_in + (size_t) cur * DERIV_IN * 256) + tid;
+                const float4 f0 = in4[0], f1 = in4[256], f2 = in4[512], f3 = in4[768];
+                const float vc[3] = {f0.x, f0.y, f0.z};
+                const float sv[3] = {f0.w, f1.x, f1.y};
+                const float nv[3] = {f1.z, f1.w, f2.x};
+                const float ev[3] = {f2.y, f2.z, f2.w};
+                const float r[7] = {f3.x, f3.y, f3.z, nv[0], nv[1], nv[2], f3.w};
+                float ds[3][3], dn[3][3], de[3][3], d[3][7];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    if (a < nslots) {
+                        const float *mm = s_pose[a];
+                        ds[a][0] = fmaf(mm[0], vc[0], fmaf(mm[1], vc[1], fmaf(mm[2], vc[2], mm[9])));
+                        ds[a][1] = fmaf(mm[3], vc[0], fmaf(mm[4], vc[1], fmaf(mm[5], vc[2], mm[10])));
+                        ds[a][2] = fmaf(mm[6], vc[0], fmaf(mm[7], vc[1], fmaf(mm[8], vc[2], mm[11])));
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            dn[a][c] = in[(REC_F + a * 6 + c) * 256];
+                            de[a][c] = in[(REC_F + a * 6 + 3 + c) * 256] - ds[a][c];
+                        }
+                        cross3(ds[a], nv, d[a]);  // d(s x n) = ds x n + s x dn
+                        cross3_add(sv, dn[a], d[a]);
+                        d[a][3] = dn[a][0];
+                        d[a][4] = dn[a][1];
+                        d[a][5] = dn[a][2];
+                        d[a][6] = dot3(dn[a], ev) + dot3(nv, de[a]);  // d(n . (d - s))
+                    }
+                }
+                if (pair) {
+                    cross3_add(ds[0], dn[1], d[2]);  // second-order cross terms of the row
+                    cross3_add(ds[1], dn[0], d[2]);
+                    d[2][6] += dot3(dn[0], de[1]) + dot3(dn[1], de[0]);
+                    accumulate_pair(acc, r, d[0], d[1], d[2], std::make_integer_sequence<int, 27>());
+                } else {
+                    accumulate_first(acc, r, d[0], std::make_integer_sequence<int, 27>());
+                }
+            }
+            if ((j & 31) == 31) flush();
+        }
+        if (nitems & 31) flush();
+        cp_async_wait<0>();
+        __syncthreads();
+        // ---------------- the 8 warps in order -> one 27-value partial of this CTA for this task
+        const int first_b = deriv_owner((long long) task * P.chunks, U, B);
+        const int writers = deriv_owner((long long) (task + 1) * P.chunks - 1, U, B) - first_b + 1;
+        double *part = P.dpartials + ((size_t) task * P.max_writers + (blockIdx.x - first_b)) * 27;
+        if (tid < 27) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sum += s_tot[w * 32 + tid];
+            part[tid] = sum;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(P.group_ticket + task, 1u) == (unsigned) writers - 1u;
+        __syncthreads();
+        if (!s_last) continue;
+        __threadfence();
+        // the last writer of the task adds the partials in CTA order (lane = product)
+        if (warp == 0) {
+            double sum = 0.0;
+            if (lane < 27) {
+                const double *src = P.dpartials + (size_t) task * P.max_writers * 27 + lane;
+                for (int w = 0; w < writers; ++w) sum += __ldcg(src + (size_t) w * 27);
+                P.sums[(size_t) (1 + task) * 27 + lane] = sum;
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                P.group_ticket[task] = 0u;
+                s_final = atomicAdd(P.done_ticket, 1u) == (unsigned) ntasks - 1u;
+            }
+        }
+        __syncthreads();
+        final_cta = final_cta || s_final;
+        __syncthreads();
+    }
+    if (!final_cta) return;  // block-uniform
+    // ---------------- tail: every task's sums are complete -> the Gauss-Newton step of every component
+    __threadfence();
+    if (tid == 0) *P.done_ticket = 0u;
+    if (!S.pose_out) return;
+    double *s_real = reinterpret_cast<double *>(s_raw);  // [27]; the staging area is idle here
+    double *s_x1 = s_real + 32;                          // [n][6] first-order solutions
+    if (tid < 27) s_real[tid] = __ldcg(P.sums + tid);    // real sums of icp_assoc_kernel (previous launch)
+    __syncthreads();
+    if (S.log)
+        for (int i = tid; i < 27 * (1 + ntasks); i += 256) S.log[i] = __ldcg(P.sums + i);
+    for (int i = tid; i < n; i += 256) icp_solve_hessian_first(S, i, s_real, s_x1 + 6 * i);
+    __syncthreads();
+    for (int k = tid; k < P.batch.m; k += 256) icp_solve_hessian_pair(S, n, k, __ldg(P.batch.pairs + k), s_real, s_x1);
+}
+
+// ---- Gauss-Newton step of a Hessian batch (kind 2), one thread per component.
+// Real prelude shared by both task kinds: status flags, real A / b, Cholesky factor and real solution (loaded from the real
+// step's cache under split chains, computed otherwise).  Returns false when the iteration is skipped (degenerate system).
+XS_DEV bool gn_real_prelude(const SolveParams &P, const double *real_sums, bool owns_real, double (&A)[6][6], double (&b)[6], Chol6 &F,
+                            double (&xr)[6]) {
+    const int st0 = __ldcg(P.status), st1 = __ldcg(P.status + 1);
+    if (st0 != 0 || st1 != 0) {
+        if (owns_real) P.status[0] = st0 != 0 ? st0 : st1;
+        return false;
+    }
+    unpack_sums(real_sums, A, b);
+    if (P.deriv_only && P.real_cache) {
+        const double *rc = P.real_cache;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) F.L[i][j] = __ldcg(rc + i * 6 + j);
+            F.inv[i] = __ldcg(rc + 36 + i);
+            xr[i] = __ldcg(rc + 42 + i);
+        }
+        return true;
+    }
+    const double det = det6_dev(A);
+    if (fabs(det) < 1e-15 || isnan(det)) {
+        if (owns_real) P.status[1] = isnan(det) ? 2 : 1;
+        return false;
+    }
+    chol6_factor(A, F);
+    chol6_solve(F, b, xr);
+    return true;
+}
+
+// pose update of KinectFusionReconstruction.cpp:212-224 for the C components comp[0..C-1] of the pose tables; components
+// c >= first_store are written, the real part only by its owner
+template <int C>
+XS_DEV void gn_pose_update(const SolveParams &P, const int (&comp)[C], const Jet<C, 1> (&x)[6], int first_store, bool owns_real) {
+    typedef Jet<C, 1> J;
+    JMat3<C> Rcurr;
+    J tcurr[3];
+    const float *pr = P.pose_in;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            Rcurr.m[i][j].v = pr[i * 3 + j];
+            for (int a = 0; a < C; ++a) Rcurr.m[i][j].d[a] = pr[(size_t) (1 + comp[a]) * 12 + i * 3 + j];
+        }
+        tcurr[i].v = pr[9 + i];
+        for (int a = 0; a < C; ++a) tcurr[i].d[a] = pr[(size_t) (1 + comp[a]) * 12 + 9 + i];
+    }
+    const JMat3<C> Rinc = jmatmul(jmatmul(jaxis_rotation<C>(x[2], 2), jaxis_rotation<C>(x[1], 1)), jaxis_rotation<C>(x[0], 0));
+    J tn[3];
+    for (int i = 0; i < 3; ++i) {
+        J sacc = Rinc.m[i][0] * tcurr[0];
+        for (int k = 1; k < 3; ++k) sacc = sacc + Rinc.m[i][k] * tcurr[k];
+        tn[i] = sacc + x[3 + i];
+    }
+    const JMat3<C> Rn = jmatmul(Rinc, Rcurr);
+    float *pw = P.pose_out;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            if (owns_real) pw[i * 3 + j] = Rn.m[i][j].v;
+            for (int a = first_store; a < C; ++a) pw[(size_t) (1 + comp[a]) * 12 + i * 3 + j] = Rn.m[i][j].d[a];
+        }
+        if (owns_real) pw[9 + i] = tn[i].v;
+        for (int a = first_store; a < C; ++a) pw[(size_t) (1 + comp[a]) * 12 + 9 + i] = tn[i].d[a];
+    }
+}
+
+// first-order component i: x_i = A^-1 (b_i - A_i x) (analytic) or the imaginary part of the Hermitian-LLT solve (LLT mode,
+// what a one-direction complex run of the reference yields).  x_out[6] is kept for the pairs.
+__device__ __noinline__ void icp_solve_hessian_first(const SolveParams &P, int i, const double *real_sums, double *x_out) {
+    const bool owns_real = i == 0 && !P.deriv_only;
+    double A[6][6], b[6], xr[6];
+    Chol6 F;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) x_out[e] = 0.0;
+    if (!gn_real_prelude(P, real_sums, owns_real, A, b, F, xr)) return;
+    double Ai[6][6], bi[6], sums[27], xi[6];
+    for (int e = 0; e < 27; ++e) sums[e] = __ldcg(P.sums + (size_t) (1 + i) * 27 + e);
+    unpack_sums(sums, Ai, bi);
+    if (P.solve_mode == XS_SOLVE_EIGEN_LLT) {
+        cplx xq[6];
+        llt_hermitian_solve6_dev(A, Ai, b, bi, xq);
+        for (int e = 0; e < 6; ++e) xi[e] = xq[e].im;
+    } else {
+        double t[6], rhs[6];
+        matvec6_dev(Ai, xr, t);
+        for (int e = 0; e < 6; ++e) rhs[e] = bi[e] - t[e];
+        chol6_solve(F, rhs, xi);
+    }
+    Jet<1, 1> x[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+        x_out[e] = xi[e];
+        x[e].v = (float) xr[e];
+        x[e].d[0] = (float) xi[e];
+    }
+    const int comp[1] = {i};
+    gn_pose_update<1>(P, comp, x, 0, owns_real);
+}
+
+// pair k = (i, j): x_ij = A^-1 (b_ij - A_ij x - A_i x_j - A_j x_i); the pose update runs in the bicomplex algebra on
+// (F_i, F_j, S_ij) and stores S_ij only
+__device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n, int k, int2 pr, const double *real_sums, const double *x_first) {
+    double A[6][6], b[6], xr[6];
+    Chol6 F;
+    if (!gn_real_prelude(P, real_sums, false, A, b, F, xr)) return;
+    double M[6][6], v[6], sums[27], rhs[6], t[6], xs[6];
+    for (int e = 0; e < 27; ++e) sums[e] = __ldcg(P.sums + (size_t) (1 + n + k) * 27 + e);
+    unpack_sums(sums, M, v);  // A_ij, b_ij
+    matvec6_dev(M, xr, t);
+    for (int e = 0; e < 6; ++e) rhs[e] = v[e] - t[e];
+    double xi[6], xj[6];
+    for (int e = 0; e < 6; ++e) xi[e] = x_first[6 * pr.x + e], xj[e] = x_first[6 * pr.y + e];
+    for (int e = 0; e < 27; ++e) sums[e] = __ldcg(P.sums + (size_t) (1 + pr.x) * 27 + e);
+    unpack_sums(sums, M, v);  // A_i
+    matvec6_dev(M, xj, t);
+    for (int e = 0; e < 6; ++e) rhs[e] -= t[e];
+    for (int e = 0; e < 27; ++e) sums[e] = __ldcg(P.sums + (size_t) (1 + pr.y) * 27 + e);
+    unpack_sums(sums, M, v);  // A_j
+    matvec6_dev(M, xi, t);
+    for (int e = 0; e < 6; ++e) rhs[e] -= t[e];
+    chol6_solve(F, rhs, xs);
+    Jet<3, 1> x[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+        x[e].v = (float) xr[e];
+        x[e].d[0] = (float) xi[e];
+        x[e].d[1] = (float) xj[e];
+        x[e].d[2] = (float) xs[e];
+    }
+    const int comp[3] = {pr.x, pr.y, n + k};
+    gn_pose_update<3>(P, comp, x, 2, false);
+}
+
 // persistent scratch of the ICP operator (gbuf / mbuf of the reference, ICP.cu:400-403)
 struct IcpScratch {
     double *d_partials = nullptr, *d_sums = nullptr, *h_sums = nullptr, *d_dpartials = nullptr;
-    unsigned int *d_ticket = nullptr, *d_group_ticket = nullptr;
+    unsigned int *d_ticket = nullptr, *d_group_ticket = nullptr, *d_done_ticket = nullptr;
     int cap_groups = 0;
     float *d_pose = nullptr, *h_pose = nullptr;  // seam-level entry point only: [(1+ncomp)][12]
     int *d_rec_idx = nullptr;
@@ -940,6 +1293,7 @@ void icp_scratch_destroy(IcpScratch *sc) {
     cudaFree(sc->d_dpartials);
     cudaFree(sc->d_ticket);
     cudaFree(sc->d_group_ticket);
+    cudaFree(sc->d_done_ticket);
     cudaFree(sc->d_pose);
     cudaFreeHost(sc->h_pose);
     cudaFree(sc->d_rec_idx);
@@ -985,6 +1339,8 @@ static int icp_reserve(IcpScratch *scp, int ncomp, int npix, size_t dpart, int g
     if (!g_icp.d_ticket) {
         XS_CUDA(cudaMalloc(&g_icp.d_ticket, sizeof(unsigned int)));
         XS_CUDA(cudaMemset(g_icp.d_ticket, 0, sizeof(unsigned int)));
+        XS_CUDA(cudaMalloc(&g_icp.d_done_ticket, sizeof(unsigned int)));
+        XS_CUDA(cudaMemset(g_icp.d_done_ticket, 0, sizeof(unsigned int)));
     }
     if (ncomp > g_icp.cap_comp) {
         cudaFree(g_icp.d_pose);
@@ -1033,16 +1389,29 @@ template <int C, int ST> static int launch_deriv(const IcpParams &P, const Solve
     return XS_OK;
 }
 
+template <int ST> static int launch_deriv_h(const IcpParams &P, const SolveParams &S, int grid, cudaStream_t s) {
+    static bool smem_set = false;
+    if (!smem_set) {
+        XS_CUDA(cudaFuncSetAttribute(icp_deriv_h_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) deriv_h_smem(ST)));
+        smem_set = true;
+    }
+    icp_deriv_h_kernel<ST><<<grid, 256, deriv_h_smem(ST), s>>>(P, S);
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
+
 // Queues one Gauss-Newton iteration: association + real sums, then (ncomp > 0) the derivative pass whose tail sums the
 // partials and - when d_pose_out is given - runs the Gauss-Newton step per direction; with ncomp == 0 the step is a
 // one-thread kernel.  d_pose_out == nullptr: accumulate only (the sums land in g_icp.d_sums).
 int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
-                        xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
-                        int dirs, float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
+                        xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, const BatchView &batch,
+                        float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
                         double *d_log, cudaStream_t s, cudaStream_t s_real, int slot) {
     IcpScratch &g_icp = *scp;
     g_last_timed = scp;
-    const int ncomp = comps * dirs;
+    const int comps = batch.kind, dirs = batch.n;
+    const int ncomp = batch.ncomp;
+    const bool hessian = batch.kind == 2;
     // Split chains: the real part of an iteration (association, real sums, real Gauss-Newton step) does not depend on any
     // derivative component, so with a second stream the real chain of a frame - association + one-thread solve per
     // iteration - runs ahead on s_real, each iteration leaving its record, sums and real pose in a slot of its own, and
@@ -1057,10 +1426,12 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
     IcpParams P;
     // derivative pass decomposition (icp_deriv_kernel): pixel units of 256 * ppt pixels, (group, unit) items cut into equal
     // contiguous ranges for min(296, items) persistent CTAs; ppt shrinks until there are at least as many items as CTA slots
-    P.groups = (ncomp + 2) / 3;
+    P.groups = hessian ? batch.n + batch.m : (ncomp + 2) / 3;  // Hessian batch: one group per task (parameter or pair)
+    P.batch = batch;
+    P.done_ticket = nullptr;
     static const int ppt_env = env_int("XS_ICP_PPT", 0), stages_env = env_int("XS_ICP_STAGES", 0);
     P.ppt = 4;
-    const int cta_slots = g_icp.max_blocks;  // two persistent CTAs per SM
+    const int cta_slots = hessian ? g_icp.max_blocks / 2 * 3 : g_icp.max_blocks;  // persistent CTAs: two per SM (three for the 27-accumulator kernel)
     while (P.ppt > 1 && (long long) div_up(npix, 256 * P.ppt) * P.groups < cta_slots) P.ppt >>= 1;
     if (ppt_env > 0) P.ppt = ppt_env < 32 ? ppt_env : 32;
     P.chunks = div_up(npix, 256 * P.ppt);
@@ -1069,6 +1440,7 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
     P.max_writers = ncomp > 0 ? (int) (P.chunks / (items / deriv_grid)) + 2 : 0;
     int rc = icp_reserve(scp, ncomp, npix, (size_t) P.groups * P.max_writers * 81, P.groups, split ? IcpScratch::MAX_SLOTS : 1);
     if (rc != XS_OK) return rc;
+    P.done_ticket = g_icp.d_done_ticket;
     const int nvals = 27 * (1 + ncomp);
     // only the current pose's derivative components enter the rows (s = Rcurr*v + tcurr); the previous pose is used
     // for the real projection only (ICP.cu:206-217 takes real parts)
@@ -1138,7 +1510,9 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
         // pipeline depth: 2 stages (one pixel ahead) measured faster than 3 on B200 (0.475 vs 0.542 ms per level-0 launch at
         // 55 directions: the deeper pipeline costs L1 capacity and does not raise issue utilisation); XS_ICP_STAGES=3 selects it
         const int stages = stages_env == 3 ? 3 : 2;
-        if (comps == 1)
+        if (hessian)
+            rc = launch_deriv_h<2>(P, S, deriv_grid, s);
+        else if (comps == 1)
             rc = stages == 2 ? launch_deriv<1, 2>(P, S, deriv_grid, s) : launch_deriv<1, DERIV_MAX_STAGES>(P, S, deriv_grid, s);
         else
             rc = stages == 2 ? launch_deriv<3, 2>(P, S, deriv_grid, s) : launch_deriv<3, DERIV_MAX_STAGES>(P, S, deriv_grid, s);
@@ -1261,9 +1635,15 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
                                     float dist_thres, float angle_thres, double *A_host, double *b_host,
                                     void *stream) {
     if (!curr || !prev || !d_vmap_curr || !d_nmap_curr || !d_vmap_g_prev || !d_nmap_g_prev || !A_host || !b_host ||
-        rows <= 0 || cols <= 0 || (comps != 1 && comps != 3) || dirs < 0)
+        rows <= 0 || cols <= 0 || (comps != 1 && comps != 2 && comps != 3) || dirs < 0)
         return XS_ERR_ARG;
-    const int ncomp = comps * dirs;
+    const int ncomp = batch_ncomp(comps, dirs, -1);  // comps == 2: dirs parameters and all their pairs
+    Batch batch;
+    if (batch_init(batch, comps, dirs, -1, nullptr) != XS_OK) return XS_ERR_ARG;
+    struct BatchGuard {
+        Batch &b;
+        ~BatchGuard() { batch_free(b); }
+    } batch_guard{batch};
     if (curr->ncomp != ncomp || prev->ncomp != ncomp) {
         set_error("xs_estimate_combined: pose derivative component count mismatch");
         return XS_ERR_ARG;
@@ -1285,7 +1665,7 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
     }
     XS_CUDA(cudaMemcpyAsync(g_icp.d_pose, h, (size_t) (1 + ncomp) * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
     rc = icp_iteration_async(scp, g_icp.d_pose, d_vmap_curr, d_nmap_curr, prev, intr, d_vmap_g_prev, d_nmap_g_prev, rows, cols,
-                             comps, dirs, dist_thres, angle_thres, nullptr, 0, nullptr, nullptr, s, nullptr, 0);
+                             batch.v, dist_thres, angle_thres, nullptr, 0, nullptr, nullptr, s, nullptr, 0);
     if (rc != XS_OK) return rc;
     const int nvals = 27 * (1 + ncomp);
     XS_CUDA(cudaMemcpyAsync(g_icp.h_sums, g_icp.d_sums, (size_t) nvals * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -14,6 +14,8 @@
 // kernel once per direction).  Bricks that cannot project into the image are culled before any load.
 #include "xs_common.cuh"
 
+#include <cstring>
+
 namespace xs {
 
 __global__ void scale_depth_kernel(const uint16_t *__restrict__ depth, size_t step, int rows, int cols,
@@ -53,6 +55,7 @@ struct IntegrateParams {
     unsigned char *live;        // [nbricks] 0 = every derivative plane of the brick is still exactly zero
     const float *tile_max;      // [tiles_y][tiles_x] largest valid depth (metres) of each 16 x 16 pixel tile, 0 = none
     int tiles_x, tiles_y;
+    BatchView batch;            // meaning of the ncomp derivative planes (kind 2: first-order planes, then one plane per pair)
 };
 
 // Largest depth of every 16 x 16 pixel tile (invalid pixels are 0), for the depth-aware part of the brick cull.
@@ -200,12 +203,18 @@ XS_DEV bool eval_voxel(const IntegrateParams &P, float vcx, float vcy, float vcz
 // One CTA pass = half a brick (256 threads, 4 z-slices): 3 CTAs per SM at <= 85 registers instead of one 512-thread CTA,
 // i.e. 24 resident warps and three independent streams of derivative-plane loads per SM.
 constexpr int INT_THREADS = 256;
-template <int C> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_kernel(const IntegrateParams P) {
+// KIND = batch kind (xs_batch.h): 1 = first-order list, 3 = bicomplex list, 2 = Hessian batch (needs gradient AND Hessian of
+// sdf like kind 3, but updates every first-order plane once and one second-order plane per listed pair).
+template <int KIND> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_kernel(const IntegrateParams P) {
+    constexpr int C = (KIND == 1) ? 1 : 3;
     constexpr int K = (C == 1) ? 3 : 6;
-    extern __shared__ float4 s_dpose4[];  // [ncomp][3] float4 = [ncomp][12] floats
+    extern __shared__ float4 s_dpose4[];  // [ncomp][3] float4 = [ncomp][12] floats, then (kind 2) the pair table int2[m]
     float *s_dpose = reinterpret_cast<float *>(s_dpose4);
     const int ncomp = P.V.ncomp;
     for (int i = threadIdx.x; i < ncomp * 12; i += INT_THREADS) s_dpose[i] = P.dpose[i];
+    int2 *s_pairs = reinterpret_cast<int2 *>(s_dpose + (size_t) ncomp * 12);
+    if (KIND == 2)
+        for (int i = threadIdx.x; i < P.batch.m; i += INT_THREADS) s_pairs[i] = P.batch.pairs[i];
     __syncthreads();
 
     const float vs = P.V.voxel;
@@ -262,7 +271,55 @@ template <int C> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_ker
         const float sc = P.trunc_inv * inv_w1;
         Jet<C, K> sdfj;
         eval_voxel<C, K>(P, vcx, vcy, vcz, sdfj);
-        if (C == 1) {
+        if (KIND == 2) {
+            // Hessian batch: gradient J and Hessian H of sdf w.r.t. v_c once per voxel (as for kind 3), then
+            //   F_i  += J . d_i v_c                                   for the n first-order planes,
+            //   S_ij += J . d_ij v_c + (d_j v_c)^T H (d_i v_c)        for the listed pairs (sorted by i: d_i v_c and H d_i v_c
+            //                                                          are formed once per run of pairs with the same i)
+            const float J0 = sdfj.d[0] * sc, J1 = sdfj.d[9] * sc, J2 = sdfj.d[15] * sc;
+            const float H00 = sdfj.d[2] * sc, H01 = sdfj.d[5] * sc, H02 = sdfj.d[8] * sc, H11 = sdfj.d[11] * sc,
+                        H12 = sdfj.d[14] * sc, H22 = sdfj.d[17] * sc;
+            const int n = P.batch.n, m = P.batch.m;
+#pragma unroll 4
+            for (int q = 0; q < n; ++q) {
+                const float o = dp[(size_t) q * BRICK_VOX];
+                const float4 *mq = s_dpose4 + 3 * q;
+                const float4 a0 = mq[0], a1 = mq[1], a2 = mq[2];
+                const float dx = fmaf(a0.x, vgx, fmaf(a0.y, vgy, fmaf(a0.z, vgz, a2.y)));
+                const float dy = fmaf(a0.w, vgx, fmaf(a1.x, vgy, fmaf(a1.y, vgz, a2.z)));
+                const float dz = fmaf(a1.z, vgx, fmaf(a1.w, vgy, fmaf(a2.x, vgz, a2.w)));
+                dp[(size_t) q * BRICK_VOX] = fmaf(o, a_keep, fmaf(J0, dx, fmaf(J1, dy, J2 * dz)));
+            }
+            int cur_i = -1;
+            float hx = 0.f, hy = 0.f, hz = 0.f;  // H d_i v_c
+            float *ps = dp + (size_t) n * BRICK_VOX;
+#pragma unroll 4
+            for (int k = 0; k < m; ++k) {
+                const float o = ps[(size_t) k * BRICK_VOX];  // the load first: it bounds this loop
+                const int2 pr = s_pairs[k];
+                if (pr.x != cur_i) {  // block-uniform
+                    cur_i = pr.x;
+                    const float4 *mi = s_dpose4 + 3 * cur_i;
+                    const float4 a0 = mi[0], a1 = mi[1], a2 = mi[2];
+                    const float ax = fmaf(a0.x, vgx, fmaf(a0.y, vgy, fmaf(a0.z, vgz, a2.y)));
+                    const float ay = fmaf(a0.w, vgx, fmaf(a1.x, vgy, fmaf(a1.y, vgz, a2.z)));
+                    const float az = fmaf(a1.z, vgx, fmaf(a1.w, vgy, fmaf(a2.x, vgz, a2.w)));
+                    hx = fmaf(H00, ax, fmaf(H01, ay, H02 * az));
+                    hy = fmaf(H01, ax, fmaf(H11, ay, H12 * az));
+                    hz = fmaf(H02, ax, fmaf(H12, ay, H22 * az));
+                }
+                const float4 *mj = s_dpose4 + 3 * pr.y, *ms = s_dpose4 + 3 * (n + k);
+                const float4 b0 = mj[0], b1 = mj[1], b2 = mj[2], c0 = ms[0], c1 = ms[1], c2 = ms[2];
+                const float bx = fmaf(b0.x, vgx, fmaf(b0.y, vgy, fmaf(b0.z, vgz, b2.y)));
+                const float by_ = fmaf(b0.w, vgx, fmaf(b1.x, vgy, fmaf(b1.y, vgz, b2.z)));
+                const float bz = fmaf(b1.z, vgx, fmaf(b1.w, vgy, fmaf(b2.x, vgz, b2.w)));
+                const float cx2 = fmaf(c0.x, vgx, fmaf(c0.y, vgy, fmaf(c0.z, vgz, c2.y)));
+                const float cy2 = fmaf(c0.w, vgx, fmaf(c1.x, vgy, fmaf(c1.y, vgz, c2.z)));
+                const float cz2 = fmaf(c1.z, vgx, fmaf(c1.w, vgy, fmaf(c2.x, vgz, c2.w)));
+                const float T = fmaf(J0, cx2, fmaf(J1, cy2, J2 * cz2)) + fmaf(bx, hx, fmaf(by_, hy, bz * hz));
+                ps[(size_t) k * BRICK_VOX] = fmaf(o, a_keep, T);
+            }
+        } else if (C == 1) {
             const float J0 = sdfj.d[0] * sc, J1 = sdfj.d[1] * sc, J2 = sdfj.d[2] * sc;
 #pragma unroll 4
             for (int q = 0; q < ncomp; ++q) {
@@ -346,11 +403,26 @@ using namespace xs;
 extern "C" {
 
 xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_range, int comps, int dirs) {
-    if (!res || res[0] <= 0 || (res[0] % 8) || (res[1] % 8) || (res[2] % 8) || (comps != 1 && comps != 3) || dirs < 0) {
-        set_error("xs_volume_create: resolution must be a positive multiple of 8 and comps in {1,3}");
+    return xs_volume_create_hessian(res, voxel_size, thres_range, comps == 2 ? dirs : -comps * 1000 - dirs, -1, nullptr);
+}
+
+// comps = 2 (Hessian batch): nparams first-order planes + one second-order plane per listed pair (pairs == NULL: all pairs).
+// Internally also the creation path of the list kinds, encoded as nparams = -(comps * 1000 + dirs) by xs_volume_create.
+xs_volume *xs_volume_create_hessian(const int res[3], float voxel_size, float thres_range, int nparams, int npairs, const int *pairs) {
+    int comps = 2, dirs = nparams;
+    if (nparams < 0) {
+        comps = (-nparams) / 1000;
+        dirs = (-nparams) % 1000;
+    }
+    if (!res || res[0] <= 0 || (res[0] % 8) || (res[1] % 8) || (res[2] % 8) || (comps != 1 && comps != 2 && comps != 3) || dirs < 0) {
+        set_error("xs_volume_create: resolution must be a positive multiple of 8 and comps in {1,2,3}");
         return nullptr;
     }
     xs_volume *v = new xs_volume();
+    if (batch_init(v->batch, comps, dirs, npairs, pairs) != XS_OK) {
+        delete v;
+        return nullptr;
+    }
     VolumeView &V = v->view;
     V.rx = res[0];
     V.ry = res[1];
@@ -358,7 +430,7 @@ xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_rang
     V.bx = res[0] / 8;
     V.by = res[1] / 8;
     V.bz = res[2] / 8;
-    V.ncomp = comps * dirs;
+    V.ncomp = v->batch.v.ncomp;
     V.voxel = voxel_size;
     V.trunc = fmaxf(voxel_size * thres_range, 2.1f * voxel_size);  // TsdfVolume.cpp:25,37
     v->comps = comps;
@@ -375,8 +447,10 @@ xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_rang
     v->tile_capacity = 0;
     if (e == cudaSuccess) e = cudaMalloc(&v->d_dpose, pose_floats * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost(&v->h_dpose, pose_floats * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&v->d_stats, 4 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMallocHost(&v->h_stats, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&v->d_stats, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&v->h_stats, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(v->d_stats, 0, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) std::memset(v->h_stats, 0, 8 * sizeof(unsigned long long));
     const size_t nbricks = nvox / BRICK_VOX;
     v->d_brick_list = nullptr;
     v->d_list_count = nullptr;
@@ -388,6 +462,8 @@ xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_rang
     v->last_kernel_ms = 0.f;
     if (e == cudaSuccess) e = cudaEventCreate(&v->ev_k0);
     if (e == cudaSuccess) e = cudaEventCreate(&v->ev_k1);
+    if (e == cudaSuccess) e = cudaEventCreate(&v->ev_h0);
+    if (e == cudaSuccess) e = cudaEventCreate(&v->ev_h1);
     v->d_depth_m = nullptr;
     v->depth_capacity = 0;
     v->d_hit_time = nullptr;
@@ -421,6 +497,9 @@ void xs_volume_destroy(xs_volume *v) {
     cudaFree(v->d_live);
     if (v->ev_k0) cudaEventDestroy(v->ev_k0);
     if (v->ev_k1) cudaEventDestroy(v->ev_k1);
+    if (v->ev_h0) cudaEventDestroy(v->ev_h0);
+    if (v->ev_h1) cudaEventDestroy(v->ev_h1);
+    batch_free(v->batch);
     delete v;
 }
 
@@ -459,6 +538,61 @@ int xs_volume_import_planes(xs_volume *v, int comp, const float *d_value, const 
 }  // extern "C"
 
 namespace xs {
+int batch_init(Batch &b, int comps, int dirs, int npairs, const int *pairs) {
+    batch_free(b);
+    if ((comps != 1 && comps != 2 && comps != 3) || dirs < 0) {
+        set_error("batch: comps must be 1 (CSFD list), 3 (DCSFD list) or 2 (Hessian batch)");
+        return XS_ERR_ARG;
+    }
+    b.v.kind = comps;
+    b.v.n = dirs;
+    b.v.m = 0;
+    b.v.pairs = nullptr;
+    if (comps == 2) {
+        const int m = pairs ? npairs : dirs * (dirs + 1) / 2;
+        if (m < 0 || (pairs == nullptr && npairs > 0 && npairs != m)) {
+            set_error("batch: bad pair list");
+            return XS_ERR_ARG;
+        }
+        b.v.m = m;
+        if (m > 0) {
+            b.h_pairs = new int2[m];
+            int k = 0;
+            if (pairs) {
+                for (; k < m; ++k) b.h_pairs[k] = make_int2(pairs[2 * k], pairs[2 * k + 1]);
+            } else {
+                for (int i = 0; i < dirs; ++i)
+                    for (int j = i; j < dirs; ++j) b.h_pairs[k++] = make_int2(i, j);
+            }
+            for (k = 0; k < m; ++k) {
+                const int2 p = b.h_pairs[k];
+                if (p.x < 0 || p.y < p.x || p.y >= dirs || (k > 0 && b.h_pairs[k - 1].x > p.x)) {
+                    set_error("batch: pairs must satisfy 0 <= i <= j < nparams and be sorted by i");
+                    batch_free(b);
+                    return XS_ERR_ARG;
+                }
+            }
+            int2 *d = nullptr;
+            if (cudaMalloc(&d, (size_t) m * sizeof(int2)) != cudaSuccess ||
+                cudaMemcpy(d, b.h_pairs, (size_t) m * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("batch: cannot upload the pair table (no CUDA device?)");
+                cudaFree(d);
+                batch_free(b);
+                return XS_ERR_CUDA;
+            }
+            b.v.pairs = d;
+        }
+    }
+    b.v.ncomp = comps == 2 ? dirs + b.v.m : comps * dirs;
+    return XS_OK;
+}
+void batch_free(Batch &b) {
+    cudaFree(const_cast<int2 *>(b.v.pairs));
+    delete[] b.h_pairs;
+    b.h_pairs = nullptr;
+    b.v = BatchView{1, 0, 0, 0, nullptr};
+}
+
 // Copies the derivative components of a pose into staging slot `slot` (0 or 1) of the volume.
 int upload_pose_derivs(const xs_volume *v, const xs_pose *p, int slot, cudaStream_t s) {
     const int ncomp = v->view.ncomp;
@@ -502,7 +636,7 @@ int integrate_prepare(xs_volume *v, const uint16_t *d_depth, size_t depth_step_b
     XS_LAUNCH_CHECK();
     depth_tile_max_kernel<<<dim3(tiles_x, tiles_y), 256, 0, s>>>(v->d_depth_m, rows, cols, v->d_tile_max, tiles_x);
     XS_LAUNCH_CHECK();
-    XS_CUDA(cudaMemsetAsync(v->d_stats, 0, 4 * sizeof(unsigned long long), s));
+    XS_CUDA(cudaMemsetAsync(v->d_stats, 0, 3 * sizeof(unsigned long long), s));  // [3] = extraction counter, [4..5] = raycast
     XS_CUDA(cudaMemsetAsync(v->d_list_count, 0, sizeof(unsigned int), s));
     v->prepared_depth = d_depth;
     return XS_OK;
@@ -550,15 +684,18 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
     cull_bricks_kernel<<<div_up(P.nbricks, 256), 256, 0, s>>>(P, v->d_brick_list);
     XS_LAUNCH_CHECK();
     int grid = 2 * P.nbricks < sm_count() * 24 ? 2 * P.nbricks : sm_count() * 24;
-    size_t smem = (size_t) (v->view.ncomp > 0 ? v->view.ncomp : 1) * 12 * sizeof(float);
+    size_t smem = (size_t) (v->view.ncomp > 0 ? v->view.ncomp : 1) * 12 * sizeof(float) + (size_t) v->batch.v.m * sizeof(int2);
+    P.batch = v->batch.v;
     XS_CUDA(cudaEventRecord(v->ev_k0, s));
     if (v->comps == 1)
         integrate_kernel<1><<<grid, INT_THREADS, smem, s>>>(P);
+    else if (v->comps == 2)
+        integrate_kernel<2><<<grid, INT_THREADS, smem, s>>>(P);
     else
         integrate_kernel<3><<<grid, INT_THREADS, smem, s>>>(P);
     XS_LAUNCH_CHECK();
     XS_CUDA(cudaEventRecord(v->ev_k1, s));
-    XS_CUDA(cudaMemcpyAsync(v->h_stats, v->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    XS_CUDA(cudaMemcpyAsync(v->h_stats, v->d_stats, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     if (v->pipelined) return XS_OK;     // the frame loop queues the raycast behind this without a host round trip
     XS_CUDA(cudaStreamSynchronize(s));  // integrateTsdfVolume syncs, TsdfFusion.cu:200
     return xs_volume_finish_frame(v, stats_host);

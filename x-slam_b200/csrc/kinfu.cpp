@@ -12,6 +12,7 @@
 // stages except where the host needs a result (the 6x6 solve).
 #include "../../include/xslam_b200.h"
 #include "host_jet.h"
+#include "xs_batch.h"
 
 #include <cuda_runtime_api.h>
 
@@ -30,9 +31,11 @@ struct IcpScratch;
 IcpScratch *icp_scratch_create();
 void icp_scratch_destroy(IcpScratch *sc);
 int icp_iteration_async(IcpScratch *sc, const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
-                        xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, int comps,
-                        int dirs, float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
+                        xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, const BatchView &batch,
+                        float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
                         double *d_log, cudaStream_t s, cudaStream_t s_real, int slot);
+// raycast.cu: resizeVMap / resizeNMap for a batch description
+int resize_map_batch(bool normalize, const float *d_in, int rows, int cols, const BatchView &B, float *d_out, cudaStream_t s);
 void icp_timing_reset(IcpScratch *sc);
 // integrate.cu: pose-independent head of the integration (metric depth, tile maxima, cleared counters)
 int integrate_prepare(xs_volume *v, const uint16_t *d_depth, size_t depth_step_bytes, int rows, int cols, cudaStream_t s);
@@ -62,6 +65,8 @@ using namespace xs;
 struct xs_kinfu {
     xs_config cfg;
     int comps, dirs, ncomp, solve_mode;
+    Batch batch;                 // what the ncomp derivative components mean (xs_batch.h)
+    std::vector<HPair> hpairs;   // host copy of the pair table for the host jets (comps == 2)
     xs_intr intr;
     HMat4 world2camera, world2volume;
     std::vector<HMat4> record;  // world2camera_record
@@ -136,6 +141,8 @@ size_t map_floats(const xs_kinfu *k, int level, bool jets) {
 void set_ctx(const xs_kinfu *k) {
     hj_ctx().comps = k->comps;
     hj_ctx().dirs = k->dirs;
+    hj_ctx().npairs = (int) k->hpairs.size();
+    hj_ctx().pairs = k->hpairs.empty() ? nullptr : k->hpairs.data();
 }
 
 // After the frame's work has completed on the stream: integration statistics and per-stage device times.
@@ -169,10 +176,21 @@ int finish_pending(xs_kinfu *k) {
 
 extern "C" {
 
+static xs_kinfu *kinfu_create(const xs_config *cfg, int comps, int dirs, int npairs, const int *pairs, const float *seeds, int solve_mode);
+
 xs_kinfu *xs_kinfu_create(const xs_config *cfg, int comps, int dirs, const float *seeds, int solve_mode) {
-    if (!cfg || (comps != 1 && comps != 3) || dirs < 0 || comps * dirs > HJ_MAX || cfg->num_levels < 1 ||
+    return kinfu_create(cfg, comps, dirs, -1, nullptr, seeds, solve_mode);
+}
+// Hessian batch (comps = 2): nparams first-order components and one second-order component per listed pair (i <= j, sorted by
+// i; pairs == NULL: all nparams (nparams + 1) / 2 pairs).  seeds: [(nparams + npairs)][16].
+xs_kinfu *xs_kinfu_create_hessian(const xs_config *cfg, int nparams, int npairs, const int *pairs, const float *seeds, int solve_mode) {
+    return kinfu_create(cfg, 2, nparams, pairs ? npairs : -1, pairs, seeds, solve_mode);
+}
+
+static xs_kinfu *kinfu_create(const xs_config *cfg, int comps, int dirs, int npairs, const int *pairs, const float *seeds, int solve_mode) {
+    if (!cfg || (comps != 1 && comps != 2 && comps != 3) || dirs < 0 || batch_ncomp(comps, dirs, npairs) > HJ_MAX || cfg->num_levels < 1 ||
         cfg->num_levels > 3) {
-        set_error("xs_kinfu_create: bad arguments (comps in {1,3}, comps*dirs <= 256, 1 <= num_levels <= 3)");
+        set_error("xs_kinfu_create: bad arguments (comps in {1,2,3}, at most 256 derivative components, 1 <= num_levels <= 3)");
         return nullptr;
     }
     int ndev = 0;
@@ -180,13 +198,22 @@ xs_kinfu *xs_kinfu_create(const xs_config *cfg, int comps, int dirs, const float
         set_error("xs_kinfu_create: no CUDA device (libxslam_b200 has no CPU fallback)");
         return nullptr;
     }
+    // the host jets size their component arrays from the thread's context: set it before any HJet is constructed
     hj_ctx().comps = comps;
     hj_ctx().dirs = dirs;
+    hj_ctx().npairs = comps == 2 ? batch_ncomp(2, dirs, npairs) - dirs : 0;
+    hj_ctx().pairs = nullptr;
     xs_kinfu *k = new xs_kinfu();
     k->cfg = *cfg;
     k->comps = comps;
     k->dirs = dirs;
-    k->ncomp = comps * dirs;
+    if (batch_init(k->batch, comps, dirs, npairs, pairs) != XS_OK) {
+        delete k;
+        return nullptr;
+    }
+    for (int i = 0; i < k->batch.v.m; ++i) k->hpairs.push_back(HPair{k->batch.h_pairs[i].x, k->batch.h_pairs[i].y});
+    k->ncomp = k->batch.v.ncomp;
+    set_ctx(k);
     k->solve_mode = solve_mode;
     k->frame_step = cfg->frame_step > 0 ? cfg->frame_step : 1;
     k->intr = xs_intr{cfg->fx, cfg->fy, cfg->cx, cfg->cy};
@@ -247,7 +274,8 @@ xs_kinfu *xs_kinfu_create(const xs_config *cfg, int comps, int dirs, const float
         return nullptr;
     }
     k->icp = icp_scratch_create();
-    k->volume = xs_volume_create(cfg->res, cfg->voxel_size, cfg->thres_range, comps, dirs);  // :66-67
+    k->volume = comps == 2 ? xs_volume_create_hessian(cfg->res, cfg->voxel_size, cfg->thres_range, dirs, k->batch.v.m, (const int *) k->batch.h_pairs)
+                           : xs_volume_create(cfg->res, cfg->voxel_size, cfg->thres_range, comps, dirs);  // :66-67
     if (!k->volume) {
         xs_kinfu_destroy(k);
         return nullptr;
@@ -261,6 +289,7 @@ void xs_kinfu_destroy(xs_kinfu *k) {
     xs_volume_destroy(k->volume);
     if (k->stream_real) cudaStreamSynchronize(k->stream_real);
     icp_scratch_destroy(k->icp);
+    batch_free(k->batch);
     cudaFree(k->d_depth2[0]);
     cudaFree(k->d_depth2[1]);
     cudaFreeHost(k->h_depth);
@@ -357,7 +386,7 @@ int xs_kinfu_pose_estimate(xs_kinfu *k) {
         for (int iter = 0; iter < k->icp_iterations[level]; ++iter, ++it) {
             const int rc = icp_iteration_async(k->icp, k->d_pose_slot(it), k->vmaps_curr[level], k->nmaps_curr[level], &prev_pose,
                                                level_intr(k->intr, level), k->vmaps_prev[level], k->nmaps_prev[level], rows,
-                                               cols, k->comps, k->dirs, c.dist_thres, k->angle_thres, k->d_pose_slot(it + 1),
+                                               cols, k->batch.v, c.dist_thres, k->angle_thres, k->d_pose_slot(it + 1),
                                                k->solve_mode, k->d_status,
                                                k->log_icp && it < 16 ? k->d_icp_log + (size_t) it * log_stride : nullptr,
                                                k->stream, split ? k->stream_real : nullptr, it);
@@ -434,11 +463,9 @@ int xs_kinfu_calculate_point_cloud(xs_kinfu *k) {
     to_pose(hrotation(v2w), htranslation(v2w), k->ncomp, k->dR2, k->dt2, p_v2w);
     int rc = xs_raycast(k->volume, k->intr, &p_c2v, &p_v2w, c.height, c.width, k->vmaps_prev[0], k->nmaps_prev[0], k->stream);
     for (int i = 1; i < c.num_levels && rc == XS_OK; ++i) {
-        rc = xs_resize_vmap(k->vmaps_prev[i - 1], c.height >> (i - 1), c.width >> (i - 1), k->comps, k->dirs,
-                            k->vmaps_prev[i], k->stream);
+        rc = resize_map_batch(false, k->vmaps_prev[i - 1], c.height >> (i - 1), c.width >> (i - 1), k->batch.v, k->vmaps_prev[i], k->stream);
         if (rc == XS_OK)
-            rc = xs_resize_nmap(k->nmaps_prev[i - 1], c.height >> (i - 1), c.width >> (i - 1), k->comps, k->dirs,
-                                k->nmaps_prev[i], k->stream);
+            rc = resize_map_batch(true, k->nmaps_prev[i - 1], c.height >> (i - 1), c.width >> (i - 1), k->batch.v, k->nmaps_prev[i], k->stream);
     }
     return rc;
 }

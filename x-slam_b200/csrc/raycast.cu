@@ -22,6 +22,8 @@ struct RaycastParams {
     int dirs;
     float time_step;
     float *vmap, *nmap;  // [(1+ncomp)][3][rows][cols]
+    BatchView batch;     // meaning of the derivative components
+    unsigned long long *stats;  // [4] pixels with a valid vertex, [5] with a valid normal (algorithmic-bytes model)
 };
 
 XS_DEV float read_value(const VolumeView &V, int x, int y, int z) {
@@ -296,19 +298,20 @@ XS_DEV bool hit_phase_c(const RaycastParams &P, const float *ctx, float (&ng)[3]
 }
 
 // derivative components of one trilinear sample for one direction; dpos = derivative of the sample position
+// dq[cc] = first element of the plane of component cc inside brick 0 (deriv + comp * BRICK_VOX): the C components of a
+// direction are consecutive planes for the list kinds, arbitrary ones (F_i, F_j, S_ij) for a Hessian batch.
 template <int C>
-XS_DEV Jet<C, 1> sample_deriv(const VolumeView &V, const float *__restrict__ dq /* deriv + q*C*BRICK_VOX */, const float *ctx,
-                              const Jet3<C, 1> &pos, float inv_vs) {
+XS_DEV Jet<C, 1> sample_deriv(const VolumeView &V, const float *const (&dq)[C], const float *ctx, const Jet3<C, 1> &pos, float inv_vs) {
     const float a = ctx[S_A * HIT_PX], b = ctx[S_B * HIT_PX], c = ctx[S_C * HIT_PX];
     float f[C][8];
-    const float *p000 = dq + ((unsigned long long) __float_as_uint(ctx[S_OFF * HIT_PX]) |
-                              ((unsigned long long) __float_as_uint(ctx[(S_OFF + 1) * HIT_PX]) << 32));
+    const long long o000 = (long long) ((unsigned long long) __float_as_uint(ctx[S_OFF * HIT_PX]) |
+                                        ((unsigned long long) __float_as_uint(ctx[(S_OFF + 1) * HIT_PX]) << 32));
     const long long sx = __float_as_int(ctx[S_SX * HIT_PX]), sy = __float_as_int(ctx[S_SY * HIT_PX]), sz = __float_as_int(ctx[S_SZ * HIT_PX]);
 #pragma unroll
     for (int cidx = 0; cidx < 8; ++cidx) {
-        const float *p = p000 + ((cidx & 4) ? sx : 0) + ((cidx & 2) ? sy : 0) + ((cidx & 1) ? sz : 0);
+        const long long o = o000 + ((cidx & 4) ? sx : 0) + ((cidx & 2) ? sy : 0) + ((cidx & 1) ? sz : 0);
 #pragma unroll
-        for (int cc = 0; cc < C; ++cc) f[cc][cidx] = __ldg(p + cc * BRICK_VOX);
+        for (int cc = 0; cc < C; ++cc) f[cc][cidx] = __ldg(dq[cc] + o);
     }
     Jet<C, 1> r;
     r.v = ctx[S_VAL * HIT_PX];
@@ -337,13 +340,78 @@ XS_DEV Jet<C, 1> sample_deriv(const VolumeView &V, const float *__restrict__ dq 
     return r;
 }
 
+// One perturbation direction of one pixel group: propagates the C derivative components comp[0..C-1] (indices into the
+// pose derivative tables, the derivative planes and the output maps) through the hit evaluation; components
+// c >= first_store are written (a pair of a Hessian batch recomputes F_i, F_j as coefficients and stores only S_ij).
+template <int C>
+XS_DEV void hit_direction(const RaycastParams &P, const float *ctx, int x, int y, float ny, float inv_vs, const int (&comp)[C],
+                          int first_store) {
+    typedef Jet<C, 1> J;
+    const VolumeView &V = P.V;
+    const float *xctx = ctx + 8 * S_FIELDS * HIT_PX;
+    const unsigned flags = __float_as_uint(xctx[X_FLAGS * HIT_PX]);
+    const float t0 = xctx[X_T0 * HIT_PX];
+    const float nx = (float(x) - P.intr.cx) * __fdividef(1.f, P.intr.fx);
+    Jet3<C, 1> vw, ng;
+    if (flags & 1u) {
+        // ray: start = t, dir = normalized(R * next)  (RayCaster.cu:56-62,207-213)
+        const JetPose<C, 1> c2v = load_pose_comps<C>(P.c2v, P.dpose_c2v, comp);
+        Jet3<C, 1> next = {jconst<C, 1>(nx), jconst<C, 1>(ny), jconst<C, 1>(1.f)};
+        const Jet3<C, 1> start = c2v.t;
+        Jet3<C, 1> dir = jnormalized_fast(jrot(c2v, next));
+        // the reference patches exactly-zero direction components with a constant (:211-213)
+        if (dir.x.v == 0.f) dir.x = jconst<C, 1>(1e-15f);
+        if (dir.y.v == 0.f) dir.y = jconst<C, 1>(1e-15f);
+        if (dir.z.v == 0.f) dir.z = jconst<C, 1>(1e-15f);
+        const float t1 = t0 + P.time_step;
+        const Jet3<C, 1> p1 = {jfmaf(dir.x, t1, start.x), jfmaf(dir.y, t1, start.y), jfmaf(dir.z, t1, start.z)};
+        const Jet3<C, 1> p0 = {jfmaf(dir.x, t0, start.x), jfmaf(dir.y, t0, start.y), jfmaf(dir.z, t0, start.z)};
+        const float *dq[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) dq[c] = V.deriv + (size_t) comp[c] * BRICK_VOX;
+        const J Ftdt = sample_deriv<C>(V, dq, ctx + 0 * S_FIELDS * HIT_PX, p1, inv_vs);
+        const J Ft = sample_deriv<C>(V, dq, ctx + 1 * S_FIELDS * HIT_PX, p0, inv_vs);
+        const J coef = jdiv_fast(Ft, Ftdt - Ft);
+        J Ts;
+        Ts.v = fmaf(-coef.v, P.time_step, t0);
+#pragma unroll
+        for (int i = 0; i < C; ++i) Ts.d[i] = -P.time_step * coef.d[i];
+        const Jet3<C, 1> vertex = {start.x + dir.x * Ts, start.y + dir.y * Ts, start.z + dir.z * Ts};
+        const JetPose<C, 1> v2w = load_pose_comps<C>(P.v2w, P.dpose_v2w, comp);
+        vw = jrot(v2w, vertex) + v2w.t;
+        if (flags & 2u) {
+            // the six normal samples sit at vertex +- half a voxel along one axis: same position derivative
+            Jet3<C, 1> n;
+            n.x = sample_deriv<C>(V, dq, ctx + 2 * S_FIELDS * HIT_PX, vertex, inv_vs) -
+                  sample_deriv<C>(V, dq, ctx + 3 * S_FIELDS * HIT_PX, vertex, inv_vs);
+            n.y = sample_deriv<C>(V, dq, ctx + 4 * S_FIELDS * HIT_PX, vertex, inv_vs) -
+                  sample_deriv<C>(V, dq, ctx + 5 * S_FIELDS * HIT_PX, vertex, inv_vs);
+            n.z = sample_deriv<C>(V, dq, ctx + 6 * S_FIELDS * HIT_PX, vertex, inv_vs) -
+                  sample_deriv<C>(V, dq, ctx + 7 * S_FIELDS * HIT_PX, vertex, inv_vs);
+            ng = jrot(v2w, jnormalized_fast(n));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        if (i < first_store) continue;
+        const int out = 1 + comp[i];
+        if (flags & 1u)
+            store3(P.vmap, out, P.rows, P.cols, y, x, vw.x.d[i], vw.y.d[i], vw.z.d[i]);
+        else
+            store3(P.vmap, out, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
+        if (flags & 2u)
+            store3(P.nmap, out, P.rows, P.cols, y, x, ng.x.d[i], ng.y.d[i], ng.z.d[i]);
+        else
+            store3(P.nmap, out, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
+    }
+}
+
 // HIT_PG pixel groups of 32 pixels per CTA: the real phases (A: one warp per group, B: one warp per (group, normal
 // sample), C: one warp per group) fill the 8 warps four times better than with a single group, and the derivative loop
 // runs over (direction, group) tasks.
 constexpr int HIT_PG = 4;
-template <int C> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS, 2) raycast_hit_kernel(const RaycastParams P, const float *__restrict__ hit_time) {
+template <int KIND> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS, 2) raycast_hit_kernel(const RaycastParams P, const float *__restrict__ hit_time) {
     extern __shared__ float s_ctx[];  // [HIT_PG][HIT_CTX_WORDS][HIT_PX]
-    typedef Jet<C, 1> J;
     const int lane = threadIdx.x, warp = threadIdx.y;
     const int y = blockIdx.y;
     const float qnan = __int_as_float(0x7fffffff);
@@ -386,83 +454,88 @@ template <int C> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS, 2) raycast
             else
                 store3(P.nmap, 0, P.rows, P.cols, y, x, qnan, 0.f, 0.f);
             xctx[X_FLAGS * HIT_PX] = __uint_as_float((flags_a & 1u) | (n_ok ? 2u : 0u));
+            flags_a = (flags_a & 1u) | (n_ok ? 2u : 0u);
+        } else {
+            flags_a = 0u;
+        }
+        if (P.stats) {  // valid-vertex / valid-normal pixel counts of the frame
+            const unsigned mv = __ballot_sync(0xffffffffu, (flags_a & 1u) != 0), mn = __ballot_sync(0xffffffffu, (flags_a & 2u) != 0);
+            if (lane == 0 && mv) atomicAdd(P.stats + 4, (unsigned long long) __popc(mv));
+            if (lane == 0 && mn) atomicAdd(P.stats + 5, (unsigned long long) __popc(mn));
         }
     }
     __syncthreads();
-    if (P.dirs == 0) return;
-    const VolumeView &V = P.V;
-    const float inv_vs = __fdividef(1.f, V.voxel);
+    if (P.batch.ncomp == 0) return;
+    const float inv_vs = __fdividef(1.f, P.V.voxel);
     const float ny = (float(y) - P.intr.cy) * __fdividef(1.f, P.intr.fy);
-    for (int task = warp; task < P.dirs * HIT_PG; task += HIT_WARPS) {
+    // tasks: (direction, pixel group) for the list kinds; for a Hessian batch first the n parameters (first-order algebra,
+    // component i) and then the m pairs (bicomplex algebra on (F_i, F_j, S_ij), of which only S_ij is stored)
+    const int ntasks = (KIND == 2 ? P.batch.n + P.batch.m : P.dirs) * HIT_PG;
+    for (int task = warp; task < ntasks; task += HIT_WARPS) {
         const int q = task / HIT_PG, pg = task % HIT_PG;
         const int x = x_of(pg);
         if (x >= P.cols) continue;
-        const float *ctx = ctx_of(pg), *xctx = ctx + 8 * S_FIELDS * HIT_PX;
-        const unsigned flags = __float_as_uint(xctx[X_FLAGS * HIT_PX]);
-        const float t0 = xctx[X_T0 * HIT_PX];
-        const float nx = (float(x) - P.intr.cx) * __fdividef(1.f, P.intr.fx);
-        Jet3<C, 1> vw, ng;
-        if (flags & 1u) {
-            // ray: start = t, dir = normalized(R * next)  (RayCaster.cu:56-62,207-213)
-            const JetPose<C, 1> c2v = load_pose_vec<C>(P.c2v, P.dpose_c2v, q);
-            Jet3<C, 1> next = {jconst<C, 1>(nx), jconst<C, 1>(ny), jconst<C, 1>(1.f)};
-            const Jet3<C, 1> start = c2v.t;
-            Jet3<C, 1> dir = jnormalized_fast(jrot(c2v, next));
-            // the reference patches exactly-zero direction components with a constant (:211-213)
-            if (dir.x.v == 0.f) dir.x = jconst<C, 1>(1e-15f);
-            if (dir.y.v == 0.f) dir.y = jconst<C, 1>(1e-15f);
-            if (dir.z.v == 0.f) dir.z = jconst<C, 1>(1e-15f);
-            const float t1 = t0 + P.time_step;
-            const Jet3<C, 1> p1 = {jfmaf(dir.x, t1, start.x), jfmaf(dir.y, t1, start.y), jfmaf(dir.z, t1, start.z)};
-            const Jet3<C, 1> p0 = {jfmaf(dir.x, t0, start.x), jfmaf(dir.y, t0, start.y), jfmaf(dir.z, t0, start.z)};
-            const float *dq = V.deriv + (size_t) q * C * BRICK_VOX;
-            const J Ftdt = sample_deriv<C>(V, dq, ctx + 0 * S_FIELDS * HIT_PX, p1, inv_vs);
-            const J Ft = sample_deriv<C>(V, dq, ctx + 1 * S_FIELDS * HIT_PX, p0, inv_vs);
-            const J coef = jdiv_fast(Ft, Ftdt - Ft);
-            J Ts;
-            Ts.v = fmaf(-coef.v, P.time_step, t0);
-#pragma unroll
-            for (int i = 0; i < C; ++i) Ts.d[i] = -P.time_step * coef.d[i];
-            const Jet3<C, 1> vertex = {start.x + dir.x * Ts, start.y + dir.y * Ts, start.z + dir.z * Ts};
-            const JetPose<C, 1> v2w = load_pose_vec<C>(P.v2w, P.dpose_v2w, q);
-            vw = jrot(v2w, vertex) + v2w.t;
-            if (flags & 2u) {
-                // the six normal samples sit at vertex +- half a voxel along one axis: same position derivative
-                Jet3<C, 1> n;
-                n.x = sample_deriv<C>(V, dq, ctx + 2 * S_FIELDS * HIT_PX, vertex, inv_vs) -
-                      sample_deriv<C>(V, dq, ctx + 3 * S_FIELDS * HIT_PX, vertex, inv_vs);
-                n.y = sample_deriv<C>(V, dq, ctx + 4 * S_FIELDS * HIT_PX, vertex, inv_vs) -
-                      sample_deriv<C>(V, dq, ctx + 5 * S_FIELDS * HIT_PX, vertex, inv_vs);
-                n.z = sample_deriv<C>(V, dq, ctx + 6 * S_FIELDS * HIT_PX, vertex, inv_vs) -
-                      sample_deriv<C>(V, dq, ctx + 7 * S_FIELDS * HIT_PX, vertex, inv_vs);
-                ng = jrot(v2w, jnormalized_fast(n));
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < C; ++i) {
-            const int comp = 1 + q * C + i;
-            if (flags & 1u)
-                store3(P.vmap, comp, P.rows, P.cols, y, x, vw.x.d[i], vw.y.d[i], vw.z.d[i]);
-            else
-                store3(P.vmap, comp, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
-            if (flags & 2u)
-                store3(P.nmap, comp, P.rows, P.cols, y, x, ng.x.d[i], ng.y.d[i], ng.z.d[i]);
-            else
-                store3(P.nmap, comp, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
+        const float *ctx = ctx_of(pg);
+        if (KIND == 1) {
+            const int comp[1] = {q};
+            hit_direction<1>(P, ctx, x, y, ny, inv_vs, comp, 0);
+        } else if (KIND == 3) {
+            const int comp[3] = {3 * q, 3 * q + 1, 3 * q + 2};
+            hit_direction<3>(P, ctx, x, y, ny, inv_vs, comp, 0);
+        } else if (q < P.batch.n) {
+            const int comp[1] = {q};
+            hit_direction<1>(P, ctx, x, y, ny, inv_vs, comp, 0);
+        } else {
+            const int2 pr = __ldg(P.batch.pairs + (q - P.batch.n));
+            const int comp[3] = {pr.x, pr.y, q};
+            hit_direction<3>(P, ctx, x, y, ny, inv_vs, comp, 2);
         }
     }
 }
 
 // resizeMapKernel, Map.cu:105-152, for packed-SoA maps with derivative components.
-// Thread = (output pixel, slot): slot 0 writes the real part with the reference's arithmetic, slot s >= 1 writes the C
-// derivative components of direction s-1 (its real coefficients come from the same four real texels, MUFU-normalised).
-template <int C, bool NORMALIZE>
-__global__ void __launch_bounds__(256) resize_map_kernel(int drows, int dcols, int srows, int scols, int dirs,
+// Thread = (output pixel, slot): slot 0 writes the real part with the reference's arithmetic, slot s >= 1 writes the
+// derivative components of task s-1 (its real coefficients come from the same four real texels, MUFU-normalised).  A task
+// is a direction for the list kinds; for a Hessian batch the n parameters come first (first-order algebra), then the m
+// pairs (bicomplex algebra on (F_i, F_j, S_ij), only S_ij stored).  Without normalisation (vertex maps) the operation is
+// linear, so every component is an independent first-order task whatever the kind.
+template <int C>
+XS_DEV void resize_task(const float *__restrict__ p00, size_t splane, int scols, bool normalize, bool invalid, const int (&comp)[C],
+                        int first_store, float *__restrict__ out, int drows, int dcols, int y, int x) {
+    if (invalid) {
+#pragma unroll
+        for (int i = 0; i < C; ++i)
+            if (i >= first_store) store3(out, 1 + comp[i], drows, dcols, y, x, 0.f, 0.f, 0.f);
+        return;
+    }
+    Jet<C, 1> c[3];
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const float *p = p00 + pl * splane;
+        const float2 a = *reinterpret_cast<const float2 *>(p), b = *reinterpret_cast<const float2 *>(p + scols);
+        c[pl].v = (a.x + a.y + b.x + b.y) * 0.25f;
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            const float *pd = p + (size_t) (1 + comp[i]) * 3 * splane;
+            const float2 da = *reinterpret_cast<const float2 *>(pd), db = *reinterpret_cast<const float2 *>(pd + scols);
+            c[pl].d[i] = (da.x + da.y + db.x + db.y) * 0.25f;
+        }
+    }
+    Jet3<C, 1> n = {c[0], c[1], c[2]};
+    if (normalize) n = jnormalized_fast(n);
+#pragma unroll
+    for (int i = 0; i < C; ++i)
+        if (i >= first_store) store3(out, 1 + comp[i], drows, dcols, y, x, n.x.d[i], n.y.d[i], n.z.d[i]);
+}
+
+template <int KIND, bool NORMALIZE>
+__global__ void __launch_bounds__(256) resize_map_kernel(int drows, int dcols, int srows, int scols, BatchView B,
                                                          const float *__restrict__ in, float *__restrict__ out) {
     const int x = threadIdx.x + blockIdx.x * 32;
     const int y = blockIdx.y;
     const int slot = threadIdx.y + blockIdx.z * 8;
-    if (x >= dcols || slot > dirs) return;
+    const int ntasks = KIND == 2 ? B.n + B.m : B.n;
+    if (x >= dcols || slot > ntasks) return;
     const size_t splane = (size_t) srows * scols;
     const float *p00 = in + (size_t) (y * 2) * scols + x * 2;
     const float qnan = __int_as_float(0x7fffffff);
@@ -485,46 +558,67 @@ __global__ void __launch_bounds__(256) resize_map_kernel(int drows, int dcols, i
         store3(out, 0, drows, dcols, y, x, n.x.v, n.y.v, n.z.v);
         return;
     }
-    const int q0 = (slot - 1) * C;
-    if (invalid) {
-#pragma unroll
-        for (int i = 0; i < C; ++i) store3(out, 1 + q0 + i, drows, dcols, y, x, 0.f, 0.f, 0.f);
-        return;
+    const int q = slot - 1;
+    if (KIND == 1) {
+        const int comp[1] = {q};
+        resize_task<1>(p00, splane, scols, NORMALIZE, invalid, comp, 0, out, drows, dcols, y, x);
+    } else if (KIND == 3) {
+        const int comp[3] = {3 * q, 3 * q + 1, 3 * q + 2};
+        resize_task<3>(p00, splane, scols, NORMALIZE, invalid, comp, 0, out, drows, dcols, y, x);
+    } else if (q < B.n) {
+        const int comp[1] = {q};
+        resize_task<1>(p00, splane, scols, NORMALIZE, invalid, comp, 0, out, drows, dcols, y, x);
+    } else {
+        const int2 pr = __ldg(B.pairs + (q - B.n));
+        const int comp[3] = {pr.x, pr.y, q};
+        resize_task<3>(p00, splane, scols, NORMALIZE, invalid, comp, 2, out, drows, dcols, y, x);
     }
-    Jet<C, 1> c[3];
-#pragma unroll
-    for (int pl = 0; pl < 3; ++pl) {
-        const float *p = p00 + pl * splane;
-        const float2 a = *reinterpret_cast<const float2 *>(p), b = *reinterpret_cast<const float2 *>(p + scols);
-        c[pl].v = (a.x + a.y + b.x + b.y) * 0.25f;
-#pragma unroll
-        for (int i = 0; i < C; ++i) {
-            const float *pd = p + (size_t) (1 + q0 + i) * 3 * splane;
-            const float2 da = *reinterpret_cast<const float2 *>(pd), db = *reinterpret_cast<const float2 *>(pd + scols);
-            c[pl].d[i] = (da.x + da.y + db.x + db.y) * 0.25f;
-        }
-    }
-    Jet3<C, 1> n = {c[0], c[1], c[2]};
-    if (NORMALIZE) n = jnormalized_fast(n);
-#pragma unroll
-    for (int i = 0; i < C; ++i) store3(out, 1 + q0 + i, drows, dcols, y, x, n.x.d[i], n.y.d[i], n.z.d[i]);
 }
 
 int upload_pose_derivs(const xs_volume *v, const xs_pose *p, int slot, cudaStream_t s);
 
-template <bool NORMALIZE>
-static int resize_map(const float *d_in, int rows, int cols, int comps, int dirs, float *d_out, void *stream) {
-    if (!d_in || !d_out || rows < 2 || cols < 2 || (comps != 1 && comps != 3) || dirs < 0) return XS_ERR_ARG;
+// resizeVMap / resizeNMap for a batch description (the frame loop's entry; the public comps / dirs forms wrap it)
+int resize_map_batch(bool normalize, const float *d_in, int rows, int cols, const BatchView &B, float *d_out, cudaStream_t s) {
+    if (!d_in || !d_out || rows < 2 || cols < 2) return XS_ERR_ARG;
     if ((cols & 1) || (rows & 1)) return XS_ERR_ARG;  // 64-bit texel pairs
     const int drows = rows / 2, dcols = cols / 2;
-    dim3 blk(32, 8), grd(div_up(dcols, 32), drows, div_up(dirs + 1, 8));
-    cudaStream_t s = (cudaStream_t) stream;
-    if (comps == 1)
-        resize_map_kernel<1, NORMALIZE><<<grd, blk, 0, s>>>(drows, dcols, rows, cols, dirs, d_in, d_out);
-    else
-        resize_map_kernel<3, NORMALIZE><<<grd, blk, 0, s>>>(drows, dcols, rows, cols, dirs, d_in, d_out);
+    BatchView L = B;
+    if (!normalize && B.kind != 1) {  // linear operation: every component is an independent first-order task
+        L.kind = 1;
+        L.n = B.ncomp;
+        L.m = 0;
+    }
+    const int ntasks = L.kind == 2 ? L.n + L.m : L.n;
+    dim3 blk(32, 8), grd(div_up(dcols, 32), drows, div_up(ntasks + 1, 8));
+    if (L.kind == 1) {
+        if (normalize)
+            resize_map_kernel<1, true><<<grd, blk, 0, s>>>(drows, dcols, rows, cols, L, d_in, d_out);
+        else
+            resize_map_kernel<1, false><<<grd, blk, 0, s>>>(drows, dcols, rows, cols, L, d_in, d_out);
+    } else if (L.kind == 3) {
+        resize_map_kernel<3, true><<<grd, blk, 0, s>>>(drows, dcols, rows, cols, L, d_in, d_out);
+    } else {
+        resize_map_kernel<2, true><<<grd, blk, 0, s>>>(drows, dcols, rows, cols, L, d_in, d_out);
+    }
     XS_LAUNCH_CHECK();
     return XS_OK;
+}
+
+// public form: comps = 1 / 3 with dirs directions, or comps = 2 with dirs parameters and all their pairs
+template <bool NORMALIZE>
+static int resize_map(const float *d_in, int rows, int cols, int comps, int dirs, float *d_out, void *stream) {
+    if ((comps != 1 && comps != 2 && comps != 3) || dirs < 0) return XS_ERR_ARG;
+    if (comps != 2 || !NORMALIZE) {
+        const BatchView B = {comps == 2 ? 1 : comps, comps == 2 ? batch_ncomp(2, dirs, -1) : dirs, 0, batch_ncomp(comps, dirs, -1), nullptr};
+        return resize_map_batch(NORMALIZE, d_in, rows, cols, B, d_out, (cudaStream_t) stream);
+    }
+    Batch b;  // normal maps of a Hessian batch need the pair table on the device
+    int rc = batch_init(b, 2, dirs, -1, nullptr);
+    if (rc != XS_OK) return rc;
+    rc = resize_map_batch(true, d_in, rows, cols, b.v, d_out, (cudaStream_t) stream);
+    if (rc == XS_OK && cudaStreamSynchronize((cudaStream_t) stream) != cudaSuccess) rc = XS_ERR_CUDA;
+    batch_free(b);
+    return rc;
 }
 
 }  // namespace xs
@@ -563,6 +657,8 @@ int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_po
     P.rows = rows;
     P.cols = cols;
     P.dirs = v->dirs;
+    P.batch = v->batch.v;
+    P.stats = v->d_stats;
     P.time_step = v->view.trunc * 0.8f;  // RayCaster.cu:350
     P.vmap = d_vmap;
     P.nmap = d_nmap;
@@ -581,15 +677,36 @@ int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_po
     static bool hit_smem_set = false;
     if (!hit_smem_set) {
         XS_CUDA(cudaFuncSetAttribute(raycast_hit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hit_smem));
+        XS_CUDA(cudaFuncSetAttribute(raycast_hit_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hit_smem));
         XS_CUDA(cudaFuncSetAttribute(raycast_hit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hit_smem));
         hit_smem_set = true;
     }
+    XS_CUDA(cudaMemsetAsync(v->d_stats + 4, 0, 2 * sizeof(unsigned long long), s));
+    XS_CUDA(cudaEventRecord(v->ev_h0, s));
     if (v->comps == 1)
         raycast_hit_kernel<1><<<g2, b2, hit_smem, s>>>(P, v->d_hit_time);
+    else if (v->comps == 2)
+        raycast_hit_kernel<2><<<g2, b2, hit_smem, s>>>(P, v->d_hit_time);
     else
         raycast_hit_kernel<3><<<g2, b2, hit_smem, s>>>(P, v->d_hit_time);
     XS_LAUNCH_CHECK();
+    XS_CUDA(cudaEventRecord(v->ev_h1, s));
+    XS_CUDA(cudaMemcpyAsync(v->h_stats + 4, v->d_stats + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     return XS_OK;  // raycast does not sync, RayCaster.cu:367
+}
+
+// device duration of the last raycast hit kernel and its valid-vertex / valid-normal pixel counts; call after the stream has
+// been synchronised (the frame loop: after the frame has been collected)
+float xs_volume_last_raycast_hit_ms(const xs_volume *v) {
+    float ms = 0.f;
+    if (v && cudaEventElapsedTime(&ms, v->ev_h0, v->ev_h1) != cudaSuccess) ms = 0.f;
+    return ms;
+}
+int xs_volume_raycast_stats(const xs_volume *v, unsigned long long *out2) {
+    if (!v || !out2) return XS_ERR_ARG;
+    out2[0] = v->h_stats[4];
+    out2[1] = v->h_stats[5];
+    return XS_OK;
 }
 
 int xs_resize_vmap(const float *d_in, int rows, int cols, int comps, int dirs, float *d_out, void *stream) {

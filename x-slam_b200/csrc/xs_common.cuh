@@ -1,6 +1,7 @@
 // xs_common.cuh — shared host/device declarations of libxslam_b200 (not part of the public ABI).
 #pragma once
 #include "../../include/xslam_b200.h"
+#include "xs_batch.h"
 #include "xs_jet.cuh"
 
 #include <cstdio>
@@ -67,6 +68,7 @@ XS_DEV size_t deriv_index(const VolumeView &V, int x, int y, int z, int comp) {
 struct xs_volume {
     xs::VolumeView view;
     int comps, dirs;
+    xs::Batch batch;     // meaning of the view.ncomp derivative planes
     float *d_dpose;      // staging for pose derivative components [3][ncomp][12]: slots 0, 1 = c2v, v2w (raycast), 2 = v2c (integration)
     bool pipelined;      // frame-loop mode: xs_integrate / xs_raycast do not synchronise (xs_volume_finish_frame collects stats)
     float *h_dpose;      // pinned host mirror
@@ -85,4 +87,6 @@ struct xs_volume {
     size_t bytes;
     cudaEvent_t ev_k0, ev_k1;  // bracket the integration kernel (roofline timing)
     float last_kernel_ms;
+    cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;  // bracket the raycast hit kernel
+    float last_hit_ms = 0.f;
 };

@@ -333,6 +333,27 @@ template <int C> XS_DEV JetPose<C, 1> load_pose_vec(const DevPose &P, const floa
     }
     return J;
 }
+// The same for an explicit list of component indices (Hessian batches: (F_i, F_j, S_ij) are not consecutive planes).
+template <int C> XS_DEV JetPose<C, 1> load_pose_comps(const DevPose &P, const float *__restrict__ dpose, const int (&comp)[C]) {
+    float e[C][12];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float4 *p4 = reinterpret_cast<const float4 *>(dpose + (size_t) comp[c] * 12);
+        const float4 a = __ldg(p4), b = __ldg(p4 + 1), d = __ldg(p4 + 2);
+        e[c][0] = a.x, e[c][1] = a.y, e[c][2] = a.z, e[c][3] = a.w;
+        e[c][4] = b.x, e[c][5] = b.y, e[c][6] = b.z, e[c][7] = b.w;
+        e[c][8] = d.x, e[c][9] = d.y, e[c][10] = d.z, e[c][11] = d.w;
+    }
+    JetPose<C, 1> J;
+    Jet<C, 1> *out[12] = {&J.r0.x, &J.r0.y, &J.r0.z, &J.r1.x, &J.r1.y, &J.r1.z, &J.r2.x, &J.r2.y, &J.r2.z, &J.t.x, &J.t.y, &J.t.z};
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        out[i]->v = (i < 9) ? P.R[i] : P.t[i - 9];
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[i]->d[c] = e[c][i];
+    }
+    return J;
+}
 // MatS33 * devComplex3, Internal.h:150-154
 template <int C, int K> XS_DEV Jet3<C, K> jrot(const JetPose<C, K> &P, const Jet3<C, K> &v) {
     return {jdot(P.r0, v), jdot(P.r1, v), jdot(P.r2, v)};

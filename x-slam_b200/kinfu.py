@@ -98,6 +98,30 @@ def pose_seeds_dcsfd(pairs=None, h=H_, n_params=6):
     return out.reshape(-1, 16).astype(np.float32), pairs
 
 
+def all_pairs(n):
+    """The n (n + 1) / 2 index pairs (i <= j) of a Hessian batch, in the order the library lists them by default."""
+    return [(i, j) for i in range(n) for j in range(i, n)]
+
+
+def hessian_seeds(params=None, pairs=None, h=H_):
+    """Seeds of a Hessian batch (comps = 2) for pose-space parameters: params [n, 6] are se3Exp coordinate directions
+    (default: the 6 axes), parameter p perturbs world2camera along G_p = sum_a params[p, a] G_a.  Returns
+    (seeds [(n + m), 16] float32, pairs): rows 0..n-1 = h G_p (first order), then h^2 (G_i G_j + G_j G_i) / 2 per pair - the
+    (eps1, eps2, eps1eps2) seeds of pose_seeds_dcsfd with every first-order seed stored once."""
+    G = se3_generators()
+    U = np.eye(6) if params is None else np.asarray(params, np.float64).reshape(-1, 6)
+    Gp = np.tensordot(U, G, 1)
+    n = Gp.shape[0]
+    if pairs is None:
+        pairs = all_pairs(n)
+    out = np.zeros((n + len(pairs), 16), np.float64)
+    for p in range(n):
+        out[p] = (h * Gp[p]).reshape(16)
+    for k, (i, j) in enumerate(pairs):
+        out[n + k] = (h * h * 0.5 * (Gp[i] @ Gp[j] + Gp[j] @ Gp[i])).reshape(16)
+    return out.astype(np.float32), list(pairs)
+
+
 class _DeviceView:
     """Zero-copy view of library-owned device memory through the CUDA array interface."""
 
@@ -117,9 +141,11 @@ class KinectFusionReconstruction:
         self.depth_height = 0
         self.config = None
 
-    def SetYamlParameters(self, config, comps=1, seeds=None, solve_mode=None):
+    def SetYamlParameters(self, config, comps=1, seeds=None, solve_mode=None, pairs=None, n_params=None):
         """KinectFusionReconstruction.cpp:9-73.  config: dict of YAML keys (or a path).
-        seeds: [dirs*comps, 16] h-scaled derivative components of the initial world2camera."""
+        seeds: [ncomp, 16] h-scaled derivative components of the initial world2camera.  comps = 1 / 3: lists of first-order /
+        bicomplex directions (ncomp = dirs * comps).  comps = 2: Hessian batch over n_params parameters - n_params first-order
+        rows followed by one second-order row per pair of `pairs` (default: all pairs; see hessian_seeds)."""
         if isinstance(config, str):
             config = load_yaml(config)
         cfg = dict(DEFAULT_CONFIG)
@@ -131,16 +157,33 @@ class KinectFusionReconstruction:
         self.frame_step = int(cfg.get("frame_step", 1))
         seeds = None if seeds is None else np.ascontiguousarray(seeds, np.float32).reshape(-1, 16)
         ncomp = 0 if seeds is None else seeds.shape[0]
-        if ncomp % comps:
-            raise ValueError("seeds must hold dirs*comps rows")
-        self.comps, self.dirs, self.ncomp = comps, ncomp // comps, ncomp
+        self.pairs = None
+        if comps == 2:
+            if n_params is None:  # all pairs: ncomp = n + n (n + 1) / 2
+                if pairs is not None:
+                    n_params = ncomp - len(pairs)
+                else:
+                    n_params = int(round((np.sqrt(9 + 8 * ncomp) - 3) / 2))
+            self.pairs = all_pairs(n_params) if pairs is None else [tuple(int(v) for v in p) for p in pairs]
+            if n_params + len(self.pairs) != ncomp:
+                raise ValueError("a Hessian batch needs n_params + len(pairs) seed rows")
+            self.comps, self.dirs, self.ncomp = 2, n_params, ncomp
+        else:
+            if ncomp % comps:
+                raise ValueError("seeds must hold dirs*comps rows")
+            self.comps, self.dirs, self.ncomp = comps, ncomp // comps, ncomp
         if solve_mode is None:
             solve_mode = self.SOLVE_EIGEN_LLT if comps == 1 else self.SOLVE_ANALYTIC
         c = make_config(cfg)
         sp = seeds.ctypes.data_as(C.POINTER(C.c_float)) if ncomp else None
         if self.h:
             self.lib.xs_kinfu_destroy(self.h)
-        self.h = self.lib.xs_kinfu_create(C.byref(c), comps, self.dirs, sp, solve_mode)
+        if comps == 2:
+            pa = np.ascontiguousarray(np.asarray(self.pairs, np.int32).reshape(-1, 2))
+            self.h = self.lib.xs_kinfu_create_hessian(C.byref(c), self.dirs, len(self.pairs), pa.ctypes.data_as(C.POINTER(C.c_int)), sp,
+                                                      solve_mode)
+        else:
+            self.h = self.lib.xs_kinfu_create(C.byref(c), comps, self.dirs, sp, solve_mode)
         if not self.h:
             raise _capi.XsError("SetYamlParameters: " + self.lib.xs_last_error().decode())
         self.use_gtPose = bool(cfg.get("flag_use_gtPose", False))  # KinectFusionReconstruction.cpp:69
@@ -224,6 +267,15 @@ class KinectFusionReconstruction:
         out = (C.c_ulonglong * 4)()
         check(self.lib.xs_kinfu_get_stats(self.h, out))
         return [int(x) for x in out]
+
+    def component_of(self, i, j=None):
+        """Index (into world2camera[1:], volume planes, maps[1:]) of a Hessian batch's first-order component F_i, or of the
+        second-order component S_ij of a listed pair."""
+        if self.comps != 2:
+            raise ValueError("component_of is defined for Hessian batches (comps = 2)")
+        if j is None:
+            return i
+        return self.dirs + self.pairs.index((min(i, j), max(i, j)))
 
     def algorithmic_bytes(self):
         out = (C.c_double * 4)()

@@ -91,7 +91,10 @@ def createNMap(vmap):
 def _resize(fn, m, comps):
     _need_cuda(m)
     nc1, _, rows, cols = m.shape
-    dirs = (nc1 - 1) // comps
+    if comps == 2:  # Hessian batch with all pairs: ncomp = n + n (n + 1) / 2
+        dirs = int(round((np.sqrt(9 + 8 * (nc1 - 1)) - 3) / 2))
+    else:
+        dirs = (nc1 - 1) // comps
     out = torch.empty((nc1, 3, rows // 2, cols // 2), dtype=torch.float32, device=m.device)
     check(fn(_ptr(m), rows, cols, comps, dirs, _ptr(out), _stream()), "resizeMap")
     return out
@@ -111,13 +114,22 @@ def resizeNMap(m, comps=1):
 class TsdfVolume:
     """TsdfVolume (TsdfVolume.h:18-60) over the brick-tiled device layout."""
 
-    def __init__(self, resolution, voxel_size, thres_range, comps=1, dirs=0):
+    def __init__(self, resolution, voxel_size, thres_range, comps=1, dirs=0, pairs=None):
+        """comps = 1 / 3: dirs first-order / bicomplex directions.  comps = 2: Hessian batch over dirs parameters with the
+        second-order planes of `pairs` (default: all dirs (dirs + 1) / 2 pairs)."""
         self.lib = _capi.load()
         self.res = tuple(int(r) for r in resolution)
-        self.comps, self.dirs, self.ncomp = comps, dirs, comps * dirs
+        self.comps, self.dirs = comps, dirs
         self.voxel_size = float(voxel_size)
         arr = (C.c_int * 3)(*self.res)
-        self.h = self.lib.xs_volume_create(arr, voxel_size, thres_range, comps, dirs)
+        if comps == 2:
+            self.pairs = [(i, j) for i in range(dirs) for j in range(i, dirs)] if pairs is None else [tuple(p) for p in pairs]
+            self.ncomp = dirs + len(self.pairs)
+            pa = np.ascontiguousarray(np.asarray(self.pairs, np.int32).reshape(-1, 2))
+            self.h = self.lib.xs_volume_create_hessian(arr, voxel_size, thres_range, dirs, len(self.pairs), pa.ctypes.data_as(C.POINTER(C.c_int)))
+        else:
+            self.ncomp = comps * dirs
+            self.h = self.lib.xs_volume_create(arr, voxel_size, thres_range, comps, dirs)
         if not self.h:
             raise _capi.XsError("TsdfVolume: " + self.lib.xs_last_error().decode())
 
@@ -233,7 +245,7 @@ def estimateCombined(curr, vmap_curr, nmap_curr, prev, intr, vmap_g_prev, nmap_g
     _need_cuda(vmap_curr, nmap_curr, vmap_g_prev, nmap_g_prev)
     _, rows, cols = vmap_curr.shape
     ncomp = vmap_g_prev.shape[0] - 1
-    dirs = ncomp // comps
+    dirs = int(round((np.sqrt(9 + 8 * ncomp) - 3) / 2)) if comps == 2 else ncomp // comps  # comps = 2: all pairs of dirs parameters
     A = np.zeros((1 + ncomp, 36), np.float64)
     b = np.zeros((1 + ncomp, 6), np.float64)
     pc, pp = curr.c(), prev.c()
