@@ -373,9 +373,13 @@ def run_ours(args, xs, rank, world, local_rank):
         planes_total = args.dirs * comps
     lib = xs.load()
     rec_len = (1 + ncomp_max) * 16
-    gather_out = torch.zeros((world * rec_len,), dtype=torch.float32, device="cuda") if world > 1 else None
-    send = torch.zeros((rec_len,), dtype=torch.float32, device="cuda") if world > 1 else None
-    rec_view = torch.as_tensor(DeviceRecord(k.pose_record_device_ptr(), (1 + ncomp_local) * 16), device="cuda")
+    comm = None
+    if world > 1:
+        # the multi-GPU layer is the library's own (csrc/comm.cpp): every ProcessFrame queues one NCCL all-gather of the ranks'
+        # pose records on an internal stream behind the frame's record upload; torch.distributed only hands out the NCCL id
+        from xslam_b200 import parallel
+        comm = parallel.Comm.from_torch_distributed(dist, device="cuda")
+        k.set_comm(comm, rec_len)
 
     # A step is one batch of FPS consecutive frames (each one ProcessFrame).  The synthetic trajectory is a closed loop of
     # period 300 frames, so frame f of the stream is frame f % 300 of the generator: at most 300 distinct frames are rendered
@@ -397,22 +401,9 @@ def run_ours(args, xs, rank, world, local_rank):
         ok = k.ProcessFrame(depth)
         if not ok:
             raise RuntimeError("frame alignment failed: " + lib.xs_last_error().decode())
-        if world > 1:  # derivatives gathered by NCCL all-gather over NVLink (north_star (4))
-            # stream-ordered behind the frame's record upload, no host wait; the collective runs on NCCL's stream beside the
-            # next frame's kernels (async_op: the pipeline's stream does not wait for it until the send buffer is reused)
-            with torch.cuda.stream(lib_stream):
-                if gather_work[0] is not None:
-                    gather_work[0].wait()
-                send[: rec_view.numel()].copy_(rec_view)
-                gather_work[0] = dist.all_gather_into_tensor(gather_out, send, async_op=True)
-
-    gather_work = [None]
 
     def sync():
-        k.sync()  # collects a deferred frame
-        if gather_work[0] is not None:
-            gather_work[0].wait()
-            gather_work[0] = None
+        k.sync()  # collects a deferred frame and waits for its all-gather
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -469,9 +460,6 @@ def run_ours(args, xs, rank, world, local_rank):
             if t_px[j] == 640 * 480:
                 icp_ms += t_ms[j]
                 icp_n += 1
-    if gather_work[0] is not None:  # the closing event also covers the last frame's all-gather
-        with torch.cuda.stream(lib_stream):
-            gather_work[0].wait()
     ev1.record(lib_stream)
     sync()
     t_wall = time.perf_counter() - t0
@@ -487,7 +475,7 @@ def run_ours(args, xs, rank, world, local_rank):
     t0 = time.perf_counter()
     for i in range(NF):
         step(next_frame(pinned).numpy().view(np.uint16))
-        w2c = k.world2camera  # the frame's result, read on the host
+        w2c = k.gathered_records() if comm is not None else k.world2camera  # the frame's result (all ranks' derivatives), read on the host
     sync()
     t_e2e = time.perf_counter() - t0
     clocks = sampler.summary()

@@ -281,10 +281,34 @@ float *xs_kinfu_pose_record_device(xs_kinfu *k);
 /* gt_poses + flag_use_gtPose (KinectFusionReconstruction.h:36,82 / .cpp:69,164-166,239-247): with use_gt_pose != 0 frames are
  * fused at the given camera-to-world poses (row-major 4x4 per frame, real) and ICP is skipped (mapping mode). */
 int xs_kinfu_set_gt_poses(xs_kinfu *k, const float *poses16, int n, int use_gt_pose);
+/* se3Exp (KinectFusionReconstruction.h:176-219), the parameterisation of the reference's pose-set / relocalisation experiments,
+ * on batched jets (host): xi [(1 + ncomp)][6] = (v, omega), component 0 real, then the h-scaled derivative components of the
+ * batch kind (comps, dirs, pairs as for xs_kinfu_create / xs_kinfu_create_hessian); T_out [(1 + ncomp)][16] row-major 4x4. */
+int xs_se3_exp(const float *xi, int comps, int dirs, int npairs, const int *pairs, float *T_out);
 /* the cudaStream_t of this pipeline object: every result a consumer can observe (maps, volume, pose record) is ordered on it
  * (for event timing and stream-ordered consumers).  Work that depends on no derivative component - the real chain of the ICP,
  * the head of a deferred frame - runs on an internal second stream and is joined back by events. */
 void *xs_kinfu_stream(xs_kinfu *k);
+
+/* ---------------------------------------------------------------- multi-GPU layer (e)
+ * One process per GPU (the reference is single-GPU).  Perturbation directions are independent given the real state, which is
+ * deterministic and identical on every rank, so ranks carry shares of the derivative components (Hessian batch: every
+ * first-order component + a share of the pairs) and exchange only the per-frame pose records: one NCCL all-gather per frame,
+ * queued by xs_kinfu_process_frame itself on an internal stream behind the frame's record upload.  NCCL is bound at run time
+ * (libnccl.so.2).  The launcher distributes the 128-byte id of rank 0 (file, MPI, torch.distributed ...). */
+typedef struct xs_comm xs_comm;
+int xs_set_device(int device);
+int xs_comm_unique_id(unsigned char id_out[128]);
+xs_comm *xs_comm_create(int rank, int world, const unsigned char id[128]); /* on the current device */
+void xs_comm_destroy(xs_comm *c);
+int xs_comm_rank(const xs_comm *c);
+int xs_comm_world(const xs_comm *c);
+int xs_comm_all_gather(xs_comm *c, const float *d_send, float *d_recv, long floats, void *stream);
+/* record_floats: floats per rank in the gather, the same on every rank and >= the largest (1 + ncomp) * 16 (records are padded) */
+int xs_kinfu_set_comm(xs_kinfu *k, xs_comm *comm, int record_floats);
+/* gathered records of the last processed frame, [world][record_floats] (waits for that frame's all-gather) */
+int xs_kinfu_get_gathered_records(xs_kinfu *k, float *host_out);
+const float *xs_kinfu_gathered_records_device(xs_kinfu *k);
 
 /* ---------------------------------------------------------------- outputs & synthetic input (a13, f1) */
 /* saveTxtMatrix, IOHelper.cpp:21-32 */

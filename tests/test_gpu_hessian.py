@@ -136,14 +136,20 @@ def test_hessian_batch_pipeline_equals_dcsfd_list(xs, out_dir, mode):
     kh, kl = KF(), KF()
     kh.SetYamlParameters(cfg, comps=2, seeds=hs, pairs=pairs, n_params=n)
     kl.SetYamlParameters(cfg, comps=3, seeds=ls.reshape(-1, 16).astype(np.float32))
-    kh.enable_icp_log()
+    kh.enable_icp_log()  # with the log the derivative pass forms the full second-order sums A_ij, b_ij (27 per pair)
     kl.enable_icp_log()
+    # without it (the production path) the pair tasks accumulate g_ij = b_ij - A_ij x directly (6 values per pair, FP32 per
+    # pixel): a third instance holds that form against the full sums
+    kr = KF()
+    kr.SetYamlParameters(cfg, comps=2, seeds=hs, pairs=pairs, n_params=n)
     rep = {"frames": []}
     for f in range(3):
         d = xs.synth_depth(f)
-        assert kh.ProcessFrame(d) == 1 and kl.ProcessFrame(d) == 1
-        wh, wl = kh.world2camera, kl.world2camera
-        fr = {"real_identical": bool(np.array_equal(wh[0], wl[0]))}
+        assert kh.ProcessFrame(d) == 1 and kl.ProcessFrame(d) == 1 and kr.ProcessFrame(d) == 1
+        wh, wl, wr = kh.world2camera, kl.world2camera, kr.world2camera
+        fr = {"real_identical": bool(np.array_equal(wh[0], wl[0]) and np.array_equal(wr[0], wh[0]))}
+        fr["reduced_first_order_rel"] = max(rel_err(wr[1 + i], wh[1 + i], floor=H_ * 1e-3) for i in range(n))
+        fr["reduced_second_order_rel"] = max(rel_err(wr[1 + n + k], wh[1 + n + k], floor=H_ * H_ * 1e-3) for k in range(len(pairs)))
         fr["pose_first_order_rel"] = max(max(rel_err(wh[1 + i], wl[1 + 3 * k], floor=H_ * 1e-3), rel_err(wh[1 + j], wl[2 + 3 * k], floor=H_ * 1e-3))
                                          for k, (i, j) in enumerate(pairs))
         fr["pose_second_order_rel"] = max(rel_err(wh[1 + n + k], wl[3 + 3 * k], floor=H_ * H_ * 1e-3) for k in range(len(pairs)))
@@ -167,6 +173,8 @@ def test_hessian_batch_pipeline_equals_dcsfd_list(xs, out_dir, mode):
     assert all(fr["real_identical"] for fr in rep["frames"]) and rep["volume_identical"] and rep["maps_real_identical"]
     assert last["icp_real_identical"]
     assert last["pose_first_order_rel"] <= 1e-4 and last["pose_second_order_rel"] <= 1e-3
+    assert max(fr["reduced_first_order_rel"] for fr in rep["frames"]) <= 1e-6
+    assert max(fr["reduced_second_order_rel"] for fr in rep["frames"]) <= 1e-3
     assert last["icp_second_order_rel"] <= 1e-3
     assert rep["grad_first_order_rel"]["p99.9"] <= 1e-5 and rep["grad_second_order_rel"]["p99.9"] <= 1e-4
     assert rep["nmap_l1_second_order_rel"]["p99.9"] <= 1e-4

@@ -445,7 +445,7 @@ def test_point_extraction_parity(xs, refcuda, torch_mod, out_dir):
     rp, rn = refcuda.extract((res,) * 3, voxel, zv, zw, zg, 1000000)
     mp, mn = ops.extractPoints(vol, 1000000, normals=True)
     mp, mn = mp.cpu().numpy(), mn.cpu().numpy()
-    assert rp.shape[0] > 20000
+    assert rp.shape[0] > 2000  # the surface seen by three nearby views of the room at 6 cm voxels
     om, orf = np.lexsort(mp.T[::-1]), np.lexsort(rp.T[::-1])
     n = min(len(om), len(orf))
     pts_equal = len(om) == len(orf) and np.array_equal(mp[om], rp[orf])
@@ -457,7 +457,7 @@ def test_point_extraction_parity(xs, refcuda, torch_mod, out_dir):
     # squared-norm quirk: |n| = 1 / |grad| rather than 1
     norms = np.linalg.norm(rn[orf][:n][fin], axis=1)
     # truncated buffer
-    small = 5000
+    small = 1000
     mp_small, _ = ops.extractPoints(vol, small, normals=False)
     _report(out_dir, "extract", ref_points=int(rp.shape[0]), points=int(mp.shape[0]), point_set_equal=bool(pts_equal),
             point_max_ulp=pt_ulp, normal_max_ulp=int(nrm_ulp.max()), normal_ulp_gt2=int((nrm_ulp > 2).sum()),

@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Hardware check of the multi-GPU layer (run under torchrun on N >= 2 GPUs of one box):
+the N-rank run - every rank carries all first-order components and its share of the second-order pairs, the library
+all-gathers the pose records over NCCL after every frame (csrc/comm.cpp) - against the 1-rank run of the full batch on rank 0:
+the gathered record must equal the full record, bit for bit on the real part and <= 1e-6 relative on derivative components.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/check_gather.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import xslam_b200 as xs
+    from xslam_b200 import parallel
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    res = int(os.environ.get("XS_CHECK_RES", "256"))
+    frames = int(os.environ.get("XS_CHECK_FRAMES", "4"))
+    cfg = dict(xs.DEFAULT_CONFIG)
+    cfg.update(tsdf_size_x=res, tsdf_size_y=res, tsdf_size_z=res, tsdf_voxel_size=7.68 / res)
+    rng = np.random.default_rng(7)
+    U = np.concatenate([np.eye(6), rng.standard_normal((2, 6)) / np.sqrt(6)])  # 8 parameters, 36 pairs
+    n = U.shape[0]
+    pairs = xs.all_pairs(n)
+    mine = parallel.shard_pairs(pairs, rank, world)
+    seeds, _ = xs.hessian_seeds(U, mine)
+    k = xs.KinectFusionReconstruction()
+    k.SetYamlParameters(cfg, comps=2, seeds=seeds, pairs=mine, n_params=n)
+    comm = parallel.Comm.from_torch_distributed(dist, device="cuda")
+    L = parallel.hessian_record_floats(n, len(pairs), world)
+    k.set_comm(comm, L)
+    k.set_deferred(True)
+    full = None
+    if rank == 0:
+        sf, _ = xs.hessian_seeds(U, pairs)
+        full = xs.KinectFusionReconstruction()
+        full.SetYamlParameters(cfg, comps=2, seeds=sf, pairs=pairs, n_params=n)
+    rep = {"world": world, "parameters": n, "pairs": len(pairs), "frames": []}
+    ok = True
+    for f in range(frames):
+        d = xs.synth_depth(f)
+        assert k.ProcessFrame(d) == 1
+        g = k.gathered_records()
+        rec = parallel.assemble_hessian_records(g, n, pairs, world)
+        # replicas: every rank produced the same real pose and the same first-order components
+        same_real = bool((g.reshape(world, -1, 16)[:, 0] == g.reshape(world, -1, 16)[0, 0]).all())
+        same_first = bool((g.reshape(world, -1, 16)[:, 1:1 + n] == g.reshape(world, -1, 16)[0, 1:1 + n]).all())
+        fr = {"frame": f, "replicas_real_identical": same_real, "replicas_first_order_identical": same_first}
+        if rank == 0:
+            assert full.ProcessFrame(d) == 1
+            w = full.world2camera.reshape(-1, 16)
+            fr["real_identical_to_1rank"] = bool(np.array_equal(rec[0], w[0]))
+            sc1 = max(np.abs(w[1:1 + n]).max(), 1e-30)
+            sc2 = max(np.abs(w[1 + n:]).max(), 1e-30)
+            fr["first_order_rel"] = float(np.abs(rec[1:1 + n] - w[1:1 + n]).max() / sc1)
+            fr["second_order_rel"] = float(np.abs(rec[1 + n:] - w[1 + n:]).max() / sc2)
+            ok = ok and fr["real_identical_to_1rank"] and fr["first_order_rel"] <= 1e-6 and fr["second_order_rel"] <= 1e-6
+        ok = ok and same_real and same_first
+        rep["frames"].append(fr)
+    k.sync()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        rep["ok"] = bool(flag.item())
+        print(json.dumps(rep), flush=True)
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "gather_check_n%d.json" % world), "w") as fh:
+            json.dump(rep, fh, indent=1)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()

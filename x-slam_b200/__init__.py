@@ -15,4 +15,4 @@ from . import _capi, dataset  # noqa: F401
 from .dataset import Dataset, ICL_Dataset, seven_scenes_Dataset  # noqa: F401
 from ._capi import Config, Intr, XsError, load  # noqa: F401
 from .kinfu import (DEFAULT_CONFIG, H_, KinectFusionReconstruction, all_pairs, exportPly, hessian_seeds, load_yaml,  # noqa: F401
-                    pose_seeds_csfd, pose_seeds_dcsfd, savePose, se3_generators, synth_depth, synth_pose)
+                    pose_seeds_csfd, pose_seeds_dcsfd, savePose, se3_exp, se3_generators, synth_depth, synth_pose)

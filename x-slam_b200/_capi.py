@@ -107,8 +107,19 @@ SYMBOLS = {
     "xs_kinfu_get_algorithmic_bytes": (_i, [_vp, _pd]),
     "xs_kinfu_pose_record_device": (_vp, [_vp]),
     "xs_kinfu_stream": (_vp, [_vp]),
+    "xs_se3_exp": (_i, [_pf, _i, _i, _i, _pi, _pf]),
     "xs_kinfu_set_world2camera": (_i, [_vp, _pf]),
     "xs_kinfu_set_gt_poses": (_i, [_vp, _pf, _i, _i]),
+    "xs_set_device": (_i, [_i]),
+    "xs_comm_unique_id": (_i, [C.c_char_p]),
+    "xs_comm_create": (_vp, [_i, _i, C.c_char_p]),
+    "xs_comm_destroy": (None, [_vp]),
+    "xs_comm_rank": (_i, [_vp]),
+    "xs_comm_world": (_i, [_vp]),
+    "xs_comm_all_gather": (_i, [_vp, _vp, _vp, _l, _vp]),
+    "xs_kinfu_set_comm": (_i, [_vp, _vp, _i]),
+    "xs_kinfu_get_gathered_records": (_i, [_vp, _pf]),
+    "xs_kinfu_gathered_records_device": (_vp, [_vp]),
     "xs_save_pose_txt": (_i, [C.c_char_p, _pf]),
     "xs_export_ply": (_i, [C.c_char_p, _pf, _pf, _l]),
     "xs_synth_depth": (_i, [_pf, Intr, _i, _i, C.POINTER(C.c_uint16)]),

@@ -138,6 +138,10 @@ inline HJet hj_apply(const HJet &a, float f0, float f1, float f2) {
     }
     return r;
 }
+inline HJet hj_sqrt(const HJet &a) {
+    const float s = std::sqrt(a.v);
+    return hj_apply(a, s, 0.5f / s, -0.25f / (s * a.v));
+}
 inline HJet hj_sin(const HJet &a) { return hj_apply(a, std::sin(a.v), std::cos(a.v), -std::sin(a.v)); }
 inline HJet hj_cos(const HJet &a) { return hj_apply(a, std::cos(a.v), -std::sin(a.v), -std::cos(a.v)); }
 

@@ -32,6 +32,7 @@
 #include "xs_common.cuh"
 
 #include <utility>
+#include <vector>
 
 namespace xs {
 
@@ -100,6 +101,7 @@ struct IcpParams {
     int max_writers;             // upper bound of the CTAs that write a partial for one group
     BatchView batch;             // Hessian batch (kind 2): a group is one task = parameter i (component i) or pair k (component n + k)
     unsigned int *done_ticket;   // kind 2: tasks whose sums are complete (self-resetting); the CTA that completes the last one solves
+    const struct HTask *htasks;  // kind 2: [groups] task table (device)
 };
 
 // the Gauss-Newton step that closes an iteration (icp_solve_direction below)
@@ -120,7 +122,8 @@ constexpr int REAL_CACHE = 48;
 template <int C> __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, const double *real_sums,
                                                                   const double *comp_sums);
 __device__ __noinline__ void icp_solve_hessian_first(const SolveParams &P, int i, const double *real_sums, double *x_out);
-__device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n, int k, int2 pr, const double *real_sums, const double *x_first);
+__device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n, int k, int2 pr, const double *real_sums, const double *x_first,
+                                                    bool reduced);
 
 // search_newton (ICP.cu:196-244) on real parts with the reference's rounding sequence: projection of the current
 // vertex into the previous frame, bounds / NaN / distance / angle gates.  Outputs vcurr, vcurr_g and the matched pixel.
@@ -170,7 +173,9 @@ XS_DEV bool search_newton_real(const IcpParams &P, const float *s_curr, int x, i
 
 // ---------------------------------------------------------------------------------------------------------------
 // pass 1: association + real normal equations
-__global__ void __launch_bounds__(256) icp_assoc_kernel(const IcpParams P) {
+// SR.pose_out != null: the last block also runs the real Gauss-Newton step of the iteration (one thread, from shared memory)
+// instead of a separate one-thread launch - one launch and one kernel-to-kernel dependency less per iteration.
+__global__ void __launch_bounds__(256) icp_assoc_kernel(const IcpParams P, const SolveParams SR) {
     __shared__ double s_acc[27];
     __shared__ double s_stage[8][32];
     const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -255,8 +260,12 @@ __global__ void __launch_bounds__(256) icp_assoc_kernel(const IcpParams P) {
 #pragma unroll
         for (int w = 0; w < 8; ++w) sum += s_stage[w][tid];
         P.sums[tid] = sum;
+        s_acc[tid] = sum;
     }
     if (tid == 0) *P.ticket = 0u;
+    if (SR.pose_out == nullptr) return;
+    __syncthreads();
+    if (tid == 0) icp_solve_direction<1>(SR, 0, s_acc, s_acc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -307,6 +316,17 @@ XS_DEV unsigned long long l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+XS_DEV void cp_async4_keep(float *smem_dst, const float *gsrc, unsigned long long policy) {
+    const unsigned sdst = (unsigned) __cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(sdst), "l"(gsrc), "l"(policy) : "memory");
+}
+XS_DEV unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// pulls the line of a streamed plane into L2 several pixels ahead of its cp.async (no register, no shared memory)
+XS_DEV void prefetch_l2(const float *g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
 XS_DEV void cp_async16(float4 *smem_dst, const float4 *gsrc) {
     const unsigned sdst = (unsigned) __cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
@@ -613,7 +633,7 @@ struct Chol6 {
     double L[6][6];
     double inv[6];
 };
-XS_DEV void chol6_factor(const double (&A)[6][6], Chol6 &F) {
+XS_DEV bool chol6_factor(const double (&A)[6][6], Chol6 &F) {  // false: a pivot was not positive (the factor is partial, as Eigen's)
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -640,6 +660,7 @@ XS_DEV void chol6_factor(const double (&A)[6][6], Chol6 &F) {
             }
         }
     }
+    return ok;
 }
 XS_DEV void chol6_solve(const Chol6 &F, const double (&b)[6], double (&x)[6]) {
     double y[6];
@@ -717,8 +738,16 @@ XS_DEV void matvec6_dev(const double (&A)[6][6], const double (&x)[6], double (&
 
 // sin / cos of a batched angle; the real part is evaluated in double and rounded (matches the host's correctly
 // rounded sinf / cosf), derivative components by the chain rule
-template <int C> XS_DEV void jsincos(const Jet<C, 1> &a, Jet<C, 1> &sn, Jet<C, 1> &cs) {
-    const float s0 = (float) sin((double) a.v), c0 = (float) cos((double) a.v);
+// coef_only: the real parts are only coefficients of the derivative formulas (a derivative tail under split chains never
+// writes a real part), so single-precision sincosf replaces the two double-precision evaluations
+template <int C> XS_DEV void jsincos(const Jet<C, 1> &a, Jet<C, 1> &sn, Jet<C, 1> &cs, bool coef_only = false) {
+    float s0, c0;
+    if (coef_only) {
+        sincosf(a.v, &s0, &c0);
+    } else {
+        s0 = (float) sin((double) a.v);
+        c0 = (float) cos((double) a.v);
+    }
     sn.v = s0;
     cs.v = c0;
     sn.d[0] = c0 * a.d[0];
@@ -734,9 +763,9 @@ template <int C> struct JMat3 {
     Jet<C, 1> m[3][3];
 };
 // rotation about a coordinate axis: Eigen AngleAxis::toRotationMatrix() specialised to a unit axis (host_jet.h)
-template <int C> XS_DEV JMat3<C> jaxis_rotation(const Jet<C, 1> &angle, int axis) {
+template <int C> XS_DEV JMat3<C> jaxis_rotation(const Jet<C, 1> &angle, int axis, bool coef_only = false) {
     Jet<C, 1> sn, cs;
-    jsincos<C>(angle, sn, cs);
+    jsincos<C>(angle, sn, cs, coef_only);
     JMat3<C> R;
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) R.m[i][j] = jconst<C, 1>(0.f);
@@ -792,14 +821,20 @@ __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, co
             xr[i] = __ldcg(rc + 42 + i);
         }
     } else {
-        const double det = det6_dev(A);
+        // A.real().determinant() guard (KinectFusionReconstruction.cpp:203-210).  For a positive definite A the determinant is
+        // the squared product of the Cholesky pivots, which the solve needs anyway; only when the factorisation meets a
+        // non-positive pivot (or NaN) is the determinant taken by elimination.
+        const bool spd = chol6_factor(A, F);
+        double det = 1.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) det *= F.L[i][i] * F.L[i][i];
+        if (!spd || !isfinite(det)) det = det6_dev(A);
         if (fabs(det) < 1e-15 || isnan(det)) {
             // every thread of every block computes the same det and takes this branch; the flag is only read at kernel
             // entry by later launches
             if (owns_real) P.status[1] = isnan(det) ? 2 : 1;
             return;
         }
-        chol6_factor(A, F);
         chol6_solve(F, b, xr);  // zero-seed solve: the canonical real part
         if (owns_real && P.real_cache) {
 #pragma unroll
@@ -874,7 +909,8 @@ __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, co
         for (int a = 0; a < C; ++a) tcurr[i].d[a] = has_dir ? pr[(size_t) (1 + q * C + a) * 12 + 9 + i] : 0.f;
     }
     // Rinc = Rz(gamma) * Ry(beta) * Rx(alpha)
-    const JMat3<C> Rinc = jmatmul(jmatmul(jaxis_rotation<C>(x[2], 2), jaxis_rotation<C>(x[1], 1)), jaxis_rotation<C>(x[0], 0));
+    const bool co = P.deriv_only != 0;
+    const JMat3<C> Rinc = jmatmul(jmatmul(jaxis_rotation<C>(x[2], 2, co), jaxis_rotation<C>(x[1], 1, co)), jaxis_rotation<C>(x[0], 0, co));
     J tn[3];
     for (int i = 0; i < 3; ++i) {
         J sacc = Rinc.m[i][0] * tcurr[0];
@@ -913,89 +949,165 @@ template <int C> __global__ void __launch_bounds__(32) icp_solve_kernel(const So
 // Work decomposition, staging, flush and per-task partial reduction are those of icp_deriv_kernel; the CTA that completes the
 // LAST task's sums (done_ticket) runs the Gauss-Newton step of every component: first-order solves first (their solutions
 // are needed by the pairs), then the pairs.
-constexpr size_t deriv_h_smem(int stages) { return (size_t) stages * DERIV_IN * 256 * sizeof(float) + 256 * sizeof(double); }
+// A task of the Hessian-batch derivative pass: either one parameter (first-order sums of component i) or up to HPMAX pairs
+// that share their first parameter i, (i, j_0) .. (i, j_np-1) with second-order components s_0 .. s_np-1.  The pairs of a task
+// share the association record and the gathers of F_i - the derivative pass is bound by L2 -> SM traffic and instruction
+// issue, not by HBM (profiles/r02_ncu_summary.md).
+//
+// Two forms of the pair sums:
+//   FULL     the 27 second-order sums A_ij, b_ij of every pair (what the ICP log and the seam-level estimateCombined return);
+//   REDUCED  under split chains the real solution x of the iteration is known before the derivative pass (the real step ran
+//            ahead), and the Gauss-Newton step needs A_ij, b_ij only through g_ij = b_ij - A_ij x.  With rho = row_6 - sum_j
+//            row_j x_j (the linearised residual after the step) and its first / second-order parts,
+//              g_ij = sum_pixels [ S(row) rho + row S(rho) + F_i(row) F_j(rho) + F_j(row) F_i(rho) ]   (6 values)
+//            i.e. 6 instead of 27 accumulators and 52 instead of 108 FMAs per pixel and pair, and three pairs per task.
+constexpr int HPMAX = 3;
+struct HTask {
+    int i;          // parameter: first-order component i
+    int np;         // 0: first-order task (sums of component i); 1..HPMAX: pair task
+    int j[HPMAX];   // second parameters
+    int s[HPMAX];   // second-order component indices (n + pair index)
+};
+__host__ __device__ constexpr int deriv_h_in(int hp) { return 12 + 6 + hp * 12; }  // staged floats per pixel: record (3 float4) | F_i (dn, dv) | per pair F_j, S
+constexpr size_t deriv_h_smem(int stages, int hp, bool reduced) {
+    return (size_t) stages * deriv_h_in(hp) * 256 * sizeof(float) + (reduced ? 1 : hp) * 256 * sizeof(double);
+}
 
 template <int... E>
-XS_DEV void accumulate_first(float (&acc)[27], const float (&r)[7], const float (&d0)[7], std::integer_sequence<int, E...>) {
+XS_DEV void accumulate_first(float *acc, const float (&r)[7], const float (&d0)[7], std::integer_sequence<int, E...>) {
     ((acc[E] = fmaf(r[tri_i(E)], d0[tri_j(E)], fmaf(d0[tri_i(E)], r[tri_j(E)], acc[E]))), ...);
 }
 template <int... E>
-XS_DEV void accumulate_pair(float (&acc)[27], const float (&r)[7], const float (&d0)[7], const float (&d1)[7], const float (&d2)[7],
+XS_DEV void accumulate_pair(float *acc, const float (&r)[7], const float (&d0)[7], const float (&d1)[7], const float (&d2)[7],
                             std::integer_sequence<int, E...>) {
     ((acc[E] = fmaf(r[tri_i(E)], d2[tri_j(E)],
                     fmaf(d2[tri_i(E)], r[tri_j(E)], fmaf(d0[tri_i(E)], d1[tri_j(E)], fmaf(d1[tri_i(E)], d0[tri_j(E)], acc[E]))))),
      ...);
 }
+// rho-type contraction of a row (or of a row's derivative) with the solution: v_6 - sum_j v_j x_j
+XS_DEV float rho_of(const float (&v)[7], const float (&x)[6]) {
+    return v[6] - fmaf(v[0], x[0], fmaf(v[1], x[1], fmaf(v[2], x[2], fmaf(v[3], x[3], fmaf(v[4], x[4], v[5] * x[5])))));
+}
+// derivative of the row [s x n, n, n . e] for one component: ds = dpose * vc + dt, (dn, dv) gathered at the matched pixel
+XS_DEV void row_first(const float4 *mm4, const float (&vc)[3], const float (&sv)[3], const float (&nv)[3], const float (&ev)[3],
+                      const float (&dn)[3], const float (&dv)[3], float (&ds)[3], float (&de)[3], float (&d)[7]) {
+    const float4 m0 = mm4[0], m1 = mm4[1], m2 = mm4[2];  // R row-major (9), t (3): broadcast 128-bit shared loads
+    ds[0] = fmaf(m0.x, vc[0], fmaf(m0.y, vc[1], fmaf(m0.z, vc[2], m2.y)));
+    ds[1] = fmaf(m0.w, vc[0], fmaf(m1.x, vc[1], fmaf(m1.y, vc[2], m2.z)));
+    ds[2] = fmaf(m1.z, vc[0], fmaf(m1.w, vc[1], fmaf(m2.x, vc[2], m2.w)));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) de[c] = dv[c] - ds[c];
+    cross3(ds, nv, d);  // d(s x n) = ds x n + s x dn
+    cross3_add(sv, dn, d);
+    d[3] = dn[0];
+    d[4] = dn[1];
+    d[5] = dn[2];
+    d[6] = dot3(dn, ev) + dot3(nv, de);  // d(n . (d - s))
+}
 
-template <int ST> __global__ void __launch_bounds__(256, 3) icp_deriv_h_kernel(const IcpParams P, const SolveParams S) {
+template <int ST, int MINB, int HPK, bool REDUCED>
+__global__ void __launch_bounds__(256, MINB) icp_deriv_h_kernel(const IcpParams P, const SolveParams S) {
+    constexpr int IN = deriv_h_in(HPK);
+    constexpr int NACC = REDUCED ? (HPK * 6 > 27 ? HPK * 6 : 27) : HPK * 27;  // accumulators per thread
+    constexpr int NPART = REDUCED ? 27 : HPK * 27;                             // values of a (task, writer) partial
     extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ float s_pose[3][12];
+    __shared__ float4 s_pose[1 + 2 * HPK][3];  // F_i | F_j0, S_0 | F_j1, S_1 | ...
+    __shared__ float s_x[6];
     __shared__ bool s_last, s_final;
-    float *s_in = reinterpret_cast<float *>(s_raw);  // [stage][DERIV_IN][256]
-    double *s_tot = reinterpret_cast<double *>(s_raw + (size_t) ST * DERIV_IN * 256 * sizeof(float));  // [256]
+    float *s_in = reinterpret_cast<float *>(s_raw);  // [stage][IN][256]
+    double *s_tot = reinterpret_cast<double *>(s_raw + (size_t) ST * IN * 256 * sizeof(float));  // [REDUCED ? 1 : HPK][256]
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const size_t plane = (size_t) P.rows * P.cols;
+    const unsigned uplane = (unsigned) plane;
     const int npix = P.rows * P.cols;
-    const int n = P.batch.n, ntasks = P.batch.n + P.batch.m;
-    const unsigned long long stream_policy = l2_policy_evict_first();
+    const int ntasks = P.groups;
+    const unsigned long long stream_policy = l2_policy_evict_first(), keep_policy = l2_policy_evict_last();
+    constexpr int R = ST + 2;  // matched indices kept ahead in registers (they come from L2)
     const long long U = (long long) P.groups * P.chunks, B = gridDim.x;
     const long long u_begin = blockIdx.x * U / B, u_end = (blockIdx.x + 1) * U / B;
+    if (REDUCED && tid < 6) s_x[tid] = (float) __ldcg(S.real_cache + 42 + tid);  // real solution of this iteration (the real step has completed)
     bool final_cta = false;
     for (long long u = u_begin; u < u_end;) {
         const int task = (int) (u / P.chunks), c_begin = (int) (u % P.chunks);
         const int c_end = (int) min((long long) P.chunks, c_begin + (u_end - u));
         u += c_end - c_begin;
-        const bool pair = task >= n;
-        int comp3[3] = {task, task, task};  // components whose planes / pose derivatives the task reads: F_i | F_i, F_j, S_k
-        if (pair) {
-            const int2 pr = __ldg(P.batch.pairs + (task - n));
-            comp3[0] = pr.x, comp3[1] = pr.y;
-        }
-        const int nslots = pair ? 3 : 1;
+        const HTask T = P.htasks[task];
+        const int np = T.np, ci = T.i;
+        // component of every gather slot as scalars (an indexed array would live in local memory)
+        int cj[HPK], cs[HPK];
+#pragma unroll
+        for (int h = 0; h < HPK; ++h) cj[h] = T.j[h], cs[h] = T.s[h];
         __syncthreads();  // s_pose / s_tot of the previous segment are no longer read
-        if (tid < 36) {
+        if (tid < 12 * (1 + 2 * HPK)) {
             const int a = tid / 12, e = tid % 12;
-            s_pose[a][e] = P.pose_curr[(size_t) (1 + comp3[a]) * 12 + e];
+            int ca = ci;
+#pragma unroll
+            for (int h = 0; h < HPK; ++h) {
+                if (a == 1 + 2 * h) ca = cj[h];
+                if (a == 2 + 2 * h) ca = cs[h];
+            }
+            reinterpret_cast<float *>(&s_pose[a][0])[e] = P.pose_curr[(size_t) (1 + ca) * 12 + e];
         }
-        s_tot[tid] = 0.0;
+#pragma unroll
+        for (int h = 0; h < (REDUCED ? 1 : HPK); ++h) s_tot[h * 256 + tid] = 0.0;
         __syncthreads();
-        float acc[27];
+        float x[6];
 #pragma unroll
-        for (int e = 0; e < 27; ++e) acc[e] = 0.f;
+        for (int e = 0; e < 6; ++e) x[e] = REDUCED ? s_x[e] : 0.f;
+        float acc[NACC];
+#pragma unroll
+        for (int e = 0; e < NACC; ++e) acc[e] = 0.f;
         auto flush = [&]() {
-            float v[32];
+            if (REDUCED) {  // first-order task: 27 sums; pair task: HPK x 6 values, one transpose-reduce either way
+                float v[32];
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = e < 27 ? acc[e] : 0.f;
-            s_tot[tid] += (double) warp_transpose_reduce_f(v);
+                for (int e = 0; e < 32; ++e) v[e] = e < NACC ? acc[e] : 0.f;
+                s_tot[tid] += (double) warp_transpose_reduce_f(v);
 #pragma unroll
-            for (int e = 0; e < 27; ++e) acc[e] = 0.f;
+                for (int e = 0; e < NACC; ++e) acc[e] = 0.f;
+            } else {
+#pragma unroll
+                for (int h = 0; h < HPK; ++h) {
+                    if (h == 0 || np > h) {  // block-uniform
+                        float v[32];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = e < 27 ? acc[h * 27 + e] : 0.f;
+                        s_tot[h * 256 + tid] += (double) warp_transpose_reduce_f(v);
+#pragma unroll
+                        for (int e = 0; e < 27; ++e) acc[h * 27 + e] = 0.f;
+                    }
+                }
+            }
         };
         const int base = c_begin * 256 * P.ppt;
         const int nitems = (c_end - c_begin) * P.ppt;
+        auto gather = [&](float *dst, int slot, int comp, unsigned q, bool stream) {
+            const unsigned o = q + (unsigned) (1 + comp) * 3u * uplane;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (stream) {  // the task's own second-order planes are read once: evict-first keeps the re-read planes in L2
+                    cp_async4_stream(dst + (12 + slot * 6 + c) * 256, P.nmap_prev + (o + c * uplane), stream_policy);
+                    cp_async4_stream(dst + (12 + slot * 6 + 3 + c) * 256, P.vmap_prev + (o + c * uplane), stream_policy);
+                } else {
+                    cp_async4_keep(dst + (12 + slot * 6 + c) * 256, P.nmap_prev + (o + c * uplane), keep_policy);
+                    cp_async4_keep(dst + (12 + slot * 6 + 3 + c) * 256, P.vmap_prev + (o + c * uplane), keep_policy);
+                }
+            }
+        };
         auto issue = [&](int stage, int p, int q) {
             if (q >= 0) {
-                float *dst = s_in + (size_t) stage * DERIV_IN * 256 + tid;
-                float4 *dst4 = reinterpret_cast<float4 *>(s_in + (size_t) stage * DERIV_IN * 256) + tid;  // [4][256] float4
-                const float4 *f = P.rec_f + (size_t) p * 4;
+                float *dst = s_in + (size_t) stage * IN * 256 + tid;
+                float4 *dst4 = reinterpret_cast<float4 *>(s_in + (size_t) stage * IN * 256) + tid;  // [3][256] float4
+                const float4 *f = P.rec_f + (size_t) p * 4;  // (vc, s.x) (s.yz, n.xy) (n.z, e): the fourth (s x n, n . e) is recomputed
 #pragma unroll
-                for (int i = 0; i < 4; ++i) cp_async16(dst4 + i * 256, f + i);
-                const unsigned uplane = (unsigned) plane;
+                for (int i = 0; i < 3; ++i) cp_async16(dst4 + i * 256, f + i);
+                gather(dst, 0, ci, (unsigned) q, np == 0);
 #pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    if (a < nslots) {  // block-uniform
-                        const unsigned o = (unsigned) q + (unsigned) (1 + comp3[a]) * 3u * uplane;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            // first-order planes are re-read by every pair they occur in (L2-resident); second-order planes are streamed once
-                            if (a == 2) {
-                                cp_async4_stream(dst + (REC_F + a * 6 + c) * 256, P.nmap_prev + (o + c * uplane), stream_policy);
-                                cp_async4_stream(dst + (REC_F + a * 6 + 3 + c) * 256, P.vmap_prev + (o + c * uplane), stream_policy);
-                            } else {
-                                cp_async4(dst + (REC_F + a * 6 + c) * 256, P.nmap_prev + (o + c * uplane));
-                                cp_async4(dst + (REC_F + a * 6 + 3 + c) * 256, P.vmap_prev + (o + c * uplane));
-                            }
-                        }
+                for (int h = 0; h < HPK; ++h) {
+                    if (h < np) {  // block-uniform
+                        gather(dst, 1 + 2 * h, cj[h], (unsigned) q, false);
+                        gather(dst, 2 + 2 * h, cs[h], (unsigned) q, true);
                     }
                 }
             }
@@ -1005,9 +1117,9 @@ template <int ST> __global__ void __launch_bounds__(256, 3) icp_deriv_h_kernel(c
             const int p = base + j * 256 + tid;
             return (j < nitems && p < npix) ? P.rec_idx[p] : -1;
         };
-        int qs[ST];
+        int qs[R];
 #pragma unroll
-        for (int i = 0; i < ST; ++i) qs[i] = idx_at(i);
+        for (int i = 0; i < R; ++i) qs[i] = idx_at(i);
 #pragma unroll
         for (int i = 0; i < ST - 1; ++i) issue(i, base + i * 256 + tid, qs[i]);
         int st = 0;
@@ -1018,48 +1130,58 @@ template <int ST> __global__ void __launch_bounds__(256, 3) icp_deriv_h_kernel(c
             issue(st_in, p + (ST - 1) * 256, qs[ST - 1]);
             const int q = qs[0];
 #pragma unroll
-            for (int i = 0; i < ST - 1; ++i) qs[i] = qs[i + 1];
-            qs[ST - 1] = idx_at(j + ST);
+            for (int i = 0; i < R - 1; ++i) qs[i] = qs[i + 1];
+            qs[R - 1] = idx_at(j + R);
             const int cur = st;
             st = (st + 1 == ST) ? 0 : st + 1;
             cp_async_wait<ST - 1>();
             if (q >= 0) {
-                const float *in = s_in + (size_t) cur * DERIV_IN * 256 + tid;
-                const float4 *in4 = reinterpret_cast<const float4 *>(s_in + (size_t) cur * DERIV_IN * 256) + tid;
-                const float4 f0 = in4[0], f1 = in4[256], f2 = in4[512], f3 = in4[768];
+                const float *in = s_in + (size_t) cur * IN * 256 + tid;
+                const float4 *in4 = reinterpret_cast<const float4 *>(s_in + (size_t) cur * IN * 256) + tid;
+                const float4 f0 = in4[0], f1 = in4[256], f2 = in4[512];
                 const float vc[3] = {f0.x, f0.y, f0.z};
                 const float sv[3] = {f0.w, f1.x, f1.y};
                 const float nv[3] = {f1.z, f1.w, f2.x};
                 const float ev[3] = {f2.y, f2.z, f2.w};
-                const float r[7] = {f3.x, f3.y, f3.z, nv[0], nv[1], nv[2], f3.w};
-                float ds[3][3], dn[3][3], de[3][3], d[3][7];
+                float r[7];
+                cross3(sv, nv, r);
+                r[3] = nv[0], r[4] = nv[1], r[5] = nv[2];
+                r[6] = dot3(nv, ev);
+                auto load6 = [&](int slot, float (&dn)[3], float (&dv)[3]) {
 #pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    if (a < nslots) {
-                        const float *mm = s_pose[a];
-                        ds[a][0] = fmaf(mm[0], vc[0], fmaf(mm[1], vc[1], fmaf(mm[2], vc[2], mm[9])));
-                        ds[a][1] = fmaf(mm[3], vc[0], fmaf(mm[4], vc[1], fmaf(mm[5], vc[2], mm[10])));
-                        ds[a][2] = fmaf(mm[6], vc[0], fmaf(mm[7], vc[1], fmaf(mm[8], vc[2], mm[11])));
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            dn[a][c] = in[(REC_F + a * 6 + c) * 256];
-                            de[a][c] = in[(REC_F + a * 6 + 3 + c) * 256] - ds[a][c];
-                        }
-                        cross3(ds[a], nv, d[a]);  // d(s x n) = ds x n + s x dn
-                        cross3_add(sv, dn[a], d[a]);
-                        d[a][3] = dn[a][0];
-                        d[a][4] = dn[a][1];
-                        d[a][5] = dn[a][2];
-                        d[a][6] = dot3(dn[a], ev) + dot3(nv, de[a]);  // d(n . (d - s))
+                    for (int c = 0; c < 3; ++c) {
+                        dn[c] = in[(12 + slot * 6 + c) * 256];
+                        dv[c] = in[(12 + slot * 6 + 3 + c) * 256];
                     }
-                }
-                if (pair) {
-                    cross3_add(ds[0], dn[1], d[2]);  // second-order cross terms of the row
-                    cross3_add(ds[1], dn[0], d[2]);
-                    d[2][6] += dot3(dn[0], de[1]) + dot3(dn[1], de[0]);
-                    accumulate_pair(acc, r, d[0], d[1], d[2], std::make_integer_sequence<int, 27>());
+                };
+                float dn0[3], dv0[3], ds0[3], de0[3], d0[7];
+                load6(0, dn0, dv0);
+                row_first(s_pose[0], vc, sv, nv, ev, dn0, dv0, ds0, de0, d0);
+                if (np == 0) {
+                    accumulate_first(acc, r, d0, std::make_integer_sequence<int, 27>());
                 } else {
-                    accumulate_first(acc, r, d[0], std::make_integer_sequence<int, 27>());
+                    const float rho = REDUCED ? rho_of(r, x) : 0.f, rho0 = REDUCED ? rho_of(d0, x) : 0.f;
+#pragma unroll
+                    for (int h = 0; h < HPK; ++h) {
+                        if (h < np) {  // block-uniform
+                            float dn1[3], dv1[3], ds1[3], de1[3], d1[7], dn2[3], dv2[3], ds2[3], de2[3], d2[7];
+                            load6(1 + 2 * h, dn1, dv1);
+                            row_first(s_pose[1 + 2 * h], vc, sv, nv, ev, dn1, dv1, ds1, de1, d1);
+                            load6(2 + 2 * h, dn2, dv2);
+                            row_first(s_pose[2 + 2 * h], vc, sv, nv, ev, dn2, dv2, ds2, de2, d2);
+                            cross3_add(ds0, dn1, d2);  // second-order cross terms of the row
+                            cross3_add(ds1, dn0, d2);
+                            d2[6] += dot3(dn0, de1) + dot3(dn1, de0);
+                            if (REDUCED) {
+                                const float rho1 = rho_of(d1, x), rho2 = rho_of(d2, x);
+#pragma unroll
+                                for (int c = 0; c < 6; ++c)
+                                    acc[h * 6 + c] = fmaf(d2[c], rho, fmaf(r[c], rho2, fmaf(d0[c], rho1, fmaf(d1[c], rho0, acc[h * 6 + c]))));
+                            } else {
+                                accumulate_pair(acc + h * 27, r, d0, d1, d2, std::make_integer_sequence<int, 27>());
+                            }
+                        }
+                    }
                 }
             }
             if ((j & 31) == 31) flush();
@@ -1067,14 +1189,15 @@ template <int ST> __global__ void __launch_bounds__(256, 3) icp_deriv_h_kernel(c
         if (nitems & 31) flush();
         cp_async_wait<0>();
         __syncthreads();
-        // ---------------- the 8 warps in order -> one 27-value partial of this CTA for this task
+        // ---------------- the 8 warps in order -> one NPART-value partial of this CTA for this task
         const int first_b = deriv_owner((long long) task * P.chunks, U, B);
         const int writers = deriv_owner((long long) (task + 1) * P.chunks - 1, U, B) - first_b + 1;
-        double *part = P.dpartials + ((size_t) task * P.max_writers + (blockIdx.x - first_b)) * 27;
-        if (tid < 27) {
+        double *part = P.dpartials + ((size_t) task * P.max_writers + (blockIdx.x - first_b)) * NPART;
+        if (tid < NPART) {
+            const int h = REDUCED ? 0 : tid / 27, e = REDUCED ? tid : tid % 27;
             double sum = 0.0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) sum += s_tot[w * 32 + tid];
+            for (int w = 0; w < 8; ++w) sum += s_tot[h * 256 + w * 32 + e];
             part[tid] = sum;
         }
         __threadfence();
@@ -1083,20 +1206,39 @@ template <int ST> __global__ void __launch_bounds__(256, 3) icp_deriv_h_kernel(c
         __syncthreads();
         if (!s_last) continue;
         __threadfence();
-        // the last writer of the task adds the partials in CTA order (lane = product)
-        if (warp == 0) {
+        // the last writer of the task adds the partials in CTA order and files them under the components they belong to:
+        // 27 sums per component (first-order tasks, FULL pairs), or the 6 values of g_ij in the first 6 slots (REDUCED pairs)
+        if (tid < NPART) {
             double sum = 0.0;
-            if (lane < 27) {
-                const double *src = P.dpartials + (size_t) task * P.max_writers * 27 + lane;
-                for (int w = 0; w < writers; ++w) sum += __ldcg(src + (size_t) w * 27);
-                P.sums[(size_t) (1 + task) * 27 + lane] = sum;
+            const double *src = P.dpartials + (size_t) task * P.max_writers * NPART + tid;
+            for (int w = 0; w < writers; ++w) sum += __ldcg(src + (size_t) w * NPART);
+            if (np == 0) {
+                if (tid < 27) P.sums[(size_t) (1 + ci) * 27 + tid] = sum;
+            } else if (REDUCED) {
+                const int h = tid / 6;
+                if (h < np) {
+                    int comp = cs[0];
+#pragma unroll
+                    for (int hh = 1; hh < HPK; ++hh)
+                        if (h == hh) comp = cs[hh];
+                    P.sums[(size_t) (1 + comp) * 27 + tid % 6] = sum;
+                }
+            } else {
+                const int h = tid / 27;
+                if (h < np) {
+                    int comp = cs[0];
+#pragma unroll
+                    for (int hh = 1; hh < HPK; ++hh)
+                        if (h == hh) comp = cs[hh];
+                    P.sums[(size_t) (1 + comp) * 27 + tid % 27] = sum;
+                }
             }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                P.group_ticket[task] = 0u;
-                s_final = atomicAdd(P.done_ticket, 1u) == (unsigned) ntasks - 1u;
-            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            P.group_ticket[task] = 0u;
+            s_final = atomicAdd(P.done_ticket, 1u) == (unsigned) ntasks - 1u;
         }
         __syncthreads();
         final_cta = final_cta || s_final;
@@ -1107,15 +1249,16 @@ template <int ST> __global__ void __launch_bounds__(256, 3) icp_deriv_h_kernel(c
     __threadfence();
     if (tid == 0) *P.done_ticket = 0u;
     if (!S.pose_out) return;
+    const int n = P.batch.n, ncomp = P.batch.n + P.batch.m;
     double *s_real = reinterpret_cast<double *>(s_raw);  // [27]; the staging area is idle here
     double *s_x1 = s_real + 32;                          // [n][6] first-order solutions
     if (tid < 27) s_real[tid] = __ldcg(P.sums + tid);    // real sums of icp_assoc_kernel (previous launch)
     __syncthreads();
     if (S.log)
-        for (int i = tid; i < 27 * (1 + ntasks); i += 256) S.log[i] = __ldcg(P.sums + i);
+        for (int i = tid; i < 27 * (1 + ncomp); i += 256) S.log[i] = __ldcg(P.sums + i);
     for (int i = tid; i < n; i += 256) icp_solve_hessian_first(S, i, s_real, s_x1 + 6 * i);
     __syncthreads();
-    for (int k = tid; k < P.batch.m; k += 256) icp_solve_hessian_pair(S, n, k, __ldg(P.batch.pairs + k), s_real, s_x1);
+    for (int k = tid; k < P.batch.m; k += 256) icp_solve_hessian_pair(S, n, k, __ldg(P.batch.pairs + k), s_real, s_x1, REDUCED);
 }
 
 // ---- Gauss-Newton step of a Hessian batch (kind 2), one thread per component.
@@ -1166,7 +1309,8 @@ XS_DEV void gn_pose_update(const SolveParams &P, const int (&comp)[C], const Jet
         tcurr[i].v = pr[9 + i];
         for (int a = 0; a < C; ++a) tcurr[i].d[a] = pr[(size_t) (1 + comp[a]) * 12 + 9 + i];
     }
-    const JMat3<C> Rinc = jmatmul(jmatmul(jaxis_rotation<C>(x[2], 2), jaxis_rotation<C>(x[1], 1)), jaxis_rotation<C>(x[0], 0));
+    const bool co = P.deriv_only != 0;
+    const JMat3<C> Rinc = jmatmul(jmatmul(jaxis_rotation<C>(x[2], 2, co), jaxis_rotation<C>(x[1], 1, co)), jaxis_rotation<C>(x[0], 0, co));
     J tn[3];
     for (int i = 0; i < 3; ++i) {
         J sacc = Rinc.m[i][0] * tcurr[0];
@@ -1220,15 +1364,21 @@ __device__ __noinline__ void icp_solve_hessian_first(const SolveParams &P, int i
 
 // pair k = (i, j): x_ij = A^-1 (b_ij - A_ij x - A_i x_j - A_j x_i); the pose update runs in the bicomplex algebra on
 // (F_i, F_j, S_ij) and stores S_ij only
-__device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n, int k, int2 pr, const double *real_sums, const double *x_first) {
+// (reduced: the derivative pass has already formed g_ij = b_ij - A_ij x, the first 6 values filed under the component)
+__device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n, int k, int2 pr, const double *real_sums, const double *x_first,
+                                                    bool reduced) {
     double A[6][6], b[6], xr[6];
     Chol6 F;
     if (!gn_real_prelude(P, real_sums, false, A, b, F, xr)) return;
     double M[6][6], v[6], sums[27], rhs[6], t[6], xs[6];
-    for (int e = 0; e < 27; ++e) sums[e] = __ldcg(P.sums + (size_t) (1 + n + k) * 27 + e);
-    unpack_sums(sums, M, v);  // A_ij, b_ij
-    matvec6_dev(M, xr, t);
-    for (int e = 0; e < 6; ++e) rhs[e] = v[e] - t[e];
+    if (reduced) {
+        for (int e = 0; e < 6; ++e) rhs[e] = __ldcg(P.sums + (size_t) (1 + n + k) * 27 + e);
+    } else {
+        for (int e = 0; e < 27; ++e) sums[e] = __ldcg(P.sums + (size_t) (1 + n + k) * 27 + e);
+        unpack_sums(sums, M, v);  // A_ij, b_ij
+        matvec6_dev(M, xr, t);
+        for (int e = 0; e < 6; ++e) rhs[e] = v[e] - t[e];
+    }
     double xi[6], xj[6];
     for (int e = 0; e < 6; ++e) xi[e] = x_first[6 * pr.x + e], xj[e] = x_first[6 * pr.y + e];
     for (int e = 0; e < 27; ++e) sums[e] = __ldcg(P.sums + (size_t) (1 + pr.x) * 27 + e);
@@ -1256,6 +1406,9 @@ __device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n,
 struct IcpScratch {
     double *d_partials = nullptr, *d_sums = nullptr, *h_sums = nullptr, *d_dpartials = nullptr;
     unsigned int *d_ticket = nullptr, *d_group_ticket = nullptr, *d_done_ticket = nullptr;
+    struct HTask *d_htasks = nullptr;  // Hessian batch: task table of the derivative pass, built once per pair list
+    const void *htasks_key = nullptr;
+    int n_htasks = 0, htasks_hp = 0;
     int cap_groups = 0;
     float *d_pose = nullptr, *h_pose = nullptr;  // seam-level entry point only: [(1+ncomp)][12]
     int *d_rec_idx = nullptr;
@@ -1294,6 +1447,7 @@ void icp_scratch_destroy(IcpScratch *sc) {
     cudaFree(sc->d_ticket);
     cudaFree(sc->d_group_ticket);
     cudaFree(sc->d_done_ticket);
+    cudaFree(sc->d_htasks);
     cudaFree(sc->d_pose);
     cudaFreeHost(sc->h_pose);
     cudaFree(sc->d_rec_idx);
@@ -1389,13 +1543,14 @@ template <int C, int ST> static int launch_deriv(const IcpParams &P, const Solve
     return XS_OK;
 }
 
-template <int ST> static int launch_deriv_h(const IcpParams &P, const SolveParams &S, int grid, cudaStream_t s) {
+template <int ST, int MINB, int HPK, bool REDUCED> static int launch_deriv_h(const IcpParams &P, const SolveParams &S, int grid, cudaStream_t s) {
     static bool smem_set = false;
     if (!smem_set) {
-        XS_CUDA(cudaFuncSetAttribute(icp_deriv_h_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) deriv_h_smem(ST)));
+        XS_CUDA(cudaFuncSetAttribute(icp_deriv_h_kernel<ST, MINB, HPK, REDUCED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int) deriv_h_smem(ST, HPK, REDUCED)));
         smem_set = true;
     }
-    icp_deriv_h_kernel<ST><<<grid, 256, deriv_h_smem(ST), s>>>(P, S);
+    icp_deriv_h_kernel<ST, MINB, HPK, REDUCED><<<grid, 256, deriv_h_smem(ST, HPK, REDUCED), s>>>(P, S);
     XS_LAUNCH_CHECK();
     return XS_OK;
 }
@@ -1404,11 +1559,12 @@ template <int ST> static int launch_deriv_h(const IcpParams &P, const SolveParam
 // partials and - when d_pose_out is given - runs the Gauss-Newton step per direction; with ncomp == 0 the step is a
 // one-thread kernel.  d_pose_out == nullptr: accumulate only (the sums land in g_icp.d_sums).
 int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
-                        xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, const BatchView &batch,
+                        xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, const Batch &batch_full,
                         float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
                         double *d_log, cudaStream_t s, cudaStream_t s_real, int slot) {
     IcpScratch &g_icp = *scp;
     g_last_timed = scp;
+    const BatchView &batch = batch_full.v;
     const int comps = batch.kind, dirs = batch.n;
     const int ncomp = batch.ncomp;
     const bool hessian = batch.kind == 2;
@@ -1426,12 +1582,42 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
     IcpParams P;
     // derivative pass decomposition (icp_deriv_kernel): pixel units of 256 * ppt pixels, (group, unit) items cut into equal
     // contiguous ranges for min(296, items) persistent CTAs; ppt shrinks until there are at least as many items as CTA slots
-    P.groups = hessian ? batch.n + batch.m : (ncomp + 2) / 3;  // Hessian batch: one group per task (parameter or pair)
+    // REDUCED pair sums (g_ij = b_ij - A_ij x, see icp_deriv_h_kernel) need the real solution before the derivative pass: split
+    // chains with a solve; the ICP log and accumulate-only calls want the full A_ij, b_ij
+    static const int h_full = env_int("XS_ICP_H_FULL", 0);  // A/B knob
+    const bool h_reduced = hessian && split && d_log == nullptr && !h_full;
+    const int hp = h_reduced ? 3 : 2;
+    if (hessian && (g_icp.htasks_key != (const void *) batch.pairs || !g_icp.d_htasks || g_icp.htasks_hp != hp)) {
+        // task table: one task per parameter (first-order sums), then the pairs in runs of up to hp that share their first parameter
+        std::vector<HTask> tasks;
+        for (int i = 0; i < batch.n; ++i) tasks.push_back(HTask{i, 0, {i, i, i}, {i, i, i}});
+        for (int k = 0; k < batch.m;) {
+            HTask t = {batch_full.h_pairs[k].x, 0, {0, 0, 0}, {0, 0, 0}};
+            while (k < batch.m && t.np < hp && batch_full.h_pairs[k].x == t.i) {
+                t.j[t.np] = batch_full.h_pairs[k].y;
+                t.s[t.np] = batch.n + k;
+                ++t.np;
+                ++k;
+            }
+            for (int h = t.np; h < HPMAX; ++h) t.j[h] = t.j[0], t.s[h] = t.s[0];
+            tasks.push_back(t);
+        }
+        g_icp.htasks_hp = hp;
+        XS_CUDA(cudaStreamSynchronize(s));  // a table still in use by queued iterations (another pair list) must not be freed under them
+        cudaFree(g_icp.d_htasks);
+        g_icp.d_htasks = nullptr;
+        XS_CUDA(cudaMalloc(&g_icp.d_htasks, tasks.size() * sizeof(HTask)));
+        XS_CUDA(cudaMemcpy(g_icp.d_htasks, tasks.data(), tasks.size() * sizeof(HTask), cudaMemcpyHostToDevice));
+        g_icp.n_htasks = (int) tasks.size();
+        g_icp.htasks_key = (const void *) batch.pairs;
+    }
+    P.groups = hessian ? g_icp.n_htasks : (ncomp + 2) / 3;  // Hessian batch: one group per task
     P.batch = batch;
+    P.htasks = g_icp.d_htasks;
     P.done_ticket = nullptr;
     static const int ppt_env = env_int("XS_ICP_PPT", 0), stages_env = env_int("XS_ICP_STAGES", 0);
     P.ppt = 4;
-    const int cta_slots = hessian ? g_icp.max_blocks / 2 * 3 : g_icp.max_blocks;  // persistent CTAs: two per SM (three for the 27-accumulator kernel)
+    const int cta_slots = g_icp.max_blocks;  // two persistent CTAs per SM
     while (P.ppt > 1 && (long long) div_up(npix, 256 * P.ppt) * P.groups < cta_slots) P.ppt >>= 1;
     if (ppt_env > 0) P.ppt = ppt_env < 32 ? ppt_env : 32;
     P.chunks = div_up(npix, 256 * P.ppt);
@@ -1477,6 +1663,7 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
     }
     S.pose_in = d_pose_curr;
     S.pose_out = d_pose_out;
+    static const int no_tail = env_int("XS_ICP_NO_TAIL", 0);  // timing experiment only: the derivative tails skip the solve (derivative poses are then stale)
     S.status = d_status;
     S.log = d_log;
     S.dirs = dirs;
@@ -1484,16 +1671,17 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
     S.solve_mode = solve_mode;
     const int ntiles = P.tiles_x * P.tiles_y;
     const int grid = ntiles < g_icp.max_blocks ? ntiles : g_icp.max_blocks;
-    icp_assoc_kernel<<<grid, dim3(32, 8), 0, split ? s_real : s>>>(P);
+    // the real step rides in the tail of the association kernel when it depends on no derivative component: under split
+    // chains (the derivative kernels then update derivative components only) and when there are none at all
+    SolveParams SR = S;  // one thread, no derivative components, owns the status flags
+    SR.dirs = 0;
+    SR.ncomp = 0;
+    SR.deriv_only = 0;
+    if (split) SR.log = nullptr;
+    if (!(split || (ncomp == 0 && d_pose_out))) SR.pose_out = nullptr;
+    icp_assoc_kernel<<<grid, dim3(32, 8), 0, split ? s_real : s>>>(P, SR);
     XS_LAUNCH_CHECK();
     if (split) {
-        SolveParams SR = S;  // the real step: one thread, no derivative components, owns the status flags
-        SR.dirs = 0;
-        SR.ncomp = 0;
-        SR.deriv_only = 0;
-        SR.log = nullptr;
-        icp_solve_kernel<1><<<1, 32, 0, s_real>>>(SR);
-        XS_LAUNCH_CHECK();
         if (!g_icp.ev_real[slot]) XS_CUDA(cudaEventCreateWithFlags(&g_icp.ev_real[slot], cudaEventDisableTiming));
         XS_CUDA(cudaEventRecord(g_icp.ev_real[slot], s_real));
         XS_CUDA(cudaStreamWaitEvent(s, g_icp.ev_real[slot], 0));
@@ -1510,8 +1698,9 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
         // pipeline depth: 2 stages (one pixel ahead) measured faster than 3 on B200 (0.475 vs 0.542 ms per level-0 launch at
         // 55 directions: the deeper pipeline costs L1 capacity and does not raise issue utilisation); XS_ICP_STAGES=3 selects it
         const int stages = stages_env == 3 ? 3 : 2;
+        if (no_tail && split) S.pose_out = nullptr;
         if (hessian)
-            rc = launch_deriv_h<2>(P, S, deriv_grid, s);
+            rc = h_reduced ? launch_deriv_h<2, 2, 3, true>(P, S, deriv_grid, s) : launch_deriv_h<2, 2, 2, false>(P, S, deriv_grid, s);
         else if (comps == 1)
             rc = stages == 2 ? launch_deriv<1, 2>(P, S, deriv_grid, s) : launch_deriv<1, DERIV_MAX_STAGES>(P, S, deriv_grid, s);
         else
@@ -1522,12 +1711,6 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
             g_icp.timed_npix[tslot] = npix;
             ++g_icp.n_timed;
         }
-    } else if (d_pose_out) {
-        if (comps == 1)
-            icp_solve_kernel<1><<<1, 32, 0, s>>>(S);
-        else
-            icp_solve_kernel<3><<<1, 32, 0, s>>>(S);
-        XS_LAUNCH_CHECK();
     }
     return XS_OK;
 }
@@ -1665,7 +1848,7 @@ extern "C" int xs_estimate_combined(const xs_pose *curr, const float *d_vmap_cur
     }
     XS_CUDA(cudaMemcpyAsync(g_icp.d_pose, h, (size_t) (1 + ncomp) * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
     rc = icp_iteration_async(scp, g_icp.d_pose, d_vmap_curr, d_nmap_curr, prev, intr, d_vmap_g_prev, d_nmap_g_prev, rows, cols,
-                             batch.v, dist_thres, angle_thres, nullptr, 0, nullptr, nullptr, s, nullptr, 0);
+                             batch, dist_thres, angle_thres, nullptr, 0, nullptr, nullptr, s, nullptr, 0);
     if (rc != XS_OK) return rc;
     const int nvals = 27 * (1 + ncomp);
     XS_CUDA(cudaMemcpyAsync(g_icp.h_sums, g_icp.d_sums, (size_t) nvals * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -707,6 +707,14 @@ extern "C" int xs_volume_finish_frame(xs_volume *v, unsigned long long *stats_ho
     if (stats_host)
         for (int i = 0; i < 4; ++i) stats_host[i] = v->h_stats[i];
     cudaEventElapsedTime(&v->last_kernel_ms, v->ev_k0, v->ev_k1);
+    // the raycast of the collected frame has completed too: its hit kernel's duration (the events are re-recorded by the next
+    // frame, so the value is taken here and kept)
+    if (cudaEventElapsedTime(&v->last_hit_ms, v->ev_h0, v->ev_h1) != cudaSuccess) {
+        v->last_hit_ms = 0.f;
+        cudaGetLastError();
+    }
+    v->hit_stats[0] = v->h_stats[4];
+    v->hit_stats[1] = v->h_stats[5];
     return XS_OK;
 }
 

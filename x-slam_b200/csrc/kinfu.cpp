@@ -31,7 +31,7 @@ struct IcpScratch;
 IcpScratch *icp_scratch_create();
 void icp_scratch_destroy(IcpScratch *sc);
 int icp_iteration_async(IcpScratch *sc, const float *d_pose_curr, const float *d_vmap_curr, const float *d_nmap_curr, const xs_pose *prev,
-                        xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, const BatchView &batch,
+                        xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, const Batch &batch,
                         float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
                         double *d_log, cudaStream_t s, cudaStream_t s_real, int slot);
 // raycast.cu: resizeVMap / resizeNMap for a batch description
@@ -105,6 +105,13 @@ struct xs_kinfu {
     const uint16_t *next_depth = nullptr;  // ProcessFrame: frame whose integration head is queued behind the ICP download
     cudaEvent_t ev_icp = nullptr;          // the ICP result has reached the host buffers
     bool h_depth_free = true;  // no upload from the pinned staging frame is in flight
+    // multi-GPU (comm.cpp): the record of every rank is all-gathered after each frame on a stream of its own
+    xs_comm *comm = nullptr;
+    int record_floats = 0;                 // floats per rank in the gather (>= (1 + ncomp) * 16, the same on every rank)
+    float *d_gathered = nullptr;           // [world][record_floats]
+    cudaStream_t stream_comm = nullptr;
+    cudaEvent_t ev_record = nullptr, ev_gather = nullptr;  // record uploaded / gather has read it and written d_gathered
+    bool gather_in_flight = false;
     bool deferred = false;  // xs_kinfu_set_deferred: ProcessFrame returns once integration + raycast are queued
     bool pending = false;   // a frame's integration / raycast may still be running; its statistics are not collected yet
 };
@@ -300,6 +307,13 @@ void xs_kinfu_destroy(xs_kinfu *k) {
         cudaFree(k->vmaps_prev[i]);
         cudaFree(k->nmaps_prev[i]);
     }
+    if (k->stream_comm) {
+        cudaStreamSynchronize(k->stream_comm);
+        cudaStreamDestroy(k->stream_comm);
+        cudaEventDestroy(k->ev_record);
+        cudaEventDestroy(k->ev_gather);
+    }
+    cudaFree(k->d_gathered);
     cudaFree(k->d_record);
     cudaFreeHost(k->h_record);
     if (k->stream_real) cudaStreamSynchronize(k->stream_real);
@@ -386,7 +400,7 @@ int xs_kinfu_pose_estimate(xs_kinfu *k) {
         for (int iter = 0; iter < k->icp_iterations[level]; ++iter, ++it) {
             const int rc = icp_iteration_async(k->icp, k->d_pose_slot(it), k->vmaps_curr[level], k->nmaps_curr[level], &prev_pose,
                                                level_intr(k->intr, level), k->vmaps_prev[level], k->nmaps_prev[level], rows,
-                                               cols, k->batch.v, c.dist_thres, k->angle_thres, k->d_pose_slot(it + 1),
+                                               cols, k->batch, c.dist_thres, k->angle_thres, k->d_pose_slot(it + 1),
                                                k->solve_mode, k->d_status,
                                                k->log_icp && it < 16 ? k->d_icp_log + (size_t) it * log_stride : nullptr,
                                                k->stream, split ? k->stream_real : nullptr, it);
@@ -572,7 +586,15 @@ int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_devi
         for (int i = 0; i < 4; ++i)
             for (int j = 0; j < 4; ++j)
                 k->h_record[(size_t) q * 16 + i * 4 + j] = q == 0 ? k->world2camera.m[i][j].v : k->world2camera.m[i][j].d[q - 1];
+    if (k->comm && k->gather_in_flight) cudaStreamWaitEvent(k->stream, k->ev_gather, 0);  // the previous gather has read d_record
     cudaMemcpyAsync(k->d_record, k->h_record, (size_t) (1 + k->ncomp) * 16 * sizeof(float), cudaMemcpyHostToDevice, k->stream);
+    if (k->comm) {  // derivatives gathered by NCCL all-gather over NVLink, beside the next frame's kernels
+        cudaEventRecord(k->ev_record, k->stream);
+        cudaStreamWaitEvent(k->stream_comm, k->ev_record, 0);
+        if (xs_comm_all_gather(k->comm, k->d_record, k->d_gathered, k->record_floats, k->stream_comm) != XS_OK) return 0;
+        cudaEventRecord(k->ev_gather, k->stream_comm);
+        k->gather_in_flight = true;
+    }
     cudaEventRecord(ev[4], k->stream);
     k->launches[3] = g_launches - l0;
     if (k->deferred) {  // pose and status are final (the ICP result was read on the host); the volume and the maps follow
@@ -607,6 +629,7 @@ int xs_kinfu_set_deferred(xs_kinfu *k, int on) {
 // Waits for everything queued on the pipeline's stream and collects the statistics of a deferred frame.
 int xs_kinfu_sync(xs_kinfu *k) {
     if (!k) return XS_ERR_ARG;
+    if (k->stream_comm && cudaStreamSynchronize(k->stream_comm) != cudaSuccess) return XS_ERR_CUDA;
     if (k->pending) return finish_pending(k);
     return cudaStreamSynchronize(k->stream) == cudaSuccess ? XS_OK : XS_ERR_CUDA;
 }
@@ -734,6 +757,117 @@ int xs_kinfu_get_algorithmic_bytes(const xs_kinfu *k, double *out4) {
 }
 
 float *xs_kinfu_pose_record_device(xs_kinfu *k) { return k ? k->d_record : nullptr; }
+
+// se3Exp (KinectFusionReconstruction.h:176-219) on batched jets: the parameterisation of the reference's relocalisation /
+// pose-set experiments.  xi: [(1 + ncomp)][6] = (v, omega), component 0 real, the rest h-scaled derivative components of the
+// batch kind (comps, dirs, pairs as for xs_kinfu_create / _create_hessian); T_out: [(1 + ncomp)][16] row-major 4x4.
+// Like the reference, |omega| < 1e-6 takes the first-order branch R = V = I + omega^ (the reference's norm includes the
+// imaginary parts, which are h-sized; the branch here is decided on the real part).
+int xs_se3_exp(const float *xi, int comps, int dirs, int npairs, const int *pairs, float *T_out) {
+    if (!xi || !T_out || (comps != 1 && comps != 2 && comps != 3) || dirs < 0) return XS_ERR_ARG;
+    std::vector<HPair> hp;
+    if (comps == 2) {
+        if (pairs)
+            for (int k = 0; k < npairs; ++k) hp.push_back(HPair{pairs[2 * k], pairs[2 * k + 1]});
+        else
+            for (int i = 0; i < dirs; ++i)
+                for (int j = i; j < dirs; ++j) hp.push_back(HPair{i, j});
+    }
+    const HJetCtx saved = hj_ctx();
+    hj_ctx().comps = comps;
+    hj_ctx().dirs = dirs;
+    hj_ctx().npairs = (int) hp.size();
+    hj_ctx().pairs = hp.empty() ? nullptr : hp.data();
+    const int ncomp = hj_ctx().ncomp();
+    if (ncomp > HJ_MAX) {
+        hj_ctx() = saved;
+        set_error("xs_se3_exp: at most 256 derivative components");
+        return XS_ERR_ARG;
+    }
+    {
+        HJet x[6];
+        for (int e = 0; e < 6; ++e) {
+            x[e] = HJet(xi[e]);
+            for (int q = 0; q < ncomp; ++q) x[e].d[q] = xi[(size_t) (1 + q) * 6 + e];
+        }
+        const HJet *v = x, *w = x + 3;
+        HMat3 W;  // omega^
+        W.m[0][1] = -w[2], W.m[0][2] = w[1], W.m[1][2] = -w[0];
+        W.m[1][0] = w[2], W.m[2][0] = -w[1], W.m[2][1] = w[0];
+        HMat3 R, V;
+        for (int i = 0; i < 3; ++i) R.m[i][i] = V.m[i][i] = HJet(1.f);
+        const float nrm = std::sqrt(w[0].v * w[0].v + w[1].v * w[1].v + w[2].v * w[2].v);
+        if (nrm < 1e-6f) {
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) R.m[i][j] = R.m[i][j] + W.m[i][j], V.m[i][j] = V.m[i][j] + W.m[i][j];
+        } else {
+            const HJet theta = hj_sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+            const HJet sn = hj_sin(theta), cs = hj_cos(theta);
+            const HMat3 W2 = hmul(W, W);
+            const HJet A = sn / theta, B = (HJet(1.f) - cs) / (theta * theta), C = (theta - sn) / (theta * theta * theta);
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    R.m[i][j] = R.m[i][j] + A * W.m[i][j] + B * W2.m[i][j];
+                    V.m[i][j] = V.m[i][j] + B * W.m[i][j] + C * W2.m[i][j];
+                }
+        }
+        HVec3 vv;
+        for (int i = 0; i < 3; ++i) vv.v[i] = v[i];
+        const HVec3 t = hmul(V, vv);
+        for (int q = 0; q <= ncomp; ++q) {
+            float *T = T_out + (size_t) q * 16;
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) T[i * 4 + j] = q == 0 ? R.m[i][j].v : R.m[i][j].d[q - 1];
+                T[i * 4 + 3] = q == 0 ? t.v[i].v : t.v[i].d[q - 1];
+            }
+            T[12] = T[13] = T[14] = 0.f;
+            T[15] = q == 0 ? 1.f : 0.f;
+        }
+    }
+    hj_ctx() = saved;
+    return XS_OK;
+}
+
+// Attaches a communicator (comm.cpp): from the next frame on, every rank's record - (1 + ncomp) 4x4 matrices, padded to
+// record_floats, which must be the same on every rank and >= the largest (1 + ncomp) * 16 - is all-gathered after each
+// processed frame.  The gather is queued by ProcessFrame on an internal stream behind the frame's record upload.
+int xs_kinfu_set_comm(xs_kinfu *k, xs_comm *comm, int record_floats) {
+    if (!k) return XS_ERR_ARG;
+    if (k->stream_comm) cudaStreamSynchronize(k->stream_comm);
+    k->gather_in_flight = false;
+    k->comm = comm;
+    if (!comm) return XS_OK;
+    if (record_floats < (1 + k->ncomp) * 16) {
+        set_error("xs_kinfu_set_comm: record_floats is smaller than this rank's record");
+        k->comm = nullptr;
+        return XS_ERR_ARG;
+    }
+    KCUDA(cudaStreamSynchronize(k->stream));
+    if (!k->stream_comm) {
+        KCUDA(cudaStreamCreateWithFlags(&k->stream_comm, cudaStreamNonBlocking));
+        KCUDA(cudaEventCreateWithFlags(&k->ev_record, cudaEventDisableTiming));
+        KCUDA(cudaEventCreateWithFlags(&k->ev_gather, cudaEventDisableTiming));
+    }
+    // the send buffer is the record itself, re-allocated at the padded size (padding stays zero)
+    cudaFree(k->d_record);
+    cudaFree(k->d_gathered);
+    k->d_record = k->d_gathered = nullptr;
+    k->record_floats = record_floats;
+    KCUDA(cudaMalloc((void **) &k->d_record, (size_t) record_floats * sizeof(float)));
+    KCUDA(cudaMemset(k->d_record, 0, (size_t) record_floats * sizeof(float)));
+    KCUDA(cudaMalloc((void **) &k->d_gathered, (size_t) xs_comm_world(comm) * record_floats * sizeof(float)));
+    KCUDA(cudaMemset(k->d_gathered, 0, (size_t) xs_comm_world(comm) * record_floats * sizeof(float)));
+    return XS_OK;
+}
+
+// The gathered records of the last processed frame, [world][record_floats]: waits for that frame's all-gather only.
+int xs_kinfu_get_gathered_records(xs_kinfu *k, float *host_out) {
+    if (!k || !host_out || !k->comm) return XS_ERR_ARG;
+    if (k->gather_in_flight) KCUDA(cudaEventSynchronize(k->ev_gather));
+    KCUDA(cudaMemcpy(host_out, k->d_gathered, (size_t) xs_comm_world(k->comm) * k->record_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    return XS_OK;
+}
+const float *xs_kinfu_gathered_records_device(xs_kinfu *k) { return k ? k->d_gathered : nullptr; }
 
 void *xs_kinfu_stream(xs_kinfu *k) { return k ? (void *) k->stream : nullptr; }
 

@@ -406,12 +406,230 @@ XS_DEV void hit_direction(const RaycastParams &P, const float *ctx, int x, int y
     }
 }
 
+// ---- Hessian batches: first-order results cached per (pixel, parameter) --------------------------------------------------
+// The second-order component of a pair (i, j) needs, at every trilinear sample, the VALUE and the GRADIENT (w.r.t. the
+// weights a, b, c) of the trilinear contraction of the first-order planes F_i and F_j - which do not depend on the pair.  The
+// parameter tasks therefore leave them in shared memory, and a pair task gathers only its own plane S_ij (8 corners per sample
+// instead of 24) and contracts it for the value only:
+//   tri_ij = <S>_w + G.abc_ij + g_j.abc_i + g_i.abc_j + abc_i^T H abc_j          (G, H: real interpolant, ctx; g: cached)
+// The six normal samples share one position derivative (the vertex's), so per axis only the DIFFERENCES (+ minus -) of value
+// and gradient are cached.  Per (pixel, parameter): 2 crossing samples x (v, g[3]) + 3 axes x (dv, dg[3]) = 20 floats.
+constexpr int HC_FIELDS = 20;
+enum { HC_S0 = 0, HC_S1 = 4, HC_AX = 8 };  // + 4 * axis
+
+// value + gradient of the contraction of one first-order plane at one sample (8 corner gathers)
+XS_DEV void sample_first(const float *__restrict__ plane, const float *ctx, float &v, float &ga, float &gb, float &gc) {
+    const float a = ctx[S_A * HIT_PX], b = ctx[S_B * HIT_PX], c = ctx[S_C * HIT_PX];
+    const long long o000 = (long long) ((unsigned long long) __float_as_uint(ctx[S_OFF * HIT_PX]) |
+                                        ((unsigned long long) __float_as_uint(ctx[(S_OFF + 1) * HIT_PX]) << 32));
+    const long long sx = __float_as_int(ctx[S_SX * HIT_PX]), sy = __float_as_int(ctx[S_SY * HIT_PX]), sz = __float_as_int(ctx[S_SZ * HIT_PX]);
+    float f[8];
+#pragma unroll
+    for (int cidx = 0; cidx < 8; ++cidx)
+        f[cidx] = __ldg(plane + o000 + ((cidx & 4) ? sx : 0) + ((cidx & 2) ? sy : 0) + ((cidx & 1) ? sz : 0));
+    float unused;
+    contract<false>(f, a, b, c, v, ga, gb, gc, unused, unused, unused);
+}
+XS_DEV float sample_value(const float *__restrict__ plane, const float *ctx) {
+    const float a = ctx[S_A * HIT_PX], b = ctx[S_B * HIT_PX], c = ctx[S_C * HIT_PX];
+    const long long o000 = (long long) ((unsigned long long) __float_as_uint(ctx[S_OFF * HIT_PX]) |
+                                        ((unsigned long long) __float_as_uint(ctx[(S_OFF + 1) * HIT_PX]) << 32));
+    const long long sx = __float_as_int(ctx[S_SX * HIT_PX]), sy = __float_as_int(ctx[S_SY * HIT_PX]), sz = __float_as_int(ctx[S_SZ * HIT_PX]);
+    float f[8];
+#pragma unroll
+    for (int cidx = 0; cidx < 8; ++cidx)
+        f[cidx] = __ldg(plane + o000 + ((cidx & 4) ? sx : 0) + ((cidx & 2) ? sy : 0) + ((cidx & 1) ? sz : 0));
+    return contract_value(f, a, b, c);
+}
+
+// Parameter task (first order) of one pixel group: the C = 1 propagation of hit_direction, leaving the per-sample value /
+// gradient of the F_i contraction in the cache hc[HC_FIELDS][HIT_PX] (+ lane)
+XS_DEV void hit_first_cached(const RaycastParams &P, const float *ctx, float *hc, int x, int y, float ny, float inv_vs, int comp) {
+    typedef Jet<1, 1> J;
+    const VolumeView &V = P.V;
+    const float *xctx = ctx + 8 * S_FIELDS * HIT_PX;
+    const unsigned flags = __float_as_uint(xctx[X_FLAGS * HIT_PX]);
+    const float t0 = xctx[X_T0 * HIT_PX];
+    const float nx = (float(x) - P.intr.cx) * __fdividef(1.f, P.intr.fx);
+    Jet3<1, 1> vw, ng;
+    if (flags & 1u) {
+        const int cc[1] = {comp};
+        const JetPose<1, 1> c2v = load_pose_comps<1>(P.c2v, P.dpose_c2v, cc);
+        Jet3<1, 1> next = {jconst<1, 1>(nx), jconst<1, 1>(ny), jconst<1, 1>(1.f)};
+        const Jet3<1, 1> start = c2v.t;
+        Jet3<1, 1> dir = jnormalized_fast(jrot(c2v, next));
+        if (dir.x.v == 0.f) dir.x = jconst<1, 1>(1e-15f);
+        if (dir.y.v == 0.f) dir.y = jconst<1, 1>(1e-15f);
+        if (dir.z.v == 0.f) dir.z = jconst<1, 1>(1e-15f);
+        const float t1 = t0 + P.time_step;
+        const float *plane = V.deriv + (size_t) comp * BRICK_VOX;
+        // crossing samples: sample 0 at t1, sample 1 at t0 (their position derivatives differ)
+        J Fs[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const float *cs = ctx + s * S_FIELDS * HIT_PX;
+            const float ts = s == 0 ? t1 : t0;
+            float v, ga, gb, gc;
+            sample_first(plane, cs, v, ga, gb, gc);
+            hc[(HC_S0 + 4 * s + 0) * HIT_PX] = v;
+            hc[(HC_S0 + 4 * s + 1) * HIT_PX] = ga;
+            hc[(HC_S0 + 4 * s + 2) * HIT_PX] = gb;
+            hc[(HC_S0 + 4 * s + 3) * HIT_PX] = gc;
+            const float px = fmaf(dir.x.d[0], ts, start.x.d[0]) * inv_vs, py = fmaf(dir.y.d[0], ts, start.y.d[0]) * inv_vs,
+                        pz = fmaf(dir.z.d[0], ts, start.z.d[0]) * inv_vs;
+            Fs[s].v = cs[S_VAL * HIT_PX];
+            Fs[s].d[0] = fmaf(cs[S_GA * HIT_PX], px, fmaf(cs[S_GB * HIT_PX], py, fmaf(cs[S_GC * HIT_PX], pz, v)));
+        }
+        const J coef = jdiv_fast(Fs[1], Fs[0] - Fs[1]);
+        J Ts;
+        Ts.v = fmaf(-coef.v, P.time_step, t0);
+        Ts.d[0] = -P.time_step * coef.d[0];
+        const Jet3<1, 1> vertex = {start.x + dir.x * Ts, start.y + dir.y * Ts, start.z + dir.z * Ts};
+        const JetPose<1, 1> v2w = load_pose_comps<1>(P.v2w, P.dpose_v2w, cc);
+        vw = jrot(v2w, vertex) + v2w.t;
+        if (flags & 2u) {
+            const float ax = vertex.x.d[0] * inv_vs, ay = vertex.y.d[0] * inv_vs, az = vertex.z.d[0] * inv_vs;
+            Jet<1, 1> nn[3];
+#pragma unroll
+            for (int axis = 0; axis < 3; ++axis) {
+                const float *cp = ctx + (2 + 2 * axis) * S_FIELDS * HIT_PX, *cm = ctx + (3 + 2 * axis) * S_FIELDS * HIT_PX;
+                float vp, gpa, gpb, gpc, vm, gma, gmb, gmc;
+                sample_first(plane, cp, vp, gpa, gpb, gpc);
+                sample_first(plane, cm, vm, gma, gmb, gmc);
+                const float dv = vp - vm;
+                hc[(HC_AX + 4 * axis + 0) * HIT_PX] = dv;
+                hc[(HC_AX + 4 * axis + 1) * HIT_PX] = gpa - gma;
+                hc[(HC_AX + 4 * axis + 2) * HIT_PX] = gpb - gmb;
+                hc[(HC_AX + 4 * axis + 3) * HIT_PX] = gpc - gmc;
+                const float dGa = cp[S_GA * HIT_PX] - cm[S_GA * HIT_PX], dGb = cp[S_GB * HIT_PX] - cm[S_GB * HIT_PX],
+                            dGc = cp[S_GC * HIT_PX] - cm[S_GC * HIT_PX];
+                nn[axis].v = cp[S_VAL * HIT_PX] - cm[S_VAL * HIT_PX];
+                nn[axis].d[0] = fmaf(dGa, ax, fmaf(dGb, ay, fmaf(dGc, az, dv)));
+            }
+            const Jet3<1, 1> n = {nn[0], nn[1], nn[2]};
+            ng = jrot(v2w, jnormalized_fast(n));
+        }
+    }
+    const int out = 1 + comp;
+    if (flags & 1u)
+        store3(P.vmap, out, P.rows, P.cols, y, x, vw.x.d[0], vw.y.d[0], vw.z.d[0]);
+    else
+        store3(P.vmap, out, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
+    if (flags & 2u)
+        store3(P.nmap, out, P.rows, P.cols, y, x, ng.x.d[0], ng.y.d[0], ng.z.d[0]);
+    else
+        store3(P.nmap, out, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
+}
+
+// Pair task (second order) of one pixel group from the cached first-order results of parameters i and j (hci, hcj): the
+// bicomplex propagation of hit_direction<3> in which every sample gathers the pair's own plane only.
+XS_DEV void hit_pair_cached(const RaycastParams &P, const float *ctx, const float *hci, const float *hcj, int x, int y, float ny,
+                            float inv_vs, int ci, int cj, int cs_) {
+    typedef Jet<3, 1> J;
+    const VolumeView &V = P.V;
+    const float *xctx = ctx + 8 * S_FIELDS * HIT_PX;
+    const unsigned flags = __float_as_uint(xctx[X_FLAGS * HIT_PX]);
+    const float t0 = xctx[X_T0 * HIT_PX];
+    const float nx = (float(x) - P.intr.cx) * __fdividef(1.f, P.intr.fx);
+    Jet3<3, 1> vw, ng;
+    if (flags & 1u) {
+        const int comp[3] = {ci, cj, cs_};
+        const JetPose<3, 1> c2v = load_pose_comps<3>(P.c2v, P.dpose_c2v, comp);
+        Jet3<3, 1> next = {jconst<3, 1>(nx), jconst<3, 1>(ny), jconst<3, 1>(1.f)};
+        const Jet3<3, 1> start = c2v.t;
+        Jet3<3, 1> dir = jnormalized_fast(jrot(c2v, next));
+        if (dir.x.v == 0.f) dir.x = jconst<3, 1>(1e-15f);
+        if (dir.y.v == 0.f) dir.y = jconst<3, 1>(1e-15f);
+        if (dir.z.v == 0.f) dir.z = jconst<3, 1>(1e-15f);
+        const float t1 = t0 + P.time_step;
+        const float *plane = V.deriv + (size_t) cs_ * BRICK_VOX;
+        J Fs[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const float *cs = ctx + s * S_FIELDS * HIT_PX;
+            const float ts = s == 0 ? t1 : t0;
+            // position derivatives of the sample in voxel units: (a, b, c) components 1, 2, 12
+            float pa[3], pb[3], pc[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                pa[q] = fmaf(dir.x.d[q], ts, start.x.d[q]) * inv_vs;
+                pb[q] = fmaf(dir.y.d[q], ts, start.y.d[q]) * inv_vs;
+                pc[q] = fmaf(dir.z.d[q], ts, start.z.d[q]) * inv_vs;
+            }
+            const float ga = cs[S_GA * HIT_PX], gb = cs[S_GB * HIT_PX], gc = cs[S_GC * HIT_PX];
+            const float hab = cs[S_HAB * HIT_PX], hac = cs[S_HAC * HIT_PX], hbc = cs[S_HBC * HIT_PX];
+            const float vi = hci[(HC_S0 + 4 * s) * HIT_PX], gia = hci[(HC_S0 + 4 * s + 1) * HIT_PX], gib = hci[(HC_S0 + 4 * s + 2) * HIT_PX],
+                        gic = hci[(HC_S0 + 4 * s + 3) * HIT_PX];
+            const float vj = hcj[(HC_S0 + 4 * s) * HIT_PX], gja = hcj[(HC_S0 + 4 * s + 1) * HIT_PX], gjb = hcj[(HC_S0 + 4 * s + 2) * HIT_PX],
+                        gjc = hcj[(HC_S0 + 4 * s + 3) * HIT_PX];
+            const float vs12 = sample_value(plane, cs);
+            Fs[s].v = cs[S_VAL * HIT_PX];
+            Fs[s].d[0] = fmaf(ga, pa[0], fmaf(gb, pb[0], fmaf(gc, pc[0], vi)));
+            Fs[s].d[1] = fmaf(ga, pa[1], fmaf(gb, pb[1], fmaf(gc, pc[1], vj)));
+            float t = fmaf(ga, pa[2], fmaf(gb, pb[2], fmaf(gc, pc[2], vs12)));
+            t = fmaf(gja, pa[0], fmaf(gjb, pb[0], fmaf(gjc, pc[0], t)));
+            t = fmaf(gia, pa[1], fmaf(gib, pb[1], fmaf(gic, pc[1], t)));
+            t = fmaf(hab, fmaf(pa[0], pb[1], pb[0] * pa[1]), fmaf(hac, fmaf(pa[0], pc[1], pc[0] * pa[1]), fmaf(hbc, fmaf(pb[0], pc[1], pc[0] * pb[1]), t)));
+            Fs[s].d[2] = t;
+        }
+        const J coef = jdiv_fast(Fs[1], Fs[0] - Fs[1]);
+        J Ts;
+        Ts.v = fmaf(-coef.v, P.time_step, t0);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) Ts.d[q] = -P.time_step * coef.d[q];
+        const Jet3<3, 1> vertex = {start.x + dir.x * Ts, start.y + dir.y * Ts, start.z + dir.z * Ts};
+        const JetPose<3, 1> v2w = load_pose_comps<3>(P.v2w, P.dpose_v2w, comp);
+        vw = jrot(v2w, vertex) + v2w.t;
+        if (flags & 2u) {
+            float pa[3], pb[3], pc[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) pa[q] = vertex.x.d[q] * inv_vs, pb[q] = vertex.y.d[q] * inv_vs, pc[q] = vertex.z.d[q] * inv_vs;
+            J nn[3];
+#pragma unroll
+            for (int axis = 0; axis < 3; ++axis) {
+                const float *cp = ctx + (2 + 2 * axis) * S_FIELDS * HIT_PX, *cm = ctx + (3 + 2 * axis) * S_FIELDS * HIT_PX;
+                const float ga = cp[S_GA * HIT_PX] - cm[S_GA * HIT_PX], gb = cp[S_GB * HIT_PX] - cm[S_GB * HIT_PX], gc = cp[S_GC * HIT_PX] - cm[S_GC * HIT_PX];
+                const float hab = cp[S_HAB * HIT_PX] - cm[S_HAB * HIT_PX], hac = cp[S_HAC * HIT_PX] - cm[S_HAC * HIT_PX],
+                            hbc = cp[S_HBC * HIT_PX] - cm[S_HBC * HIT_PX];
+                const float vi = hci[(HC_AX + 4 * axis) * HIT_PX], gia = hci[(HC_AX + 4 * axis + 1) * HIT_PX], gib = hci[(HC_AX + 4 * axis + 2) * HIT_PX],
+                            gic = hci[(HC_AX + 4 * axis + 3) * HIT_PX];
+                const float vj = hcj[(HC_AX + 4 * axis) * HIT_PX], gja = hcj[(HC_AX + 4 * axis + 1) * HIT_PX], gjb = hcj[(HC_AX + 4 * axis + 2) * HIT_PX],
+                            gjc = hcj[(HC_AX + 4 * axis + 3) * HIT_PX];
+                const float vs12 = sample_value(plane, cp) - sample_value(plane, cm);
+                nn[axis].v = cp[S_VAL * HIT_PX] - cm[S_VAL * HIT_PX];
+                nn[axis].d[0] = fmaf(ga, pa[0], fmaf(gb, pb[0], fmaf(gc, pc[0], vi)));
+                nn[axis].d[1] = fmaf(ga, pa[1], fmaf(gb, pb[1], fmaf(gc, pc[1], vj)));
+                float t = fmaf(ga, pa[2], fmaf(gb, pb[2], fmaf(gc, pc[2], vs12)));
+                t = fmaf(gja, pa[0], fmaf(gjb, pb[0], fmaf(gjc, pc[0], t)));
+                t = fmaf(gia, pa[1], fmaf(gib, pb[1], fmaf(gic, pc[1], t)));
+                t = fmaf(hab, fmaf(pa[0], pb[1], pb[0] * pa[1]), fmaf(hac, fmaf(pa[0], pc[1], pc[0] * pa[1]), fmaf(hbc, fmaf(pb[0], pc[1], pc[0] * pb[1]), t)));
+                nn[axis].d[2] = t;
+            }
+            const Jet3<3, 1> n = {nn[0], nn[1], nn[2]};
+            ng = jrot(v2w, jnormalized_fast(n));
+        }
+    }
+    const int out = 1 + cs_;
+    if (flags & 1u)
+        store3(P.vmap, out, P.rows, P.cols, y, x, vw.x.d[2], vw.y.d[2], vw.z.d[2]);
+    else
+        store3(P.vmap, out, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
+    if (flags & 2u)
+        store3(P.nmap, out, P.rows, P.cols, y, x, ng.x.d[2], ng.y.d[2], ng.z.d[2]);
+    else
+        store3(P.nmap, out, P.rows, P.cols, y, x, 0.f, 0.f, 0.f);
+}
+
 // HIT_PG pixel groups of 32 pixels per CTA: the real phases (A: one warp per group, B: one warp per (group, normal
 // sample), C: one warp per group) fill the 8 warps four times better than with a single group, and the derivative loop
 // runs over (direction, group) tasks.
-constexpr int HIT_PG = 4;
-template <int KIND> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS, 2) raycast_hit_kernel(const RaycastParams P, const float *__restrict__ hit_time) {
-    extern __shared__ float s_ctx[];  // [HIT_PG][HIT_CTX_WORDS][HIT_PX]
+// CACHED (Hessian batches with few enough parameters): the parameter tasks leave their per-sample contractions in shared
+// memory ([HIT_PG][n][HC_FIELDS][HIT_PX] floats behind the context) and the pair tasks gather their own plane only.
+constexpr int HIT_PG_LIST = 4, HIT_PG_CACHED = 2;
+constexpr size_t hit_smem_bytes(int pg, int n_cached) { return (size_t) pg * (HIT_CTX_WORDS + (size_t) n_cached * HC_FIELDS) * HIT_PX * sizeof(float); }
+template <int KIND, int HIT_PG, bool CACHED>
+__global__ void __launch_bounds__(HIT_PX *HIT_WARPS, 2) raycast_hit_kernel(const RaycastParams P, const float *__restrict__ hit_time) {
+    extern __shared__ float s_ctx[];  // [HIT_PG][HIT_CTX_WORDS][HIT_PX] (+ the first-order cache)
     const int lane = threadIdx.x, warp = threadIdx.y;
     const int y = blockIdx.y;
     const float qnan = __int_as_float(0x7fffffff);
@@ -470,7 +688,7 @@ template <int KIND> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS, 2) rayc
     const float ny = (float(y) - P.intr.cy) * __fdividef(1.f, P.intr.fy);
     // tasks: (direction, pixel group) for the list kinds; for a Hessian batch first the n parameters (first-order algebra,
     // component i) and then the m pairs (bicomplex algebra on (F_i, F_j, S_ij), of which only S_ij is stored)
-    const int ntasks = (KIND == 2 ? P.batch.n + P.batch.m : P.dirs) * HIT_PG;
+    const int ntasks = (KIND == 2 ? (CACHED ? 0 : P.batch.n + P.batch.m) : P.dirs) * HIT_PG;
     for (int task = warp; task < ntasks; task += HIT_WARPS) {
         const int q = task / HIT_PG, pg = task % HIT_PG;
         const int x = x_of(pg);
@@ -482,13 +700,34 @@ template <int KIND> __global__ void __launch_bounds__(HIT_PX *HIT_WARPS, 2) rayc
         } else if (KIND == 3) {
             const int comp[3] = {3 * q, 3 * q + 1, 3 * q + 2};
             hit_direction<3>(P, ctx, x, y, ny, inv_vs, comp, 0);
-        } else if (q < P.batch.n) {
-            const int comp[1] = {q};
-            hit_direction<1>(P, ctx, x, y, ny, inv_vs, comp, 0);
-        } else {
-            const int2 pr = __ldg(P.batch.pairs + (q - P.batch.n));
-            const int comp[3] = {pr.x, pr.y, q};
-            hit_direction<3>(P, ctx, x, y, ny, inv_vs, comp, 2);
+        } else if (!CACHED) {
+            if (q < P.batch.n) {
+                const int comp[1] = {q};
+                hit_direction<1>(P, ctx, x, y, ny, inv_vs, comp, 0);
+            } else {
+                const int2 pr = __ldg(P.batch.pairs + (q - P.batch.n));
+                const int comp[3] = {pr.x, pr.y, q};
+                hit_direction<3>(P, ctx, x, y, ny, inv_vs, comp, 2);
+            }
+        }
+    }
+    if (KIND == 2 && CACHED) {
+        const int n = P.batch.n;
+        float *s_hc = s_ctx + (size_t) HIT_PG * HIT_CTX_WORDS * HIT_PX;  // [HIT_PG][n][HC_FIELDS][HIT_PX]
+        for (int task = warp; task < n * HIT_PG; task += HIT_WARPS) {
+            const int q = task / HIT_PG, pg = task % HIT_PG;
+            const int x = x_of(pg);
+            if (x >= P.cols) continue;
+            hit_first_cached(P, ctx_of(pg), s_hc + ((size_t) (pg * n + q) * HC_FIELDS) * HIT_PX + lane, x, y, ny, inv_vs, q);
+        }
+        __syncthreads();  // a pair reads the caches two parameter tasks (other warps) wrote
+        for (int task = warp; task < P.batch.m * HIT_PG; task += HIT_WARPS) {
+            const int k = task / HIT_PG, pg = task % HIT_PG;
+            const int x = x_of(pg);
+            if (x >= P.cols) continue;
+            const int2 pr = __ldg(P.batch.pairs + k);
+            hit_pair_cached(P, ctx_of(pg), s_hc + ((size_t) (pg * n + pr.x) * HC_FIELDS) * HIT_PX + lane,
+                            s_hc + ((size_t) (pg * n + pr.y) * HC_FIELDS) * HIT_PX + lane, x, y, ny, inv_vs, pr.x, pr.y, n + k);
         }
     }
 }
@@ -672,23 +911,30 @@ int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_po
     dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
     raycast_march_kernel<<<grd, blk, 0, s>>>(P, v->d_hit_time);
     XS_LAUNCH_CHECK();
-    dim3 g2(div_up(cols, HIT_PX * HIT_PG), rows), b2(HIT_PX, HIT_WARPS);
-    const size_t hit_smem = (size_t) HIT_PG * HIT_CTX_WORDS * HIT_PX * sizeof(float);
+    // Hessian batches cache the first-order contractions in shared memory when two CTAs of two pixel groups still fit an SM
+    static const bool no_cache = getenv("XS_HIT_NO_CACHE") != nullptr;  // A/B knob
+    const bool cached = v->comps == 2 && !no_cache && 2 * (hit_smem_bytes(HIT_PG_CACHED, v->batch.v.n) + 1024) <= 227 * 1024;
+    const int pg = cached ? HIT_PG_CACHED : HIT_PG_LIST;
+    dim3 g2(div_up(cols, HIT_PX * pg), rows), b2(HIT_PX, HIT_WARPS);
+    const size_t hit_smem = hit_smem_bytes(pg, cached ? v->batch.v.n : 0);
     static bool hit_smem_set = false;
     if (!hit_smem_set) {
-        XS_CUDA(cudaFuncSetAttribute(raycast_hit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hit_smem));
-        XS_CUDA(cudaFuncSetAttribute(raycast_hit_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hit_smem));
-        XS_CUDA(cudaFuncSetAttribute(raycast_hit_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hit_smem));
+        XS_CUDA(cudaFuncSetAttribute(raycast_hit_kernel<1, HIT_PG_LIST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hit_smem_bytes(HIT_PG_LIST, 0)));
+        XS_CUDA(cudaFuncSetAttribute(raycast_hit_kernel<3, HIT_PG_LIST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hit_smem_bytes(HIT_PG_LIST, 0)));
+        XS_CUDA(cudaFuncSetAttribute(raycast_hit_kernel<2, HIT_PG_LIST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hit_smem_bytes(HIT_PG_LIST, 0)));
+        XS_CUDA(cudaFuncSetAttribute(raycast_hit_kernel<2, HIT_PG_CACHED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
         hit_smem_set = true;
     }
     XS_CUDA(cudaMemsetAsync(v->d_stats + 4, 0, 2 * sizeof(unsigned long long), s));
     XS_CUDA(cudaEventRecord(v->ev_h0, s));
     if (v->comps == 1)
-        raycast_hit_kernel<1><<<g2, b2, hit_smem, s>>>(P, v->d_hit_time);
+        raycast_hit_kernel<1, HIT_PG_LIST, false><<<g2, b2, hit_smem, s>>>(P, v->d_hit_time);
+    else if (cached)
+        raycast_hit_kernel<2, HIT_PG_CACHED, true><<<g2, b2, hit_smem, s>>>(P, v->d_hit_time);
     else if (v->comps == 2)
-        raycast_hit_kernel<2><<<g2, b2, hit_smem, s>>>(P, v->d_hit_time);
+        raycast_hit_kernel<2, HIT_PG_LIST, false><<<g2, b2, hit_smem, s>>>(P, v->d_hit_time);
     else
-        raycast_hit_kernel<3><<<g2, b2, hit_smem, s>>>(P, v->d_hit_time);
+        raycast_hit_kernel<3, HIT_PG_LIST, false><<<g2, b2, hit_smem, s>>>(P, v->d_hit_time);
     XS_LAUNCH_CHECK();
     XS_CUDA(cudaEventRecord(v->ev_h1, s));
     XS_CUDA(cudaMemcpyAsync(v->h_stats + 4, v->d_stats + 4, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -697,15 +943,12 @@ int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_po
 
 // device duration of the last raycast hit kernel and its valid-vertex / valid-normal pixel counts; call after the stream has
 // been synchronised (the frame loop: after the frame has been collected)
-float xs_volume_last_raycast_hit_ms(const xs_volume *v) {
-    float ms = 0.f;
-    if (v && cudaEventElapsedTime(&ms, v->ev_h0, v->ev_h1) != cudaSuccess) ms = 0.f;
-    return ms;
-}
+// (values of the last COLLECTED frame: xs_volume_finish_frame takes them once the frame's work has completed)
+float xs_volume_last_raycast_hit_ms(const xs_volume *v) { return v ? v->last_hit_ms : 0.f; }
 int xs_volume_raycast_stats(const xs_volume *v, unsigned long long *out2) {
     if (!v || !out2) return XS_ERR_ARG;
-    out2[0] = v->h_stats[4];
-    out2[1] = v->h_stats[5];
+    out2[0] = v->hit_stats[0];
+    out2[1] = v->hit_stats[1];
     return XS_OK;
 }
 

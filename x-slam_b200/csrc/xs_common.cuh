@@ -89,4 +89,5 @@ struct xs_volume {
     float last_kernel_ms;
     cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;  // bracket the raycast hit kernel
     float last_hit_ms = 0.f;
+    unsigned long long hit_stats[2] = {0, 0};  // pixels with a valid vertex / normal of the last collected raycast
 };

@@ -122,6 +122,26 @@ def hessian_seeds(params=None, pairs=None, h=H_):
     return out.astype(np.float32), list(pairs)
 
 
+def se3_exp(xi, comps=1, dirs=None, pairs=None):
+    """se3Exp (KinectFusionReconstruction.h:176-219) on batched jets.  xi: [(1 + ncomp), 6] = (v, omega) with component 0 real
+    and the rest h-scaled derivative components (comps / dirs / pairs as for SetYamlParameters).  Returns [(1 + ncomp), 4, 4]."""
+    x = np.ascontiguousarray(xi, np.float32).reshape(-1, 6)
+    ncomp = x.shape[0] - 1
+    if comps == 2:
+        if dirs is None:
+            dirs = ncomp - len(pairs) if pairs is not None else int(round((np.sqrt(9 + 8 * ncomp) - 3) / 2))
+        plist = all_pairs(dirs) if pairs is None else list(pairs)
+        pa = np.ascontiguousarray(np.asarray(plist, np.int32).reshape(-1, 2))
+        pp, npairs = pa.ctypes.data_as(C.POINTER(C.c_int)), len(plist)
+    else:
+        dirs = ncomp // comps if dirs is None else dirs
+        pp, npairs = None, 0
+    out = np.zeros((1 + ncomp, 16), np.float32)
+    check(_capi.load().xs_se3_exp(x.ctypes.data_as(C.POINTER(C.c_float)), comps, dirs, npairs, pp, out.ctypes.data_as(C.POINTER(C.c_float))),
+          "se3_exp")
+    return out.reshape(-1, 4, 4)
+
+
 class _DeviceView:
     """Zero-copy view of library-owned device memory through the CUDA array interface."""
 
@@ -322,6 +342,18 @@ class KinectFusionReconstruction:
                                        C.c_void_p(nrm.data_ptr()), max_buffer, None)
         check(n, "ExportPointCloud")
         return pts[:n].cpu().numpy(), nrm[:n].cpu().numpy()
+
+    def set_comm(self, comm, record_floats):
+        """Multi-GPU: attach the library's communicator (parallel.Comm); every later frame all-gathers the ranks' records."""
+        self._comm = comm  # keep it alive
+        check(self.lib.xs_kinfu_set_comm(self.h, comm.h if comm is not None else None, int(record_floats)), "set_comm")
+        self._record_floats, self._world = int(record_floats), (comm.world if comm is not None else 1)
+
+    def gathered_records(self):
+        """[world, record_floats] float32: the records of the last processed frame, gathered by the library over NCCL."""
+        out = np.zeros((self._world, self._record_floats), np.float32)
+        check(self.lib.xs_kinfu_get_gathered_records(self.h, out.ctypes.data_as(C.POINTER(C.c_float))), "gathered_records")
+        return out
 
     def pose_record_device_ptr(self):
         return self.lib.xs_kinfu_pose_record_device(self.h)

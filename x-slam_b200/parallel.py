@@ -51,3 +51,73 @@ def real_parts_agree(gathered_out, atol=0.0):
     """Replica check: every rank must have produced the same real pose (rows 0 of the gathered records)."""
     ref = gathered_out[0, :16]
     return bool(((gathered_out[:, :16] - ref).abs() <= atol).all())
+
+
+# ------------------------------------------------------------------ in-library NCCL layer (csrc/comm.cpp)
+class Comm:
+    """The library's own communicator (xs_comm: NCCL bound at run time).  The 128-byte id of rank 0 reaches the other ranks
+    through whatever the launcher offers: torch.distributed (any backend), or a file for the C++ driver."""
+
+    def __init__(self, rank, world, uid):
+        import ctypes as C
+        from . import _capi
+        self.lib = _capi.load()
+        self.rank, self.world = rank, world
+        self.h = self.lib.xs_comm_create(rank, world, C.c_char_p(bytes(uid)))
+        if not self.h:
+            raise _capi.XsError("xs_comm_create: " + self.lib.xs_last_error().decode())
+
+    @staticmethod
+    def unique_id():
+        import ctypes as C
+        from . import _capi
+        buf = C.create_string_buffer(128)
+        _capi.check(_capi.load().xs_comm_unique_id(buf), "xs_comm_unique_id")
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, dist, device=None):
+        """Rank 0 draws the id, torch.distributed broadcasts it (gloo: CPU tensor, nccl: tensor on `device`)."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        t = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            t = torch.frombuffer(bytearray(cls.unique_id()), dtype=torch.uint8).clone()
+        if device is not None:
+            t = t.to(device)
+        dist.broadcast(t, 0)
+        return cls(rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    def close(self):
+        if self.h:
+            self.lib.xs_comm_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+def shard_pairs(pairs, rank, world):
+    """Second-order pairs owned by `rank` of a Hessian batch (round robin keeps every share sorted by i); every rank also
+    carries all first-order components."""
+    return list(pairs[rank::world])
+
+
+def hessian_record_floats(n_params, n_pairs, world):
+    """floats per rank in the gather: the largest record, (1 + n + ceil(m / world)) 4x4 matrices."""
+    return (1 + n_params + (n_pairs + world - 1) // world) * 16
+
+
+def assemble_hessian_records(gathered, n_params, pairs, world):
+    """gathered: [world, record_floats] (numpy or torch).  Returns the full record [(1 + n + m), 16] in the order of `pairs`:
+    the real part and the first-order components are replicated (rank 0's copy is taken), pair k lives on rank k % world."""
+    g = gathered.reshape(world, -1, 16)
+    full = g[0][: 1 + n_params + len(pairs)].clone() if hasattr(g, "clone") else g[0][: 1 + n_params + len(pairs)].copy()
+    full = full[: 1 + n_params]
+    rows = []
+    for k in range(len(pairs)):
+        r, local = k % world, k // world
+        rows.append(g[r][1 + n_params + local])
+    if hasattr(g, "clone"):
+        import torch
+        return torch.cat([full, torch.stack(rows)]) if rows else full
+    return np.concatenate([full, np.stack(rows)]) if rows else full
