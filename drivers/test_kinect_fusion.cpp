@@ -10,12 +10,18 @@
 //    commented seeding line KinectFusionReconstruction.cpp:22 — and log_pose_derivatives writes, next to every
 //    frame-%06d.pose.txt, frame-%06d.dpose.txt with one row of 16 values per derivative component (d world2camera
 //    / d theta, i.e. the stored h-scaled component divided by h, or by h^2 for eps1eps2);
-//  * when frame alignment fails the driver stops (the reference spins forever).
+//  * when frame alignment fails the driver stops (the reference spins forever);
+//  * multi-GPU: `test_kinect_fusion cfg.yaml out/ --rank R --world W --nccl-id FILE` runs one process per GPU (device R); the
+//    perturbation directions are sharded over the ranks - csfd_mode hessian: every rank carries the 6 first-order components
+//    and its share of the 21 pairs - and the library all-gathers the pose records over NCCL after every frame
+//    (xs_kinfu_set_comm).  Rank 0 draws the NCCL id into FILE, the other ranks wait for it; rank 0 writes the outputs, the
+//    derivative log then holds the gathered components of all ranks.
 #include "../include/xslam_b200.h"
 #include "flat_yaml.h"
 
 #include <algorithm>
 #include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <filesystem>
@@ -85,7 +91,48 @@ int main(int argc, char *argv[]) {
     const std::string dataset_format = config.str("dataset_format");
     const int start_frame = config.i("start_frame"), end_frame = config.i("end_frame");
     std::string output_path = config.str("output_dir");
-    if (argc > 2) output_path = argv[2];
+    if (argc > 2 && argv[2][0] != '-') output_path = argv[2];
+    int rank = 0, world = 1;
+    std::string id_file;
+    for (int a = 2; a + 1 < argc; ++a) {
+        if (!std::strcmp(argv[a], "--rank")) rank = std::atoi(argv[a + 1]);
+        if (!std::strcmp(argv[a], "--world")) world = std::atoi(argv[a + 1]);
+        if (!std::strcmp(argv[a], "--nccl-id")) id_file = argv[a + 1];
+    }
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && id_file.empty())) {
+        std::cerr << "usage: test_kinect_fusion cfg.yaml [out/] [--rank R --world W --nccl-id FILE]\n";
+        return -1;
+    }
+    xs_comm *comm = nullptr;
+    if (world > 1) {  // one process per GPU: device = rank; the NCCL id travels through a file
+        if (xs_set_device(rank) != XS_OK) {
+            std::cerr << "rank " << rank << ": " << xs_last_error() << "\n";
+            return -1;
+        }
+        unsigned char id[128];
+        if (rank == 0) {
+            if (xs_comm_unique_id(id) != XS_OK) {
+                std::cerr << "xs_comm_unique_id: " << xs_last_error() << "\n";
+                return -1;
+            }
+            std::ofstream f(id_file + ".tmp", std::ios::binary);
+            f.write((const char *) id, 128);
+            f.close();
+            std::filesystem::rename(id_file + ".tmp", id_file);
+        } else {
+            for (int tries = 0; !std::filesystem::exists(id_file) && tries < 600; ++tries) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+            std::ifstream f(id_file, std::ios::binary);
+            if (!f.read((char *) id, 128)) {
+                std::cerr << "rank " << rank << ": cannot read the NCCL id from " << id_file << "\n";
+                return -1;
+            }
+        }
+        comm = xs_comm_create(rank, world, id);
+        if (!comm) {
+            std::cerr << "xs_comm_create: " << xs_last_error() << "\n";
+            return -1;
+        }
+    }
     if (!output_path.empty() && output_path.back() != '/') output_path += '/';
     // dataset = ICL_Dataset(dataset_dir, start_frame, end_frame, is_flip), main.cpp:34
     xs_dataset *dataset = nullptr;
@@ -135,46 +182,64 @@ int main(int argc, char *argv[]) {
     }
     const xs_intr intr = {cfg.fx, cfg.fy, cfg.cx, cfg.cy};
 
-    // perturbation directions
+    // perturbation directions, sharded over the ranks (round robin)
     const std::string mode = config.str("csfd_mode", "none");
-    int comps = 1, dirs = 0;
+    int comps = 1, dirs = 0, ncomp = 0, ncomp_max = 0, nparams = 0;
     std::vector<float> seeds;
+    std::vector<int> my_pairs;  // hessian mode: (i, j) of this rank's share
+    xs_kinfu *kinfu = nullptr;
     if (mode == "gradient") {
-        comps = 1, dirs = 6;
-        seeds.assign((size_t) dirs * 16, 0.f);
+        comps = 1;
+        for (int i = rank; i < 6; i += world) {
+            float G[16];
+            generator(i, G);
+            for (int e = 0; e < 16; ++e) seeds.push_back(H_ * G[e]);
+            ++dirs;
+        }
+        ncomp = dirs;
+        ncomp_max = (6 + world - 1) / world;
+        kinfu = xs_kinfu_create(&cfg, 1, dirs, seeds.empty() ? nullptr : seeds.data(), XS_SOLVE_EIGEN_LLT);
+    } else if (mode == "hessian") {
+        // Hessian batch over the 6 pose parameters: first-order seeds h G_i, second-order seeds h^2 (G_i G_j + G_j G_i) / 2
+        comps = 2, nparams = dirs = 6;
         for (int i = 0; i < 6; ++i) {
             float G[16];
             generator(i, G);
-            for (int e = 0; e < 16; ++e) seeds[(size_t) i * 16 + e] = H_ * G[e];
+            for (int e = 0; e < 16; ++e) seeds.push_back(H_ * G[e]);
         }
-    } else if (mode == "hessian") {
-        comps = 3, dirs = 21;
-        seeds.assign((size_t) dirs * 3 * 16, 0.f);
         int k = 0;
         for (int i = 0; i < 6; ++i)
             for (int j = i; j < 6; ++j, ++k) {
+                if (k % world != rank) continue;
                 float Gi[16], Gj[16], GiGj[16], GjGi[16];
                 generator(i, Gi), generator(j, Gj);
                 mul4(Gi, Gj, GiGj), mul4(Gj, Gi, GjGi);
-                for (int e = 0; e < 16; ++e) {
-                    seeds[((size_t) k * 3 + 0) * 16 + e] = H_ * Gi[e];
-                    seeds[((size_t) k * 3 + 1) * 16 + e] = H_ * Gj[e];
-                    seeds[((size_t) k * 3 + 2) * 16 + e] = H_ * H_ * 0.5f * (GiGj[e] + GjGi[e]);
-                }
+                for (int e = 0; e < 16; ++e) seeds.push_back(H_ * H_ * 0.5f * (GiGj[e] + GjGi[e]));
+                my_pairs.push_back(i);
+                my_pairs.push_back(j);
             }
-    } else if (mode != "none") {
+        ncomp = 6 + (int) my_pairs.size() / 2;
+        ncomp_max = 6 + (21 + world - 1) / world;
+        kinfu = xs_kinfu_create_hessian(&cfg, 6, (int) my_pairs.size() / 2, my_pairs.data(), seeds.data(), XS_SOLVE_ANALYTIC);
+    } else if (mode == "none") {
+        kinfu = xs_kinfu_create(&cfg, 1, 0, nullptr, XS_SOLVE_EIGEN_LLT);
+    } else {
         std::cerr << "csfd_mode must be none, gradient or hessian\n";
         return -1;
     }
-    xs_kinfu *kinfu = xs_kinfu_create(&cfg, comps, dirs, seeds.empty() ? nullptr : seeds.data(),
-                                      comps == 1 ? XS_SOLVE_EIGEN_LLT : XS_SOLVE_ANALYTIC);
     if (!kinfu) {
         std::cerr << "initialisation failed: " << xs_last_error() << "\n";
         return -1;
     }
-    const bool log_slam = config.b("log_slam_pose"), log_gt = config.b("log_gt_pose"), draw_pcd = config.b("draw_pcd");
-    const bool log_deriv = config.b("log_pose_derivatives", false) && dirs > 0;
-    const int ncomp = comps * dirs;
+    const int record_floats = (1 + ncomp_max) * 16;
+    if (comm && xs_kinfu_set_comm(kinfu, comm, record_floats) != XS_OK) {
+        std::cerr << "xs_kinfu_set_comm: " << xs_last_error() << "\n";
+        return -1;
+    }
+    const bool writer = rank == 0;  // rank 0 writes the outputs
+    const bool log_slam = config.b("log_slam_pose") && writer, log_gt = config.b("log_gt_pose") && writer, draw_pcd = config.b("draw_pcd") && writer;
+    const bool log_deriv = config.b("log_pose_derivatives", false) && mode != "none" && writer;
+    std::vector<float> gathered((size_t) world * record_floats);
     double total_time = 0;
     std::cout << "start slam!" << std::endl;
     std::vector<uint16_t> depth((size_t) cfg.width * cfg.height);
@@ -227,15 +292,27 @@ int main(int argc, char *argv[]) {
             savePose(output_path + "gt/", frame_id, gt_c2w);
         }
         if (log_deriv) {
+            // one row per derivative component of world2camera, unscaled (d / d theta_i, then d2 / d theta_i d theta_j in the
+            // order of the pair list): this rank's own record, or with several ranks the records the library gathered
             std::filesystem::create_directories(output_path + "slam/");
-            xs_kinfu_get_world2camera(kinfu, w2c.data());
             std::stringstream ss;
             ss << output_path << "slam/frame-" << std::setw(6) << std::setfill('0') << frame_id << ".dpose.txt";
             std::ofstream out(ss.str());
-            for (int q = 0; q < ncomp; ++q) {
-                const double scale = (comps == 3 && q % 3 == 2) ? 1.0 / ((double) H_ * H_) : 1.0 / H_;
-                for (int e = 0; e < 16; ++e) out << std::setprecision(7) << std::scientific << w2c[(size_t) (1 + q) * 16 + e] * scale << " ";
+            auto row = [&](const float *m, double scale) {
+                for (int e = 0; e < 16; ++e) out << std::setprecision(7) << std::scientific << m[e] * scale << " ";
                 out << "\n";
+            };
+            if (!comm) {
+                xs_kinfu_get_world2camera(kinfu, w2c.data());
+                for (int q = 0; q < ncomp; ++q) row(&w2c[(size_t) (1 + q) * 16], comps == 2 && q >= nparams ? 1.0 / ((double) H_ * H_) : 1.0 / H_);
+            } else {
+                xs_kinfu_get_gathered_records(kinfu, gathered.data());
+                if (comps == 2) {
+                    for (int i = 0; i < 6; ++i) row(&gathered[(size_t) (1 + i) * 16], 1.0 / H_);
+                    for (int k = 0; k < 21; ++k) row(&gathered[(size_t) (k % world) * record_floats + (size_t) (1 + 6 + k / world) * 16], 1.0 / ((double) H_ * H_));
+                } else {
+                    for (int i = 0; i < 6; ++i) row(&gathered[(size_t) (i % world) * record_floats + (size_t) (1 + i / world) * 16], 1.0 / H_);
+                }
             }
         }
         if (draw_pcd && frame_id + cfg.frame_step >= last_frame) {
@@ -262,6 +339,7 @@ int main(int argc, char *argv[]) {
     const int frames = (xs_kinfu_frame_id(kinfu) + cfg.frame_step - 1) / cfg.frame_step;  // frames processed
     printf("mean frame time = %.3f ms\n", total_time / (frames > 0 ? frames : 1));
     xs_kinfu_destroy(kinfu);
+    xs_comm_destroy(comm);
     xs_dataset_close(dataset);
     return 0;
 }

@@ -1586,7 +1586,8 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
     // chains with a solve; the ICP log and accumulate-only calls want the full A_ij, b_ij
     static const int h_full = env_int("XS_ICP_H_FULL", 0);  // A/B knob
     const bool h_reduced = hessian && split && d_log == nullptr && !h_full;
-    const int hp = h_reduced ? 3 : 2;
+    static const int red_hp = env_int("XS_ICP_H_RED_HP", 2);  // pairs per task of the reduced form: 2 measured faster than 3 (profiles/r02_ab_table.md)
+    const int hp = h_reduced ? (red_hp == 2 ? 2 : 3) : 2;
     if (hessian && (g_icp.htasks_key != (const void *) batch.pairs || !g_icp.d_htasks || g_icp.htasks_hp != hp)) {
         // task table: one task per parameter (first-order sums), then the pairs in runs of up to hp that share their first parameter
         std::vector<HTask> tasks;
@@ -1700,7 +1701,8 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
         const int stages = stages_env == 3 ? 3 : 2;
         if (no_tail && split) S.pose_out = nullptr;
         if (hessian)
-            rc = h_reduced ? launch_deriv_h<2, 2, 3, true>(P, S, deriv_grid, s) : launch_deriv_h<2, 2, 2, false>(P, S, deriv_grid, s);
+            rc = h_reduced ? (hp == 2 ? launch_deriv_h<2, 2, 2, true>(P, S, deriv_grid, s) : launch_deriv_h<2, 2, 3, true>(P, S, deriv_grid, s))
+                           : launch_deriv_h<2, 2, 2, false>(P, S, deriv_grid, s);
         else if (comps == 1)
             rc = stages == 2 ? launch_deriv<1, 2>(P, S, deriv_grid, s) : launch_deriv<1, DERIV_MAX_STAGES>(P, S, deriv_grid, s);
         else

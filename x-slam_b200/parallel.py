@@ -121,3 +121,15 @@ def assemble_hessian_records(gathered, n_params, pairs, world):
         import torch
         return torch.cat([full, torch.stack(rows)]) if rows else full
     return np.concatenate([full, np.stack(rows)]) if rows else full
+
+
+def assemble_list_records(gathered, n_dirs, comps, world):
+    """gathered: [world, record_floats] of a CSFD / DCSFD list run sharded round robin (direction d on rank d % world at local
+    index d // world).  Returns the full record [(1 + n_dirs * comps), 16]."""
+    g = np.asarray(gathered).reshape(world, -1, 16)
+    rows = [g[0][0]]
+    for d in range(n_dirs):
+        r, local = d % world, d // world
+        for c in range(comps):
+            rows.append(g[r][1 + local * comps + c])
+    return np.stack(rows)
