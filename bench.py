@@ -43,6 +43,9 @@ def parse():
                     help="how the DCSFD workload is carried: hessian (default) = Hessian-structured batch, n first-order + one "
                          "second-order plane per parameter pair (65 planes for the 55 pairs of 10 parameters); dcsfd = the same 55 "
                          "pairs as independent bicomplex directions (165 planes, round 1's layout); csfd = first-order directions")
+    ap.add_argument("--pose-only", action="store_true",
+                    help="hessian / dcsfd mode: the parameters beyond the 6 pose DoF are mixed pose-space directions instead of the "
+                         "intrinsics fx, fy, cx, cy (round 1's workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-frames", action="store_true",
                     help="ProcessFrame waits for the end of each frame like the reference's (default: deferred mode, the "
@@ -79,16 +82,24 @@ def all_directions(xs, comps, dirs):
     return out.reshape(-1, 16).astype(np.float32)
 
 
-def hessian_params(dirs):
-    """The parameters whose Hessian the DCSFD workload asks for: n with n (n + 1) / 2 = dirs (10 for 55 pairs): the 6 pose axes,
-    then deterministic mixed pose-space directions (intrinsic parameters are not seedable in the reference: Intr is plain
-    floats, Internal.h:49-59).  Returns (U [n, 6], pairs)."""
+def hessian_params(dirs, intrinsics=True):
+    """The parameters whose Hessian the DCSFD workload asks for: n with n (n + 1) / 2 = dirs (10 for 55 pairs).  BASELINE.json
+    configs[3] names them: the 6 pose DoF (se3Exp coordinates) + the 4 intrinsics fx, fy, cx, cy.  With intrinsics=False the
+    parameters beyond the sixth are deterministic mixed pose-space directions instead (round 1's workload).
+    Returns (U [n, 6] pose-space directions, pairs, intrinsic seeds [n, 4] or None)."""
     n = int(round((np.sqrt(8 * dirs + 1) - 1) / 2))
     if n * (n + 1) // 2 != dirs:
         raise SystemExit("--mode hessian needs --dirs = n (n + 1) / 2 (21, 55, ...)")
+    pairs = [(i, j) for i in range(n) for j in range(i, n)]
+    if intrinsics and n > 6:
+        U = np.concatenate([np.eye(6), np.zeros((n - 6, 6))])[:n]
+        di = np.zeros((n, 4), np.float32)
+        for p in range(6, min(n, 10)):
+            di[p, p - 6] = H_STEP  # fx, fy, cx, cy
+        return U, pairs, di
     rng = np.random.default_rng(7)
     U = np.concatenate([np.eye(6), rng.standard_normal((max(n - 6, 0), 6)) / np.sqrt(6)])[:n]
-    return U, [(i, j) for i in range(n) for j in range(i, n)]
+    return U, pairs, None
 
 
 class ClockSampler(threading.Thread):
@@ -348,17 +359,17 @@ def run_ours(args, xs, rank, world, local_rank):
     max_dirs = (args.dirs + world - 1) // world
     if mode == "hessian":
         # every rank carries the n first-order components (cheap, and every pair needs two of them) and its share of the pairs
-        U, pairs = hessian_params(args.dirs)
+        U, pairs, dintr = hessian_params(args.dirs, intrinsics=not args.pose_only)
         n_params = U.shape[0]
         my_pairs = pairs[rank::world]
         my_seeds, _ = xs.hessian_seeds(U, my_pairs)
-        k.SetYamlParameters(cfg, comps=2, seeds=my_seeds, pairs=my_pairs, n_params=n_params)
+        k.SetYamlParameters(cfg, comps=2, seeds=my_seeds, pairs=my_pairs, n_params=n_params, intrinsic_seeds=dintr)
         ncomp_local, ncomp_max = n_params + len(my_pairs), n_params + max_dirs
         planes_total = n_params + len(pairs)
     else:
         comps = 1 if mode == "csfd" else 3
         if mode == "dcsfd":  # the pairs of the same parameters as independent bicomplex directions (eps1, eps2, eps1eps2)
-            U, pairs = hessian_params(args.dirs)
+            U, pairs, _ = hessian_params(args.dirs, intrinsics=False)  # a DCSFD list cannot carry intrinsic parameters
             G = np.tensordot(U, xs.se3_generators(), 1)
             seeds = np.zeros((args.dirs, 3, 16))
             for d, (i, j) in enumerate(pairs):
@@ -519,6 +530,8 @@ def run_ours(args, xs, rank, world, local_rank):
         "config": {"workload": "icl_synth_640x480_tsdf%d_dcsfd%d" % (args.res, args.dirs), "step": "one batch of %d consecutive depth frames, each one ProcessFrame" % FPS,
                    "depth": "640x480 uint16 mm",
                    "tsdf": "%d^3 @ %.4f m" % (args.res, 7.68 / args.res), "directions": args.dirs, "batch": BATCH_NOTE[mode],
+                   "parameters": ("6 pose DoF + fx, fy, cx, cy" if (mode == "hessian" and not args.pose_only and args.dirs == 55)
+                                  else "pose-space directions") if mode != "csfd" else "pose-space directions",
                    "derivative_planes": planes_total, "derivative_planes_rank0": ncomp_local, "directions_per_rank": max_dirs,
                    "sharding": "second-order pairs over ranks, first-order components and real state replicated" if mode == "hessian"
                                else "directions over ranks, real state replicated",

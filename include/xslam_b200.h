@@ -124,6 +124,8 @@ typedef struct xs_volume xs_volume;
 xs_volume *xs_volume_create(const int res[3], float voxel_size, float thres_range, int comps, int dirs);
 /* Hessian batch (comps = 2) with an explicit pair list: pairs = int[npairs][2], 0 <= i <= j < nparams, sorted by i (NULL: all) */
 xs_volume *xs_volume_create_hessian(const int res[3], float voxel_size, float thres_range, int nparams, int npairs, const int *pairs);
+/* parameters of a Hessian batch that move the intrinsics: dintr[nparams][4] = h d(fx, fy, cx, cy) / d theta_p (see xs_kinfu_set_intrinsic_seeds) */
+int xs_volume_set_intrinsic_seeds(xs_volume *v, const float *dintr);
 void xs_volume_destroy(xs_volume *v);
 /* initVolume, TsdfVolume.h:16 / TsdfFusion.cu:34 */
 int xs_volume_reset(xs_volume *v, void *stream);
@@ -235,6 +237,15 @@ xs_kinfu *xs_kinfu_create(const xs_config *cfg, int comps, int dirs, const float
  * parameters, h^2 (G_i G_j + G_j G_i) / 2 for the pairs when the parameters are se3Exp coordinates. */
 xs_kinfu *xs_kinfu_create_hessian(const xs_config *cfg, int nparams, int npairs, const int *pairs, const float *seeds, int solve_mode);
 void xs_kinfu_destroy(xs_kinfu *k);
+/* Intrinsic parameters (BASELINE.json configs[3]: Hessian w.r.t. pose + intrinsics; new behaviour, the reference's Intr is plain
+ * floats, Internal.h:49-59).  Hessian batches only, before the first frame: dintr[nparams][4] = h d(fx, fy, cx, cy) / d theta_p for
+ * every parameter (zero rows for pure pose parameters).  The current-frame vertex / normal maps then carry derivative components
+ * for these parameters and their pairs (xs_kinfu_map reports them), the ICP and the raycast differentiate through them.  With
+ * biInterpolate_threshold = 0 the TSDF integration does not depend on the intrinsics; the bilinear branch is rejected. */
+int xs_kinfu_set_intrinsic_seeds(xs_kinfu *k, const float *dintr);
+/* stores the derivative components of the current-frame vertex / normal maps (xs_kinfu_map, which = 1, 2) - the frame loop itself
+ * forms them on the fly, so they are kept only on request; before the first frame, after xs_kinfu_set_intrinsic_seeds */
+int xs_kinfu_keep_current_map_derivatives(xs_kinfu *k, int on);
 /* ProcessFrame, KinectFusionReconstruction.cpp:147-159.  depth: 640x480 uint16 mm, dense; host pointer
  * unless depth_on_device != 0.  Returns 1 on success, 0 when frame alignment failed (as the reference). */
 int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_device);

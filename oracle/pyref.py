@@ -392,6 +392,10 @@ class Oracle:
         tf = tf.reshape(3, 2)
         return ok, (Rf[:, 0] + 1j * Rf[:, 1]).reshape(3, 3).astype(np.complex64), (tf[:, 0] + 1j * tf[:, 1]).astype(np.complex64)
 
+    def set_intrinsic_imag(self, fx0, dfx=0.0, dfy=0.0, dcx=0.0, dcy=0.0):
+        """Complex intrinsics for the following calls (an extension: see oracle/xslam_oracle.cpp complex_intr)."""
+        self.lib.oracle_set_intrinsic_imag(C.c_float(fx0), C.c_float(dfx), C.c_float(dfy), C.c_float(dcx), C.c_float(dcy))
+
     def llt_solve6(self, A, b):
         """The restated Eigen LLT (lower, Hermitian semantics) solve alone; A: [6, 6] complex, b: [6] complex."""
         Ac = np.ascontiguousarray(np.stack([A.T.real, A.T.imag], -1), np.float64)  # column-major

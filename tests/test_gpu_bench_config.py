@@ -33,7 +33,7 @@ def test_bench_workload_first_order_vs_reference_512(xs, refcuda, out_dir):
     pass of the reference's kernels seeded with h G_p."""
     import bench
     cfg = bench.workload_cfg(xs, 512)
-    U, pairs = bench.hessian_params(55)
+    U, pairs, _ = bench.hessian_params(55, intrinsics=False)
     n = U.shape[0]
     seeds, _ = xs.hessian_seeds(U, pairs)
     frames = [xs.synth_depth(f) for f in range(3)]

@@ -86,6 +86,9 @@ SYMBOLS = {
     "xs_compute_optimize_matrix": (_l, [_PP, _vp, _vp, _PP, Intr, _vp, _vp, _i, _i, _f, _f, _pd, _pd, _vp]),
     "xs_kinfu_create": (_vp, [C.POINTER(Config), _i, _i, _pf, _i]),
     "xs_kinfu_create_hessian": (_vp, [C.POINTER(Config), _i, _i, _pi, _pf, _i]),
+    "xs_kinfu_set_intrinsic_seeds": (_i, [_vp, _pf]),
+    "xs_kinfu_keep_current_map_derivatives": (_i, [_vp, _i]),
+    "xs_volume_set_intrinsic_seeds": (_i, [_vp, _pf]),
     "xs_kinfu_destroy": (None, [_vp]),
     "xs_kinfu_process_frame": (_i, [_vp, _vp, _i]),
     "xs_kinfu_set_deferred": (_i, [_vp, _i]),

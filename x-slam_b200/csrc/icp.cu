@@ -985,16 +985,24 @@ XS_DEV void accumulate_pair(float *acc, const float (&r)[7], const float (&d0)[7
      ...);
 }
 // rho-type contraction of a row (or of a row's derivative) with the solution: v_6 - sum_j v_j x_j
+// rotation part of a pose component (row-major in three float4: R (9), t (3)) times a 3-vector, added to o
+XS_DEV void rot_add(const float4 *mm4, const float (&v)[3], float (&o)[3]) {
+    const float4 m0 = mm4[0], m1 = mm4[1], m2 = mm4[2];
+    o[0] += fmaf(m0.x, v[0], fmaf(m0.y, v[1], m0.z * v[2]));
+    o[1] += fmaf(m0.w, v[0], fmaf(m1.x, v[1], m1.y * v[2]));
+    o[2] += fmaf(m1.z, v[0], fmaf(m1.w, v[1], m2.x * v[2]));
+}
 XS_DEV float rho_of(const float (&v)[7], const float (&x)[6]) {
     return v[6] - fmaf(v[0], x[0], fmaf(v[1], x[1], fmaf(v[2], x[2], fmaf(v[3], x[3], fmaf(v[4], x[4], v[5] * x[5])))));
 }
 // derivative of the row [s x n, n, n . e] for one component: ds = dpose * vc + dt, (dn, dv) gathered at the matched pixel
+// (ex: what the derivative of the current-frame vertex adds to ds when a parameter moves the intrinsics: R dvc + cross terms)
 XS_DEV void row_first(const float4 *mm4, const float (&vc)[3], const float (&sv)[3], const float (&nv)[3], const float (&ev)[3],
-                      const float (&dn)[3], const float (&dv)[3], float (&ds)[3], float (&de)[3], float (&d)[7]) {
+                      const float (&dn)[3], const float (&dv)[3], const float (&ex)[3], float (&ds)[3], float (&de)[3], float (&d)[7]) {
     const float4 m0 = mm4[0], m1 = mm4[1], m2 = mm4[2];  // R row-major (9), t (3): broadcast 128-bit shared loads
-    ds[0] = fmaf(m0.x, vc[0], fmaf(m0.y, vc[1], fmaf(m0.z, vc[2], m2.y)));
-    ds[1] = fmaf(m0.w, vc[0], fmaf(m1.x, vc[1], fmaf(m1.y, vc[2], m2.z)));
-    ds[2] = fmaf(m1.z, vc[0], fmaf(m1.w, vc[1], fmaf(m2.x, vc[2], m2.w)));
+    ds[0] = fmaf(m0.x, vc[0], fmaf(m0.y, vc[1], fmaf(m0.z, vc[2], m2.y))) + ex[0];
+    ds[1] = fmaf(m0.w, vc[0], fmaf(m1.x, vc[1], fmaf(m1.y, vc[2], m2.z))) + ex[1];
+    ds[2] = fmaf(m1.z, vc[0], fmaf(m1.w, vc[1], fmaf(m2.x, vc[2], m2.w))) + ex[2];
 #pragma unroll
     for (int c = 0; c < 3; ++c) de[c] = dv[c] - ds[c];
     cross3(ds, nv, d);  // d(s x n) = ds x n + s x dn
@@ -1005,13 +1013,21 @@ XS_DEV void row_first(const float4 *mm4, const float (&vc)[3], const float (&sv)
     d[6] = dot3(dn, ev) + dot3(nv, de);  // d(n . (d - s))
 }
 
-template <int ST, int MINB, int HPK, bool REDUCED>
+// CURR: some parameter moves the intrinsics, so the current-frame vertex has derivative components (xs_batch.h):
+// s = R vc + t then has d s = dR vc + dt + R dvc, and for a pair also dR_i dvc_j + dR_j dvc_i.  The components of vc are not
+// read from memory: with vx = z (u - cx) / fx (Map.cu:19-21) they are linear in the real vertex,
+//   F_p(vx) = -(dcx_p z + dfx_p vx) / fx,   S_ij(vx) = ((dcx_i dfx_j + dcx_j dfx_i) z + 2 dfx_i dfx_j vx) / fx^2,   d vz = 0
+// (vy likewise), with coefficients that are the same at every pyramid level (seed and focal length scale together) and are
+// formed once per task (s_cur).
+template <int ST, int MINB, int HPK, bool REDUCED, bool CURR>
 __global__ void __launch_bounds__(256, MINB) icp_deriv_h_kernel(const IcpParams P, const SolveParams S) {
     constexpr int IN = deriv_h_in(HPK);
     constexpr int NACC = REDUCED ? (HPK * 6 > 27 ? HPK * 6 : 27) : HPK * 27;  // accumulators per thread
     constexpr int NPART = REDUCED ? 27 : HPK * 27;                             // values of a (task, writer) partial
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ float4 s_pose[1 + 2 * HPK][3];  // F_i | F_j0, S_0 | F_j1, S_1 | ...
+    __shared__ float4 s_real_pose[3];          // CURR: the real current pose
+    __shared__ float4 s_cur[1 + 2 * HPK];      // CURR: d vc = (x z + y vx, z z + w vy, 0) per gather slot
     __shared__ float s_x[6];
     __shared__ bool s_last, s_final;
     float *s_in = reinterpret_cast<float *>(s_raw);  // [stage][IN][256]
@@ -1027,6 +1043,7 @@ __global__ void __launch_bounds__(256, MINB) icp_deriv_h_kernel(const IcpParams 
     const long long U = (long long) P.groups * P.chunks, B = gridDim.x;
     const long long u_begin = blockIdx.x * U / B, u_end = (blockIdx.x + 1) * U / B;
     if (REDUCED && tid < 6) s_x[tid] = (float) __ldcg(S.real_cache + 42 + tid);  // real solution of this iteration (the real step has completed)
+    if (CURR && tid >= 32 && tid < 44) reinterpret_cast<float *>(&s_real_pose[0])[tid - 32] = P.pose_curr[tid - 32];
     bool final_cta = false;
     for (long long u = u_begin; u < u_end;) {
         const int task = (int) (u / P.chunks), c_begin = (int) (u % P.chunks);
@@ -1038,6 +1055,15 @@ __global__ void __launch_bounds__(256, MINB) icp_deriv_h_kernel(const IcpParams 
         int cj[HPK], cs[HPK];
 #pragma unroll
         for (int h = 0; h < HPK; ++h) cj[h] = T.j[h], cs[h] = T.s[h];
+        // CURR: slots of these components in the current-frame derivative maps (-1: identically zero)
+        int ki = -1, kj[HPK], ks[HPK];
+#pragma unroll
+        for (int h = 0; h < HPK; ++h) kj[h] = ks[h] = -1;
+        if (CURR) {
+            ki = __ldg(P.batch.cslot + ci);
+#pragma unroll
+            for (int h = 0; h < HPK; ++h) kj[h] = __ldg(P.batch.cslot + cj[h]), ks[h] = __ldg(P.batch.cslot + cs[h]);
+        }
         __syncthreads();  // s_pose / s_tot of the previous segment are no longer read
         if (tid < 12 * (1 + 2 * HPK)) {
             const int a = tid / 12, e = tid % 12;
@@ -1048,6 +1074,24 @@ __global__ void __launch_bounds__(256, MINB) icp_deriv_h_kernel(const IcpParams 
                 if (a == 2 + 2 * h) ca = cs[h];
             }
             reinterpret_cast<float *>(&s_pose[a][0])[e] = P.pose_curr[(size_t) (1 + ca) * 12 + e];
+        }
+        if (CURR && tid >= 128 && tid < 128 + 1 + 2 * HPK) {
+            const int a = tid - 128;
+            const float4 *din = reinterpret_cast<const float4 *>(P.batch.dintr);  // (dfx, dfy, dcx, dcy) at level 0
+            const float gx = P.batch.gx0, gy = P.batch.gy0;
+            const float4 di = __ldg(din + ci);
+            float4 o = make_float4(-di.z * gx, -di.x * gx, -di.w * gy, -di.y * gy);
+#pragma unroll
+            for (int h = 0; h < HPK; ++h) {
+                if (h < np) {
+                    const float4 dj = __ldg(din + cj[h]);
+                    if (a == 1 + 2 * h) o = make_float4(-dj.z * gx, -dj.x * gx, -dj.w * gy, -dj.y * gy);
+                    if (a == 2 + 2 * h)
+                        o = make_float4((di.z * dj.x + dj.z * di.x) * gx * gx, 2.f * di.x * dj.x * gx * gx, (di.w * dj.y + dj.w * di.y) * gy * gy,
+                                        2.f * di.y * dj.y * gy * gy);
+                }
+            }
+            s_cur[a] = o;
         }
 #pragma unroll
         for (int h = 0; h < (REDUCED ? 1 : HPK); ++h) s_tot[h * 256 + tid] = 0.0;
@@ -1154,9 +1198,19 @@ __global__ void __launch_bounds__(256, MINB) icp_deriv_h_kernel(const IcpParams 
                         dv[c] = in[(12 + slot * 6 + 3 + c) * 256];
                     }
                 };
-                float dn0[3], dv0[3], ds0[3], de0[3], d0[7];
+                auto load_dvc = [&](int a, float (&o)[3]) {  // derivative of the current-frame vertex for gather slot a
+                    const float4 k = s_cur[a];
+                    o[0] = fmaf(k.x, vc[2], k.y * vc[0]);
+                    o[1] = fmaf(k.z, vc[2], k.w * vc[1]);
+                    o[2] = 0.f;
+                };
+                float dn0[3], dv0[3], ds0[3], de0[3], d0[7], ex0[3] = {0.f, 0.f, 0.f}, dvc0[3] = {0.f, 0.f, 0.f};
                 load6(0, dn0, dv0);
-                row_first(s_pose[0], vc, sv, nv, ev, dn0, dv0, ds0, de0, d0);
+                if (CURR && ki >= 0) {  // block-uniform
+                    load_dvc(0, dvc0);
+                    rot_add(s_real_pose, dvc0, ex0);
+                }
+                row_first(s_pose[0], vc, sv, nv, ev, dn0, dv0, ex0, ds0, de0, d0);
                 if (np == 0) {
                     accumulate_first(acc, r, d0, std::make_integer_sequence<int, 27>());
                 } else {
@@ -1165,10 +1219,24 @@ __global__ void __launch_bounds__(256, MINB) icp_deriv_h_kernel(const IcpParams 
                     for (int h = 0; h < HPK; ++h) {
                         if (h < np) {  // block-uniform
                             float dn1[3], dv1[3], ds1[3], de1[3], d1[7], dn2[3], dv2[3], ds2[3], de2[3], d2[7];
+                            float ex1[3] = {0.f, 0.f, 0.f}, ex2[3] = {0.f, 0.f, 0.f};
+                            if (CURR) {
+                                float dvc1[3] = {0.f, 0.f, 0.f}, dvc2[3];
+                                if (kj[h] >= 0) {  // block-uniform
+                                    load_dvc(1 + 2 * h, dvc1);
+                                    rot_add(s_real_pose, dvc1, ex1);
+                                    rot_add(s_pose[0], dvc1, ex2);  // dR_i dvc_j
+                                }
+                                if (ki >= 0) rot_add(s_pose[1 + 2 * h], dvc0, ex2);  // dR_j dvc_i
+                                if (ks[h] >= 0) {
+                                    load_dvc(2 + 2 * h, dvc2);
+                                    rot_add(s_real_pose, dvc2, ex2);
+                                }
+                            }
                             load6(1 + 2 * h, dn1, dv1);
-                            row_first(s_pose[1 + 2 * h], vc, sv, nv, ev, dn1, dv1, ds1, de1, d1);
+                            row_first(s_pose[1 + 2 * h], vc, sv, nv, ev, dn1, dv1, ex1, ds1, de1, d1);
                             load6(2 + 2 * h, dn2, dv2);
-                            row_first(s_pose[2 + 2 * h], vc, sv, nv, ev, dn2, dv2, ds2, de2, d2);
+                            row_first(s_pose[2 + 2 * h], vc, sv, nv, ev, dn2, dv2, ex2, ds2, de2, d2);
                             cross3_add(ds0, dn1, d2);  // second-order cross terms of the row
                             cross3_add(ds1, dn0, d2);
                             d2[6] += dot3(dn0, de1) + dot3(dn1, de0);
@@ -1543,14 +1611,14 @@ template <int C, int ST> static int launch_deriv(const IcpParams &P, const Solve
     return XS_OK;
 }
 
-template <int ST, int MINB, int HPK, bool REDUCED> static int launch_deriv_h(const IcpParams &P, const SolveParams &S, int grid, cudaStream_t s) {
+template <int ST, int MINB, int HPK, bool REDUCED, bool CURR> static int launch_deriv_h(const IcpParams &P, const SolveParams &S, int grid, cudaStream_t s) {
     static bool smem_set = false;
     if (!smem_set) {
-        XS_CUDA(cudaFuncSetAttribute(icp_deriv_h_kernel<ST, MINB, HPK, REDUCED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        XS_CUDA(cudaFuncSetAttribute(icp_deriv_h_kernel<ST, MINB, HPK, REDUCED, CURR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int) deriv_h_smem(ST, HPK, REDUCED)));
         smem_set = true;
     }
-    icp_deriv_h_kernel<ST, MINB, HPK, REDUCED><<<grid, 256, deriv_h_smem(ST, HPK, REDUCED), s>>>(P, S);
+    icp_deriv_h_kernel<ST, MINB, HPK, REDUCED, CURR><<<grid, 256, deriv_h_smem(ST, HPK, REDUCED), s>>>(P, S);
     XS_LAUNCH_CHECK();
     return XS_OK;
 }
@@ -1587,7 +1655,7 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
     static const int h_full = env_int("XS_ICP_H_FULL", 0);  // A/B knob
     const bool h_reduced = hessian && split && d_log == nullptr && !h_full;
     static const int red_hp = env_int("XS_ICP_H_RED_HP", 2);  // pairs per task of the reduced form: 2 measured faster than 3 (profiles/r02_ab_table.md)
-    const int hp = h_reduced ? (red_hp == 2 ? 2 : 3) : 2;
+    const int hp = h_reduced ? ((red_hp == 2 || batch.ncurr > 0) ? 2 : 3) : 2;
     if (hessian && (g_icp.htasks_key != (const void *) batch.pairs || !g_icp.d_htasks || g_icp.htasks_hp != hp)) {
         // task table: one task per parameter (first-order sums), then the pairs in runs of up to hp that share their first parameter
         std::vector<HTask> tasks;
@@ -1701,8 +1769,13 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
         const int stages = stages_env == 3 ? 3 : 2;
         if (no_tail && split) S.pose_out = nullptr;
         if (hessian)
-            rc = h_reduced ? (hp == 2 ? launch_deriv_h<2, 2, 2, true>(P, S, deriv_grid, s) : launch_deriv_h<2, 2, 3, true>(P, S, deriv_grid, s))
-                           : launch_deriv_h<2, 2, 2, false>(P, S, deriv_grid, s);
+        {
+            if (batch.ncurr > 0)  // a parameter moves the intrinsics: the current-frame maps carry derivative components
+                rc = h_reduced ? launch_deriv_h<2, 2, 2, true, true>(P, S, deriv_grid, s) : launch_deriv_h<2, 2, 2, false, true>(P, S, deriv_grid, s);
+            else
+                rc = h_reduced ? (hp == 2 ? launch_deriv_h<2, 2, 2, true, false>(P, S, deriv_grid, s) : launch_deriv_h<2, 2, 3, true, false>(P, S, deriv_grid, s))
+                               : launch_deriv_h<2, 2, 2, false, false>(P, S, deriv_grid, s);
+        }
         else if (comps == 1)
             rc = stages == 2 ? launch_deriv<1, 2>(P, S, deriv_grid, s) : launch_deriv<1, DERIV_MAX_STAGES>(P, S, deriv_grid, s);
         else

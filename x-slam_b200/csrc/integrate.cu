@@ -514,6 +514,12 @@ int xs_volume_reset(xs_volume *v, void *stream) {
     return XS_OK;
 }
 
+// intrinsic parameters of a Hessian batch (xs_batch.h): the raycast then differentiates the pixel ray as well
+int xs_volume_set_intrinsic_seeds(xs_volume *v, const float *dintr) {
+    if (!v) return XS_ERR_ARG;
+    return batch_set_intrinsics(v->batch, dintr, 1.f, 1.f);  // the raycast takes 1 / fx, 1 / fy from its own intrinsics argument
+}
+
 float xs_volume_trunc_dist(const xs_volume *v) { return v ? v->view.trunc : 0.f; }
 size_t xs_volume_bytes(const xs_volume *v) { return v ? v->bytes : 0; }
 float xs_volume_last_integrate_ms(const xs_volume *v) { return v ? v->last_kernel_ms : 0.f; }
@@ -548,6 +554,9 @@ int batch_init(Batch &b, int comps, int dirs, int npairs, const int *pairs) {
     b.v.n = dirs;
     b.v.m = 0;
     b.v.pairs = nullptr;
+    b.v.dintr = nullptr;
+    b.v.cslot = nullptr;
+    b.v.ncurr = 0;
     if (comps == 2) {
         const int m = pairs ? npairs : dirs * (dirs + 1) / 2;
         if (m < 0 || (pairs == nullptr && npairs > 0 && npairs != m)) {
@@ -588,9 +597,53 @@ int batch_init(Batch &b, int comps, int dirs, int npairs, const int *pairs) {
 }
 void batch_free(Batch &b) {
     cudaFree(const_cast<int2 *>(b.v.pairs));
+    cudaFree(const_cast<float *>(b.v.dintr));
+    cudaFree(const_cast<int *>(b.v.cslot));
     delete[] b.h_pairs;
+    delete[] b.h_dintr;
+    delete[] b.h_cslot;
     b.h_pairs = nullptr;
-    b.v = BatchView{1, 0, 0, 0, nullptr};
+    b.h_dintr = nullptr;
+    b.h_cslot = nullptr;
+    b.v = BatchView{1, 0, 0, 0, nullptr, nullptr, nullptr, 0, 0.f, 0.f};
+}
+int batch_set_intrinsics(Batch &b, const float *dintr, float fx0, float fy0) {
+    if (b.v.kind != 2) {
+        set_error("intrinsic parameters need a Hessian batch (comps = 2)");
+        return XS_ERR_ARG;
+    }
+    cudaFree(const_cast<float *>(b.v.dintr));
+    cudaFree(const_cast<int *>(b.v.cslot));
+    delete[] b.h_dintr;
+    delete[] b.h_cslot;
+    b.h_dintr = nullptr, b.h_cslot = nullptr, b.v.dintr = nullptr, b.v.cslot = nullptr, b.v.ncurr = 0;
+    bool any = false;
+    for (int i = 0; dintr && i < 4 * b.v.n; ++i) any = any || dintr[i] != 0.f;
+    if (!any) return XS_OK;
+    const int n = b.v.n, m = b.v.m;
+    b.h_dintr = new float[4 * n];
+    b.h_cslot = new int[n + m];
+    std::memcpy(b.h_dintr, dintr, sizeof(float) * 4 * n);
+    int slots = 0;
+    auto moves = [&](int p) { return dintr[4 * p] != 0.f || dintr[4 * p + 1] != 0.f || dintr[4 * p + 2] != 0.f || dintr[4 * p + 3] != 0.f; };
+    for (int p = 0; p < n; ++p) b.h_cslot[p] = moves(p) ? slots++ : -1;
+    for (int k = 0; k < m; ++k) b.h_cslot[n + k] = (moves(b.h_pairs[k].x) && moves(b.h_pairs[k].y)) ? slots++ : -1;
+    float *dd = nullptr;
+    int *dc = nullptr;
+    if (cudaMalloc(&dd, sizeof(float) * 4 * n) != cudaSuccess || cudaMalloc(&dc, sizeof(int) * (n + m)) != cudaSuccess ||
+        cudaMemcpy(dd, b.h_dintr, sizeof(float) * 4 * n, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(dc, b.h_cslot, sizeof(int) * (n + m), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(dd);
+        cudaFree(dc);
+        set_error("batch: cannot upload the intrinsic seeds");
+        return XS_ERR_CUDA;
+    }
+    b.v.dintr = dd;
+    b.v.cslot = dc;
+    b.v.ncurr = slots;
+    b.v.gx0 = 1.f / fx0;
+    b.v.gy0 = 1.f / fy0;
+    return XS_OK;
 }
 
 // Copies the derivative components of a pose into staging slot `slot` (0 or 1) of the volume.
@@ -648,6 +701,12 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
                             unsigned long long *stats_host, void *stream) {
     if (!v || !d_depth || !v2c || rows <= 0 || cols <= 0) return XS_ERR_ARG;
     cudaStream_t s = (cudaStream_t) stream;
+    if (v->batch.v.dintr != nullptr && bilinear_threshold > 0.f) {
+        // with the nearest-neighbour depth look-up (biInterpolate_threshold = 0, the reference's default) sdf does not depend on
+        // the intrinsics at all: xl = (image_x - cx) / fx = X / Z.  The bilinear branch does (through the sub-pixel weights).
+        set_error("xs_integrate: intrinsic parameters with the bilinear depth look-up (biInterpolate_threshold > 0) are not implemented");
+        return XS_ERR_ARG;
+    }
     // the staging buffer is reused by the next call: make sure the previous consumer is done.  In the frame loop (pipelined)
     // the caller synchronises once per frame and integration has a staging slot of its own, so nothing waits here.
     if (!v->pipelined) XS_CUDA(cudaStreamSynchronize(s));

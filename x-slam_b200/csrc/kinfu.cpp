@@ -34,6 +34,9 @@ int icp_iteration_async(IcpScratch *sc, const float *d_pose_curr, const float *d
                         xs_intr intr, const float *d_vmap_g_prev, const float *d_nmap_g_prev, int rows, int cols, const Batch &batch,
                         float dist_thres, float angle_thres, float *d_pose_out, int solve_mode, int *d_status,
                         double *d_log, cudaStream_t s, cudaStream_t s_real, int slot);
+// surface.cu: derivative components of the current-frame maps (parameters that move the intrinsics)
+int surface_derivs(const float *d_depth, int rows, int cols, int level, xs_intr intr_level0, const BatchView &B, float *d_vmap, float *d_nmap,
+                   cudaStream_t s);
 // raycast.cu: resizeVMap / resizeNMap for a batch description
 int resize_map_batch(bool normalize, const float *d_in, int rows, int cols, const BatchView &B, float *d_out, cudaStream_t s);
 void icp_timing_reset(IcpScratch *sc);
@@ -112,6 +115,7 @@ struct xs_kinfu {
     cudaStream_t stream_comm = nullptr;
     cudaEvent_t ev_record = nullptr, ev_gather = nullptr;  // record uploaded / gather has read it and written d_gathered
     bool gather_in_flight = false;
+    bool keep_curr_derivs = false;  // xs_kinfu_keep_current_map_derivatives
     bool deferred = false;  // xs_kinfu_set_deferred: ProcessFrame returns once integration + raycast are queued
     bool pending = false;   // a frame's integration / raycast may still be running; its statistics are not collected yet
 };
@@ -348,6 +352,10 @@ static int surface_measure_on(xs_kinfu *k, const uint16_t *d_depth, cudaStream_t
     for (int i = 0; i < c.num_levels && rc == XS_OK; ++i) {
         rc = xs_create_vmap(level_intr(k->intr, i), k->depths[i], c.height >> i, c.width >> i, k->vmaps_curr[i], stream);
         if (rc == XS_OK) rc = xs_create_nmap(k->vmaps_curr[i], c.height >> i, c.width >> i, k->nmaps_curr[i], stream);
+        // parameters that move the intrinsics: the maps of the current frame carry derivative components.  The frame loop does
+        // not need them stored (the ICP forms d vcurr analytically from the real vertex), so they are written only on request
+        if (rc == XS_OK && k->keep_curr_derivs)
+            rc = surface_derivs(k->depths[i], c.height >> i, c.width >> i, i, k->intr, k->batch.v, k->vmaps_curr[i], k->nmaps_curr[i], stream);
     }
     return rc;
 }
@@ -667,6 +675,49 @@ int xs_kinfu_set_world2camera(xs_kinfu *k, const float *in) {
     return XS_OK;
 }
 
+// Intrinsic parameters of a Hessian batch (BASELINE.json configs[3]: "Hessian w.r.t. pose + intrinsics"): dintr[nparams][4] =
+// h d(fx, fy, cx, cy) / d theta_p.  New behaviour - the reference's Intr is plain floats (Internal.h:49-59): the current-frame
+// vertex / normal maps then carry derivative components (Map.cu:8-70 on jets), the ICP row takes d s = dR vc + dt + R dvc, and
+// the raycast ray ((x - cx) / fx, (y - cy) / fy, 1) its intrinsic derivatives (RayCaster.cu:56-62).  TSDF integration does not
+// depend on the intrinsics with the nearest-neighbour depth look-up (xl = (image_x - cx) / fx = X / Z, TsdfFusion.cu:118-146);
+// the bilinear branch is rejected.  Only before the first frame.
+int xs_kinfu_set_intrinsic_seeds(xs_kinfu *k, const float *dintr) {
+    if (!k || k->frame_id != 0 || k->comps != 2) {
+        set_error("xs_kinfu_set_intrinsic_seeds: needs a Hessian batch (comps = 2), before the first frame");
+        return XS_ERR_ARG;
+    }
+    if (k->cfg.bi_threshold > 0.f && dintr) {
+        set_error("xs_kinfu_set_intrinsic_seeds: not implemented with biInterpolate_threshold > 0 (bilinear depth look-up)");
+        return XS_ERR_ARG;
+    }
+    KCUDA(cudaStreamSynchronize(k->stream));
+    int rc = batch_set_intrinsics(k->batch, dintr, k->intr.fx, k->intr.fy);
+    if (rc == XS_OK) rc = xs_volume_set_intrinsic_seeds(k->volume, dintr);
+    if (rc != XS_OK) return rc;
+    return XS_OK;
+}
+
+// With intrinsic parameters the current-frame vertex / normal maps have derivative components (xs_kinfu_map then reports
+// [(1 + ncurr)][3][rows][cols]).  The frame loop itself does not read them, so they are stored only when asked for.
+int xs_kinfu_keep_current_map_derivatives(xs_kinfu *k, int on) {
+    if (!k || k->frame_id != 0) {
+        set_error("xs_kinfu_keep_current_map_derivatives: only before the first frame");
+        return XS_ERR_ARG;
+    }
+    KCUDA(cudaStreamSynchronize(k->stream));
+    k->keep_curr_derivs = on != 0 && k->batch.v.ncurr > 0;
+    const int ncurr = k->keep_curr_derivs ? k->batch.v.ncurr : 0;
+    for (int i = 0; i < k->cfg.num_levels; ++i) {  // current-frame maps: [(1 + ncurr)][3][rows][cols]
+        const size_t floats = map_floats(k, i, false) * (size_t) (1 + ncurr);
+        cudaFree(k->vmaps_curr[i]);
+        cudaFree(k->nmaps_curr[i]);
+        k->vmaps_curr[i] = k->nmaps_curr[i] = nullptr;
+        KCUDA(cudaMalloc((void **) &k->vmaps_curr[i], floats * sizeof(float)));
+        KCUDA(cudaMalloc((void **) &k->nmaps_curr[i], floats * sizeof(float)));
+    }
+    return XS_OK;
+}
+
 // gt_poses (camera-to-world, row-major 4x4 per frame) + flag_use_gtPose (KinectFusionReconstruction.h:36,82): with the flag
 // set, frames are fused at the given poses and ICP is skipped (mapping mode of the relocalisation experiments).
 int xs_kinfu_set_gt_poses(xs_kinfu *k, const float *poses16, int n, int use_gt_pose) {
@@ -691,7 +742,7 @@ const float *xs_kinfu_map(const xs_kinfu *k, int which, int level, int *rows, in
     if (!k || level < 0 || level >= k->cfg.num_levels) return nullptr;
     if (rows) *rows = k->cfg.height >> level;
     if (cols) *cols = k->cfg.width >> level;
-    if (ncomp) *ncomp = (which >= 3) ? k->ncomp : 0;
+    if (ncomp) *ncomp = (which >= 3) ? k->ncomp : (which >= 1 && k->keep_curr_derivs ? k->batch.v.ncurr : 0);
     switch (which) {
         case 0: return k->depths[level];
         case 1: return k->vmaps_curr[level];

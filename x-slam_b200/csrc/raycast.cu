@@ -417,6 +417,26 @@ XS_DEV void hit_direction(const RaycastParams &P, const float *ctx, int x, int y
 constexpr int HC_FIELDS = 20;
 enum { HC_S0 = 0, HC_S1 = 4, HC_AX = 8 };  // + 4 * axis
 
+// Pixel ray ((x - cx) / fx, (y - cy) / fy, 1) (RayCaster.cu:56-62) with the derivative components of parameters that move the
+// intrinsics (xs_batch.h): with g = 1 / fx, a = x - cx:  F_p = -dcx_p g - a g^2 dfx_p,
+// S_ij = (dcx_i dfx_j + dcx_j dfx_i) g^2 + 2 a g^3 dfx_i dfx_j; the y component likewise with (fy, cy).
+XS_DEV void next_first(const RaycastParams &P, int x, int y, int p, float &dx, float &dy) {
+    dx = dy = 0.f;
+    if (P.batch.dintr == nullptr) return;
+    const float4 d = __ldg(reinterpret_cast<const float4 *>(P.batch.dintr) + p);  // (dfx, dfy, dcx, dcy)
+    const float gx = __fdividef(1.f, P.intr.fx), gy = __fdividef(1.f, P.intr.fy);
+    dx = -d.z * gx - (float(x) - P.intr.cx) * gx * gx * d.x;
+    dy = -d.w * gy - (float(y) - P.intr.cy) * gy * gy * d.y;
+}
+XS_DEV void next_second(const RaycastParams &P, int x, int y, int i, int j, float &dx, float &dy) {
+    dx = dy = 0.f;
+    if (P.batch.dintr == nullptr) return;
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(P.batch.dintr) + i), b = __ldg(reinterpret_cast<const float4 *>(P.batch.dintr) + j);
+    const float gx = __fdividef(1.f, P.intr.fx), gy = __fdividef(1.f, P.intr.fy);
+    dx = (a.z * b.x + b.z * a.x) * gx * gx + 2.f * (float(x) - P.intr.cx) * gx * gx * gx * a.x * b.x;
+    dy = (a.w * b.y + b.w * a.y) * gy * gy + 2.f * (float(y) - P.intr.cy) * gy * gy * gy * a.y * b.y;
+}
+
 // value + gradient of the contraction of one first-order plane at one sample (8 corner gathers)
 XS_DEV void sample_first(const float *__restrict__ plane, const float *ctx, float &v, float &ga, float &gb, float &gc) {
     const float a = ctx[S_A * HIT_PX], b = ctx[S_B * HIT_PX], c = ctx[S_C * HIT_PX];
@@ -456,6 +476,7 @@ XS_DEV void hit_first_cached(const RaycastParams &P, const float *ctx, float *hc
         const int cc[1] = {comp};
         const JetPose<1, 1> c2v = load_pose_comps<1>(P.c2v, P.dpose_c2v, cc);
         Jet3<1, 1> next = {jconst<1, 1>(nx), jconst<1, 1>(ny), jconst<1, 1>(1.f)};
+        next_first(P, x, y, comp, next.x.d[0], next.y.d[0]);
         const Jet3<1, 1> start = c2v.t;
         Jet3<1, 1> dir = jnormalized_fast(jrot(c2v, next));
         if (dir.x.v == 0.f) dir.x = jconst<1, 1>(1e-15f);
@@ -536,6 +557,9 @@ XS_DEV void hit_pair_cached(const RaycastParams &P, const float *ctx, const floa
         const int comp[3] = {ci, cj, cs_};
         const JetPose<3, 1> c2v = load_pose_comps<3>(P.c2v, P.dpose_c2v, comp);
         Jet3<3, 1> next = {jconst<3, 1>(nx), jconst<3, 1>(ny), jconst<3, 1>(1.f)};
+        next_first(P, x, y, ci, next.x.d[0], next.y.d[0]);
+        next_first(P, x, y, cj, next.x.d[1], next.y.d[1]);
+        next_second(P, x, y, ci, cj, next.x.d[2], next.y.d[2]);
         const Jet3<3, 1> start = c2v.t;
         Jet3<3, 1> dir = jnormalized_fast(jrot(c2v, next));
         if (dir.x.v == 0.f) dir.x = jconst<3, 1>(1e-15f);
@@ -848,7 +872,7 @@ template <bool NORMALIZE>
 static int resize_map(const float *d_in, int rows, int cols, int comps, int dirs, float *d_out, void *stream) {
     if ((comps != 1 && comps != 2 && comps != 3) || dirs < 0) return XS_ERR_ARG;
     if (comps != 2 || !NORMALIZE) {
-        const BatchView B = {comps == 2 ? 1 : comps, comps == 2 ? batch_ncomp(2, dirs, -1) : dirs, 0, batch_ncomp(comps, dirs, -1), nullptr};
+        const BatchView B = {comps == 2 ? 1 : comps, comps == 2 ? batch_ncomp(2, dirs, -1) : dirs, 0, batch_ncomp(comps, dirs, -1), nullptr, nullptr, nullptr, 0, 0.f, 0.f};
         return resize_map_batch(NORMALIZE, d_in, rows, cols, B, d_out, (cudaStream_t) stream);
     }
     Batch b;  // normal maps of a Hessian batch need the pair table on the device
@@ -914,6 +938,10 @@ int xs_raycast(const xs_volume *v, xs_intr intr, const xs_pose *c2v, const xs_po
     // Hessian batches cache the first-order contractions in shared memory when two CTAs of two pixel groups still fit an SM
     static const bool no_cache = getenv("XS_HIT_NO_CACHE") != nullptr;  // A/B knob
     const bool cached = v->comps == 2 && !no_cache && 2 * (hit_smem_bytes(HIT_PG_CACHED, v->batch.v.n) + 1024) <= 227 * 1024;
+    if (v->batch.v.dintr != nullptr && !cached) {
+        set_error("xs_raycast: intrinsic parameters are implemented on the cached Hessian-batch path (too many parameters for shared memory)");
+        return XS_ERR_ARG;
+    }
     const int pg = cached ? HIT_PG_CACHED : HIT_PG_LIST;
     dim3 g2(div_up(cols, HIT_PX * pg), rows), b2(HIT_PX, HIT_WARPS);
     const size_t hit_smem = hit_smem_bytes(pg, cached ? v->batch.v.n : 0);

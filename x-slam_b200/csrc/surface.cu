@@ -112,6 +112,106 @@ __global__ void nmap_kernel(int rows, int cols, const float *__restrict__ vmap, 
     nmap[pix + 2 * plane] = r.z.v;
 }
 
+// ---- derivative components of the current-frame maps (intrinsic parameters of a Hessian batch, xs_batch.h) ---------------
+// createVMap with a perturbed intrinsic: vx = z (u - cx) g, g = 1 / fx (Map.cu:19-21, 84).  For parameter p with seeds
+// (dfx, dcx):  F_p(vx) = z [ -dcx g - (u - cx) g^2 dfx ];  for a pair (i, j) of such parameters
+// S_ij(vx) = z [ (dcx_i dfx_j + dcx_j dfx_i) g^2 + 2 (u - cx) g^3 dfx_i dfx_j ];  vy likewise with (fy, cy); vz = z is constant.
+// vmap: [(1 + ncurr)][3][rows][cols]; thread = pixel, loop over the slots.  `scale` = 1 / 2^level (Intr::operator(), Internal.h:55-58).
+__global__ void vmap_deriv_kernel(const float *__restrict__ depth, int rows, int cols, float *__restrict__ vmap, xs_intr k, float scale,
+                                  BatchView B) {
+    const int u = threadIdx.x + blockIdx.x * blockDim.x;
+    const int v = threadIdx.y + blockIdx.y * blockDim.y;
+    if (u >= cols || v >= rows) return;
+    const size_t plane = (size_t) rows * cols, pix = (size_t) v * cols + u;
+    const float z = __fdiv_rn(depth[pix], 1000.f);
+    const float gx = 1.f / k.fx, gy = 1.f / k.fy, ax = float(u) - k.cx, ay = float(v) - k.cy;
+    for (int c = 0; c < B.ncomp; ++c) {
+        const int slot = __ldg(B.cslot + c);
+        if (slot < 0) continue;
+        float dx = 0.f, dy = 0.f;
+        if (z != 0.f) {
+            if (c < B.n) {
+                const float4 d = __ldg(reinterpret_cast<const float4 *>(B.dintr) + c);  // (dfx, dfy, dcx, dcy) at level 0
+                dx = z * (-d.z * scale * gx - ax * gx * gx * d.x * scale);
+                dy = z * (-d.w * scale * gy - ay * gy * gy * d.y * scale);
+            } else {
+                const int2 pr = __ldg(B.pairs + (c - B.n));
+                const float4 di = __ldg(reinterpret_cast<const float4 *>(B.dintr) + pr.x), dj = __ldg(reinterpret_cast<const float4 *>(B.dintr) + pr.y);
+                const float s2 = scale * scale;
+                dx = z * s2 * ((di.z * dj.x + dj.z * di.x) * gx * gx + 2.f * ax * gx * gx * gx * di.x * dj.x);
+                dy = z * s2 * ((di.w * dj.y + dj.w * di.y) * gy * gy + 2.f * ay * gy * gy * gy * di.y * dj.y);
+            }
+        }
+        float *o = vmap + (size_t) (1 + slot) * 3 * plane + pix;
+        o[0] = dx;
+        o[plane] = dy;
+        o[2 * plane] = 0.f;
+    }
+}
+
+// createNMap on jets: n = normalized(cross(v01 - v00, v10 - v00)) (Map.cu:32-70) for the derivative slots; first-order
+// slots in the dual algebra, pair slots in the bicomplex one on (F_i, F_j, S_ij).
+template <int C>
+XS_DEV void nmap_deriv_task(const float *__restrict__ vmap, float *__restrict__ nmap, size_t plane, size_t pix, int cols, bool ok,
+                            const int (&slot)[C], int out_slot) {
+    float *o = nmap + (size_t) (1 + out_slot) * 3 * plane + pix;
+    if (!ok) {
+        o[0] = o[plane] = o[2 * plane] = 0.f;
+        return;
+    }
+    Jet3<C, 1> p[3];  // v00, v01, v10
+    const size_t off[3] = {0, 1, (size_t) cols};
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        Jet<C, 1> *cmp[3] = {&p[t].x, &p[t].y, &p[t].z};
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            cmp[pl]->v = vmap[pix + off[t] + pl * plane];
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                cmp[pl]->d[c] = slot[c] >= 0 ? vmap[(size_t) (1 + slot[c]) * 3 * plane + pix + off[t] + pl * plane] : 0.f;
+        }
+    }
+    const Jet3<C, 1> r = jnormalized_fast(jcross(p[1] - p[0], p[2] - p[0]));
+    o[0] = r.x.d[C - 1];
+    o[plane] = r.y.d[C - 1];
+    o[2 * plane] = r.z.d[C - 1];
+}
+__global__ void nmap_deriv_kernel(int rows, int cols, const float *__restrict__ vmap, float *__restrict__ nmap, BatchView B) {
+    const int u = threadIdx.x + blockIdx.x * blockDim.x;
+    const int v = threadIdx.y + blockIdx.y * blockDim.y;
+    if (u >= cols || v >= rows) return;
+    const size_t plane = (size_t) rows * cols, pix = (size_t) v * cols + u;
+    bool ok = !(u == cols - 1 || v == rows - 1);
+    if (ok) ok = !isnan(vmap[pix]) && !isnan(vmap[pix + 1]) && !isnan(vmap[pix + cols]);
+    for (int c = 0; c < B.ncomp; ++c) {
+        const int slot = __ldg(B.cslot + c);
+        if (slot < 0) continue;
+        if (c < B.n) {
+            const int s1[1] = {slot};
+            nmap_deriv_task<1>(vmap, nmap, plane, pix, cols, ok, s1, slot);
+        } else {
+            const int2 pr = __ldg(B.pairs + (c - B.n));
+            const int s3[3] = {__ldg(B.cslot + pr.x), __ldg(B.cslot + pr.y), slot};
+            nmap_deriv_task<3>(vmap, nmap, plane, pix, cols, ok, s3, slot);
+        }
+    }
+}
+
+// derivative components of the vertex / normal maps of one pyramid level (after the real maps): [(1 + ncurr)][3][rows][cols]
+int surface_derivs(const float *d_depth, int rows, int cols, int level, xs_intr intr_level0, const BatchView &B, float *d_vmap, float *d_nmap,
+                   cudaStream_t s) {
+    if (B.ncurr == 0) return XS_OK;
+    const float scale = 1.f / float(1 << level);
+    const xs_intr k = {intr_level0.fx * scale, intr_level0.fy * scale, intr_level0.cx * scale, intr_level0.cy * scale};
+    dim3 blk(32, 8), grd(div_up(cols, 32), div_up(rows, 8));
+    vmap_deriv_kernel<<<grd, blk, 0, s>>>(d_depth, rows, cols, d_vmap, k, scale, B);
+    XS_LAUNCH_CHECK();
+    nmap_deriv_kernel<<<grd, blk, 0, s>>>(rows, cols, d_vmap, d_nmap, B);
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
+
 // Seam layout <-> packed SoA.  The reference's maps are pitched arrays of interleaved complex<float> with the planes
 // stacked by rows (MapArr = DeviceArray2D<devComplex>, Internal.h:31; `nplanes*rows` x cols).  Component 0 of the SoA
 // map is the real part; the imaginary part maps to derivative component `comp` (comp < 0: dropped / written as zero).

@@ -161,7 +161,8 @@ class KinectFusionReconstruction:
         self.depth_height = 0
         self.config = None
 
-    def SetYamlParameters(self, config, comps=1, seeds=None, solve_mode=None, pairs=None, n_params=None):
+    def SetYamlParameters(self, config, comps=1, seeds=None, solve_mode=None, pairs=None, n_params=None, intrinsic_seeds=None,
+                          keep_current_map_derivatives=False):
         """KinectFusionReconstruction.cpp:9-73.  config: dict of YAML keys (or a path).
         seeds: [ncomp, 16] h-scaled derivative components of the initial world2camera.  comps = 1 / 3: lists of first-order /
         bicomplex directions (ncomp = dirs * comps).  comps = 2: Hessian batch over n_params parameters - n_params first-order
@@ -206,6 +207,14 @@ class KinectFusionReconstruction:
             self.h = self.lib.xs_kinfu_create(C.byref(c), comps, self.dirs, sp, solve_mode)
         if not self.h:
             raise _capi.XsError("SetYamlParameters: " + self.lib.xs_last_error().decode())
+        if intrinsic_seeds is not None:
+            # [n_params, 4]: h d(fx, fy, cx, cy) / d theta_p - parameters of a Hessian batch that move the intrinsics
+            d = np.ascontiguousarray(intrinsic_seeds, np.float32).reshape(-1, 4)
+            if comps != 2 or d.shape[0] != self.dirs:
+                raise ValueError("intrinsic_seeds: [n_params, 4] rows for a Hessian batch (comps = 2)")
+            check(self.lib.xs_kinfu_set_intrinsic_seeds(self.h, d.ctypes.data_as(C.POINTER(C.c_float))), "intrinsic_seeds")
+            if keep_current_map_derivatives:
+                check(self.lib.xs_kinfu_keep_current_map_derivatives(self.h, 1), "keep_current_map_derivatives")
         self.use_gtPose = bool(cfg.get("flag_use_gtPose", False))  # KinectFusionReconstruction.cpp:69
         self._gt_poses = []                                        # :70 gt_poses.resize(0)
         if self.use_gtPose:
