@@ -31,7 +31,7 @@ static SingleComplex div_first_order(SingleComplex a, SingleComplex b) {
 }
 static SingleComplex exp_first_order(SingleComplex a) { return {std::exp(a.real()), std::exp(a.real()) * std::sin(a.imag())}; }
 static SingleComplex sin_first_order(SingleComplex a) { return {std::sin(a.real()), -std::sinh(-a.imag()) * std::cos(a.real())}; }
-static SingleComplex pow_first_order(SingleComplex a, int n) { return {std::pow(a.real(), n), std::pow(std::norm(a), n) * std::sin(n * std::arg(a))}; }
+static SingleComplex pow_first_order(SingleComplex a, int n) { return {(float) std::pow(a.real(), n), (float) (std::pow(std::norm(a), n) * std::sin(n * std::arg(a)))}; }
 
 int main() {
     const float h = 1e-6f;       // main.cpp:93

@@ -49,6 +49,11 @@ def main():
         f[1] += i[1]
     for f, (a, b) in sorted(files.items(), key=lambda kv: -kv[1][0]):
         print("  %-20s inst %5.1f%%  samples %5.1f%%" % (f, 100 * a / max(ti, 1), 100 * b / max(ts, 1)))
+    if "--by-inst" in sys.argv:
+        print("top lines by instructions:")
+        for inst, samp, f, ln, src in sorted(items, key=lambda t: -t[0])[:top]:
+            print("  %5.1f%% inst %5.1f%% smp  %s:%s  %s" % (100 * inst / max(ti, 1), 100 * samp / max(ts, 1), f, ln, src.strip()))
+        return
     print("top lines by samples:")
     for inst, samp, f, ln, src in sorted(items, key=lambda t: -t[1])[:top]:
         print("  %5.1f%% smp %5.1f%% inst  %s:%s  %s" % (100 * samp / max(ts, 1), 100 * inst / max(ti, 1), f, ln, src.strip()))

@@ -31,6 +31,7 @@
 // order is fixed by construction, so results are deterministic run to run.
 #include "xs_common.cuh"
 
+#include <algorithm>
 #include <utility>
 #include <vector>
 
@@ -102,6 +103,7 @@ struct IcpParams {
     BatchView batch;             // Hessian batch (kind 2): a group is one task = parameter i (component i) or pair k (component n + k)
     unsigned int *done_ticket;   // kind 2: tasks whose sums are complete (self-resetting); the CTA that completes the last one solves
     const struct HTask *htasks;  // kind 2: [groups] task table (device)
+    const int *tile_wp;          // kind 2, tile form: [warps][pairs per warp] pair index of every warp slot (-1: empty)
 };
 
 // the Gauss-Newton step that closes an iteration (icp_solve_direction below)
@@ -1329,6 +1331,356 @@ __global__ void __launch_bounds__(256, MINB) icp_deriv_h_kernel(const IcpParams 
     for (int k = tid; k < P.batch.m; k += 256) icp_solve_hessian_pair(S, n, k, __ldg(P.batch.pairs + k), s_real, s_x1, REDUCED);
 }
 
+// ---- tile form of the REDUCED Hessian derivative pass -------------------------------------------------------------------------
+// The task form above reads the association record once per task and the first-order planes of parameter i once per pair run:
+// ~3.4x the algorithmic bytes cross L2 -> SM at 10 parameters / 55 pairs, and that link, not HBM, bounds it (profiles/
+// r02_ncu_summary.md).  Here a CTA owns pixels instead of tasks: a tile of 32 pixels (lane = pixel) is staged ONCE for all
+// components - the record, the n first-order and the m second-order gathers at the matched pixels, cp.async, two tiles ahead -
+// so every byte crosses L2 -> SM once per launch.  The NW warps of the CTA then split the components of the tile:
+//   phase B: warp p < n forms the first-order row of parameter p (d_p, ds_p, de_p, rho_p = d_p6 - d_p . x: 14 floats per pixel,
+//            left in shared memory) and accumulates its 27 first-order sums;
+//   phase C: warp w owns a contiguous run of <= PPW pairs (the pair list is sorted by i, so the row of i stays in registers
+//            along the run), reads row j, its own gathers and accumulates the 6 values of g_ij = b_ij - A_ij x.
+// The rows are double buffered: between two barriers a warp runs phase B of tile j + 1 and phase C of tile j (one barrier per
+// tile); the staging runs two iterations ahead of its reader (4 buffers for the record + first-order part, 3 for the
+// second-order part, which only its own warp reads).
+// FP32 accumulators are flushed every 32 tiles through the lane transpose into per-lane doubles (as in the task form); a CTA
+// writes one partial [n x 27 + m x 6], the last CTA (ticket) adds the partials in CTA order and runs the tail.
+constexpr int TILE_ROW = 14;
+// staging buffers for a look-ahead of `depth` tiles: record + first-order gathers (read by phases B and C) | second-order gathers
+__host__ __device__ constexpr int tile_small(int depth) { return depth + 2; }
+__host__ __device__ constexpr int tile_big(int depth) { return depth + 1; }
+__host__ __device__ constexpr int tile_groups(int ppw) { return (27 + 6 * ppw + 31) / 32; }
+constexpr size_t tile_smem(int n, int m, int nw, int ppw, int depth, bool pipe) {
+    return (size_t) (tile_small(depth) * (12 + 6 * n) + tile_big(depth) * 6 * m + (pipe ? 2 : 1) * n * TILE_ROW) * 32 * sizeof(float) + (size_t) (n + m) * 4 * sizeof(float4) +
+           (size_t) nw * tile_groups(ppw) * 32 * sizeof(double) + (size_t) m * sizeof(int2);
+}
+
+template <int NW, int PPW, bool CURR, bool PIPE, int DEPTH>
+__global__ void __launch_bounds__(NW * 32, 1) icp_deriv_tile_kernel(const IcpParams P, const SolveParams S) {
+    constexpr int G = tile_groups(PPW);
+    constexpr int NS = tile_small(DEPTH), NB = tile_big(DEPTH);
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ float4 s_real_pose[3];
+    __shared__ __align__(16) float s_x[6];
+    __shared__ bool s_last;
+    __shared__ int s_tb;  // first tile of this CTA (read where needed: held in a register it is spilled, and the staging traffic keeps evicting L1)
+    const int n = P.batch.n, m = P.batch.m;
+    const int INS = 12 + 6 * n, INB = 6 * m;
+    float *s_small = reinterpret_cast<float *>(s_raw);                    // [NS][INS][32]: record, first-order gathers
+    float *s_big = s_small + (size_t) NS * INS * 32;                      // [NB][INB][32]: second-order gathers
+    float *s_row = s_big + (size_t) NB * INB * 32;                        // [PIPE ? 2 : 1][n][TILE_ROW][32]
+    float4 *s_pose = reinterpret_cast<float4 *>(s_row + (PIPE ? 2 : 1) * n * TILE_ROW * 32);  // [n + m][3]
+    float4 *s_cur = s_pose + 3 * (n + m);                                 // [n + m]: d vc = (x z + y vx, z z + w vy, 0)
+    double *s_tot = reinterpret_cast<double *>(s_cur + (n + m));          // [NW][G][32]
+    int2 *s_pair = reinterpret_cast<int2 *>(s_tot + NW * G * 32);         // [m]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned uplane = (unsigned) (P.rows * P.cols);
+    const int npix = P.rows * P.cols;
+    const int ntile = (npix + 31) >> 5;
+    const unsigned long long stream_policy = l2_policy_evict_first();
+    // ---- per-CTA tables
+    if (tid < 6) s_x[tid] = (float) __ldcg(S.real_cache + 42 + tid);
+    if (tid == 6) s_tb = (int) ((long long) blockIdx.x * ntile / gridDim.x);
+    if (tid >= 32 && tid < 44) reinterpret_cast<float *>(&s_real_pose[0])[tid - 32] = P.pose_curr[tid - 32];
+    for (int e = tid; e < 12 * (n + m); e += NW * 32) reinterpret_cast<float *>(s_pose)[e] = P.pose_curr[12 + e];
+    if (CURR) {
+        const float4 *din = reinterpret_cast<const float4 *>(P.batch.dintr);  // (dfx, dfy, dcx, dcy) at level 0
+        const float gx = P.batch.gx0, gy = P.batch.gy0;
+        for (int c = tid; c < n + m; c += NW * 32) {
+            float4 o;
+            if (c < n) {
+                const float4 d = __ldg(din + c);
+                o = make_float4(-d.z * gx, -d.x * gx, -d.w * gy, -d.y * gy);
+            } else {
+                const int2 pr = __ldg(P.batch.pairs + (c - n));
+                const float4 di = __ldg(din + pr.x), dj = __ldg(din + pr.y);
+                o = make_float4((di.z * dj.x + dj.z * di.x) * gx * gx, 2.f * di.x * dj.x * gx * gx, (di.w * dj.y + dj.w * di.y) * gy * gy,
+                                2.f * di.y * dj.y * gy * gy);
+            }
+            s_cur[c] = o;
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) s_tot[(warp * G + g) * 32 + lane] = 0.0;
+    // ---- this warp's components
+    const int fp = warp < n ? warp : -1;  // first-order parameter (host: n <= NW)
+    // this warp's pairs (P.tile_wp: [NW][PPW] pair indices, -1 = none; dealt by the host so that the warps carry equal work)
+    int wk[PPW];
+#pragma unroll
+    for (int h = 0; h < PPW; ++h) wk[h] = __ldg(P.tile_wp + warp * PPW + h);
+    for (int k = tid; k < m; k += NW * 32) s_pair[k] = __ldg(P.batch.pairs + k);  // read per pair (broadcast) rather than held in registers
+    __syncthreads();
+    const float (&x)[6] = s_x;  // broadcast shared loads where used
+    float accf[27], accp[PPW][6];
+#pragma unroll
+    for (int e = 0; e < 27; ++e) accf[e] = 0.f;
+#pragma unroll
+    for (int h = 0; h < PPW; ++h)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) accp[h][c] = 0.f;
+    // FP32 accumulators -> per-lane double totals: accumulator a is summed over the lanes by a fixed butterfly and added by lane
+    // a % 32 to its slot of group a / 32 (one accumulator at a time: the lane transpose of the task form would need 32 more
+    // registers here, and what it spills is reloaded from an L1 that the staging traffic keeps evicting)
+    auto flush = [&]() {
+        double tot[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) tot[g] = 0.0;
+#pragma unroll
+        for (int a = 0; a < 27 + 6 * PPW; ++a) {
+            float v = a < 27 ? accf[a % 27] : accp[((a < 27 ? 27 : a) - 27) / 6][((a < 27 ? 27 : a) - 27) % 6];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == (a & 31)) tot[a / 32] += (double) v;
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) s_tot[(warp * G + g) * 32 + lane] += tot[g];
+#pragma unroll
+        for (int e = 0; e < 27; ++e) accf[e] = 0.f;
+#pragma unroll
+        for (int h = 0; h < PPW; ++h)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) accp[h][c] = 0.f;
+    };
+    const int nt = (int) ((long long) (blockIdx.x + 1) * ntile / gridDim.x) - (int) ((long long) blockIdx.x * ntile / gridDim.x);
+    auto idx_at = [&](int j) {
+        const int p = (s_tb + j) * 32 + lane;
+        return (j < nt && p < npix) ? P.rec_idx[p] : -1;
+    };
+    // staging of tile j.  Small part: the record (3 x 16 bytes per pixel) by the last three warps, the six gather rows (normal and
+    // vertex planes at the matched pixel) of parameter p by warp p.  Big part: every warp stages the gathers of its own pairs.
+    auto gather6 = [&](float *d, unsigned o) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            cp_async4_stream(d + c * 32, P.nmap_prev + (o + c * uplane), stream_policy);
+            cp_async4_stream(d + (3 + c) * 32, P.vmap_prev + (o + c * uplane), stream_policy);
+        }
+    };
+    auto issue_small = [&](int buf, int j, int q) {
+        if (q < 0) return;
+        float *dst = s_small + (size_t) buf * INS * 32;
+        if (warp >= NW - 3)
+            cp_async16(reinterpret_cast<float4 *>(dst) + (warp - (NW - 3)) * 32 + lane, P.rec_f + (size_t) ((s_tb + j) * 32 + lane) * 4 + (warp - (NW - 3)));
+        if (fp >= 0) gather6(dst + (12 + fp * 6) * 32 + lane, (unsigned) q + (unsigned) (1 + fp) * 3u * uplane);
+    };
+    auto issue_big = [&](int buf, int q) {
+        if (q < 0) return;
+        float *d = s_big + (size_t) buf * INB * 32 + lane;
+        const unsigned o = (unsigned) q + (unsigned) (1 + n) * 3u * uplane;
+#pragma unroll
+        for (int h = 0; h < PPW; ++h)
+            if (wk[h] >= 0) gather6(d + wk[h] * (6 * 32), o + (unsigned) wk[h] * 3u * uplane);
+    };
+    // per-pixel real quantities of a staged tile
+    struct Px {
+        float vc[3], sv[3], nv[3], ev[3], r[7], rho;
+    };
+    auto pixel = [&](int buf, Px &p) {
+        const float4 *in4 = reinterpret_cast<const float4 *>(s_small + (size_t) buf * INS * 32) + lane;
+        const float4 f0 = in4[0], f1 = in4[32], f2 = in4[64];
+        p.vc[0] = f0.x, p.vc[1] = f0.y, p.vc[2] = f0.z;
+        p.sv[0] = f0.w, p.sv[1] = f1.x, p.sv[2] = f1.y;
+        p.nv[0] = f1.z, p.nv[1] = f1.w, p.nv[2] = f2.x;
+        p.ev[0] = f2.y, p.ev[1] = f2.z, p.ev[2] = f2.w;
+        cross3(p.sv, p.nv, p.r);
+        p.r[3] = p.nv[0], p.r[4] = p.nv[1], p.r[5] = p.nv[2];
+        p.r[6] = dot3(p.nv, p.ev);
+        p.rho = rho_of(p.r, x);
+    };
+    auto dvc_of = [&](int c, const Px &p, float (&o)[3]) {
+        const float4 k = s_cur[c];
+        o[0] = fmaf(k.x, p.vc[2], k.y * p.vc[0]);
+        o[1] = fmaf(k.z, p.vc[2], k.w * p.vc[1]);
+        o[2] = 0.f;
+    };
+    // phase B of a staged tile: the first-order row of this warp's parameter -> rows[rb], and its 27 sums
+    auto phase_b = [&](int buf, int rb, int q) {
+        if (fp < 0 || q < 0) return;  // fp: warp-uniform
+        Px p;
+        pixel(buf, p);
+        const float *in = s_small + (size_t) buf * INS * 32 + lane;
+        float dn[3], dv[3], ds[3], de[3], d[7], ex[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dn[c] = in[(12 + fp * 6 + c) * 32], dv[c] = in[(12 + fp * 6 + 3 + c) * 32];
+        if (CURR) {
+            float dvc[3];
+            dvc_of(fp, p, dvc);
+            rot_add(s_real_pose, dvc, ex);
+        }
+        row_first(s_pose + 3 * fp, p.vc, p.sv, p.nv, p.ev, dn, dv, ex, ds, de, d);
+        accumulate_first(accf, p.r, d, std::make_integer_sequence<int, 27>());
+        float *o = s_row + ((size_t) rb * n + fp) * TILE_ROW * 32 + lane;
+        o[0] = d[0], o[32] = d[1], o[64] = d[2];
+        o[96] = dn[0], o[128] = dn[1], o[160] = dn[2];
+        o[192] = d[6];
+        o[224] = ds[0], o[256] = ds[1], o[288] = ds[2];
+        o[320] = de[0], o[352] = de[1], o[384] = de[2];
+        o[416] = rho_of(d, x);
+    };
+    // CURR: which of this warp's pairs involve a parameter that moves the intrinsics (bit h: parameter i, bit 8 + h: parameter j)
+    unsigned curmask = 0u;
+    if (CURR) {
+#pragma unroll
+        for (int h = 0; h < PPW; ++h) {
+            if (wk[h] >= 0) {
+                const float4 ki = s_cur[s_pair[wk[h]].x], kj = s_cur[s_pair[wk[h]].y];
+                if ((ki.x != 0.f) | (ki.y != 0.f) | (ki.z != 0.f) | (ki.w != 0.f)) curmask |= 1u << h;
+                if ((kj.x != 0.f) | (kj.y != 0.f) | (kj.z != 0.f) | (kj.w != 0.f)) curmask |= 1u << (8 + h);
+            }
+        }
+    }
+    // Pipeline.  Between two barriers a warp runs phase B of tile j + 1 and phase C of tile j; the small part of tile j + 3 and
+    // the big part of tile j + 2 are issued at the top of iteration j (one commit group), two iterations before they are read.
+    int qs[5];  // matched indices of tiles j .. j + 4
+#pragma unroll
+    for (int i = 0; i < 5; ++i) qs[i] = idx_at(i);
+    issue_small(0, 0, qs[0]);
+    issue_small(1, 1, qs[1]);
+    issue_big(0, qs[0]);
+    cp_async_commit();
+    if (DEPTH == 2) {
+        issue_small(2, 2, qs[2]);
+        issue_big(1, qs[1]);
+        cp_async_commit();
+    }
+    if (PIPE) {
+        cp_async_wait<DEPTH - 1>();
+        __syncthreads();
+        phase_b(0, 0, qs[0]);
+    }
+    int sb = 0, bb = 0;  // buffers of tile j: small part (of NS), big part (of NB)
+    for (int j = 0; j < nt; ++j) {
+        cp_async_wait<DEPTH - 1>();  // this thread's copies up to (small j + 1, big j) have landed
+        __syncthreads();             // ... everyone's have; rows of tile j are complete; phase C of tile j - 1 is over
+        issue_small((sb + DEPTH + 1) % NS, j + DEPTH + 1, qs[DEPTH + 1]);
+        issue_big((bb + DEPTH) % NB, qs[DEPTH]);
+        cp_async_commit();
+        if (PIPE) {
+            phase_b((sb + 1) % NS, (j + 1) & 1, qs[1]);
+        } else {  // A/B form: rows of tile j, a second barrier, then its pairs
+            phase_b(sb, 0, qs[0]);
+            __syncthreads();
+        }
+        const int q = qs[0];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qs[i] = qs[i + 1];
+        qs[4] = idx_at(j + 5);
+        // ---- phase C: this warp's pairs on tile j
+        if (q >= 0) {
+            Px p;
+            pixel(sb, p);
+            const float *in = s_big + (size_t) bb * INB * 32 + lane;
+            const float *rows = s_row + (size_t) (PIPE ? (j & 1) : 0) * n * TILE_ROW * 32 + lane;
+            int have_i = -1;
+            float di[7], dsi[3], dei[3], rhoi = 0.f;
+            auto load_row = [&](int p_, float (&d)[7], float (&ds)[3], float (&de)[3], float &rh) {
+                const float *o = rows + (size_t) p_ * TILE_ROW * 32;
+#pragma unroll
+                for (int e = 0; e < 7; ++e) d[e] = o[e * 32];
+#pragma unroll
+                for (int e = 0; e < 3; ++e) ds[e] = o[(7 + e) * 32], de[e] = o[(10 + e) * 32];
+                rh = o[13 * 32];
+            };
+#pragma unroll
+            for (int h = 0; h < PPW; ++h) {
+                if (wk[h] >= 0) {  // warp-uniform
+                    const int k = wk[h];
+                    const int2 pr = s_pair[k];
+                    const int i = pr.x, jj = pr.y;
+                    if (i != have_i) {
+                        load_row(i, di, dsi, dei, rhoi);
+                        have_i = i;
+                    }
+                    float dj[7], dsj[3], dej[3], rhoj;
+                    load_row(jj, dj, dsj, dej, rhoj);
+                    float dn2[3], dv2[3], ds2[3], de2[3], d2[7], ex2[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) dn2[c] = in[(k * 6 + c) * 32], dv2[c] = in[(k * 6 + 3 + c) * 32];
+                    if (CURR) {
+                        const bool ci = (curmask >> h) & 1u, cj = (curmask >> (8 + h)) & 1u;
+                        if (ci | cj) {  // warp-uniform
+                            float a[3];
+                            if (cj) {
+                                dvc_of(jj, p, a);
+                                rot_add(s_pose + 3 * i, a, ex2);  // dR_i dvc_j
+                            }
+                            if (ci) {
+                                dvc_of(i, p, a);
+                                rot_add(s_pose + 3 * jj, a, ex2);  // dR_j dvc_i
+                            }
+                            if (ci & cj) {
+                                dvc_of(n + k, p, a);
+                                rot_add(s_real_pose, a, ex2);  // R dvc_ij
+                            }
+                        }
+                    }
+                    row_first(s_pose + 3 * (n + k), p.vc, p.sv, p.nv, p.ev, dn2, dv2, ex2, ds2, de2, d2);
+                    const float *dni = di + 3, *dnj = dj + 3;
+                    cross3_add(dsi, dnj, d2);  // second-order cross terms of the row
+                    cross3_add(dsj, dni, d2);
+                    d2[6] += dot3(dni, dej) + dot3(dnj, dei);
+                    const float rho2 = rho_of(d2, x);
+#pragma unroll
+                    for (int c = 0; c < 6; ++c)
+                        accp[h][c] = fmaf(d2[c], p.rho, fmaf(p.r[c], rho2, fmaf(di[c], rhoj, fmaf(dj[c], rhoi, accp[h][c]))));
+                }
+            }
+        }
+        sb = sb + 1 == NS ? 0 : sb + 1;
+        bb = bb + 1 == NB ? 0 : bb + 1;
+        if ((j & 31) == 31) flush();
+    }
+    if (nt & 31) flush();
+    cp_async_wait<0>();
+    // ---- one partial per CTA: [n][27] first-order sums, [m][6] reduced pair values
+    const int NV = n * 27 + m * 6;
+    double *part = P.dpartials + (size_t) blockIdx.x * NV;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int a = g * 32 + lane;
+        const double v = s_tot[(warp * G + g) * 32 + lane];
+        if (a < 27) {
+            if (fp >= 0) part[fp * 27 + a] = v;
+        } else if (a - 27 < 6 * PPW) {
+            int k = -1;
+#pragma unroll
+            for (int h = 0; h < PPW; ++h)
+                if ((a - 27) / 6 == h) k = wk[h];
+            if (k >= 0) part[n * 27 + k * 6 + (a - 27) % 6] = v;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(P.done_ticket, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int v = tid; v < NV; v += NW * 32) {
+        double sum = 0.0;
+        const double *src = P.dpartials + v;
+#pragma unroll 8
+        for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(src + (size_t) b * NV);
+        if (v < n * 27) {
+            P.sums[27 + v] = sum;  // component 1 + p, element e: 27 (1 + p) + e
+        } else {
+            const int k = (v - n * 27) / 6, c = (v - n * 27) - k * 6;
+            P.sums[(size_t) (1 + n + k) * 27 + c] = sum;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *P.done_ticket = 0u;
+    if (!S.pose_out) return;
+    // ---- tail: the Gauss-Newton step of every component (as in the task form)
+    double *s_real = reinterpret_cast<double *>(s_raw);  // [27]; the staging area is idle here
+    double *s_x1 = s_real + 32;                          // [n][6] first-order solutions
+    if (tid < 27) s_real[tid] = __ldcg(P.sums + tid);
+    __syncthreads();
+    for (int i = tid; i < n; i += NW * 32) icp_solve_hessian_first(S, i, s_real, s_x1 + 6 * i);
+    __syncthreads();
+    for (int k = tid; k < m; k += NW * 32) icp_solve_hessian_pair(S, n, k, __ldg(P.batch.pairs + k), s_real, s_x1, true);
+}
+
 // ---- Gauss-Newton step of a Hessian batch (kind 2), one thread per component.
 // Real prelude shared by both task kinds: status flags, real A / b, Cholesky factor and real solution (loaded from the real
 // step's cache under split chains, computed otherwise).  Returns false when the iteration is skipped (degenerate system).
@@ -1474,6 +1826,10 @@ __device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n,
 struct IcpScratch {
     double *d_partials = nullptr, *d_sums = nullptr, *h_sums = nullptr, *d_dpartials = nullptr;
     unsigned int *d_ticket = nullptr, *d_group_ticket = nullptr, *d_done_ticket = nullptr;
+    int *d_tile_wp = nullptr;          // Hessian batch, tile form: pair slots of the warps (built with the task table)
+    int tile_wp_nw = 0;
+    bool tile_wp_cur = false;
+    const void *tile_wp_key = nullptr;
     struct HTask *d_htasks = nullptr;  // Hessian batch: task table of the derivative pass, built once per pair list
     const void *htasks_key = nullptr;
     int n_htasks = 0, htasks_hp = 0;
@@ -1516,6 +1872,7 @@ void icp_scratch_destroy(IcpScratch *sc) {
     cudaFree(sc->d_group_ticket);
     cudaFree(sc->d_done_ticket);
     cudaFree(sc->d_htasks);
+    cudaFree(sc->d_tile_wp);
     cudaFree(sc->d_pose);
     cudaFreeHost(sc->h_pose);
     cudaFree(sc->d_rec_idx);
@@ -1611,6 +1968,20 @@ template <int C, int ST> static int launch_deriv(const IcpParams &P, const Solve
     return XS_OK;
 }
 
+constexpr int TILE_NW = 11, TILE_PPW = 5;  // 10 parameters + 55 pairs: one row and five pairs per warp
+template <int NW, int PPW, bool CURR, bool PIPE, int DEPTH> static int launch_deriv_tile(const IcpParams &P, const SolveParams &S, int grid, cudaStream_t s) {
+    static size_t smem_set = 0;
+    static const int pad_kb = env_int("XS_ICP_TILE_PAD_KB", 0);  // experiment: unused shared memory (shrinks L1)
+    const size_t smem = std::min<size_t>(tile_smem(P.batch.n, P.batch.m, NW, PPW, DEPTH, PIPE) + (size_t) pad_kb * 1024, 227 * 1024);
+    if (smem > smem_set) {
+        XS_CUDA(cudaFuncSetAttribute(icp_deriv_tile_kernel<NW, PPW, CURR, PIPE, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        smem_set = smem;
+    }
+    icp_deriv_tile_kernel<NW, PPW, CURR, PIPE, DEPTH><<<grid, NW * 32, smem, s>>>(P, S);
+    XS_LAUNCH_CHECK();
+    return XS_OK;
+}
+
 template <int ST, int MINB, int HPK, bool REDUCED, bool CURR> static int launch_deriv_h(const IcpParams &P, const SolveParams &S, int grid, cudaStream_t s) {
     static bool smem_set = false;
     if (!smem_set) {
@@ -1693,7 +2064,63 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
     const long long items = (long long) P.groups * P.chunks;
     const int deriv_grid = (int) (items < cta_slots ? items : cta_slots);
     P.max_writers = ncomp > 0 ? (int) (P.chunks / (items / deriv_grid)) + 2 : 0;
-    int rc = icp_reserve(scp, ncomp, npix, (size_t) P.groups * P.max_writers * 81, P.groups, split ? IcpScratch::MAX_SLOTS : 1);
+    // tile form of the reduced pass (icp_deriv_tile_kernel): one CTA per SM over 32-pixel tiles, all components of a tile at once
+    static const int h_tile = env_int("XS_ICP_H_TILE", 1);
+    const size_t smem_cap = 227 * 1024;
+    const int tile_nw = TILE_NW;  // measured and rejected: 16 warps x 4 pairs at 128 registers (spills; 0.48 vs 0.39 ms, profiles/r02_ab_table.md)
+    const bool tile = h_reduced && h_tile && batch.n <= TILE_NW && batch.m <= TILE_NW * TILE_PPW &&
+                      tile_smem(batch.n, batch.m, TILE_NW, TILE_PPW, 2, true) <= smem_cap;
+    const int tile_grid = std::min((npix + 31) / 32, sm_count());
+    P.tile_wp = nullptr;
+    if (tile) {
+        const int nw = tile_nw, ppw = TILE_PPW;
+        if (g_icp.tile_wp_key != (const void *) batch.pairs || g_icp.tile_wp_nw != nw || g_icp.tile_wp_cur != (batch.ncurr > 0)) {
+            // pairs -> warp slots: greedy on the estimated cost of a pair (more with parameters that move the intrinsics, and when
+            // the row of its first parameter is not already held by the warp), warps that also form a first-order row start loaded
+            std::vector<char> moves(batch.n, 0);
+            if (batch.ncurr > 0 && batch_full.h_dintr)
+                for (int i = 0; i < batch.n; ++i)
+                    for (int c = 0; c < 4; ++c) moves[i] |= batch_full.h_dintr[4 * i + c] != 0.f;
+            std::vector<double> cost(batch.m), load(nw, 0.0);
+            std::vector<int> order(batch.m);
+            for (int k = 0; k < batch.m; ++k) {
+                const bool ci = moves[batch_full.h_pairs[k].x], cj = moves[batch_full.h_pairs[k].y];
+                cost[k] = 1.0 + 0.12 * ci + 0.12 * cj + 0.12 * (ci && cj);
+                order[k] = k;
+            }
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+            for (int w = 0; w < nw && w < batch.n; ++w) load[w] = 0.15;
+            std::vector<std::vector<int>> slots(nw);
+            for (int k : order) {
+                int best = -1;
+                double best_load = 0.0;
+                for (int w = 0; w < nw; ++w) {
+                    if ((int) slots[w].size() >= ppw) continue;
+                    bool has_i = false;
+                    for (int o : slots[w]) has_i |= batch_full.h_pairs[o].x == batch_full.h_pairs[k].x;
+                    const double l = load[w] + cost[k] + (has_i ? 0.0 : 0.13);
+                    if (best < 0 || l < best_load) best = w, best_load = l;
+                }
+                slots[best].push_back(k);
+                load[best] = best_load;
+            }
+            std::vector<int> wp((size_t) 16 * 5, -1);
+            for (int w = 0; w < nw; ++w) {
+                std::sort(slots[w].begin(), slots[w].end());
+                for (size_t h = 0; h < slots[w].size(); ++h) wp[(size_t) w * ppw + h] = slots[w][h];
+            }
+            XS_CUDA(cudaStreamSynchronize(s));  // queued iterations may still read the previous table
+            if (!g_icp.d_tile_wp) XS_CUDA(cudaMalloc(&g_icp.d_tile_wp, wp.size() * sizeof(int)));
+            XS_CUDA(cudaMemcpy(g_icp.d_tile_wp, wp.data(), wp.size() * sizeof(int), cudaMemcpyHostToDevice));
+            g_icp.tile_wp_key = (const void *) batch.pairs;
+            g_icp.tile_wp_nw = nw;
+            g_icp.tile_wp_cur = batch.ncurr > 0;
+        }
+        P.tile_wp = g_icp.d_tile_wp;
+    }
+    size_t dpart_need = (size_t) P.groups * P.max_writers * 81;
+    if (tile) dpart_need = std::max(dpart_need, (size_t) tile_grid * (batch.n * 27 + batch.m * 6));
+    int rc = icp_reserve(scp, ncomp, npix, dpart_need, P.groups, split ? IcpScratch::MAX_SLOTS : 1);
     if (rc != XS_OK) return rc;
     P.done_ticket = g_icp.d_done_ticket;
     const int nvals = 27 * (1 + ncomp);
@@ -1768,8 +2195,17 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
         // 55 directions: the deeper pipeline costs L1 capacity and does not raise issue utilisation); XS_ICP_STAGES=3 selects it
         const int stages = stages_env == 3 ? 3 : 2;
         if (no_tail && split) S.pose_out = nullptr;
-        if (hessian)
-        {
+        if (hessian && tile) {
+            static const int tile_pipe = env_int("XS_ICP_TILE_PIPE", 1), tile_depth = env_int("XS_ICP_TILE_DEPTH", 1);
+            const bool cur = batch.ncurr > 0;
+#define XS_TILE(NW_, PPW_, PIPE_, DEPTH_) \
+    (cur ? launch_deriv_tile<NW_, PPW_, true, PIPE_, DEPTH_>(P, S, tile_grid, s) : launch_deriv_tile<NW_, PPW_, false, PIPE_, DEPTH_>(P, S, tile_grid, s))
+            if (tile_pipe)
+                rc = tile_depth == 2 ? XS_TILE(TILE_NW, TILE_PPW, true, 2) : XS_TILE(TILE_NW, TILE_PPW, true, 1);
+            else
+                rc = tile_depth == 2 ? XS_TILE(TILE_NW, TILE_PPW, false, 2) : XS_TILE(TILE_NW, TILE_PPW, false, 1);
+#undef XS_TILE
+        } else if (hessian) {
             if (batch.ncurr > 0)  // a parameter moves the intrinsics: the current-frame maps carry derivative components
                 rc = h_reduced ? launch_deriv_h<2, 2, 2, true, true>(P, S, deriv_grid, s) : launch_deriv_h<2, 2, 2, false, true>(P, S, deriv_grid, s);
             else
