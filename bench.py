@@ -164,9 +164,10 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this same
-# command (profiles/r01g_ncu_summary.md: 512^3, 55 DCSFD directions, 1 GPU); None for any other configuration.
-TRAFFIC_BY_MODE = {"dcsfd": {"icp_deriv": 1.243e9, "integrate": 6.40e8, "raycast_hit": 1.40e9}}  # profiles/r01g_ncu_summary.md
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this same
+# command (512^3, 55 directions, 1 GPU; the Hessian batch with its default parameters); None for any other configuration.
+TRAFFIC_BY_MODE = {"dcsfd": {"icp_deriv": 1.243e9, "integrate": 6.40e8, "raycast_hit": 1.40e9},      # profiles/r01g_ncu_summary.md
+                   "hessian": {"icp_deriv": 5.306e8, "integrate": 2.449e8, "raycast_hit": 5.190e8}}  # profiles/r02s_ncu_summary.md
 TRAFFIC = {}
 
 
@@ -339,7 +340,7 @@ def run_reference(args, rank):
 BATCH_NOTE = {"hessian": "Hessian-structured batch (comps = 2): n first-order planes + one second-order plane per parameter pair",
               "dcsfd": "DCSFD list (comps = 3): every pair an independent bicomplex direction (eps1, eps2, eps1eps2)",
               "csfd": "CSFD list (comps = 1): independent first-order directions"}
-ICP_KERNEL = {"hessian": "icp_deriv_h_kernel", "dcsfd": "icp_deriv_kernel<3>", "csfd": "icp_deriv_kernel<1>"}
+ICP_KERNEL = {"hessian": "icp_deriv_tile_kernel", "dcsfd": "icp_deriv_kernel<3>", "csfd": "icp_deriv_kernel<1>"}
 
 
 class DeviceRecord:
@@ -498,7 +499,7 @@ def run_ours(args, xs, rank, world, local_rank):
         if world > 1:
             dist.destroy_process_group()
         return
-    if world == 1 and args.res == 512 and args.dirs == 55:
+    if world == 1 and args.res == 512 and args.dirs == 55 and not (mode == "hessian" and args.pose_only):
         TRAFFIC.update(TRAFFIC_BY_MODE.get(mode, {}))
     peak, peak_src = measured_hbm_peak()
     int_bytes = abytes["integrate"] / NF
@@ -544,7 +545,7 @@ def run_ours(args, xs, rank, world, local_rank):
                      "achieved": icp_achieved, "peak": peak, "unit": "GB/s", "frac": icp_achieved / peak, "traffic": TRAFFIC.get("icp_deriv"),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": icp_bytes, "kernel_ms": icp_kernel_ms, "launches_timed": icp_n,
                      "bytes_model": "P0 x (48 + 24 D) + 27 x 8 x (1 + D), D = derivative planes, each counted once (SURVEY 8d)",
-                     "fp32_floor_note": "this kernel is co-bound by the FP32 FMA pipe (DESIGN.md 5.2)"},
+                     "co_bound_note": "instruction issue at 11 warps per SM and the L1 capacity left beside 158 KB of staging bound this kernel before HBM does (DESIGN.md 5.2)"},
         "roofline_integrate": {"bound": "hbm", "kernel": "integrate_kernel<%s>" % mode, "achieved": achieved, "peak": peak, "unit": "GB/s",
                                "frac": achieved / peak, "traffic": TRAFFIC.get("integrate"), "algorithmic_bytes_per_launch": int_bytes,
                                "kernel_ms": int_ms, "updated_voxels_per_launch": upd / NF,
