@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--pose-only", action="store_true",
                     help="hessian / dcsfd mode: the parameters beyond the 6 pose DoF are mixed pose-space directions instead of the "
                          "intrinsics fx, fy, cx, cy (round 1's workload)")
+    ap.add_argument("--emulate-share", default=None, metavar="R/N",
+                    help="hessian mode on one GPU: run rank R's share of an N-rank job (profiling aid; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sync-frames", action="store_true",
                     help="ProcessFrame waits for the end of each frame like the reference's (default: deferred mode, the "
@@ -360,12 +362,22 @@ def run_ours(args, xs, rank, world, local_rank):
     max_dirs = (args.dirs + world - 1) // world
     if mode == "hessian":
         # every rank carries the n first-order components (cheap, and every pair needs two of them) and its share of the pairs
+        # blocked shards (parallel.plan_hessian_shards): a rank carries its block of the pairs and the first-order components of
+        # the parameters those pairs touch - the real state is replicated
+        from xslam_b200 import parallel as par
         U, pairs, dintr = hessian_params(args.dirs, intrinsics=not args.pose_only)
         n_params = U.shape[0]
-        my_pairs = pairs[rank::world]
-        my_seeds, _ = xs.hessian_seeds(U, my_pairs)
-        k.SetYamlParameters(cfg, comps=2, seeds=my_seeds, pairs=my_pairs, n_params=n_params, intrinsic_seeds=dintr)
-        ncomp_local, ncomp_max = n_params + len(my_pairs), n_params + max_dirs
+        share_rank, share_world = rank, world
+        if args.emulate_share:  # one GPU running rank r's share of an N-rank job (profiling aid)
+            share_rank, share_world = (int(t) for t in args.emulate_share.split("/"))
+        plan = par.plan_hessian_shards(n_params, pairs, share_world)
+        mine = plan[share_rank]
+        my_seeds, _ = xs.hessian_seeds(U[mine["params"]], mine["local_pairs"])
+        my_dintr = None if dintr is None else np.ascontiguousarray(dintr[mine["params"]])
+        if my_dintr is not None and not my_dintr.any():
+            my_dintr = None
+        k.SetYamlParameters(cfg, comps=2, seeds=my_seeds, pairs=mine["local_pairs"], n_params=len(mine["params"]), intrinsic_seeds=my_dintr)
+        ncomp_local, ncomp_max = len(mine["params"]) + len(mine["pair_ids"]), par.planned_record_floats(plan) // 16 - 1
         planes_total = n_params + len(pairs)
     else:
         comps = 1 if mode == "csfd" else 3
@@ -534,7 +546,7 @@ def run_ours(args, xs, rank, world, local_rank):
                    "parameters": ("6 pose DoF + fx, fy, cx, cy" if (mode == "hessian" and not args.pose_only and args.dirs == 55)
                                   else "pose-space directions") if mode != "csfd" else "pose-space directions",
                    "derivative_planes": planes_total, "derivative_planes_rank0": ncomp_local, "directions_per_rank": max_dirs,
-                   "sharding": "second-order pairs over ranks, first-order components and real state replicated" if mode == "hessian"
+                   "sharding": "blocks of the second-order pairs over ranks, each with the first-order components its pairs touch; real state replicated" if mode == "hessian"
                                else "directions over ranks, real state replicated",
                    "frame_sync": "deferred (end-of-frame wait at the start of the next ProcessFrame; ICP result read on the host every frame)" if deferred else "every frame",
                    "l2": "per-step working set (volume %.1f GB/rank) >> 126 MB L2, no flush needed" % (lib.xs_volume_bytes(vol) / 1e9)},

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Hardware check of the multi-GPU layer (run under torchrun on N >= 2 GPUs of one box):
-the N-rank run - every rank carries all first-order components and its share of the second-order pairs, the library
+the N-rank run - every rank carries its block of the second-order pairs and the first-order components of the parameters
+those pairs touch (parallel.plan_hessian_shards), the library
 all-gathers the pose records over NCCL after every frame (csrc/comm.cpp) - against the 1-rank run of the full batch on rank 0:
 the gathered record must equal the full record, bit for bit on the real part and <= 1e-6 relative on derivative components.
 
@@ -32,12 +33,13 @@ def main():
     U = np.concatenate([np.eye(6), rng.standard_normal((2, 6)) / np.sqrt(6)])  # 8 parameters, 36 pairs
     n = U.shape[0]
     pairs = xs.all_pairs(n)
-    mine = parallel.shard_pairs(pairs, rank, world)
-    seeds, _ = xs.hessian_seeds(U, mine)
+    plan = parallel.plan_hessian_shards(n, pairs, world)  # blocked shards: a rank carries only the parameters its pairs touch
+    mine = plan[rank]
+    seeds, _ = xs.hessian_seeds(U[mine["params"]], mine["local_pairs"])
     k = xs.KinectFusionReconstruction()
-    k.SetYamlParameters(cfg, comps=2, seeds=seeds, pairs=mine, n_params=n)
+    k.SetYamlParameters(cfg, comps=2, seeds=seeds, pairs=mine["local_pairs"], n_params=len(mine["params"]))
     comm = parallel.Comm.from_torch_distributed(dist, device="cuda")
-    L = parallel.hessian_record_floats(n, len(pairs), world)
+    L = parallel.planned_record_floats(plan)
     k.set_comm(comm, L)
     k.set_deferred(True)
     full = None
@@ -45,16 +47,19 @@ def main():
         sf, _ = xs.hessian_seeds(U, pairs)
         full = xs.KinectFusionReconstruction()
         full.SetYamlParameters(cfg, comps=2, seeds=sf, pairs=pairs, n_params=n)
-    rep = {"world": world, "parameters": n, "pairs": len(pairs), "frames": []}
+    rep = {"world": world, "parameters": n, "pairs": len(pairs), "planes_per_rank": [len(sh["params"]) + len(sh["pair_ids"]) for sh in plan],
+           "frames": []}
     ok = True
     for f in range(frames):
         d = xs.synth_depth(f)
         assert k.ProcessFrame(d) == 1
         g = k.gathered_records()
-        rec = parallel.assemble_hessian_records(g, n, pairs, world)
-        # replicas: every rank produced the same real pose and the same first-order components
-        same_real = bool((g.reshape(world, -1, 16)[:, 0] == g.reshape(world, -1, 16)[0, 0]).all())
-        same_first = bool((g.reshape(world, -1, 16)[:, 1:1 + n] == g.reshape(world, -1, 16)[0, 1:1 + n]).all())
+        g = np.asarray(g.cpu() if hasattr(g, "cpu") else g)
+        rec = parallel.assemble_planned_records(g, plan, n, len(pairs))
+        # replicas: every rank produced the same real pose, and the ranks that share a parameter the same first-order component
+        gr = g.reshape(world, -1, 16)
+        same_real = bool((gr[:, 0] == gr[0, 0]).all())
+        same_first = all(np.array_equal(gr[r][1 + i], rec[1 + q]) for r, sh in enumerate(plan) for i, q in enumerate(sh["params"]))
         fr = {"frame": f, "replicas_real_identical": same_real, "replicas_first_order_identical": same_first}
         if rank == 0:
             assert full.ProcessFrame(d) == 1

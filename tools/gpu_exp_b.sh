@@ -1,7 +1,7 @@
 #!/bin/bash
 TAG=${1:-r02m}
 mkdir -p gpurun_out
-XS_ICP_TILE_PIPE=0 timeout 1200 python -m pytest tests/test_gpu_hessian.py -m gpu -q > gpurun_out/test_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_$TAG.log
+timeout 1200 python -m pytest tests/test_gpu_hessian.py -m gpu -q > gpurun_out/test_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_$TAG.log
 rm -f gpurun_out/*.npz
 tail -5 gpurun_out/test_$TAG.log | cut -c1-600
 run() {
@@ -9,13 +9,19 @@ echo "== $* $EXTRA"
 env "$@" timeout 300 python bench.py --no-cpu-baseline --no-ref-cuda --steps 10 --warmup 3 $EXTRA 2> gpurun_out/exp_$TAG.err | python -c "
 import sys, json
 r = json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('fps %.1f' % r['value'], r['config']['parameters'], r['stages_ms_per_frame'], r['kernel_ms_per_frame'], r['roofline']['kernel_ms'])
+print('fps %.1f' % r['value'], r['config']['derivative_planes_rank0'], r['stages_ms_per_frame'], r['kernel_ms_per_frame'], r['roofline']['kernel_ms'])
 " | tee -a gpurun_out/exp_$TAG.txt
 tail -3 gpurun_out/exp_$TAG.err
 }
+EXTRA="--emulate-share 3/8"
+run XS_ICP_TILE_DEPTH=1
+run XS_ICP_TILE_DEPTH=2
+run XS_ICP_TILE_DEPTH=4
+run XS_ICP_H_TILE=0
+EXTRA="--emulate-share 1/4"
+run XS_ICP_TILE_DEPTH=1
+run XS_ICP_TILE_DEPTH=0
+EXTRA="--emulate-share 0/2"
+run XS_ICP_TILE_DEPTH=0
 EXTRA=""
-run XS_ICP_TILE_PIPE=1
-run XS_ICP_TILE_PIPE=0
-EXTRA="--pose-only"
-run XS_ICP_TILE_PIPE=1
-run XS_ICP_TILE_PIPE=0
+run XS_ICP_TILE_DEPTH=0

@@ -1531,16 +1531,15 @@ __global__ void __launch_bounds__(NW * 32, 1) icp_deriv_tile_kernel(const IcpPar
     }
     // Pipeline.  Between two barriers a warp runs phase B of tile j + 1 and phase C of tile j; the small part of tile j + 3 and
     // the big part of tile j + 2 are issued at the top of iteration j (one commit group), two iterations before they are read.
-    int qs[5];  // matched indices of tiles j .. j + 4
+    constexpr int R = DEPTH + 3;
+    int qs[R];  // matched indices of tiles j .. j + DEPTH + 2
 #pragma unroll
-    for (int i = 0; i < 5; ++i) qs[i] = idx_at(i);
+    for (int i = 0; i < R; ++i) qs[i] = idx_at(i);
     issue_small(0, 0, qs[0]);
-    issue_small(1, 1, qs[1]);
-    issue_big(0, qs[0]);
-    cp_async_commit();
-    if (DEPTH == 2) {
-        issue_small(2, 2, qs[2]);
-        issue_big(1, qs[1]);
+#pragma unroll
+    for (int g = 0; g < DEPTH; ++g) {  // commit group g: small part of tile g + 1, big part of tile g
+        issue_small(g + 1, g + 1, qs[g + 1]);
+        issue_big(g, qs[g]);
         cp_async_commit();
     }
     if (PIPE) {
@@ -1563,8 +1562,8 @@ __global__ void __launch_bounds__(NW * 32, 1) icp_deriv_tile_kernel(const IcpPar
         }
         const int q = qs[0];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) qs[i] = qs[i + 1];
-        qs[4] = idx_at(j + 5);
+        for (int i = 0; i < R - 1; ++i) qs[i] = qs[i + 1];
+        qs[R - 1] = idx_at(j + R);
         // ---- phase C: this warp's pairs on tile j
         if (q >= 0) {
             Px p;
@@ -2068,8 +2067,10 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
     static const int h_tile = env_int("XS_ICP_H_TILE", 1);
     const size_t smem_cap = 227 * 1024;
     const int tile_nw = TILE_NW;  // measured and rejected: 16 warps x 4 pairs at 128 registers (spills; 0.48 vs 0.39 ms, profiles/r02_ab_table.md)
-    const bool tile = h_reduced && h_tile && batch.n <= TILE_NW && batch.m <= TILE_NW * TILE_PPW &&
-                      tile_smem(batch.n, batch.m, TILE_NW, TILE_PPW, 2, true) <= smem_cap;
+    // (a small share of the pairs - one rank of an 8-GPU job holds 7 - leaves the tiles too little work per barrier: the task
+    // form is faster there, 0.104 vs 0.120 ms per level-0 launch at 4 parameters + 7 pairs)
+    const bool tile = h_reduced && h_tile && batch.m >= 24 && batch.n <= TILE_NW && batch.m <= TILE_NW * TILE_PPW &&
+                      tile_smem(batch.n, batch.m, TILE_NW, TILE_PPW, 1, true) <= smem_cap;
     const int tile_grid = std::min((npix + 31) / 32, sm_count());
     P.tile_wp = nullptr;
     if (tile) {
@@ -2196,14 +2197,25 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
         const int stages = stages_env == 3 ? 3 : 2;
         if (no_tail && split) S.pose_out = nullptr;
         if (hessian && tile) {
-            static const int tile_pipe = env_int("XS_ICP_TILE_PIPE", 1), tile_depth = env_int("XS_ICP_TILE_DEPTH", 1);
+            // look-ahead of the staging: as deep as fits beside ~96 KB of L1 (the L1 left over holds the lines of the in-flight
+            // gathers: profiles/r02_ab_table.md) - one tile at 10 parameters / 55 pairs, four for an 8-rank share
+            static const int tile_pipe = env_int("XS_ICP_TILE_PIPE", 1), tile_depth_env = env_int("XS_ICP_TILE_DEPTH", 0);
             const bool cur = batch.ncurr > 0;
+            int tile_depth = 1;
+            for (int d : {2, 4})
+                if (tile_smem(batch.n, batch.m, TILE_NW, TILE_PPW, d, true) <= 160 * 1024) tile_depth = d;
+            if (tile_depth_env == 1 || tile_depth_env == 2 || tile_depth_env == 4) tile_depth = tile_depth_env;
+            if (tile_smem(batch.n, batch.m, TILE_NW, TILE_PPW, tile_depth, true) > smem_cap) tile_depth = 1;
 #define XS_TILE(NW_, PPW_, PIPE_, DEPTH_) \
     (cur ? launch_deriv_tile<NW_, PPW_, true, PIPE_, DEPTH_>(P, S, tile_grid, s) : launch_deriv_tile<NW_, PPW_, false, PIPE_, DEPTH_>(P, S, tile_grid, s))
-            if (tile_pipe)
-                rc = tile_depth == 2 ? XS_TILE(TILE_NW, TILE_PPW, true, 2) : XS_TILE(TILE_NW, TILE_PPW, true, 1);
+            if (!tile_pipe)
+                rc = XS_TILE(TILE_NW, TILE_PPW, false, 1);
+            else if (tile_depth == 4)
+                rc = XS_TILE(TILE_NW, TILE_PPW, true, 4);
+            else if (tile_depth == 2)
+                rc = XS_TILE(TILE_NW, TILE_PPW, true, 2);
             else
-                rc = tile_depth == 2 ? XS_TILE(TILE_NW, TILE_PPW, false, 2) : XS_TILE(TILE_NW, TILE_PPW, false, 1);
+                rc = XS_TILE(TILE_NW, TILE_PPW, true, 1);
 #undef XS_TILE
         } else if (hessian) {
             if (batch.ncurr > 0)  // a parameter moves the intrinsics: the current-frame maps carry derivative components

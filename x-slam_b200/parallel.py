@@ -133,3 +133,92 @@ def assemble_list_records(gathered, n_dirs, comps, world):
         for c in range(comps):
             rows.append(g[r][1 + local * comps + c])
     return np.stack(rows)
+
+
+# ------------------------------------------------------------------ blocked shards of a Hessian batch
+def plan_hessian_shards(n_params, pairs, world, iters=20000):
+    """Which rank carries which second-order pairs - and therefore which parameters - of a Hessian batch.
+
+    A rank that holds pair (i, j) needs the first-order components of i and j as well, so round-robin shards end up carrying
+    all n first-order planes on every rank (17 planes per rank for 10 parameters / 55 pairs on 8 ranks).  Here the pairs are
+    dealt so that a rank's pairs share few parameters (blocks of the upper triangle): a deterministic local search on
+    (max planes per rank, sum of squares), planes = |parameters touched| + |pairs|, reaches 12 planes per rank for that case.
+    Every rank computes the same plan.  Returns one dict per rank:
+      params: sorted global parameter ids, pair_ids: sorted indices into `pairs`, local_pairs: the pairs in local parameter indices."""
+    import random
+    pairs = [tuple(p) for p in pairs]
+    m = len(pairs)
+    if world == 1:
+        shards = [list(range(m))]
+    else:
+        order = sorted(range(m), key=lambda k: (max(pairs[k]), min(pairs[k])))
+        shards = [[] for _ in range(world)]
+        for t, k in enumerate(order):
+            shards[t * world // m].append(k)
+
+        def score(sh):
+            c = [len({q for k in s_ for q in pairs[k]}) + len(s_) for s_ in sh]
+            return max(c), sum(x * x for x in c)
+
+        rnd = random.Random(12345)
+        best = score(shards)
+        for _ in range(iters):
+            a, b = rnd.randrange(world), rnd.randrange(world)
+            if a == b or not shards[a]:
+                continue
+            ia = rnd.randrange(len(shards[a]))
+            if shards[b] and rnd.random() < 0.5:
+                ib = rnd.randrange(len(shards[b]))
+                shards[a][ia], shards[b][ib] = shards[b][ib], shards[a][ia]
+                sc = score(shards)
+                if sc <= best:
+                    best = sc
+                else:
+                    shards[a][ia], shards[b][ib] = shards[b][ib], shards[a][ia]
+            else:
+                k = shards[a].pop(ia)
+                shards[b].append(k)
+                sc = score(shards)
+                if sc <= best:
+                    best = sc
+                else:
+                    shards[b].pop()
+                    shards[a].insert(ia, k)
+    plan = []
+    for s_ in shards:
+        ids = sorted(s_, key=lambda k: pairs[k])
+        params = sorted({q for k in ids for q in pairs[k]})
+        loc = {g: i for i, g in enumerate(params)}
+        plan.append({"params": params, "pair_ids": ids, "local_pairs": [(loc[pairs[k][0]], loc[pairs[k][1]]) for k in ids]})
+    # every parameter's first-order component must come from somewhere: parameters no pair touches go to the lightest rank
+    seen = {q for sh in plan for q in sh["params"]}
+    for g in range(n_params):
+        if g not in seen:
+            sh = min(plan, key=lambda d: len(d["params"]) + len(d["pair_ids"]))
+            sh["params"] = sorted(sh["params"] + [g])
+            loc = {q: i for i, q in enumerate(sh["params"])}
+            sh["local_pairs"] = [(loc[pairs[k][0]], loc[pairs[k][1]]) for k in sh["pair_ids"]]
+    return plan
+
+
+def planned_record_floats(plan):
+    """floats per rank in the gather: the largest record of the plan, (1 + n_local + m_local) 4x4 matrices."""
+    return max(1 + len(sh["params"]) + len(sh["pair_ids"]) for sh in plan) * 16
+
+
+def assemble_planned_records(gathered, plan, n_params, n_pairs):
+    """gathered: [world, record_floats] (numpy).  Returns the full record [(1 + n + m), 16]: the real part from rank 0, the
+    first-order component of a parameter from the lowest rank that carries it, pair k from the rank that owns it."""
+    g = np.asarray(gathered).reshape(len(plan), -1, 16)
+    full = np.zeros((1 + n_params + n_pairs, 16), g.dtype)
+    full[0] = g[0][0]
+    done = set()
+    for r, sh in enumerate(plan):
+        nl = len(sh["params"])
+        for i, q in enumerate(sh["params"]):
+            if q not in done:
+                full[1 + q] = g[r][1 + i]
+                done.add(q)
+        for i, k in enumerate(sh["pair_ids"]):
+            full[1 + n_params + k] = g[r][1 + nl + i]
+    return full
