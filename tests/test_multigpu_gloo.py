@@ -51,3 +51,57 @@ def test_shards_partition_all_directions():
             shards = [parallel.shard_directions(n, r, w) for r in range(w)]
             assert sorted(sum(shards, [])) == list(range(n))
             assert max(len(s) for s in shards) == parallel.max_dirs_per_rank(n, w)
+
+
+def _planned_worker(rank, world, port, n, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from xslam_b200 import parallel
+    pairs = [(i, j) for i in range(n) for j in range(i, n)]
+    plan = parallel.plan_hessian_shards(n, pairs, world)  # every rank computes the same plan
+    mine = plan[rank]
+    L = parallel.planned_record_floats(plan)
+    # fake record of this rank: real row, one row per local parameter (value 1000 + global id), one per local pair (2000 + pair id)
+    rec = torch.zeros(L)
+    rows = rec.view(-1, 16)
+    rows[0] = torch.arange(16.0)
+    for i, q in enumerate(mine["params"]):
+        rows[1 + i] = 1000.0 + q
+    for i, k in enumerate(mine["pair_ids"]):
+        rows[1 + len(mine["params"]) + i] = 2000.0 + k
+    out = torch.zeros(world * L)
+    dist.all_gather_into_tensor(out, rec)
+    full = parallel.assemble_planned_records(out.numpy().reshape(world, L), plan, n, len(pairs))
+    ok = full.shape == (1 + n + len(pairs), 16) and bool((full[0] == np.arange(16.0)).all())
+    ok = ok and all((full[1 + q] == 1000.0 + q).all() for q in range(n))
+    ok = ok and all((full[1 + n + k] == 2000.0 + k).all() for k in range(len(pairs)))
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_blocked_hessian_shards_gather_over_gloo():
+    world = 2
+    port = 29500 + (os.getpid() + 77) % 500
+    ret = mp.Manager().dict()
+    mp.spawn(_planned_worker, args=(world, port, 10, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
+
+
+def test_blocked_hessian_shards_cover_every_pair_once():
+    sys.path.insert(0, ROOT)
+    from xslam_b200 import parallel
+    for n in (3, 6, 10):
+        pairs = [(i, j) for i in range(n) for j in range(i, n)]
+        for w in (1, 2, 4, 8):
+            plan = parallel.plan_hessian_shards(n, pairs, w, iters=4000)
+            assert sorted(k for sh in plan for k in sh["pair_ids"]) == list(range(len(pairs)))
+            assert {q for sh in plan for q in sh["params"]} == set(range(n))
+            for sh in plan:  # the local pairs address the rank's own parameter list, sorted by the first parameter
+                assert [(sh["params"][a], sh["params"][b]) for a, b in sh["local_pairs"]] == [pairs[k] for k in sh["pair_ids"]]
+                assert sh["local_pairs"] == sorted(sh["local_pairs"])
+            planes = max(len(sh["params"]) + len(sh["pair_ids"]) for sh in plan)
+            assert planes <= n + (len(pairs) + w - 1) // w  # never more planes per rank than round-robin shards
+    plan = parallel.plan_hessian_shards(10, [(i, j) for i in range(10) for j in range(i, 10)], 8)
+    assert max(len(sh["params"]) + len(sh["pair_ids"]) for sh in plan) <= 12
