@@ -1,27 +1,19 @@
 #!/bin/bash
 TAG=${1:-r02m}
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_hessian.py -m gpu -q > gpurun_out/test_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_$TAG.log
+XS_INT_BULK=1 timeout 100 python -m pytest tests/test_gpu_hessian.py -m gpu -q -x > gpurun_out/test_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_$TAG.log
 rm -f gpurun_out/*.npz
 tail -5 gpurun_out/test_$TAG.log | cut -c1-600
+grep -q "rc=0" gpurun_out/test_$TAG.log || exit 1
 run() {
 echo "== $* $EXTRA"
-env "$@" timeout 300 python bench.py --no-cpu-baseline --no-ref-cuda --steps 10 --warmup 3 $EXTRA 2> gpurun_out/exp_$TAG.err | python -c "
+env "$@" timeout 120 python bench.py --no-cpu-baseline --no-ref-cuda --steps 10 --warmup 3 $EXTRA 2> gpurun_out/exp_$TAG.err | python -c "
 import sys, json
 r = json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('fps %.1f' % r['value'], r['config']['derivative_planes_rank0'], r['stages_ms_per_frame'], r['kernel_ms_per_frame'], r['roofline']['kernel_ms'])
 " | tee -a gpurun_out/exp_$TAG.txt
 tail -3 gpurun_out/exp_$TAG.err
 }
-EXTRA="--emulate-share 3/8"
-run XS_ICP_TILE_DEPTH=1
-run XS_ICP_TILE_DEPTH=2
-run XS_ICP_TILE_DEPTH=4
-run XS_ICP_H_TILE=0
-EXTRA="--emulate-share 1/4"
-run XS_ICP_TILE_DEPTH=1
-run XS_ICP_TILE_DEPTH=0
-EXTRA="--emulate-share 0/2"
-run XS_ICP_TILE_DEPTH=0
 EXTRA=""
-run XS_ICP_TILE_DEPTH=0
+run XS_INT_BULK=1
+XS_INT_BULK=1 timeout 200 bash tools/gpu_ncu.sh ${TAG}_bulk integrate

@@ -116,6 +116,8 @@ struct SolveParams {
     int dirs, ncomp, solve_mode;
     int deriv_only;        // the real part of the step is owned by another launch (split chains): only the derivative
                            // components of pose_out are written, the status flags are read but not set
+    const int *status_in;  // Hessian tails: the two status flags staged in shared memory (null: read P.status)
+    int staged;            // Hessian tails: sums / real_cache / pose_in point to shared-memory copies (plain loads)
     double *real_cache;    // split chains, [REAL_CACHE]: Cholesky factor (36), reciprocal pivots (6) and real solution (6) of
                            // this iteration, stored by the real step and loaded by the derivative tails (which then skip the
                            // determinant guard - the real step has already set the status - the factorisation and the real solve)
@@ -123,9 +125,7 @@ struct SolveParams {
 constexpr int REAL_CACHE = 48;
 template <int C> __device__ __noinline__ void icp_solve_direction(const SolveParams &P, int q, const double *real_sums,
                                                                   const double *comp_sums);
-__device__ __noinline__ void icp_solve_hessian_first(const SolveParams &P, int i, const double *real_sums, double *x_out);
-__device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n, int k, int2 pr, const double *real_sums, const double *x_first,
-                                                    bool reduced);
+template <int NT> __device__ void icp_hessian_tail(const IcpParams &P, const SolveParams &S, unsigned char *s_raw, bool reduced, int tid);
 
 // search_newton (ICP.cu:196-244) on real parts with the reference's rounding sequence: projection of the current
 // vertex into the previous frame, bounds / NaN / distance / angle gates.  Outputs vcurr, vcurr_g and the matched pixel.
@@ -1319,16 +1319,7 @@ __global__ void __launch_bounds__(256, MINB) icp_deriv_h_kernel(const IcpParams 
     __threadfence();
     if (tid == 0) *P.done_ticket = 0u;
     if (!S.pose_out) return;
-    const int n = P.batch.n, ncomp = P.batch.n + P.batch.m;
-    double *s_real = reinterpret_cast<double *>(s_raw);  // [27]; the staging area is idle here
-    double *s_x1 = s_real + 32;                          // [n][6] first-order solutions
-    if (tid < 27) s_real[tid] = __ldcg(P.sums + tid);    // real sums of icp_assoc_kernel (previous launch)
-    __syncthreads();
-    if (S.log)
-        for (int i = tid; i < 27 * (1 + ncomp); i += 256) S.log[i] = __ldcg(P.sums + i);
-    for (int i = tid; i < n; i += 256) icp_solve_hessian_first(S, i, s_real, s_x1 + 6 * i);
-    __syncthreads();
-    for (int k = tid; k < P.batch.m; k += 256) icp_solve_hessian_pair(S, n, k, __ldg(P.batch.pairs + k), s_real, s_x1, REDUCED);
+    icp_hessian_tail<256>(P, S, s_raw, REDUCED, tid);
 }
 
 // ---- tile form of the REDUCED Hessian derivative pass -------------------------------------------------------------------------
@@ -1406,9 +1397,10 @@ __global__ void __launch_bounds__(NW * 32, 1) icp_deriv_tile_kernel(const IcpPar
     // ---- this warp's components
     const int fp = warp < n ? warp : -1;  // first-order parameter (host: n <= NW)
     // this warp's pairs (P.tile_wp: [NW][PPW] pair indices, -1 = none; dealt by the host so that the warps carry equal work)
-    int wk[PPW];
-#pragma unroll
-    for (int h = 0; h < PPW; ++h) wk[h] = __ldg(P.tile_wp + warp * PPW + h);
+    // (kept in shared memory: as registers they are spilled, and the local-memory reloads miss an L1 the staging keeps evicting)
+    __shared__ int s_wk[NW * PPW];
+    for (int e = tid; e < NW * PPW; e += NW * 32) s_wk[e] = __ldg(P.tile_wp + e);
+    const int *wk = s_wk + warp * PPW;
     for (int k = tid; k < m; k += NW * 32) s_pair[k] = __ldg(P.batch.pairs + k);  // read per pair (broadcast) rather than held in registers
     __syncthreads();
     const float (&x)[6] = s_x;  // broadcast shared loads where used
@@ -1670,22 +1662,16 @@ __global__ void __launch_bounds__(NW * 32, 1) icp_deriv_tile_kernel(const IcpPar
     __syncthreads();
     if (tid == 0) *P.done_ticket = 0u;
     if (!S.pose_out) return;
-    // ---- tail: the Gauss-Newton step of every component (as in the task form)
-    double *s_real = reinterpret_cast<double *>(s_raw);  // [27]; the staging area is idle here
-    double *s_x1 = s_real + 32;                          // [n][6] first-order solutions
-    if (tid < 27) s_real[tid] = __ldcg(P.sums + tid);
-    __syncthreads();
-    for (int i = tid; i < n; i += NW * 32) icp_solve_hessian_first(S, i, s_real, s_x1 + 6 * i);
-    __syncthreads();
-    for (int k = tid; k < m; k += NW * 32) icp_solve_hessian_pair(S, n, k, __ldg(P.batch.pairs + k), s_real, s_x1, true);
+    icp_hessian_tail<NW * 32>(P, S, s_raw, true, tid);  // the Gauss-Newton step of every component
 }
 
 // ---- Gauss-Newton step of a Hessian batch (kind 2), one thread per component.
 // Real prelude shared by both task kinds: status flags, real A / b, Cholesky factor and real solution (loaded from the real
 // step's cache under split chains, computed otherwise).  Returns false when the iteration is skipped (degenerate system).
+XS_DEV double ld_sum(const SolveParams &P, const double *p) { return P.staged ? *p : __ldcg(p); }
 XS_DEV bool gn_real_prelude(const SolveParams &P, const double *real_sums, bool owns_real, double (&A)[6][6], double (&b)[6], Chol6 &F,
                             double (&xr)[6]) {
-    const int st0 = __ldcg(P.status), st1 = __ldcg(P.status + 1);
+    const int st0 = P.status_in ? P.status_in[0] : __ldcg(P.status), st1 = P.status_in ? P.status_in[1] : __ldcg(P.status + 1);
     if (st0 != 0 || st1 != 0) {
         if (owns_real) P.status[0] = st0 != 0 ? st0 : st1;
         return false;
@@ -1696,9 +1682,9 @@ XS_DEV bool gn_real_prelude(const SolveParams &P, const double *real_sums, bool 
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
 #pragma unroll
-            for (int j = 0; j < 6; ++j) F.L[i][j] = __ldcg(rc + i * 6 + j);
-            F.inv[i] = __ldcg(rc + 36 + i);
-            xr[i] = __ldcg(rc + 42 + i);
+            for (int j = 0; j < 6; ++j) F.L[i][j] = ld_sum(P, rc + i * 6 + j);
+            F.inv[i] = ld_sum(P, rc + 36 + i);
+            xr[i] = ld_sum(P, rc + 42 + i);
         }
         return true;
     }
@@ -1748,32 +1734,35 @@ XS_DEV void gn_pose_update(const SolveParams &P, const int (&comp)[C], const Jet
     }
 }
 
-// first-order component i: x_i = A^-1 (b_i - A_i x) (analytic) or the imaginary part of the Hermitian-LLT solve (LLT mode,
-// what a one-direction complex run of the reference yields).  x_out[6] is kept for the pairs.
-__device__ __noinline__ void icp_solve_hessian_first(const SolveParams &P, int i, const double *real_sums, double *x_out) {
-    const bool owns_real = i == 0 && !P.deriv_only;
-    double A[6][6], b[6], xr[6];
-    Chol6 F;
-#pragma unroll
-    for (int e = 0; e < 6; ++e) x_out[e] = 0.0;
-    if (!gn_real_prelude(P, real_sums, owns_real, A, b, F, xr)) return;
-    double Ai[6][6], bi[6], sums[27], xi[6];
-    for (int e = 0; e < 27; ++e) sums[e] = __ldcg(P.sums + (size_t) (1 + i) * 27 + e);
-    unpack_sums(sums, Ai, bi);
+// first-order solution of parameter p: x_p = A^-1 (b_p - A_p x) (analytic) or the imaginary part of the Hermitian-LLT solve
+// (LLT mode, what a one-direction complex run of the reference yields); A_p is returned for the pairs
+XS_DEV void first_order_solution(const SolveParams &P, int p, const double (&A)[6][6], const double (&b)[6], const Chol6 &F,
+                                 const double (&xr)[6], double (&Ap)[6][6], double (&xp)[6]) {
+    double bp[6], sums[27];
+    for (int e = 0; e < 27; ++e) sums[e] = ld_sum(P, P.sums + (size_t) (1 + p) * 27 + e);
+    unpack_sums(sums, Ap, bp);
     if (P.solve_mode == XS_SOLVE_EIGEN_LLT) {
         cplx xq[6];
-        llt_hermitian_solve6_dev(A, Ai, b, bi, xq);
-        for (int e = 0; e < 6; ++e) xi[e] = xq[e].im;
+        llt_hermitian_solve6_dev(A, Ap, b, bp, xq);
+        for (int e = 0; e < 6; ++e) xp[e] = xq[e].im;
     } else {
         double t[6], rhs[6];
-        matvec6_dev(Ai, xr, t);
-        for (int e = 0; e < 6; ++e) rhs[e] = bi[e] - t[e];
-        chol6_solve(F, rhs, xi);
+        matvec6_dev(Ap, xr, t);
+        for (int e = 0; e < 6; ++e) rhs[e] = bp[e] - t[e];
+        chol6_solve(F, rhs, xp);
     }
+}
+
+// first-order component i of a Hessian batch: solution + pose update
+__device__ __noinline__ void icp_solve_hessian_first(const SolveParams &P, int i, const double *real_sums) {
+    const bool owns_real = i == 0 && !P.deriv_only;
+    double A[6][6], b[6], xr[6], Ai[6][6], xi[6];
+    Chol6 F;
+    if (!gn_real_prelude(P, real_sums, owns_real, A, b, F, xr)) return;
+    first_order_solution(P, i, A, b, F, xr, Ai, xi);
     Jet<1, 1> x[6];
 #pragma unroll
     for (int e = 0; e < 6; ++e) {
-        x_out[e] = xi[e];
         x[e].v = (float) xr[e];
         x[e].d[0] = (float) xi[e];
     }
@@ -1782,32 +1771,36 @@ __device__ __noinline__ void icp_solve_hessian_first(const SolveParams &P, int i
 }
 
 // pair k = (i, j): x_ij = A^-1 (b_ij - A_ij x - A_i x_j - A_j x_i); the pose update runs in the bicomplex algebra on
-// (F_i, F_j, S_ij) and stores S_ij only
+// (F_i, F_j, S_ij) and stores S_ij only.  The thread forms x_i and x_j itself (the same arithmetic as the first-order threads,
+// so the same values) rather than waiting for them: one phase, no barrier.
 // (reduced: the derivative pass has already formed g_ij = b_ij - A_ij x, the first 6 values filed under the component)
-__device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n, int k, int2 pr, const double *real_sums, const double *x_first,
-                                                    bool reduced) {
+__device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n, int k, int2 pr, const double *real_sums, bool reduced) {
     double A[6][6], b[6], xr[6];
     Chol6 F;
     if (!gn_real_prelude(P, real_sums, false, A, b, F, xr)) return;
     double M[6][6], v[6], sums[27], rhs[6], t[6], xs[6];
     if (reduced) {
-        for (int e = 0; e < 6; ++e) rhs[e] = __ldcg(P.sums + (size_t) (1 + n + k) * 27 + e);
+        for (int e = 0; e < 6; ++e) rhs[e] = ld_sum(P, P.sums + (size_t) (1 + n + k) * 27 + e);
     } else {
-        for (int e = 0; e < 27; ++e) sums[e] = __ldcg(P.sums + (size_t) (1 + n + k) * 27 + e);
+        for (int e = 0; e < 27; ++e) sums[e] = ld_sum(P, P.sums + (size_t) (1 + n + k) * 27 + e);
         unpack_sums(sums, M, v);  // A_ij, b_ij
         matvec6_dev(M, xr, t);
         for (int e = 0; e < 6; ++e) rhs[e] = v[e] - t[e];
     }
     double xi[6], xj[6];
-    for (int e = 0; e < 6; ++e) xi[e] = x_first[6 * pr.x + e], xj[e] = x_first[6 * pr.y + e];
-    for (int e = 0; e < 27; ++e) sums[e] = __ldcg(P.sums + (size_t) (1 + pr.x) * 27 + e);
-    unpack_sums(sums, M, v);  // A_i
-    matvec6_dev(M, xj, t);
-    for (int e = 0; e < 6; ++e) rhs[e] -= t[e];
-    for (int e = 0; e < 27; ++e) sums[e] = __ldcg(P.sums + (size_t) (1 + pr.y) * 27 + e);
-    unpack_sums(sums, M, v);  // A_j
-    matvec6_dev(M, xi, t);
-    for (int e = 0; e < 6; ++e) rhs[e] -= t[e];
+    first_order_solution(P, pr.x, A, b, F, xr, M, xi);  // M = A_i
+    if (pr.y == pr.x) {
+        for (int e = 0; e < 6; ++e) xj[e] = xi[e];
+        matvec6_dev(M, xi, t);
+        for (int e = 0; e < 6; ++e) rhs[e] -= 2.0 * t[e];
+    } else {
+        double Mj[6][6];
+        first_order_solution(P, pr.y, A, b, F, xr, Mj, xj);
+        matvec6_dev(M, xj, t);  // A_i x_j
+        for (int e = 0; e < 6; ++e) rhs[e] -= t[e];
+        matvec6_dev(Mj, xi, t);  // A_j x_i
+        for (int e = 0; e < 6; ++e) rhs[e] -= t[e];
+    }
     chol6_solve(F, rhs, xs);
     Jet<3, 1> x[6];
 #pragma unroll
@@ -1819,6 +1812,37 @@ __device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n,
     }
     const int comp[3] = {pr.x, pr.y, n + k};
     gn_pose_update<3>(P, comp, x, 2, false);
+}
+
+// Tail of a Hessian derivative pass (run by the CTA that completed the last sums): the Gauss-Newton step of every component.
+// Everything the solves read - the sums of all components, the real step's factor, the pose tables, the status flags - is
+// staged into shared memory by the whole CTA first (one round of global latency instead of one per dependent load of a
+// single thread), then first-order components and pairs run side by side on different warps.
+template <int NT>
+XS_DEV void icp_hessian_tail(const IcpParams &P, const SolveParams &S, unsigned char *s_raw, bool reduced, int tid) {
+    const int n = P.batch.n, m = P.batch.m, nv = 27 * (1 + n + m), npose = 12 * (1 + n + m);
+    double *s_sums = reinterpret_cast<double *>(s_raw);  // the staging area of the derivative pass is idle here
+    double *s_rc = s_sums + nv;
+    float *s_pose = reinterpret_cast<float *>(s_rc + REAL_CACHE);
+    int *s_st = reinterpret_cast<int *>(s_pose + npose);
+    const bool cached_real = S.deriv_only && S.real_cache;
+    for (int i = tid; i < nv; i += NT) s_sums[i] = __ldcg(P.sums + i);
+    if (cached_real)
+        for (int i = tid; i < REAL_CACHE; i += NT) s_rc[i] = __ldcg(S.real_cache + i);
+    for (int i = tid; i < npose; i += NT) s_pose[i] = __ldcg(S.pose_in + i);
+    if (tid < 2) s_st[tid] = __ldcg(S.status + tid);
+    __syncthreads();
+    if (S.log)
+        for (int i = tid; i < nv; i += NT) S.log[i] = s_sums[i];
+    SolveParams L = S;
+    L.sums = s_sums;
+    L.pose_in = s_pose;
+    L.status_in = s_st;
+    L.staged = 1;
+    if (cached_real) L.real_cache = s_rc;
+    const int first_threads = ((n + 31) & ~31) % NT;  // pairs start on the warp after the first-order components
+    for (int i = tid; i < n; i += NT) icp_solve_hessian_first(L, i, s_sums);
+    for (int k = (tid + NT - first_threads) % NT; k < m; k += NT) icp_solve_hessian_pair(L, n, k, __ldg(P.batch.pairs + k), s_sums, reduced);
 }
 
 // persistent scratch of the ICP operator (gbuf / mbuf of the reference, ICP.cu:400-403)
@@ -2151,6 +2175,8 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
     P.tiles_x = div_up(cols, 32);
     P.tiles_y = div_up(rows, 8);
     SolveParams S;
+    S.status_in = nullptr;
+    S.staged = 0;
     S.sums = P.sums;
     S.deriv_only = split ? 1 : 0;
     S.real_cache = nullptr;

@@ -205,7 +205,41 @@ XS_DEV bool eval_voxel(const IntegrateParams &P, float vcx, float vcy, float vcz
 constexpr int INT_THREADS = 256;
 // KIND = batch kind (xs_batch.h): 1 = first-order list, 3 = bicomplex list, 2 = Hessian batch (needs gradient AND Hessian of
 // sdf like kind 3, but updates every first-order plane once and one second-order plane per listed pair).
-template <int KIND> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_kernel(const IntegrateParams P) {
+// ---- cp.async.bulk staging (experiment, XS_INT_BULK=1): north_star (2) asks for shared-memory staging of the brick spans with
+// TMA bulk copies "where the brick layout allows".  The layout allows it - the planes of a half brick are ncomp contiguous 1 KB
+// spans - so the variant below stages every plane of an already-live half brick with cp.async.bulk (UBLKCP) behind an mbarrier,
+// updates it in shared memory and writes it back with bulk stores; bricks that are not live yet keep the predicated LDG / STG
+// path.  Measured against the default path in profiles/r02_ab_table.md.
+XS_DEV unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+XS_DEV void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+XS_DEV void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+XS_DEV bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+XS_DEV void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+XS_DEV void bulk_s2g(void *gdst, const void *smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+XS_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+XS_DEV void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+XS_DEV void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+XS_DEV void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int KIND, bool BULK = false> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_kernel(const IntegrateParams P) {
     constexpr int C = (KIND == 1) ? 1 : 3;
     constexpr int K = (C == 1) ? 3 : 6;
     extern __shared__ float4 s_dpose4[];  // [ncomp][3] float4 = [ncomp][12] floats, then (kind 2) the pair table int2[m]
@@ -215,6 +249,12 @@ template <int KIND> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_
     int2 *s_pairs = reinterpret_cast<int2 *>(s_dpose + (size_t) ncomp * 12);
     if (KIND == 2)
         for (int i = threadIdx.x; i < P.batch.m; i += INT_THREADS) s_pairs[i] = P.batch.pairs[i];
+    // BULK: [ncomp][256] floats of the half brick in flight, 128-byte aligned behind the tables
+    float *s_stage = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(s_pairs + (KIND == 2 ? P.batch.m : 0)) + 127) & ~uintptr_t(127));
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ bool s_live;
+    unsigned bar_phase = 0;
+    if (BULK && threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
 
     const float vs = P.V.voxel;
@@ -231,7 +271,24 @@ template <int KIND> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_
         const int bx = entry.y & 1023, by = (entry.y >> 10) & 1023, bz = entry.y >> 20;
         // derivative planes of a brick that never held a truncation-band voxel are exactly zero: scaling them by
         // w/(w+1) is the identity, so free-space bricks move no derivative bytes at all
-        const bool live = ncomp > 0 && P.live[b] != 0;
+        bool live = ncomp > 0 && P.live[b] != 0;
+        if (BULK) {  // the flag may be raised by the CTA that holds the other half of the brick while this one reads it: one reader
+            __syncthreads();
+            if (threadIdx.x == 0) s_live = live;
+            __syncthreads();
+            live = s_live;
+        }
+        const bool staged = BULK && live;  // CTA-uniform
+        if (staged) {
+            if (threadIdx.x == 0) bulk_wait_read0();  // the stores of the previous staged half brick have left the buffer
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&s_bar, (unsigned) ncomp * 1024u);
+                const float *src = P.V.deriv + (size_t) b * ncomp * BRICK_VOX + ((hi & 1) << 8);
+                for (int q = 0; q < ncomp; ++q) bulk_g2s(s_stage + q * 256, src + (size_t) q * BRICK_VOX, 1024u, &s_bar);
+            }
+        }
+        [&]() {
         // ---- per-voxel real path (TsdfFusion.cu:110-114)
         const int x = bx * 8 + lx, y = by * 8 + ly, z = bz * 8 + lz;
         const float vgx = __fmul_rn(__fadd_rn(float(x), 0.5f), vs);
@@ -244,7 +301,7 @@ template <int KIND> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_
         // zero derivative); only voxels inside the truncation band pay for the Jacobian / Hessian jets below.
         Jet<1, 0> sdf;
         const bool upd = eval_voxel<1, 0>(P, vcx, vcy, vcz, sdf);
-        if (!upd) continue;  // no barrier inside the brick loop: threads are independent
+        if (!upd) return;  // no barrier inside the per-voxel work: threads are independent
         ++n_upd;
         // ---- TsdfFusion.cu:152-167
         const bool saturated = sdf.v > P.V.trunc;
@@ -254,17 +311,22 @@ template <int KIND> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_
         const float wf = __int2float_rn(w_prev), wf1 = __int2float_rn(w_prev + 1);
         P.V.value[vi] = __fdiv_rn(__fmaf_rn(P.V.value[vi], wf, tsdf), wf1);
         P.V.weight[vi] = min(w_prev + 1, P.max_weight);
-        if (ncomp == 0) continue;
+        if (ncomp == 0) return;
         // ---- derivative components
         const float inv_w1 = __fdiv_rn(1.f, wf1);
         const float a_keep = wf * inv_w1;
-        float *dp = P.V.deriv + (size_t) b * ncomp * BRICK_VOX + tid;
+        // derivative planes of this voxel: in HBM (plane stride BRICK_VOX) or, staged, in shared memory (plane stride 256)
+        float *dp = staged ? s_stage + threadIdx.x : P.V.deriv + (size_t) b * ncomp * BRICK_VOX + tid;
+        const size_t DS = staged ? 256 : BRICK_VOX;
+        if (staged)
+            while (!mbar_try_wait(&s_bar, bar_phase)) {
+            }
         if (saturated) {  // tsdf = (1, 0): F_q <- F_q * w / (w + 1)
-            if (!live) continue;
+            if (!live) return;
             ++n_der;
 #pragma unroll 8
-            for (int q = 0; q < ncomp; ++q) dp[(size_t) q * BRICK_VOX] *= a_keep;
-            continue;
+            for (int q = 0; q < ncomp; ++q) dp[(size_t) q * DS] *= a_keep;
+            return;
         }
         ++n_der;
         if (!live) P.live[b] = 1;  // benign race: every writer stores 1; other voxels of the brick hold zeros
@@ -282,20 +344,20 @@ template <int KIND> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_
             const int n = P.batch.n, m = P.batch.m;
 #pragma unroll 4
             for (int q = 0; q < n; ++q) {
-                const float o = dp[(size_t) q * BRICK_VOX];
+                const float o = dp[(size_t) q * DS];
                 const float4 *mq = s_dpose4 + 3 * q;
                 const float4 a0 = mq[0], a1 = mq[1], a2 = mq[2];
                 const float dx = fmaf(a0.x, vgx, fmaf(a0.y, vgy, fmaf(a0.z, vgz, a2.y)));
                 const float dy = fmaf(a0.w, vgx, fmaf(a1.x, vgy, fmaf(a1.y, vgz, a2.z)));
                 const float dz = fmaf(a1.z, vgx, fmaf(a1.w, vgy, fmaf(a2.x, vgz, a2.w)));
-                dp[(size_t) q * BRICK_VOX] = fmaf(o, a_keep, fmaf(J0, dx, fmaf(J1, dy, J2 * dz)));
+                dp[(size_t) q * DS] = fmaf(o, a_keep, fmaf(J0, dx, fmaf(J1, dy, J2 * dz)));
             }
             int cur_i = -1;
             float hx = 0.f, hy = 0.f, hz = 0.f;  // H d_i v_c
-            float *ps = dp + (size_t) n * BRICK_VOX;
+            float *ps = dp + (size_t) n * DS;
 #pragma unroll 4
             for (int k = 0; k < m; ++k) {
-                const float o = ps[(size_t) k * BRICK_VOX];  // the load first: it bounds this loop
+                const float o = ps[(size_t) k * DS];  // the load first: it bounds this loop
                 const int2 pr = s_pairs[k];
                 if (pr.x != cur_i) {  // block-uniform
                     cur_i = pr.x;
@@ -317,7 +379,7 @@ template <int KIND> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_
                 const float cy2 = fmaf(c0.w, vgx, fmaf(c1.x, vgy, fmaf(c1.y, vgz, c2.z)));
                 const float cz2 = fmaf(c1.z, vgx, fmaf(c1.w, vgy, fmaf(c2.x, vgz, c2.w)));
                 const float T = fmaf(J0, cx2, fmaf(J1, cy2, J2 * cz2)) + fmaf(bx, hx, fmaf(by_, hy, bz * hz));
-                ps[(size_t) k * BRICK_VOX] = fmaf(o, a_keep, T);
+                ps[(size_t) k * DS] = fmaf(o, a_keep, T);
             }
         } else if (C == 1) {
             const float J0 = sdfj.d[0] * sc, J1 = sdfj.d[1] * sc, J2 = sdfj.d[2] * sc;
@@ -328,7 +390,7 @@ template <int KIND> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_
                 const float dy = fmaf(m[3], vgx, fmaf(m[4], vgy, fmaf(m[5], vgz, m[10])));
                 const float dz = fmaf(m[6], vgx, fmaf(m[7], vgy, fmaf(m[8], vgz, m[11])));
                 const float T = fmaf(J0, dx, fmaf(J1, dy, J2 * dz));
-                dp[(size_t) q * BRICK_VOX] = fmaf(dp[(size_t) q * BRICK_VOX], a_keep, T);
+                dp[(size_t) q * DS] = fmaf(dp[(size_t) q * DS], a_keep, T);
             }
         } else {
             // gradient from the diagonal pairs, Hessian from eps1eps2 of each pair
@@ -338,8 +400,8 @@ template <int KIND> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_
             const int dirs = ncomp / 3;
 #pragma unroll 2
             for (int k = 0; k < dirs; ++k) {
-                float *p = dp + (size_t) (3 * k) * BRICK_VOX;
-                const float o1 = p[0], o2 = p[BRICK_VOX], o12 = p[2 * BRICK_VOX];  // loads first: they bound this loop
+                float *p = dp + (size_t) (3 * k) * DS;
+                const float o1 = p[0], o2 = p[DS], o12 = p[2 * DS];  // loads first: they bound this loop
                 const float4 *m = s_dpose4 + 9 * k;  // rows of (dR | dt) for eps1, eps2, eps1eps2
                 const float4 a0 = m[0], a1 = m[1], a2 = m[2], b0 = m[3], b1 = m[4], b2 = m[5], c0 = m[6], c1 = m[7], c2 = m[8];
                 const float ax = fmaf(a0.x, vgx, fmaf(a0.y, vgy, fmaf(a0.z, vgz, a2.y)));
@@ -358,11 +420,25 @@ template <int KIND> __global__ void __launch_bounds__(INT_THREADS, 3) integrate_
                 const float hz = fmaf(H02, bxx, fmaf(H12, byy, H22 * bzz));
                 const float T12 = fmaf(J0, cx2, fmaf(J1, cy2, J2 * cz2)) + fmaf(ax, hx, fmaf(ay, hy, az * hz));
                 p[0] = fmaf(o1, a_keep, T1);
-                p[BRICK_VOX] = fmaf(o2, a_keep, T2);
-                p[2 * BRICK_VOX] = fmaf(o12, a_keep, T12);
+                p[DS] = fmaf(o2, a_keep, T2);
+                p[2 * DS] = fmaf(o12, a_keep, T12);
             }
         }
+        }();
+        if (staged) {  // the updated planes go back as bulk stores
+            while (!mbar_try_wait(&s_bar, bar_phase)) {  // every thread: the loads have landed (also when no voxel of the half brick
+            }                                            // was updated), so the barrier's phase is over before it is armed again
+            fence_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float *dst = P.V.deriv + (size_t) b * ncomp * BRICK_VOX + ((hi & 1) << 8);
+                for (int q = 0; q < ncomp; ++q) bulk_s2g(dst + (size_t) q * BRICK_VOX, s_stage + q * 256, 1024u);
+                bulk_commit();
+            }
+            bar_phase ^= 1u;
+        }
     }
+    if (BULK && threadIdx.x == 0) bulk_wait0();
     // updated-voxel count (drives the algorithmic-bytes model)
     if (P.stats) {
         for (int o = 16; o > 0; o >>= 1) {
@@ -748,8 +824,20 @@ extern "C" int xs_integrate(xs_volume *v, const uint16_t *d_depth, size_t depth_
     XS_CUDA(cudaEventRecord(v->ev_k0, s));
     if (v->comps == 1)
         integrate_kernel<1><<<grid, INT_THREADS, smem, s>>>(P);
-    else if (v->comps == 2)
-        integrate_kernel<2><<<grid, INT_THREADS, smem, s>>>(P);
+    else if (v->comps == 2) {
+        static const char *bulk_env = getenv("XS_INT_BULK");  // experiment: cp.async.bulk staging of live half bricks
+        if (bulk_env && *bulk_env == '1' && v->view.ncomp > 0) {
+            const size_t smem_bulk = smem + 128 + (size_t) v->view.ncomp * 1024;
+            static size_t smem_set = 0;
+            if (smem_bulk > smem_set) {
+                XS_CUDA(cudaFuncSetAttribute(integrate_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bulk));
+                smem_set = smem_bulk;
+            }
+            integrate_kernel<2, true><<<grid, INT_THREADS, smem_bulk, s>>>(P);
+        } else {
+            integrate_kernel<2><<<grid, INT_THREADS, smem, s>>>(P);
+        }
+    }
     else
         integrate_kernel<3><<<grid, INT_THREADS, smem, s>>>(P);
     XS_LAUNCH_CHECK();
