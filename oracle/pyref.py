@@ -533,3 +533,154 @@ class OracleKinfu:
             self.nprev[i] = o.resize_map(self.nprev[i - 1], True, self.f64)
         self.frame_id += 1
         return 1
+
+
+# ------------------------------------------------------------------ second order in FP64: the dual-complex frame loop
+class DC:
+    """A matrix of dual-complex numbers as a pair of complex128 arrays: m = (re.v + i im.v), d = (re.d + i im.d), i.e. the
+    value and its exact derivative along one more parameter theta_j (oracle_types.h Dual).  The imaginary unit carries
+    h d/d theta_i as everywhere in the reference, so d.imag / h is the mixed second derivative."""
+
+    def __init__(self, m, d=None):
+        self.m = np.asarray(m, np.complex128)
+        self.d = np.zeros_like(self.m) if d is None else np.asarray(d, np.complex128)
+
+    def __matmul__(self, o):
+        return DC(self.m @ o.m, self.d @ o.m + self.m @ o.d)
+
+    def __add__(self, o):
+        return DC(self.m + o.m, self.d + o.d)
+
+    def inv(self):
+        mi = np.linalg.inv(self.m)
+        return DC(mi, -mi @ self.d @ mi)
+
+    def sub(self, rows, cols):
+        return DC(self.m[rows, cols], self.d[rows, cols])
+
+    def floats(self):
+        """[2][n][2] float32: primary (re, im) pairs followed by the dual-part pairs (the layout the Dual stages read)."""
+        f = lambda a: np.stack([a.reshape(-1).real, a.reshape(-1).imag], -1)
+        return np.ascontiguousarray(np.stack([f(self.m), f(self.d)]), np.float32)
+
+
+def _dc_axis(angle_m, angle_d, axis):
+    """AngleAxis(angle, unit axis).toRotationMatrix() (host_algebra.h angle_axis_matrix) with its derivative."""
+    c, s = np.cos(angle_m), np.sin(angle_m)
+    dc, ds = -s * angle_d, c * angle_d
+    i, j = [(1, 2), (2, 0), (0, 1)][axis]
+    R, dR = np.eye(3, dtype=np.complex128), np.zeros((3, 3), np.complex128)
+    R[i, i] = R[j, j] = c
+    R[i, j], R[j, i] = -s, s
+    dR[i, i] = dR[j, j] = dc
+    dR[i, j], dR[j, i] = -ds, ds
+    return DC(R, dR)
+
+
+class OracleKinfu2:
+    """The frame loop of OracleKinfu in dual-complex FP64 arithmetic (the stages instantiated with T = Dual, the pose algebra in
+    numpy): one PAIR of perturbation parameters (i, j) per instance.  seed_i, seed_j, seed_ij: 4x4 real matrices G_i, G_j,
+    (G_i G_j + G_j G_i) / 2 - the same seeds the product's Hessian batch takes, without their h factors.  After a frame
+      w2c.m.imag / h  = d w2c / d theta_i,   w2c.d.real = d w2c / d theta_j,   w2c.d.imag / h = d2 w2c / (d theta_i d theta_j).
+    The Gauss-Newton solve is the plain complex(-symmetric) one, i.e. the product's XS_SOLVE_ANALYTIC semantics: second order has
+    no reference semantics to follow (the reference has no DCSFD frame loop)."""
+
+    def __init__(self, cfg, seed_i, seed_j, seed_ij, h=1e-7, oracle=None):
+        self.o = oracle or Oracle()
+        self.cfg, self.h = cfg, h
+        self.W, self.H, self.L = int(cfg["depth_width"]), int(cfg["depth_height"]), int(cfg["num_levels"])
+        self.res = (int(cfg["tsdf_size_x"]), int(cfg["tsdf_size_y"]), int(cfg["tsdf_size_z"]))
+        self.voxel = float(np.float32(cfg["tsdf_voxel_size"]))
+        self.trunc = float(max(np.float32(self.voxel) * np.float32(cfg["thres_range"]), np.float32(2.1) * np.float32(self.voxel)))
+        self.intr = tuple(float(np.float32(cfg[k])) for k in ("fx", "fy", "cx", "cy"))
+        G = lambda a: np.asarray(a, np.float64).reshape(4, 4)
+        self.w2c = DC(np.eye(4) + 1j * h * G(seed_i), G(seed_j) + 1j * h * G(seed_ij))
+        self.record = [self.w2c]
+        w2v = np.eye(4)
+        w2v[:3, 3] = [cfg["init_x"], cfg["init_y"], cfg["init_z"]]
+        self.w2v = DC(w2v)
+        self.angle_thres = float(np.float32(np.sin(np.float32(cfg["angleThres"]) / np.float32(180.0) * np.pi)))
+        self.dist_thres = float(cfg["distThres"])
+        shape = (2, self.res[2], self.res[1], self.res[0])  # [0] values, [1] dual parts
+        self.value = np.zeros(shape, np.float32)
+        self.grad = np.zeros(shape, np.float32)
+        self.weight = np.zeros(shape[1:], np.int32)
+        self.vprev, self.nprev = [None] * self.L, [None] * self.L
+        self.frame_id = 0
+        self.iters = [5, 4, 3]
+
+    def level_intr(self, i):
+        d = np.float32(1 << i)
+        return tuple(float(np.float32(v) / d) for v in self.intr)
+
+    def _maps2(self, rows, cols):
+        m = np.zeros((2, 3, rows, cols, 2), np.float32)
+        m[0, 0, ..., 0] = np.nan
+        return m
+
+    def _estimate(self, Rc, tc, vc, nc, Rpi, tp, intr, vp, npv):
+        lib = self.o.lib
+        rows, cols = vc.shape[2:4]
+        A = np.zeros((2, 72), np.float64)
+        b = np.zeros((2, 12), np.float64)
+        lib.oracle_estimate_combined(_p(Rc.floats()), _p(tc.floats()), _p(vc), _p(nc), _p(Rpi.floats()), _p(tp.floats()),
+                                     C.c_float(intr[0]), C.c_float(intr[1]), C.c_float(intr[2]), C.c_float(intr[3]), _p(vp), _p(npv),
+                                     rows, cols, C.c_float(self.dist_thres), C.c_float(self.angle_thres), _p(A, C.c_double),
+                                     _p(b, C.c_double), 2)
+        cA = lambda a: (a.reshape(6, 6, 2)[..., 0] + 1j * a.reshape(6, 6, 2)[..., 1]).T.copy()
+        cb = lambda a: a.reshape(6, 2)[:, 0] + 1j * a.reshape(6, 2)[:, 1]
+        return DC(cA(A[0]), cA(A[1])), DC(cb(b[0]), cb(b[1]))
+
+    def process_frame(self, depth):
+        o, lib = self.o, self.o.lib
+        lev = [o.bilateral(depth)]
+        for i in range(1, self.L):
+            lev.append(o.pyrdown(lev[-1]))
+        vc, nc = [], []
+        for i in range(self.L):  # the current-frame maps do not depend on the pose: zero dual parts
+            v, n = o.vmap_nmap(lev[i], self.level_intr(i), True)
+            vc.append(np.ascontiguousarray(np.stack([v, np.zeros_like(v)])))
+            nc.append(np.ascontiguousarray(np.stack([n, np.zeros_like(n)])))
+        if self.frame_id > 0:
+            c2w_prev = self.record[-1].inv()
+            Rprev, tprev = c2w_prev.sub(slice(0, 3), slice(0, 3)), c2w_prev.sub(slice(0, 3), 3)
+            Rprev_inv = Rprev.inv()
+            Rcurr, tcurr = DC(Rprev.m.copy(), Rprev.d.copy()), DC(tprev.m.copy(), tprev.d.copy())
+            for level in range(self.L - 1, -1, -1):
+                for _ in range(self.iters[level]):
+                    A, b = self._estimate(Rcurr, tcurr, vc[level], nc[level], Rprev_inv, tprev, self.level_intr(level),
+                                          self.vprev[level], self.nprev[level])
+                    x = np.linalg.solve(A.m, b.m)
+                    dx = np.linalg.solve(A.m, b.d - A.d @ x)
+                    Rinc = _dc_axis(x[2], dx[2], 2) @ _dc_axis(x[1], dx[1], 1) @ _dc_axis(x[0], dx[0], 0)
+                    tn = DC(Rinc.m @ tcurr.m + x[3:], Rinc.d @ tcurr.m + Rinc.m @ tcurr.d + dx[3:])
+                    Rcurr, tcurr = Rinc @ Rcurr, tn
+            c2w = DC(np.eye(4))
+            c2w.m[:3, :3], c2w.m[:3, 3], c2w.d[:3, :3], c2w.d[:3, 3] = Rcurr.m, tcurr.m, Rcurr.d, tcurr.d
+            self.w2c = c2w.inv()
+            self.record.append(self.w2c)
+        c2w = self.record[-1].inv()
+        c2v = self.w2v @ c2w
+        v2c = c2v.inv()
+        r = (C.c_int * 3)(*self.res)
+        d = np.ascontiguousarray(depth, np.uint16)
+        R3, t3 = lambda M: M.sub(slice(0, 3), slice(0, 3)).floats(), lambda M: M.sub(slice(0, 3), 3).floats()
+        lib.oracle_integrate(_p(d, C.c_uint16), d.shape[0], d.shape[1], C.c_float(self.intr[0]), C.c_float(self.intr[1]),
+                             C.c_float(self.intr[2]), C.c_float(self.intr[3]), int(self.cfg["max_integration_weight"]), r,
+                             C.c_float(self.voxel), _p(R3(v2c)), _p(t3(v2c)), C.c_float(self.trunc), _p(self.value),
+                             _p(self.weight, C.c_int), _p(self.grad), C.c_float(float(self.cfg["biInterpolate_threshold"])), 0,
+                             int(self.res[2]), 2)
+        v2w = self.w2v.inv()
+        v, n = self._maps2(self.H, self.W), self._maps2(self.H, self.W)
+        lib.oracle_raycast(C.c_float(self.intr[0]), C.c_float(self.intr[1]), C.c_float(self.intr[2]), C.c_float(self.intr[3]),
+                           _p(R3(c2v)), _p(t3(c2v)), _p(R3(v2w)), _p(t3(v2w)), C.c_float(self.trunc), r, C.c_float(self.voxel),
+                           _p(self.value), _p(self.grad), self.H, self.W, 0, self.H, _p(v), _p(n), 2)
+        self.vprev[0], self.nprev[0] = v, n
+        for i in range(1, self.L):
+            rows, cols = self.vprev[i - 1].shape[2:4]
+            for src, dst, norm in ((self.vprev, self.vprev, 0), (self.nprev, self.nprev, 1)):
+                out = np.zeros((2, 3, rows // 2, cols // 2, 2), np.float32)
+                lib.oracle_resize_map(_p(src[i - 1]), rows, cols, norm, _p(out), 2)
+                dst[i] = out
+        self.frame_id += 1
+        return 1
