@@ -55,6 +55,25 @@ def test_pipeline_second_order_vs_dual_complex_oracle(xs, out_dir):
             want1 = w.w2c.m.imag / H_
             fr["first_order_rel"].append(float(np.abs(poses[f][1 + i] / H_ - want1).max() / np.abs(want1).max()))
             fr["real_abs"] = float(np.abs(poses[f][0] - w.w2c.m.real).max())
+        # the state behind the pose, for three of the pairs: second-order TSDF planes and raycast maps after the last frame
+        if (i, j) in ((0, 4), (3, 3), (2, 5)):
+            _, wgt, g = k.volume_planes(n + kk)
+            g = g.cpu().numpy().astype(np.float64) / (H_ * H_)
+            want = w.grad[1].astype(np.float64) / H_
+            sc = np.abs(want).max()
+            dd = np.abs(g - want)
+            st = {"tsdf_weight_mismatch": int((wgt.cpu().numpy() != w.weight).sum()), "tsdf_scale": float(sc),
+                  "tsdf_max": float(dd.max() / sc), "tsdf_p99.9": float(np.percentile(dd[want != 0], 99.9) / sc)}
+            for name, mine, ref in (("vmap", k.map("vmap_g_prev", 0), w.vprev[0]), ("nmap", k.map("nmap_g_prev", 0), w.nprev[0])):
+                mine = mine.cpu().numpy().astype(np.float64)
+                both = ~np.isnan(mine[0, 0]) & ~np.isnan(ref[0, 0, ..., 0])
+                want = ref[1, ..., 1].astype(np.float64)[:, both] / H_
+                got = mine[1 + n + kk][:, both] / (H_ * H_)
+                sc = np.abs(want).max()
+                dd = np.abs(got - want)
+                st[name + "_mask_mismatch"] = int((np.isnan(mine[0, 0]) != np.isnan(ref[0, 0, ..., 0])).sum())
+                st[name + "_max"], st[name + "_p99.9"] = float(dd.max() / sc), float(np.percentile(dd, 99.9) / sc)
+            rep.setdefault("state_second_order", {})["pair_%d_%d" % (i, j)] = st
     with open(os.path.join(out_dir, "second_order_vs_dual_oracle.json"), "w") as fh:
         json.dump(rep, fh, indent=1)
     print("[parity] second_order_vs_dual_oracle.json", json.dumps(rep)[:3000])
@@ -65,3 +84,8 @@ def test_pipeline_second_order_vs_dual_complex_oracle(xs, out_dir):
         # measured max 1.8e-4, median 7e-5 over the 21 pairs (profiles/r02s_second_order_vs_dual_oracle.json)
         assert max(fr["second_order_rel"]) <= 2e-3, fr["second_order_rel"]
         assert float(np.median(fr["second_order_rel"])) <= 7e-4, fr["second_order_rel"]
+    for st in rep["state_second_order"].values():
+        assert st["tsdf_weight_mismatch"] == 0 and st["vmap_mask_mismatch"] == 0 and st["nmap_mask_mismatch"] == 0, st
+        # measured: TSDF planes p99.9 <= 9e-4, raycast maps p99.9 <= 1.6e-5 (max 7.6e-4)
+        assert st["tsdf_p99.9"] <= 5e-3 and st["vmap_p99.9"] <= 2e-4 and st["nmap_p99.9"] <= 2e-4, st
+        assert st["vmap_max"] <= 1e-2 and st["nmap_max"] <= 1e-2, st
