@@ -1,10 +1,9 @@
 #!/bin/bash
 TAG=${1:-r02m}
 mkdir -p gpurun_out
-XS_INT_BULK=1 timeout 100 python -m pytest tests/test_gpu_hessian.py -m gpu -q -x > gpurun_out/test_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_$TAG.log
+timeout 200 python -m pytest tests/test_gpu_hessian.py -m gpu -q -x > gpurun_out/test_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_$TAG.log
 rm -f gpurun_out/*.npz
-tail -5 gpurun_out/test_$TAG.log | cut -c1-600
-grep -q "rc=0" gpurun_out/test_$TAG.log || exit 1
+tail -3 gpurun_out/test_$TAG.log | cut -c1-600
 run() {
 echo "== $* $EXTRA"
 env "$@" timeout 120 python bench.py --no-cpu-baseline --no-ref-cuda --steps 10 --warmup 3 $EXTRA 2> gpurun_out/exp_$TAG.err | python -c "
@@ -15,5 +14,6 @@ print('fps %.1f' % r['value'], r['config']['derivative_planes_rank0'], r['stages
 tail -3 gpurun_out/exp_$TAG.err
 }
 EXTRA=""
-run XS_INT_BULK=1
-XS_INT_BULK=1 timeout 200 bash tools/gpu_ncu.sh ${TAG}_bulk integrate
+run XS_X=0
+EXTRA="--pose-only"
+run XS_X=0
