@@ -178,3 +178,49 @@ def test_hessian_batch_pipeline_equals_dcsfd_list(xs, out_dir, mode):
     assert last["icp_second_order_rel"] <= 1e-3
     assert rep["grad_first_order_rel"]["p99.9"] <= 1e-5 and rep["grad_second_order_rel"]["p99.9"] <= 1e-4
     assert rep["nmap_l1_second_order_rel"]["p99.9"] <= 1e-4
+
+
+def test_blocked_shards_reassemble_the_full_batch(xs, out_dir):
+    """The multi-GPU decomposition on one GPU: every rank's share of an 8-rank plan (parallel.plan_hessian_shards: a block of the
+    pairs + the parameters those pairs touch, including intrinsic parameters) is run as its own pipeline, the records are
+    reassembled with the code the N-rank runs use, and the result must equal the record of the full batch - real part bit for
+    bit, derivative components to FP32 summation noise (different component sets sum their ICP normal equations in different
+    orders and may take different kernel forms)."""
+    from xslam_b200 import parallel
+    W, Hh = 160, 120
+    intr = (481.20 / 4, -480.00 / 4, 319.50 / 4, 239.50 / 4)
+    cfg = dict(xs.DEFAULT_CONFIG)
+    cfg.update(tsdf_size_x=64, tsdf_size_y=64, tsdf_size_z=64, tsdf_voxel_size=0.12, depth_width=W, depth_height=Hh,
+               fx=intr[0], fy=intr[1], cx=intr[2], cy=intr[3])
+    frames = [xs.synth_depth(f, W, Hh, *intr) for f in range(3)]
+    n, world = 8, 4  # 6 pose DoF + fx, cx; 36 pairs
+    U = np.concatenate([np.eye(6), np.zeros((2, 6))])
+    dintr = np.zeros((n, 4), np.float32)
+    dintr[6, 0] = dintr[7, 2] = H_
+    pairs = xs.all_pairs(n)
+
+    def run(params, local_pairs):
+        seeds, lp = xs.hessian_seeds(U[params], local_pairs)
+        di = np.ascontiguousarray(dintr[params])
+        k = xs.KinectFusionReconstruction()
+        k.SetYamlParameters(cfg, comps=2, seeds=seeds, pairs=lp, n_params=len(params), intrinsic_seeds=di if di.any() else None)
+        for d in frames:
+            assert k.ProcessFrame(d) == 1
+        return k.world2camera.reshape(-1, 16)
+
+    full = run(list(range(n)), pairs)
+    plan = parallel.plan_hessian_shards(n, pairs, world)
+    L = parallel.planned_record_floats(plan)
+    gathered = np.zeros((world, L), np.float32)
+    for r, sh in enumerate(plan):
+        rec = run(sh["params"], sh["local_pairs"]).reshape(-1)
+        gathered[r, : rec.size] = rec
+    rec = parallel.assemble_planned_records(gathered, plan, n, len(pairs))
+    sc1, sc2 = np.abs(full[1:1 + n]).max(), np.abs(full[1 + n:]).max()
+    rep = {"planes_per_rank": [len(sh["params"]) + len(sh["pair_ids"]) for sh in plan],
+           "real_identical": bool(np.array_equal(rec[0], full[0])),
+           "first_order_rel": float(np.abs(rec[1:1 + n] - full[1:1 + n]).max() / sc1),
+           "second_order_rel": float(np.abs(rec[1 + n:] - full[1 + n:]).max() / sc2)}
+    _save(out_dir, "hessian_blocked_shards.json", rep)
+    assert rep["real_identical"]
+    assert rep["first_order_rel"] <= 2e-6 and rep["second_order_rel"] <= 5e-6
