@@ -1,7 +1,7 @@
 #!/bin/bash
 TAG=${1:-r02m}
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests/test_gpu_hessian.py -m gpu -q -x > gpurun_out/test_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_$TAG.log
+timeout 250 python -m pytest tests/test_gpu_hessian.py tests/test_gpu_second_order_oracle.py tests/test_gpu_intrinsics.py -m gpu -q -x > gpurun_out/test_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/test_$TAG.log
 rm -f gpurun_out/*.npz
 tail -3 gpurun_out/test_$TAG.log | cut -c1-600
 run() {
@@ -15,5 +15,6 @@ tail -3 gpurun_out/exp_$TAG.err
 }
 EXTRA=""
 run XS_X=0
-EXTRA="--pose-only"
+run XS_ICP_NO_TAIL=1
+EXTRA="--emulate-share 3/8"
 run XS_X=0

@@ -1814,6 +1814,103 @@ __device__ __noinline__ void icp_solve_hessian_pair(const SolveParams &P, int n,
     gn_pose_update<3>(P, comp, x, 2, false);
 }
 
+// ---- register-resident form of the two solves for the staged, analytic, split-chain case (the frame loop's): the generic
+// functions above unpack every 6x6 system into local arrays (five of them per pair: 1.4 KB of stack) and the single thread of a
+// component then waits on local-memory round trips.  Here the packed sums and the real step's factor are read from their
+// shared-memory copies at the point of use with compile-time indices; the arithmetic and its order are those of
+// unpack_sums / matvec6_dev / chol6_solve.
+XS_DEV constexpr int sum_idx(int i, int j) { return i <= j ? i * 7 - i * (i - 1) / 2 + (j - i) : j * 7 - j * (j - 1) / 2 + (i - j); }
+XS_DEV void packed_matvec(const double *s27, const double (&x)[6], double (&y)[6]) {  // y = A x, A from the 27 packed sums
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double sacc = 0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) sacc += s27[sum_idx(i, j)] * x[j];
+        y[i] = sacc;
+    }
+}
+XS_DEV void staged_chol_solve(const double *rc, const double (&b)[6], double (&x)[6]) {  // rc: L[6][6], inv[6] (REAL_CACHE layout)
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double sacc = b[i];
+#pragma unroll
+        for (int j = 0; j < i; ++j) sacc -= rc[i * 6 + j] * y[j];
+        y[i] = sacc * rc[36 + i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double sacc = y[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) sacc -= rc[j * 6 + i] * x[j];
+        x[i] = sacc * rc[36 + i];
+    }
+}
+XS_DEV void staged_first_order(const SolveParams &P, int p, const double (&xr)[6], double (&xp)[6]) {  // x_p = A^-1 (b_p - A_p x)
+    const double *sp = P.sums + (size_t) (1 + p) * 27;
+    double t[6], rhs[6];
+    packed_matvec(sp, xr, t);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) rhs[e] = sp[sum_idx(e, 6)] - t[e];
+    staged_chol_solve(P.real_cache, rhs, xp);
+}
+XS_DEV bool staged_fast_path(const SolveParams &P) { return P.staged && P.deriv_only && P.real_cache && P.solve_mode != XS_SOLVE_EIGEN_LLT; }
+__device__ __noinline__ void staged_solve_first(const SolveParams &P, int i) {
+    if (P.status_in[0] != 0 || P.status_in[1] != 0) return;
+    double xr[6], xi[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) xr[e] = P.real_cache[42 + e];
+    staged_first_order(P, i, xr, xi);
+    Jet<1, 1> x[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+        x[e].v = (float) xr[e];
+        x[e].d[0] = (float) xi[e];
+    }
+    const int comp[1] = {i};
+    gn_pose_update<1>(P, comp, x, 0, false);
+}
+__device__ __noinline__ void staged_solve_pair(const SolveParams &P, int n, int k, int2 pr, bool reduced) {
+    if (P.status_in[0] != 0 || P.status_in[1] != 0) return;
+    double xr[6], xi[6], xj[6], rhs[6], t[6], xs[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) xr[e] = P.real_cache[42 + e];
+    const double *ss = P.sums + (size_t) (1 + n + k) * 27, *si = P.sums + (size_t) (1 + pr.x) * 27, *sj = P.sums + (size_t) (1 + pr.y) * 27;
+    if (reduced) {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) rhs[e] = ss[e];
+    } else {
+        packed_matvec(ss, xr, t);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) rhs[e] = ss[sum_idx(e, 6)] - t[e];
+    }
+    staged_first_order(P, pr.x, xr, xi);
+    if (pr.y == pr.x) {
+        packed_matvec(si, xi, t);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) xj[e] = xi[e], rhs[e] -= 2.0 * t[e];
+    } else {
+        staged_first_order(P, pr.y, xr, xj);
+        packed_matvec(si, xj, t);  // A_i x_j
+#pragma unroll
+        for (int e = 0; e < 6; ++e) rhs[e] -= t[e];
+        packed_matvec(sj, xi, t);  // A_j x_i
+#pragma unroll
+        for (int e = 0; e < 6; ++e) rhs[e] -= t[e];
+    }
+    staged_chol_solve(P.real_cache, rhs, xs);
+    Jet<3, 1> x[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+        x[e].v = (float) xr[e];
+        x[e].d[0] = (float) xi[e];
+        x[e].d[1] = (float) xj[e];
+        x[e].d[2] = (float) xs[e];
+    }
+    const int comp[3] = {pr.x, pr.y, n + k};
+    gn_pose_update<3>(P, comp, x, 2, false);
+}
+
 // Tail of a Hessian derivative pass (run by the CTA that completed the last sums): the Gauss-Newton step of every component.
 // Everything the solves read - the sums of all components, the real step's factor, the pose tables, the status flags - is
 // staged into shared memory by the whole CTA first (one round of global latency instead of one per dependent load of a
@@ -1841,6 +1938,11 @@ XS_DEV void icp_hessian_tail(const IcpParams &P, const SolveParams &S, unsigned 
     L.staged = 1;
     if (cached_real) L.real_cache = s_rc;
     const int first_threads = ((n + 31) & ~31) % NT;  // pairs start on the warp after the first-order components
+    if (staged_fast_path(L)) {
+        for (int i = tid; i < n; i += NT) staged_solve_first(L, i);
+        for (int k = (tid + NT - first_threads) % NT; k < m; k += NT) staged_solve_pair(L, n, k, __ldg(P.batch.pairs + k), reduced);
+        return;
+    }
     for (int i = tid; i < n; i += NT) icp_solve_hessian_first(L, i, s_sums);
     for (int k = (tid + NT - first_threads) % NT; k < m; k += NT) icp_solve_hessian_pair(L, n, k, __ldg(P.batch.pairs + k), s_sums, reduced);
 }
