@@ -169,7 +169,7 @@ class ClockSampler(threading.Thread):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this same
 # command (512^3, 55 directions, 1 GPU; the Hessian batch with its default parameters); None for any other configuration.
 TRAFFIC_BY_MODE = {"dcsfd": {"icp_deriv": 1.243e9, "integrate": 6.40e8, "raycast_hit": 1.40e9},      # profiles/r01g_ncu_summary.md
-                   "hessian": {"icp_deriv": 5.306e8, "integrate": 2.449e8, "raycast_hit": 5.190e8}}  # profiles/r02s_ncu_summary.md
+                   "hessian": {"icp_deriv": 5.275e8, "integrate": 2.463e8, "raycast_hit": 5.204e8}}  # profiles/r02t_ncu_summary.md
 TRAFFIC = {}
 
 
