@@ -954,7 +954,7 @@ template <int C> __global__ void __launch_bounds__(32) icp_solve_kernel(const So
 // A task of the Hessian-batch derivative pass: either one parameter (first-order sums of component i) or up to HPMAX pairs
 // that share their first parameter i, (i, j_0) .. (i, j_np-1) with second-order components s_0 .. s_np-1.  The pairs of a task
 // share the association record and the gathers of F_i - the derivative pass is bound by L2 -> SM traffic and instruction
-// issue, not by HBM (profiles/r02_ncu_summary.md).
+// issue, not by HBM (profiles/r02_ab_table.md).
 //
 // Two forms of the pair sums:
 //   FULL     the 27 second-order sums A_ij, b_ij of every pair (what the ICP log and the seam-level estimateCombined return);
@@ -1325,7 +1325,7 @@ __global__ void __launch_bounds__(256, MINB) icp_deriv_h_kernel(const IcpParams 
 // ---- tile form of the REDUCED Hessian derivative pass -------------------------------------------------------------------------
 // The task form above reads the association record once per task and the first-order planes of parameter i once per pair run:
 // ~3.4x the algorithmic bytes cross L2 -> SM at 10 parameters / 55 pairs, and that link, not HBM, bounds it (profiles/
-// r02_ncu_summary.md).  Here a CTA owns pixels instead of tasks: a tile of 32 pixels (lane = pixel) is staged ONCE for all
+// r02_ab_table.md).  Here a CTA owns pixels instead of tasks: a tile of 32 pixels (lane = pixel) is staged ONCE for all
 // components - the record, the n first-order and the m second-order gathers at the matched pixels, cp.async, two tiles ahead -
 // so every byte crosses L2 -> SM once per launch.  The NW warps of the CTA then split the components of the tile:
 //   phase B: warp p < n forms the first-order row of parameter p (d_p, ds_p, de_p, rho_p = d_p6 - d_p . x: 14 floats per pixel,
