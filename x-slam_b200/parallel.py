@@ -184,6 +184,13 @@ def plan_hessian_shards(n_params, pairs, world, iters=20000):
                 else:
                     shards[b].pop()
                     shards[a].insert(ia, k)
+    # blocks pay off when they take planes off the heaviest rank; where they do not (2 ranks: 37 against 38 planes) the
+    # round-robin shards are kept - they spread the pairs of every parameter, and with them the costlier intrinsic pairs, evenly
+    if world > 1:
+        rr = [list(range(r, m, world)) for r in range(world)]
+        planes = lambda sh: max(len({q for k in s_ for q in pairs[k]}) + len(s_) for s_ in sh)
+        if planes(shards) > 0.9 * planes(rr):
+            shards = rr
     plan = []
     for s_ in shards:
         ids = sorted(s_, key=lambda k: pairs[k])
