@@ -499,7 +499,15 @@ def run_ours(args, xs, rank, world, local_rank):
     t0 = time.perf_counter()
     for i in range(NF):
         step(next_frame(pinned).numpy().view(np.uint16))
-        w2c = k.gathered_records() if comm is not None else k.world2camera  # the frame's result (all ranks' derivatives), read on the host
+        # the frame's result, read on the host every frame.  One rank: the pose record (value + derivative components).  N ranks:
+        # all ranks' records; the consumer runs one frame behind - after submitting frame i it reads frame i - 1's gathered
+        # records, whose all-gather ran beside frame i's kernels - and reads the last frame's after the loop
+        if comm is None:
+            w2c = k.world2camera
+        elif i > 0:
+            w2c = k.gathered_records(lag=1)
+    if comm is not None:
+        w2c = k.gathered_records()
     sync()
     t_e2e = time.perf_counter() - t0
     clocks = sampler.summary()

@@ -319,6 +319,9 @@ int xs_comm_all_gather(xs_comm *c, const float *d_send, float *d_recv, long floa
 int xs_kinfu_set_comm(xs_kinfu *k, xs_comm *comm, int record_floats);
 /* gathered records of the last processed frame, [world][record_floats] (waits for that frame's all-gather) */
 int xs_kinfu_get_gathered_records(xs_kinfu *k, float *host_out);
+/* lag = 0: as above; lag = 1: the records of the frame before the last processed one (two buffers alternate), whose all-gather
+ * ran beside the last frame's kernels - the read of a consumer that runs one frame behind never waits for a collective */
+int xs_kinfu_get_gathered_records_lagged(xs_kinfu *k, int lag, float *host_out);
 const float *xs_kinfu_gathered_records_device(xs_kinfu *k);
 
 /* ---------------------------------------------------------------- outputs & synthetic input (a13, f1) */

@@ -43,7 +43,7 @@ def main():
     L = parallel.planned_record_floats(plan)
     k.set_comm(comm, L)
     k.set_deferred(True)
-    full = None
+    full, g_prev = None, None
     if rank == 0:
         sf, _ = xs.hessian_seeds(U, pairs)
         full = xs.KinectFusionReconstruction()
@@ -55,6 +55,9 @@ def main():
         d = xs.synth_depth(f)
         assert k.ProcessFrame(d) == 1
         g = k.gathered_records()
+        if f > 0:  # the two gather buffers alternate: the previous frame's records stay readable while this frame's gather runs
+            ok = ok and bool(np.array_equal(k.gathered_records(lag=1), g_prev))
+        g_prev = np.array(g, copy=True)
         g = np.asarray(g.cpu() if hasattr(g, "cpu") else g)
         rec = parallel.assemble_planned_records(g, plan, n, len(pairs))
         # replicas: every rank produced the same real pose, and the ranks that share a parameter the same first-order component

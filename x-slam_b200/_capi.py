@@ -122,6 +122,7 @@ SYMBOLS = {
     "xs_comm_all_gather": (_i, [_vp, _vp, _vp, _l, _vp]),
     "xs_kinfu_set_comm": (_i, [_vp, _vp, _i]),
     "xs_kinfu_get_gathered_records": (_i, [_vp, _pf]),
+    "xs_kinfu_get_gathered_records_lagged": (_i, [_vp, _i, _pf]),
     "xs_kinfu_gathered_records_device": (_vp, [_vp]),
     "xs_save_pose_txt": (_i, [C.c_char_p, _pf]),
     "xs_export_ply": (_i, [C.c_char_p, _pf, _pf, _l]),

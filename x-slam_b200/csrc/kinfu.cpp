@@ -111,9 +111,11 @@ struct xs_kinfu {
     // multi-GPU (comm.cpp): the record of every rank is all-gathered after each frame on a stream of its own
     xs_comm *comm = nullptr;
     int record_floats = 0;                 // floats per rank in the gather (>= (1 + ncomp) * 16, the same on every rank)
-    float *d_gathered = nullptr;           // [world][record_floats]
+    float *d_gathered[2] = {nullptr, nullptr};  // [world][record_floats], alternating per frame: the host may read frame f - 1's
+                                                // records while frame f's gather is in flight (xs_kinfu_get_gathered_records_lagged)
+    int gather_slot = 0;                        // buffer of the last queued gather
     cudaStream_t stream_comm = nullptr;
-    cudaEvent_t ev_record = nullptr, ev_gather = nullptr;  // record uploaded / gather has read it and written d_gathered
+    cudaEvent_t ev_record = nullptr, ev_gather[2] = {nullptr, nullptr};  // record uploaded / gather has read it and written its buffer
     bool gather_in_flight = false;
     bool keep_curr_derivs = false;  // xs_kinfu_keep_current_map_derivatives
     bool deferred = false;  // xs_kinfu_set_deferred: ProcessFrame returns once integration + raycast are queued
@@ -315,9 +317,11 @@ void xs_kinfu_destroy(xs_kinfu *k) {
         cudaStreamSynchronize(k->stream_comm);
         cudaStreamDestroy(k->stream_comm);
         cudaEventDestroy(k->ev_record);
-        cudaEventDestroy(k->ev_gather);
+        cudaEventDestroy(k->ev_gather[0]);
+        cudaEventDestroy(k->ev_gather[1]);
     }
-    cudaFree(k->d_gathered);
+    cudaFree(k->d_gathered[0]);
+    cudaFree(k->d_gathered[1]);
     cudaFree(k->d_record);
     cudaFreeHost(k->h_record);
     if (k->stream_real) cudaStreamSynchronize(k->stream_real);
@@ -594,13 +598,14 @@ int xs_kinfu_process_frame(xs_kinfu *k, const uint16_t *depth, int depth_on_devi
         for (int i = 0; i < 4; ++i)
             for (int j = 0; j < 4; ++j)
                 k->h_record[(size_t) q * 16 + i * 4 + j] = q == 0 ? k->world2camera.m[i][j].v : k->world2camera.m[i][j].d[q - 1];
-    if (k->comm && k->gather_in_flight) cudaStreamWaitEvent(k->stream, k->ev_gather, 0);  // the previous gather has read d_record
+    if (k->comm && k->gather_in_flight) cudaStreamWaitEvent(k->stream, k->ev_gather[k->gather_slot], 0);  // the previous gather has read d_record
     cudaMemcpyAsync(k->d_record, k->h_record, (size_t) (1 + k->ncomp) * 16 * sizeof(float), cudaMemcpyHostToDevice, k->stream);
     if (k->comm) {  // derivatives gathered by NCCL all-gather over NVLink, beside the next frame's kernels
         cudaEventRecord(k->ev_record, k->stream);
         cudaStreamWaitEvent(k->stream_comm, k->ev_record, 0);
-        if (xs_comm_all_gather(k->comm, k->d_record, k->d_gathered, k->record_floats, k->stream_comm) != XS_OK) return 0;
-        cudaEventRecord(k->ev_gather, k->stream_comm);
+        k->gather_slot ^= 1;
+        if (xs_comm_all_gather(k->comm, k->d_record, k->d_gathered[k->gather_slot], k->record_floats, k->stream_comm) != XS_OK) return 0;
+        cudaEventRecord(k->ev_gather[k->gather_slot], k->stream_comm);
         k->gather_in_flight = true;
     }
     cudaEventRecord(ev[4], k->stream);
@@ -897,28 +902,36 @@ int xs_kinfu_set_comm(xs_kinfu *k, xs_comm *comm, int record_floats) {
     if (!k->stream_comm) {
         KCUDA(cudaStreamCreateWithFlags(&k->stream_comm, cudaStreamNonBlocking));
         KCUDA(cudaEventCreateWithFlags(&k->ev_record, cudaEventDisableTiming));
-        KCUDA(cudaEventCreateWithFlags(&k->ev_gather, cudaEventDisableTiming));
+        KCUDA(cudaEventCreateWithFlags(&k->ev_gather[0], cudaEventDisableTiming));
+        KCUDA(cudaEventCreateWithFlags(&k->ev_gather[1], cudaEventDisableTiming));
     }
     // the send buffer is the record itself, re-allocated at the padded size (padding stays zero)
     cudaFree(k->d_record);
-    cudaFree(k->d_gathered);
-    k->d_record = k->d_gathered = nullptr;
+    cudaFree(k->d_gathered[0]);
+    cudaFree(k->d_gathered[1]);
+    k->d_record = k->d_gathered[0] = k->d_gathered[1] = nullptr;
     k->record_floats = record_floats;
     KCUDA(cudaMalloc((void **) &k->d_record, (size_t) record_floats * sizeof(float)));
     KCUDA(cudaMemset(k->d_record, 0, (size_t) record_floats * sizeof(float)));
-    KCUDA(cudaMalloc((void **) &k->d_gathered, (size_t) xs_comm_world(comm) * record_floats * sizeof(float)));
-    KCUDA(cudaMemset(k->d_gathered, 0, (size_t) xs_comm_world(comm) * record_floats * sizeof(float)));
+    for (int b = 0; b < 2; ++b) {
+        KCUDA(cudaMalloc((void **) &k->d_gathered[b], (size_t) xs_comm_world(comm) * record_floats * sizeof(float)));
+        KCUDA(cudaMemset(k->d_gathered[b], 0, (size_t) xs_comm_world(comm) * record_floats * sizeof(float)));
+    }
     return XS_OK;
 }
 
 // The gathered records of the last processed frame, [world][record_floats]: waits for that frame's all-gather only.
-int xs_kinfu_get_gathered_records(xs_kinfu *k, float *host_out) {
-    if (!k || !host_out || !k->comm) return XS_ERR_ARG;
-    if (k->gather_in_flight) KCUDA(cudaEventSynchronize(k->ev_gather));
-    KCUDA(cudaMemcpy(host_out, k->d_gathered, (size_t) xs_comm_world(k->comm) * k->record_floats * sizeof(float), cudaMemcpyDeviceToHost));
+int xs_kinfu_get_gathered_records(xs_kinfu *k, float *host_out) { return xs_kinfu_get_gathered_records_lagged(k, 0, host_out); }
+// lag = 1: the records of the frame BEFORE the last processed one.  Their all-gather ran beside the last frame's kernels, so a
+// consumer that reads one frame late (process frame f, then read frame f - 1) never waits for a collective.
+int xs_kinfu_get_gathered_records_lagged(xs_kinfu *k, int lag, float *host_out) {
+    if (!k || !host_out || !k->comm || (lag != 0 && lag != 1)) return XS_ERR_ARG;
+    const int slot = k->gather_slot ^ lag;
+    if (k->gather_in_flight) KCUDA(cudaEventSynchronize(k->ev_gather[slot]));
+    KCUDA(cudaMemcpy(host_out, k->d_gathered[slot], (size_t) xs_comm_world(k->comm) * k->record_floats * sizeof(float), cudaMemcpyDeviceToHost));
     return XS_OK;
 }
-const float *xs_kinfu_gathered_records_device(xs_kinfu *k) { return k ? k->d_gathered : nullptr; }
+const float *xs_kinfu_gathered_records_device(xs_kinfu *k) { return k ? k->d_gathered[k->gather_slot] : nullptr; }
 
 void *xs_kinfu_stream(xs_kinfu *k) { return k ? (void *) k->stream : nullptr; }
 

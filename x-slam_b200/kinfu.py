@@ -358,10 +358,11 @@ class KinectFusionReconstruction:
         check(self.lib.xs_kinfu_set_comm(self.h, comm.h if comm is not None else None, int(record_floats)), "set_comm")
         self._record_floats, self._world = int(record_floats), (comm.world if comm is not None else 1)
 
-    def gathered_records(self):
-        """[world, record_floats] float32: the records of the last processed frame, gathered by the library over NCCL."""
+    def gathered_records(self, lag=0):
+        """[world, record_floats] float32: the records of the last processed frame (lag = 0) or of the one before (lag = 1: its
+        all-gather ran beside the last frame's kernels, so the read does not wait), gathered by the library over NCCL."""
         out = np.zeros((self._world, self._record_floats), np.float32)
-        check(self.lib.xs_kinfu_get_gathered_records(self.h, out.ctypes.data_as(C.POINTER(C.c_float))), "gathered_records")
+        check(self.lib.xs_kinfu_get_gathered_records_lagged(self.h, int(lag), out.ctypes.data_as(C.POINTER(C.c_float))), "gathered_records")
         return out
 
     def pose_record_device_ptr(self):
