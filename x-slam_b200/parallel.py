@@ -54,6 +54,16 @@ def real_parts_agree(gathered_out, atol=0.0):
 
 
 # ------------------------------------------------------------------ in-library NCCL layer (csrc/comm.cpp)
+def _load_torch_nccl_first():
+    """The library binds NCCL with dlopen("libnccl.so.2").  In a process that will also import PyTorch, PyTorch's bundled NCCL
+    must be the copy that soname resolves to (an older system NCCL loaded first would later break `import torch`), so torch is
+    imported before the first NCCL call whenever it is installed."""
+    try:
+        import torch  # noqa: F401
+    except Exception:
+        pass
+
+
 class Comm:
     """The library's own communicator (xs_comm: NCCL bound at run time).  The 128-byte id of rank 0 reaches the other ranks
     through whatever the launcher offers: torch.distributed (any backend), or a file for the C++ driver."""
@@ -61,6 +71,7 @@ class Comm:
     def __init__(self, rank, world, uid):
         import ctypes as C
         from . import _capi
+        _load_torch_nccl_first()
         self.lib = _capi.load()
         self.rank, self.world = rank, world
         self.h = self.lib.xs_comm_create(rank, world, C.c_char_p(bytes(uid)))
@@ -71,6 +82,7 @@ class Comm:
     def unique_id():
         import ctypes as C
         from . import _capi
+        _load_torch_nccl_first()
         buf = C.create_string_buffer(128)
         _capi.check(_capi.load().xs_comm_unique_id(buf), "xs_comm_unique_id")
         return buf.raw
