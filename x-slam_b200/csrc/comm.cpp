@@ -9,6 +9,8 @@
 // NCCL is bound at run time (dlopen of libnccl.so.2: the copy PyTorch has already loaded in a Python process, the system
 // one in the C++ driver), so libxslam_b200.so has no link-time dependency on a particular NCCL build; the five entry points
 // used are declared here with their published signatures (nccl.h, NCCL 2.x).  Without NCCL every call fails loudly.
+// (A process that also imports PyTorch must import it before the first call here, so that the soname resolves to PyTorch's
+// bundled NCCL rather than an older system copy: x-slam_b200/parallel.py does.)
 #include "../../include/xslam_b200.h"
 
 #include <cuda_runtime_api.h>
