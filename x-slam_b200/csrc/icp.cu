@@ -1923,6 +1923,20 @@ XS_DEV void icp_hessian_tail(const IcpParams &P, const SolveParams &S, unsigned 
     float *s_pose = reinterpret_cast<float *>(s_rc + REAL_CACHE);
     int *s_st = reinterpret_cast<int *>(s_pose + npose);
     const bool cached_real = S.deriv_only && S.real_cache;
+    const int first_threads = ((n + 31) & ~31) % NT;  // pairs start on the warp after the first-order components
+    unsigned smem_avail;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(smem_avail));
+    if ((size_t) nv * sizeof(double) + REAL_CACHE * sizeof(double) + (size_t) npose * sizeof(float) + 2 * sizeof(int) > smem_avail) {
+        // a batch too large for the staging area (several hundred components): every thread reads what it needs itself
+        if (S.log)
+            for (int i = tid; i < nv; i += NT) S.log[i] = __ldcg(P.sums + i);
+        double *s_real = reinterpret_cast<double *>(s_raw);
+        if (tid < 27) s_real[tid] = __ldcg(P.sums + tid);
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) icp_solve_hessian_first(S, i, s_real);
+        for (int k = (tid + NT - first_threads) % NT; k < m; k += NT) icp_solve_hessian_pair(S, n, k, __ldg(P.batch.pairs + k), s_real, reduced);
+        return;
+    }
     for (int i = tid; i < nv; i += NT) s_sums[i] = __ldcg(P.sums + i);
     if (cached_real)
         for (int i = tid; i < REAL_CACHE; i += NT) s_rc[i] = __ldcg(S.real_cache + i);
@@ -1937,7 +1951,6 @@ XS_DEV void icp_hessian_tail(const IcpParams &P, const SolveParams &S, unsigned 
     L.status_in = s_st;
     L.staged = 1;
     if (cached_real) L.real_cache = s_rc;
-    const int first_threads = ((n + 31) & ~31) % NT;  // pairs start on the warp after the first-order components
     if (staged_fast_path(L)) {
         for (int i = tid; i < n; i += NT) staged_solve_first(L, i);
         for (int k = (tid + NT - first_threads) % NT; k < m; k += NT) staged_solve_pair(L, n, k, __ldg(P.batch.pairs + k), reduced);
