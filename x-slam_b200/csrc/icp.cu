@@ -2107,6 +2107,7 @@ template <int C, int ST> static int launch_deriv(const IcpParams &P, const Solve
 }
 
 constexpr int TILE_NW = 11, TILE_PPW = 5;  // 10 parameters + 55 pairs: one row and five pairs per warp
+constexpr int TILE_NW_DEFAULT = 12;  // 0.302 vs 0.316 ms per level-0 launch at 10 parameters / 55 pairs (profiles/r02_ab_table.md)
 template <int NW, int PPW, bool CURR, bool PIPE, int DEPTH> static int launch_deriv_tile(const IcpParams &P, const SolveParams &S, int grid, cudaStream_t s) {
     static size_t smem_set = 0;
     static const int pad_kb = env_int("XS_ICP_TILE_PAD_KB", 0);  // experiment: unused shared memory (shrinks L1)
@@ -2205,7 +2206,11 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
     // tile form of the reduced pass (icp_deriv_tile_kernel): one CTA per SM over 32-pixel tiles, all components of a tile at once
     static const int h_tile = env_int("XS_ICP_H_TILE", 1);
     const size_t smem_cap = 227 * 1024;
-    const int tile_nw = TILE_NW;  // measured and rejected: 16 warps x 4 pairs at 128 registers (spills; 0.48 vs 0.39 ms, profiles/r02_ab_table.md)
+    // warps per CTA: 12 (default: the register file is allotted per four warps, so the twelfth costs nothing and takes pairs off
+    // the others) or 11 (one first-order row + five pairs each at 10 parameters / 55 pairs); XS_ICP_TILE_NW selects.  Measured and
+    // rejected: 16 warps x 4 pairs at 128 registers (spills; 0.48 vs 0.39 ms, profiles/r02_ab_table.md)
+    static const int tile_nw_env = env_int("XS_ICP_TILE_NW", TILE_NW_DEFAULT);
+    const int tile_nw = tile_nw_env == 12 ? 12 : 11;
     // (a small share of the pairs - one rank of an 8-GPU job holds 7 - leaves the tiles too little work per barrier: the task
     // form is faster there, 0.104 vs 0.120 ms per level-0 launch at 4 parameters + 7 pairs)
     const bool tile = h_reduced && h_tile && batch.m >= 24 && batch.n <= TILE_NW && batch.m <= TILE_NW * TILE_PPW &&
@@ -2229,7 +2234,7 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
                 order[k] = k;
             }
             std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-            for (int w = 0; w < nw && w < batch.n; ++w) load[w] = 0.15;
+            for (int w = 0; w < nw && w < batch.n; ++w) load[w] = 0.5;  // a first-order row + its 27 sums: about half a pair
             std::vector<std::vector<int>> slots(nw);
             for (int k : order) {
                 int best = -1;
@@ -2351,6 +2356,8 @@ int icp_iteration_async(IcpScratch *scp, const float *d_pose_curr, const float *
     (cur ? launch_deriv_tile<NW_, PPW_, true, PIPE_, DEPTH_>(P, S, tile_grid, s) : launch_deriv_tile<NW_, PPW_, false, PIPE_, DEPTH_>(P, S, tile_grid, s))
             if (!tile_pipe)
                 rc = XS_TILE(TILE_NW, TILE_PPW, false, 1);
+            else if (tile_nw == 12)
+                rc = tile_depth == 4 ? XS_TILE(12, TILE_PPW, true, 4) : tile_depth == 2 ? XS_TILE(12, TILE_PPW, true, 2) : XS_TILE(12, TILE_PPW, true, 1);
             else if (tile_depth == 4)
                 rc = XS_TILE(TILE_NW, TILE_PPW, true, 4);
             else if (tile_depth == 2)
