@@ -105,3 +105,16 @@ def test_blocked_hessian_shards_cover_every_pair_once():
             assert planes <= n + (len(pairs) + w - 1) // w  # never more planes per rank than round-robin shards
     plan = parallel.plan_hessian_shards(10, [(i, j) for i in range(10) for j in range(i, 10)], 8)
     assert max(len(sh["params"]) + len(sh["pair_ids"]) for sh in plan) <= 12
+
+
+def test_round_robin_is_kept_where_blocks_do_not_pay():
+    """2 ranks, 10 parameters: blocks would leave 37 planes on the heavier rank against 38, so the plan stays round robin (which
+    spreads the pairs of every parameter evenly); at 4 and 8 ranks the blocks are taken."""
+    sys.path.insert(0, ROOT)
+    from xslam_b200 import parallel
+    pairs = [(i, j) for i in range(10) for j in range(i, 10)]
+    p2 = parallel.plan_hessian_shards(10, pairs, 2)
+    assert [sh["pair_ids"] for sh in p2] == [list(range(0, 55, 2)), list(range(1, 55, 2))]
+    for w, planes in ((4, 21), (8, 12)):
+        plan = parallel.plan_hessian_shards(10, pairs, w)
+        assert max(len(sh["params"]) + len(sh["pair_ids"]) for sh in plan) <= planes
